@@ -1,0 +1,706 @@
+// libbioslam_b200: C ABI (include/bioslam_b200.h) of the B200-native Levenberg-Marquardt path.
+// Host-side orchestration only; all arithmetic runs in the kernels of kernels_*.cuh.  There is NO CPU fallback: every
+// entry point that computes launches CUDA kernels on the problem's device and reports CUDA errors as B200_CUDA_ERROR.
+#include <algorithm>
+#include <string>
+#include <vector>
+#include "kernels_preint.cuh"
+#include "kernels_solve.cuh"
+
+using namespace b200d;
+
+static thread_local std::string g_last_error;
+static void set_err(const std::string& s) { g_last_error = s; }
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            set_err(std::string(#call) + ": " + cudaGetErrorString(e__));                          \
+            return B200_CUDA_ERROR;                                                                \
+        }                                                                                          \
+    } while (0)
+
+static const int kValDim[4] = {12, 3, 6, 3};
+static const int kTanDim[4] = {6, 3, 6, 2};
+
+struct FInfo { int nvars; int vt[B200_MAX_FACTOR_VARS]; int nconst; };
+static bool finfo(int type, FInfo& f) {
+    const int P = B200_VAR_POSE3, V = B200_VAR_VEC3, B = B200_VAR_BIAS6, U = B200_VAR_UNIT3;
+    switch (type) {
+    case B200_F_IMU_COMBINED: f = {6, {P, V, P, V, B, B}, 190}; return true;
+    case B200_F_IMU_STATICBIAS: f = {5, {P, V, P, V, B}, 115}; return true;
+    case B200_F_ANGVEL: f = {2, {V, B}, 3}; return true;
+    case B200_F_HINGE_VEC: case B200_F_HINGE_NORM: f = {5, {P, V, P, V, U}, 0}; return true;
+    case B200_F_JOINTPOS_VEC: case B200_F_JOINTPOS_NORM: f = {4, {P, P, V, V}, 0}; return true;
+    case B200_F_JOINTVEL_VEC: f = {8, {P, V, V, V, P, V, V, V}, 0}; return true;
+    case B200_F_SEGLEN_MAG: case B200_F_SEGLEN_MAX: case B200_F_SEGLEN_MIN: f = {2, {V, V}, 0}; return true;
+    case B200_F_SEGLEN_DISCREPANCY: f = {4, {V, V, V, V}, 0}; return true;
+    case B200_F_ANGLE_AXIS_SEG: f = {3, {U, V, V}, 0}; return true;
+    case B200_F_POSE3_TRANSLATION_PRIOR: case B200_F_POSE3_COMPASS_PRIOR: case B200_F_PRIOR_POSE3: f = {1, {P}, 0}; return true;
+    case B200_F_PRIOR_VEC3: f = {1, {V}, 0}; return true;
+    case B200_F_PRIOR_BIAS6: f = {1, {B}, 0}; return true;
+    case B200_F_PRIOR_UNIT3: f = {1, {U}, 0}; return true;
+    case B200_F_MAG_POSE3: f = {1, {P}, 3}; return true;
+    default: return false;
+    }
+}
+
+enum { SC_LIN_ERR = 0, SC_MODEL_ERR = 1, SC_NEW_ERR = 2, SC_CUR_ERR = 3, SC_COUNT = 8 };
+
+struct b200_problem {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int K = 0, ntv = 0, nsv = 0, cstride = 0, n_slots = 0;
+    std::vector<int> tvtype, svtype;
+    std::vector<b200_factor_slot> slots;
+    std::vector<DevSlot> hslots;
+    Dims dm{};
+    int tvd = 0, svd = 0;
+    std::vector<int> tv_valoff, tv_tan_int, tv_tan_ext, sv_valoff, sv_tan;
+    std::vector<int> int2ext;  // internal tangent index -> external (or -1 for the padding variable)
+    // device buffers
+    double *d_tv = nullptr, *d_tv_try = nullptr, *d_sv = nullptr, *d_sv_try = nullptr, *d_cst = nullptr, *d_stage = nullptr;
+    size_t stage_doubles = 0;
+    DevSlot* d_slots = nullptr;
+    DevVar *d_tvars = nullptr, *d_svars = nullptr;
+    double *d_J = nullptr, *d_r = nullptr, *d_e = nullptr, *d_e2 = nullptr;
+    long long nJ = 0, nr = 0, ne = 0;
+    int max_inst = 0;
+    double *d_D = nullptr, *d_O = nullptr, *d_A = nullptr, *d_S = nullptr;
+    SolveBuffers sb{};
+    int* d_begin = nullptr;
+    std::vector<int> begin;
+    int P = 1, rmax = 0;
+    size_t smem_sweep = 0, smem_asm[2] = {0, 0};
+    double* h_scal = nullptr;  // pinned: SC_COUNT doubles + status
+    // LM state
+    b200_lm_params lm{};
+    double err = 0, lambda = 0;
+    int iterations = 0, total_trials = 0;
+    bool have_lin = false;
+    long long launches = 0;
+    cudaEvent_t ev[8] = {};
+    double phase_ms[4] = {0, 0, 0, 0};
+    bool time_phases = false;
+    // sharding (time axis): this rank owns chunks [c_lo, c_hi) == keyframes [k_lo, k_hi)
+    int world = 1, rank = 0, c_lo = 0, c_hi = 1, k_lo = 0, k_hi = 0;
+    b200_allgather_fn ag_fn = nullptr;
+    b200_allreduce_fn ar_fn = nullptr;
+    void* comm_ctx = nullptr;
+    double *d_sepD = nullptr, *d_sepA = nullptr, *d_sepS = nullptr, *d_sepO = nullptr;
+};
+
+template <class T>
+static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, (n ? n : 1) * sizeof(T)); }
+
+static int choose_ld(int ntp) { int ld = ntp; while ((ld & 3) != 2) ld++; return ld; }
+
+extern "C" {
+
+const char* b200_last_error(void) { return g_last_error.c_str(); }
+
+void b200_problem_destroy(b200_problem* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    void* ptrs[] = {p->d_tv, p->d_tv_try, p->d_sv, p->d_sv_try, p->d_cst, p->d_stage, p->d_slots, p->d_tvars, p->d_svars, p->d_J, p->d_r,
+                    p->d_e, p->d_e2, p->d_D, p->d_O, p->d_A, p->d_S, p->sb.Lst, p->sb.Pst, p->sb.Fchunk, p->sb.Schunk, p->sb.Dred,
+                    p->sb.Ored, p->sb.Ared, p->sb.Sred, p->sb.Ftop, p->sb.Stop, p->sb.sep_idx, p->sb.delta, p->sb.dstat, p->sb.scal,
+                    p->sb.status, p->d_begin, p->d_sepD, p->d_sepA, p->d_sepS, p->d_sepO};
+    for (void* q : ptrs) if (q) cudaFree(q);
+    if (p->h_scal) cudaFreeHost(p->h_scal);
+    for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+static b200_status set_partition(b200_problem* p, int P);
+
+b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200_problem** out) {
+    if (!d || !out || d->K < 1 || d->n_time_vars < 1 || d->n_slots < 1) { set_err("bad description"); return B200_BAD_ARG; }
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { set_err("no such CUDA device"); return B200_BAD_ARG; }
+    CK(cudaSetDevice(device));
+    b200_problem* p = new b200_problem();
+    p->device = device;
+    p->K = d->K; p->ntv = d->n_time_vars; p->nsv = d->n_static_vars; p->cstride = d->const_stride; p->n_slots = d->n_slots;
+    p->tvtype.assign(d->time_var_type, d->time_var_type + d->n_time_vars);
+    if (d->n_static_vars) p->svtype.assign(d->static_var_type, d->static_var_type + d->n_static_vars);
+    p->slots.assign(d->slots, d->slots + d->n_slots);
+    auto fail = [&](const std::string& m, b200_status st) { set_err(m); b200_problem_destroy(p); return st; };
+    // ---- classify time variables: chained (appear in a factor spanning k and k+1) vs keyframe-local
+    std::vector<char> chained(p->ntv, 0);
+    for (const auto& s : p->slots) {
+        FInfo fi;
+        if (!finfo(s.type, fi) || s.nvars != fi.nvars) return fail("slot: unknown type or wrong variable count", B200_BAD_ARG);
+        bool spans = false, any_time = false;
+        for (int v = 0; v < s.nvars; v++) {
+            const int kind = s.var_kind[v], idx = s.var_index[v];
+            if (kind == B200_AT_STATIC) { if (idx < 0 || idx >= p->nsv || p->svtype[idx] != fi.vt[v]) return fail("slot: bad static variable", B200_BAD_ARG); }
+            else if (kind == B200_AT_K || kind == B200_AT_K1) {
+                if (idx < 0 || idx >= p->ntv || p->tvtype[idx] != fi.vt[v]) return fail("slot: bad time variable", B200_BAD_ARG);
+                any_time = true;
+                if (kind == B200_AT_K1) spans = true;
+            } else return fail("slot: bad var_kind", B200_BAD_ARG);
+        }
+        if (s.k_begin < 0 || s.k_end > d->K - (spans ? 1 : 0) || s.k_begin >= s.k_end) return fail("slot: bad keyframe range", B200_BAD_ARG);
+        if (!any_time && !(s.k_begin == 0 && s.k_end == 1)) return fail("static-only slot must have k range [0,1)", B200_BAD_ARG);
+        if ((fi.nconst > 0) != (s.const_offset >= 0)) return fail("slot: const_offset mismatch", B200_BAD_ARG);
+        if (fi.nconst > 0 && s.const_offset + fi.nconst > d->const_stride) return fail("slot: constants out of range", B200_BAD_ARG);
+        if (spans) for (int v = 0; v < s.nvars; v++) if (s.var_kind[v] != B200_AT_STATIC) chained[s.var_index[v]] = 1;
+    }
+    // ---- layouts
+    p->tv_valoff.resize(p->ntv); p->tv_tan_ext.resize(p->ntv); p->tv_tan_int.resize(p->ntv);
+    int nt = 0;
+    for (int v = 0; v < p->ntv; v++) { p->tv_valoff[v] = p->tvd; p->tv_tan_ext[v] = nt; p->tvd += kValDim[p->tvtype[v]]; nt += kTanDim[p->tvtype[v]]; }
+    int nl = 0;
+    for (int v = 0; v < p->ntv; v++) if (!chained[v]) { p->tv_tan_int[v] = nl; nl += kTanDim[p->tvtype[v]]; }
+    int pos = nl;
+    for (int v = 0; v < p->ntv; v++) if (chained[v]) { p->tv_tan_int[v] = pos; pos += kTanDim[p->tvtype[v]]; }
+    p->sv_valoff.resize(p->nsv); p->sv_tan.resize(p->nsv);
+    int ns = 0;
+    for (int v = 0; v < p->nsv; v++) { p->sv_valoff[v] = p->svd; p->sv_tan[v] = ns; p->svd += kValDim[p->svtype[v]]; ns += kTanDim[p->svtype[v]]; }
+    Dims& dm = p->dm;
+    dm.K = p->K; dm.Kld = (p->K + 3) & ~3LL;
+    dm.nt = nt; dm.ntp = nt + (nt & 1); dm.nl = nl; dm.nc = dm.ntp - nl; dm.ns = ns; dm.ns1 = ns + 1;
+    dm.ld = choose_ld(dm.ntp); dm.hmax = dm.ns1 + dm.nc;
+    if (dm.ntp > 256 || dm.hmax > 512) return fail("time block larger than 256 or arrow larger than 512 tangent dims is not supported", B200_NOT_IMPLEMENTED);
+    p->int2ext.assign(dm.ntp, -1);
+    for (int v = 0; v < p->ntv; v++) for (int j = 0; j < kTanDim[p->tvtype[v]]; j++) p->int2ext[p->tv_tan_int[v] + j] = p->tv_tan_ext[v] + j;
+    // ---- device slots
+    p->hslots.resize(p->n_slots);
+    for (int si = 0; si < p->n_slots; si++) {
+        const auto& s = p->slots[si];
+        DevSlot& ds = p->hslots[si];
+        FInfo fi; finfo(s.type, fi);
+        std::memset(&ds, 0, sizeof(ds));
+        ds.type = s.type; ds.k_begin = s.k_begin; ds.k_end = s.k_end; ds.n_inst = s.k_end - s.k_begin;
+        ds.nvars = s.nvars; ds.rows = factor_rows(s.type); ds.const_off = s.const_offset;
+        int col = 0;
+        for (int v = 0; v < s.nvars; v++) {
+            ds.var_kind[v] = s.var_kind[v]; ds.var_type[v] = fi.vt[v];
+            const int idx = s.var_index[v];
+            if (s.var_kind[v] == B200_AT_STATIC) { ds.val_off[v] = p->sv_valoff[idx]; ds.tan_off[v] = p->sv_tan[idx]; }
+            else { ds.val_off[v] = p->tv_valoff[idx]; ds.tan_off[v] = p->tv_tan_int[idx]; }
+            ds.col_off[v] = col; ds.tan_dim[v] = kTanDim[fi.vt[v]]; col += ds.tan_dim[v];
+        }
+        ds.cols = col;
+        ds.J_off = p->nJ; ds.r_off = p->nr; ds.e_off = p->ne;
+        p->nJ += (long long)ds.rows * ds.cols * ds.n_inst; p->nr += (long long)ds.rows * ds.n_inst; p->ne += ds.n_inst;
+        p->max_inst = std::max(p->max_inst, ds.n_inst);
+        std::memcpy(ds.params, s.params, sizeof(ds.params));
+    }
+    // ---- allocate
+    const long long Kld = dm.Kld;
+    CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    for (auto& e : p->ev) CK(cudaEventCreate(&e));
+    CK(dalloc(&p->d_tv, (size_t)p->tvd * Kld)); CK(dalloc(&p->d_tv_try, (size_t)p->tvd * Kld));
+    CK(dalloc(&p->d_sv, (size_t)p->svd)); CK(dalloc(&p->d_sv_try, (size_t)p->svd));
+    CK(dalloc(&p->d_cst, (size_t)std::max(p->cstride, 1) * Kld));
+    p->stage_doubles = (size_t)p->K * std::max(std::max(p->tvd, p->cstride), dm.ntp);
+    CK(dalloc(&p->d_stage, p->stage_doubles));
+    CK(dalloc(&p->d_slots, (size_t)p->n_slots)); CK(dalloc(&p->d_tvars, (size_t)p->ntv)); CK(dalloc(&p->d_svars, (size_t)p->nsv));
+    CK(dalloc(&p->d_J, (size_t)p->nJ)); CK(dalloc(&p->d_r, (size_t)p->nr)); CK(dalloc(&p->d_e, (size_t)p->ne)); CK(dalloc(&p->d_e2, (size_t)p->ne));
+    const size_t K = p->K;
+    CK(dalloc(&p->d_D, K * dm.ntp * dm.ntp)); CK(dalloc(&p->d_O, K * dm.nc * dm.nc));
+    CK(dalloc(&p->d_A, K * dm.ns1 * dm.ntp)); CK(dalloc(&p->d_S, K * dm.ns1 * dm.ns1));
+    CK(dalloc(&p->sb.Lst, K * dm.ntp * dm.ntp)); CK(dalloc(&p->sb.Pst, K * (size_t)(dm.nc + dm.hmax) * dm.ntp));
+    CK(dalloc(&p->sb.delta, K * dm.ntp)); CK(dalloc(&p->sb.dstat, (size_t)ns + 1)); CK(dalloc(&p->sb.scal, (size_t)SC_COUNT));
+    CK(dalloc(&p->sb.status, (size_t)1));
+    CK(dalloc(&p->sb.Ftop, (size_t)2 * (dm.nc + dm.hmax) * dm.nc)); CK(dalloc(&p->sb.Stop, (size_t)dm.hmax * dm.hmax));
+    CK(cudaMallocHost((void**)&p->h_scal, (SC_COUNT + 2) * sizeof(double)));
+    p->sb.Dsrc = p->d_D; p->sb.Osrc = p->d_O; p->sb.Asrc = p->d_A; p->sb.Ssrc = p->d_S;
+    // uploads
+    CK(cudaMemcpy(p->d_slots, p->hslots.data(), sizeof(DevSlot) * p->n_slots, cudaMemcpyHostToDevice));
+    std::vector<DevVar> tvars(p->ntv), svars(std::max(p->nsv, 1));
+    for (int v = 0; v < p->ntv; v++) tvars[v] = {p->tvtype[v], p->tv_valoff[v], p->tv_tan_int[v]};
+    for (int v = 0; v < p->nsv; v++) svars[v] = {p->svtype[v], p->sv_valoff[v], p->sv_tan[v]};
+    CK(cudaMemcpy(p->d_tvars, tvars.data(), sizeof(DevVar) * p->ntv, cudaMemcpyHostToDevice));
+    if (p->nsv) CK(cudaMemcpy(p->d_svars, svars.data(), sizeof(DevVar) * p->nsv, cudaMemcpyHostToDevice));
+    CK(cudaMemset(p->d_cst, 0, sizeof(double) * std::max(p->cstride, 1) * Kld));
+    if (p->cstride > 0 && d->consts) {
+        CK(cudaMemcpy(p->d_stage, d->consts, sizeof(double) * K * p->cstride, cudaMemcpyHostToDevice));
+        const long long n = (long long)K * p->cstride;
+        B200_LAUNCH(transpose_in_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, p->stream, p->d_stage, p->K, p->cstride, Kld, p->d_cst);
+        p->launches++;
+        CK(cudaStreamSynchronize(p->stream));
+    }
+    // ---- shared memory budgets
+    p->smem_asm[0] = sizeof(double) * ((size_t)dm.ntp * dm.ntp + (size_t)dm.ns1 * dm.ns1 + B200_MAX_FACTOR_ROWS * (B200_MAX_FACTOR_COLS + 1));
+    p->smem_asm[1] = sizeof(double) * ((size_t)dm.nc * dm.nc + (size_t)dm.ns1 * dm.ntp + B200_MAX_FACTOR_ROWS * (B200_MAX_FACTOR_COLS + 1));
+    const size_t smem_cap = 227 * 1024 - 8 * 1024;  // leave room for the kernels' static shared arrays
+    if (std::max(p->smem_asm[0], p->smem_asm[1]) > smem_cap || sizeof(double) * (size_t)dm.ntp * dm.ld > smem_cap)
+        return fail("time block does not fit in shared memory", B200_NOT_IMPLEMENTED);
+    {
+        long long rows_fit = (long long)(smem_cap / sizeof(double)) / dm.ld - B200_NB - 32;
+        const int rn_max = dm.nc + dm.hmax;
+        p->rmax = (int)std::min<long long>(rows_fit, rn_max);
+        if (rows_fit < 32) return fail("panel does not fit in shared memory", B200_NOT_IMPLEMENTED);
+        p->smem_sweep = sizeof(double) * (size_t)sweep_smem_doubles(dm.ntp, dm.ld, p->rmax);
+        const size_t stat = sizeof(double) * (size_t)(dm.ns + 2) * dm.ns1;
+        if (stat > p->smem_sweep) p->smem_sweep = stat;
+    }
+#ifndef B200_USE_EMU
+    CK(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(p->smem_asm[0], p->smem_asm[1])));
+    CK(cudaFuncSetAttribute(chain_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sweep));
+    CK(cudaFuncSetAttribute(top_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sweep));
+    CK(cudaFuncSetAttribute(chain_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sweep));
+#endif
+    p->k_lo = 0; p->k_hi = p->K;
+    // default partition: P ~ sqrt(2.2 K) chunks (interior steps cost ~2.2x a top-level step), at most one CTA per SM
+    int P = (int)std::lround(std::sqrt(2.2 * (double)p->K));
+    if (const char* env = std::getenv("B200_CHUNKS")) P = std::atoi(env);
+    b200_status st = set_partition(p, P);
+    if (st != B200_OK) { b200_problem_destroy(p); return st; }
+    *out = p;
+    return B200_OK;
+}
+
+// choose P chunks of >= 2 keyframes (P == 1: plain sequential sweep)
+static b200_status set_partition(b200_problem* p, int P) {
+    const Dims& dm = p->dm;
+    P = std::max(1, std::min(P, 148));
+    if (p->world > 1) { P = std::max(P, p->world); P = (P + p->world - 1) / p->world * p->world; }
+    while (P > 1 && p->K / P < 3) P -= (p->world > 1 ? p->world : 1);
+    if (P < 1) P = 1;
+    if (p->world > 1 && P % p->world) { set_err("too few keyframes for this many ranks"); return B200_BAD_ARG; }
+    p->P = P;
+    p->begin.resize(P + 1);
+    for (int c = 0; c <= P; c++) p->begin[c] = (int)((long long)c * p->K / P);
+    void* olds[] = {p->sb.Fchunk, p->sb.Schunk, p->sb.Dred, p->sb.Ored, p->sb.Ared, p->sb.Sred, p->sb.sep_idx, p->d_begin};
+    for (void* q : olds) if (q) cudaFree(q);
+    CK(dalloc(&p->sb.Fchunk, (size_t)P * 2 * (dm.nc + dm.hmax) * dm.nc));
+    CK(dalloc(&p->sb.Schunk, (size_t)P * dm.hmax * dm.hmax));
+    CK(dalloc(&p->sb.Dred, (size_t)P * dm.ntp * dm.ntp)); CK(dalloc(&p->sb.Ored, (size_t)P * dm.nc * dm.nc));
+    CK(dalloc(&p->sb.Ared, (size_t)P * dm.ns1 * dm.ntp)); CK(dalloc(&p->sb.Sred, (size_t)P * dm.ns1 * dm.ns1));
+    CK(dalloc(&p->sb.sep_idx, (size_t)P)); CK(dalloc(&p->d_begin, (size_t)P + 1));
+    CK(cudaMemcpy(p->d_begin, p->begin.data(), sizeof(int) * (P + 1), cudaMemcpyHostToDevice));
+    const int per = P / p->world;
+    p->c_lo = p->rank * per; p->c_hi = p->c_lo + per;
+    p->k_lo = p->begin[p->c_lo]; p->k_hi = p->begin[p->c_hi];
+    p->have_lin = false;
+    return B200_OK;
+}
+
+b200_status b200_set_chunks(b200_problem* p, int32_t n_chunks) {
+    if (!p) return B200_BAD_ARG;
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    return set_partition(p, n_chunks);
+}
+int32_t b200_get_chunks(const b200_problem* p) { return p ? p->P : 0; }
+
+int32_t b200_time_value_dim(const b200_problem* p) { return p->tvd; }
+int32_t b200_static_value_dim(const b200_problem* p) { return p->svd; }
+int32_t b200_time_tangent_dim(const b200_problem* p) { return p->dm.nt; }
+int32_t b200_static_tangent_dim(const b200_problem* p) { return p->dm.ns; }
+int64_t b200_launch_count(const b200_problem* p) { return p->launches; }
+
+b200_status b200_set_values(b200_problem* p, const double* tv, const double* sv) {
+    if (!p || !tv || (p->svd && !sv)) return B200_BAD_ARG;
+    CK(cudaSetDevice(p->device));
+    const long long n = (long long)p->K * p->tvd;
+    CK(cudaMemcpyAsync(p->d_stage, tv, sizeof(double) * n, cudaMemcpyHostToDevice, p->stream));
+    B200_LAUNCH(transpose_in_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, p->stream, p->d_stage, p->K, p->tvd, p->dm.Kld, p->d_tv);
+    p->launches++;
+    if (p->svd) CK(cudaMemcpyAsync(p->d_sv, sv, sizeof(double) * p->svd, cudaMemcpyHostToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    CK(cudaGetLastError());
+    p->have_lin = false;
+    return B200_OK;
+}
+
+b200_status b200_get_values(b200_problem* p, double* tv, double* sv) {
+    if (!p || !tv || (p->svd && !sv)) return B200_BAD_ARG;
+    CK(cudaSetDevice(p->device));
+    const long long n = (long long)p->K * p->tvd;
+    B200_LAUNCH(transpose_out_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, p->stream, p->d_tv, p->K, p->tvd, p->dm.Kld, p->d_stage);
+    p->launches++;
+    CK(cudaMemcpyAsync(tv, p->d_stage, sizeof(double) * n, cudaMemcpyDeviceToHost, p->stream));
+    if (p->svd) CK(cudaMemcpyAsync(sv, p->d_sv, sizeof(double) * p->svd, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    CK(cudaGetLastError());
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ pipeline stages (async)
+static void launch_error(b200_problem* p, const double* tv, const double* sv, double* ebuf, int scal_idx) {
+    dim3 grid((p->max_inst + 127) / 128, p->n_slots);
+    B200_LAUNCH(linearize_kernel<false>, grid, dim3(128), 0, p->stream, p->d_slots, tv, sv, p->d_cst, p->dm.Kld, (double*)nullptr,
+                (double*)nullptr, ebuf, p->k_lo, p->k_hi);
+    B200_LAUNCH(reduce_sum_kernel, dim3(1), dim3(1024), 0, p->stream, ebuf, p->ne, p->sb.scal + scal_idx);
+    p->launches += 2;
+}
+
+static void launch_linearize(b200_problem* p) {
+    dim3 grid((p->max_inst + 127) / 128, p->n_slots);
+    // Jacobians are needed one keyframe to the left of the window (the IMU factor k_lo-1 -> k_lo feeds D[k_lo])
+    B200_LAUNCH(linearize_kernel<true>, grid, dim3(128), 0, p->stream, p->d_slots, p->d_tv, p->d_sv, p->d_cst, p->dm.Kld, p->d_J, p->d_r,
+                p->d_e, std::max(p->k_lo - 1, 0), p->k_hi);
+    p->launches++;
+    for (int half = 0; half < 2; half++) {
+        // (two launches: the halves need different amounts of shared memory)
+    }
+    B200_LAUNCH(assemble_kernel, dim3(p->k_hi - p->k_lo, 2), dim3(256), std::max(p->smem_asm[0], p->smem_asm[1]), p->stream, p->dm,
+                p->d_slots, p->n_slots, p->d_J, p->d_r, (const int*)nullptr, p->k_lo, 0, p->K, p->d_D, p->d_O, p->d_A, p->d_S);
+    p->launches++;
+}
+
+static b200_status exchange_reduced(b200_problem* p);
+
+static b200_status launch_solve(b200_problem* p, double lambda) {
+    CK(cudaMemsetAsync(p->sb.status, 0, sizeof(int), p->stream));
+    ChunkPlan pl{p->d_begin, p->P};
+    if (p->P > 1) {
+        B200_LAUNCH(chain_sweep_kernel, dim3(p->c_hi - p->c_lo), dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, p->dm, pl, p->sb, lambda,
+                    p->rmax, p->c_lo);
+        p->launches++;
+        if (p->world > 1) { b200_status st = exchange_reduced(p); if (st != B200_OK) return st; }
+        B200_LAUNCH(reduced_assemble_kernel, dim3(p->P - 1), dim3(256), 0, p->stream, p->dm, pl, p->sb);
+        p->launches++;
+    }
+    B200_LAUNCH(top_solve_kernel, dim3(1), dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, p->dm, pl, p->sb, lambda, p->rmax);
+    p->launches++;
+    if (p->P > 1) {
+        B200_LAUNCH(chain_backsub_kernel, dim3(p->c_hi - p->c_lo), dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, p->dm, pl, p->sb, p->c_lo);
+        p->launches++;
+    }
+    return B200_OK;
+}
+
+// multi-rank: make every rank hold every chunk's Schur complement / fill and every separator's assembled blocks, and (after
+// back-substitution) every keyframe's step.  Collectives are supplied by the host (NCCL through torch.distributed or
+// ncclAllGather in a C++ host); payloads stay on the device.
+static b200_status exchange_reduced(b200_problem* p) {
+    if (!p->ag_fn) { set_err("world_size > 1 but no collective registered"); return B200_NCCL_ERROR; }
+    const Dims& dm = p->dm;
+    const int per = p->P / p->world;
+    const size_t fsz = (size_t)2 * (dm.nc + dm.hmax) * dm.nc, ssz = (size_t)dm.hmax * dm.hmax;
+    if (p->ag_fn(p->comm_ctx, p->sb.Fchunk, sizeof(double) * fsz * per, p->stream)) { set_err("allgather failed"); return B200_NCCL_ERROR; }
+    if (p->ag_fn(p->comm_ctx, p->sb.Schunk, sizeof(double) * ssz * per, p->stream)) { set_err("allgather failed"); return B200_NCCL_ERROR; }
+    return B200_OK;
+}
+
+static b200_status fetch_scalars(b200_problem* p) {
+    CK(cudaMemcpyAsync(p->h_scal, p->sb.scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaMemcpyAsync(p->h_scal + SC_COUNT, p->sb.status, sizeof(int), cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    CK(cudaGetLastError());
+    return B200_OK;
+}
+static int host_status(const b200_problem* p) { return *reinterpret_cast<const int*>(p->h_scal + SC_COUNT); }
+
+static b200_status allreduce_scal(b200_problem* p) {
+    if (p->world <= 1) return B200_OK;
+    if (!p->ar_fn) { set_err("world_size > 1 but no collective registered"); return B200_NCCL_ERROR; }
+    if (p->ar_fn(p->comm_ctx, p->sb.scal, SC_COUNT, p->stream)) { set_err("allreduce failed"); return B200_NCCL_ERROR; }
+    return B200_OK;
+}
+
+b200_status b200_error(b200_problem* p, double* error) {
+    if (!p || !error) return B200_BAD_ARG;
+    CK(cudaSetDevice(p->device));
+    CK(cudaMemsetAsync(p->sb.scal, 0, sizeof(double) * SC_COUNT, p->stream));
+    launch_error(p, p->d_tv, p->d_sv, p->d_e2, SC_CUR_ERR);
+    b200_status st = allreduce_scal(p); if (st != B200_OK) return st;
+    st = fetch_scalars(p); if (st != B200_OK) return st;
+    *error = p->h_scal[SC_CUR_ERR];
+    return B200_OK;
+}
+
+b200_status b200_lm_begin(b200_problem* p, const b200_lm_params* prm, double* initial_error) {
+    if (!p || !prm) return B200_BAD_ARG;
+    p->lm = *prm;
+    p->lambda = prm->gauss_newton ? 0.0 : prm->lambda_initial;
+    p->iterations = 0; p->total_trials = 0; p->have_lin = false;
+    double e;
+    b200_status st = b200_error(p, &e);
+    if (st != B200_OK) return st;
+    p->err = e;
+    if (initial_error) *initial_error = e;
+    return B200_OK;
+}
+
+static b200_status gather_delta(b200_problem* p) {
+    if (p->world <= 1) return B200_OK;
+    // every rank back-substituted its own window; exchange the steps so the replicated values stay identical
+    return B200_NOT_IMPLEMENTED;
+}
+
+// == LevenbergMarquardtOptimizer::iterate() (gtsam @4.2: iterate / tryLambda / increaseLambda / decreaseLambda)
+b200_status b200_lm_iterate(b200_problem* p, b200_lm_state* state) {
+    if (!p) return B200_BAD_ARG;
+    CK(cudaSetDevice(p->device));
+    const b200_lm_params& L = p->lm;
+    if (p->time_phases) CK(cudaEventRecord(p->ev[0], p->stream));
+    CK(cudaMemsetAsync(p->sb.scal, 0, sizeof(double) * SC_COUNT, p->stream));
+    launch_linearize(p);
+    B200_LAUNCH(reduce_sum_kernel, dim3(1), dim3(1024), 0, p->stream, p->d_e, p->ne, p->sb.scal + SC_LIN_ERR);
+    p->launches++;
+    if (p->time_phases) CK(cudaEventRecord(p->ev[1], p->stream));
+    p->have_lin = true;
+    int status = B200_OK, inner = 0;
+    while (true) {  // tryLambda
+        inner++;
+        if (p->time_phases) CK(cudaEventRecord(p->ev[2], p->stream));
+        b200_status st = launch_solve(p, p->lambda);
+        if (st != B200_OK) return st;
+        st = gather_delta(p); if (st != B200_OK) return st;
+        if (p->time_phases) CK(cudaEventRecord(p->ev[3], p->stream));
+        dim3 grid((p->max_inst + 127) / 128, p->n_slots);
+        B200_LAUNCH(model_error_kernel, grid, dim3(128), 0, p->stream, p->d_slots, p->d_J, p->d_r, p->sb.delta, p->dm.ntp, p->sb.dstat, p->d_e2,
+                    p->k_lo, p->k_hi);
+        B200_LAUNCH(reduce_sum_kernel, dim3(1), dim3(1024), 0, p->stream, p->d_e2, p->ne, p->sb.scal + SC_MODEL_ERR);
+        B200_LAUNCH(retract_kernel, dim3((p->K + 127) / 128, 1, p->ntv), dim3(128), 0, p->stream, p->d_tvars, p->ntv, p->d_svars, p->nsv, p->K,
+                    p->dm.Kld, p->d_tv, p->d_sv, p->sb.delta, p->dm.ntp, p->sb.dstat, p->d_tv_try, p->d_sv_try);
+        p->launches += 3;
+        if (p->nsv) {
+            B200_LAUNCH(retract_kernel, dim3((p->nsv + 127) / 128, 2, 1), dim3(128), 0, p->stream, p->d_tvars, 0, p->d_svars, p->nsv, 0, p->dm.Kld,
+                        p->d_tv, p->d_sv, p->sb.delta, p->dm.ntp, p->sb.dstat, p->d_tv_try, p->d_sv_try);
+            p->launches++;
+        }
+        launch_error(p, p->d_tv_try, p->d_sv_try, p->d_e2, SC_NEW_ERR);
+        st = allreduce_scal(p); if (st != B200_OK) return st;
+        if (p->time_phases) CK(cudaEventRecord(p->ev[4], p->stream));
+        st = fetch_scalars(p); if (st != B200_OK) return st;
+        if (p->time_phases) {
+            float ms;
+            if (inner == 1) { cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]); p->phase_ms[0] += ms; }
+            cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]); p->phase_ms[1] += ms;
+            cudaEventElapsedTime(&ms, p->ev[3], p->ev[4]); p->phase_ms[2] += ms;
+        }
+        const bool solved = host_status(p) == 0;
+        const double oldLin = p->h_scal[SC_LIN_ERR], newLin = p->h_scal[SC_MODEL_ERR], newError = p->h_scal[SC_NEW_ERR];
+        double modelFidelity = 0.0;
+        bool step_ok = false, stop = false;
+        if (solved) {
+            const double linChange = oldLin - newLin;
+            if (L.gauss_newton) step_ok = true;
+            else if (linChange >= 0) {
+                const double costChange = p->err - newError;
+                if (linChange > 2.220446049250313e-16 * oldLin) {
+                    modelFidelity = costChange / linChange;
+                    step_ok = modelFidelity > L.min_model_fidelity;
+                }
+                if (std::fabs(costChange) < L.relative_error_tol * p->err) stop = true;
+            }
+            status = B200_OK;
+        } else status = B200_INDETERMINATE_SYSTEM;
+        if (step_ok) {
+            std::swap(p->d_tv, p->d_tv_try); std::swap(p->d_sv, p->d_sv_try);
+            p->err = newError;
+            if (!L.gauss_newton) p->lambda = std::max(L.lambda_lower_bound, p->lambda / L.lambda_factor);
+            p->iterations++; p->total_trials++;
+            p->have_lin = false;
+            status = B200_OK;
+            break;
+        } else if (!stop) {
+            p->lambda *= L.lambda_factor; p->total_trials++;
+            if (p->lambda >= L.lambda_upper_bound) { status = B200_LAMBDA_MAXED; break; }
+            if (L.gauss_newton) { status = B200_INDETERMINATE_SYSTEM; break; }
+        } else break;
+    }
+    if (state) {
+        state->error = p->err; state->lambda = p->lambda; state->iterations = p->iterations; state->inner_trials = inner;
+        state->total_trials = p->total_trials; state->status = status;
+    }
+    return (b200_status)status;
+}
+
+// bioslam's fastOptimize loops (reference src/lowerBodyPoseEstimator.cpp:651-667 ; src/imuPoseEstimator.cpp:330-359)
+b200_status b200_optimize(b200_problem* p, const b200_lm_params* lm, const b200_outer_params* op, double* hist, b200_optimize_result* res) {
+    if (!p || !lm || !op) return B200_BAD_ARG;
+    CK(cudaSetDevice(p->device));
+    double e0 = 0;
+    b200_status st = b200_lm_begin(p, lm, &e0);
+    if (st != B200_OK) return st;
+    CK(cudaEventRecord(p->ev[6], p->stream));
+    double current = e0, previous = e0;
+    int nh = 0, consec = 0, calls = 0;
+    if (hist && nh < op->max_history) hist[nh++] = e0;
+    b200_lm_state s{};
+    if (op->single_imu_rule) {
+        double absDec = 9.0e9, relDec = 9.0e9;
+        while (relDec > op->rel_err_decrease_limit && absDec > op->abs_err_decrease_limit && current > op->abs_err_limit &&
+               p->iterations < op->max_iterations) {
+            const int before = p->iterations;
+            st = b200_lm_iterate(p, &s); calls++;
+            if (st == B200_CUDA_ERROR || st == B200_BAD_ARG || st == B200_NCCL_ERROR || st == B200_NOT_IMPLEMENTED) return st;
+            previous = current; current = s.error;
+            absDec = previous - current; relDec = absDec / previous;
+            if (hist && nh < op->max_history) hist[nh++] = current;
+            if (p->iterations == before) break;
+        }
+    } else {
+        while (consec < op->converge_at_consec_small_iter && p->iterations < op->max_iterations) {
+            const int before = p->iterations;
+            previous = current;
+            st = b200_lm_iterate(p, &s); calls++;
+            if (st == B200_CUDA_ERROR || st == B200_BAD_ARG || st == B200_NCCL_ERROR || st == B200_NOT_IMPLEMENTED) return st;
+            current = s.error;
+            const double absDec = previous - current, relDec = absDec / previous;
+            if (absDec < op->abs_err_decrease_limit || relDec < op->rel_err_decrease_limit || current < op->abs_err_limit) consec++;
+            else consec = 0;
+            if (hist && nh < op->max_history) hist[nh++] = current;
+            if (p->iterations == before && st != B200_OK) break;
+        }
+    }
+    CK(cudaEventRecord(p->ev[7], p->stream));
+    CK(cudaEventSynchronize(p->ev[7]));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, p->ev[6], p->ev[7]);
+    if (res) {
+        res->initial_error = e0; res->final_error = p->err; res->final_lambda = p->lambda; res->iterations = p->iterations;
+        res->outer_calls = calls; res->total_trials = p->total_trials; res->n_history = nh; res->status = st; res->device_ms = ms;
+    }
+    return st;
+}
+
+b200_status b200_phase_ms(b200_problem* p, double out[4], int32_t reset) {
+    if (!p) return B200_BAD_ARG;
+    p->time_phases = true;
+    if (out) for (int i = 0; i < 4; i++) out[i] = p->phase_ms[i];
+    if (reset) for (int i = 0; i < 4; i++) p->phase_ms[i] = 0;
+    return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ preintegration (A0)
+b200_status b200_preintegrate(int32_t device, int32_t n_imu, int32_t n_samples, int32_t n_per, int32_t n_intervals, const double* acc,
+                              const double* gyro, double dt, const double* bias_hat, const b200_imu_noise* noise, int32_t combined,
+                              double* out) {
+    if (!acc || !gyro || !bias_hat || !noise || !out || n_imu < 1 || n_per < 1 || n_intervals < 1 || !(dt > 0) ||
+        (long long)n_intervals * n_per > n_samples) { set_err("bad preintegration arguments"); return B200_BAD_ARG; }
+    CK(cudaSetDevice(device));
+    const int rec = combined ? 190 : 115;
+    const size_t ns3 = (size_t)n_imu * n_samples * 3;
+    double *d_acc = nullptr, *d_gyro = nullptr, *d_bh = nullptr, *d_out = nullptr, *d_outT = nullptr;
+    int* d_bad = nullptr;
+    b200_status ret = B200_OK;
+    auto cleanup = [&]() { cudaFree(d_acc); cudaFree(d_gyro); cudaFree(d_bh); cudaFree(d_out); cudaFree(d_outT); cudaFree(d_bad); };
+#define CKP(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_err(std::string(#call) + ": " + cudaGetErrorString(e__)); cleanup(); return B200_CUDA_ERROR; } } while (0)
+    CKP(dalloc(&d_acc, ns3)); CKP(dalloc(&d_gyro, ns3)); CKP(dalloc(&d_bh, (size_t)n_imu * 6));
+    CKP(dalloc(&d_out, (size_t)n_imu * rec * n_intervals)); CKP(dalloc(&d_outT, (size_t)n_imu * rec * n_intervals)); CKP(dalloc(&d_bad, (size_t)1));
+    CKP(cudaMemcpy(d_acc, acc, sizeof(double) * ns3, cudaMemcpyHostToDevice));
+    CKP(cudaMemcpy(d_gyro, gyro, sizeof(double) * ns3, cudaMemcpyHostToDevice));
+    CKP(cudaMemcpy(d_bh, bias_hat, sizeof(double) * n_imu * 6, cudaMemcpyHostToDevice));
+    CKP(cudaMemset(d_bad, 0, sizeof(int)));
+    B200_LAUNCH(preintegrate_kernel, dim3((n_intervals + 63) / 64, n_imu), dim3(64), 0, (cudaStream_t)0, n_imu, n_samples, n_per, n_intervals,
+                d_acc, d_gyro, dt, d_bh, *noise, combined, d_out, (long long)n_intervals, d_bad);
+    // d_out is [n_imu*rec][n_intervals] (SoA); ABI output is [n_imu][n_intervals][rec]
+    for (int m = 0; m < n_imu; m++) {
+        const long long n = (long long)n_intervals * rec;
+        B200_LAUNCH(transpose_out_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)0, d_out + (size_t)m * rec * n_intervals,
+                    n_intervals, rec, (long long)n_intervals, d_outT + (size_t)m * rec * n_intervals);
+    }
+    CKP(cudaDeviceSynchronize());
+    CKP(cudaGetLastError());
+    int bad = 0;
+    CKP(cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost));
+    CKP(cudaMemcpy(out, d_outT, sizeof(double) * n_imu * rec * n_intervals, cudaMemcpyDeviceToHost));
+    cleanup();
+    if (bad) { set_err("preintegrated covariance not positive definite"); ret = B200_INDETERMINATE_SYSTEM; }
+    return ret;
+}
+
+b200_status b200_preintegrate_combined(int32_t device, int32_t n_imu, int32_t n_samples, int32_t n_per, int32_t n_intervals, const double* acc,
+                                       const double* gyro, double dt, const double* bias_hat, const b200_imu_noise* noise, double* out) {
+    return b200_preintegrate(device, n_imu, n_samples, n_per, n_intervals, acc, gyro, dt, bias_hat, noise, 1, out);
+}
+
+// ------------------------------------------------------------------------------------------ multi-rank plumbing
+b200_status b200_comm_set(b200_problem* p, int32_t world_size, int32_t rank, b200_allgather_fn ag, b200_allreduce_fn ar, void* ctx) {
+    if (!p || world_size < 1 || rank < 0 || rank >= world_size) return B200_BAD_ARG;
+    CK(cudaSetDevice(p->device));
+    p->world = world_size; p->rank = rank; p->ag_fn = ag; p->ar_fn = ar; p->comm_ctx = ctx;
+    return set_partition(p, p->P);
+}
+
+// ------------------------------------------------------------------------------------------ parity / debug accessors
+b200_status b200_debug_linearize(b200_problem* p) {
+    if (!p) return B200_BAD_ARG;
+    CK(cudaSetDevice(p->device));
+    launch_linearize(p);
+    CK(cudaStreamSynchronize(p->stream));
+    CK(cudaGetLastError());
+    p->have_lin = true;
+    return B200_OK;
+}
+
+b200_status b200_debug_get_gradient(b200_problem* p, double* g_time, double* g_static) {
+    if (!p || !p->have_lin) return B200_BAD_ARG;
+    const Dims& dm = p->dm;
+    std::vector<double> A((size_t)p->K * dm.ns1 * dm.ntp), S((size_t)dm.ns1 * dm.ns1);
+    CK(cudaMemcpy(A.data(), p->d_A, sizeof(double) * A.size(), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < p->K; k++)
+        for (int i = 0; i < dm.ntp; i++)
+            if (p->int2ext[i] >= 0) g_time[(size_t)k * dm.nt + p->int2ext[i]] = -A[((size_t)k * dm.ns1 + dm.ns) * dm.ntp + i];
+    // static gradient: sum over keyframes of the rhs column of Sx_k
+    std::vector<double> Sall((size_t)p->K * dm.ns1 * dm.ns1);
+    CK(cudaMemcpy(Sall.data(), p->d_S, sizeof(double) * Sall.size(), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < dm.ns; i++) {
+        double acc = 0;
+        for (int k = 0; k < p->K; k++) acc += Sall[(size_t)k * dm.ns1 * dm.ns1 + (size_t)i * dm.ns1 + dm.ns];
+        g_static[i] = -acc;
+    }
+    return B200_OK;
+}
+
+b200_status b200_debug_get_hessian_blocks(b200_problem* p, int32_t k, double* D, double* O, double* A) {
+    if (!p || !p->have_lin || k < 0 || k >= p->K) return B200_BAD_ARG;
+    const Dims& dm = p->dm;
+    const int nt = dm.nt, ntp = dm.ntp, nc = dm.nc, nl = dm.nl, ns = dm.ns, ns1 = dm.ns1;
+    std::vector<double> Db((size_t)ntp * ntp), Ob((size_t)nc * nc), Ab((size_t)ns1 * ntp);
+    CK(cudaMemcpy(Db.data(), p->d_D + (size_t)k * ntp * ntp, sizeof(double) * Db.size(), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(Ob.data(), p->d_O + (size_t)k * nc * nc, sizeof(double) * Ob.size(), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(Ab.data(), p->d_A + (size_t)k * ns1 * ntp, sizeof(double) * Ab.size(), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < nt * nt; i++) { D[i] = 0; O[i] = 0; }
+    for (int i = 0; i < ntp; i++)
+        for (int j = 0; j < ntp; j++) {
+            const int ei = p->int2ext[i], ej = p->int2ext[j];
+            if (ei < 0 || ej < 0) continue;
+            D[(size_t)ei * nt + ej] = Db[(size_t)i * ntp + j];
+            // O (k, k+1): rows k, cols k+1 ; device stores (k+1 chain) x (k chain)
+            if (k + 1 < p->K && i >= nl && j >= nl) O[(size_t)ej * nt + ei] = Ob[(size_t)(i - nl) * nc + (j - nl)];
+        }
+    for (int i = 0; i < ntp; i++) {
+        const int ei = p->int2ext[i];
+        if (ei < 0) continue;
+        for (int s = 0; s < ns; s++) A[(size_t)ei * ns + s] = Ab[(size_t)s * ntp + i];
+    }
+    return B200_OK;
+}
+
+b200_status b200_debug_get_static_hessian(b200_problem* p, double* S) {
+    if (!p || !p->have_lin) return B200_BAD_ARG;
+    const Dims& dm = p->dm;
+    std::vector<double> Sall((size_t)p->K * dm.ns1 * dm.ns1);
+    CK(cudaMemcpy(Sall.data(), p->d_S, sizeof(double) * Sall.size(), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < dm.ns; i++)
+        for (int j = 0; j < dm.ns; j++) {
+            double acc = 0;
+            for (int k = 0; k < p->K; k++) acc += Sall[(size_t)k * dm.ns1 * dm.ns1 + (size_t)i * dm.ns1 + j];
+            S[(size_t)i * dm.ns + j] = acc;
+        }
+    return B200_OK;
+}
+
+b200_status b200_debug_solve(b200_problem* p, double lambda, double* delta_time, double* delta_static) {
+    if (!p || !p->have_lin) return B200_BAD_ARG;
+    CK(cudaSetDevice(p->device));
+    const Dims& dm = p->dm;
+    b200_status st = launch_solve(p, lambda);
+    if (st != B200_OK) return st;
+    st = fetch_scalars(p);
+    if (st != B200_OK) return st;
+    if (host_status(p) != 0) return B200_INDETERMINATE_SYSTEM;
+    std::vector<double> dl((size_t)p->K * dm.ntp);
+    CK(cudaMemcpy(dl.data(), p->sb.delta, sizeof(double) * dl.size(), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < p->K; k++)
+        for (int i = 0; i < dm.ntp; i++)
+            if (p->int2ext[i] >= 0) delta_time[(size_t)k * dm.nt + p->int2ext[i]] = dl[(size_t)k * dm.ntp + i];
+    if (dm.ns) CK(cudaMemcpy(delta_static, p->sb.dstat, sizeof(double) * dm.ns, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+}  // extern "C"

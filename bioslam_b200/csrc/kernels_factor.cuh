@@ -1,0 +1,176 @@
+// Factor-level kernels: linearization (residual + whitened Jacobian per factor instance), error-only evaluation,
+// deterministic cost reduction, linear-model error (GaussianFactorGraph::error(delta)) and retraction.
+//
+// Layout in HBM (DESIGN.md "data layout"): keyframe-major SoA.  Time-variable values tv[component][Kld], per-keyframe
+// constants cst[component][Kld], whitened Jacobians Jbuf[slot][row*cols+col][n_inst] and residuals rbuf[slot][row][n_inst]:
+// consecutive lanes (consecutive keyframes of one factor slot) touch consecutive addresses.
+#pragma once
+#include "factors.cuh"
+
+namespace b200d {
+
+struct DevSlot {
+    int type, k_begin, k_end, n_inst;
+    int nvars, rows, cols, const_off;   // const_off: first component row in cst (or -1)
+    int var_kind[B200_MAX_FACTOR_VARS];
+    int var_type[B200_MAX_FACTOR_VARS];
+    int val_off[B200_MAX_FACTOR_VARS];  // time var: first component row in tv ; static var: offset in sv
+    int tan_off[B200_MAX_FACTOR_VARS];  // internal tangent offset inside the time block / static block
+    int col_off[B200_MAX_FACTOR_VARS];  // first Jacobian column of the variable
+    int tan_dim[B200_MAX_FACTOR_VARS];
+    long long J_off, r_off, e_off;      // offsets (doubles) into Jbuf / rbuf / ebuf
+    double params[B200_MAX_FACTOR_PARAMS];
+};
+
+__device__ __forceinline__ int val_dim_of(int vt) { return vt == B200_VAR_POSE3 ? 12 : (vt == B200_VAR_BIAS6 ? 6 : 3); }
+
+// gather the variable values of one factor instance into registers/local memory
+__device__ __forceinline__ void load_vars(const DevSlot& s, int k, const double* __restrict__ tv, long long Kld,
+                                          const double* __restrict__ sv, double (*xv)[12], const double** x) {
+    for (int v = 0; v < s.nvars; v++) {
+        const int n = val_dim_of(s.var_type[v]);
+        if (s.var_kind[v] == B200_AT_STATIC) {
+            for (int c = 0; c < n; c++) xv[v][c] = sv[s.val_off[v] + c];
+        } else {
+            const long long kk = k + (s.var_kind[v] == B200_AT_K1 ? 1 : 0);
+            for (int c = 0; c < n; c++) xv[v][c] = tv[(long long)(s.val_off[v] + c) * Kld + kk];
+        }
+        x[v] = xv[v];
+    }
+}
+
+// grid: (ceil(max_inst/128), n_slots), block 128.  One thread = one factor instance.
+template <bool WJ>
+__global__ void __launch_bounds__(128) linearize_kernel(const DevSlot* __restrict__ slots, const double* __restrict__ tv,
+                                                        const double* __restrict__ sv, const double* __restrict__ cst, long long Kld,
+                                                        double* __restrict__ Jbuf, double* __restrict__ rbuf, double* __restrict__ ebuf,
+                                                        int k_lo, int k_hi) {
+    const DevSlot& s = slots[blockIdx.y];
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= s.n_inst) return;
+    const int k = s.k_begin + inst;
+    if (k < k_lo || k >= k_hi) {  // outside this rank's window: contributes nothing to the local cost
+        ebuf[s.e_off + inst] = 0.0;
+        return;
+    }
+    double xv[B200_MAX_FACTOR_VARS][12];
+    const double* x[B200_MAX_FACTOR_VARS];
+    load_vars(s, k, tv, Kld, sv, xv, x);
+    CstRef c;
+    c.p = cst + (long long)(s.const_off < 0 ? 0 : s.const_off) * Kld + k;
+    c.stride = Kld;
+    double r[B200_MAX_FACTOR_ROWS];
+    double J[WJ ? B200_MAX_FACTOR_ROWS * B200_MAX_FACTOR_COLS : 1];
+    factor_eval<WJ>(s.type, s.params, c, x, r, J, s.cols);
+    factor_whiten<WJ>(s.type, s.params, c, r, J, s.cols);
+    double e = 0.0;
+    for (int i = 0; i < s.rows; i++) e += r[i] * r[i];
+    ebuf[s.e_off + inst] = 0.5 * e;
+    if (WJ) {
+        const long long n = s.n_inst;
+        for (int i = 0; i < s.rows; i++) rbuf[s.r_off + (long long)i * n + inst] = r[i];
+        const int ne = s.rows * s.cols;
+        for (int i = 0; i < ne; i++) Jbuf[s.J_off + (long long)i * n + inst] = J[i];
+    }
+}
+
+// deterministic sum of n doubles: fixed strided partials per thread, fixed shared-memory tree.  grid 1, block 1024.
+__global__ void __launch_bounds__(1024) reduce_sum_kernel(const double* __restrict__ v, long long n, double* __restrict__ out) {
+    __shared__ double sh[1024];
+    double acc = 0.0;
+    for (long long i = threadIdx.x; i < n; i += 1024) acc += v[i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 512; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sh[0];
+}
+
+// 0.5*||J delta + r||^2 per factor instance on the stored linearization; delta in internal order:
+// dtime[K][ntp], dstat[ns].  zero_delta: evaluate at delta = 0 (== linear.error(Zero)).
+__global__ void __launch_bounds__(128) model_error_kernel(const DevSlot* __restrict__ slots, const double* __restrict__ Jbuf,
+                                                          const double* __restrict__ rbuf, const double* __restrict__ dtime, int ntp,
+                                                          const double* __restrict__ dstat, double* __restrict__ ebuf, int k_lo, int k_hi) {
+    const DevSlot& s = slots[blockIdx.y];
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= s.n_inst) return;
+    const int k = s.k_begin + inst;
+    if (k < k_lo || k >= k_hi) { ebuf[s.e_off + inst] = 0.0; return; }
+    double dl[B200_MAX_FACTOR_COLS];
+    for (int v = 0; v < s.nvars; v++) {
+        const double* src = (s.var_kind[v] == B200_AT_STATIC)
+                                ? dstat + s.tan_off[v]
+                                : dtime + (long long)(k + (s.var_kind[v] == B200_AT_K1 ? 1 : 0)) * ntp + s.tan_off[v];
+        for (int j = 0; j < s.tan_dim[v]; j++) dl[s.col_off[v] + j] = src[j];
+    }
+    const long long n = s.n_inst;
+    double e = 0.0;
+    for (int i = 0; i < s.rows; i++) {
+        double a = rbuf[s.r_off + (long long)i * n + inst];
+        for (int c = 0; c < s.cols; c++) a += Jbuf[s.J_off + (long long)(i * s.cols + c) * n + inst] * dl[c];
+        e += a * a;
+    }
+    ebuf[s.e_off + inst] = 0.5 * e;
+}
+
+struct DevVar {
+    int type, val_off, tan_off;  // val_off: component row (time) or offset (static); tan_off internal
+};
+
+// retraction of every variable: thread = (keyframe, time variable) ; static variables by block y==1.
+__global__ void __launch_bounds__(128) retract_kernel(const DevVar* __restrict__ tvars, int ntv, const DevVar* __restrict__ svars, int nsv,
+                                                      int K, long long Kld, const double* __restrict__ tv, const double* __restrict__ sv,
+                                                      const double* __restrict__ dtime, int ntp, const double* __restrict__ dstat,
+                                                      double* __restrict__ tv_out, double* __restrict__ sv_out) {
+    if (blockIdx.y == 1) {
+        const int v = blockIdx.x * blockDim.x + threadIdx.x;
+        if (v >= nsv) return;
+        const DevVar var = svars[v];
+        const int n = val_dim_of(var.type);
+        double xin[12], xout[12], d[6];
+        for (int c = 0; c < n; c++) xin[c] = sv[var.val_off + c];
+        const int td = (var.type == B200_VAR_UNIT3) ? 2 : (var.type == B200_VAR_VEC3 ? 3 : 6);
+        for (int c = 0; c < td; c++) d[c] = dstat[var.tan_off + c];
+        switch (var.type) {
+        case B200_VAR_POSE3: pose3_retract(xout, xin, d); break;
+        case B200_VAR_UNIT3: unit3_retract(xout, xin, d); break;
+        default: for (int c = 0; c < n; c++) xout[c] = xin[c] + d[c]; break;
+        }
+        for (int c = 0; c < n; c++) sv_out[var.val_off + c] = xout[c];
+        return;
+    }
+    // time variables: blockIdx.z = variable, x-dimension = keyframes (coalesced)
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = blockIdx.z;
+    if (k >= K || v >= ntv) return;
+    const DevVar var = tvars[v];
+    const int n = val_dim_of(var.type);
+    double xin[12], xout[12], d[6];
+    for (int c = 0; c < n; c++) xin[c] = tv[(long long)(var.val_off + c) * Kld + k];
+    const int td = (var.type == B200_VAR_UNIT3) ? 2 : (var.type == B200_VAR_VEC3 ? 3 : 6);
+    for (int c = 0; c < td; c++) d[c] = dtime[(long long)k * ntp + var.tan_off + c];
+    switch (var.type) {
+    case B200_VAR_POSE3: pose3_retract(xout, xin, d); break;
+    case B200_VAR_UNIT3: unit3_retract(xout, xin, d); break;
+    default: for (int c = 0; c < n; c++) xout[c] = xin[c] + d[c]; break;
+    }
+    for (int c = 0; c < n; c++) tv_out[(long long)(var.val_off + c) * Kld + k] = xout[c];
+}
+
+// [K][dim] (host/ABI layout) <-> [dim][Kld] (device SoA)
+__global__ void transpose_in_kernel(const double* __restrict__ src, int K, int dim, long long Kld, double* __restrict__ dst) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)K * dim) return;
+    const int c = (int)(i / K), k = (int)(i % K);
+    dst[(long long)c * Kld + k] = src[(long long)k * dim + c];
+}
+__global__ void transpose_out_kernel(const double* __restrict__ src, int K, int dim, long long Kld, double* __restrict__ dst) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)K * dim) return;
+    const int k = (int)(i / dim), c = (int)(i % dim);
+    dst[(long long)k * dim + c] = src[(long long)c * Kld + k];
+}
+
+}  // namespace b200d

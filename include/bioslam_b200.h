@@ -251,13 +251,30 @@ b200_status b200_preintegrate_combined(int32_t device, int32_t n_imu, int32_t n_
                                        int32_t n_intervals, const double* acc, const double* gyro, double dt,
                                        const double* bias_hat, const b200_imu_noise* noise, double* out);
 
+/* static-bias twin (gtsam::ImuFactor / PreintegratedImuMeasurements, reference src/imuPoseEstimator.cpp:271-296):
+ * combined=0 -> 115-double records laid out as B200_F_IMU_STATICBIAS consts; combined=1 == b200_preintegrate_combined */
+b200_status b200_preintegrate(int32_t device, int32_t n_imu, int32_t n_samples, int32_t n_per, int32_t n_intervals,
+                              const double* acc, const double* gyro, double dt, const double* bias_hat,
+                              const b200_imu_noise* noise, int32_t combined, double* out);
+
+/* ---------------------------------------------------------------- solver partition
+ * The time chain is cut into n_chunks contiguous windows that are eliminated in parallel (one CTA each) and joined through
+ * a reduced system on the separator keyframes.  Default: ~sqrt(2.2 K), at most one per SM; 1 = plain sequential sweep. */
+b200_status b200_set_chunks(b200_problem* p, int32_t n_chunks);
+int32_t b200_get_chunks(const b200_problem* p);
+
 /* ---------------------------------------------------------------- multi-GPU (time axis sharded, section 8(e))
- * One process per GPU.  Rank 0 calls b200_comm_unique_id, the host broadcasts the 128 bytes (any transport),
- * every rank calls b200_comm_init; the library then owns an NCCL communicator for this problem.
- * The problem must have been created with the FULL description on every rank; each rank linearizes and eliminates
- * its contiguous window of keyframes only. */
-b200_status b200_comm_unique_id(char id[128]);
-b200_status b200_comm_init(b200_problem* p, int32_t world_size, int32_t rank, const char id[128]);
+ * One process per GPU, every rank creates the problem with the FULL description and the same values.  Rank r owns a
+ * contiguous range of chunks (== a window of keyframes): it linearizes and eliminates only that window.  The two
+ * exchange steps are delegated to host-supplied collectives operating on DEVICE pointers and ordered on the given CUDA
+ * stream (torch.distributed / NCCL in the Python host, ncclAllGather / ncclAllReduce in a C++ host):
+ *   allgather: in place; buf holds world_size segments of bytes_per_rank, segment `rank` is this rank's contribution.
+ *   allreduce: in-place sum of n doubles.
+ * Both return 0 on success. */
+typedef int (*b200_allgather_fn)(void* ctx, void* dev_buf, uint64_t bytes_per_rank, void* cuda_stream);
+typedef int (*b200_allreduce_fn)(void* ctx, double* dev_buf, int32_t n, void* cuda_stream);
+b200_status b200_comm_set(b200_problem* p, int32_t world_size, int32_t rank, b200_allgather_fn allgather,
+                          b200_allreduce_fn allreduce, void* ctx);
 
 /* ---------------------------------------------------------------- parity/debug accessors (used by tests only)
  * External tangent order == variable table order (the library permutes internally). */
