@@ -229,7 +229,15 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
     // ---- shared memory budgets
     p->smem_asm[0] = sizeof(double) * ((size_t)dm.ntp * dm.ntp + (size_t)dm.ns1 * dm.ns1 + B200_MAX_FACTOR_ROWS * (B200_MAX_FACTOR_COLS + 1));
     p->smem_asm[1] = sizeof(double) * ((size_t)dm.nc * dm.nc + (size_t)dm.ns1 * dm.ntp + B200_MAX_FACTOR_ROWS * (B200_MAX_FACTOR_COLS + 1));
-    const size_t smem_cap = 227 * 1024 - 8 * 1024;  // leave room for the kernels' static shared arrays
+    size_t static_smem = 0;
+    {
+        cudaFuncAttributes fa;
+        CK(cudaFuncGetAttributes(&fa, top_solve_kernel)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
+        CK(cudaFuncGetAttributes(&fa, chain_sweep_kernel)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
+        CK(cudaFuncGetAttributes(&fa, chain_backsub_kernel)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
+        CK(cudaFuncGetAttributes(&fa, assemble_kernel)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
+    }
+    const size_t smem_cap = (227 * 1024 - static_smem - 1024) & ~(size_t)15;  // dynamic budget next to the kernels' static arrays
     if (std::max(p->smem_asm[0], p->smem_asm[1]) > smem_cap || sizeof(double) * (size_t)dm.ntp * dm.ld > smem_cap)
         return fail("time block does not fit in shared memory", B200_NOT_IMPLEMENTED);
     {
@@ -238,8 +246,11 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
         p->rmax = (int)std::min<long long>(rows_fit, rn_max);
         if (rows_fit < 32) return fail("panel does not fit in shared memory", B200_NOT_IMPLEMENTED);
         p->smem_sweep = sizeof(double) * (size_t)sweep_smem_doubles(dm.ntp, dm.ld, p->rmax);
-        const size_t stat = sizeof(double) * (size_t)(dm.ns + 2) * dm.ns1;
-        if (stat > p->smem_sweep) p->smem_sweep = stat;
+        const size_t stat = sizeof(double) * (size_t)static_lds(dm.ns) * (dm.ns1 + 1);
+        if (stat + 512 * sizeof(double) > p->smem_sweep) p->smem_sweep = stat + 512 * sizeof(double);
+        p->smem_sweep = (p->smem_sweep + 15) & ~(size_t)15;
+        dm.sm_doubles = (int)(p->smem_sweep / sizeof(double));
+        if (p->smem_sweep > smem_cap) return fail("solver working set does not fit in shared memory", B200_NOT_IMPLEMENTED);
     }
 #ifndef B200_USE_EMU
     CK(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(p->smem_asm[0], p->smem_asm[1])));
@@ -702,5 +713,13 @@ b200_status b200_debug_solve(b200_problem* p, double lambda, double* delta_time,
     if (dm.ns) CK(cudaMemcpy(delta_static, p->sb.dstat, sizeof(double) * dm.ns, cudaMemcpyDeviceToHost));
     return B200_OK;
 }
+
+#ifdef B200_PHASE_CLOCKS
+b200_status b200_debug_phase_clocks(unsigned long long* out, int32_t reset) {
+    CK(cudaMemcpyFromSymbol(out, g_phase_clk, sizeof(unsigned long long) * 16));
+    if (reset) { unsigned long long z[16] = {0}; CK(cudaMemcpyToSymbol(g_phase_clk, z, sizeof(z))); }
+    return B200_OK;
+}
+#endif
 
 }  // extern "C"

@@ -15,3 +15,22 @@
     extern __shared__ __align__(16) unsigned char b200_dyn_smem_[]; \
     type* name = reinterpret_cast<type*>(b200_dyn_smem_)
 #endif
+
+// asynchronous global->shared copies (LDGSTS on sm_100a); the emulator copies synchronously.
+#ifdef B200_USE_EMU
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) { std::memcpy(dst, src, 16); }
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) { std::memcpy(dst, src, 8); }
+__device__ __forceinline__ void cp_async_wait_all() {}
+__device__ __forceinline__ void prefetch_l2(const void*) {}
+#else
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif

@@ -15,6 +15,7 @@ struct Dims {
     int nt, ntp, nl, nc, ns, ns1;  // ntp = nt padded to even, nc = ntp - nl, ns1 = ns + 1
     int ld;                        // shared-memory leading dimension (>= ntp, == 2 mod 4)
     int hmax;                      // ns1 + nc
+    int sm_doubles;                // dynamic shared memory of the solver kernels, in doubles
 };
 
 // which (slot, instance) pairs touch keyframe k: instance k (variables AT_K, AT_STATIC, and the K1 x K cross block) and

@@ -26,6 +26,16 @@ namespace b200d {
 #define B200_NB 16        // Cholesky / TRSM block width
 #define B200_SOLVE_THREADS 256
 
+// optional per-phase cycle counters of the sweep (debug builds: -DB200_PHASE_CLOCKS), accumulated by thread 0 of block 0
+#ifdef B200_PHASE_CLOCKS
+__device__ unsigned long long g_phase_clk[16];
+#define PH_T0() unsigned long long ph_t_ = clock64()
+#define PH_ADD(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { unsigned long long n_ = clock64(); g_phase_clk[i] += n_ - ph_t_; ph_t_ = n_; } } while (0)
+#else
+#define PH_T0()
+#define PH_ADD(i)
+#endif
+
 // ------------------------------------------------------------------------------------------------- micro-kernel
 // out(m, n, sum_{k in [k0,k1)} A[m][k]*B[n][k]) for m<M, n<N.  A, B in shared memory, lda/ldb even, k0 even, (k1-k0) even.
 // Warp tile 32 x 16: lane -> (ty = lane>>2, tx = lane&3), thread rows m0+ty+8i, cols n0+tx+4j.
@@ -64,6 +74,7 @@ __device__ __forceinline__ void cta_gemm_nt(const double* __restrict__ A, int ld
 #pragma unroll
                 for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i].y, b[j].y, fma(a[i].x, b[j].x, acc[i][j]));
         }
+        __syncwarp();  // in-place use (C aliases A within the warp's own rows): all lanes have finished reading
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int m = m0 + ty + 8 * i;
@@ -76,88 +87,232 @@ __device__ __forceinline__ void cta_gemm_nt(const double* __restrict__ A, int ld
     }
 }
 
-// ------------------------------------------------------------------------------------------------- in-smem Cholesky
-// Lower Cholesky of the n x n matrix in shared memory (row-major, ld), blocked left-looking.  Returns (to all threads)
-// 0 on success or 1 + index of the first non-positive pivot.  Must be called by all threads of the CTA.
-__device__ int cta_chol_smem(double* Ms, int ld, int n) {
-    __shared__ int fail;
-    if (threadIdx.x == 0) fail = 0;
-    __syncthreads();
-    for (int j0 = 0; j0 < n; j0 += B200_NB) {
-        const int jb = (n - j0 < B200_NB) ? (n - j0) : B200_NB;
-        if (j0 > 0) {
-            double* Cb = Ms + (long long)j0 * ld + j0;
-            cta_gemm_nt(Ms + (long long)j0 * ld, ld, n - j0, Ms + (long long)j0 * ld, ld, jb, 0, j0, false,
-                        [&](int m, int c, double v) { Cb[(long long)m * ld + c] -= v; });
+// ------------------------------------------------------------------------------------------------- 16 x 16 building blocks
+// Diagonal block factorisation by ONE warp, entirely in registers: lane l owns row l of the jb x jb block (jb <= 16, padded
+// with identity), pivots / column entries travel by warp shuffle.  Writes L back in place, its transpose into Tdiag
+// (Tdiag[c*16+c2] = L[c2][c]) and the reciprocal diagonal into invd.  Returns 0 or 1 + index of a non-positive pivot.
+#define B200_WLD 18  // leading dimension of the 16 x 16 inverse diagonal block in shared memory (== 2 mod 4)
+__device__ __forceinline__ int warp_potrf16(double* Db, int ld, int jb, double* Tdiag, double* invd, double* Wd) {
+    const int l = threadIdx.x & 31;
+    double r[B200_NB];
+#pragma unroll
+    for (int c = 0; c < B200_NB; c++) r[c] = (l < jb && c < jb && c <= l) ? Db[(long long)l * ld + c] : ((l == c) ? 1.0 : 0.0);
+    int fail = 0;
+#pragma unroll
+    for (int c = 0; c < B200_NB; c++) {
+        double d = __shfl_sync(0xffffffffu, r[c], c);
+        if (!(d > 0.0) || !(d < 1.0e300)) { if (!fail) fail = 1 + c; d = 1.0; }
+        const double inv = rsqrt(d);
+        const double x = r[c] * inv;   // lane c: sqrt(d) ; lanes > c: L[l][c]
+        r[c] = x;
+        if (l == c) invd[c] = inv;
+#pragma unroll
+        for (int c2 = c + 1; c2 < B200_NB; c2++) {
+            const double lc2 = __shfl_sync(0xffffffffu, x, c2);
+            r[c2] = fma(-x, lc2, r[c2]);
         }
-        __syncthreads();
-        if (threadIdx.x < 32) {  // diagonal block: right-looking, lane = row
-            const int l = threadIdx.x;
-            double* Db = Ms + (long long)j0 * ld + j0;
-            for (int c = 0; c < jb; c++) {
-                if (l == c) {
-                    const double d = Db[c * ld + c];
-                    if (!(d > 0.0) || !(d < 1.0e300)) { if (fail == 0) fail = 1 + j0 + c; Db[c * ld + c] = 1.0; }
-                    else Db[c * ld + c] = sqrt(d);
-                }
-                __syncwarp();
-                if (l > c && l < jb) Db[l * ld + c] /= Db[c * ld + c];
-                __syncwarp();
-                if (l > c && l < jb) {
-                    const double lc = Db[l * ld + c];
-                    for (int c2 = c + 1; c2 <= l; c2++) Db[l * ld + c2] -= lc * Db[c2 * ld + c];
-                }
-                __syncwarp();
+    }
+    if (l < B200_NB) {
+#pragma unroll
+        for (int c = 0; c < B200_NB; c++) {
+            if (c <= l) {
+                if (l < jb && c < jb) Db[(long long)l * ld + c] = r[c];
+                Tdiag[c * B200_NB + l] = r[c];
             }
         }
-        __syncthreads();
-        // rows below the diagonal block: x <- x * Ljj^-T (thread per row)
-        for (int row = j0 + jb + threadIdx.x; row < n; row += blockDim.x) {
-            double* xr = Ms + (long long)row * ld + j0;
-            const double* Db = Ms + (long long)j0 * ld + j0;
-            double x[B200_NB];
-            for (int c = 0; c < jb; c++) {
-                double v = xr[c];
-                for (int l2 = 0; l2 < c; l2++) v -= x[l2] * Db[c * ld + l2];
-                x[c] = v / Db[c * ld + c];
-            }
-            for (int c = 0; c < jb; c++) xr[c] = x[c];
+    }
+    __syncwarp();
+    // W = L^-1: lane c solves L w = e_c by right-looking forward substitution (L entries broadcast from Tdiag)
+    if (l < B200_NB) {
+        double w[B200_NB];
+#pragma unroll
+        for (int i = 0; i < B200_NB; i++) w[i] = (i == l) ? 1.0 : 0.0;
+#pragma unroll
+        for (int i = 0; i < B200_NB; i++) {
+            w[i] *= invd[i];
+#pragma unroll
+            for (int i2 = i + 1; i2 < B200_NB; i2++) w[i2] = fma(-Tdiag[i * B200_NB + i2], w[i], w[i2]);
         }
-        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < B200_NB; i++) {
+            Wd[i * B200_WLD + l] = (i >= l) ? w[i] : 0.0;
+            // stash the strictly lower part of W in the (otherwise unused) upper triangle of the diagonal block of L
+            if (i > l && i < jb) Db[(long long)l * ld + i] = w[i];
+        }
     }
     return fail;
 }
 
-// rows (cr x n, shared, ld) <- rows * L^-T where L (n x n lower) is read block-row by block-row from global memory
-// (ldg) through the shared slab Ls (NB x ld).
-__device__ void cta_trsm_rows(double* Ps, int ld, int cr, int n, const double* __restrict__ Lg, int ldg, double* Ls) {
+// rows x 16 block X (shared, ld) <- X * W^T  (== X * Ljj^-T) on the tensor-less fp64 micro-kernel; jb even.
+__device__ __forceinline__ void cta_rows_times_WT(double* X, int ld, int nrows, int jb, const double* Wd) {
+    cta_gemm_nt(X, ld, nrows, Wd, B200_WLD, jb, 0, jb, false, [&](int m, int c, double v) { X[(long long)m * ld + c] = v; });
+}
+
+// x (one row, 16 entries at xr) <- x * Ljj^-T, right-looking in registers.  Tdiag / invd as written by warp_potrf16
+// (or rebuilt from a slab of L).  jb < 16: only the first jb entries exist.
+__device__ __forceinline__ void row_trisolve16(double* xr, int jb, const double* Tdiag, const double* invd) {
+    double x[B200_NB];
+    if (jb == B200_NB) {
+#pragma unroll
+        for (int c = 0; c < B200_NB; c += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(xr + c);
+            x[c] = v.x; x[c + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < B200_NB; c++) x[c] = (c < jb) ? xr[c] : 0.0;
+    }
+#pragma unroll
+    for (int c = 0; c < B200_NB; c++) {
+        if (c < jb) {
+            x[c] *= invd[c];
+#pragma unroll
+            for (int c2 = c + 1; c2 < B200_NB; c2++)
+                if (c2 < jb) x[c2] = fma(-x[c], Tdiag[c * B200_NB + c2], x[c2]);
+        }
+    }
+    if (jb == B200_NB) {
+#pragma unroll
+        for (int c = 0; c < B200_NB; c += 2) *reinterpret_cast<double2*>(xr + c) = make_double2(x[c], x[c + 1]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < B200_NB; c++) if (c < jb) xr[c] = x[c];
+    }
+}
+
+// small static shared scratch shared by the Cholesky and the triangular solve (one instance per kernel)
+__device__ __forceinline__ void solve_scratch(double*& Tdiag, double*& Wd, double*& invd) {
+    __shared__ __align__(16) double s_Tdiag[B200_NB * B200_NB];
+    __shared__ __align__(16) double s_Wd[B200_NB * B200_WLD];
+    __shared__ double s_invd[B200_NB];
+    Tdiag = s_Tdiag; Wd = s_Wd; invd = s_invd;
+}
+
+// ------------------------------------------------------------------------------------------------- in-smem Cholesky
+// Lower Cholesky of the leading n x n block of the (nrows x n) panel in shared memory (row-major, ld), blocked
+// left-looking; rows [n, nrows) are carried along (they end up multiplied by L^-T, i.e. forward-substituted).
+// Returns (to all threads) 0 or 1 + index of the first non-positive pivot.  Must be called by all threads of the CTA.
+__device__ int cta_chol_smem(double* Ms, int ld, int n, int nrows) {
+    __shared__ int fail;
+    double *Tdiag, *Wd, *invd;
+    solve_scratch(Tdiag, Wd, invd);
+    if (threadIdx.x == 0) fail = 0;
+    __syncthreads();
+    PH_T0();
     for (int j0 = 0; j0 < n; j0 += B200_NB) {
         const int jb = (n - j0 < B200_NB) ? (n - j0) : B200_NB;
-        const int w = j0 + jb;
+        if (j0 > 0) {
+            double* Cb = Ms + (long long)j0 * ld + j0;
+            cta_gemm_nt(Ms + (long long)j0 * ld, ld, nrows - j0, Ms + (long long)j0 * ld, ld, jb, 0, j0, false,
+                        [&](int m, int c, double v) { Cb[(long long)m * ld + c] -= v; });
+            __syncthreads();
+        }
+        PH_ADD(8);
+        if (threadIdx.x < 32) {
+            const int f = warp_potrf16(Ms + (long long)j0 * ld + j0, ld, jb, Tdiag, invd, Wd);
+            if (f && threadIdx.x == 0 && fail == 0) fail = j0 + f;
+        }
+        PH_ADD(9);
         __syncthreads();
-        for (int i = threadIdx.x; i < jb * w; i += blockDim.x) {
-            const int r = i / w, c = i % w;
-            Ls[r * ld + c] = Lg[(long long)(j0 + r) * ldg + c];
+        if ((jb & 1) == 0) {
+            if (nrows > j0 + jb) cta_rows_times_WT(Ms + (long long)(j0 + jb) * ld + j0, ld, nrows - j0 - jb, jb, Wd);
+        } else {
+            for (int row = j0 + jb + threadIdx.x; row < nrows; row += blockDim.x)
+                row_trisolve16(Ms + (long long)row * ld + j0, jb, Tdiag, invd);
         }
         __syncthreads();
+        PH_ADD(10);
+    }
+    return fail;
+}
+
+// copy rows [r0, r0+nr) x cols [0, w) (w even) of a global row-major matrix (ldg even) into shared rows (ld even), async
+__device__ __forceinline__ void cp_rows_async(double* dst, int ld, const double* __restrict__ src, int ldg, int nr, int w) {
+    const int w2 = (w + 1) >> 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int r = warp; r < nr; r += nwarps)
+        for (int c2 = lane; c2 < w2; c2 += 32) cp_async16(dst + (long long)r * ld + 2 * c2, src + (long long)r * ldg + 2 * c2);
+}
+
+// rows (cr x n, shared, ld) <- rows * L^-T where L (n x n lower, upper part zero) is streamed block-row by block-row from
+// global memory (ldg) through two shared slabs (NB x ld each), the next slab being fetched (cp.async) while the current
+// block column is updated and solved.
+__device__ void cta_trsm_rows(double* Ps, int ld, int cr, int n, const double* __restrict__ Lg, int ldg, double* slab0, double* slab1) {
+    double *Tdiag, *Wd, *invd;
+    solve_scratch(Tdiag, Wd, invd);
+    {
+        const int jb0 = (n < B200_NB) ? n : B200_NB;
+        cp_rows_async(slab0, ld, Lg, ldg, jb0, jb0 + (jb0 & 1));
+    }
+    int blk = 0;
+    PH_T0();
+    for (int j0 = 0; j0 < n; j0 += B200_NB, blk++) {
+        const int jb = (n - j0 < B200_NB) ? (n - j0) : B200_NB;
+        double* Ls = (blk & 1) ? slab1 : slab0;
+        double* Ln = (blk & 1) ? slab0 : slab1;
+        cp_async_wait_all();
+        __syncthreads();
+        PH_ADD(11);
+        if (j0 + jb < n) {
+            const int j1 = j0 + jb;
+            const int jb1 = (n - j1 < B200_NB) ? (n - j1) : B200_NB;
+            const int w1 = j1 + jb1;
+            cp_rows_async(Ln, ld, Lg + (long long)j1 * ldg, ldg, jb1, w1 + (w1 & 1));
+        }
+        if (threadIdx.x < B200_NB * B200_NB) {
+            const int c = threadIdx.x / B200_NB, c2 = threadIdx.x % B200_NB;
+            if (c2 >= c && c2 < jb) Tdiag[c * B200_NB + c2] = Ls[(long long)c2 * ld + j0 + c];
+            if (c2 == c && c < jb) invd[c] = 1.0 / Ls[(long long)c * ld + j0 + c];
+            // W (inverse of the diagonal block): strictly lower part stashed above the diagonal of L, diagonal = 1/L_cc
+            double wv = 0.0;
+            if (c < jb && c2 < jb) {
+                if (c2 == c) wv = 1.0 / Ls[(long long)c * ld + j0 + c];
+                else if (c2 < c) wv = Ls[(long long)c2 * ld + j0 + c];
+            } else if (c == c2) wv = 1.0;
+            Wd[c * B200_WLD + c2] = wv;
+        }
         if (j0 > 0) {
             double* Cb = Ps + j0;
             cta_gemm_nt(Ps, ld, cr, Ls, ld, jb, 0, j0, false, [&](int m, int c, double v) { Cb[(long long)m * ld + c] -= v; });
-            __syncthreads();
         }
-        for (int row = threadIdx.x; row < cr; row += blockDim.x) {
-            double* xr = Ps + (long long)row * ld + j0;
-            const double* Db = Ls + j0;
-            double x[B200_NB];
-            for (int c = 0; c < jb; c++) {
-                double v = xr[c];
-                for (int l2 = 0; l2 < c; l2++) v -= x[l2] * Db[c * ld + l2];
-                x[c] = v / Db[c * ld + c];
-            }
-            for (int c = 0; c < jb; c++) xr[c] = x[c];
-        }
+        __syncthreads();
+        PH_ADD(12);
+        if ((jb & 1) == 0) cta_rows_times_WT(Ps + j0, ld, cr, jb, Wd);
+        else for (int row = threadIdx.x; row < cr; row += blockDim.x) row_trisolve16(Ps + (long long)row * ld + j0, jb, Tdiag, invd);
+        PH_ADD(13);
     }
     __syncthreads();
+}
+
+// x <- L^-T x for the n x n lower factor in shared memory (ld); x in shared memory (tv).  Blocked: the 16 x 16 diagonal
+// solves run in one warp (registers + shuffles), the updates of the remaining entries on all threads.
+__device__ void cta_solve_LT(const double* Ms, int ld, int n, double* tv) {
+    const int nblk = (n + B200_NB - 1) / B200_NB;
+    for (int b = nblk - 1; b >= 0; b--) {
+        const int j0 = b * B200_NB;
+        const int jb = (n - j0 < B200_NB) ? (n - j0) : B200_NB;
+        if (threadIdx.x < 32) {
+            const int l = threadIdx.x;
+            double t = (l < jb) ? tv[j0 + l] : 0.0;
+            const double dinv = (l < jb) ? 1.0 / Ms[(long long)(j0 + l) * ld + j0 + l] : 0.0;
+#pragma unroll
+            for (int m = B200_NB - 1; m >= 0; m--) {
+                if (m < jb) {
+                    const double xm = __shfl_sync(0xffffffffu, t * dinv, m);
+                    if (l == m) t = xm;
+                    else if (l < m) t = fma(-Ms[(long long)(j0 + m) * ld + j0 + l], xm, t);
+                }
+            }
+            if (l < jb) tv[j0 + l] = t;
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < j0; c += blockDim.x) {
+            double t = tv[c];
+            for (int r = 0; r < jb; r++) t = fma(-Ms[(long long)(j0 + r) * ld + c], tv[j0 + r], t);
+            tv[c] = t;
+        }
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------- the sweep
@@ -183,9 +338,10 @@ struct SweepArgs {
 
 // shared-memory carve-up (doubles): phase A uses [0, ntp*ld) ; phase B: Ps [rmax*ld] | Ls [NB*ld] | Bs [32*ld]
 __host__ __device__ inline long long sweep_smem_doubles(int ntp, int ld, int rmax) {
-    long long a = (long long)ntp * ld, b = (long long)(rmax + B200_NB + 32) * ld;
+    long long a = (long long)ntp * ld + 256 + 256 + 1024 + 512, b = (long long)(rmax + B200_NB + 32) * ld;
     return a > b ? a : b;
 }
+__host__ __device__ inline int static_lds(int ns) { int lds = ns + (ns & 1); while ((lds & 3) != 2) lds += 2; return lds; }
 
 __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
     const int ntp = dm.ntp, nl = dm.nl, nc = dm.nc, ns1 = dm.ns1, ld = dm.ld, hmax = dm.hmax;
@@ -201,28 +357,50 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
         double* Fout = a.F + (long long)((i + 1) & 1) * Fsz;
         double* Lg = a.Lst + st * ntp * ntp;
         double* Pg = a.Pst + st * (long long)(nc + hmax) * ntp;
-        // ---------------- phase A: pivot block
+        const double* Og = a.Osrc + src * nc * nc;
+        const double* Ag = a.Asrc + src * ns1 * ntp;
+        // ---------------- phase A: pivot block  Dacc = D + lambda I - fill
+        PH_T0();
         {
             const double* Dg = a.Dsrc + src * ntp * ntp;
-            for (int e = threadIdx.x; e < ntp * ntp; e += blockDim.x) {
-                const int r = e / ntp, c = e % ntp;
-                double v = Dg[e];
-                if (r == c) v += a.lambda;
-                if (i > 0 && r >= nl && c >= nl) v -= Fin[(long long)(r - nl) * nc + (c - nl)];
-                sm[r * ld + c] = v;
+            cp_rows_async(sm, ld, Dg, ntp, ntp, ntp);
+            if (i + 1 < a.n) {  // pull the next keyframe's blocks towards L2 while this one is factorised
+                const double* Dn = a.Dsrc + (src + 1) * ntp * ntp;
+                for (int e = threadIdx.x * 16; e < ntp * ntp; e += blockDim.x * 16) prefetch_l2(Dn + e);
+            }
+            cp_async_wait_all();
+            __syncthreads();
+            for (int r = threadIdx.x; r < ntp; r += blockDim.x) sm[r * ld + r] += a.lambda;
+            if (i > 0) {
+                const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+                for (int r = warp; r < nc; r += nwarps) {
+                    const double* fr = Fin + (long long)r * nc;
+                    double* dr = sm + (nl + r) * ld + nl;
+#pragma unroll 4
+                    for (int c = lane; c < nc; c += 32) dr[c] -= fr[c];
+                }
             }
             __syncthreads();
-            const int fail = cta_chol_smem(sm, ld, ntp);
+            PH_ADD(0);
+            const int fail = cta_chol_smem(sm, ld, ntp, ntp);
+            PH_ADD(1);
             if (fail) {
                 if (threadIdx.x == 0) atomicCAS(a.status, 0, (int)(st + 1));
                 return;
             }
-            for (int e = threadIdx.x; e < ntp * ntp; e += blockDim.x) {
-                const int r = e / ntp, c = e % ntp;
-                Lg[e] = (c <= r) ? sm[r * ld + c] : 0.0;
+            {
+                const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+                for (int r = warp; r < ntp; r += nwarps)
+                    for (int c = 2 * lane; c < ntp; c += 64) {
+                        const double2 v = *reinterpret_cast<const double2*>(sm + r * ld + c);
+                        const bool diag_blk = (c / B200_NB) == (r / B200_NB);   // (c even: c and c+1 share the block)
+                        *reinterpret_cast<double2*>(Lg + (long long)r * ntp + c) =
+                            make_double2((c <= r || diag_blk) ? v.x : 0.0, (c + 1 <= r || diag_blk) ? v.y : 0.0);
+                    }
             }
             __threadfence_block();
             __syncthreads();
+            PH_ADD(2);
         }
         // ---------------- phase B: panel rows [X (nc, if has_x) ; arrow (h)]
         double* Ps = sm;
@@ -244,32 +422,60 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
             const int r0 = ch * csz;
             const int cr = (Rn - r0 < csz) ? (Rn - r0) : csz;
             __syncthreads();
-            // load rows
-            const double* Og = a.Osrc + src * nc * nc;
-            const double* Ag = a.Asrc + src * ns1 * ntp;
-            for (int e = threadIdx.x; e < cr * ntp; e += blockDim.x) {
-                const int lr = e / ntp, c = e % ntp;
-                const int pr = r0 + lr;
-                double v = 0.0;
-                if (pr < xo) {
-                    if (c >= nl) v = Og[(long long)pr * nc + (c - nl)];
-                } else {
-                    const int ar = pr - xo;
-                    if (ar < ns1) v = Ag[(long long)ar * ntp + c];
-                    else if (i == 0 && a.Oleft && c >= nl) v = a.Oleft[(long long)(c - nl) * nc + (ar - ns1)];
-                    if (i > 0 && c >= nl) v -= Fin[(long long)(nc + ar) * nc + (c - nl)];
+            // load rows (one warp per row): sources through cp.async, then the fill correction in shared memory
+            {
+                const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+                for (int lr = warp; lr < cr; lr += nwarps) {
+                    const int pr = r0 + lr;
+                    double* dst = Ps + lr * ld;
+                    if (pr < xo) {
+                        const double* og = Og + (long long)pr * nc - nl;
+                        for (int c = lane; c < ntp; c += 32) {
+                            if (c >= nl) cp_async8(dst + c, og + c);
+                            else dst[c] = 0.0;
+                        }
+                    } else {
+                        const int ar = pr - xo;
+                        if (ar < ns1) {
+                            const double* ag = Ag + (long long)ar * ntp;
+                            for (int c = 2 * lane; c < ntp; c += 64) cp_async16(dst + c, ag + c);
+                        } else if (i == 0 && a.Oleft) {
+                            const double* ol = a.Oleft + (ar - ns1);
+                            for (int c = lane; c < ntp; c += 32) dst[c] = (c >= nl) ? ol[(long long)(c - nl) * nc] : 0.0;
+                        } else {
+                            for (int c = lane; c < ntp; c += 32) dst[c] = 0.0;
+                        }
+                    }
                 }
-                Ps[lr * ld + c] = v;
+                cp_async_wait_all();
+                __syncthreads();
+                if (i > 0) {
+                    // arrow rows of this chunk: subtract Y_prev X_prev^T (chain columns)
+                    for (int lr = warp; lr < cr; lr += nwarps) {
+                        const int pr = r0 + lr;
+                        if (pr < xo) continue;
+                        const double* fr = Fin + (long long)(nc + pr - xo) * nc;
+                        double* dr = Ps + lr * ld + nl;
+#pragma unroll 4
+                        for (int c = lane; c < nc; c += 32) dr[c] -= fr[c];
+                    }
+                }
             }
             // (cta_trsm_rows starts with a barrier)
-            cta_trsm_rows(Ps, ld, cr, ntp, Lg, ntp, Ls);
+            __syncthreads();
+            PH_ADD(3);
+            cta_trsm_rows(Ps, ld, cr, ntp, Lg, ntp, Ls, Bs);
+            PH_ADD(4);
             // store
-            for (int e = threadIdx.x; e < cr * ntp; e += blockDim.x) {
-                const int lr = e / ntp, c = e % ntp;
-                const int pr = r0 + lr;
-                const int sr = has_x ? pr : nc + pr;
-                Pg[(long long)sr * ntp + c] = Ps[lr * ld + c];
+            {
+                const int sro_ = has_x ? 0 : nc;
+                const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+                for (int lr = warp; lr < cr; lr += nwarps)
+                    for (int c = 2 * lane; c < ntp; c += 64)
+                        *reinterpret_cast<double2*>(Pg + (long long)(sro_ + r0 + lr) * ntp + c) = *reinterpret_cast<const double2*>(Ps + lr * ld + c);
             }
+            __syncthreads();
+            PH_ADD(5);
             // rank update, diagonal chunk pair
             auto emit = [&](int sr1, int sr2, double v) {
                 // sr1 >= sr2 (storage rows)
@@ -279,7 +485,7 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                 } else if (sr2 < nc) {
                     Fout[(long long)sr1 * nc + sr2] = v;
                 } else {
-                    a.Sacc[(long long)(sr1 - nc) * hmax + (sr2 - nc)] -= v;
+                    atomicAdd(a.Sacc + (long long)(sr1 - nc) * hmax + (sr2 - nc), -v);  // one contributor per entry and step: deterministic
                 }
             };
             const int sro = has_x ? 0 : nc;  // storage row of present row 0
@@ -290,10 +496,8 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
             for (int p0 = 0; p0 < r0; p0 += 32) {
                 const int pb = (r0 - p0 < 32) ? (r0 - p0) : 32;
                 __syncthreads();
-                for (int e = threadIdx.x; e < pb * ntp; e += blockDim.x) {
-                    const int lr = e / ntp, c = e % ntp;
-                    Bs[lr * ld + c] = Pg[(long long)(sro + p0 + lr) * ntp + c];
-                }
+                cp_rows_async(Bs, ld, Pg + (long long)(sro + p0) * ntp, ntp, pb, ntp);
+                cp_async_wait_all();
                 __syncthreads();
                 cta_gemm_nt(Ps, ld, cr, Bs, ld, pb, 0, ntp, false,
                             [&](int m, int n2, double v) { emit(sro + r0 + m, sro + p0 + n2, v); });
@@ -301,6 +505,7 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
         }
         __threadfence_block();
         __syncthreads();
+        PH_ADD(6);
     }
 }
 
@@ -309,9 +514,10 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
 __device__ void cta_backsub(const Dims& dm, const SweepArgs& a, const double* coefA, long long right_st, double* delta, double* sm) {
     const int ntp = dm.ntp, nl = dm.nl, nc = dm.nc, ld = dm.ld, hmax = dm.hmax;
     const int h = a.h;
-    double* Ms = sm;                 // L in shared memory
-    __shared__ double tvec[256];     // ntp <= 256
-    __shared__ double cx[256];
+    double* Ms = sm;                 // L in shared memory, then scratch vectors (ntp, nc <= 256)
+    double* tvec = sm + (long long)ntp * ld;
+    double* cx = tvec + 256;
+    double* tpart = cx + 256;        // blockDim.x doubles
     for (int i = a.n - 1; i >= 0; i--) {
         const long long src = a.src0 + i;
         const long long st = a.st_idx ? a.st_idx[i] : src;
@@ -322,30 +528,36 @@ __device__ void cta_backsub(const Dims& dm, const SweepArgs& a, const double* co
         if (i + 1 < a.n) nxt = a.st_idx ? a.st_idx[i + 1] : src + 1;
         else if (a.has_right) nxt = right_st;
         __syncthreads();
+        cp_rows_async(Ms, ld, Lg, ntp, ntp, ntp);
         if (has_x) for (int j = threadIdx.x; j < nc; j += blockDim.x) cx[j] = delta[nxt * ntp + nl + j];
-        for (int e = threadIdx.x; e < ntp * ntp; e += blockDim.x) {
-            const int r = e / ntp, c = e % ntp;
-            if (c <= r) Ms[r * ld + c] = Lg[e];
-        }
         __syncthreads();
-        for (int c = threadIdx.x; c < ntp; c += blockDim.x) {
-            double t = 0.0;
-            if (has_x) for (int r = 0; r < nc; r++) t -= Pg[(long long)r * ntp + c] * cx[r];
-            for (int r = 0; r < h; r++) t -= Pg[(long long)(nc + r) * ntp + c] * coefA[r];
-            tvec[c] = t;
-        }
-        __syncthreads();
-        if (threadIdx.x < 32) {  // L^T x = t, right-looking over rows of L (contiguous in shared memory)
-            const int lane = threadIdx.x;
-            for (int r = ntp - 1; r >= 0; r--) {
-                const double xr = tvec[r] / Ms[r * ld + r];
-                __syncwarp();
-                if (lane == 0) tvec[r] = xr;
-                for (int c = lane; c < r; c += 32) tvec[c] -= Ms[r * ld + c] * xr;
-                __syncwarp();
+        // t[c] = - sum_r P[r][c] * coef[r]; thread groups of 128 split the rows, column passes of 128
+        {
+            const int grp = threadIdx.x >> 7, ngrp = blockDim.x >> 7;
+            for (int cb = 0; cb < ntp; cb += 128) {
+                const int c = cb + (threadIdx.x & 127);
+                double t = 0.0;
+                if (c < ntp) {
+                    if (has_x) {
+#pragma unroll 4
+                        for (int r = grp; r < nc; r += ngrp) t = fma(-Pg[(long long)r * ntp + c], cx[r], t);
+                    }
+#pragma unroll 4
+                    for (int r = grp; r < h; r += ngrp) t = fma(-Pg[(long long)(nc + r) * ntp + c], coefA[r], t);
+                }
+                tpart[threadIdx.x] = t;
+                __syncthreads();
+                if (grp == 0 && c < ntp) {
+                    double acc = 0.0;
+                    for (int q = 0; q < ngrp; q++) acc += tpart[q * 128 + (threadIdx.x & 127)];
+                    tvec[c] = acc;
+                }
+                __syncthreads();
             }
         }
+        cp_async_wait_all();
         __syncthreads();
+        cta_solve_LT(Ms, ld, ntp, tvec);
         for (int c = threadIdx.x; c < ntp; c += blockDim.x) delta[st * ntp + c] = tvec[c];
         __threadfence_block();
     }
@@ -470,41 +682,21 @@ __global__ void __launch_bounds__(B200_SOLVE_THREADS) top_solve_kernel(Dims dm, 
     cta_sweep(dm, a, sm);
     __syncthreads();
     if (*sb.status != 0) return;
-    // static system: (Sacc[0:ns,0:ns] + lambda I) ds = Sacc[ns][0:ns]
-    __shared__ double coefA[512];   // hmax <= 512
-    const int lds = ns + 2;
+    // static system: (Sacc[0:ns,0:ns] + lambda I) ds = Sacc[ns][0:ns]; the rhs row rides along as a panel row
+    double* coefA = sm + dm.sm_doubles - 512;   // hmax <= 512, lives at the end of the dynamic region
+    int lds = ns + (ns & 1); while ((lds & 3) != 2) lds += 2;
     double* Ss = sm;
     for (int e = threadIdx.x; e < ns1 * ns1; e += blockDim.x) {
         const int r = e / ns1, c = e % ns1;
-        if (c <= r) Ss[r * lds + c] = a.Sacc[(long long)r * hmax + c] + ((r == c && r < ns) ? lambda : 0.0);
+        if (c <= r && c < ns) Ss[r * lds + c] = a.Sacc[(long long)r * hmax + c] + ((r == c) ? lambda : 0.0);
     }
     __syncthreads();
     if (ns > 0) {
-        if (threadIdx.x == 0) {
-            int fail = 0;
-            for (int j = 0; j < ns && !fail; j++) {
-                double d = Ss[j * lds + j];
-                for (int l = 0; l < j; l++) d -= Ss[j * lds + l] * Ss[j * lds + l];
-                if (!(d > 0.0) || !(d < 1.0e300)) { fail = 1; break; }
-                const double ljj = sqrt(d);
-                Ss[j * lds + j] = ljj;
-                for (int i = j + 1; i < ns1; i++) {   // includes the rhs row (i == ns): forward substitution
-                    double v = Ss[i * lds + j];
-                    for (int l = 0; l < j; l++) v -= Ss[i * lds + l] * Ss[j * lds + l];
-                    Ss[i * lds + j] = v / ljj;
-                }
-            }
-            if (fail) atomicCAS(sb.status, 0, 1 << 30);
-            else {
-                for (int i = ns - 1; i >= 0; i--) {
-                    double v = Ss[ns * lds + i];
-                    for (int l = i + 1; l < ns; l++) v -= Ss[l * lds + i] * coefA[l];
-                    coefA[i] = v / Ss[i * lds + i];
-                }
-            }
-        }
+        const int fail = cta_chol_smem(Ss, lds, ns, ns1);
+        if (fail) { if (threadIdx.x == 0) atomicCAS(sb.status, 0, 1 << 30); return; }
+        for (int i = threadIdx.x; i < ns; i += blockDim.x) coefA[i] = Ss[ns * lds + i];
         __syncthreads();
-        if (*sb.status != 0) return;
+        cta_solve_LT(Ss, lds, ns, coefA);
     }
     if (threadIdx.x == 0) coefA[ns] = -1.0;
     __syncthreads();
@@ -527,7 +719,7 @@ __global__ void __launch_bounds__(B200_SOLVE_THREADS) chain_backsub_kernel(Dims 
     a.has_right = (c < P - 1);
     a.h = ns1 + ((c > 0) ? nc : 0);
     a.Lst = sb.Lst; a.Pst = sb.Pst;
-    __shared__ double coefA[512];
+    double* coefA = sm + dm.sm_doubles - 512;
     for (int i = threadIdx.x; i < ns; i += blockDim.x) coefA[i] = sb.dstat[i];
     if (threadIdx.x == 0) coefA[ns] = -1.0;
     if (c > 0) for (int j = threadIdx.x; j < nc; j += blockDim.x) coefA[ns1 + j] = sb.delta[(long long)(kb - 1) * ntp + nl + j];

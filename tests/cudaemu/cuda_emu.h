@@ -25,6 +25,7 @@
 #define __restrict__ __restrict
 #define __launch_bounds__(...)
 #define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
 
 struct emu_uint3 { unsigned x, y, z; };
 struct dim3 {
@@ -68,6 +69,8 @@ inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b)
     return cudaSuccess;
 }
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+struct cudaFuncAttributes { size_t sharedSizeBytes = 0; int numRegs = 0; };
+template <class F> inline cudaError_t cudaFuncGetAttributes(cudaFuncAttributes* a, F) { *a = cudaFuncAttributes(); return cudaSuccess; }
 
 namespace emu {
 void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body);
