@@ -1,0 +1,268 @@
+#!/usr/bin/env python
+"""bench.py -- LM iterations/sec of the 7-IMU lower-body factor-graph solve (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # B200 path (this repo)
+  python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the reference's algorithm on the host cores
+
+A "step" is one LevenbergMarquardtOptimizer::iterate() (one linearization + the lambda trials it needs) of the
+synthetic 10-minute 100 Hz 7-IMU trial (K = 6000 keyframes, 756 058 unknowns; BASELINE.json configs[3], the trial the
+north_star target is quoted on) starting from the reference's initial values (identity poses, zero velocity/bias,
+statics at their prior means).  `value` = iterations/s with everything resident in HBM; `e2e` = the same through the
+C ABI with HOST buffers (values uploaded and downloaded every step).  Time axis sharded over N GPUs for N > 1.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {  # name -> (seconds of 100 Hz data, BASELINE.json config)
+    "gait_10min_100hz_7imu": (600.0, "configs[3]"),
+    "gait_60s_100hz_7imu": (60.0, "configs[2]"),
+    "gait_30s_100hz_7imu": (30.0, "configs[1] stand-in"),
+}
+# algorithmic bytes per keyframe (dense-block model): the sweep kernel reads the compact normal
+# equations H (4167 doubles) and writes the block factor F (28539 doubles)
+SWEEP_BYTES_PER_KEYFRAME = (4167 + 28539) * 8
+TRIAL_BYTES_PER_KEYFRAME = 505472
+LINEARIZE_BYTES_PER_KEYFRAME = 45488
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, device=0):
+        super().__init__(daemon=True)
+        self.device, self.samples, self.stop_flag = device, [], False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        mhz = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(mhz)}
+
+
+def build_problem_inputs(workload, preint, seed=0, n_keyframes=None):
+    from bioslam_b200 import graphs, synth
+    dur = WORKLOADS[workload][0]
+    if n_keyframes is not None:
+        dur = min(dur, n_keyframes * 0.1)
+    trial = synth.make_trial(seed=seed, duration_s=dur)
+    g, tv, sv = graphs.lower_body_graph(trial, preint=preint)
+    return trial, g, tv, sv
+
+
+def run_reference(args):
+    """CPU arm: the reference's algorithm (oracle restatement of GTSAM LM + bioslam factors; real GTSAM cannot be built
+    here) with all host threads, on a bounded window of the same workload; value scaled to the full trial (the cost of an
+    LM iteration is linear in the number of keyframes for this structured solver)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from bioslam_b200 import abi
+    from oracle import pyoracle as po
+    po.build()
+    threads = po.lib().orc_max_threads()
+    K_full = int(round(WORKLOADS[args.workload][0] * 10))
+    K_s = min(K_full, args.ref_keyframes)
+    _, g, tv, sv = build_problem_inputs(args.workload, lambda a, w, dt, n, bh: po.preintegrate(a, w, dt, n, bh), n_keyframes=K_s)
+    o = po.OracleProblem(g, threads=threads)
+    o.set_values(tv, sv)
+    lm = abi.LmParams.lower_body()
+    o.lm_begin(lm)
+    trials = 0
+    for _ in range(args.warmup):
+        o.lm_iterate()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        trials += o.lm_iterate().inner_trials
+    dt = time.perf_counter() - t0
+    value = args.steps / dt * (g.K / K_full)
+    line = {
+        "impl": "reference", "metric": "lm_iterations_per_sec", "value": value, "unit": "iter/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3 * (K_full / g.K), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "baseline_config": WORKLOADS[args.workload][1], "keyframes": K_full, "unknowns": 126 * K_full + 58},
+        "cpu_baseline": {"value": value, "unit": "iter/s", "cores": threads, "kind": "port",
+                         "sample": f"first {g.K} of {K_full} keyframes, {args.steps} LM iterations ({trials} lambda trials) after {args.warmup} warm-up; "
+                                   f"value scaled by {g.K}/{K_full} (per-iteration cost is linear in keyframes)"},
+        "e2e": {"value": value, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(args, K_full):
+    """bounded CPU sample for the default line (rank 0, N=1)"""
+    from bioslam_b200 import abi
+    from oracle import pyoracle as po
+    po.build()
+    threads = po.lib().orc_max_threads()
+    K_s = min(K_full, args.cpu_keyframes)
+    _, g, tv, sv = build_problem_inputs(args.workload, lambda a, w, dt, n, bh: po.preintegrate(a, w, dt, n, bh), n_keyframes=K_s)
+    o = po.OracleProblem(g, threads=threads)
+    o.set_values(tv, sv)
+    o.lm_begin(abi.LmParams.lower_body())
+    o.lm_iterate()
+    n, trials = 3, 0
+    t0 = time.perf_counter()
+    for _ in range(n):
+        trials += o.lm_iterate().inner_trials
+    dt = time.perf_counter() - t0
+    return {"value": n / dt * (g.K / K_full), "unit": "iter/s", "cores": threads, "kind": "port",
+            "sample": f"first {g.K} of {K_full} keyframes, {n} LM iterations ({trials} lambda trials) after 1 warm-up, scaled by {g.K}/{K_full}"}
+
+
+def run_b200(args):
+    import torch
+    from bioslam_b200 import abi, lib
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: bioslam_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib.load()
+    preint = lambda a, w, dt, n, bh: lib.preintegrate(a, w, dt, n, bh, device=local)
+    _, g, tv0, sv0 = build_problem_inputs(args.workload, preint)
+    K = g.K
+    p = lib.Problem(g, device=local, chunks=args.chunks)
+    if world > 1:
+        from bioslam_b200 import sharding
+        sharding.attach(p, dist, local)
+    lm = abi.LmParams.lower_body()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm
+    p.set_values(tv0, sv0)
+    p.lm_begin(lm)
+    p.phase_ms(reset=True)
+    for _ in range(args.warmup):
+        p.lm_iterate()
+    p.phase_ms(reset=True)
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    l0 = p.launch_count()
+    p.timer_begin()
+    trials = 0
+    for _ in range(args.steps):
+        st = p.lm_iterate(); trials += st.inner_trials
+    ms = p.timer_end()
+    barrier()
+    launches = p.launch_count() - l0
+    clocks = sampler.summary()
+    ph = p.phase_ms()
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    value = args.steps / (ms * 1e-3)
+    err_after = st.error
+
+    # ---------------- end-to-end arm: host buffers in, host buffers out, every step
+    p.set_values(tv0, sv0)
+    p.lm_begin(lm)
+    tv, sv = tv0, sv0
+    for _ in range(args.warmup):
+        p.set_values(tv, sv); p.lm_iterate(); tv, sv = p.get_values()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        p.set_values(tv, sv); st2 = p.lm_iterate(); tv, sv = p.get_values()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
+    h2d = tv.nbytes + sv.nbytes
+    d2h = tv.nbytes + sv.nbytes + 8 * 10
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peaks()
+    P = p.chunks
+    sweep_ms = ph[3] / max(ph[4], 1)
+    units = K - (P - 1)
+    if ph[4] > 0:
+        achieved = units * SWEEP_BYTES_PER_KEYFRAME / (sweep_ms * 1e-3) / 1e9
+        kern = "chain_sweep_kernel"
+    else:  # single chunk: everything happens in top_solve_kernel
+        sweep_ms = ph[5] / max(ph[6], 1)
+        achieved = K * SWEEP_BYTES_PER_KEYFRAME / (sweep_ms * 1e-3) / 1e9
+        kern = "top_solve_kernel"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "sweep_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    line = {
+        "metric": "lm_iterations_per_sec", "value": value, "unit": "iter/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "baseline_config": WORKLOADS[args.workload][1], "keyframes": K, "unknowns": 126 * K + 58,
+                   "chunks": P, "cache": "working set (>2 GB of Hessian/factor blocks at K=6000) exceeds the 126 MB L2; no flush needed",
+                   "init": "reference initial values (identity poses, zero vel/bias, statics at prior means)"},
+        "lm_trials_per_sec": trials / (ms * 1e-3), "lambda_trials": trials, "error_after": err_after,
+        "phase_ms_per_step": {"linearize+assemble": ph[0] / args.steps, "solve": ph[1] / args.steps, "model+retract+error": ph[2] / args.steps},
+        "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "launch_ms": sweep_ms,
+                     "note": "algorithmic bytes = (H 4167 + F 28539 doubles) per keyframe x keyframes per launch; the kernel is fp64-latency bound, not HBM bound"},
+        "e2e": {"value": args.steps / e2e_s, "unit": "iter/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, K)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="gait_10min_100hz_7imu", choices=sorted(WORKLOADS))
+    ap.add_argument("--chunks", type=int, default=None, help="solver partition (default: library heuristic)")
+    ap.add_argument("--ref-keyframes", type=int, default=600, help="window of the trial the CPU reference arm runs per step")
+    ap.add_argument("--cpu-keyframes", type=int, default=600, help="window for the cpu_baseline sample of the default line")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -80,8 +80,9 @@ struct b200_problem {
     int iterations = 0, total_trials = 0;
     bool have_lin = false;
     long long launches = 0;
-    cudaEvent_t ev[8] = {};
-    double phase_ms[4] = {0, 0, 0, 0};
+    cudaEvent_t ev[16] = {};
+    double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // lin, solve, retract+error, sweep ms, sweep launches, top ms, top launches, backsub ms
+    std::vector<float> pending;
     bool time_phases = false;
     // sharding (time axis): this rank owns chunks [c_lo, c_hi) == keyframes [k_lo, k_hi)
     int world = 1, rank = 0, c_lo = 0, c_hi = 1, k_lo = 0, k_hi = 0;
@@ -364,17 +365,22 @@ static b200_status launch_solve(b200_problem* p, double lambda) {
     CK(cudaMemsetAsync(p->sb.status, 0, sizeof(int), p->stream));
     ChunkPlan pl{p->d_begin, p->P};
     if (p->P > 1) {
+        if (p->time_phases) CK(cudaEventRecord(p->ev[8], p->stream));
         B200_LAUNCH(chain_sweep_kernel, dim3(p->c_hi - p->c_lo), dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, p->dm, pl, p->sb, lambda,
                     p->rmax, p->c_lo);
+        if (p->time_phases) CK(cudaEventRecord(p->ev[9], p->stream));
         p->launches++;
         if (p->world > 1) { b200_status st = exchange_reduced(p); if (st != B200_OK) return st; }
         B200_LAUNCH(reduced_assemble_kernel, dim3(p->P - 1), dim3(256), 0, p->stream, p->dm, pl, p->sb);
         p->launches++;
     }
+    if (p->time_phases) CK(cudaEventRecord(p->ev[10], p->stream));
     B200_LAUNCH(top_solve_kernel, dim3(1), dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, p->dm, pl, p->sb, lambda, p->rmax);
+    if (p->time_phases) CK(cudaEventRecord(p->ev[11], p->stream));
     p->launches++;
     if (p->P > 1) {
         B200_LAUNCH(chain_backsub_kernel, dim3(p->c_hi - p->c_lo), dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, p->dm, pl, p->sb, p->c_lo);
+        if (p->time_phases) CK(cudaEventRecord(p->ev[12], p->stream));
         p->launches++;
     }
     return B200_OK;
@@ -480,6 +486,11 @@ b200_status b200_lm_iterate(b200_problem* p, b200_lm_state* state) {
             if (inner == 1) { cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]); p->phase_ms[0] += ms; }
             cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]); p->phase_ms[1] += ms;
             cudaEventElapsedTime(&ms, p->ev[3], p->ev[4]); p->phase_ms[2] += ms;
+            if (p->P > 1) {
+                cudaEventElapsedTime(&ms, p->ev[8], p->ev[9]); p->phase_ms[3] += ms; p->phase_ms[4] += 1;
+                cudaEventElapsedTime(&ms, p->ev[11], p->ev[12]); p->phase_ms[7] += ms;
+            }
+            cudaEventElapsedTime(&ms, p->ev[10], p->ev[11]); p->phase_ms[5] += ms; p->phase_ms[6] += 1;
         }
         const bool solved = host_status(p) == 0;
         const double oldLin = p->h_scal[SC_LIN_ERR], newLin = p->h_scal[SC_MODEL_ERR], newError = p->h_scal[SC_NEW_ERR];
@@ -568,11 +579,29 @@ b200_status b200_optimize(b200_problem* p, const b200_lm_params* lm, const b200_
     return st;
 }
 
-b200_status b200_phase_ms(b200_problem* p, double out[4], int32_t reset) {
+b200_status b200_phase_ms(b200_problem* p, double out[8], int32_t reset) {
     if (!p) return B200_BAD_ARG;
     p->time_phases = true;
-    if (out) for (int i = 0; i < 4; i++) out[i] = p->phase_ms[i];
-    if (reset) for (int i = 0; i < 4; i++) p->phase_ms[i] = 0;
+    if (out) for (int i = 0; i < 8; i++) out[i] = p->phase_ms[i];
+    if (reset) for (int i = 0; i < 8; i++) p->phase_ms[i] = 0;
+    return B200_OK;
+}
+
+b200_status b200_timer_begin(b200_problem* p) {
+    if (!p) return B200_BAD_ARG;
+    CK(cudaSetDevice(p->device));
+    CK(cudaStreamSynchronize(p->stream));
+    CK(cudaEventRecord(p->ev[13], p->stream));
+    return B200_OK;
+}
+b200_status b200_timer_end(b200_problem* p, double* ms) {
+    if (!p || !ms) return B200_BAD_ARG;
+    CK(cudaSetDevice(p->device));
+    CK(cudaEventRecord(p->ev[14], p->stream));
+    CK(cudaEventSynchronize(p->ev[14]));
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, p->ev[13], p->ev[14]));
+    *ms = f;
     return B200_OK;
 }
 

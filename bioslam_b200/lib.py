@@ -120,9 +120,17 @@ class Problem:
         return int(self.L.b200_launch_count(self.h))
 
     def phase_ms(self, reset=False):
-        out = (C.c_double * 4)()
+        out = (C.c_double * 8)()
         self._ck(self.L.b200_phase_ms(self.h, out, C.c_int32(1 if reset else 0)))
         return list(out)
+
+    def timer_begin(self):
+        self._ck(self.L.b200_timer_begin(self.h))
+
+    def timer_end(self):
+        ms = C.c_double()
+        self._ck(self.L.b200_timer_end(self.h, C.byref(ms)))
+        return ms.value
 
     # ---- parity/debug accessors
     def linearize(self):

@@ -287,8 +287,14 @@ b200_status b200_debug_get_static_hessian(b200_problem* p, double* S /*[ns*ns]*/
 b200_status b200_debug_solve(b200_problem* p, double lambda, double* delta_time /*[K][nt]*/, double* delta_static);
 /* kernel launch counter (all launches issued by this library for p since creation) */
 int64_t b200_launch_count(const b200_problem* p);
-/* sum of device time (ms) spent in the named phase since the last reset: 0 linearize, 1 solve, 2 retract+error */
-b200_status b200_phase_ms(b200_problem* p, double out[4], int32_t reset);
+/* device time (CUDA events on the problem's stream) since the last reset.  out[0] linearize+assemble ms, out[1] solve ms,
+ * out[2] model-error+retract+error ms, out[3] chain_sweep_kernel ms, out[4] chain_sweep_kernel launches,
+ * out[5] top_solve_kernel ms, out[6] top_solve_kernel launches, out[7] chain_backsub_kernel ms.
+ * The first call switches the per-phase events on. */
+b200_status b200_phase_ms(b200_problem* p, double out[8], int32_t reset);
+/* CUDA-event stopwatch on the problem's stream (the stream every kernel of this problem is launched on) */
+b200_status b200_timer_begin(b200_problem* p);
+b200_status b200_timer_end(b200_problem* p, double* ms);
 
 #ifdef __cplusplus
 }

@@ -521,7 +521,7 @@ int orc_factor_nconst(int type) { return factor_info(type).nconst; }
 // x: concatenated variable values in factor order
 void orc_factor_eval(int type, const double* params, const double* consts, const double* xcat, double* r, double* J, int whiten) {
     const FactorInfo& fi = factor_info(type);
-    const double* x[B200_MAX_FACTOR_VARS];
+    const double* x[B200_MAX_FACTOR_VARS] = {nullptr};
     int o = 0;
     for (int v = 0; v < fi.nvars; v++) { x[v] = xcat + o; o += kValDim[fi.vartype[v]]; }
     factor_eval(type, params, consts, x, r, J);
