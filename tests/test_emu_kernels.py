@@ -1,0 +1,92 @@
+"""-m "not gpu": the CUDA sources executed under the CUDA-thread emulator (tests/cudaemu, TEST TOOL ONLY) against the
+oracle.  Catches indexing / barrier / host-control-flow bugs in the build container, which has no GPU; numerical parity
+on real hardware is tests/test_gpu_parity.py."""
+import os
+import subprocess
+import numpy as np
+import pytest
+from bioslam_b200 import abi, lib, synth
+from oracle import pyoracle as po
+import graphs
+import parity_checks as pc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "cudaemu", "libbioslam_b200_emu.so")
+
+
+@pytest.fixture(scope="module")
+def emu(oracle_lib):
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "cudaemu")])
+    return EMU
+
+
+def lower_body(seconds, seed=3):
+    tr = synth.make_trial(seed=seed, duration_s=seconds)
+    g, tv, sv = graphs.lower_body_graph(tr)
+    tv, sv = graphs.perturbed_truth_values(tr, g, tv, sv)
+    return tr, g, tv, sv
+
+
+@pytest.mark.parametrize("chunks", [1, 3])
+def test_lower_body_linearization_and_solve(emu, chunks):
+    _, g, tv, sv = lower_body(1.2)
+    o = po.OracleProblem(g); o.set_values(tv, sv)
+    p = lib.Problem(g, so_path=emu, chunks=chunks); p.set_values(tv, sv)
+    assert p.chunks == chunks
+    tv2, sv2 = p.get_values()
+    assert np.array_equal(tv2, tv) and np.array_equal(sv2, sv)
+    pc.assert_linearization_parity(p, o, g)
+    pc.assert_solve_parity(p, o, g)
+
+
+def test_lower_body_lm_iterations(emu):
+    _, g, tv, sv = lower_body(1.0)
+    o = po.OracleProblem(g); o.set_values(tv, sv)
+    p = lib.Problem(g, so_path=emu, chunks=2); p.set_values(tv, sv)
+    pc.assert_lm_parity(p, o, abi.LmParams.lower_body(), 3)
+    assert p.launch_count() > 10
+
+
+@pytest.mark.parametrize("static_bias", [False, True])
+def test_single_imu(emu, static_bias):
+    tr = synth.make_trial(seed=4, duration_s=2.0)
+    K = graphs.n_keyframes(tr.N, 10)
+    R0 = tr.poses_at((graphs.keyframe_sample_idx(K, 10) + 1) * tr.dt)["sacrum"][0] @ synth.exp_so3(np.random.default_rng(0).normal(scale=0.05, size=(K, 3)))
+    g, tv, sv = graphs.single_imu_graph(tr.acc[0], tr.gyro[0], tr.dt, static_bias=static_bias, init_R=R0, ref_local=(0, 1, 0))
+    o = po.OracleProblem(g); o.set_values(tv, sv)
+    p = lib.Problem(g, so_path=emu, chunks=2); p.set_values(tv, sv)
+    pc.assert_linearization_parity(p, o, g)
+    pc.assert_solve_parity(p, o, g, lams=(1e-2, 10.0))
+    pc.assert_lm_parity(p, o, abi.LmParams.single_imu(), 2, rel=2e-2)
+
+
+def test_preintegration_kernel(emu):
+    tr = synth.make_trial(seed=9, duration_s=1.0)
+    bh = np.random.default_rng(1).normal(scale=0.01, size=(7, 6))
+    for combined in (True, False):
+        a = po.preintegrate(tr.acc, tr.gyro, tr.dt, 10, bh, combined=combined)
+        b = lib.preintegrate(tr.acc, tr.gyro, tr.dt, 10, bh, combined=combined, so_path=emu)
+        pc.assert_preintegration_parity(a, b, combined)
+
+
+def test_indeterminate_system_is_reported(emu):
+    """a pose with no factor attached makes the undamped system singular: status, not a crash
+    (== gtsam::IndeterminantLinearSystemException, reference src/imuPoseEstimator.cpp:360)"""
+    g = abi.GraphDesc(3, [abi.VAR_VEC3, abi.VAR_VEC3], [])
+    g.add_slot(abi.F_PRIOR_VEC3, [(abi.AT_K, 0)], [1, 1, 1, 0, 0, 0])
+    p = lib.Problem(g, so_path=emu, chunks=1)
+    p.set_values(np.ones((3, 6)), np.zeros(0))
+    p.linearize()
+    st, _, _ = p.solve(0.0)
+    assert st == abi.INDETERMINATE_SYSTEM
+    st, dt, _ = p.solve(1.0)
+    assert st == abi.OK and np.allclose(dt[:, :3], -0.5) and np.allclose(dt[:, 3:], 0.0)
+
+
+def test_bad_arguments_are_rejected(emu):
+    g = abi.GraphDesc(2, [abi.VAR_POSE3], [])
+    g.add_slot(abi.F_POSE3_TRANSLATION_PRIOR, [(abi.AT_K, 0)], [1, 1, 1, 0, 0, 0])
+    g.slots[0].k_end = 5
+    with pytest.raises(lib.B200Error) as e:
+        lib.Problem(g, so_path=emu)
+    assert e.value.status == abi.BAD_ARG

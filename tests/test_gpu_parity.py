@@ -1,0 +1,164 @@
+"""-m gpu: the parity tests proper.  The CUDA library (through the C ABI) against the oracle on identical seeded inputs,
+at sizes the oracle finishes in seconds, plus size-independent properties at the bench size.
+
+Tolerances (north_star): final cost within 1e-6 relative; per-factor sums 1e-11 relative (fp64, different summation
+order); positions within 1e-6 m and hip/knee angles within 1e-3 deg at convergence (see test_converged_solution_parity)."""
+import numpy as np
+import pytest
+from bioslam_b200 import abi, lib, synth
+import graphs
+import parity_checks as pc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def po(oracle_lib):
+    return oracle_lib
+
+
+def lower_body(seconds, seed=3, near_truth=True, device_preint=False):
+    tr = synth.make_trial(seed=seed, duration_s=seconds)
+    pre = (lambda a, w, dt, n, bh: lib.preintegrate(a, w, dt, n, bh)) if device_preint else None
+    g, tv, sv = graphs.lower_body_graph(tr, preint=pre)
+    if near_truth:
+        tv, sv = graphs.perturbed_truth_values(tr, g, tv, sv)
+    return tr, g, tv, sv
+
+
+def test_library_is_the_cuda_build():
+    L = lib.load()
+    assert not hasattr(L, "emu_marker")
+    import torch
+    assert torch.cuda.is_available()
+
+
+@pytest.mark.parametrize("chunks", [1, 2, 5, None])
+def test_linearization_and_solve_parity(po, chunks):
+    _, g, tv, sv = lower_body(6.0)
+    o = po.OracleProblem(g, threads=8); o.set_values(tv, sv)
+    p = lib.Problem(g, chunks=chunks); p.set_values(tv, sv)
+    tv2, sv2 = p.get_values()
+    assert np.array_equal(tv2, tv) and np.array_equal(sv2, sv)
+    pc.assert_linearization_parity(p, o, g)
+    pc.assert_solve_parity(p, o, g, lams=(1e-5, 1e-3, 1.0, 1e3))
+    p.close()
+
+
+def test_preintegration_parity(po):
+    tr = synth.make_trial(seed=9, duration_s=20.0)
+    bh = np.random.default_rng(1).normal(scale=0.01, size=(7, 6))
+    for combined in (True, False):
+        a = po.preintegrate(tr.acc, tr.gyro, tr.dt, 10, bh, combined=combined)
+        b = lib.preintegrate(tr.acc, tr.gyro, tr.dt, 10, bh, combined=combined)
+        pc.assert_preintegration_parity(a, b, combined)
+    # ragged: n_per = 7 does not divide the sample count; n_per = 1 (one keyframe per sample)
+    for n_per in (7, 1):
+        a = po.preintegrate(tr.acc[:, :300], tr.gyro[:, :300], tr.dt, n_per, bh)
+        b = lib.preintegrate(tr.acc[:, :300], tr.gyro[:, :300], tr.dt, n_per, bh)
+        pc.assert_preintegration_parity(a, b, True)
+
+
+@pytest.mark.parametrize("chunks", [1, 4])
+def test_lm_iteration_parity_zero_init(po, chunks):
+    """reference initial values (identity poses): same accept/reject sequence and errors for the first iterations"""
+    _, g, tv, sv = lower_body(4.0, seed=1, near_truth=False)
+    o = po.OracleProblem(g, threads=8); o.set_values(tv, sv)
+    p = lib.Problem(g, chunks=chunks); p.set_values(tv, sv)
+    pc.assert_lm_parity(p, o, abi.LmParams.lower_body(), 8, rel=2e-2)
+    p.close()
+
+
+def test_converged_solution_parity(po):
+    """full LM to a fixed iteration budget from the reference's initial values: final cost within 1e-6 relative, IMU
+    positions within 1e-6 m, rotations within 1e-3 deg"""
+    _, g, tv, sv = lower_body(3.0, seed=2, near_truth=False)
+    lm, outer = abi.LmParams.lower_body(), abi.OuterParams.lower_body(max_iterations=400)
+    o = po.OracleProblem(g, threads=8); o.set_values(tv, sv)
+    ro, ho = o.optimize(lm, outer)
+    p = lib.Problem(g, chunks=3); p.set_values(tv, sv)
+    rp, hp = p.optimize(lm, outer)
+    assert rp.status == ro.status
+    assert abs(rp.final_error - ro.final_error) <= 1e-6 * ro.final_error, (rp.final_error, ro.final_error, rp.iterations, ro.iterations)
+    tvo, svo = o.get_values(); tvp, svp = p.get_values()
+    off = g.time_value_offsets()
+    for i in range(7):
+        po_, pp_ = tvo[:, off[3 * i] + 9:off[3 * i] + 12], tvp[:, off[3 * i] + 9:off[3 * i] + 12]
+        assert np.abs(po_ - pp_).max() < 1e-6
+        Ro, Rp = tvo[:, off[3 * i]:off[3 * i] + 9].reshape(-1, 3, 3), tvp[:, off[3 * i]:off[3 * i] + 9].reshape(-1, 3, 3)
+        ang = np.degrees(np.linalg.norm(synth.log_so3(np.swapaxes(Ro, 1, 2) @ Rp), axis=-1))
+        assert ang.max() < 1e-3
+    p.close()
+
+
+@pytest.mark.parametrize("static_bias", [False, True])
+def test_single_imu_parity(po, static_bias):
+    tr = synth.make_trial(seed=4, duration_s=10.0)
+    K = graphs.n_keyframes(tr.N, 10)
+    R0 = tr.poses_at((graphs.keyframe_sample_idx(K, 10) + 1) * tr.dt)["sacrum"][0] @ synth.exp_so3(np.random.default_rng(0).normal(scale=0.05, size=(K, 3)))
+    g, tv, sv = graphs.single_imu_graph(tr.acc[0], tr.gyro[0], tr.dt, static_bias=static_bias, init_R=R0, ref_local=(0, 1, 0))
+    o = po.OracleProblem(g); o.set_values(tv, sv)
+    p = lib.Problem(g, chunks=4); p.set_values(tv, sv)
+    pc.assert_linearization_parity(p, o, g)
+    pc.assert_solve_parity(p, o, g, lams=(1e-2, 10.0))
+    pc.assert_lm_parity(p, o, abi.LmParams.single_imu(), 3, rel=2e-2)
+    p.close()
+
+
+def test_joint_velocity_factor_variant(po):
+    tr = synth.make_trial(seed=6, duration_s=3.0)
+    g, tv, sv = graphs.lower_body_graph(tr, use_joint_vel=True)
+    tv, sv = graphs.perturbed_truth_values(tr, g, tv, sv)
+    o = po.OracleProblem(g, threads=8); o.set_values(tv, sv)
+    p = lib.Problem(g, chunks=2); p.set_values(tv, sv)
+    pc.assert_linearization_parity(p, o, g)
+    p.close()
+
+
+def test_partition_independence_and_determinism():
+    """size-independent properties at a larger size (K = 600): the solve does not depend on the partition beyond
+    rounding, and repeated runs are bit-identical (no atomics with more than one contributor)"""
+    _, g, tv, sv = lower_body(60.0, seed=5, device_preint=True)
+    sols = []
+    for chunks in (12, 36, 36):
+        p = lib.Problem(g, chunks=chunks); p.set_values(tv, sv)
+        p.linearize()
+        st, dt, ds = p.solve(1e-2)
+        assert st == abi.OK
+        sols.append((dt, ds))
+        p.close()
+    assert np.array_equal(sols[1][0], sols[2][0]) and np.array_equal(sols[1][1], sols[2][1])
+    assert np.abs(sols[0][0] - sols[1][0]).max() <= 1e-5 * np.abs(sols[1][0]).max()
+
+
+def test_lm_monotone_and_matches_error_recompute():
+    _, g, tv, sv = lower_body(60.0, seed=5, near_truth=False, device_preint=True)
+    p = lib.Problem(g); p.set_values(tv, sv)
+    e_prev = p.lm_begin(abi.LmParams.lower_body())
+    for _ in range(6):
+        st = p.lm_iterate()
+        assert st.error <= e_prev
+        e_prev = st.error
+    assert abs(p.error() - st.error) <= 1e-12 * st.error
+    tv2, sv2 = p.get_values()
+    # rotations stay orthonormal, Unit3 statics stay unit
+    R = tv2[:, :9].reshape(-1, 3, 3)
+    assert np.abs(R @ np.swapaxes(R, 1, 2) - np.eye(3)).max() < 1e-9
+    axes = sv2[36:].reshape(-1, 3)
+    assert np.abs(np.linalg.norm(axes, axis=1) - 1).max() < 1e-12
+    p.close()
+
+
+def test_indeterminate_and_bad_args():
+    g = abi.GraphDesc(3, [abi.VAR_VEC3, abi.VAR_VEC3], [])
+    g.add_slot(abi.F_PRIOR_VEC3, [(abi.AT_K, 0)], [1, 1, 1, 0, 0, 0])
+    p = lib.Problem(g, chunks=1)
+    p.set_values(np.ones((3, 6)), np.zeros(0))
+    p.linearize()
+    assert p.solve(0.0)[0] == abi.INDETERMINATE_SYSTEM
+    st, dt, _ = p.solve(1.0)
+    assert st == abi.OK and np.allclose(dt[:, :3], -0.5)
+    p.close()
+    g.slots[0].k_end = 9
+    with pytest.raises(lib.B200Error):
+        lib.Problem(g)
