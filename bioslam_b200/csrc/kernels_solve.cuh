@@ -408,14 +408,7 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
         double* Bs = Ls + (long long)B200_NB * ld;
         const int xo = has_x ? nc : 0;
         const int Rn = xo + h;
-        // add this node's own static block to the arrow Schur complement (lower triangle)
-        {
-            const double* Sg = a.Ssrc + src * ns1 * ns1;
-            for (int e = threadIdx.x; e < ns1 * ns1; e += blockDim.x) {
-                const int r = e / ns1, c = e % ns1;
-                if (c <= r) a.Sacc[(long long)r * hmax + c] += Sg[e];
-            }
-        }
+        const double* Sg = a.Ssrc + src * ns1 * ns1;   // this node's own static block, folded into the Schur update below
         const int nchunks = (Rn + a.rmax - 1) / a.rmax;
         const int csz = (Rn + nchunks - 1) / nchunks;
         for (int ch = 0; ch < nchunks; ch++) {
@@ -485,7 +478,12 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                 } else if (sr2 < nc) {
                     Fout[(long long)sr1 * nc + sr2] = v;
                 } else {
-                    atomicAdd(a.Sacc + (long long)(sr1 - nc) * hmax + (sr2 - nc), -v);  // one contributor per entry and step: deterministic
+                    // exactly one reduction per entry and step (own static block - Y Y^T): deterministic, never mixed with
+                    // plain loads of Sacc inside the sweep (atomics resolve in L2)
+                    const int a1 = sr1 - nc, a2 = sr2 - nc;
+                    double add = -v;
+                    if (a1 < ns1) add += Sg[a1 * ns1 + a2];
+                    atomicAdd(a.Sacc + (long long)a1 * hmax + a2, add);
                 }
             };
             const int sro = has_x ? 0 : nc;  // storage row of present row 0
@@ -688,7 +686,7 @@ __global__ void __launch_bounds__(B200_SOLVE_THREADS) top_solve_kernel(Dims dm, 
     double* Ss = sm;
     for (int e = threadIdx.x; e < ns1 * ns1; e += blockDim.x) {
         const int r = e / ns1, c = e % ns1;
-        if (c <= r && c < ns) Ss[r * lds + c] = a.Sacc[(long long)r * hmax + c] + ((r == c) ? lambda : 0.0);
+        if (c <= r && c < ns) Ss[r * lds + c] = __ldcg(a.Sacc + (long long)r * hmax + c) + ((r == c) ? lambda : 0.0);
     }
     __syncthreads();
     if (ns > 0) {

@@ -116,6 +116,7 @@ inline double __dsqrt_rn(double x) { return std::sqrt(x); }
 inline double __ddiv_rn(double a, double b) { return a / b; }
 inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
 template <class T> inline T __ldg(const T* p) { return *p; }
+template <class T> inline T __ldcg(const T* p) { return *p; }
 struct double2 { double x, y; };
 inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 using std::fabs; using std::sqrt; using std::sin; using std::cos; using std::acos; using std::atan2; using std::tanh; using std::tan;
