@@ -69,9 +69,18 @@ struct b200_problem {
     int max_inst = 0;
     double *d_D = nullptr, *d_O = nullptr, *d_A = nullptr, *d_S = nullptr;
     SolveBuffers sb{};
-    int* d_begin = nullptr;
-    std::vector<int> begin;
-    int P = 1, rmax = 0;
+    struct HostLevel {
+        int n_nodes = 0, P = 1, c_lo = 0, c_hi = 1;
+        std::vector<int> begin, st, sep_st;     // partition over nodes; storage index per node; per separator
+        int *d_begin = nullptr, *d_st = nullptr, *d_sep_st = nullptr;
+        double *F = nullptr, *S = nullptr, *Dred = nullptr, *Ored = nullptr, *Ared = nullptr, *Sred = nullptr;
+        Level dev{};
+    };
+    std::vector<HostLevel> levels;             // levels[0]: keyframes, levels[1]: its separators (optional)
+    int P = 1, P2 = 1, rmax = 0;               // chunks of level 0 / level 1
+    int Wk = 0;                                // keyframes per rank window
+    double *d_stageS = nullptr, *d_stageF = nullptr, *d_pack = nullptr;
+    size_t pack_doubles = 0;
     size_t smem_sweep = 0, smem_asm[2] = {0, 0};
     double* h_scal = nullptr;  // pinned: SC_COUNT doubles + status
     // LM state
@@ -89,13 +98,20 @@ struct b200_problem {
     b200_allgather_fn ag_fn = nullptr;
     b200_allreduce_fn ar_fn = nullptr;
     void* comm_ctx = nullptr;
-    double *d_sepD = nullptr, *d_sepA = nullptr, *d_sepS = nullptr, *d_sepO = nullptr;
 };
 
 template <class T>
 static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, (n ? n : 1) * sizeof(T)); }
 
 static int choose_ld(int ntp) { int ld = ntp; while ((ld & 3) != 2) ld++; return ld; }
+
+static void free_levels(b200_problem* p) {
+    for (auto& l : p->levels) {
+        void* q[] = {l.d_begin, l.d_st, l.d_sep_st, l.F, l.S, l.Dred, l.Ored, l.Ared, l.Sred};
+        for (void* x : q) if (x) cudaFree(x);
+    }
+    p->levels.clear();
+}
 
 extern "C" {
 
@@ -105,17 +121,17 @@ void b200_problem_destroy(b200_problem* p) {
     if (!p) return;
     cudaSetDevice(p->device);
     void* ptrs[] = {p->d_tv, p->d_tv_try, p->d_sv, p->d_sv_try, p->d_cst, p->d_stage, p->d_slots, p->d_tvars, p->d_svars, p->d_J, p->d_r,
-                    p->d_e, p->d_e2, p->d_D, p->d_O, p->d_A, p->d_S, p->sb.Lst, p->sb.Pst, p->sb.Fchunk, p->sb.Schunk, p->sb.Dred,
-                    p->sb.Ored, p->sb.Ared, p->sb.Sred, p->sb.Ftop, p->sb.Stop, p->sb.sep_idx, p->sb.delta, p->sb.dstat, p->sb.scal,
-                    p->sb.status, p->d_begin, p->d_sepD, p->d_sepA, p->d_sepS, p->d_sepO};
+                    p->d_e, p->d_e2, p->d_D, p->d_O, p->d_A, p->d_S, p->sb.Lst, p->sb.Pst, p->sb.Ftop, p->sb.Stop, p->sb.delta, p->sb.dstat,
+                    p->sb.scal, p->sb.status, p->d_stageS, p->d_stageF, p->d_pack};
     for (void* q : ptrs) if (q) cudaFree(q);
+    free_levels(p);
     if (p->h_scal) cudaFreeHost(p->h_scal);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
 }
 
-static b200_status set_partition(b200_problem* p, int P);
+static b200_status set_partition(b200_problem* p, int P1, int P2);
 
 b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200_problem** out) {
     if (!d || !out || d->K < 1 || d->n_time_vars < 1 || d->n_slots < 1) { set_err("bad description"); return B200_BAD_ARG; }
@@ -207,11 +223,10 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
     CK(dalloc(&p->d_D, K * dm.ntp * dm.ntp)); CK(dalloc(&p->d_O, K * dm.nc * dm.nc));
     CK(dalloc(&p->d_A, K * dm.ns1 * dm.ntp)); CK(dalloc(&p->d_S, K * dm.ns1 * dm.ns1));
     CK(dalloc(&p->sb.Lst, K * dm.ntp * dm.ntp)); CK(dalloc(&p->sb.Pst, K * (size_t)(dm.nc + dm.hmax) * dm.ntp));
-    CK(dalloc(&p->sb.delta, K * dm.ntp)); CK(dalloc(&p->sb.dstat, (size_t)ns + 1)); CK(dalloc(&p->sb.scal, (size_t)SC_COUNT));
+    CK(dalloc(&p->sb.delta, (K + 1024) * dm.ntp)); CK(dalloc(&p->sb.dstat, (size_t)ns + 1)); CK(dalloc(&p->sb.scal, (size_t)SC_COUNT));
     CK(dalloc(&p->sb.status, (size_t)1));
     CK(dalloc(&p->sb.Ftop, (size_t)2 * (dm.nc + dm.hmax) * dm.nc)); CK(dalloc(&p->sb.Stop, (size_t)dm.hmax * dm.hmax));
     CK(cudaMallocHost((void**)&p->h_scal, (SC_COUNT + 2) * sizeof(double)));
-    p->sb.Dsrc = p->d_D; p->sb.Osrc = p->d_O; p->sb.Asrc = p->d_A; p->sb.Ssrc = p->d_S;
     // uploads
     CK(cudaMemcpy(p->d_slots, p->hslots.data(), sizeof(DevSlot) * p->n_slots, cudaMemcpyHostToDevice));
     std::vector<DevVar> tvars(p->ntv), svars(std::max(p->nsv, 1));
@@ -234,8 +249,8 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
     {
         cudaFuncAttributes fa;
         CK(cudaFuncGetAttributes(&fa, top_solve_kernel)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
-        CK(cudaFuncGetAttributes(&fa, chain_sweep_kernel)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
-        CK(cudaFuncGetAttributes(&fa, chain_backsub_kernel)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
+        CK(cudaFuncGetAttributes(&fa, level_sweep_kernel)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
+        CK(cudaFuncGetAttributes(&fa, level_backsub_kernel)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
         CK(cudaFuncGetAttributes(&fa, assemble_kernel)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
     }
     const size_t smem_cap = (227 * 1024 - static_smem - 1024) & ~(size_t)15;  // dynamic budget next to the kernels' static arrays
@@ -255,53 +270,149 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
     }
 #ifndef B200_USE_EMU
     CK(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(p->smem_asm[0], p->smem_asm[1])));
-    CK(cudaFuncSetAttribute(chain_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sweep));
+    CK(cudaFuncSetAttribute(level_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sweep));
     CK(cudaFuncSetAttribute(top_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sweep));
-    CK(cudaFuncSetAttribute(chain_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sweep));
+    CK(cudaFuncSetAttribute(level_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sweep));
 #endif
     p->k_lo = 0; p->k_hi = p->K;
-    // default partition: P ~ sqrt(2.2 K) chunks (interior steps cost ~2.2x a top-level step), at most one CTA per SM
-    int P = (int)std::lround(std::sqrt(2.2 * (double)p->K));
-    if (const char* env = std::getenv("B200_CHUNKS")) P = std::atoi(env);
-    b200_status st = set_partition(p, P);
+    int P1 = 0, P2 = 0;   // 0: choose from the cost model
+    if (const char* env = std::getenv("B200_CHUNKS")) P1 = std::atoi(env);
+    if (const char* env = std::getenv("B200_GROUPS")) P2 = std::atoi(env);
+    b200_status st = set_partition(p, P1, P2);
     if (st != B200_OK) { b200_problem_destroy(p); return st; }
     *out = p;
     return B200_OK;
 }
 
-// choose P chunks of >= 2 keyframes (P == 1: plain sequential sweep)
-static b200_status set_partition(b200_problem* p, int P) {
+// cost model (units of one narrow elimination step; an interior step carries the left separator and costs ~1.8 of them):
+// T = waves(P1) * 1.8 * (K/P1 - 1) + [P2 > 1 ? 1.8 * ((P1-1)/P2 - 1) + (P2 - 1) : (P1 - 1)]
+static double partition_cost(int K, int P1, int P2, int sms) {
+    if (P1 <= 1) return (double)K;
+    const double waves = std::ceil((double)P1 / sms);
+    double t = waves * 1.8 * ((double)K / P1 - 1.0);
+    const int n2 = P1 - 1;
+    if (P2 > 1) t += 1.8 * ((double)n2 / P2 - 1.0) + (P2 - 1);
+    else t += n2;
+    return t;
+}
+
+// Build the nested partition.  P1 chunks over the keyframes (every rank owns P1/world of them, inside its window of
+// ceil(K/world) keyframes); P2 > 1: the P1-1 separators are themselves cut into P2 groups (rank-aligned) and only the
+// P2-1 group separators are eliminated sequentially by the single top-level CTA.  Chunks hold >= 2 nodes.
+static b200_status set_partition(b200_problem* p, int P1, int P2) {
     const Dims& dm = p->dm;
-    P = std::max(1, std::min(P, 148));
-    if (p->world > 1) { P = std::max(P, p->world); P = (P + p->world - 1) / p->world * p->world; }
-    while (P > 1 && p->K / P < 3) P -= (p->world > 1 ? p->world : 1);
-    if (P < 1) P = 1;
-    if (p->world > 1 && P % p->world) { set_err("too few keyframes for this many ranks"); return B200_BAD_ARG; }
-    p->P = P;
-    p->begin.resize(P + 1);
-    for (int c = 0; c <= P; c++) p->begin[c] = (int)((long long)c * p->K / P);
-    void* olds[] = {p->sb.Fchunk, p->sb.Schunk, p->sb.Dred, p->sb.Ored, p->sb.Ared, p->sb.Sred, p->sb.sep_idx, p->d_begin};
-    for (void* q : olds) if (q) cudaFree(q);
-    CK(dalloc(&p->sb.Fchunk, (size_t)P * 2 * (dm.nc + dm.hmax) * dm.nc));
-    CK(dalloc(&p->sb.Schunk, (size_t)P * dm.hmax * dm.hmax));
-    CK(dalloc(&p->sb.Dred, (size_t)P * dm.ntp * dm.ntp)); CK(dalloc(&p->sb.Ored, (size_t)P * dm.nc * dm.nc));
-    CK(dalloc(&p->sb.Ared, (size_t)P * dm.ns1 * dm.ntp)); CK(dalloc(&p->sb.Sred, (size_t)P * dm.ns1 * dm.ns1));
-    CK(dalloc(&p->sb.sep_idx, (size_t)P)); CK(dalloc(&p->d_begin, (size_t)P + 1));
-    CK(cudaMemcpy(p->d_begin, p->begin.data(), sizeof(int) * (P + 1), cudaMemcpyHostToDevice));
-    const int per = P / p->world;
-    p->c_lo = p->rank * per; p->c_hi = p->c_lo + per;
-    p->k_lo = p->begin[p->c_lo]; p->k_hi = p->begin[p->c_hi];
+    const int K = p->K, W = p->world, sms = 148;
+    p->Wk = (K + W - 1) / W;
+    if ((long long)(W - 1) * p->Wk >= K || K - (W - 1) * p->Wk < 3) { set_err("too few keyframes for this many ranks"); return B200_BAD_ARG; }
+    const int max_p1 = std::max(1, K / 3);
+    if (P1 <= 0) {  // search the cost model
+        double best = 1e300; int bp1 = 1, bp2 = 1;
+        for (int c1 = 1; c1 <= std::min(max_p1, 8 * sms); c1++) {
+            if (c1 % W) continue;
+            for (int c2 = 1; c2 <= std::max(1, (c1 - 1) / 3); c2++) {
+                if (c2 > 1 && c2 % W) continue;
+                if (W > 1 && c2 < W) continue;
+                const double t = partition_cost(K, c1, c2, sms);
+                if (t < best) { best = t; bp1 = c1; bp2 = c2; }
+            }
+        }
+        P1 = bp1; if (P2 <= 0) P2 = bp2;
+    }
+    P1 = std::max(1, std::min(P1, max_p1));
+    if (W > 1) { P1 = std::max(P1, 2 * W); P1 = (P1 + W - 1) / W * W; while (P1 > W && p->Wk / (P1 / W) < 3) P1 -= W; }
+    if (P2 <= 0) {  // choose groups for the given P1
+        double best = 1e300; int bp2 = 1;
+        for (int c2 = 1; c2 <= std::max(1, (P1 - 1) / 3); c2++) {
+            if (W > 1 && c2 % W) continue;
+            const double t = partition_cost(K, P1, c2, sms);
+            if (t < best) { best = t; bp2 = c2; }
+        }
+        P2 = bp2;
+    }
+    if (W > 1) { P2 = std::max(P2, W); P2 = (P2 + W - 1) / W * W; while (P2 > W && (P1 / W) / (P2 / W) < 3) P2 -= W; if ((P1 / W) / (P2 / W) < 2) { set_err("partition too fine for this many ranks"); return B200_BAD_ARG; } }
+    else { if (P1 < 4) P2 = 1; while (P2 > 1 && (P1 - 1) / P2 < 2) P2--; }
+    free_levels(p);
+    p->P = P1; p->P2 = P2;
+    const int nlev = (P1 > 1) ? ((P2 > 1) ? 2 : 1) : 0;
+    p->levels.resize(std::max(nlev, 1));
+    // ---- level 0: keyframes
+    {
+        auto& l = p->levels[0];
+        l.n_nodes = K; l.P = P1;
+        l.begin.resize(P1 + 1);
+        const int per = P1 / W;
+        for (int r = 0; r < W; r++) {
+            const int k0 = r * p->Wk, k1 = std::min(K, (r + 1) * p->Wk);
+            for (int j = 0; j < per; j++) l.begin[r * per + j] = k0 + (int)((long long)j * (k1 - k0) / per);
+        }
+        l.begin[P1] = K;
+        l.c_lo = p->rank * per; l.c_hi = l.c_lo + per;
+        l.sep_st.resize(std::max(P1 - 1, 1));
+        for (int c = 0; c + 1 < P1; c++) l.sep_st[c] = l.begin[c + 1] - 1;
+        p->k_lo = l.begin[l.c_lo]; p->k_hi = l.begin[l.c_hi];
+    }
+    // ---- level 1: the separators of level 0
+    if (nlev == 2) {
+        auto& l0 = p->levels[0];
+        auto& l = p->levels[1];
+        l.n_nodes = P1 - 1; l.P = P2;
+        l.st = l0.sep_st; l.st.resize(l.n_nodes);
+        l.begin.resize(P2 + 1);
+        const int per1 = P1 / W, gpr = P2 / W;
+        for (int r = 0; r < W; r++) {
+            const int n0 = r * per1, n1 = std::min(P1 - 1, (r + 1) * per1);   // this rank's separators
+            for (int j = 0; j < gpr; j++) l.begin[r * gpr + j] = n0 + (int)((long long)j * (n1 - n0) / gpr);
+        }
+        l.begin[P2] = P1 - 1;
+        l.c_lo = p->rank * gpr; l.c_hi = l.c_lo + gpr;
+        l.sep_st.resize(std::max(P2 - 1, 1));
+        for (int g = 0; g + 1 < P2; g++) l.sep_st[g] = l.st[l.begin[g + 1] - 1];
+    }
+    const size_t Fsz = (size_t)(dm.nc + dm.hmax) * dm.nc, Ssz = (size_t)dm.hmax * dm.hmax;
+    for (int li = 0; li < nlev; li++) {
+        auto& l = p->levels[li];
+        for (int c = 0; c < l.P; c++) {
+            const int n = l.begin[c + 1] - l.begin[c];
+            if (n < 2) { set_err("internal: partition produced a chunk with fewer than 2 nodes"); return B200_BAD_ARG; }
+        }
+        const size_t P = l.P;
+        CK(dalloc(&l.d_begin, P + 1)); CK(dalloc(&l.d_sep_st, P)); CK(dalloc(&l.d_st, (size_t)std::max(l.n_nodes, 1)));
+        CK(cudaMemcpy(l.d_begin, l.begin.data(), sizeof(int) * (P + 1), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(l.d_sep_st, l.sep_st.data(), sizeof(int) * l.sep_st.size(), cudaMemcpyHostToDevice));
+        if (!l.st.empty()) CK(cudaMemcpy(l.d_st, l.st.data(), sizeof(int) * l.st.size(), cudaMemcpyHostToDevice));
+        CK(dalloc(&l.F, (P + 1) * 2 * Fsz)); CK(dalloc(&l.S, (P + 1) * Ssz));
+        CK(dalloc(&l.Dred, P * dm.ntp * dm.ntp)); CK(dalloc(&l.Ored, P * dm.nc * dm.nc));
+        CK(dalloc(&l.Ared, P * dm.ns1 * dm.ntp)); CK(dalloc(&l.Sred, P * dm.ns1 * dm.ns1));
+        Level& d = l.dev;
+        if (li == 0) { d.Dsrc = p->d_D; d.Osrc = p->d_O; d.Asrc = p->d_A; d.Ssrc = p->d_S; d.st = nullptr; }
+        else { auto& lp = p->levels[li - 1]; d.Dsrc = lp.Dred; d.Osrc = lp.Ored; d.Asrc = lp.Ared; d.Ssrc = lp.Sred; d.st = l.d_st; }
+        d.begin = l.d_begin; d.P = l.P; d.F = l.F; d.S = l.S;
+        d.Dred = l.Dred; d.Ored = l.Ored; d.Ared = l.Ared; d.Sred = l.Sred; d.sep_st = l.d_sep_st;
+    }
+    if (nlev == 0) { auto& l = p->levels[0]; l.n_nodes = K; l.P = 1; p->k_lo = 0; p->k_hi = K; }
+    if (W > 1) {
+        if (p->d_stageS) cudaFree(p->d_stageS);
+        if (p->d_stageF) cudaFree(p->d_stageF);
+        if (p->d_pack) cudaFree(p->d_pack);
+        p->d_stageS = p->d_stageF = p->d_pack = nullptr;
+        CK(dalloc(&p->d_stageS, (size_t)W * Ssz)); CK(dalloc(&p->d_stageF, (size_t)W * 2 * Fsz));
+        p->pack_doubles = (size_t)dm.ntp * dm.ntp + (size_t)dm.ns1 * dm.ntp + (size_t)dm.ns1 * dm.ns1;
+        CK(dalloc(&p->d_pack, (size_t)P2 * p->pack_doubles));
+    }
     p->have_lin = false;
     return B200_OK;
 }
 
-b200_status b200_set_chunks(b200_problem* p, int32_t n_chunks) {
+b200_status b200_set_partition(b200_problem* p, int32_t n_chunks, int32_t n_groups) {
     if (!p) return B200_BAD_ARG;
     CK(cudaSetDevice(p->device));
     CK(cudaStreamSynchronize(p->stream));
-    return set_partition(p, n_chunks);
+    return set_partition(p, n_chunks, n_groups);
 }
+// n_chunks > 0 with the separators eliminated by one sequential top-level sweep (two-level scheme)
+b200_status b200_set_chunks(b200_problem* p, int32_t n_chunks) { return b200_set_partition(p, n_chunks, n_chunks > 0 ? 1 : 0); }
 int32_t b200_get_chunks(const b200_problem* p) { return p ? p->P : 0; }
+int32_t b200_get_groups(const b200_problem* p) { return p ? p->P2 : 0; }
 
 int32_t b200_time_value_dim(const b200_problem* p) { return p->tvd; }
 int32_t b200_static_value_dim(const b200_problem* p) { return p->svd; }
@@ -351,51 +462,111 @@ static void launch_linearize(b200_problem* p) {
     B200_LAUNCH(linearize_kernel<true>, grid, dim3(128), 0, p->stream, p->d_slots, p->d_tv, p->d_sv, p->d_cst, p->dm.Kld, p->d_J, p->d_r,
                 p->d_e, std::max(p->k_lo - 1, 0), p->k_hi);
     p->launches++;
-    for (int half = 0; half < 2; half++) {
-        // (two launches: the halves need different amounts of shared memory)
-    }
-    B200_LAUNCH(assemble_kernel, dim3(p->k_hi - p->k_lo, 2), dim3(256), std::max(p->smem_asm[0], p->smem_asm[1]), p->stream, p->dm,
-                p->d_slots, p->n_slots, p->d_J, p->d_r, (const int*)nullptr, p->k_lo, 0, p->K, p->d_D, p->d_O, p->d_A, p->d_S);
+    // one extra keyframe on the left: its O block (coupling k_lo-1 -> k_lo) is the left-separator coupling of this window
+    const int ka = std::max(p->k_lo - 1, 0);
+    B200_LAUNCH(assemble_kernel, dim3(p->k_hi - ka, 2), dim3(256), std::max(p->smem_asm[0], p->smem_asm[1]), p->stream, p->dm,
+                p->d_slots, p->n_slots, p->d_J, p->d_r, (const int*)nullptr, ka, 0, p->K, p->d_D, p->d_O, p->d_A, p->d_S);
     p->launches++;
 }
 
-static b200_status exchange_reduced(b200_problem* p);
-
-static b200_status launch_solve(b200_problem* p, double lambda) {
-    CK(cudaMemsetAsync(p->sb.status, 0, sizeof(int), p->stream));
-    ChunkPlan pl{p->d_begin, p->P};
-    if (p->P > 1) {
-        if (p->time_phases) CK(cudaEventRecord(p->ev[8], p->stream));
-        B200_LAUNCH(chain_sweep_kernel, dim3(p->c_hi - p->c_lo), dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, p->dm, pl, p->sb, lambda,
-                    p->rmax, p->c_lo);
-        if (p->time_phases) CK(cudaEventRecord(p->ev[9], p->stream));
-        p->launches++;
-        if (p->world > 1) { b200_status st = exchange_reduced(p); if (st != B200_OK) return st; }
-        B200_LAUNCH(reduced_assemble_kernel, dim3(p->P - 1), dim3(256), 0, p->stream, p->dm, pl, p->sb);
-        p->launches++;
-    }
-    if (p->time_phases) CK(cudaEventRecord(p->ev[10], p->stream));
-    B200_LAUNCH(top_solve_kernel, dim3(1), dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, p->dm, pl, p->sb, lambda, p->rmax);
-    if (p->time_phases) CK(cudaEventRecord(p->ev[11], p->stream));
-    p->launches++;
-    if (p->P > 1) {
-        B200_LAUNCH(chain_backsub_kernel, dim3(p->c_hi - p->c_lo), dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, p->dm, pl, p->sb, p->c_lo);
-        if (p->time_phases) CK(cudaEventRecord(p->ev[12], p->stream));
-        p->launches++;
-    }
+static b200_status allgather(b200_problem* p, void* buf, size_t bytes_per_rank) {
+    if (!p->ag_fn) { set_err("world_size > 1 but no collective registered (b200_comm_set)"); return B200_NCCL_ERROR; }
+    if (p->ag_fn(p->comm_ctx, buf, (uint64_t)bytes_per_rank, p->stream)) { set_err("allgather failed"); return B200_NCCL_ERROR; }
     return B200_OK;
 }
 
-// multi-rank: make every rank hold every chunk's Schur complement / fill and every separator's assembled blocks, and (after
-// back-substitution) every keyframe's step.  Collectives are supplied by the host (NCCL through torch.distributed or
-// ncclAllGather in a C++ host); payloads stay on the device.
-static b200_status exchange_reduced(b200_problem* p) {
-    if (!p->ag_fn) { set_err("world_size > 1 but no collective registered"); return B200_NCCL_ERROR; }
+// pack / unpack the level-1 source blocks of the group separators (D, A, S of the reduced system) for the all-gather
+__global__ void pack_groups_kernel(Dims dm, Level lv1, const double* Dred, const double* Ared, const double* Sred, double* pack, long long stride,
+                                   int g_first, int unpack, int skip_lo, int skip_hi) {
+    const int g = g_first + blockIdx.x;
+    if (g >= lv1.P - 1) return;
+    if (unpack && g >= skip_lo && g < skip_hi) return;   // own groups: already in place
+    const long long q = lv1.begin[g + 1] - 1;
+    const long long nD = (long long)dm.ntp * dm.ntp, nA = (long long)dm.ns1 * dm.ntp, nS = (long long)dm.ns1 * dm.ns1;
+    double* pk = pack + (long long)g * stride;
+    double* D = const_cast<double*>(Dred) + q * nD; double* A = const_cast<double*>(Ared) + q * nA; double* S = const_cast<double*>(Sred) + q * nS;
+    for (long long i = threadIdx.x; i < nD + nA + nS; i += blockDim.x) {
+        double* x = (i < nD) ? D + i : (i < nD + nA ? A + (i - nD) : S + (i - nD - nA));
+        if (unpack) *x = pk[i]; else pk[i] = *x;
+    }
+}
+
+// (H + lambda I) delta = -g : nested partitioned factorisation + back-substitution, all on p->stream
+static b200_status launch_solve(b200_problem* p, double lambda) {
+    CK(cudaMemsetAsync(p->sb.status, 0, sizeof(int), p->stream));
     const Dims& dm = p->dm;
-    const int per = p->P / p->world;
-    const size_t fsz = (size_t)2 * (dm.nc + dm.hmax) * dm.nc, ssz = (size_t)dm.hmax * dm.hmax;
-    if (p->ag_fn(p->comm_ctx, p->sb.Fchunk, sizeof(double) * fsz * per, p->stream)) { set_err("allgather failed"); return B200_NCCL_ERROR; }
-    if (p->ag_fn(p->comm_ctx, p->sb.Schunk, sizeof(double) * ssz * per, p->stream)) { set_err("allgather failed"); return B200_NCCL_ERROR; }
+    const int W = p->world, r = p->rank;
+    const size_t Fsz = (size_t)(dm.nc + dm.hmax) * dm.nc, Ssz = (size_t)dm.hmax * dm.hmax;
+    const dim3 tb(B200_SOLVE_THREADS);
+    const int nlev = (p->P > 1) ? ((p->P2 > 1) ? 2 : 1) : 0;
+    if (p->time_phases) CK(cudaEventRecord(p->ev[8], p->stream));
+    if (nlev >= 1) {
+        auto& l0 = p->levels[0];
+        B200_LAUNCH(level_sweep_kernel, dim3(l0.c_hi - l0.c_lo), tb, p->smem_sweep, p->stream, dm, l0.dev, p->sb, lambda, p->rmax, l0.c_lo);
+        p->launches++;
+        if (p->time_phases) CK(cudaEventRecord(p->ev[9], p->stream));
+        int red_lo = l0.c_lo, red_hi = std::min(l0.c_hi, l0.P - 1);
+        if (W > 1) {
+            // the separator that closes this rank's window needs the Schur complement / fill of the NEXT rank's first chunk
+            CK(cudaMemcpyAsync(p->d_stageS + (size_t)r * Ssz, l0.S + (size_t)l0.c_lo * Ssz, sizeof(double) * Ssz, cudaMemcpyDeviceToDevice, p->stream));
+            CK(cudaMemcpyAsync(p->d_stageF + (size_t)r * 2 * Fsz, l0.F + (size_t)l0.c_lo * 2 * Fsz, sizeof(double) * 2 * Fsz, cudaMemcpyDeviceToDevice, p->stream));
+            b200_status st = allgather(p, p->d_stageS, sizeof(double) * Ssz); if (st != B200_OK) return st;
+            st = allgather(p, p->d_stageF, sizeof(double) * 2 * Fsz); if (st != B200_OK) return st;
+            if (r + 1 < W) {
+                CK(cudaMemcpyAsync(l0.S + (size_t)l0.c_hi * Ssz, p->d_stageS + (size_t)(r + 1) * Ssz, sizeof(double) * Ssz, cudaMemcpyDeviceToDevice, p->stream));
+                CK(cudaMemcpyAsync(l0.F + (size_t)l0.c_hi * 2 * Fsz, p->d_stageF + (size_t)(r + 1) * 2 * Fsz, sizeof(double) * 2 * Fsz, cudaMemcpyDeviceToDevice, p->stream));
+            }
+            // the coupling block between the previous rank's closing separator and this rank's first separator comes
+            // from this rank's own first chunk: recompute that separator's reduced O here (D/A/S parts are unused)
+            if (r > 0) red_lo = l0.c_lo - 1;
+        }
+        if (red_hi > red_lo) {
+            B200_LAUNCH(level_reduce_kernel, dim3(red_hi - red_lo), dim3(256), 0, p->stream, dm, l0.dev, red_lo);
+            p->launches++;
+        }
+    }
+    const double *tD = p->d_D, *tO = p->d_O, *tA = p->d_A, *tS = p->d_S;
+    const int* tst = nullptr;
+    int tn = p->K;
+    if (nlev == 1) { auto& l0 = p->levels[0]; tD = l0.Dred; tO = l0.Ored; tA = l0.Ared; tS = l0.Sred; tst = l0.d_sep_st; tn = l0.P - 1; }
+    if (nlev == 2) {
+        auto& l0 = p->levels[0];
+        auto& l1 = p->levels[1];
+        B200_LAUNCH(level_sweep_kernel, dim3(l1.c_hi - l1.c_lo), tb, p->smem_sweep, p->stream, dm, l1.dev, p->sb, lambda, p->rmax, l1.c_lo);
+        p->launches++;
+        if (W > 1) {
+            const int gpr = l1.P / W;
+            b200_status st = allgather(p, l1.F, sizeof(double) * 2 * Fsz * gpr); if (st != B200_OK) return st;
+            st = allgather(p, l1.S, sizeof(double) * Ssz * gpr); if (st != B200_OK) return st;
+            B200_LAUNCH(pack_groups_kernel, dim3(gpr), dim3(256), 0, p->stream, dm, l1.dev, l0.Dred, l0.Ared, l0.Sred, p->d_pack,
+                        (long long)p->pack_doubles, l1.c_lo, 0, 0, 0);
+            st = allgather(p, p->d_pack, sizeof(double) * p->pack_doubles * gpr); if (st != B200_OK) return st;
+            B200_LAUNCH(pack_groups_kernel, dim3(l1.P), dim3(256), 0, p->stream, dm, l1.dev, l0.Dred, l0.Ared, l0.Sred, p->d_pack,
+                        (long long)p->pack_doubles, 0, 1, l1.c_lo, l1.c_hi);
+            p->launches += 2;
+        }
+        B200_LAUNCH(level_reduce_kernel, dim3(l1.P - 1), dim3(256), 0, p->stream, dm, l1.dev, 0);
+        p->launches++;
+        tD = l1.Dred; tO = l1.Ored; tA = l1.Ared; tS = l1.Sred; tst = l1.d_sep_st; tn = l1.P - 1;
+    }
+    if (p->time_phases) CK(cudaEventRecord(p->ev[10], p->stream));
+    B200_LAUNCH(top_solve_kernel, dim3(1), tb, p->smem_sweep, p->stream, dm, tD, tO, tA, tS, tst, tn, p->sb, lambda, p->rmax);
+    p->launches++;
+    if (p->time_phases) CK(cudaEventRecord(p->ev[11], p->stream));
+    if (nlev == 2) {
+        auto& l1 = p->levels[1];
+        B200_LAUNCH(level_backsub_kernel, dim3(l1.c_hi - l1.c_lo), tb, p->smem_sweep, p->stream, dm, l1.dev, p->sb, l1.c_lo);
+        p->launches++;
+    }
+    if (nlev >= 1) {
+        auto& l0 = p->levels[0];
+        B200_LAUNCH(level_backsub_kernel, dim3(l0.c_hi - l0.c_lo), tb, p->smem_sweep, p->stream, dm, l0.dev, p->sb, l0.c_lo);
+        p->launches++;
+    }
+    if (p->time_phases) CK(cudaEventRecord(p->ev[12], p->stream));
+    if (W > 1) {  // every rank needs every keyframe's step: the values are replicated
+        b200_status st = allgather(p, p->sb.delta, sizeof(double) * (size_t)p->Wk * dm.ntp); if (st != B200_OK) return st;
+    }
     return B200_OK;
 }
 
@@ -439,12 +610,6 @@ b200_status b200_lm_begin(b200_problem* p, const b200_lm_params* prm, double* in
     return B200_OK;
 }
 
-static b200_status gather_delta(b200_problem* p) {
-    if (p->world <= 1) return B200_OK;
-    // every rank back-substituted its own window; exchange the steps so the replicated values stay identical
-    return B200_NOT_IMPLEMENTED;
-}
-
 // == LevenbergMarquardtOptimizer::iterate() (gtsam @4.2: iterate / tryLambda / increaseLambda / decreaseLambda)
 b200_status b200_lm_iterate(b200_problem* p, b200_lm_state* state) {
     if (!p) return B200_BAD_ARG;
@@ -463,7 +628,6 @@ b200_status b200_lm_iterate(b200_problem* p, b200_lm_state* state) {
         if (p->time_phases) CK(cudaEventRecord(p->ev[2], p->stream));
         b200_status st = launch_solve(p, p->lambda);
         if (st != B200_OK) return st;
-        st = gather_delta(p); if (st != B200_OK) return st;
         if (p->time_phases) CK(cudaEventRecord(p->ev[3], p->stream));
         dim3 grid((p->max_inst + 127) / 128, p->n_slots);
         B200_LAUNCH(model_error_kernel, grid, dim3(128), 0, p->stream, p->d_slots, p->d_J, p->d_r, p->sb.delta, p->dm.ntp, p->sb.dstat, p->d_e2,
@@ -653,7 +817,7 @@ b200_status b200_comm_set(b200_problem* p, int32_t world_size, int32_t rank, b20
     if (!p || world_size < 1 || rank < 0 || rank >= world_size) return B200_BAD_ARG;
     CK(cudaSetDevice(p->device));
     p->world = world_size; p->rank = rank; p->ag_fn = ag; p->ar_fn = ar; p->comm_ctx = ctx;
-    return set_partition(p, p->P);
+    return set_partition(p, 0, 0);
 }
 
 // ------------------------------------------------------------------------------------------ parity / debug accessors

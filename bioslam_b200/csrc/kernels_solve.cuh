@@ -563,86 +563,93 @@ __device__ void cta_backsub(const Dims& dm, const SweepArgs& a, const double* co
 }
 
 // ------------------------------------------------------------------------------------------------- kernels
-struct ChunkPlan {            // device arrays describing the partition
-    const int* begin;         // [P+1] chunk c covers keyframes [begin[c], begin[c+1])
+// One level of the nested partition.  Level 0: nodes = keyframes (sources = assembled blocks, storage index = node index).
+// Level l+1: nodes = the separators of level l (sources = the reduced blocks written by level_reduce_kernel, storage index =
+// the separator's keyframe).  The nodes of a level are cut into P chunks; the last node of every chunk but the last is that
+// chunk's separator and becomes a node of the next level.
+struct Level {
+    const double *Dsrc, *Osrc, *Asrc, *Ssrc;  // per node: [ntp*ntp], [nc*nc], [ns1*ntp], [ns1*ns1]
+    const int* st;                            // storage (keyframe) index per node, nullptr = identity
+    const int* begin;                         // [P+1] chunk c covers nodes [begin[c], begin[c+1])
     int P;
+    double *F;                                // [P][2][(nc+hmax)*nc] fill buffers (ping-pong) of each chunk sweep
+    double *S;                                // [P][hmax*hmax] arrow Schur complement of each chunk sweep
+    double *Dred, *Ored, *Ared, *Sred;        // [P-1] reduced sources == next level's node sources
+    int* sep_st;                              // [P-1] storage index of separator c == next level's st
 };
 
 struct SolveBuffers {
-    const double *Dsrc, *Osrc, *Asrc, *Ssrc;  // assembled per-keyframe blocks
-    double *Lst, *Pst;                        // factors, per keyframe
-    double *Fchunk;                           // [P][2][(nc+hmax)*nc]
-    double *Schunk;                           // [P][hmax*hmax]
-    double *Dred, *Ored, *Ared, *Sred;        // reduced (separator) system sources, [P-1] each
+    double *Lst, *Pst;                        // factors, per storage index (keyframe)
     double *Ftop, *Stop;                      // scratch of the top-level sweep
-    int* sep_idx;                             // [P-1] separator keyframe of chunk c
-    double *delta, *dstat;                    // solution (internal order)
+    double *delta, *dstat;                    // solution (internal order), delta per storage index
     double* scal;                             // scalar outputs
     int* status;
 };
 
-// grid = number of chunks owned by this rank (chunk = c_first + blockIdx.x)
-__global__ void __launch_bounds__(B200_SOLVE_THREADS) chain_sweep_kernel(Dims dm, ChunkPlan pl, SolveBuffers sb, double lambda, int rmax,
-                                                                         int c_first) {
-    B200_DYN_SMEM(double, sm);
-    const int c = c_first + blockIdx.x;
-    const int P = pl.P;
-    const int kb = pl.begin[c], ke = pl.begin[c + 1];
-    SweepArgs a;
-    a.Dsrc = sb.Dsrc; a.Osrc = sb.Osrc; a.Asrc = sb.Asrc; a.Ssrc = sb.Ssrc;
+__device__ __forceinline__ void level_chunk_args(const Dims& dm, const Level& lv, const SolveBuffers& sb, int c, SweepArgs& a) {
+    const int kb = lv.begin[c], ke = lv.begin[c + 1];
+    a.Dsrc = lv.Dsrc; a.Osrc = lv.Osrc; a.Asrc = lv.Asrc; a.Ssrc = lv.Ssrc;
     a.src0 = kb;
-    a.n = (c < P - 1) ? (ke - 1 - kb) : (ke - kb);   // the last keyframe of every chunk but the last is a separator
-    a.st_idx = nullptr;
-    a.has_right = (c < P - 1);
-    a.Oleft = (c > 0) ? sb.Osrc + (long long)(kb - 1) * dm.nc * dm.nc : nullptr;
+    a.n = (c < lv.P - 1) ? (ke - 1 - kb) : (ke - kb);   // the last node of every chunk but the last is a separator
+    a.st_idx = lv.st ? lv.st + kb : nullptr;
+    a.has_right = (c < lv.P - 1);
+    a.Oleft = (c > 0) ? lv.Osrc + (long long)(kb - 1) * dm.nc * dm.nc : nullptr;
     a.h = dm.ns1 + ((c > 0) ? dm.nc : 0);
-    a.lambda = lambda;
     a.Lst = sb.Lst; a.Pst = sb.Pst;
-    a.F = sb.Fchunk + (long long)c * 2 * (dm.nc + dm.hmax) * dm.nc;
-    a.Sacc = sb.Schunk + (long long)c * dm.hmax * dm.hmax;
+    a.F = lv.F + (long long)c * 2 * (dm.nc + dm.hmax) * dm.nc;
+    a.Sacc = lv.S + (long long)c * dm.hmax * dm.hmax;
     a.status = sb.status;
+}
+
+// grid = number of chunks of this level owned by this rank (chunk = c_first + blockIdx.x)
+__global__ void __launch_bounds__(B200_SOLVE_THREADS) level_sweep_kernel(Dims dm, Level lv, SolveBuffers sb, double lambda, int rmax, int c_first) {
+    B200_DYN_SMEM(double, sm);
+    SweepArgs a;
+    level_chunk_args(dm, lv, sb, c_first + blockIdx.x, a);
+    a.lambda = lambda;
     a.rmax = rmax;
     cta_sweep(dm, a, sm);
 }
 
-// grid = P-1: Schur complements of chunk c (right side = separator c) and chunk c+1 (left side = separator c)
-__global__ void __launch_bounds__(256) reduced_assemble_kernel(Dims dm, ChunkPlan pl, SolveBuffers sb) {
-    const int c = blockIdx.x;
-    const int P = pl.P;
+// Schur complements onto separator c of this level: from chunk c (its right side) and chunk c+1 (its left side).
+// grid = separators handled (separator = c_first + blockIdx.x)
+__global__ void __launch_bounds__(256) level_reduce_kernel(Dims dm, Level lv, int c_first) {
+    const int c = c_first + blockIdx.x;
+    const int P = lv.P;
     const int ntp = dm.ntp, nl = dm.nl, nc = dm.nc, ns1 = dm.ns1, hmax = dm.hmax;
-    const long long q = pl.begin[c + 1] - 1;
+    const long long q = lv.begin[c + 1] - 1;                 // node index of the separator
     const long long Fsz = (long long)(nc + hmax) * nc;
-    const int n_c = (int)(q - pl.begin[c]);                 // interior nodes of chunk c
-    const double* Fc = sb.Fchunk + ((long long)c * 2 + (n_c & 1)) * Fsz;   // written by its last node
-    const double* Sn = sb.Schunk + (long long)(c + 1) * hmax * hmax;        // chunk c+1 (has left rows)
-    if (threadIdx.x == 0) sb.sep_idx[c] = (int)q;
-    double* Dr = sb.Dred + (long long)c * ntp * ntp;
-    const double* Dg = sb.Dsrc + q * ntp * ntp;
+    const int n_c = (int)(q - lv.begin[c]);                  // interior nodes of chunk c
+    const double* Fc = lv.F + ((long long)c * 2 + (n_c & 1)) * Fsz;   // written by its last node
+    const double* Sn = lv.S + (long long)(c + 1) * hmax * hmax;        // chunk c+1 (has left rows)
+    if (threadIdx.x == 0) lv.sep_st[c] = lv.st ? lv.st[q] : (int)q;
+    double* Dr = lv.Dred + (long long)c * ntp * ntp;
+    const double* Dg = lv.Dsrc + q * ntp * ntp;
     for (int e = threadIdx.x; e < ntp * ntp; e += blockDim.x) {
         const int r = e / ntp, col = e % ntp;
         double v = Dg[e];
         if (r >= nl && col >= nl) {
             const int i = r - nl, j = col - nl;
-            v -= Fc[(long long)i * nc + j];
+            if (n_c > 0) v -= Fc[(long long)i * nc + j];
             const int hi = i > j ? i : j, lo = i > j ? j : i;
             v += Sn[(long long)(ns1 + hi) * hmax + (ns1 + lo)];
         }
         Dr[e] = v;
     }
-    double* Ar = sb.Ared + (long long)c * ns1 * ntp;
-    const double* Ag = sb.Asrc + q * ns1 * ntp;
+    double* Ar = lv.Ared + (long long)c * ns1 * ntp;
+    const double* Ag = lv.Asrc + q * ns1 * ntp;
     for (int e = threadIdx.x; e < ns1 * ntp; e += blockDim.x) {
         const int ar = e / ntp, col = e % ntp;
         double v = Ag[e];
         if (col >= nl) {
-            v -= Fc[(long long)(nc + ar) * nc + (col - nl)];
+            if (n_c > 0) v -= Fc[(long long)(nc + ar) * nc + (col - nl)];
             v += Sn[(long long)(ns1 + (col - nl)) * hmax + ar];
         }
         Ar[e] = v;
     }
-    double* Sr = sb.Sred + (long long)c * ns1 * ns1;
-    const double* Sg = sb.Ssrc + q * ns1 * ns1;
-    const double* S0 = sb.Schunk;
+    double* Sr = lv.Sred + (long long)c * ns1 * ns1;
+    const double* Sg = lv.Ssrc + q * ns1 * ns1;
+    const double* S0 = lv.S;
     for (int e = threadIdx.x; e < ns1 * ns1; e += blockDim.x) {
         const int r = e / ns1, col = e % ns1;
         const int hi = r > col ? r : col, lo = r > col ? col : r;
@@ -652,9 +659,9 @@ __global__ void __launch_bounds__(256) reduced_assemble_kernel(Dims dm, ChunkPla
     }
     if (c < P - 2) {
         // coupling separator c -> separator c+1 through chunk c+1: -(Y_left X^T) of that chunk's last node
-        const int n_n = (int)(pl.begin[c + 2] - 1 - pl.begin[c + 1]);
-        const double* Fn = sb.Fchunk + ((long long)(c + 1) * 2 + (n_n & 1)) * Fsz;
-        double* Or = sb.Ored + (long long)c * nc * nc;
+        const int n_n = (int)(lv.begin[c + 2] - 1 - lv.begin[c + 1]);
+        const double* Fn = lv.F + ((long long)(c + 1) * 2 + (n_n & 1)) * Fsz;
+        double* Or = lv.Ored + (long long)c * nc * nc;
         for (int e = threadIdx.x; e < nc * nc; e += blockDim.x) {
             const int j = e / nc, i = e % nc;   // Or[j][i]: row = chain j of separator c+1, col = chain i of separator c
             Or[e] = -Fn[(long long)(nc + ns1 + i) * nc + j];
@@ -662,19 +669,15 @@ __global__ void __launch_bounds__(256) reduced_assemble_kernel(Dims dm, ChunkPla
     }
 }
 
-// single CTA: top-level sweep (over separators, or over all keyframes when P == 1), static solve, top-level back-substitution
-__global__ void __launch_bounds__(B200_SOLVE_THREADS) top_solve_kernel(Dims dm, ChunkPlan pl, SolveBuffers sb, double lambda, int rmax) {
+// single CTA: sweep over the n nodes of the top level, static solve, back-substitution of the top-level nodes
+__global__ void __launch_bounds__(B200_SOLVE_THREADS) top_solve_kernel(Dims dm, const double* Dsrc, const double* Osrc, const double* Asrc,
+                                                                       const double* Ssrc, const int* st, int n, SolveBuffers sb, double lambda,
+                                                                       int rmax) {
     B200_DYN_SMEM(double, sm);
-    const int P = pl.P;
-    const int ns = dm.ns, ns1 = dm.ns1, hmax = dm.hmax, nc = dm.nc;
+    const int ns = dm.ns, ns1 = dm.ns1, hmax = dm.hmax;
     SweepArgs a;
-    if (P == 1) {
-        a.Dsrc = sb.Dsrc; a.Osrc = sb.Osrc; a.Asrc = sb.Asrc; a.Ssrc = sb.Ssrc;
-        a.src0 = 0; a.n = dm.K; a.st_idx = nullptr;
-    } else {
-        a.Dsrc = sb.Dred; a.Osrc = sb.Ored; a.Asrc = sb.Ared; a.Ssrc = sb.Sred;
-        a.src0 = 0; a.n = P - 1; a.st_idx = sb.sep_idx;
-    }
+    a.Dsrc = Dsrc; a.Osrc = Osrc; a.Asrc = Asrc; a.Ssrc = Ssrc;
+    a.src0 = 0; a.n = n; a.st_idx = st;
     a.has_right = 0; a.Oleft = nullptr; a.h = ns1; a.lambda = lambda;
     a.Lst = sb.Lst; a.Pst = sb.Pst; a.F = sb.Ftop; a.Sacc = sb.Stop; a.status = sb.status; a.rmax = rmax;
     cta_sweep(dm, a, sm);
@@ -682,7 +685,7 @@ __global__ void __launch_bounds__(B200_SOLVE_THREADS) top_solve_kernel(Dims dm, 
     if (*sb.status != 0) return;
     // static system: (Sacc[0:ns,0:ns] + lambda I) ds = Sacc[ns][0:ns]; the rhs row rides along as a panel row
     double* coefA = sm + dm.sm_doubles - 512;   // hmax <= 512, lives at the end of the dynamic region
-    int lds = ns + (ns & 1); while ((lds & 3) != 2) lds += 2;
+    const int lds = static_lds(ns);
     double* Ss = sm;
     for (int e = threadIdx.x; e < ns1 * ns1; e += blockDim.x) {
         const int r = e / ns1, c = e % ns1;
@@ -699,30 +702,27 @@ __global__ void __launch_bounds__(B200_SOLVE_THREADS) top_solve_kernel(Dims dm, 
     if (threadIdx.x == 0) coefA[ns] = -1.0;
     __syncthreads();
     for (int i = threadIdx.x; i < ns; i += blockDim.x) sb.dstat[i] = coefA[i];
-    (void)nc;
     cta_backsub(dm, a, coefA, -1, sb.delta, sm);
 }
 
-// grid = chunks owned by this rank: back-substitution of interior keyframes
-__global__ void __launch_bounds__(B200_SOLVE_THREADS) chain_backsub_kernel(Dims dm, ChunkPlan pl, SolveBuffers sb, int c_first) {
+// grid = chunks of this level owned by this rank: back-substitution of the chunk's interior nodes
+__global__ void __launch_bounds__(B200_SOLVE_THREADS) level_backsub_kernel(Dims dm, Level lv, SolveBuffers sb, int c_first) {
     B200_DYN_SMEM(double, sm);
     const int c = c_first + blockIdx.x;
-    const int P = pl.P;
-    const int kb = pl.begin[c], ke = pl.begin[c + 1];
+    const int kb = lv.begin[c], ke = lv.begin[c + 1];
     const int ns = dm.ns, ns1 = dm.ns1, nc = dm.nc, nl = dm.nl, ntp = dm.ntp;
     SweepArgs a;
-    a.src0 = kb;
-    a.n = (c < P - 1) ? (ke - 1 - kb) : (ke - kb);
-    a.st_idx = nullptr;
-    a.has_right = (c < P - 1);
-    a.h = ns1 + ((c > 0) ? nc : 0);
-    a.Lst = sb.Lst; a.Pst = sb.Pst;
+    level_chunk_args(dm, lv, sb, c, a);
     double* coefA = sm + dm.sm_doubles - 512;
     for (int i = threadIdx.x; i < ns; i += blockDim.x) coefA[i] = sb.dstat[i];
     if (threadIdx.x == 0) coefA[ns] = -1.0;
-    if (c > 0) for (int j = threadIdx.x; j < nc; j += blockDim.x) coefA[ns1 + j] = sb.delta[(long long)(kb - 1) * ntp + nl + j];
+    if (c > 0) {
+        const long long lst = lv.st ? lv.st[kb - 1] : kb - 1;
+        for (int j = threadIdx.x; j < nc; j += blockDim.x) coefA[ns1 + j] = sb.delta[lst * ntp + nl + j];
+    }
     __syncthreads();
-    cta_backsub(dm, a, coefA, (long long)ke - 1, sb.delta, sm);
+    const long long rst = (c < lv.P - 1) ? (lv.st ? lv.st[ke - 1] : ke - 1) : -1;
+    cta_backsub(dm, a, coefA, rst, sb.delta, sm);
 }
 
 }  // namespace b200d

@@ -36,7 +36,7 @@ def load(path=None):
     L.b200_problem_destroy.restype = None
     L.b200_launch_count.restype = C.c_int64
     L.b200_launch_count.argtypes = [C.c_void_p]
-    for f in ("b200_time_value_dim", "b200_static_value_dim", "b200_time_tangent_dim", "b200_static_tangent_dim", "b200_get_chunks"):
+    for f in ("b200_time_value_dim", "b200_static_value_dim", "b200_time_tangent_dim", "b200_static_tangent_dim", "b200_get_chunks", "b200_get_groups"):
         getattr(L, f).argtypes = [C.c_void_p]
     L.b200_comm_set.argtypes = [C.c_void_p, C.c_int32, C.c_int32, ALLGATHER_FN, ALLREDUCE_FN, C.c_void_p]
     _libs[path] = L
@@ -49,7 +49,7 @@ D = abi.dptr
 class Problem:
     """One device-resident factor-graph problem == gtsam::LevenbergMarquardtOptimizer(graph, values, params) on a B200."""
 
-    def __init__(self, g: abi.GraphDesc, device=0, so_path=None, chunks=None):
+    def __init__(self, g: abi.GraphDesc, device=0, so_path=None, chunks=None, groups=None):
         self.L = load(so_path)
         self.g = g
         self.h = C.c_void_p()
@@ -57,8 +57,10 @@ class Problem:
         self._ck(self.L.b200_problem_create(C.byref(d), C.c_int32(device), C.byref(self.h)))
         self.K, self.nt, self.ns = g.K, g.nt, g.ns
         self.tvd, self.svd = g.time_value_dim, g.static_value_dim
-        if chunks is not None:
+        if chunks is not None and groups is None:
             self.set_chunks(chunks)
+        elif chunks is not None or groups is not None:
+            self.set_partition(chunks or 0, groups or 0)
 
     def _ck(self, st, ok=(abi.OK,)):
         if st not in ok:
@@ -79,9 +81,16 @@ class Problem:
     def set_chunks(self, n):
         self._ck(self.L.b200_set_chunks(self.h, C.c_int32(n)))
 
+    def set_partition(self, chunks, groups):
+        self._ck(self.L.b200_set_partition(self.h, C.c_int32(chunks), C.c_int32(groups)))
+
     @property
     def chunks(self):
         return self.L.b200_get_chunks(self.h)
+
+    @property
+    def groups(self):
+        return self.L.b200_get_groups(self.h)
 
     def set_values(self, tv, sv):
         tv = np.ascontiguousarray(tv, dtype=np.float64)

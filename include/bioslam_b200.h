@@ -262,6 +262,11 @@ b200_status b200_preintegrate(int32_t device, int32_t n_imu, int32_t n_samples, 
  * a reduced system on the separator keyframes.  Default: ~sqrt(2.2 K), at most one per SM; 1 = plain sequential sweep. */
 b200_status b200_set_chunks(b200_problem* p, int32_t n_chunks);
 int32_t b200_get_chunks(const b200_problem* p);
+/* nested partition: n_chunks chunks of keyframes; their n_chunks-1 separators are cut into n_groups groups that are
+ * eliminated in parallel as well, and only the n_groups-1 group separators are swept sequentially.  0 = choose from the
+ * built-in cost model, n_groups = 1 = two-level scheme. */
+b200_status b200_set_partition(b200_problem* p, int32_t n_chunks, int32_t n_groups);
+int32_t b200_get_groups(const b200_problem* p);
 
 /* ---------------------------------------------------------------- multi-GPU (time axis sharded, section 8(e))
  * One process per GPU, every rank creates the problem with the FULL description and the same values.  Rank r owns a

@@ -21,9 +21,8 @@ def test_header_declares_entry_points():
 
 def test_library_exports_every_declared_symbol():
     so = os.path.join(ROOT, "bioslam_b200", "libbioslam_b200.so")
-    if not os.path.exists(so):
-        import __graft_entry__ as ge
-        ge.build()
+    import __graft_entry__ as ge
+    ge.build()   # incremental (make): nvcc cross-compiles sm_100a without a GPU
     L = ctypes.CDLL(so)
     missing = [s for s in declared_symbols() if not hasattr(L, s)]
     assert not missing, missing

@@ -1,0 +1,74 @@
+"""-m "not gpu": the N > 1 path (time axis sharded over ranks) with world_size 2 and 3 over gloo on the CPU, each rank
+running the CUDA sources under the emulator (tests/cudaemu, TEST TOOL ONLY): every rank must end up with the same
+values as the single-rank run, and with the oracle's accept/reject sequence."""
+import os
+import subprocess
+import sys
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+WORKER = r'''
+import os, sys, json
+import numpy as np
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(here)r)
+import torch, torch.distributed as dist
+from bioslam_b200 import abi, lib, synth, sharding
+import graphs
+rank, world = int(sys.argv[1]), int(sys.argv[2])
+os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = sys.argv[3]
+dist.init_process_group("gloo", rank=rank, world_size=world)
+EMU = os.path.join(%(here)r, "cudaemu", "libbioslam_b200_emu.so")
+tr = synth.make_trial(seed=3, duration_s=float(sys.argv[4]))
+g, tv, sv = graphs.lower_body_graph(tr)
+tv, sv = graphs.perturbed_truth_values(tr, g, tv, sv)
+p = lib.Problem(g, so_path=EMU)
+sharding.attach(p, dist, None)
+p.set_values(tv, sv)
+out = {"chunks": p.chunks, "groups": p.groups}
+e0 = p.lm_begin(abi.LmParams.lower_body())
+trace = []
+for _ in range(3):
+    st = p.lm_iterate(); trace.append([st.error, st.lambda_, st.inner_trials, st.iterations])
+tv2, sv2 = p.get_values()
+np.savez(sys.argv[5] + f".rank{rank}.npz", e0=e0, trace=np.array(trace), tv=tv2, sv=sv2, chunks=p.chunks, groups=p.groups)
+dist.destroy_process_group()
+'''
+
+
+def run_world(world, seconds, tmp_path, port):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT, "here": HERE})
+    prefix = str(tmp_path / f"w{world}")
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), str(world), str(port), str(seconds), prefix]) for r in range(world)]
+    for pr in procs:
+        assert pr.wait(timeout=600) == 0
+    return [np.load(prefix + f".rank{r}.npz") for r in range(world)]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_lm_matches_single_rank_and_oracle(world, tmp_path, oracle_lib):
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "cudaemu")])
+    seconds = 4.0
+    outs = run_world(world, seconds, tmp_path, 29500 + world)
+    # all ranks agree bit-for-bit (replicated values, redundant top-level solve)
+    for o in outs[1:]:
+        assert np.array_equal(o["tv"], outs[0]["tv"]) and np.array_equal(o["sv"], outs[0]["sv"])
+        assert np.array_equal(o["trace"], outs[0]["trace"])
+    assert int(outs[0]["groups"]) % world == 0 and int(outs[0]["chunks"]) % world == 0
+    # oracle on the same inputs
+    from bioslam_b200 import abi, synth
+    from oracle import pyoracle as po
+    import graphs
+    tr = synth.make_trial(seed=3, duration_s=seconds)
+    g, tv, sv = graphs.lower_body_graph(tr)
+    tv, sv = graphs.perturbed_truth_values(tr, g, tv, sv)
+    o = po.OracleProblem(g, threads=4); o.set_values(tv, sv)
+    e0 = o.lm_begin(abi.LmParams.lower_body())
+    assert abs(e0 - float(outs[0]["e0"])) <= 1e-11 * e0
+    for row in outs[0]["trace"]:
+        st = o.lm_iterate()
+        assert st.inner_trials == int(row[2]) and st.iterations == int(row[3])
+        assert abs(st.error - row[0]) <= 5e-3 * st.error
