@@ -100,8 +100,16 @@ struct b200_problem {
     void* comm_ctx = nullptr;
 };
 
+// B200_POISON=1 (debugging): fill every allocation with 0xFF bytes (NaN doubles / -1 ints) so that a read of memory the
+// library never wrote shows up in the results instead of depending on what the allocator handed out.
 template <class T>
-static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, (n ? n : 1) * sizeof(T)); }
+static cudaError_t dalloc(T** p, size_t n) {
+    static const bool poison = std::getenv("B200_POISON") != nullptr;
+    cudaError_t e = cudaMalloc((void**)p, (n ? n : 1) * sizeof(T));
+    if (e == cudaSuccess && poison) e = cudaMemset(*p, 0xFF, (n ? n : 1) * sizeof(T));
+    if (e == cudaSuccess && poison) e = cudaDeviceSynchronize();
+    return e;
+}
 
 static int choose_ld(int ntp) { int ld = ntp; while ((ld & 3) != 2) ld++; return ld; }
 
@@ -228,15 +236,17 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
     CK(dalloc(&p->sb.Ftop, (size_t)2 * (dm.nc + dm.hmax) * dm.nc)); CK(dalloc(&p->sb.Stop, (size_t)dm.hmax * dm.hmax));
     CK(cudaMallocHost((void**)&p->h_scal, (SC_COUNT + 2) * sizeof(double)));
     // uploads
-    CK(cudaMemcpy(p->d_slots, p->hslots.data(), sizeof(DevSlot) * p->n_slots, cudaMemcpyHostToDevice));
+    // every upload goes through p->stream (a non-blocking stream is not ordered against legacy-stream copies)
+    CK(cudaMemcpyAsync(p->d_slots, p->hslots.data(), sizeof(DevSlot) * p->n_slots, cudaMemcpyHostToDevice, p->stream));
     std::vector<DevVar> tvars(p->ntv), svars(std::max(p->nsv, 1));
     for (int v = 0; v < p->ntv; v++) tvars[v] = {p->tvtype[v], p->tv_valoff[v], p->tv_tan_int[v]};
     for (int v = 0; v < p->nsv; v++) svars[v] = {p->svtype[v], p->sv_valoff[v], p->sv_tan[v]};
-    CK(cudaMemcpy(p->d_tvars, tvars.data(), sizeof(DevVar) * p->ntv, cudaMemcpyHostToDevice));
-    if (p->nsv) CK(cudaMemcpy(p->d_svars, svars.data(), sizeof(DevVar) * p->nsv, cudaMemcpyHostToDevice));
-    CK(cudaMemset(p->d_cst, 0, sizeof(double) * std::max(p->cstride, 1) * Kld));
+    CK(cudaMemcpyAsync(p->d_tvars, tvars.data(), sizeof(DevVar) * p->ntv, cudaMemcpyHostToDevice, p->stream));
+    if (p->nsv) CK(cudaMemcpyAsync(p->d_svars, svars.data(), sizeof(DevVar) * p->nsv, cudaMemcpyHostToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    CK(cudaMemsetAsync(p->d_cst, 0, sizeof(double) * std::max(p->cstride, 1) * Kld, p->stream));  // same stream as the transpose below (a legacy-stream memset would race with it)
     if (p->cstride > 0 && d->consts) {
-        CK(cudaMemcpy(p->d_stage, d->consts, sizeof(double) * K * p->cstride, cudaMemcpyHostToDevice));
+        CK(cudaMemcpyAsync(p->d_stage, d->consts, sizeof(double) * K * p->cstride, cudaMemcpyHostToDevice, p->stream));
         const long long n = (long long)K * p->cstride;
         B200_LAUNCH(transpose_in_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, p->stream, p->d_stage, p->K, p->cstride, Kld, p->d_cst);
         p->launches++;
@@ -377,9 +387,10 @@ static b200_status set_partition(b200_problem* p, int P1, int P2) {
         }
         const size_t P = l.P;
         CK(dalloc(&l.d_begin, P + 1)); CK(dalloc(&l.d_sep_st, P)); CK(dalloc(&l.d_st, (size_t)std::max(l.n_nodes, 1)));
-        CK(cudaMemcpy(l.d_begin, l.begin.data(), sizeof(int) * (P + 1), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(l.d_sep_st, l.sep_st.data(), sizeof(int) * l.sep_st.size(), cudaMemcpyHostToDevice));
-        if (!l.st.empty()) CK(cudaMemcpy(l.d_st, l.st.data(), sizeof(int) * l.st.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpyAsync(l.d_begin, l.begin.data(), sizeof(int) * (P + 1), cudaMemcpyHostToDevice, p->stream));
+        CK(cudaMemcpyAsync(l.d_sep_st, l.sep_st.data(), sizeof(int) * l.sep_st.size(), cudaMemcpyHostToDevice, p->stream));
+        if (!l.st.empty()) CK(cudaMemcpyAsync(l.d_st, l.st.data(), sizeof(int) * l.st.size(), cudaMemcpyHostToDevice, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
         CK(dalloc(&l.F, (P + 1) * 2 * Fsz)); CK(dalloc(&l.S, (P + 1) * Ssz));
         CK(dalloc(&l.Dred, P * dm.ntp * dm.ntp)); CK(dalloc(&l.Ored, P * dm.nc * dm.nc));
         CK(dalloc(&l.Ared, P * dm.ns1 * dm.ntp)); CK(dalloc(&l.Sred, P * dm.ns1 * dm.ns1));
