@@ -311,7 +311,7 @@ static double partition_cost(int K, int P1, int P2, int sms) {
 // P2-1 group separators are eliminated sequentially by the single top-level CTA.  Chunks hold >= 2 nodes.
 static b200_status set_partition(b200_problem* p, int P1, int P2) {
     const Dims& dm = p->dm;
-    const int K = p->K, W = p->world, sms = 148;
+    const int K = p->K, W = p->world, sms = 148 * p->world;   // one chunk CTA per SM and wave, on every rank
     p->Wk = (K + W - 1) / W;
     if ((long long)(W - 1) * p->Wk >= K || K - (W - 1) * p->Wk < 3) { set_err("too few keyframes for this many ranks"); return B200_BAD_ARG; }
     const int max_p1 = std::max(1, K / 3);
