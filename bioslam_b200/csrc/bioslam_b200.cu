@@ -2,7 +2,9 @@
 // Host-side orchestration only; all arithmetic runs in the kernels of kernels_*.cuh.  There is NO CPU fallback: every
 // entry point that computes launches CUDA kernels on the problem's device and reports CUDA errors as B200_CUDA_ERROR.
 #include <algorithm>
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 #include "kernels_preint.cuh"
 #include "kernels_solve.cuh"
@@ -82,6 +84,8 @@ struct b200_problem {
     double *d_stageS = nullptr, *d_stageF = nullptr, *d_pack = nullptr;
     size_t pack_doubles = 0;
     size_t smem_sweep = 0, smem_asm[2] = {0, 0};
+    AsmPlan asm_plan{};
+    AsmItem* d_asm_items = nullptr; AsmTerm* d_asm_terms = nullptr; AsmBlock* d_asm_blocks[2] = {nullptr, nullptr};
     double* h_scal = nullptr;  // pinned: SC_COUNT doubles + status
     // LM state
     b200_lm_params lm{};
@@ -113,6 +117,88 @@ static cudaError_t dalloc(T** p, size_t n) {
 
 static int choose_ld(int ntp) { int ld = ntp; while ((ld & 3) != 2) ld++; return ld; }
 
+// assembly plan: see kernels_assemble.cuh
+static b200_status build_asm_plan(b200_problem* p, size_t smem_cap) {
+    const Dims& dm = p->dm;
+    std::vector<AsmItem> items;
+    std::vector<std::vector<int>> item_of(p->n_slots, std::vector<int>(2, -1));
+    int off = 0;
+    for (int si = 0; si < p->n_slots; si++) {
+        const DevSlot& s = p->hslots[si];
+        bool k1 = false;
+        for (int v = 0; v < s.nvars; v++) k1 |= (s.var_kind[v] == B200_AT_K1);
+        for (int sel = 0; sel < (k1 ? 2 : 1); sel++) {
+            item_of[si][sel] = (int)items.size();
+            items.push_back({si, sel, off});
+            off += s.rows * (s.cols + 1);
+        }
+    }
+    if (items.size() > 256) { set_err("more than 256 factor instances per keyframe"); return B200_NOT_IMPLEMENTED; }
+    struct Key { int half, which, row, col; bool operator<(const Key& o) const { return std::tie(half, which, row, col) < std::tie(o.half, o.which, o.row, o.col); } };
+    struct Blk { int da, db; std::vector<AsmTerm> terms; };
+    std::map<Key, Blk> blocks;
+    auto add = [&](int half, int which, int row, int col, int da, int db, AsmTerm t) {
+        Blk& b = blocks[Key{half, which, row, col}];
+        b.da = da; b.db = db; b.terms.push_back(t);
+    };
+    for (int si = 0; si < p->n_slots; si++) {
+        const DevSlot& s = p->hslots[si];
+        for (int sel = 0; sel < 2; sel++) {
+            const int it = item_of[si][sel];
+            if (it < 0) continue;
+            for (int a = 0; a < s.nvars; a++) {
+                const int kda = s.var_kind[a];
+                const bool a_static = kda == B200_AT_STATIC;
+                const bool a_atk = (kda == B200_AT_K && sel == 0) || (kda == B200_AT_K1 && sel == 1);
+                const bool a_atk1 = (kda == B200_AT_K1 && sel == 0);
+                const int ta = s.tan_off[a], da = s.tan_dim[a], ca = s.col_off[a];
+                if (a_atk) add(1, 1, dm.ns, ta, 1, da, AsmTerm{it, ca, -1, 2});                       // Ax rhs row: -g_k
+                if (a_static && sel == 0) {
+                    add(0, 1, ta, dm.ns, da, 1, AsmTerm{it, ca, -1, 1});                               // Sx rhs column
+                    add(0, 1, dm.ns, ta, 1, da, AsmTerm{it, ca, -1, 2});                               // Sx rhs row
+                }
+                for (int b = 0; b < s.nvars; b++) {
+                    const int kdb = s.var_kind[b];
+                    const bool b_static = kdb == B200_AT_STATIC;
+                    const bool b_atk = (kdb == B200_AT_K && sel == 0) || (kdb == B200_AT_K1 && sel == 1);
+                    const int tb = s.tan_off[b], db = s.tan_dim[b], cb = s.col_off[b];
+                    if (a_atk && b_atk) add(0, 0, ta, tb, da, db, AsmTerm{it, ca, cb, 0});
+                    else if (a_static && b_static && sel == 0) add(0, 1, ta, tb, da, db, AsmTerm{it, ca, cb, 0});
+                    if (a_atk1 && b_atk) add(1, 0, ta - dm.nl, tb - dm.nl, da, db, AsmTerm{it, ca, cb, 0});
+                    else if (a_static && b_atk) add(1, 1, ta, tb, da, db, AsmTerm{it, ca, cb, 0});
+                }
+            }
+        }
+    }
+    std::vector<AsmTerm> terms;
+    std::vector<AsmBlock> hb[2];
+    for (auto& kv : blocks) {
+        AsmBlock b{kv.first.which, kv.first.row, kv.first.col, kv.second.da, kv.second.db, (int)terms.size(), 0};
+        terms.insert(terms.end(), kv.second.terms.begin(), kv.second.terms.end());
+        b.term_end = (int)terms.size();
+        if (b.da * b.db > 64) { set_err("internal: destination block larger than 64 entries"); return B200_NOT_IMPLEMENTED; }
+        hb[kv.first.half].push_back(b);
+    }
+    const size_t base0 = sizeof(double) * ((size_t)dm.ntp * dm.ntp + (size_t)dm.ns1 * dm.ns1);
+    const size_t base1 = sizeof(double) * ((size_t)dm.nc * dm.nc + (size_t)dm.ns1 * dm.ntp);
+    p->smem_asm[0] = base0 + sizeof(double) * off;
+    p->smem_asm[1] = base1 + sizeof(double) * off;
+    if (std::max(p->smem_asm[0], p->smem_asm[1]) > smem_cap) { set_err("time block + staged Jacobians do not fit in shared memory"); return B200_NOT_IMPLEMENTED; }
+    CK(dalloc(&p->d_asm_items, items.size())); CK(dalloc(&p->d_asm_terms, terms.size()));
+    CK(cudaMemcpyAsync(p->d_asm_items, items.data(), sizeof(AsmItem) * items.size(), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaMemcpyAsync(p->d_asm_terms, terms.data(), sizeof(AsmTerm) * terms.size(), cudaMemcpyHostToDevice, p->stream));
+    for (int h = 0; h < 2; h++) {
+        CK(dalloc(&p->d_asm_blocks[h], hb[h].size()));
+        CK(cudaMemcpyAsync(p->d_asm_blocks[h], hb[h].data(), sizeof(AsmBlock) * hb[h].size(), cudaMemcpyHostToDevice, p->stream));
+    }
+    CK(cudaStreamSynchronize(p->stream));
+    AsmPlan& pl = p->asm_plan;
+    pl.items = p->d_asm_items; pl.n_items = (int)items.size(); pl.terms = p->d_asm_terms;
+    for (int h = 0; h < 2; h++) { pl.blocks[h] = p->d_asm_blocks[h]; pl.n_blocks[h] = (int)hb[h].size(); }
+    pl.stage_doubles = off;
+    return B200_OK;
+}
+
 static void free_levels(b200_problem* p) {
     for (auto& l : p->levels) {
         void* q[] = {l.d_begin, l.d_st, l.d_sep_st, l.F, l.S, l.Dred, l.Ored, l.Ared, l.Sred};
@@ -130,7 +216,7 @@ void b200_problem_destroy(b200_problem* p) {
     cudaSetDevice(p->device);
     void* ptrs[] = {p->d_tv, p->d_tv_try, p->d_sv, p->d_sv_try, p->d_cst, p->d_stage, p->d_slots, p->d_tvars, p->d_svars, p->d_J, p->d_r,
                     p->d_e, p->d_e2, p->d_D, p->d_O, p->d_A, p->d_S, p->sb.Lst, p->sb.Pst, p->sb.Ftop, p->sb.Stop, p->sb.delta, p->sb.dstat,
-                    p->sb.scal, p->sb.status, p->d_stageS, p->d_stageF, p->d_pack};
+                    p->sb.scal, p->sb.status, p->d_stageS, p->d_stageF, p->d_pack, p->d_asm_items, p->d_asm_terms, p->d_asm_blocks[0], p->d_asm_blocks[1]};
     for (void* q : ptrs) if (q) cudaFree(q);
     free_levels(p);
     if (p->h_scal) cudaFreeHost(p->h_scal);
@@ -264,8 +350,11 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
         CK(cudaFuncGetAttributes(&fa, assemble_kernel)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
     }
     const size_t smem_cap = (227 * 1024 - static_smem - 1024) & ~(size_t)15;  // dynamic budget next to the kernels' static arrays
-    if (std::max(p->smem_asm[0], p->smem_asm[1]) > smem_cap || sizeof(double) * (size_t)dm.ntp * dm.ld > smem_cap)
-        return fail("time block does not fit in shared memory", B200_NOT_IMPLEMENTED);
+    {
+        b200_status ast = build_asm_plan(p, smem_cap);
+        if (ast != B200_OK) { b200_problem_destroy(p); return ast; }
+        if (sizeof(double) * (size_t)dm.ntp * dm.ld > smem_cap) return fail("time block does not fit in shared memory", B200_NOT_IMPLEMENTED);
+    }
     {
         long long rows_fit = (long long)(smem_cap / sizeof(double)) / dm.ld - B200_NB - 32;
         const int rn_max = dm.nc + dm.hmax;
@@ -476,7 +565,7 @@ static void launch_linearize(b200_problem* p) {
     // one extra keyframe on the left: its O block (coupling k_lo-1 -> k_lo) is the left-separator coupling of this window
     const int ka = std::max(p->k_lo - 1, 0);
     B200_LAUNCH(assemble_kernel, dim3(p->k_hi - ka, 2), dim3(256), std::max(p->smem_asm[0], p->smem_asm[1]), p->stream, p->dm,
-                p->d_slots, p->n_slots, p->d_J, p->d_r, (const int*)nullptr, ka, 0, p->K, p->d_D, p->d_O, p->d_A, p->d_S);
+                p->d_slots, p->asm_plan, p->d_J, p->d_r, ka, 0, p->K, p->d_D, p->d_O, p->d_A, p->d_S);
     p->launches++;
 }
 

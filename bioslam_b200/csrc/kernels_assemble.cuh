@@ -18,89 +18,92 @@ struct Dims {
     int sm_doubles;                // dynamic shared memory of the solver kernels, in doubles
 };
 
-// which (slot, instance) pairs touch keyframe k: instance k (variables AT_K, AT_STATIC, and the K1 x K cross block) and
-// instance k-1 (its AT_K1 variables live at keyframe k).
-__global__ void __launch_bounds__(256) assemble_kernel(Dims dm, const DevSlot* __restrict__ slots, int n_slots,
+// Assembly plan, built once per problem on the host (bioslam_b200.cu: build_asm_plan):
+//   items  = the (slot, sel) factor instances that touch keyframe k: sel 0 = instance k (its AT_K / static variables and the
+//            K1 x K cross block), sel 1 = instance k-1 (its AT_K1 variables live at keyframe k);
+//   blocks = destination sub-blocks (one per pair of variables) of D / Sx (half 0) or O / Ax (half 1), each with the ordered
+//            list of terms J[:, a]^T J[:, b] (or -J[:, a]^T r for the gradient rows) that sum into it.
+// One warp owns one destination block at a time and accumulates all of its terms in registers, in table order: no
+// atomics, no barriers between factors, deterministic.
+struct AsmItem { int slot, sel, stage_off; };
+struct AsmTerm { int item, ca, cb, mode; };     // mode 0: J_a^T J_b ; 1: -J_a^T r (column block) ; 2: -(J_a^T r)^T (row block)
+struct AsmBlock { int which, row, col, da, db, term_begin, term_end; };   // which: 0 = B1 (D or O), 1 = B2 (Sx or Ax)
+struct AsmPlan {
+    const AsmItem* items; int n_items;
+    const AsmTerm* terms;
+    const AsmBlock* blocks[2]; int n_blocks[2];
+    int stage_doubles;
+};
+
+__global__ void __launch_bounds__(256) assemble_kernel(Dims dm, const DevSlot* __restrict__ slots, AsmPlan pl,
                                                        const double* __restrict__ Jbuf, const double* __restrict__ rbuf,
-                                                       const int* __restrict__ klist, int k_first, int win_lo, int win_hi,
+                                                       int k_first, int win_lo, int win_hi,
                                                        double* __restrict__ Dsrc, double* __restrict__ Osrc, double* __restrict__ Asrc,
                                                        double* __restrict__ Ssrc) {
     B200_DYN_SMEM(double, sm);
-    const int k = klist ? klist[blockIdx.x] : k_first + (int)blockIdx.x;
+    const int k = k_first + (int)blockIdx.x;
     const int half = blockIdx.y;
-    const int ntp = dm.ntp, nc = dm.nc, nl = dm.nl, ns = dm.ns, ns1 = dm.ns1;
+    const int ntp = dm.ntp, nc = dm.nc, ns1 = dm.ns1;
     const int n1 = half == 0 ? ntp * ntp : nc * nc;
     const int n2 = half == 0 ? ns1 * ns1 : ns1 * ntp;
+    const int ld1 = half == 0 ? ntp : nc, ld2 = half == 0 ? ns1 : ntp;
     double* B1 = sm;            // D or O
     double* B2 = sm + n1;       // Sx or Ax
-    double* Js = B2 + n2;       // staged Jacobian (<= 15*30) followed by residual (<= 15)
-    __shared__ unsigned char colvar[B200_MAX_FACTOR_COLS + 1];
+    double* St = B2 + n2;       // staged Jacobians (rows*cols) + residuals (rows) of every item
+    __shared__ unsigned char valid[256];
     for (int i = threadIdx.x; i < n1 + n2; i += blockDim.x) sm[i] = 0.0;
-    if (half == 0 && ntp > dm.nt && threadIdx.x == 0) B1[(ntp - 1) * ntp + ntp - 1] = 1.0;  // padding variable: identity
+    // ---- which items exist at this keyframe; stage their Jacobians (independent strided loads, issued in bulk)
+    for (int it = threadIdx.x; it < pl.n_items; it += blockDim.x) {
+        const AsmItem im = pl.items[it];
+        const DevSlot& s = slots[im.slot];
+        const int ki = k - im.sel;
+        valid[it] = (ki >= s.k_begin && ki < s.k_end && ki >= win_lo && ki < win_hi) ? 1 : 0;
+    }
     __syncthreads();
-    if (half == 0 && ntp > dm.nt && threadIdx.x == 0) B1[(ntp - 1) * ntp + ntp - 1] = 1.0;
-    for (int si = 0; si < n_slots; si++) {
-        const DevSlot& s = slots[si];
-        bool has_k1 = false;
-        for (int v = 0; v < s.nvars; v++) has_k1 |= (s.var_kind[v] == B200_AT_K1);
-        for (int sel = 0; sel < 2; sel++) {
-            const int ki = k - sel;
-            if (sel == 1 && !has_k1) continue;
-            if (ki < s.k_begin || ki >= s.k_end) continue;
-            if (ki < win_lo || ki >= win_hi) continue;  // factor instance owned by another rank's window
+    if (half == 0 && ntp > dm.nt && threadIdx.x == 0) B1[(ntp - 1) * ntp + ntp - 1] = 1.0;  // padding variable: identity
+    for (int it = 0; it < pl.n_items; it++) {
+        if (!valid[it]) continue;
+        const AsmItem im = pl.items[it];
+        const DevSlot& s = slots[im.slot];
+        const long long inst = (k - im.sel) - s.k_begin;
+        const int nj = s.rows * s.cols;
+        double* dst = St + im.stage_off;
+        const double* jg = Jbuf + s.J_off + inst * nj;
+        const double* rg = rbuf + s.r_off + inst * s.rows;
+        for (int i = threadIdx.x; i < nj; i += blockDim.x) cp_async8(dst + i, jg + i);
+        if (threadIdx.x < (unsigned)s.rows) cp_async8(dst + nj + threadIdx.x, rg + threadIdx.x);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    // ---- one warp per destination block
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const AsmBlock* blocks = pl.blocks[half];
+    for (int b = warp; b < pl.n_blocks[half]; b += nwarps) {
+        const AsmBlock bk = blocks[b];
+        const int ne = bk.da * bk.db;
+        double acc0 = 0.0, acc1 = 0.0;
+        const int e0 = lane, e1 = lane + 32;
+        const int ia0 = e0 / bk.db, ib0 = e0 - ia0 * bk.db, ia1 = e1 / bk.db, ib1 = e1 - ia1 * bk.db;
+        for (int t = bk.term_begin; t < bk.term_end; t++) {
+            const AsmTerm tm = pl.terms[t];
+            if (!valid[tm.item]) continue;
+            const AsmItem im = pl.items[tm.item];
+            const DevSlot& s = slots[im.slot];
             const int rows = s.rows, cols = s.cols;
-            const long long n = s.n_inst, inst = ki - s.k_begin;
-            __syncthreads();
-            for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) Js[i] = Jbuf[s.J_off + (long long)i * n + inst];
-            for (int i = threadIdx.x; i < rows; i += blockDim.x) Js[rows * cols + i] = rbuf[s.r_off + (long long)i * n + inst];
-            if (threadIdx.x < (unsigned)cols) {
-                int v = 0;
-                while (v + 1 < s.nvars && (int)threadIdx.x >= s.col_off[v + 1]) v++;
-                colvar[threadIdx.x] = (unsigned char)v;
-            }
-            __syncthreads();
+            const double* Js = St + im.stage_off;
             const double* rr = Js + rows * cols;
-            const int ne = cols * (cols + 1);
-            for (int e = threadIdx.x; e < ne; e += blockDim.x) {
-                const int ca = e / (cols + 1), cb = e % (cols + 1);
-                const int va = colvar[ca];
-                const int kda = s.var_kind[va];
-                const bool a_static = kda == B200_AT_STATIC;
-                const bool a_atk = (kda == B200_AT_K && sel == 0) || (kda == B200_AT_K1 && sel == 1);
-                const bool a_atk1 = (kda == B200_AT_K1 && sel == 0);
-                const int ta = s.tan_off[va] + (ca - s.col_off[va]);
-                if (cb == cols) {  // gradient column: -J^T r
-                    if (half == 1 && a_atk) {
-                        double acc = 0;
-                        for (int i = 0; i < rows; i++) acc += Js[i * cols + ca] * rr[i];
-                        B2[ns * ntp + ta] -= acc;
-                    } else if (half == 0 && a_static && sel == 0) {
-                        double acc = 0;
-                        for (int i = 0; i < rows; i++) acc += Js[i * cols + ca] * rr[i];
-                        B2[ta * ns1 + ns] -= acc;
-                        B2[ns * ns1 + ta] -= acc;
-                    }
-                    continue;
-                }
-                const int vb = colvar[cb];
-                const int kdb = s.var_kind[vb];
-                const bool b_static = kdb == B200_AT_STATIC;
-                const bool b_atk = (kdb == B200_AT_K && sel == 0) || (kdb == B200_AT_K1 && sel == 1);
-                const int tb = s.tan_off[vb] + (cb - s.col_off[vb]);
-                double* dst = nullptr;
-                if (half == 0) {
-                    if (a_atk && b_atk) dst = B1 + ta * ntp + tb;
-                    else if (a_static && b_static && sel == 0) dst = B2 + ta * ns1 + tb;
-                } else {
-                    if (a_atk1 && b_atk) dst = B1 + (ta - nl) * nc + (tb - nl);
-                    else if (a_static && b_atk) dst = B2 + ta * ntp + tb;
-                }
-                if (!dst) continue;
-                double acc = 0;
-                for (int i = 0; i < rows; i++) acc += Js[i * cols + ca] * Js[i * cols + cb];
-                *dst += acc;
+            if (tm.mode == 0) {
+                if (e0 < ne) for (int r = 0; r < rows; r++) acc0 = fma(Js[r * cols + tm.ca + ia0], Js[r * cols + tm.cb + ib0], acc0);
+                if (e1 < ne) for (int r = 0; r < rows; r++) acc1 = fma(Js[r * cols + tm.ca + ia1], Js[r * cols + tm.cb + ib1], acc1);
+            } else {
+                const int j0 = tm.ca + (tm.mode == 1 ? ia0 : ib0);
+                if (e0 < ne) for (int r = 0; r < rows; r++) acc0 = fma(-Js[r * cols + j0], rr[r], acc0);
             }
         }
+        double* B = bk.which == 0 ? B1 : B2;
+        const int ld = bk.which == 0 ? ld1 : ld2;
+        if (e0 < ne) B[(bk.row + ia0) * ld + bk.col + ib0] = acc0;
+        if (e1 < ne) B[(bk.row + ia1) * ld + bk.col + ib1] = acc1;
     }
     __syncthreads();
     double* g1 = half == 0 ? Dsrc + (long long)k * ntp * ntp : Osrc + (long long)k * nc * nc;

@@ -2,8 +2,8 @@
 // deterministic cost reduction, linear-model error (GaussianFactorGraph::error(delta)) and retraction.
 //
 // Layout in HBM (DESIGN.md "data layout"): keyframe-major SoA.  Time-variable values tv[component][Kld], per-keyframe
-// constants cst[component][Kld], whitened Jacobians Jbuf[slot][row*cols+col][n_inst] and residuals rbuf[slot][row][n_inst]:
-// consecutive lanes (consecutive keyframes of one factor slot) touch consecutive addresses.
+// constants cst[component][Kld]: consecutive lanes (consecutive keyframes of one factor slot) touch consecutive addresses.
+// Whitened Jacobians / residuals are per-instance records Jbuf[slot][inst][rows*cols], rbuf[slot][inst][rows].
 #pragma once
 #include "factors.cuh"
 
@@ -67,10 +67,13 @@ __global__ void __launch_bounds__(128) linearize_kernel(const DevSlot* __restric
     for (int i = 0; i < s.rows; i++) e += r[i] * r[i];
     ebuf[s.e_off + inst] = 0.5 * e;
     if (WJ) {
-        const long long n = s.n_inst;
-        for (int i = 0; i < s.rows; i++) rbuf[s.r_off + (long long)i * n + inst] = r[i];
+        // per-instance records (rows*cols then rows): the consumer (assemble_kernel) copies one keyframe's records as
+        // contiguous chunks; each thread streams its own record, full 32-byte sectors
+        double* rp = rbuf + s.r_off + (long long)inst * s.rows;
+        for (int i = 0; i < s.rows; i++) rp[i] = r[i];
         const int ne = s.rows * s.cols;
-        for (int i = 0; i < ne; i++) Jbuf[s.J_off + (long long)i * n + inst] = J[i];
+        double* jp = Jbuf + s.J_off + (long long)inst * ne;
+        for (int i = 0; i < ne; i++) jp[i] = J[i];
     }
 }
 
@@ -105,11 +108,12 @@ __global__ void __launch_bounds__(128) model_error_kernel(const DevSlot* __restr
                                 : dtime + (long long)(k + (s.var_kind[v] == B200_AT_K1 ? 1 : 0)) * ntp + s.tan_off[v];
         for (int j = 0; j < s.tan_dim[v]; j++) dl[s.col_off[v] + j] = src[j];
     }
-    const long long n = s.n_inst;
+    const double* rp = rbuf + s.r_off + (long long)inst * s.rows;
+    const double* jp = Jbuf + s.J_off + (long long)inst * s.rows * s.cols;
     double e = 0.0;
     for (int i = 0; i < s.rows; i++) {
-        double a = rbuf[s.r_off + (long long)i * n + inst];
-        for (int c = 0; c < s.cols; c++) a += Jbuf[s.J_off + (long long)(i * s.cols + c) * n + inst] * dl[c];
+        double a = rp[i];
+        for (int c = 0; c < s.cols; c++) a += jp[i * s.cols + c] * dl[c];
         e += a * a;
     }
     ebuf[s.e_off + inst] = 0.5 * e;
