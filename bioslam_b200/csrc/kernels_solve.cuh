@@ -24,13 +24,13 @@
 namespace b200d {
 
 #define B200_NB 16        // Cholesky / TRSM block width
-#define B200_SOLVE_THREADS 256
+#define B200_SOLVE_THREADS 512
 
 // optional per-phase cycle counters of the sweep (debug builds: -DB200_PHASE_CLOCKS), accumulated by thread 0 of block 0
 #ifdef B200_PHASE_CLOCKS
 __device__ unsigned long long g_phase_clk[16];
 #define PH_T0() unsigned long long ph_t_ = clock64()
-#define PH_ADD(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { unsigned long long n_ = clock64(); g_phase_clk[i] += n_ - ph_t_; ph_t_ = n_; } } while (0)
+#define PH_ADD(i) do { if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1) { unsigned long long n_ = clock64(); g_phase_clk[i] += n_ - ph_t_; ph_t_ = n_; } } while (0)
 #else
 #define PH_T0()
 #define PH_ADD(i)

@@ -1,0 +1,163 @@
+// extern "C" shim over the host classes so that Python (ctypes) tests and tools can drive them; exceptions become status codes.
+#include <cstring>
+#include <map>
+#include "lowerBodyPoseEstimator.h"
+
+using namespace bioslam_b200;
+static thread_local std::string g_err;
+#define GUARD(stmt)                                      \
+    try { stmt; return 0; }                              \
+    catch (const std::exception& e) { g_err = e.what(); return 1; }
+
+static bool setVec3(Vector3& dst, const double* v, int n) { if (n != 3) return false; dst = Vector3(v[0], v[1], v[2]); return true; }
+
+extern "C" {
+
+const char* b200h_last_error(void) { return g_err.c_str(); }
+void b200h_set_device(int d) { setDevice(d); }
+
+// acc, gyro: [n][3]; mag may be null; t: [n]
+void* b200h_imu_create(int n, const double* acc, const double* gyro, const double* mag, const double* t, const char* label) {
+    imu* m = new imu();
+    m->label = label ? label : "";
+    for (int i = 0; i < n; i++) {
+        m->ax.push_back(acc[3 * i]); m->ay.push_back(acc[3 * i + 1]); m->az.push_back(acc[3 * i + 2]);
+        m->gx.push_back(gyro[3 * i]); m->gy.push_back(gyro[3 * i + 1]); m->gz.push_back(gyro[3 * i + 2]);
+        if (mag) { m->mx.push_back(mag[3 * i]); m->my.push_back(mag[3 * i + 1]); m->mz.push_back(mag[3 * i + 2]); }
+        m->relTimeSec.push_back(t[i]);
+    }
+    return m;
+}
+void b200h_imu_destroy(void* m) { delete (imu*)m; }
+
+void* b200h_ipe_create(void* m, const char* id) { return new imuPoseEstimator(*(imu*)m, id ? id : ""); }
+void b200h_ipe_destroy(void* p) { delete (imuPoseEstimator*)p; }
+
+// set a public setting by its member name
+int b200h_ipe_set(void* pv, const char* name, const double* v, int n) {
+    imuPoseEstimator& p = *(imuPoseEstimator*)pv;
+    const std::string s(name);
+    bool ok = true;
+    if (s == "m_numMeasToPreint") p.m_numMeasToPreint = (unsigned)v[0];
+    else if (s == "imuBiasModelMode") { GUARD(p.setImuBiasModelMode((unsigned)v[0])); }
+    else if (s == "m_useMagnetometer") p.m_useMagnetometer = v[0] != 0;
+    else if (s == "m_usePositionPrior") p.m_usePositionPrior = v[0] != 0;
+    else if (s == "m_useVelocityPrior") p.m_useVelocityPrior = v[0] != 0;
+    else if (s == "m_useImuBiasPrior") p.m_useImuBiasPrior = v[0] != 0;
+    else if (s == "m_useCompassPrior") p.m_useCompassPrior = v[0] != 0;
+    else if (s == "m_globalAcc") ok = setVec3(p.m_globalAcc, v, n);
+    else if (s == "m_globalB") ok = setVec3(p.m_globalB, v, n);
+    else if (s == "m_refVecLocal") ok = setVec3(p.m_refVecLocal, v, n);
+    else if (s == "m_refVecNav") ok = setVec3(p.m_refVecNav, v, n);
+    else if (s == "m_priorCompassAngle") p.m_priorCompassAngle = v[0];
+    else if (s == "m_magnetometerNoise") ok = setVec3(p.m_magnetometerNoise, v, n);
+    else if (s == "m_maxIterations") p.m_maxIterations = (unsigned)v[0];
+    else if (s == "m_initializationScheme") p.m_initializationScheme = (unsigned)v[0];
+    else if (s == "m_optType") p.m_optType = (unsigned)v[0];
+    else if (s == "initialOrientations") {  // [K][9]: overrides the zero initialisation (stand-in for the EKF initialiser)
+        if (!p.isSetup() || n != (int)p.m_nKeyframes * 9) ok = false;
+        else for (unsigned k = 0; k < p.m_nKeyframes; k++) for (int c = 0; c < 9; c++) p.m_initPose[k].R.m[c] = v[(size_t)k * 9 + c];
+    } else ok = false;
+    if (!ok) { g_err = "unknown setting or wrong size: " + s; return 1; }
+    return 0;
+}
+int b200h_ipe_setup(void* p) { GUARD(((imuPoseEstimator*)p)->setup()); }
+int b200h_ipe_set_optimized_to_initial(void* p) { GUARD(((imuPoseEstimator*)p)->setOptimizedValuesToInitialValues()); }
+int b200h_ipe_fast_optimize(void* p) { GUARD(((imuPoseEstimator*)p)->fastOptimize()); }
+int b200h_ipe_n_keyframes(void* p) { return (int)((imuPoseEstimator*)p)->m_nKeyframes; }
+
+static int copyOut(const std::vector<double>& src, double* out, int cap) {
+    if ((int)src.size() > cap) { g_err = "output buffer too small"; return -1; }
+    std::memcpy(out, src.data(), sizeof(double) * src.size());
+    return (int)src.size();
+}
+static std::vector<double> flatPoses(const std::vector<Pose3>& v) {
+    std::vector<double> o;
+    for (const auto& p : v) { o.insert(o.end(), p.R.m, p.R.m + 9); o.insert(o.end(), p.t.v, p.t.v + 3); }
+    return o;
+}
+static std::vector<double> flatVecs(const std::vector<Vector3>& v) { std::vector<double> o; for (const auto& x : v) o.insert(o.end(), x.v, x.v + 3); return o; }
+
+// results by member name; returns the number of doubles written or -1
+int b200h_ipe_get(void* pv, const char* name, double* out, int cap) {
+    imuPoseEstimator& p = *(imuPoseEstimator*)pv;
+    const std::string s(name);
+    if (s == "m_pose") return copyOut(flatPoses(p.m_pose), out, cap);
+    if (s == "m_velocity") return copyOut(flatVecs(p.m_velocity), out, cap);
+    if (s == "m_gyroBias") return copyOut(flatVecs(p.m_gyroBias), out, cap);
+    if (s == "m_accelBias") return copyOut(flatVecs(p.m_accelBias), out, cap);
+    if (s == "m_time") return copyOut(p.m_time, out, cap);
+    if (s == "m_optimizationTotalError") return copyOut(p.m_optimizationTotalError, out, cap);
+    g_err = "unknown result: " + s;
+    return -1;
+}
+
+void* b200h_lbpe_create(void* const* ipe, const char* id) {
+    auto g = [&](int i) -> const imuPoseEstimator& { return *(const imuPoseEstimator*)ipe[i]; };
+    return new lowerBodyPoseEstimator(g(0), g(1), g(2), g(3), g(4), g(5), g(6), id ? id : "");
+}
+void b200h_lbpe_destroy(void* p) { delete (lowerBodyPoseEstimator*)p; }
+int b200h_lbpe_set(void* pv, const char* name, const double* v, int n) {
+    lowerBodyPoseEstimator& p = *(lowerBodyPoseEstimator*)pv;
+    const std::string s(name);
+    (void)n;
+    if (s == "m_useJointVelFactor") p.m_useJointVelFactor = v[0] != 0;
+    else if (s == "m_assumeHipHinge") p.m_assumeHipHinge = v[0] != 0;
+    else if (s == "m_assumeAnkleHinge") p.m_assumeAnkleHinge = v[0] != 0;
+    else if (s == "m_hingeAxisFactorDim") p.m_hingeAxisFactorDim = (unsigned)v[0];
+    else if (s == "m_jointPosFactorDim") p.m_jointPosFactorDim = (unsigned)v[0];
+    else if (s == "m_maxIterations") p.m_maxIterations = (unsigned)v[0];
+    else if (s == "m_convergeAtConsecSmallIter") p.m_convergeAtConsecSmallIter = (unsigned)v[0];
+    else if (s == "m_optimizerType") p.m_optimizerType = (unsigned)v[0];
+    else if (s == "m_lambdaInitial") p.m_lambdaInitial = v[0];
+    else if (s == "m_useMaxAnthroConstraint") p.m_useMaxAnthroConstraint = v[0] != 0;
+    else if (s == "m_useMinAnthroConstraint") p.m_useMinAnthroConstraint = v[0] != 0;
+    else if (s == "m_usePriorsOnImuToJointCtrVectors") p.m_usePriorsOnImuToJointCtrVectors = v[0] != 0;
+    else { g_err = "unknown setting: " + s; return 1; }
+    return 0;
+}
+int b200h_lbpe_setup(void* p) { GUARD(((lowerBodyPoseEstimator*)p)->setup()); }
+int b200h_lbpe_fast_optimize(void* p) { GUARD(((lowerBodyPoseEstimator*)p)->fastOptimize()); }
+// the flat description setup() produced (valid until the estimator is destroyed) and its current values
+const b200_problem_desc* b200h_lbpe_desc(void* p) { auto& e = *(lowerBodyPoseEstimator*)p; return e.isSetup() ? &e.graph().desc() : nullptr; }
+int b200h_lbpe_values(void* pv, double* tv, double* sv) {
+    auto& e = *(lowerBodyPoseEstimator*)pv;
+    if (!e.isSetup()) { g_err = "setup() must be called first"; return 1; }
+    std::memcpy(tv, e.graph().timeValues().data(), sizeof(double) * e.graph().timeValues().size());
+    std::memcpy(sv, e.graph().staticValues().data(), sizeof(double) * e.graph().staticValues().size());
+    return 0;
+}
+int b200h_lbpe_set_values(void* pv, const double* tv, const double* sv) {
+    auto& e = *(lowerBodyPoseEstimator*)pv;
+    if (!e.isSetup()) { g_err = "setup() must be called first"; return 1; }
+    std::memcpy(e.graph().timeValues().data(), tv, sizeof(double) * e.graph().timeValues().size());
+    std::memcpy(e.graph().staticValues().data(), sv, sizeof(double) * e.graph().staticValues().size());
+    return 0;
+}
+int b200h_lbpe_get(void* pv, const char* name, double* out, int cap) {
+    lowerBodyPoseEstimator& p = *(lowerBodyPoseEstimator*)pv;
+    const std::string s(name);
+    if (s == "m_optimizationTotalError") return copyOut(p.m_optimizationTotalError, out, cap);
+    if (s == "m_time") return copyOut(p.m_time, out, cap);
+    const std::map<std::string, const std::vector<Pose3>*> poses = {{"m_sacrumImuPose", &p.m_sacrumImuPose}, {"m_rthighImuPose", &p.m_rthighImuPose},
+        {"m_rshankImuPose", &p.m_rshankImuPose}, {"m_rfootImuPose", &p.m_rfootImuPose}, {"m_lthighImuPose", &p.m_lthighImuPose},
+        {"m_lshankImuPose", &p.m_lshankImuPose}, {"m_lfootImuPose", &p.m_lfootImuPose}};
+    auto it = poses.find(s);
+    if (it != poses.end()) return copyOut(flatPoses(*it->second), out, cap);
+    const std::map<std::string, const std::vector<Vector3>*> vecs = {{"m_sacrumImuAngVel", &p.m_sacrumImuAngVel}, {"m_rthighImuAngVel", &p.m_rthighImuAngVel},
+        {"m_sacrumImuVelocity", &p.m_sacrumImuVelocity}, {"m_rthighImuVelocity", &p.m_rthighImuVelocity}, {"m_sacrumImuGyroBias", &p.m_sacrumImuGyroBias}};
+    auto iv = vecs.find(s);
+    if (iv != vecs.end()) return copyOut(flatVecs(*iv->second), out, cap);
+    const std::map<std::string, const Unit3*> ax = {{"m_rkneeAxisThigh", &p.m_rkneeAxisThigh}, {"m_rkneeAxisShank", &p.m_rkneeAxisShank},
+        {"m_lkneeAxisThigh", &p.m_lkneeAxisThigh}, {"m_lkneeAxisShank", &p.m_lkneeAxisShank}, {"m_hipAxisSacrum", &p.m_hipAxisSacrum}};
+    auto ia = ax.find(s);
+    if (ia != ax.end()) return copyOut({ia->second->p[0], ia->second->p[1], ia->second->p[2]}, out, cap);
+    const std::map<std::string, const Point3*> pt = {{"m_sacrumImuToRHipCtr", &p.m_sacrumImuToRHipCtr}, {"m_rthighImuToKneeCtr", &p.m_rthighImuToKneeCtr},
+        {"m_lfootImuToAnkleCtr", &p.m_lfootImuToAnkleCtr}};
+    auto ip = pt.find(s);
+    if (ip != pt.end()) return copyOut({ip->second->v[0], ip->second->v[1], ip->second->v[2]}, out, cap);
+    g_err = "unknown result: " + s;
+    return -1;
+}
+
+}  // extern "C"

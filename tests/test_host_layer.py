@@ -1,0 +1,100 @@
+"""The C++ host layer (bioslam_b200/host: imuPoseEstimator / lowerBodyPoseEstimator mirrors of the reference classes).
+CPU (-m "not gpu"): under the emulator build, setup() must produce exactly the flat graph the independent Python builder
+(bioslam_b200/graphs.py, which follows the reference's setup() line by line) produces.  GPU: fastOptimize() == driving the
+C ABI directly."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+import pytest
+from bioslam_b200 import abi, host, lib, synth
+import graphs
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "cudaemu", "libbioslam_b200_emu.so")
+
+
+def slots_equal(a, b):
+    for f, _ in a._fields_:
+        x, y = getattr(a, f), getattr(b, f)
+        if hasattr(x, "__len__"):
+            if not np.allclose(list(x), list(y), rtol=4e-16, atol=0.0):     # numeric (-0.0 == 0.0; Unit3 normalisation may differ by 1 ulp)
+                return False
+        elif x != y:
+            return False
+    return True
+
+
+def check_same_graph(gh, tvh, svh, gp, tvp, svp):
+    assert gh.K == gp.K and gh.time_var_types == gp.time_var_types and gh.static_var_types == gp.static_var_types
+    assert gh.const_stride == gp.const_stride and len(gh.slots) == len(gp.slots)
+    for i, (a, b) in enumerate(zip(gh.slots, gp.slots)):
+        assert slots_equal(a, b), f"slot {i}: type {a.type} vs {b.type}"
+    assert np.array_equal(tvh, tvp) and np.allclose(svh, svp, rtol=4e-16, atol=0.0)
+    assert np.abs(gh.consts[:, :70] - gp.consts[:, :70]).max() < 1e-13   # device vs oracle preintegration (zeta part)
+    assert np.array_equal(gh.consts[:, 1330:], gp.consts[:, 1330:])       # gyro samples
+
+
+def test_host_setup_builds_the_reference_graph(oracle_lib):
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "cudaemu")])
+    tr = synth.make_trial(seed=8, duration_s=1.5)
+    for jv in (0, 1):
+        lb = host.lower_body_from_trial(tr, so_path=EMU)
+        lb.set(m_useJointVelFactor=jv)
+        lb.setup()
+        gh, tvh, svh = lb.graph()
+        gp, tvp, svp = graphs.lower_body_graph(tr, use_joint_vel=bool(jv))
+        check_same_graph(gh, tvh, svh, gp, tvp, svp)
+
+
+def test_host_error_behaviour(oracle_lib):
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "cudaemu")])
+    tr = synth.make_trial(seed=8, duration_s=1.0)
+    m = host.Imu(tr.acc[0], tr.gyro[0], tr.time, so_path=EMU)
+    p = host.ImuPoseEstimator(m, "x", so_path=EMU)
+    with pytest.raises(host.HostError):
+        p.setImuBiasModelMode(2)            # reference: "imuBiasModelMode not recognized"
+    with pytest.raises(host.HostError):
+        p.setOptimizedValuesToInitialValues()   # before setup()
+    p.set(m_initializationScheme=1)
+    with pytest.raises(host.HostError):
+        p.setup()                            # EKF initialiser is not part of this build
+
+
+@pytest.mark.gpu
+def test_host_fast_optimize_matches_c_abi():
+    tr = synth.make_trial(seed=8, duration_s=3.0)
+    lb = host.lower_body_from_trial(tr)
+    lb.set(m_maxIterations=12)
+    lb.setup()
+    g, tv, sv = lb.graph()
+    p = lib.Problem(g); p.set_values(tv, sv)
+    res, hist = p.optimize(abi.LmParams.lower_body(), abi.OuterParams.lower_body(max_iterations=12))
+    lb.fastOptimize()
+    h = lb.get("m_optimizationTotalError")
+    assert np.array_equal(h, hist)                       # deterministic: bit-identical error history
+    tvo, svo = p.get_values()
+    _, tvh, svh = lb.graph()
+    assert np.array_equal(tvh, tvo) and np.array_equal(svh, svo)
+    pose = lb.get("m_rthighImuPose").reshape(-1, 12)
+    off = g.time_value_offsets()
+    assert np.array_equal(pose, tvo[:, off[3]:off[3] + 12])
+    assert np.allclose(np.linalg.norm(lb.get("m_rkneeAxisThigh")), 1.0)
+
+
+@pytest.mark.gpu
+def test_host_single_imu_fast_optimize():
+    tr = synth.make_trial(seed=4, duration_s=10.0)
+    m = host.Imu(tr.acc[0], tr.gyro[0], tr.time)
+    for mode in (1, 0):
+        p = host.ImuPoseEstimator(m, "sacrum")
+        p.set(m_useCompassPrior=1, m_refVecLocal=[0, 1, 0], m_refVecNav=[1, 0, 0])
+        p.setImuBiasModelMode(mode)
+        p.setup()
+        K = p.nKeyframes
+        R0 = tr.poses_at((graphs.keyframe_sample_idx(K, 10) + 1) * tr.dt)["sacrum"][0] @ synth.exp_so3(np.random.default_rng(0).normal(scale=0.05, size=(K, 3)))
+        p.set(initialOrientations=R0.reshape(-1))
+        p.fastOptimize()
+        err = p.get("m_optimizationTotalError")
+        assert err[-1] < 1e-5 * err[0]              # reference solution test: final error <= 1e-5 (testImuEstimationSolution.cpp:20,42)
+        assert p.get("m_pose").size == K * 12 and p.get("m_gyroBias").size == (3 * K if mode == 1 else 3)
