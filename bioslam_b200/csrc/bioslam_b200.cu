@@ -79,7 +79,13 @@ struct b200_problem {
         Level dev{};
     };
     std::vector<HostLevel> levels;             // levels[0]: keyframes, levels[1]: its separators (optional)
-    int P = 1, P2 = 1, rmax = 0;               // chunks of level 0 / level 1
+    int P = 1, P2 = 1;                         // chunks of level 0 / level 1
+    Level top{};                               // top level: one chunk over the remaining separators (or all keyframes)
+    int* d_top_begin = nullptr;
+    int *d_orow = nullptr, *d_ocol = nullptr, *d_ozs = nullptr;
+    double *d_Ftop = nullptr, *d_Stop = nullptr;
+    size_t smem_schur = 0, smem_backsub = 0;
+    int schur_ldy = 0, schur_kslab = 0;
     int Wk = 0;                                // keyframes per rank window
     double *d_stageS = nullptr, *d_stageF = nullptr, *d_pack = nullptr;
     size_t pack_doubles = 0;
@@ -215,7 +221,8 @@ void b200_problem_destroy(b200_problem* p) {
     if (!p) return;
     cudaSetDevice(p->device);
     void* ptrs[] = {p->d_tv, p->d_tv_try, p->d_sv, p->d_sv_try, p->d_cst, p->d_stage, p->d_slots, p->d_tvars, p->d_svars, p->d_J, p->d_r,
-                    p->d_e, p->d_e2, p->d_D, p->d_O, p->d_A, p->d_S, p->sb.Lst, p->sb.Pst, p->sb.Ftop, p->sb.Stop, p->sb.delta, p->sb.dstat,
+                    p->d_e, p->d_e2, p->d_D, p->d_O, p->d_A, p->d_S, p->sb.Wst, p->sb.Yst, p->sb.ybuf, p->d_Ftop, p->d_Stop, p->sb.delta, p->sb.dstat,
+                    p->d_top_begin, p->d_orow, p->d_ocol, p->d_ozs,
                     p->sb.scal, p->sb.status, p->d_stageS, p->d_stageF, p->d_pack, p->d_asm_items, p->d_asm_terms, p->d_asm_blocks[0], p->d_asm_blocks[1]};
     for (void* q : ptrs) if (q) cudaFree(q);
     free_levels(p);
@@ -316,10 +323,43 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
     const size_t K = p->K;
     CK(dalloc(&p->d_D, K * dm.ntp * dm.ntp)); CK(dalloc(&p->d_O, K * dm.nc * dm.nc));
     CK(dalloc(&p->d_A, K * dm.ns1 * dm.ntp)); CK(dalloc(&p->d_S, K * dm.ns1 * dm.ns1));
-    CK(dalloc(&p->sb.Lst, K * dm.ntp * dm.ntp)); CK(dalloc(&p->sb.Pst, K * (size_t)(dm.nc + dm.hmax) * dm.ntp));
+    CK(dalloc(&p->sb.Wst, K * dm.ntp * dm.ntp)); CK(dalloc(&p->sb.Yst, K * (size_t)dm.hmax * dm.ntp)); CK(dalloc(&p->sb.ybuf, K * dm.ntp));
     CK(dalloc(&p->sb.delta, (K + 1024) * dm.ntp)); CK(dalloc(&p->sb.dstat, (size_t)ns + 1)); CK(dalloc(&p->sb.scal, (size_t)SC_COUNT));
     CK(dalloc(&p->sb.status, (size_t)1));
-    CK(dalloc(&p->sb.Ftop, (size_t)2 * (dm.nc + dm.hmax) * dm.nc)); CK(dalloc(&p->sb.Stop, (size_t)dm.hmax * dm.hmax));
+    CK(dalloc(&p->d_Ftop, (size_t)2 * (dm.nc + dm.hmax) * dm.nc)); CK(dalloc(&p->d_Stop, (size_t)dm.hmax * dm.hmax));
+    CK(dalloc(&p->d_top_begin, (size_t)2));
+    {
+        // structure of the time-coupling block O: which chain dofs of keyframe k+1 (rows) meet which chain dofs of k (columns)
+        const int nc = dm.nc, nl_ = dm.nl;
+        std::vector<int> orow(2 * nc), ocol(2 * nc), ozs(nc);
+        for (int i = 0; i < nc; i++) { orow[2 * i] = nc; orow[2 * i + 1] = 0; ocol[2 * i] = nc; ocol[2 * i + 1] = 0; }
+        for (const DevSlot& s : p->hslots)
+            for (int a = 0; a < s.nvars; a++) {
+                if (s.var_kind[a] != B200_AT_K1) continue;
+                for (int b = 0; b < s.nvars; b++) {
+                    if (s.var_kind[b] != B200_AT_K) continue;
+                    const int ra = s.tan_off[a] - nl_, cb = s.tan_off[b] - nl_;
+                    for (int i = ra; i < ra + s.tan_dim[a]; i++) { orow[2 * i] = std::min(orow[2 * i], cb); orow[2 * i + 1] = std::max(orow[2 * i + 1], cb + s.tan_dim[b]); }
+                    for (int j = cb; j < cb + s.tan_dim[b]; j++) { ocol[2 * j] = std::min(ocol[2 * j], ra); ocol[2 * j + 1] = std::max(ocol[2 * j + 1], ra + s.tan_dim[a]); }
+                }
+            }
+        int ow = 2;
+        for (int i = 0; i < nc; i++) {
+            if (orow[2 * i + 1] <= orow[2 * i]) { orow[2 * i] = orow[2 * i + 1] = 0; }
+            if (ocol[2 * i + 1] <= ocol[2 * i]) { ocol[2 * i] = ocol[2 * i + 1] = 0; }
+            ozs[i] = (nl_ + orow[2 * i]) & ~1;
+            ow = std::max(ow, (nl_ + orow[2 * i + 1] - ozs[i] + 1) & ~1);
+        }
+        ow = std::min(ow, dm.ntp);
+        for (int i = 0; i < nc; i++) if (ozs[i] + ow > dm.ntp) ozs[i] = dm.ntp - ow;
+        dm.ow = ow; dm.owp = ow + 2;
+        CK(dalloc(&p->d_orow, (size_t)2 * nc)); CK(dalloc(&p->d_ocol, (size_t)2 * nc)); CK(dalloc(&p->d_ozs, (size_t)nc));
+        CK(cudaMemcpyAsync(p->d_orow, orow.data(), sizeof(int) * 2 * nc, cudaMemcpyHostToDevice, p->stream));
+        CK(cudaMemcpyAsync(p->d_ocol, ocol.data(), sizeof(int) * 2 * nc, cudaMemcpyHostToDevice, p->stream));
+        CK(cudaMemcpyAsync(p->d_ozs, ozs.data(), sizeof(int) * nc, cudaMemcpyHostToDevice, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+        dm.orow = p->d_orow; dm.ocol = p->d_ocol; dm.ozs = p->d_ozs;
+    }
     CK(cudaMallocHost((void**)&p->h_scal, (SC_COUNT + 2) * sizeof(double)));
     // uploads
     // every upload goes through p->stream (a non-blocking stream is not ordered against legacy-stream copies)
@@ -344,34 +384,48 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
     size_t static_smem = 0;
     {
         cudaFuncAttributes fa;
-        CK(cudaFuncGetAttributes(&fa, top_solve_kernel)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
-        CK(cudaFuncGetAttributes(&fa, level_sweep_kernel)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
-        CK(cudaFuncGetAttributes(&fa, level_backsub_kernel)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
+        CK(cudaFuncGetAttributes(&fa, top_finish_kernel)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
+        CK(cudaFuncGetAttributes(&fa, chain_sweep_kernel)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
+        CK(cudaFuncGetAttributes(&fa, chain_backsub_kernel)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
+        CK(cudaFuncGetAttributes(&fa, chain_schur_kernel)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
         CK(cudaFuncGetAttributes(&fa, assemble_kernel)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
     }
     const size_t smem_cap = (227 * 1024 - static_smem - 1024) & ~(size_t)15;  // dynamic budget next to the kernels' static arrays
     {
         b200_status ast = build_asm_plan(p, smem_cap);
         if (ast != B200_OK) { b200_problem_destroy(p); return ast; }
-        if (sizeof(double) * (size_t)dm.ntp * dm.ld > smem_cap) return fail("time block does not fit in shared memory", B200_NOT_IMPLEMENTED);
     }
     {
-        long long rows_fit = (long long)(smem_cap / sizeof(double)) / dm.ld - B200_NB - 32;
-        const int rn_max = dm.nc + dm.hmax;
-        p->rmax = (int)std::min<long long>(rows_fit, rn_max);
-        if (rows_fit < 32) return fail("panel does not fit in shared memory", B200_NOT_IMPLEMENTED);
-        p->smem_sweep = sizeof(double) * (size_t)sweep_smem_doubles(dm.ntp, dm.ld, p->rmax);
-        const size_t stat = sizeof(double) * (size_t)static_lds(dm.ns) * (dm.ns1 + 1);
-        if (stat + 512 * sizeof(double) > p->smem_sweep) p->smem_sweep = stat + 512 * sizeof(double);
-        p->smem_sweep = (p->smem_sweep + 15) & ~(size_t)15;
+        // sweep: pivot block + packed O rows resident, the panel streams through in chunks of cr rows
+        const long long cap_d = (long long)(smem_cap / sizeof(double));
+        const long long fixed = (long long)dm.ntp * dm.ld + sweep_op_doubles(dm.nc, dm.owp);
+        long long rows_fit = (cap_d - fixed) / dm.ld;
+        if (rows_fit < 16) return fail("time block does not fit in shared memory", B200_NOT_IMPLEMENTED);
+        dm.cr = (int)std::min<long long>(64, rows_fit & ~15LL);
+        p->smem_sweep = sizeof(double) * (size_t)sweep_smem_doubles(dm.ntp, dm.ld, dm.cr, dm.nc, dm.owp);
+        // back-substitution / top level: factor block + vectors; the static system (ns1 x lds) reuses the block area
+        const size_t bs = (size_t)backsub_smem_doubles(dm.ntp, dm.ld);
+        if ((size_t)static_lds(dm.ns) * (dm.ns1 + 1) > (size_t)dm.ntp * dm.ld + 4 * 256)
+            return fail("static block larger than the time block is not supported", B200_NOT_IMPLEMENTED);
+        p->smem_backsub = (sizeof(double) * bs + 15) & ~(size_t)15;
+        if (p->smem_backsub > smem_cap) return fail("solver working set does not fit in shared memory", B200_NOT_IMPLEMENTED);
         dm.sm_doubles = (int)(p->smem_sweep / sizeof(double));
-        if (p->smem_sweep > smem_cap) return fail("solver working set does not fit in shared memory", B200_NOT_IMPLEMENTED);
+        // Schur kernel: the stored arrow panel of one node (hmax rows), whole rows if they fit, else column slabs
+        int ldy = choose_ld(dm.ntp), kslab = dm.ntp;
+        if ((long long)dm.hmax * ldy > cap_d) {
+            kslab = (int)((cap_d / dm.hmax) & ~3LL) - 2;
+            if (kslab < 2) return fail("arrow panel does not fit in shared memory", B200_NOT_IMPLEMENTED);
+            ldy = kslab;   // == 2 mod 4
+        }
+        p->schur_ldy = ldy; p->schur_kslab = kslab;
+        p->smem_schur = sizeof(double) * (size_t)dm.hmax * ldy;
     }
 #ifndef B200_USE_EMU
     CK(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(p->smem_asm[0], p->smem_asm[1])));
-    CK(cudaFuncSetAttribute(level_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sweep));
-    CK(cudaFuncSetAttribute(top_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sweep));
-    CK(cudaFuncSetAttribute(level_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sweep));
+    CK(cudaFuncSetAttribute(chain_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sweep));
+    CK(cudaFuncSetAttribute(chain_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_schur));
+    CK(cudaFuncSetAttribute(top_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_backsub));
+    CK(cudaFuncSetAttribute(chain_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_backsub));
 #endif
     p->k_lo = 0; p->k_hi = p->K;
     int P1 = 0, P2 = 0;   // 0: choose from the cost model
@@ -487,9 +541,20 @@ static b200_status set_partition(b200_problem* p, int P1, int P2) {
         if (li == 0) { d.Dsrc = p->d_D; d.Osrc = p->d_O; d.Asrc = p->d_A; d.Ssrc = p->d_S; d.st = nullptr; }
         else { auto& lp = p->levels[li - 1]; d.Dsrc = lp.Dred; d.Osrc = lp.Ored; d.Asrc = lp.Ared; d.Ssrc = lp.Sred; d.st = l.d_st; }
         d.begin = l.d_begin; d.P = l.P; d.F = l.F; d.S = l.S;
-        d.Dred = l.Dred; d.Ored = l.Ored; d.Ared = l.Ared; d.Sred = l.Sred; d.sep_st = l.d_sep_st;
+        d.Dred = l.Dred; d.Ored = l.Ored; d.Ared = l.Ared; d.Sred = l.Sred; d.sep_st = l.d_sep_st; d.dense_o = (li > 0);
     }
     if (nlev == 0) { auto& l = p->levels[0]; l.n_nodes = K; l.P = 1; p->k_lo = 0; p->k_hi = K; }
+    {   // top level: a single chunk (no separators) over whatever the levels below left
+        Level& t = p->top;
+        t = Level{};
+        int tn = K;
+        if (nlev == 0) { t.Dsrc = p->d_D; t.Osrc = p->d_O; t.Asrc = p->d_A; t.Ssrc = p->d_S; t.st = nullptr; }
+        else { auto& l = p->levels[nlev - 1]; t.Dsrc = l.Dred; t.Osrc = l.Ored; t.Asrc = l.Ared; t.Ssrc = l.Sred; t.st = l.d_sep_st; tn = l.P - 1; }
+        const int tb[2] = {0, tn};
+        CK(cudaMemcpyAsync(p->d_top_begin, tb, sizeof(tb), cudaMemcpyHostToDevice, p->stream));
+        CK(cudaStreamSynchronize(p->stream));
+        t.begin = p->d_top_begin; t.P = 1; t.F = p->d_Ftop; t.S = p->d_Stop; t.dense_o = (nlev > 0);
+    }
     if (W > 1) {
         if (p->d_stageS) cudaFree(p->d_stageS);
         if (p->d_stageF) cudaFree(p->d_stageF);
@@ -591,20 +656,39 @@ __global__ void pack_groups_kernel(Dims dm, Level lv1, const double* Dred, const
     }
 }
 
+// one level: sweep (CTA per chunk) + arrow Schur complement (CTA per chunk)
+static void launch_level_factor(b200_problem* p, const Level& lv, int c_lo, int c_hi, double lambda) {
+    const Dims& dm = p->dm;
+    B200_LAUNCH(chain_sweep_kernel, dim3(c_hi - c_lo), dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, dm, lv, p->sb, lambda, c_lo);
+    B200_LAUNCH(chain_schur_kernel, dim3(c_hi - c_lo), dim3(B200_SCHUR_THREADS), p->smem_schur, p->stream, dm, lv, p->sb, c_lo, p->schur_ldy,
+                p->schur_kslab);
+    p->launches += 2;
+}
+static void launch_level_backsub(b200_problem* p, const b200_problem::HostLevel& l) {
+    const Dims& dm = p->dm;
+    int max_nodes = 1;
+    for (int c = l.c_lo; c < l.c_hi; c++) max_nodes = std::max(max_nodes, l.begin[c + 1] - l.begin[c]);
+    B200_LAUNCH(chain_backsub_prepass_kernel, dim3(max_nodes, l.c_hi - l.c_lo), dim3(B200_PREPASS_THREADS), 0, p->stream, dm, l.dev, p->sb, l.c_lo);
+    B200_LAUNCH(chain_backsub_kernel, dim3(l.c_hi - l.c_lo), dim3(B200_SOLVE_THREADS), p->smem_backsub, p->stream, dm, l.dev, p->sb, l.c_lo);
+    p->launches += 2;
+}
+
 // (H + lambda I) delta = -g : nested partitioned factorisation + back-substitution, all on p->stream
 static b200_status launch_solve(b200_problem* p, double lambda) {
     CK(cudaMemsetAsync(p->sb.status, 0, sizeof(int), p->stream));
     const Dims& dm = p->dm;
     const int W = p->world, r = p->rank;
     const size_t Fsz = (size_t)(dm.nc + dm.hmax) * dm.nc, Ssz = (size_t)dm.hmax * dm.hmax;
-    const dim3 tb(B200_SOLVE_THREADS);
     const int nlev = (p->P > 1) ? ((p->P2 > 1) ? 2 : 1) : 0;
     if (p->time_phases) CK(cudaEventRecord(p->ev[8], p->stream));
     if (nlev >= 1) {
         auto& l0 = p->levels[0];
-        B200_LAUNCH(level_sweep_kernel, dim3(l0.c_hi - l0.c_lo), tb, p->smem_sweep, p->stream, dm, l0.dev, p->sb, lambda, p->rmax, l0.c_lo);
+        B200_LAUNCH(chain_sweep_kernel, dim3(l0.c_hi - l0.c_lo), dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, dm, l0.dev, p->sb, lambda, l0.c_lo);
         p->launches++;
         if (p->time_phases) CK(cudaEventRecord(p->ev[9], p->stream));
+        B200_LAUNCH(chain_schur_kernel, dim3(l0.c_hi - l0.c_lo), dim3(B200_SCHUR_THREADS), p->smem_schur, p->stream, dm, l0.dev, p->sb, l0.c_lo,
+                    p->schur_ldy, p->schur_kslab);
+        p->launches++;
         int red_lo = l0.c_lo, red_hi = std::min(l0.c_hi, l0.P - 1);
         if (W > 1) {
             // the separator that closes this rank's window needs the Schur complement / fill of the NEXT rank's first chunk
@@ -621,19 +705,14 @@ static b200_status launch_solve(b200_problem* p, double lambda) {
             if (r > 0) red_lo = l0.c_lo - 1;
         }
         if (red_hi > red_lo) {
-            B200_LAUNCH(level_reduce_kernel, dim3(red_hi - red_lo), dim3(256), 0, p->stream, dm, l0.dev, red_lo);
+            B200_LAUNCH(chain_reduce_kernel, dim3(red_hi - red_lo), dim3(256), 0, p->stream, dm, l0.dev, red_lo);
             p->launches++;
         }
     }
-    const double *tD = p->d_D, *tO = p->d_O, *tA = p->d_A, *tS = p->d_S;
-    const int* tst = nullptr;
-    int tn = p->K;
-    if (nlev == 1) { auto& l0 = p->levels[0]; tD = l0.Dred; tO = l0.Ored; tA = l0.Ared; tS = l0.Sred; tst = l0.d_sep_st; tn = l0.P - 1; }
     if (nlev == 2) {
         auto& l0 = p->levels[0];
         auto& l1 = p->levels[1];
-        B200_LAUNCH(level_sweep_kernel, dim3(l1.c_hi - l1.c_lo), tb, p->smem_sweep, p->stream, dm, l1.dev, p->sb, lambda, p->rmax, l1.c_lo);
-        p->launches++;
+        launch_level_factor(p, l1.dev, l1.c_lo, l1.c_hi, lambda);
         if (W > 1) {
             const int gpr = l1.P / W;
             b200_status st = allgather(p, l1.F, sizeof(double) * 2 * Fsz * gpr); if (st != B200_OK) return st;
@@ -645,24 +724,16 @@ static b200_status launch_solve(b200_problem* p, double lambda) {
                         (long long)p->pack_doubles, 0, 1, l1.c_lo, l1.c_hi);
             p->launches += 2;
         }
-        B200_LAUNCH(level_reduce_kernel, dim3(l1.P - 1), dim3(256), 0, p->stream, dm, l1.dev, 0);
+        B200_LAUNCH(chain_reduce_kernel, dim3(l1.P - 1), dim3(256), 0, p->stream, dm, l1.dev, 0);
         p->launches++;
-        tD = l1.Dred; tO = l1.Ored; tA = l1.Ared; tS = l1.Sred; tst = l1.d_sep_st; tn = l1.P - 1;
     }
     if (p->time_phases) CK(cudaEventRecord(p->ev[10], p->stream));
-    B200_LAUNCH(top_solve_kernel, dim3(1), tb, p->smem_sweep, p->stream, dm, tD, tO, tA, tS, tst, tn, p->sb, lambda, p->rmax);
+    launch_level_factor(p, p->top, 0, 1, lambda);
+    B200_LAUNCH(top_finish_kernel, dim3(1), dim3(B200_SOLVE_THREADS), p->smem_backsub, p->stream, dm, p->top, p->sb, lambda);
     p->launches++;
     if (p->time_phases) CK(cudaEventRecord(p->ev[11], p->stream));
-    if (nlev == 2) {
-        auto& l1 = p->levels[1];
-        B200_LAUNCH(level_backsub_kernel, dim3(l1.c_hi - l1.c_lo), tb, p->smem_sweep, p->stream, dm, l1.dev, p->sb, l1.c_lo);
-        p->launches++;
-    }
-    if (nlev >= 1) {
-        auto& l0 = p->levels[0];
-        B200_LAUNCH(level_backsub_kernel, dim3(l0.c_hi - l0.c_lo), tb, p->smem_sweep, p->stream, dm, l0.dev, p->sb, l0.c_lo);
-        p->launches++;
-    }
+    if (nlev == 2) launch_level_backsub(p, p->levels[1]);
+    if (nlev >= 1) launch_level_backsub(p, p->levels[0]);
     if (p->time_phases) CK(cudaEventRecord(p->ev[12], p->stream));
     if (W > 1) {  // every rank needs every keyframe's step: the values are replicated
         b200_status st = allgather(p, p->sb.delta, sizeof(double) * (size_t)p->Wk * dm.ntp); if (st != B200_OK) return st;

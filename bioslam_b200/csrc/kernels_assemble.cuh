@@ -16,6 +16,12 @@ struct Dims {
     int ld;                        // shared-memory leading dimension (>= ntp, == 2 mod 4)
     int hmax;                      // ns1 + nc
     int sm_doubles;                // dynamic shared memory of the solver kernels, in doubles
+    // solver: structure of the time-coupling block O (rows = chain dofs of keyframe k+1, columns = chain dofs of k)
+    int cr;                        // panel rows resident in shared memory at a time (multiple of 16)
+    int ow, owp;                   // packed width of a row of O (even) and its shared-memory stride (ow + 2)
+    const int* orow;               // [nc][2] structural non-zero column range [c0, c1) of every row of O
+    const int* ocol;               // [nc][2] structural non-zero row range [r0, r1) of every column of O
+    const int* ozs;                // [nc] even start column (time-block coordinates) of the packed row
 };
 
 // Assembly plan, built once per problem on the host (bioslam_b200.cu: build_asm_plan):

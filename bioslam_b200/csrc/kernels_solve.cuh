@@ -5,28 +5,41 @@
 //                                    [        ...            ...   ]
 //                                    [ A_0  A_1   ...        S     ]
 //
-// Two-level partitioned (SPIKE-style) factorisation so one solve exposes P-way parallelism:
+// Nested partitioned (SPIKE-style) factorisation so one solve exposes P-way parallelism:
 //   1. chain_sweep_kernel, one CTA per chunk: eliminate the chunk's interior keyframes left to right.  The coupling to
 //      the chunk's LEFT separator keyframe is carried as extra "arrow" rows, exactly like the static variables, and the
-//      right-hand side is carried as one more arrow row (so forward substitution, the Schur complement onto the
-//      statics/separators and the reduced right-hand side all come out of the same rank-k update).
-//   2. reduced_assemble_kernel: gather the chunks' Schur complements onto the separator keyframes.
-//   3. top_solve_kernel, one CTA: the same sweep over the P-1 separators, the static system, back-substitution of the
-//      separators.
-//   4. chain_backsub_kernel, one CTA per chunk: back-substitution of the interior keyframes.
-// Per keyframe the work is: in-shared-memory blocked Cholesky of the (ntp x ntp) pivot, a blocked triangular solve of
-// the panel [O_k ; arrow rows] against it, and a symmetric rank-ntp update (panel * panel^T) that yields the fill for
-// the next keyframe and the arrow Schur complement.  All three run on a register-tiled fp64 micro-kernel (4x4 per
-// thread, operands in shared memory read as 16-byte pairs).
+//      right-hand side is carried as one more arrow row.
+//   2. chain_schur_kernel, one CTA per chunk: the arrow Schur complement  S - sum_k Y_k Y_k^T  of the chunk, computed
+//      from the stored arrow panels in one pass (off the sequential path, accumulators in registers, no atomics).
+//   3. chain_reduce_kernel: gather the chunks' Schur complements onto the separator keyframes (= nodes of the next level).
+//   4. the same three steps on the separators (level 1), then on the group separators by a single CTA (top level),
+//      top_finish_kernel: static system + back-substitution of the top-level nodes.
+//   5. chain_backsub_prepass_kernel (all nodes in parallel: y_k = Y_k^T coef) and chain_backsub_kernel (one CTA per
+//      chunk, sequential over its nodes, matrix-vector products only).
+//
+// One elimination step (node k, pivot block M = D_k + lambda I - fill, n x n):
+//   a. right-looking blocked Cholesky of M fused with the inversion of its factor: the identity is carried along as
+//      appended rows, which turns them into W^T = L^-T.  L lives in the lower triangle of the shared-memory block while it
+//      is needed, W^T (upper triangle, diagonal included) is what remains; 16 x 16 diagonal blocks are factorised and
+//      inverted by one warp in registers (shuffles), panels and trailing updates run on all warps.
+//   b. every row p of the panel [O_k ; arrow rows] (processed in chunks of <= 64 rows that fit in shared memory):
+//        y = p W^T            (forward substitution, one triangular GEMM against the resident W^T)
+//        z = y W  = p M^-1    (second triangular GEMM against the same block)
+//        fill row = z O_k^T   (O_k is block-sparse: packed rows, <= 16 terms per entry for the IMU chain)
+//      y is stored for the Schur complement / back-substitution; the fill rows are the corrections of the next node.
+// All GEMMs run on a register-tiled fp64 micro-kernel (4 x 4 per thread, 16 x 32 per warp, operands in shared memory
+// read as 16-byte pairs, bank-conflict free for a leading dimension == 2 mod 4).  No tensor cores (north_star).
 #pragma once
 #include "kernels_assemble.cuh"
 
 namespace b200d {
 
-#define B200_NB 16        // Cholesky / TRSM block width
+#define B200_NB 16        // Cholesky block width
 #define B200_SOLVE_THREADS 512
+#define B200_SCHUR_THREADS 384
+#define B200_PREPASS_THREADS 256
 
-// optional per-phase cycle counters of the sweep (debug builds: -DB200_PHASE_CLOCKS), accumulated by thread 0 of block 0
+// optional per-phase cycle counters of the sweep (debug builds: -DB200_PHASE_CLOCKS), accumulated by thread 0 of the last block
 #ifdef B200_PHASE_CLOCKS
 __device__ unsigned long long g_phase_clk[16];
 #define PH_T0() unsigned long long ph_t_ = clock64()
@@ -36,18 +49,94 @@ __device__ unsigned long long g_phase_clk[16];
 #define PH_ADD(i)
 #endif
 
-// ------------------------------------------------------------------------------------------------- micro-kernel
-// out(m, n, sum_{k in [k0,k1)} A[m][k]*B[n][k]) for m<M, n<N.  A, B in shared memory, lda/ldb even, k0 even, (k1-k0) even.
-// Warp tile 32 x 16: lane -> (ty = lane>>2, tx = lane&3), thread rows m0+ty+8i, cols n0+tx+4j.
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ void st2(double* p, double x, double y) { *reinterpret_cast<double2*>(p) = make_double2(x, y); }
+
+// ------------------------------------------------------------------------------------------------- micro-kernels
+// Warp tile 16 x 32, thread tile 4 x 4.  lane -> (ty = lane >> 3, tx = lane & 7); rows m0 + ty + 4 i.
+// NN:  C += A(16 x k) B(k x 32), B row-major indexed [k][c]; columns c0 + 2 tx + 16 j + {0, 1}; ka, kb, N even.
+__device__ __forceinline__ void warp_mma_nn(const double* __restrict__ A, int lda, int m0, int M, const double* __restrict__ B, int ldb,
+                                            int c0, int N, int ka, int kb, double (&acc)[4][4]) {
+    const int lane = threadIdx.x & 31, ty = lane >> 3, tx = lane & 7;
+    const double* ap[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { int m = m0 + ty + 4 * i; if (m > M - 1) m = M - 1; ap[i] = A + (long long)m * lda; }
+    int cj[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) { int c = c0 + 2 * tx + 16 * j; if (c > N - 2) c = N - 2; cj[j] = c; }
+    const double* bp = B + (long long)ka * ldb;
+    for (int k = ka; k < kb; k += 2, bp += 2 * ldb) {
+        double2 a[4], b0[2], b1[2];
+#pragma unroll
+        for (int i = 0; i < 4; i++) a[i] = ld2(ap[i] + k);
+#pragma unroll
+        for (int j = 0; j < 2; j++) { b0[j] = ld2(bp + cj[j]); b1[j] = ld2(bp + ldb + cj[j]); }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                acc[i][2 * j] = fma(a[i].y, b1[j].x, fma(a[i].x, b0[j].x, acc[i][2 * j]));
+                acc[i][2 * j + 1] = fma(a[i].y, b1[j].y, fma(a[i].x, b0[j].y, acc[i][2 * j + 1]));
+            }
+    }
+}
+// element (i, q) of an NN tile: row m0 + ty + 4 i, column c0 + 2 tx + 16 (q >> 1) + (q & 1)
+
+// NT:  C += A(16 x k) B(32 x k)^T, both row-major along k; columns r0 + tx + 8 j.
+__device__ __forceinline__ void warp_mma_nt(const double* __restrict__ A, int lda, int m0, int M, const double* __restrict__ B, int ldb,
+                                            int r0, int R, int ka, int kb, double (&acc)[4][4]) {
+    const int lane = threadIdx.x & 31, ty = lane >> 3, tx = lane & 7;
+    const double* ap[4];
+    const double* bp[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int m = m0 + ty + 4 * i; if (m > M - 1) m = M - 1;
+        int r = r0 + tx + 8 * i; if (r > R - 1) r = R - 1;
+        ap[i] = A + (long long)m * lda;
+        bp[i] = B + (long long)r * ldb;
+    }
+    for (int k = ka; k < kb; k += 2) {
+        double2 a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { a[i] = ld2(ap[i] + k); b[i] = ld2(bp[i] + k); }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i].y, b[j].y, fma(a[i].x, b[j].x, acc[i][j]));
+    }
+}
+
+// NT, warp tile 32 x 32, thread tile 8 x 4 (Schur complement kernel): rows m0 + ty + 4 i (i < 8), columns r0 + tx + 8 j.
+__device__ __forceinline__ void warp_mma_nt32(const double* __restrict__ A, int lda, int m0, int M, int r0, int ka, int kb, double (&acc)[8][4]) {
+    const int lane = threadIdx.x & 31, ty = lane >> 3, tx = lane & 7;
+    const double* ap[8];
+    const double* bp[4];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { int m = m0 + ty + 4 * i; if (m > M - 1) m = M - 1; ap[i] = A + (long long)m * lda; }
+#pragma unroll
+    for (int j = 0; j < 4; j++) { int r = r0 + tx + 8 * j; if (r > M - 1) r = M - 1; bp[j] = A + (long long)r * lda; }
+    for (int k = ka; k < kb; k += 2) {
+        double2 a[8], b[4];
+#pragma unroll
+        for (int i = 0; i < 8; i++) a[i] = ld2(ap[i] + k);
+#pragma unroll
+        for (int j = 0; j < 4; j++) b[j] = ld2(bp[j] + k);
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i].y, b[j].y, fma(a[i].x, b[j].x, acc[i][j]));
+    }
+}
+
+// legacy 32 x 16 NT tile loop over the whole CTA (used by the small static system only)
 template <class Out>
 __device__ __forceinline__ void cta_gemm_nt(const double* __restrict__ A, int lda, int M, const double* __restrict__ B, int ldb, int N,
-                                            int k0, int k1, bool lower_only, Out out) {
+                                            int k0, int k1, Out out) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int tx = lane & 3, ty = lane >> 2;
     const int mt = (M + 31) >> 5, ntl = (N + 15) >> 4;
     for (int tile = warp; tile < mt * ntl; tile += nwarps) {
         const int m0 = (tile / ntl) << 5, n0 = (tile % ntl) << 4;
-        if (lower_only && n0 > m0 + 31) continue;
         const double* ap[4];
         const double* bp[4];
 #pragma unroll
@@ -65,10 +154,7 @@ __device__ __forceinline__ void cta_gemm_nt(const double* __restrict__ A, int ld
         for (int k = k0; k < k1; k += 2) {
             double2 a[4], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                a[i] = *reinterpret_cast<const double2*>(ap[i] + k);
-                b[i] = *reinterpret_cast<const double2*>(bp[i] + k);
-            }
+            for (int i = 0; i < 4; i++) { a[i] = ld2(ap[i] + k); b[i] = ld2(bp[i] + k); }
 #pragma unroll
             for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -88,11 +174,15 @@ __device__ __forceinline__ void cta_gemm_nt(const double* __restrict__ A, int ld
 }
 
 // ------------------------------------------------------------------------------------------------- 16 x 16 building blocks
-// Diagonal block factorisation by ONE warp, entirely in registers: lane l owns row l of the jb x jb block (jb <= 16, padded
-// with identity), pivots / column entries travel by warp shuffle.  Writes L back in place, its transpose into Tdiag
-// (Tdiag[c*16+c2] = L[c2][c]) and the reciprocal diagonal into invd.  Returns 0 or 1 + index of a non-positive pivot.
 #define B200_WLD 18  // leading dimension of the 16 x 16 inverse diagonal block in shared memory (== 2 mod 4)
-__device__ __forceinline__ int warp_potrf16(double* Db, int ld, int jb, double* Tdiag, double* invd, double* Wd) {
+
+// Diagonal block by ONE warp, entirely in registers: lane l owns row l of the jb x jb block (jb <= 16, padded with
+// identity), pivots / column entries travel by warp shuffle.  Produces W = L^-1 (L = Cholesky factor of the block):
+// Wd[i * WLD + l] = W[i][l] (row-major, lower), Tdiag / invd = L^T / reciprocal diagonal (scratch, used by the legacy
+// solver below).  If inv_in_place: the block itself becomes W^T (upper triangle incl. diagonal, strictly lower part
+// zeroed), else L is written back in place (lower) with the strictly lower part of W stashed above the diagonal.
+// Returns 0 or 1 + index of a non-positive pivot (uniform over the warp).
+__device__ __forceinline__ int warp_potrf16(double* Db, int ld, int jb, double* Tdiag, double* invd, double* Wd, bool inv_in_place) {
     const int l = threadIdx.x & 31;
     double r[B200_NB];
 #pragma unroll
@@ -116,7 +206,7 @@ __device__ __forceinline__ int warp_potrf16(double* Db, int ld, int jb, double* 
 #pragma unroll
         for (int c = 0; c < B200_NB; c++) {
             if (c <= l) {
-                if (l < jb && c < jb) Db[(long long)l * ld + c] = r[c];
+                if (!inv_in_place && l < jb && c < jb) Db[(long long)l * ld + c] = r[c];
                 Tdiag[c * B200_NB + l] = r[c];
             }
         }
@@ -136,51 +226,17 @@ __device__ __forceinline__ int warp_potrf16(double* Db, int ld, int jb, double* 
 #pragma unroll
         for (int i = 0; i < B200_NB; i++) {
             Wd[i * B200_WLD + l] = (i >= l) ? w[i] : 0.0;
-            // stash the strictly lower part of W in the (otherwise unused) upper triangle of the diagonal block of L
-            if (i > l && i < jb) Db[(long long)l * ld + i] = w[i];
+            if (inv_in_place) {
+                if (l < jb && i < jb) Db[(long long)l * ld + i] = (i >= l) ? w[i] : 0.0;   // row l of W^T
+            } else {
+                if (i > l && i < jb) Db[(long long)l * ld + i] = w[i];
+            }
         }
     }
     return fail;
 }
 
-// rows x 16 block X (shared, ld) <- X * W^T  (== X * Ljj^-T) on the tensor-less fp64 micro-kernel; jb even.
-__device__ __forceinline__ void cta_rows_times_WT(double* X, int ld, int nrows, int jb, const double* Wd) {
-    cta_gemm_nt(X, ld, nrows, Wd, B200_WLD, jb, 0, jb, false, [&](int m, int c, double v) { X[(long long)m * ld + c] = v; });
-}
-
-// x (one row, 16 entries at xr) <- x * Ljj^-T, right-looking in registers.  Tdiag / invd as written by warp_potrf16
-// (or rebuilt from a slab of L).  jb < 16: only the first jb entries exist.
-__device__ __forceinline__ void row_trisolve16(double* xr, int jb, const double* Tdiag, const double* invd) {
-    double x[B200_NB];
-    if (jb == B200_NB) {
-#pragma unroll
-        for (int c = 0; c < B200_NB; c += 2) {
-            const double2 v = *reinterpret_cast<const double2*>(xr + c);
-            x[c] = v.x; x[c + 1] = v.y;
-        }
-    } else {
-#pragma unroll
-        for (int c = 0; c < B200_NB; c++) x[c] = (c < jb) ? xr[c] : 0.0;
-    }
-#pragma unroll
-    for (int c = 0; c < B200_NB; c++) {
-        if (c < jb) {
-            x[c] *= invd[c];
-#pragma unroll
-            for (int c2 = c + 1; c2 < B200_NB; c2++)
-                if (c2 < jb) x[c2] = fma(-x[c], Tdiag[c * B200_NB + c2], x[c2]);
-        }
-    }
-    if (jb == B200_NB) {
-#pragma unroll
-        for (int c = 0; c < B200_NB; c += 2) *reinterpret_cast<double2*>(xr + c) = make_double2(x[c], x[c + 1]);
-    } else {
-#pragma unroll
-        for (int c = 0; c < B200_NB; c++) if (c < jb) xr[c] = x[c];
-    }
-}
-
-// small static shared scratch shared by the Cholesky and the triangular solve (one instance per kernel)
+// small static shared scratch of the diagonal-block routines (one instance per kernel)
 __device__ __forceinline__ void solve_scratch(double*& Tdiag, double*& Wd, double*& invd) {
     __shared__ __align__(16) double s_Tdiag[B200_NB * B200_NB];
     __shared__ __align__(16) double s_Wd[B200_NB * B200_WLD];
@@ -188,100 +244,144 @@ __device__ __forceinline__ void solve_scratch(double*& Tdiag, double*& Wd, doubl
     Tdiag = s_Tdiag; Wd = s_Wd; invd = s_invd;
 }
 
-// ------------------------------------------------------------------------------------------------- in-smem Cholesky
-// Lower Cholesky of the leading n x n block of the (nrows x n) panel in shared memory (row-major, ld), blocked
-// left-looking; rows [n, nrows) are carried along (they end up multiplied by L^-T, i.e. forward-substituted).
+// ------------------------------------------------------------------------------------------------- fused Cholesky + inverse
+// In: the lower triangle (diagonal included) of the SPD matrix M in Ms (n x n, row-major, ld), strictly upper part ZERO.
+// Out: the upper triangle (diagonal included) holds W^T = L^-T (Ms[k][c] = W[c][k], c >= k); below the diagonal blocks what is
+// left of L remains (the caller clears it).
+// Right-looking, block width 16.  Step j: (a) diagonal block -> W_jj^T (one warp); (b) column block j of every other
+// row times W_jj^T (rows below: the L panel; rows above: the appended identity rows); (c) trailing update with the L panel
+// of the rows that are alive: r >= c (Cholesky) or r < j0 + 16 (appended rows already started).
 // Returns (to all threads) 0 or 1 + index of the first non-positive pivot.  Must be called by all threads of the CTA.
+__device__ int cta_chol_inv(double* Ms, int ld, int n) {
+    __shared__ int fail;
+    double *Tdiag, *Wd, *invd;
+    solve_scratch(Tdiag, Wd, invd);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int ty = lane >> 3, tx = lane & 7;
+    if (threadIdx.x == 0) fail = 0;
+    __syncthreads();
+    PH_T0();
+    for (int j0 = 0; j0 < n; j0 += B200_NB) {
+        const int jb = (n - j0 < B200_NB) ? (n - j0) : B200_NB;
+        if (warp == 0) {
+            const int f = warp_potrf16(Ms + (long long)j0 * ld + j0, ld, jb, Tdiag, invd, Wd, true);
+            if (f && lane == 0) fail = j0 + f;
+        }
+        __syncthreads();
+        PH_ADD(8);
+        if (fail) return fail;
+        // (b) rows r in [0, j0) U [j0 + jb, n): X[r][j0 .. j0+jb) <- X * W_jj^T, 16 (virtual) rows per warp, in place
+        const int nvr = n - jb;
+        for (int t = warp; t * 16 < nvr; t += nwarps) {
+            const double* ap[4];
+            bool ok[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                int vr = t * 16 + ty + 4 * i;
+                ok[i] = vr < nvr;
+                if (!ok[i]) vr = nvr - 1;
+                const int r = (vr < j0) ? vr : vr + jb;
+                ap[i] = Ms + (long long)r * ld + j0;
+            }
+            double acc[4][2];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+#pragma unroll
+            for (int c2 = 0; c2 < B200_NB; c2 += 2) {
+                if (j0 + c2 < n) {
+                    const double2 b0 = ld2(Wd + tx * B200_WLD + c2), b1 = ld2(Wd + (tx + 8) * B200_WLD + c2);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const double2 a = ld2(ap[i] + c2);
+                        acc[i][0] = fma(a.y, b0.y, fma(a.x, b0.x, acc[i][0]));
+                        acc[i][1] = fma(a.y, b1.y, fma(a.x, b1.x, acc[i][1]));
+                    }
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (!ok[i]) continue;
+                double* xr = const_cast<double*>(ap[i]);
+                if (tx < jb) xr[tx] = acc[i][0];
+                if (tx + 8 < jb) xr[tx + 8] = acc[i][1];
+            }
+        }
+        __syncthreads();
+        PH_ADD(9);
+        // (c) trailing update: Ms[r][c] -= sum_t Ms[r][j0+t] Ms[c][j0+t], c >= j0+16, alive rows only
+        const int cb0 = j0 + B200_NB;
+        if (cb0 < n) {
+            const int ntr = (n + 15) >> 4, ntc = (n - cb0 + 31) >> 5;
+            for (int tile = warp; tile < ntr * ntc; tile += nwarps) {
+                const int m0 = (tile / ntc) << 4, c0 = cb0 + ((tile % ntc) << 5);
+                if (m0 >= cb0 && m0 + 15 < c0) continue;   // dead zone: not-yet-started appended rows
+                double acc[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+                warp_mma_nt(Ms, ld, m0, n, Ms, ld, c0, n, j0, cb0, acc);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int r = m0 + ty + 4 * i;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int c = c0 + tx + 8 * j;
+                        if (r < n && c < n && (r >= c || r < cb0)) Ms[(long long)r * ld + c] -= acc[i][j];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        PH_ADD(10);
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------- legacy in-smem Cholesky
+// (only for the small static system of the top level) Lower Cholesky of the leading n x n block of the (nrows x n) panel
+// in shared memory, blocked left-looking; rows [n, nrows) are carried along (they end up multiplied by L^-T).
 __device__ int cta_chol_smem(double* Ms, int ld, int n, int nrows) {
     __shared__ int fail;
     double *Tdiag, *Wd, *invd;
     solve_scratch(Tdiag, Wd, invd);
     if (threadIdx.x == 0) fail = 0;
     __syncthreads();
-    PH_T0();
     for (int j0 = 0; j0 < n; j0 += B200_NB) {
         const int jb = (n - j0 < B200_NB) ? (n - j0) : B200_NB;
         if (j0 > 0) {
             double* Cb = Ms + (long long)j0 * ld + j0;
-            cta_gemm_nt(Ms + (long long)j0 * ld, ld, nrows - j0, Ms + (long long)j0 * ld, ld, jb, 0, j0, false,
+            cta_gemm_nt(Ms + (long long)j0 * ld, ld, nrows - j0, Ms + (long long)j0 * ld, ld, jb, 0, j0,
                         [&](int m, int c, double v) { Cb[(long long)m * ld + c] -= v; });
             __syncthreads();
         }
-        PH_ADD(8);
         if (threadIdx.x < 32) {
-            const int f = warp_potrf16(Ms + (long long)j0 * ld + j0, ld, jb, Tdiag, invd, Wd);
+            const int f = warp_potrf16(Ms + (long long)j0 * ld + j0, ld, jb, Tdiag, invd, Wd, false);
             if (f && threadIdx.x == 0 && fail == 0) fail = j0 + f;
         }
-        PH_ADD(9);
         __syncthreads();
-        if ((jb & 1) == 0) {
-            if (nrows > j0 + jb) cta_rows_times_WT(Ms + (long long)(j0 + jb) * ld + j0, ld, nrows - j0 - jb, jb, Wd);
-        } else {
-            for (int row = j0 + jb + threadIdx.x; row < nrows; row += blockDim.x)
-                row_trisolve16(Ms + (long long)row * ld + j0, jb, Tdiag, invd);
+        // rows below the diagonal block: X <- X * L_jj^-T, right-looking in registers, one row per thread
+        for (int row = j0 + jb + threadIdx.x; row < nrows; row += blockDim.x) {
+            double* xr = Ms + (long long)row * ld + j0;
+            double x[B200_NB];
+#pragma unroll
+            for (int c = 0; c < B200_NB; c++) x[c] = (c < jb) ? xr[c] : 0.0;
+#pragma unroll
+            for (int c = 0; c < B200_NB; c++) {
+                if (c < jb) {
+                    x[c] *= invd[c];
+#pragma unroll
+                    for (int c2 = c + 1; c2 < B200_NB; c2++)
+                        if (c2 < jb) x[c2] = fma(-x[c], Tdiag[c * B200_NB + c2], x[c2]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < B200_NB; c++) if (c < jb) xr[c] = x[c];
         }
         __syncthreads();
-        PH_ADD(10);
     }
     return fail;
-}
-
-// copy rows [r0, r0+nr) x cols [0, w) (w even) of a global row-major matrix (ldg even) into shared rows (ld even), async
-__device__ __forceinline__ void cp_rows_async(double* dst, int ld, const double* __restrict__ src, int ldg, int nr, int w) {
-    const int w2 = (w + 1) >> 1;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int r = warp; r < nr; r += nwarps)
-        for (int c2 = lane; c2 < w2; c2 += 32) cp_async16(dst + (long long)r * ld + 2 * c2, src + (long long)r * ldg + 2 * c2);
-}
-
-// rows (cr x n, shared, ld) <- rows * L^-T where L (n x n lower, upper part zero) is streamed block-row by block-row from
-// global memory (ldg) through two shared slabs (NB x ld each), the next slab being fetched (cp.async) while the current
-// block column is updated and solved.
-__device__ void cta_trsm_rows(double* Ps, int ld, int cr, int n, const double* __restrict__ Lg, int ldg, double* slab0, double* slab1) {
-    double *Tdiag, *Wd, *invd;
-    solve_scratch(Tdiag, Wd, invd);
-    {
-        const int jb0 = (n < B200_NB) ? n : B200_NB;
-        cp_rows_async(slab0, ld, Lg, ldg, jb0, jb0 + (jb0 & 1));
-    }
-    int blk = 0;
-    PH_T0();
-    for (int j0 = 0; j0 < n; j0 += B200_NB, blk++) {
-        const int jb = (n - j0 < B200_NB) ? (n - j0) : B200_NB;
-        double* Ls = (blk & 1) ? slab1 : slab0;
-        double* Ln = (blk & 1) ? slab0 : slab1;
-        cp_async_wait_all();
-        __syncthreads();
-        PH_ADD(11);
-        if (j0 + jb < n) {
-            const int j1 = j0 + jb;
-            const int jb1 = (n - j1 < B200_NB) ? (n - j1) : B200_NB;
-            const int w1 = j1 + jb1;
-            cp_rows_async(Ln, ld, Lg + (long long)j1 * ldg, ldg, jb1, w1 + (w1 & 1));
-        }
-        if (threadIdx.x < B200_NB * B200_NB) {
-            const int c = threadIdx.x / B200_NB, c2 = threadIdx.x % B200_NB;
-            if (c2 >= c && c2 < jb) Tdiag[c * B200_NB + c2] = Ls[(long long)c2 * ld + j0 + c];
-            if (c2 == c && c < jb) invd[c] = 1.0 / Ls[(long long)c * ld + j0 + c];
-            // W (inverse of the diagonal block): strictly lower part stashed above the diagonal of L, diagonal = 1/L_cc
-            double wv = 0.0;
-            if (c < jb && c2 < jb) {
-                if (c2 == c) wv = 1.0 / Ls[(long long)c * ld + j0 + c];
-                else if (c2 < c) wv = Ls[(long long)c2 * ld + j0 + c];
-            } else if (c == c2) wv = 1.0;
-            Wd[c * B200_WLD + c2] = wv;
-        }
-        if (j0 > 0) {
-            double* Cb = Ps + j0;
-            cta_gemm_nt(Ps, ld, cr, Ls, ld, jb, 0, j0, false, [&](int m, int c, double v) { Cb[(long long)m * ld + c] -= v; });
-        }
-        __syncthreads();
-        PH_ADD(12);
-        if ((jb & 1) == 0) cta_rows_times_WT(Ps + j0, ld, cr, jb, Wd);
-        else for (int row = threadIdx.x; row < cr; row += blockDim.x) row_trisolve16(Ps + (long long)row * ld + j0, jb, Tdiag, invd);
-        PH_ADD(13);
-    }
-    __syncthreads();
 }
 
 // x <- L^-T x for the n x n lower factor in shared memory (ld); x in shared memory (tv).  Blocked: the 16 x 16 diagonal
@@ -315,6 +415,19 @@ __device__ void cta_solve_LT(const double* Ms, int ld, int n, double* tv) {
     }
 }
 
+// copy the lower triangle (rows [0, nr), columns [0, r] rounded up to a pair) of a global row-major matrix into shared rows
+__device__ __forceinline__ void cp_lower_async(double* dst, int ld, const double* __restrict__ src, int ldg, int nr) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int r = warp; r < nr; r += nwarps)
+        for (int c2 = lane; 2 * c2 <= r; c2 += 32) cp_async16(dst + (long long)r * ld + 2 * c2, src + (long long)r * ldg + 2 * c2);
+}
+// copy the upper triangle (columns [r & ~1, w)) of a global row-major matrix into shared rows
+__device__ __forceinline__ void cp_upper_async(double* dst, int ld, const double* __restrict__ src, int ldg, int nr, int w) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int r = warp; r < nr; r += nwarps)
+        for (int c2 = (r >> 1) + lane; 2 * c2 < w; c2 += 32) cp_async16(dst + (long long)r * ld + 2 * c2, src + (long long)r * ldg + 2 * c2);
+}
+
 // ------------------------------------------------------------------------------------------------- the sweep
 struct SweepArgs {
     // sources, indexed by src index (src0 + i)
@@ -328,245 +441,337 @@ struct SweepArgs {
     const double* Oleft; // O block of the left separator (nullptr: none) -> arrow rows [ns1, ns1+nc)
     int h;               // arrow height of this sweep: ns1 (+ nc with a left separator)
     double lambda;
-    double* Lst;         // [storage idx][ntp*ntp]
-    double* Pst;         // [storage idx][(nc+hmax)*ntp]  rows [0,nc): X, rows [nc, nc+h): arrow
-    double* F;           // 2 x [(nc+hmax)*nc] ping-pong fill buffers of this sweep
-    double* Sacc;        // [hmax*hmax] (lower triangle) Schur complement accumulated by this sweep
+    double* Wst;         // [storage idx][ntp*ntp]   W^T = L^-T of the pivot block (upper triangle, lower part zero)
+    double* Yst;         // [storage idx][hmax*ntp]  forward-substituted arrow rows y = p W^T
+    double* F;           // 2 x [(nc+hmax)*nc] ping-pong fill buffers of this sweep (rows [0,nc): lower triangle only)
+    double* Sacc;        // [hmax*hmax] (lower triangle) Schur complement of this sweep (chain_schur_kernel)
     int* status;
-    int rmax;            // rows of the panel resident in shared memory at a time
+    int dense_o;         // the coupling blocks are dense (reduced systems of the upper levels), else block-sparse (dm.orow)
 };
 
-// shared-memory carve-up (doubles): phase A uses [0, ntp*ld) ; phase B: Ps [rmax*ld] | Ls [NB*ld] | Bs [32*ld]
-__host__ __device__ inline long long sweep_smem_doubles(int ntp, int ld, int rmax) {
-    long long a = (long long)ntp * ld + 256 + 256 + 1024 + 512, b = (long long)(rmax + B200_NB + 32) * ld;
+// shared-memory carve-up of the sweep (doubles): Ms [ntp*ld] | Yb [cr*ld] | Op [max(nc*owp, 2*nc*OSLD)]
+#define B200_OSLD 18   // row stride of a 16-column slab of a dense coupling block (== 2 mod 4)
+__host__ __device__ inline long long sweep_op_doubles(int nc, int owp) {
+    const long long a = ((long long)nc * owp + 1) & ~1LL, b = 2LL * nc * B200_OSLD;
     return a > b ? a : b;
+}
+__host__ __device__ inline long long sweep_smem_doubles(int ntp, int ld, int cr, int nc, int owp) {
+    return (long long)ntp * ld + (long long)cr * ld + sweep_op_doubles(nc, owp);
 }
 __host__ __device__ inline int static_lds(int ns) { int lds = ns + (ns & 1); while ((lds & 3) != 2) lds += 2; return lds; }
 
+// [ka, kb) (even bounds, time-block coordinates) of the columns in which rows [r0, r0+16) of O can be non-zero
+__device__ __forceinline__ void xrow_range(const Dims& dm, bool dense, int r0, int& ka, int& kb) {
+    if (dense) { ka = dm.nl & ~1; kb = dm.ntp; return; }
+    const int lane = threadIdx.x & 31;
+    int lo = dm.ntp, hi = 0;
+    const int r = r0 + (lane & 15);
+    if (r < dm.nc) {
+        const int c0 = dm.orow[2 * r], c1 = dm.orow[2 * r + 1];
+        if (c1 > c0) { lo = (dm.nl + c0) & ~1; hi = (dm.nl + c1 + 1) & ~1; }
+    }
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) {
+        const int lo2 = __shfl_xor_sync(0xffffffffu, lo, o), hi2 = __shfl_xor_sync(0xffffffffu, hi, o);
+        lo = lo2 < lo ? lo2 : lo; hi = hi2 > hi ? hi2 : hi;
+    }
+    ka = lo; kb = hi > dm.ntp ? dm.ntp : hi;
+}
+
 __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
-    const int ntp = dm.ntp, nl = dm.nl, nc = dm.nc, ns1 = dm.ns1, ld = dm.ld, hmax = dm.hmax;
+    const int n = dm.ntp, nl = dm.nl, nc = dm.nc, ns1 = dm.ns1, ld = dm.ld, hmax = dm.hmax, CR = dm.cr, ow = dm.ow, owp = dm.owp;
     const int h = a.h;
     const long long Fsz = (long long)(nc + hmax) * nc;
-    for (int i = threadIdx.x; i < hmax * hmax; i += blockDim.x) a.Sacc[i] = 0.0;
-    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int ty = lane >> 3, tx = lane & 7;
+    double* Ms = sm;
+    double* Yb = sm + (long long)n * ld;
+    double* Op = Yb + (long long)CR * ld;
+    const int kz0 = nl & ~1;                        // first column of z that is needed (chain columns, pair aligned)
     for (int i = 0; i < a.n; i++) {
         const long long src = a.src0 + i;
         const long long st = a.st_idx ? a.st_idx[i] : src;
-        const bool has_x = (i + 1 < a.n) || a.has_right;
+        const bool has_x = nc > 0 && ((i + 1 < a.n) || a.has_right);
         const double* Fin = a.F + (long long)(i & 1) * Fsz;
         double* Fout = a.F + (long long)((i + 1) & 1) * Fsz;
-        double* Lg = a.Lst + st * ntp * ntp;
-        double* Pg = a.Pst + st * (long long)(nc + hmax) * ntp;
+        double* Wg = a.Wst + st * n * n;
+        double* Yg = a.Yst + st * (long long)hmax * n;
         const double* Og = a.Osrc + src * nc * nc;
-        const double* Ag = a.Asrc + src * ns1 * ntp;
-        // ---------------- phase A: pivot block  Dacc = D + lambda I - fill
+        const double* Ag = a.Asrc + src * ns1 * n;
+        // ---------------- phase A: pivot block  M = D + lambda I - fill ; W^T = chol(M)^-T
         PH_T0();
-        {
-            const double* Dg = a.Dsrc + src * ntp * ntp;
-            cp_rows_async(sm, ld, Dg, ntp, ntp, ntp);
-            if (i + 1 < a.n) {  // pull the next keyframe's blocks towards L2 while this one is factorised
-                const double* Dn = a.Dsrc + (src + 1) * ntp * ntp;
-                for (int e = threadIdx.x * 16; e < ntp * ntp; e += blockDim.x * 16) prefetch_l2(Dn + e);
+        __syncthreads();   // previous node done with Ms / Yb / Op
+        cp_lower_async(Ms, ld, a.Dsrc + src * n * n, n, n);
+        if (has_x && !a.dense_o) {   // packed rows of O: Op[r][t] = O[r][ozs[r] - nl + t]
+            for (int e = threadIdx.x; e < nc * ow; e += blockDim.x) {
+                const int r = e / ow, t = e - r * ow;
+                const int cc = dm.ozs[r] - nl + t;
+                if (cc >= 0 && cc < nc) cp_async8(Op + r * owp + t, Og + (long long)r * nc + cc);
+                else Op[r * owp + t] = 0.0;
             }
-            cp_async_wait_all();
-            __syncthreads();
-            for (int r = threadIdx.x; r < ntp; r += blockDim.x) sm[r * ld + r] += a.lambda;
-            if (i > 0) {
-                const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-                for (int r = warp; r < nc; r += nwarps) {
-                    const double* fr = Fin + (long long)r * nc;
-                    double* dr = sm + (nl + r) * ld + nl;
-#pragma unroll 4
-                    for (int c = lane; c < nc; c += 32) dr[c] -= fr[c];
+        }
+        if (i + 1 < a.n) {  // pull the next node's pivot block towards L2 while this one is factorised
+            const double* Dn = a.Dsrc + (src + 1) * n * n;
+            for (int e = threadIdx.x * 16; e < n * n; e += blockDim.x * 16) prefetch_l2(Dn + e);
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        for (int r = warp; r < n; r += nwarps) {
+            double* row = Ms + (long long)r * ld;
+            const bool chain_r = (i > 0) && r >= nl;
+            const double* fr = Fin + (long long)(r - nl) * nc - nl;
+            for (int c = lane; c < n; c += 32) {
+                if (c > r) row[c] = 0.0;
+                else {
+                    double v = row[c];
+                    if (c == r) v += a.lambda;
+                    if (chain_r && c >= nl) v -= fr[c];
+                    row[c] = v;
                 }
             }
-            __syncthreads();
-            PH_ADD(0);
-            const int fail = cta_chol_smem(sm, ld, ntp, ntp);
-            PH_ADD(1);
-            if (fail) {
-                if (threadIdx.x == 0) atomicCAS(a.status, 0, (int)(st + 1));
-                return;
-            }
-            {
-                const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-                for (int r = warp; r < ntp; r += nwarps)
-                    for (int c = 2 * lane; c < ntp; c += 64) {
-                        const double2 v = *reinterpret_cast<const double2*>(sm + r * ld + c);
-                        const bool diag_blk = (c / B200_NB) == (r / B200_NB);   // (c even: c and c+1 share the block)
-                        *reinterpret_cast<double2*>(Lg + (long long)r * ntp + c) =
-                            make_double2((c <= r || diag_blk) ? v.x : 0.0, (c + 1 <= r || diag_blk) ? v.y : 0.0);
-                    }
-            }
-            __threadfence_block();
-            __syncthreads();
-            PH_ADD(2);
         }
-        // ---------------- phase B: panel rows [X (nc, if has_x) ; arrow (h)]
-        double* Ps = sm;
-        double* Ls = sm + (long long)a.rmax * ld;
-        double* Bs = Ls + (long long)B200_NB * ld;
+        __syncthreads();
+        PH_ADD(0);
+        const int fail = cta_chol_inv(Ms, ld, n);
+        PH_ADD(1);
+        if (fail) {
+#ifdef B200_USE_EMU
+            if (threadIdx.x == 0 && std::getenv("B200_EMU_DEBUG")) printf("pivot failure: node %d (storage %lld) index %d\n", i, st, fail - 1);
+#endif
+            if (threadIdx.x == 0) atomicCAS(a.status, 0, (int)(st + 1));
+            return;
+        }
+        // clear what is left of L below the diagonal (the GEMMs below rely on W^T being upper triangular) and store W^T
+        for (int r = warp; r < n; r += nwarps)
+            for (int c = 2 * lane; c < n; c += 64) {
+                double2 v = ld2(Ms + (long long)r * ld + c);
+                if (c < r) { v.x = 0.0; if (c + 1 < r) v.y = 0.0; st2(Ms + (long long)r * ld + c, v.x, v.y); }
+                st2(Wg + (long long)r * n + c, v.x, v.y);
+            }
+        PH_ADD(2);
+        // ---------------- phase B: panel rows [X (nc, if has_x) ; arrow (h)] in chunks of <= CR rows
         const int xo = has_x ? nc : 0;
-        const int Rn = xo + h;
-        const double* Sg = a.Ssrc + src * ns1 * ns1;   // this node's own static block, folded into the Schur update below
-        const int nchunks = (Rn + a.rmax - 1) / a.rmax;
-        const int csz = (Rn + nchunks - 1) / nchunks;
-        for (int ch = 0; ch < nchunks; ch++) {
-            const int r0 = ch * csz;
-            const int cr = (Rn - r0 < csz) ? (Rn - r0) : csz;
-            __syncthreads();
-            // load rows (one warp per row): sources through cp.async, then the fill correction in shared memory
-            {
-                const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+        for (int seg = 0; seg < 2; seg++) {
+            const int base = seg == 0 ? 0 : xo, cnt = seg == 0 ? xo : h;
+            if (cnt == 0) continue;
+            const int nch = (cnt + CR - 1) / CR;
+            int csz = (cnt + nch - 1) / nch;
+            csz = (csz + 15) & ~15;
+            for (int ch = 0; ch < nch; ch++) {
+                const int r0 = base + ch * csz;
+                const int cr = (base + cnt - r0 < csz) ? (base + cnt - r0) : csz;
+                __syncthreads();   // Yb free
+                // ---- load rows (one warp per row): sources through cp.async, then the fill correction in shared memory
                 for (int lr = warp; lr < cr; lr += nwarps) {
                     const int pr = r0 + lr;
-                    double* dst = Ps + lr * ld;
-                    if (pr < xo) {
+                    double* dst = Yb + (long long)lr * ld;
+                    if (seg == 0) {
                         const double* og = Og + (long long)pr * nc - nl;
-                        for (int c = lane; c < ntp; c += 32) {
+                        for (int c = lane; c < n; c += 32) {
                             if (c >= nl) cp_async8(dst + c, og + c);
                             else dst[c] = 0.0;
                         }
                     } else {
                         const int ar = pr - xo;
                         if (ar < ns1) {
-                            const double* ag = Ag + (long long)ar * ntp;
-                            for (int c = 2 * lane; c < ntp; c += 64) cp_async16(dst + c, ag + c);
+                            const double* ag = Ag + (long long)ar * n;
+                            for (int c = 2 * lane; c < n; c += 64) cp_async16(dst + c, ag + c);
                         } else if (i == 0 && a.Oleft) {
                             const double* ol = a.Oleft + (ar - ns1);
-                            for (int c = lane; c < ntp; c += 32) dst[c] = (c >= nl) ? ol[(long long)(c - nl) * nc] : 0.0;
+                            for (int c = lane; c < n; c += 32) dst[c] = (c >= nl) ? ol[(long long)(c - nl) * nc] : 0.0;
                         } else {
-                            for (int c = lane; c < ntp; c += 32) dst[c] = 0.0;
+                            for (int c = lane; c < n; c += 32) dst[c] = 0.0;
                         }
                     }
                 }
                 cp_async_wait_all();
                 __syncthreads();
-                if (i > 0) {
-                    // arrow rows of this chunk: subtract Y_prev X_prev^T (chain columns)
+                if (seg == 1 && i > 0) {
+                    // arrow rows: subtract the fill  Y_prev Dinv O^T  (chain columns)
                     for (int lr = warp; lr < cr; lr += nwarps) {
-                        const int pr = r0 + lr;
-                        if (pr < xo) continue;
-                        const double* fr = Fin + (long long)(nc + pr - xo) * nc;
-                        double* dr = Ps + lr * ld + nl;
+                        const double* fr = Fin + (long long)(nc + r0 - xo + lr) * nc;
+                        double* dr = Yb + (long long)lr * ld + nl;
 #pragma unroll 4
                         for (int c = lane; c < nc; c += 32) dr[c] -= fr[c];
                     }
+                    __syncthreads();
                 }
-            }
-            // (cta_trsm_rows starts with a barrier)
-            __syncthreads();
-            PH_ADD(3);
-            cta_trsm_rows(Ps, ld, cr, ntp, Lg, ntp, Ls, Bs);
-            PH_ADD(4);
-            // store
-            {
-                const int sro_ = has_x ? 0 : nc;
-                const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-                for (int lr = warp; lr < cr; lr += nwarps)
-                    for (int c = 2 * lane; c < ntp; c += 64)
-                        *reinterpret_cast<double2*>(Pg + (long long)(sro_ + r0 + lr) * ntp + c) = *reinterpret_cast<const double2*>(Ps + lr * ld + c);
-            }
-            __syncthreads();
-            PH_ADD(5);
-            // rank update, diagonal chunk pair
-            auto emit = [&](int sr1, int sr2, double v) {
-                // sr1 >= sr2 (storage rows)
-                if (sr1 < nc) {
-                    Fout[(long long)sr1 * nc + sr2] = v;
-                    if (sr1 != sr2) Fout[(long long)sr2 * nc + sr1] = v;
-                } else if (sr2 < nc) {
-                    Fout[(long long)sr1 * nc + sr2] = v;
-                } else {
-                    // exactly one reduction per entry and step (own static block - Y Y^T): deterministic, never mixed with
-                    // plain loads of Sacc inside the sweep (atomics resolve in L2)
-                    const int a1 = sr1 - nc, a2 = sr2 - nc;
-                    double add = -v;
-                    if (a1 < ns1) add += Sg[a1 * ns1 + a2];
-                    atomicAdd(a.Sacc + (long long)a1 * hmax + a2, add);
-                }
-            };
-            const int sro = has_x ? 0 : nc;  // storage row of present row 0
-            cta_gemm_nt(Ps, ld, cr, Ps, ld, cr, 0, ntp, true, [&](int m, int n2, double v) {
-                if (n2 <= m) emit(sro + r0 + m, sro + r0 + n2, v);
-            });
-            // cross terms with earlier chunks, streamed back from global memory 32 rows at a time
-            for (int p0 = 0; p0 < r0; p0 += 32) {
-                const int pb = (r0 - p0 < 32) ? (r0 - p0) : 32;
-                __syncthreads();
-                cp_rows_async(Bs, ld, Pg + (long long)(sro + p0) * ntp, ntp, pb, ntp);
-                cp_async_wait_all();
-                __syncthreads();
-                cta_gemm_nt(Ps, ld, cr, Bs, ld, pb, 0, ntp, false,
-                            [&](int m, int n2, double v) { emit(sro + r0 + m, sro + p0 + n2, v); });
-            }
-        }
-        __threadfence_block();
-        __syncthreads();
-        PH_ADD(6);
-    }
-}
-
-// back-substitution over the nodes of a sweep (reverse order).  coefA = [delta_static (ns), -1, delta_left_chain (nc)].
-// delta (global) [storage idx][ntp].  right_st: storage index of the right neighbour (or -1).
-__device__ void cta_backsub(const Dims& dm, const SweepArgs& a, const double* coefA, long long right_st, double* delta, double* sm) {
-    const int ntp = dm.ntp, nl = dm.nl, nc = dm.nc, ld = dm.ld, hmax = dm.hmax;
-    const int h = a.h;
-    double* Ms = sm;                 // L in shared memory, then scratch vectors (ntp, nc <= 256)
-    double* tvec = sm + (long long)ntp * ld;
-    double* cx = tvec + 256;
-    double* tpart = cx + 256;        // blockDim.x doubles
-    for (int i = a.n - 1; i >= 0; i--) {
-        const long long src = a.src0 + i;
-        const long long st = a.st_idx ? a.st_idx[i] : src;
-        const bool has_x = (i + 1 < a.n) || a.has_right;
-        const double* Lg = a.Lst + st * ntp * ntp;
-        const double* Pg = a.Pst + st * (long long)(nc + hmax) * ntp;
-        long long nxt = -1;
-        if (i + 1 < a.n) nxt = a.st_idx ? a.st_idx[i + 1] : src + 1;
-        else if (a.has_right) nxt = right_st;
-        __syncthreads();
-        cp_rows_async(Ms, ld, Lg, ntp, ntp, ntp);
-        if (has_x) for (int j = threadIdx.x; j < nc; j += blockDim.x) cx[j] = delta[nxt * ntp + nl + j];
-        __syncthreads();
-        // t[c] = - sum_r P[r][c] * coef[r]; thread groups of 128 split the rows, column passes of 128
-        {
-            const int grp = threadIdx.x >> 7, ngrp = blockDim.x >> 7;
-            for (int cb = 0; cb < ntp; cb += 128) {
-                const int c = cb + (threadIdx.x & 127);
-                double t = 0.0;
-                if (c < ntp) {
-                    if (has_x) {
-#pragma unroll 4
-                        for (int r = grp; r < nc; r += ngrp) t = fma(-Pg[(long long)r * ntp + c], cx[r], t);
+                PH_ADD(3);
+                const int rtiles = (cr + 15) >> 4;
+                const int tpw = nwarps / rtiles;              // column tiles per wave (rtiles <= CR/16 <= nwarps)
+                // ---- y = p W^T : column-tile waves from the right, results written back in place after a barrier
+                {
+                    const int nct = (n + 31) >> 5;
+                    for (int hi = nct; hi > 0; hi -= tpw) {
+                        const int lo = hi - tpw > 0 ? hi - tpw : 0;
+                        const int slot = warp % tpw, rt = warp / tpw;
+                        // spread long and short column tiles over the four schedulers (warp & 3)
+                        const int ct = lo + (slot + rt) % tpw;
+                        const bool act = rt < rtiles && ct < hi;
+                        double acc[4][4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+#pragma unroll
+                            for (int j = 0; j < 4; j++) acc[q][j] = 0.0;
+                        const int m0 = rt << 4, c0 = ct << 5;
+                        if (act) {
+                            int ka = 0, kb = n;
+                            if (seg == 0) xrow_range(dm, a.dense_o != 0, r0 + m0, ka, kb);
+                            const int kend = (c0 + 32 < kb) ? c0 + 32 : kb;
+                            warp_mma_nn(Yb, ld, m0, cr, Ms, ld, c0, n, ka, kend, acc);
+                        }
+                        __syncthreads();
+                        if (act) {
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const int lr = m0 + ty + 4 * q;
+                                if (lr >= cr) continue;
+#pragma unroll
+                                for (int j = 0; j < 2; j++) {
+                                    const int c = c0 + 2 * tx + 16 * j;
+                                    if (c >= n) continue;
+                                    st2(Yb + (long long)lr * ld + c, acc[q][2 * j], acc[q][2 * j + 1]);
+                                    if (seg == 1) st2(Yg + (long long)(r0 - xo + lr) * n + c, acc[q][2 * j], acc[q][2 * j + 1]);
+                                }
+                            }
+                        }
+                        __syncthreads();
                     }
-#pragma unroll 4
-                    for (int r = grp; r < h; r += ngrp) t = fma(-Pg[(long long)(nc + r) * ntp + c], coefA[r], t);
                 }
-                tpart[threadIdx.x] = t;
-                __syncthreads();
-                if (grp == 0 && c < ntp) {
-                    double acc = 0.0;
-                    for (int q = 0; q < ngrp; q++) acc += tpart[q * 128 + (threadIdx.x & 127)];
-                    tvec[c] = acc;
+                PH_ADD(4);
+                if (!has_x) continue;
+                // ---- z = y W (chain columns only), in place after a barrier
+                {
+                    const int nct = (n - kz0 + 31) >> 5;
+                    for (int lo = 0; lo < nct; lo += tpw) {
+                        const int hi = lo + tpw < nct ? lo + tpw : nct;
+                        const int slot = warp % tpw, rt = warp / tpw;
+                        const int ct = lo + (slot + rt) % tpw;
+                        const bool act = rt < rtiles && ct < hi;
+                        double acc[4][4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+#pragma unroll
+                            for (int j = 0; j < 4; j++) acc[q][j] = 0.0;
+                        const int m0 = rt << 4, k0 = kz0 + (ct << 5);
+                        if (act) {
+                            int ca = k0;
+                            if (seg == 0) { int ka, kb; xrow_range(dm, a.dense_o != 0, r0 + m0, ka, kb); if (ka > ca) ca = ka; }
+                            warp_mma_nt(Yb, ld, m0, cr, Ms, ld, k0, n, ca, n, acc);
+                        }
+                        __syncthreads();
+                        if (act) {
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const int lr = m0 + ty + 4 * q;
+                                if (lr >= cr) continue;
+#pragma unroll
+                                for (int j = 0; j < 4; j++) {
+                                    const int c = k0 + tx + 8 * j;
+                                    if (c < n) Yb[(long long)lr * ld + c] = acc[q][j];
+                                }
+                            }
+                        }
+                        __syncthreads();
+                    }
                 }
-                __syncthreads();
+                PH_ADD(5);
+                // ---- fill rows  F = z[:, chain] O^T
+                if (a.dense_o) {
+                    // dense coupling block: O streams through two 16-column slabs (cp.async), accumulators stay in registers
+                    const int nsl = (n - kz0 + 15) >> 4;
+                    const int nctf = (nc + 31) >> 5;
+                    auto load_slab = [&](int sidx, double* Os) {
+                        const int cbase = kz0 - nl + 16 * sidx;
+                        for (int e = threadIdx.x; e < nc * 16; e += blockDim.x) {
+                            const int j = e >> 4, t = e & 15, cc = cbase + t;
+                            if (cc >= 0 && cc < nc) cp_async8(Os + j * B200_OSLD + t, Og + (long long)j * nc + cc);
+                            else Os[j * B200_OSLD + t] = 0.0;
+                        }
+                    };
+                    for (int lo = 0; lo < nctf; lo += tpw) {
+                        const int slot = warp % tpw, rt = warp / tpw;
+                        const int ct = lo + slot;
+                        const bool act = rt < rtiles && ct < nctf;
+                        double acc[4][4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+#pragma unroll
+                            for (int j = 0; j < 4; j++) acc[q][j] = 0.0;
+                        const int m0 = rt << 4;
+                        load_slab(0, Op);
+                        for (int sidx = 0; sidx < nsl; sidx++) {
+                            cp_async_wait_all();
+                            __syncthreads();
+                            if (sidx + 1 < nsl) load_slab(sidx + 1, Op + ((sidx + 1) & 1) * nc * B200_OSLD);
+                            int kw = n - kz0 - 16 * sidx; if (kw > 16) kw = 16;
+                            if (act) warp_mma_nt(Yb + kz0 + 16 * sidx, ld, m0, cr, Op + (sidx & 1) * nc * B200_OSLD, B200_OSLD, ct << 5, nc, 0, kw, acc);
+                        }
+                        if (act) {
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const int lr = m0 + ty + 4 * q;
+                                if (lr >= cr) continue;
+#pragma unroll
+                                for (int j = 0; j < 4; j++) {
+                                    const int ci = (ct << 5) + tx + 8 * j;
+                                    if (ci < nc) Fout[(long long)(r0 + lr) * nc + ci] = acc[q][j];
+                                }
+                            }
+                        }
+                        __syncthreads();
+                    }
+                } else {
+                    const int ng = (nc + 31) >> 5;
+                    const int nq = (nwarps / ng) > 0 ? (nwarps / ng) : 1;
+                    const int rpq = (cr + nq - 1) / nq;
+                    for (int item = warp; item < ng * nq; item += nwarps) {
+                        const int g = item % ng, q = item / ng;
+                        const int ci = 32 * g + lane;
+                        const bool act = ci < nc;
+                        const int cic = act ? ci : nc - 1;
+                        const int zs = dm.ozs[cic];
+                        const int lr1 = ((q + 1) * rpq < cr) ? (q + 1) * rpq : cr;
+                        if (ow <= 16) {
+                            double op[16];
+#pragma unroll
+                            for (int t = 0; t < 16; t += 2) {
+                                if (t < ow) { const double2 v = ld2(Op + cic * owp + t); op[t] = v.x; op[t + 1] = v.y; }
+                                else { op[t] = 0.0; op[t + 1] = 0.0; }
+                            }
+                            for (int lr = q * rpq; lr < lr1; lr++) {
+                                const double* z = Yb + (long long)lr * ld + zs;
+                                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                                for (int t = 0; t < 16; t += 2) {
+                                    if (t < ow) { const double2 v = ld2(z + t); s0 = fma(v.x, op[t], s0); s1 = fma(v.y, op[t + 1], s1); }
+                                }
+                                if (act) Fout[(long long)(r0 + lr) * nc + ci] = s0 + s1;
+                            }
+                        } else {
+                            for (int lr = q * rpq; lr < lr1; lr++) {
+                                const double* z = Yb + (long long)lr * ld + zs;
+                                const double* o = Op + cic * owp;
+                                double s0 = 0.0;
+                                for (int t = 0; t < ow; t++) s0 = fma(z[t], o[t], s0);
+                                if (act) Fout[(long long)(r0 + lr) * nc + ci] = s0;
+                            }
+                        }
+                    }
+                }
+                PH_ADD(6);
             }
         }
-        cp_async_wait_all();
-        __syncthreads();
-        cta_solve_LT(Ms, ld, ntp, tvec);
-        for (int c = threadIdx.x; c < ntp; c += blockDim.x) delta[st * ntp + c] = tvec[c];
         __threadfence_block();
     }
     __syncthreads();
 }
 
-// ------------------------------------------------------------------------------------------------- kernels
+// ------------------------------------------------------------------------------------------------- levels
 // One level of the nested partition.  Level 0: nodes = keyframes (sources = assembled blocks, storage index = node index).
-// Level l+1: nodes = the separators of level l (sources = the reduced blocks written by level_reduce_kernel, storage index =
+// Level l+1: nodes = the separators of level l (sources = the reduced blocks written by chain_reduce_kernel, storage index =
 // the separator's keyframe).  The nodes of a level are cut into P chunks; the last node of every chunk but the last is that
-// chunk's separator and becomes a node of the next level.
+// chunk's separator and becomes a node of the next level.  The top level is a Level with P == 1.
 struct Level {
     const double *Dsrc, *Osrc, *Asrc, *Ssrc;  // per node: [ntp*ntp], [nc*nc], [ns1*ntp], [ns1*ns1]
     const int* st;                            // storage (keyframe) index per node, nullptr = identity
@@ -576,11 +781,12 @@ struct Level {
     double *S;                                // [P][hmax*hmax] arrow Schur complement of each chunk sweep
     double *Dred, *Ored, *Ared, *Sred;        // [P-1] reduced sources == next level's node sources
     int* sep_st;                              // [P-1] storage index of separator c == next level's st
+    int dense_o;                              // coupling blocks of this level are dense (reduced systems)
 };
 
 struct SolveBuffers {
-    double *Lst, *Pst;                        // factors, per storage index (keyframe)
-    double *Ftop, *Stop;                      // scratch of the top-level sweep
+    double *Wst, *Yst;                        // factors, per storage index (keyframe)
+    double *ybuf;                             // [storage idx][ntp]  y = Y^T coef of the back-substitution pre-pass
     double *delta, *dstat;                    // solution (internal order), delta per storage index
     double* scal;                             // scalar outputs
     int* status;
@@ -595,25 +801,97 @@ __device__ __forceinline__ void level_chunk_args(const Dims& dm, const Level& lv
     a.has_right = (c < lv.P - 1);
     a.Oleft = (c > 0) ? lv.Osrc + (long long)(kb - 1) * dm.nc * dm.nc : nullptr;
     a.h = dm.ns1 + ((c > 0) ? dm.nc : 0);
-    a.Lst = sb.Lst; a.Pst = sb.Pst;
+    a.Wst = sb.Wst; a.Yst = sb.Yst;
     a.F = lv.F + (long long)c * 2 * (dm.nc + dm.hmax) * dm.nc;
     a.Sacc = lv.S + (long long)c * dm.hmax * dm.hmax;
     a.status = sb.status;
+    a.lambda = 0.0;
+    a.dense_o = lv.dense_o;
 }
 
 // grid = number of chunks of this level owned by this rank (chunk = c_first + blockIdx.x)
-__global__ void __launch_bounds__(B200_SOLVE_THREADS) level_sweep_kernel(Dims dm, Level lv, SolveBuffers sb, double lambda, int rmax, int c_first) {
+__global__ void __launch_bounds__(B200_SOLVE_THREADS) chain_sweep_kernel(Dims dm, Level lv, SolveBuffers sb, double lambda, int c_first) {
     B200_DYN_SMEM(double, sm);
     SweepArgs a;
     level_chunk_args(dm, lv, sb, c_first + blockIdx.x, a);
     a.lambda = lambda;
-    a.rmax = rmax;
     cta_sweep(dm, a, sm);
+}
+
+// Arrow Schur complement of one chunk sweep:  Sacc = sum_nodes ( S_node - Y_node Y_node^T ), lower triangle of h x h.
+// One CTA per chunk, 12 warps; every warp owns up to two 32 x 32 output tiles whose accumulators stay in registers over
+// all nodes of the chunk (fixed summation order, no atomics).  The stored panel of a node is staged through shared memory.
+__global__ void __launch_bounds__(B200_SCHUR_THREADS) chain_schur_kernel(Dims dm, Level lv, SolveBuffers sb, int c_first, int ldy, int kslab) {
+    B200_DYN_SMEM(double, Ys);
+    SweepArgs a;
+    level_chunk_args(dm, lv, sb, c_first + blockIdx.x, a);
+    const int n = dm.ntp, ns1 = dm.ns1, hmax = dm.hmax, h = a.h;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int ty = lane >> 3, tx = lane & 7;
+    if (*sb.status != 0) return;
+    const int nrt = (h + 31) >> 5;
+    const int ntiles = nrt * (nrt + 1) / 2;
+    for (int base = 0; base < ntiles; base += 2 * nwarps) {
+        int tr[2], tc[2];
+        bool act[2];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const int t = base + s * nwarps + warp;
+            act[s] = t < ntiles;
+            int r = 0;
+            while ((r + 1) * (r + 2) / 2 <= (act[s] ? t : 0)) r++;
+            tr[s] = r; tc[s] = (act[s] ? t : 0) - r * (r + 1) / 2;
+        }
+        double acc[2][8][4];
+#pragma unroll
+        for (int s = 0; s < 2; s++)
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[s][i][j] = 0.0;
+        for (int i = 0; i < a.n; i++) {
+            const long long st = a.st_idx ? a.st_idx[i] : (long long)a.src0 + i;
+            const double* Yg = a.Yst + st * (long long)hmax * n;
+            for (int k0 = 0; k0 < n; k0 += kslab) {
+                const int kw = (n - k0 < kslab) ? (n - k0) : kslab;
+                __syncthreads();
+                for (int r = warp; r < h; r += nwarps)
+                    for (int c = 2 * lane; c < kw; c += 64) cp_async16(Ys + (long long)r * ldy + c, Yg + (long long)r * n + k0 + c);
+                cp_async_wait_all();
+                __syncthreads();
+#pragma unroll
+                for (int s = 0; s < 2; s++)
+                    if (act[s]) warp_mma_nt32(Ys, ldy, tr[s] << 5, h, tc[s] << 5, 0, kw, acc[s]);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            if (!act[s]) continue;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int a1 = (tr[s] << 5) + ty + 4 * i;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int a2 = (tc[s] << 5) + tx + 8 * j;
+                    if (a1 < h && a2 <= a1) a.Sacc[(long long)a1 * hmax + a2] = -acc[s][i][j];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // the nodes' own static blocks
+    for (int e = threadIdx.x; e < ns1 * ns1; e += blockDim.x) {
+        const int a1 = e / ns1, a2 = e - a1 * ns1;
+        if (a2 > a1) continue;
+        double s = 0.0;
+        for (int i = 0; i < a.n; i++) s += a.Ssrc[((long long)a.src0 + i) * ns1 * ns1 + e];
+        a.Sacc[(long long)a1 * hmax + a2] += s;
+    }
 }
 
 // Schur complements onto separator c of this level: from chunk c (its right side) and chunk c+1 (its left side).
 // grid = separators handled (separator = c_first + blockIdx.x)
-__global__ void __launch_bounds__(256) level_reduce_kernel(Dims dm, Level lv, int c_first) {
+__global__ void __launch_bounds__(256) chain_reduce_kernel(Dims dm, Level lv, int c_first) {
     const int c = c_first + blockIdx.x;
     const int P = lv.P;
     const int ntp = dm.ntp, nl = dm.nl, nc = dm.nc, ns1 = dm.ns1, hmax = dm.hmax;
@@ -630,8 +908,8 @@ __global__ void __launch_bounds__(256) level_reduce_kernel(Dims dm, Level lv, in
         double v = Dg[e];
         if (r >= nl && col >= nl) {
             const int i = r - nl, j = col - nl;
-            if (n_c > 0) v -= Fc[(long long)i * nc + j];
             const int hi = i > j ? i : j, lo = i > j ? j : i;
+            if (n_c > 0) v -= Fc[(long long)hi * nc + lo];
             v += Sn[(long long)(ns1 + hi) * hmax + (ns1 + lo)];
         }
         Dr[e] = v;
@@ -658,7 +936,7 @@ __global__ void __launch_bounds__(256) level_reduce_kernel(Dims dm, Level lv, in
         Sr[e] = v;
     }
     if (c < P - 2) {
-        // coupling separator c -> separator c+1 through chunk c+1: -(Y_left X^T) of that chunk's last node
+        // coupling separator c -> separator c+1 through chunk c+1: -(fill of the left rows) of that chunk's last node
         const int n_n = (int)(lv.begin[c + 2] - 1 - lv.begin[c + 1]);
         const double* Fn = lv.F + ((long long)(c + 1) * 2 + (n_n & 1)) * Fsz;
         double* Or = lv.Ored + (long long)c * nc * nc;
@@ -669,60 +947,175 @@ __global__ void __launch_bounds__(256) level_reduce_kernel(Dims dm, Level lv, in
     }
 }
 
-// single CTA: sweep over the n nodes of the top level, static solve, back-substitution of the top-level nodes
-__global__ void __launch_bounds__(B200_SOLVE_THREADS) top_solve_kernel(Dims dm, const double* Dsrc, const double* Osrc, const double* Asrc,
-                                                                       const double* Ssrc, const int* st, int n, SolveBuffers sb, double lambda,
-                                                                       int rmax) {
+// ------------------------------------------------------------------------------------------------- back-substitution
+// delta_k = -W^T ( W_c O_k^T delta_{k+1}(chain) + Y_k^T coef ),  coef = [delta_static (ns), -1, delta_left_chain (nc)].
+// The second term does not depend on the neighbour: chain_backsub_prepass_kernel computes it for all nodes in parallel.
+__device__ __forceinline__ void load_coef(const Dims& dm, const Level& lv, const SolveBuffers& sb, int c, double* coef) {
+    const int ns = dm.ns, ns1 = dm.ns1, nc = dm.nc, nl = dm.nl, n = dm.ntp;
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) coef[i] = sb.dstat[i];
+    if (threadIdx.x == 0) coef[ns] = -1.0;
+    if (c > 0) {
+        const int kb = lv.begin[c];
+        const long long lst = lv.st ? lv.st[kb - 1] : kb - 1;
+        for (int j = threadIdx.x; j < nc; j += blockDim.x) coef[ns1 + j] = sb.delta[lst * n + nl + j];
+    }
+}
+
+// y[c] = sum_r Y[r][c] coef[r]   (h x n panel in global memory), all threads of the CTA; part: blockDim.x doubles of scratch
+__device__ __forceinline__ void cta_yt_coef(const double* __restrict__ Yg, int n, int h, const double* coef, double* part, double* y) {
+    const int half = threadIdx.x >> 7, nhalf = blockDim.x >> 7;
+    for (int cb = 0; cb < n; cb += 128) {
+        const int c = cb + (threadIdx.x & 127);
+        double t0 = 0.0, t1 = 0.0;
+        if (c < n) {
+            int r = half;
+            for (; r + nhalf < h; r += 2 * nhalf) {
+                t0 = fma(Yg[(long long)r * n + c], coef[r], t0);
+                t1 = fma(Yg[(long long)(r + nhalf) * n + c], coef[r + nhalf], t1);
+            }
+            if (r < h) t0 = fma(Yg[(long long)r * n + c], coef[r], t0);
+        }
+        part[threadIdx.x] = t0 + t1;
+        __syncthreads();
+        if (half == 0 && c < n) {
+            double s = 0.0;
+            for (int q = 0; q < nhalf; q++) s += part[q * 128 + (threadIdx.x & 127)];
+            y[c] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// grid = (max nodes per chunk, chunks owned)
+__global__ void __launch_bounds__(B200_PREPASS_THREADS) chain_backsub_prepass_kernel(Dims dm, Level lv, SolveBuffers sb, int c_first) {
+    __shared__ double coef[512];
+    __shared__ double part[B200_PREPASS_THREADS];
+    const int c = c_first + blockIdx.y;
+    SweepArgs a;
+    level_chunk_args(dm, lv, sb, c, a);
+    if ((int)blockIdx.x >= a.n) return;
+    const long long st = a.st_idx ? a.st_idx[blockIdx.x] : (long long)a.src0 + blockIdx.x;
+    load_coef(dm, lv, sb, c, coef);
+    __syncthreads();
+    cta_yt_coef(a.Yst + st * (long long)dm.hmax * dm.ntp, dm.ntp, a.h, coef, part, sb.ybuf + st * dm.ntp);
+}
+
+// shared-memory carve-up of the back-substitution (doubles): Ms [ntp*ld] | u [256] | v [256] | cx [256] | yv [256] | coef [512] | part [512]
+__host__ __device__ inline long long backsub_smem_doubles(int ntp, int ld) { return (long long)ntp * ld + 4 * 256 + 512 + 512; }
+
+// back-substitution over the nodes of a sweep (reverse order).  right_st: storage index of the right neighbour (or -1).
+// y_ready: y = Y^T coef was computed by the pre-pass (sb.ybuf), else it is computed here from coef (shared memory).
+__device__ void cta_backsub(const Dims& dm, const SweepArgs& a, const double* coef, long long right_st, const SolveBuffers& sb, bool y_ready,
+                            double* sm) {
+    const int n = dm.ntp, nl = dm.nl, nc = dm.nc, ld = dm.ld, hmax = dm.hmax;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    double* Ms = sm;
+    double* u = sm + (long long)n * ld;
+    double* v = u + 256;
+    double* cx = v + 256;
+    double* yv = cx + 256;
+    double* part = yv + 256 + 512;
+    double* delta = sb.delta;
+    for (int i = a.n - 1; i >= 0; i--) {
+        const long long src = a.src0 + i;
+        const long long st = a.st_idx ? a.st_idx[i] : src;
+        const bool has_x = nc > 0 && ((i + 1 < a.n) || a.has_right);
+        long long nxt = -1;
+        if (i + 1 < a.n) nxt = a.st_idx ? a.st_idx[i + 1] : src + 1;
+        else if (a.has_right) nxt = right_st;
+        __syncthreads();
+        cp_upper_async(Ms, ld, a.Wst + st * n * n, n, n, n);
+        if (i > 0) {   // pull the next factor towards L2
+            const long long stn = a.st_idx ? a.st_idx[i - 1] : src - 1;
+            const double* Wn = a.Wst + stn * n * n;
+            for (int e = threadIdx.x * 16; e < n * n; e += blockDim.x * 16) prefetch_l2(Wn + e);
+        }
+        if (has_x) for (int j = threadIdx.x; j < nc; j += blockDim.x) cx[j] = delta[nxt * n + nl + j];
+        if (y_ready) for (int c = threadIdx.x; c < n; c += blockDim.x) yv[c] = sb.ybuf[st * n + c];
+        __syncthreads();
+        if (!y_ready) cta_yt_coef(a.Yst + st * (long long)hmax * n, n, a.h, coef, part, yv);
+        if (has_x) {
+            // u = O^T delta_next (structural row range of every column)
+            const double* Og = a.Osrc + src * nc * nc;
+            for (int k = threadIdx.x; k < nc; k += blockDim.x) {
+                const int r0 = a.dense_o ? 0 : dm.ocol[2 * k], r1 = a.dense_o ? nc : dm.ocol[2 * k + 1];
+                double s = 0.0;
+                for (int r = r0; r < r1; r++) s = fma(Og[(long long)r * nc + k], cx[r], s);
+                u[k] = s;
+            }
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        // v = y + W[:, chain] u :  v[c] = y[c] + sum_{k: nl+k <= c} Wt[nl+k][c] u[k]
+        for (int c = threadIdx.x; c < n; c += blockDim.x) {
+            double s0 = yv[c], s1 = 0.0;
+            if (has_x) {
+                const int kmax = c - nl;   // inclusive
+                int k = 0;
+                for (; k + 1 <= kmax; k += 2) {
+                    s0 = fma(Ms[(long long)(nl + k) * ld + c], u[k], s0);
+                    s1 = fma(Ms[(long long)(nl + k + 1) * ld + c], u[k + 1], s1);
+                }
+                if (k <= kmax) s0 = fma(Ms[(long long)(nl + k) * ld + c], u[k], s0);
+            }
+            v[c] = s0 + s1;
+        }
+        __syncthreads();
+        // delta[k] = - sum_{c >= k} Wt[k][c] v[c] : one warp per row
+        for (int k = warp; k < n; k += nwarps) {
+            const double* row = Ms + (long long)k * ld;
+            double s = 0.0;
+            for (int c = k + lane; c < n; c += 32) s = fma(row[c], v[c], s);
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) delta[st * n + k] = -s;
+        }
+        __threadfence_block();
+    }
+    __syncthreads();
+}
+
+// grid = chunks of this level owned by this rank: back-substitution of the chunk's interior nodes
+__global__ void __launch_bounds__(B200_SOLVE_THREADS) chain_backsub_kernel(Dims dm, Level lv, SolveBuffers sb, int c_first) {
+    B200_DYN_SMEM(double, sm);
+    const int c = c_first + blockIdx.x;
+    const int ke = lv.begin[c + 1];
+    SweepArgs a;
+    level_chunk_args(dm, lv, sb, c, a);
+    double* coef = sm + (long long)dm.ntp * dm.ld + 4 * 256;
+    load_coef(dm, lv, sb, c, coef);
+    __syncthreads();
+    const long long rst = (c < lv.P - 1) ? (lv.st ? lv.st[ke - 1] : ke - 1) : -1;
+    cta_backsub(dm, a, coef, rst, sb, true, sm);
+}
+
+// single CTA, after the top-level sweep + Schur kernels (Level with P == 1): static system, back-substitution of the top nodes
+__global__ void __launch_bounds__(B200_SOLVE_THREADS) top_finish_kernel(Dims dm, Level lv, SolveBuffers sb, double lambda) {
     B200_DYN_SMEM(double, sm);
     const int ns = dm.ns, ns1 = dm.ns1, hmax = dm.hmax;
-    SweepArgs a;
-    a.Dsrc = Dsrc; a.Osrc = Osrc; a.Asrc = Asrc; a.Ssrc = Ssrc;
-    a.src0 = 0; a.n = n; a.st_idx = st;
-    a.has_right = 0; a.Oleft = nullptr; a.h = ns1; a.lambda = lambda;
-    a.Lst = sb.Lst; a.Pst = sb.Pst; a.F = sb.Ftop; a.Sacc = sb.Stop; a.status = sb.status; a.rmax = rmax;
-    cta_sweep(dm, a, sm);
-    __syncthreads();
     if (*sb.status != 0) return;
+    SweepArgs a;
+    level_chunk_args(dm, lv, sb, 0, a);
     // static system: (Sacc[0:ns,0:ns] + lambda I) ds = Sacc[ns][0:ns]; the rhs row rides along as a panel row
-    double* coefA = sm + dm.sm_doubles - 512;   // hmax <= 512, lives at the end of the dynamic region
+    double* coef = sm + (long long)dm.ntp * dm.ld + 4 * 256;
     const int lds = static_lds(ns);
     double* Ss = sm;
     for (int e = threadIdx.x; e < ns1 * ns1; e += blockDim.x) {
         const int r = e / ns1, c = e % ns1;
-        if (c <= r && c < ns) Ss[r * lds + c] = __ldcg(a.Sacc + (long long)r * hmax + c) + ((r == c) ? lambda : 0.0);
+        if (c <= r && c < ns) Ss[r * lds + c] = a.Sacc[(long long)r * hmax + c] + ((r == c) ? lambda : 0.0);
     }
     __syncthreads();
     if (ns > 0) {
         const int fail = cta_chol_smem(Ss, lds, ns, ns1);
         if (fail) { if (threadIdx.x == 0) atomicCAS(sb.status, 0, 1 << 30); return; }
-        for (int i = threadIdx.x; i < ns; i += blockDim.x) coefA[i] = Ss[ns * lds + i];
+        for (int i = threadIdx.x; i < ns; i += blockDim.x) coef[i] = Ss[ns * lds + i];
         __syncthreads();
-        cta_solve_LT(Ss, lds, ns, coefA);
+        cta_solve_LT(Ss, lds, ns, coef);
     }
-    if (threadIdx.x == 0) coefA[ns] = -1.0;
+    if (threadIdx.x == 0) coef[ns] = -1.0;
     __syncthreads();
-    for (int i = threadIdx.x; i < ns; i += blockDim.x) sb.dstat[i] = coefA[i];
-    cta_backsub(dm, a, coefA, -1, sb.delta, sm);
-}
-
-// grid = chunks of this level owned by this rank: back-substitution of the chunk's interior nodes
-__global__ void __launch_bounds__(B200_SOLVE_THREADS) level_backsub_kernel(Dims dm, Level lv, SolveBuffers sb, int c_first) {
-    B200_DYN_SMEM(double, sm);
-    const int c = c_first + blockIdx.x;
-    const int kb = lv.begin[c], ke = lv.begin[c + 1];
-    const int ns = dm.ns, ns1 = dm.ns1, nc = dm.nc, nl = dm.nl, ntp = dm.ntp;
-    SweepArgs a;
-    level_chunk_args(dm, lv, sb, c, a);
-    double* coefA = sm + dm.sm_doubles - 512;
-    for (int i = threadIdx.x; i < ns; i += blockDim.x) coefA[i] = sb.dstat[i];
-    if (threadIdx.x == 0) coefA[ns] = -1.0;
-    if (c > 0) {
-        const long long lst = lv.st ? lv.st[kb - 1] : kb - 1;
-        for (int j = threadIdx.x; j < nc; j += blockDim.x) coefA[ns1 + j] = sb.delta[lst * ntp + nl + j];
-    }
-    __syncthreads();
-    const long long rst = (c < lv.P - 1) ? (lv.st ? lv.st[ke - 1] : ke - 1) : -1;
-    cta_backsub(dm, a, coefA, rst, sb.delta, sm);
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) sb.dstat[i] = coef[i];
+    cta_backsub(dm, a, coef, -1, sb, false, sm);
 }
 
 }  // namespace b200d

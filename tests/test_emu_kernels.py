@@ -43,7 +43,8 @@ def test_lower_body_lm_iterations(emu):
     _, g, tv, sv = lower_body(1.0)
     o = po.OracleProblem(g); o.set_values(tv, sv)
     p = lib.Problem(g, so_path=emu, chunks=2); p.set_values(tv, sv)
-    pc.assert_lm_parity(p, o, abi.LmParams.lower_body(), 3)
+    # lambda <= 1e-5 in these first iterations: the damped systems have condition numbers ~1e16, two correct solvers agree to ~1e-2 in cost
+    pc.assert_lm_parity(p, o, abi.LmParams.lower_body(), 3, rel=2e-2)
     assert p.launch_count() > 10
 
 

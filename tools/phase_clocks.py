@@ -16,10 +16,10 @@ L = lib.load(SO)
 out = (C.c_ulonglong * 16)()
 p.solve(1e-3); L.b200_debug_phase_clocks(out, 1)
 p.solve(1e-3); L.b200_debug_phase_clocks(out, 1)
-names = ["A:load D+fill", "A:chol", "A:store L", "B:load panel", "B:trsm", "B:store P", "B:syrk+rest"]
+names = ["A:load D+fill", "A:chol+inv", "A:store W", "B:load panel", "B:y=pW^T", "B:z=yW", "B:fill=zO^T"]
 tot = sum(out[:7])
 print("K", g.K, "chunks", p.chunks, "last-block cycles per phase (one solve; includes the top-level kernel):")
 for n, v in zip(names, out[:7]):
     print("  %-14s %10d  %5.1f%%" % (n, v, 100.0 * v / max(tot, 1)))
-for n, i in (("chol:gemm", 8), ("chol:potrf(thr0)", 9), ("chol:trisolve", 10), ("trsm:wait slab", 11), ("trsm:gemm", 12), ("trsm:trisolve(thr0)", 13)):
+for n, i in (("chol:potrf16+inv(warp0)", 8), ("chol:panel scale", 9), ("chol:trailing", 10)):
     print("  %-20s %10d  %5.1f%%" % (n, out[i], 100.0 * out[i] / max(tot, 1)))
