@@ -185,10 +185,8 @@ static b200_status build_asm_plan(b200_problem* p, size_t smem_cap) {
         if (b.da * b.db > 64) { set_err("internal: destination block larger than 64 entries"); return B200_NOT_IMPLEMENTED; }
         hb[kv.first.half].push_back(b);
     }
-    const size_t base0 = sizeof(double) * ((size_t)dm.ntp * dm.ntp + (size_t)dm.ns1 * dm.ns1);
-    const size_t base1 = sizeof(double) * ((size_t)dm.nc * dm.nc + (size_t)dm.ns1 * dm.ntp);
-    p->smem_asm[0] = base0 + sizeof(double) * off;
-    p->smem_asm[1] = base1 + sizeof(double) * off;
+    p->smem_asm[0] = sizeof(double) * (size_t)off;   // staged Jacobians only: the dense blocks are written straight to global memory
+    p->smem_asm[1] = sizeof(double) * (size_t)off;
     if (std::max(p->smem_asm[0], p->smem_asm[1]) > smem_cap) { set_err("time block + staged Jacobians do not fit in shared memory"); return B200_NOT_IMPLEMENTED; }
     CK(dalloc(&p->d_asm_items, items.size())); CK(dalloc(&p->d_asm_terms, terms.size()));
     CK(cudaMemcpyAsync(p->d_asm_items, items.data(), sizeof(AsmItem) * items.size(), cudaMemcpyHostToDevice, p->stream));
@@ -323,6 +321,9 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
     const size_t K = p->K;
     CK(dalloc(&p->d_D, K * dm.ntp * dm.ntp)); CK(dalloc(&p->d_O, K * dm.nc * dm.nc));
     CK(dalloc(&p->d_A, K * dm.ns1 * dm.ntp)); CK(dalloc(&p->d_S, K * dm.ns1 * dm.ns1));
+    // assemble_kernel only rewrites the structurally non-zero sub-blocks: everything else is zeroed here, once
+    CK(cudaMemsetAsync(p->d_D, 0, sizeof(double) * K * dm.ntp * dm.ntp, p->stream)); CK(cudaMemsetAsync(p->d_O, 0, sizeof(double) * K * dm.nc * dm.nc, p->stream));
+    CK(cudaMemsetAsync(p->d_A, 0, sizeof(double) * K * dm.ns1 * dm.ntp, p->stream)); CK(cudaMemsetAsync(p->d_S, 0, sizeof(double) * K * dm.ns1 * dm.ns1, p->stream));
     CK(dalloc(&p->sb.Wst, K * dm.ntp * dm.ntp)); CK(dalloc(&p->sb.Yst, K * (size_t)dm.hmax * dm.ntp)); CK(dalloc(&p->sb.ybuf, K * dm.ntp));
     CK(dalloc(&p->sb.delta, (K + 1024) * dm.ntp)); CK(dalloc(&p->sb.dstat, (size_t)ns + 1)); CK(dalloc(&p->sb.scal, (size_t)SC_COUNT));
     CK(dalloc(&p->sb.status, (size_t)1));
@@ -449,6 +450,29 @@ static double partition_cost(int K, int P1, int P2, int sms) {
     return t;
 }
 
+// Upper levels (single rank): the m separators left by a level form a chain again.  Either one CTA sweeps them sequentially
+// (cost m) or they are cut into P chunks whose interior nodes are eliminated in parallel (every step carries the left
+// separator and a dense coupling block: ~2 units, plus a fixed per-level cost for the Schur / reduce / back-substitution
+// launches) and the P-1 chunk separators recurse.  Dynamic programme over m; appends the chosen chunk counts to Ps.
+static void plan_upper_levels(int m, std::vector<int>& Ps) {
+    const double step_dense = 2.0, level_fixed = 0.7, step_top = 1.0;
+    std::vector<double> T(m + 1, 0.0);
+    std::vector<int> choice(m + 1, 1);
+    for (int mm = 0; mm <= m; mm++) {
+        T[mm] = step_top * mm;
+        for (int P = 2; P <= mm / 2; P++) {
+            int steps = 0;
+            for (int j = 0; j < P; j++) {
+                const int b0 = (int)((long long)j * mm / P), b1 = (j + 1 < P) ? (int)((long long)(j + 1) * mm / P) : mm;
+                steps = std::max(steps, (j + 1 < P) ? b1 - b0 - 1 : b1 - b0);
+            }
+            const double t = step_dense * steps + level_fixed + T[P - 1];
+            if (t < T[mm]) { T[mm] = t; choice[mm] = P; }
+        }
+    }
+    while (m > 0 && choice[m] > 1) { Ps.push_back(choice[m]); m = choice[m] - 1; }
+}
+
 // Build the nested partition.  P1 chunks over the keyframes (every rank owns P1/world of them, inside its window of
 // ceil(K/world) keyframes); P2 > 1: the P1-1 separators are themselves cut into P2 groups (rank-aligned) and only the
 // P2-1 group separators are eliminated sequentially by the single top-level CTA.  Chunks hold >= 2 nodes.
@@ -458,6 +482,7 @@ static b200_status set_partition(b200_problem* p, int P1, int P2) {
     p->Wk = (K + W - 1) / W;
     if ((long long)(W - 1) * p->Wk >= K || K - (W - 1) * p->Wk < 3) { set_err("too few keyframes for this many ranks"); return B200_BAD_ARG; }
     const int max_p1 = std::max(1, K / 3);
+    const bool auto_groups = P2 <= 0;
     if (P1 <= 0) {  // search the cost model
         double best = 1e300; int bp1 = 1, bp2 = 1;
         for (int c1 = 1; c1 <= std::min(max_p1, 8 * sms); c1++) {
@@ -485,8 +510,15 @@ static b200_status set_partition(b200_problem* p, int P1, int P2) {
     if (W > 1) { P2 = std::max(P2, W); P2 = (P2 + W - 1) / W * W; while (P2 > W && (P1 / W) / (P2 / W) < 3) P2 -= W; if ((P1 / W) / (P2 / W) < 2) { set_err("partition too fine for this many ranks"); return B200_BAD_ARG; } }
     else { if (P1 < 4) P2 = 1; while (P2 > 1 && (P1 - 1) / P2 < 2) P2--; }
     free_levels(p);
-    p->P = P1; p->P2 = P2;
-    const int nlev = (P1 > 1) ? ((P2 > 1) ? 2 : 1) : 0;
+    // chunk counts per level: Ps[0] over the K keyframes, Ps[l] over the Ps[l-1]-1 separators of the level below
+    std::vector<int> Ps;
+    if (P1 > 1) {
+        Ps.push_back(P1);
+        if (W > 1 || !auto_groups) { if (P2 > 1) Ps.push_back(P2); }
+        else plan_upper_levels(P1 - 1, Ps);
+    }
+    p->P = P1; p->P2 = Ps.size() > 1 ? Ps[1] : 1; P2 = p->P2;
+    const int nlev = (int)Ps.size();
     p->levels.resize(std::max(nlev, 1));
     // ---- level 0: keyframes
     {
@@ -504,22 +536,28 @@ static b200_status set_partition(b200_problem* p, int P1, int P2) {
         for (int c = 0; c + 1 < P1; c++) l.sep_st[c] = l.begin[c + 1] - 1;
         p->k_lo = l.begin[l.c_lo]; p->k_hi = l.begin[l.c_hi];
     }
-    // ---- level 1: the separators of level 0
-    if (nlev == 2) {
-        auto& l0 = p->levels[0];
-        auto& l = p->levels[1];
-        l.n_nodes = P1 - 1; l.P = P2;
-        l.st = l0.sep_st; l.st.resize(l.n_nodes);
-        l.begin.resize(P2 + 1);
-        const int per1 = P1 / W, gpr = P2 / W;
-        for (int r = 0; r < W; r++) {
-            const int n0 = r * per1, n1 = std::min(P1 - 1, (r + 1) * per1);   // this rank's separators
-            for (int j = 0; j < gpr; j++) l.begin[r * gpr + j] = n0 + (int)((long long)j * (n1 - n0) / gpr);
+    // ---- level li >= 1: the separators of level li-1 (level 1 is rank-aligned when the time axis is sharded)
+    for (int li = 1; li < nlev; li++) {
+        auto& lp = p->levels[li - 1];
+        auto& l = p->levels[li];
+        const int Pl = Ps[li];
+        l.n_nodes = lp.P - 1; l.P = Pl;
+        l.st = lp.sep_st; l.st.resize(l.n_nodes);
+        l.begin.resize(Pl + 1);
+        if (li == 1 && W > 1) {
+            const int per1 = P1 / W, gpr = Pl / W;
+            for (int r = 0; r < W; r++) {
+                const int n0 = r * per1, n1 = std::min(P1 - 1, (r + 1) * per1);   // this rank's separators
+                for (int j = 0; j < gpr; j++) l.begin[r * gpr + j] = n0 + (int)((long long)j * (n1 - n0) / gpr);
+            }
+            l.c_lo = p->rank * gpr; l.c_hi = l.c_lo + gpr;
+        } else {
+            for (int j = 0; j < Pl; j++) l.begin[j] = (int)((long long)j * l.n_nodes / Pl);
+            l.c_lo = 0; l.c_hi = Pl;
         }
-        l.begin[P2] = P1 - 1;
-        l.c_lo = p->rank * gpr; l.c_hi = l.c_lo + gpr;
-        l.sep_st.resize(std::max(P2 - 1, 1));
-        for (int g = 0; g + 1 < P2; g++) l.sep_st[g] = l.st[l.begin[g + 1] - 1];
+        l.begin[Pl] = l.n_nodes;
+        l.sep_st.resize(std::max(Pl - 1, 1));
+        for (int g = 0; g + 1 < Pl; g++) l.sep_st[g] = l.st[l.begin[g + 1] - 1];
     }
     const size_t Fsz = (size_t)(dm.nc + dm.hmax) * dm.nc, Ssz = (size_t)dm.hmax * dm.hmax;
     for (int li = 0; li < nlev; li++) {
@@ -578,6 +616,12 @@ b200_status b200_set_partition(b200_problem* p, int32_t n_chunks, int32_t n_grou
 b200_status b200_set_chunks(b200_problem* p, int32_t n_chunks) { return b200_set_partition(p, n_chunks, n_chunks > 0 ? 1 : 0); }
 int32_t b200_get_chunks(const b200_problem* p) { return p ? p->P : 0; }
 int32_t b200_get_groups(const b200_problem* p) { return p ? p->P2 : 0; }
+int32_t b200_get_levels(const b200_problem* p, int32_t* sizes, int32_t max_levels) {
+    if (!p || p->P <= 1) return 0;
+    const int n = (int)p->levels.size();
+    if (sizes) for (int i = 0; i < n && i < max_levels; i++) sizes[i] = p->levels[i].P;
+    return n;
+}
 
 int32_t b200_time_value_dim(const b200_problem* p) { return p->tvd; }
 int32_t b200_static_value_dim(const b200_problem* p) { return p->svd; }
@@ -679,7 +723,7 @@ static b200_status launch_solve(b200_problem* p, double lambda) {
     const Dims& dm = p->dm;
     const int W = p->world, r = p->rank;
     const size_t Fsz = (size_t)(dm.nc + dm.hmax) * dm.nc, Ssz = (size_t)dm.hmax * dm.hmax;
-    const int nlev = (p->P > 1) ? ((p->P2 > 1) ? 2 : 1) : 0;
+    const int nlev = (p->P > 1) ? (int)p->levels.size() : 0;
     if (p->time_phases) CK(cudaEventRecord(p->ev[8], p->stream));
     if (nlev >= 1) {
         auto& l0 = p->levels[0];
@@ -709,11 +753,11 @@ static b200_status launch_solve(b200_problem* p, double lambda) {
             p->launches++;
         }
     }
-    if (nlev == 2) {
+    for (int li = 1; li < nlev; li++) {
         auto& l0 = p->levels[0];
-        auto& l1 = p->levels[1];
+        auto& l1 = p->levels[li];
         launch_level_factor(p, l1.dev, l1.c_lo, l1.c_hi, lambda);
-        if (W > 1) {
+        if (W > 1 && li == 1) {
             const int gpr = l1.P / W;
             b200_status st = allgather(p, l1.F, sizeof(double) * 2 * Fsz * gpr); if (st != B200_OK) return st;
             st = allgather(p, l1.S, sizeof(double) * Ssz * gpr); if (st != B200_OK) return st;
@@ -732,8 +776,7 @@ static b200_status launch_solve(b200_problem* p, double lambda) {
     B200_LAUNCH(top_finish_kernel, dim3(1), dim3(B200_SOLVE_THREADS), p->smem_backsub, p->stream, dm, p->top, p->sb, lambda);
     p->launches++;
     if (p->time_phases) CK(cudaEventRecord(p->ev[11], p->stream));
-    if (nlev == 2) launch_level_backsub(p, p->levels[1]);
-    if (nlev >= 1) launch_level_backsub(p, p->levels[0]);
+    for (int li = nlev - 1; li >= 0; li--) launch_level_backsub(p, p->levels[li]);
     if (p->time_phases) CK(cudaEventRecord(p->ev[12], p->stream));
     if (W > 1) {  // every rank needs every keyframe's step: the values are replicated
         b200_status st = allgather(p, p->sb.delta, sizeof(double) * (size_t)p->Wk * dm.ntp); if (st != B200_OK) return st;

@@ -1,5 +1,5 @@
-// Hessian / gradient accumulation (north_star subsystem 2): per-keyframe dense blocks of J^T J built in shared memory from the
-// whitened per-factor Jacobians, one CTA per (keyframe, half):
+// Hessian / gradient accumulation (north_star subsystem 2): per-keyframe dense blocks of J^T J built from the whitened
+// per-factor Jacobians (staged in shared memory), one CTA per (keyframe, half):
 //   half 0:  D_k  (ntp x ntp, time block of keyframe k)            + Sx_k ((ns+1) x (ns+1): static block and -g_static)
 //   half 1:  O_k  (nc x nc, chain part of keyframe k+1 vs k)        + Ax_k ((ns+1) x ntp: static rows, last row = -g_k)
 // Every block is owned by exactly one CTA and slots are visited in table order, so the sums are deterministic
@@ -41,24 +41,22 @@ struct AsmPlan {
     int stage_doubles;
 };
 
+// The dense blocks live in global memory and are ZEROED ONCE at problem creation: the set of destination sub-blocks is the
+// same at every keyframe and every linearization, each one is rewritten completely (a block whose factors are all outside
+// their keyframe range writes zeros), everything else stays zero.  So a CTA only needs shared memory for the staged
+// Jacobians (several CTAs per SM) and writes ~4 k doubles per keyframe instead of the 38 k of the dense blocks.
 __global__ void __launch_bounds__(256) assemble_kernel(Dims dm, const DevSlot* __restrict__ slots, AsmPlan pl,
                                                        const double* __restrict__ Jbuf, const double* __restrict__ rbuf,
                                                        int k_first, int win_lo, int win_hi,
                                                        double* __restrict__ Dsrc, double* __restrict__ Osrc, double* __restrict__ Asrc,
                                                        double* __restrict__ Ssrc) {
-    B200_DYN_SMEM(double, sm);
+    B200_DYN_SMEM(double, St);  // staged Jacobians (rows*cols) + residuals (rows) of every item
     const int k = k_first + (int)blockIdx.x;
     const int half = blockIdx.y;
     const int ntp = dm.ntp, nc = dm.nc, ns1 = dm.ns1;
-    const int n1 = half == 0 ? ntp * ntp : nc * nc;
-    const int n2 = half == 0 ? ns1 * ns1 : ns1 * ntp;
     const int ld1 = half == 0 ? ntp : nc, ld2 = half == 0 ? ns1 : ntp;
-    double* B1 = sm;            // D or O
-    double* B2 = sm + n1;       // Sx or Ax
-    double* St = B2 + n2;       // staged Jacobians (rows*cols) + residuals (rows) of every item
     __shared__ unsigned char valid[256];
-    for (int i = threadIdx.x; i < n1 + n2; i += blockDim.x) sm[i] = 0.0;
-    // ---- which items exist at this keyframe; stage their Jacobians (independent strided loads, issued in bulk)
+    // ---- which items exist at this keyframe; stage their Jacobians (contiguous per-instance records, issued in bulk)
     for (int it = threadIdx.x; it < pl.n_items; it += blockDim.x) {
         const AsmItem im = pl.items[it];
         const DevSlot& s = slots[im.slot];
@@ -66,7 +64,6 @@ __global__ void __launch_bounds__(256) assemble_kernel(Dims dm, const DevSlot* _
         valid[it] = (ki >= s.k_begin && ki < s.k_end && ki >= win_lo && ki < win_hi) ? 1 : 0;
     }
     __syncthreads();
-    if (half == 0 && ntp > dm.nt && threadIdx.x == 0) B1[(ntp - 1) * ntp + ntp - 1] = 1.0;  // padding variable: identity
     for (int it = 0; it < pl.n_items; it++) {
         if (!valid[it]) continue;
         const AsmItem im = pl.items[it];
@@ -81,7 +78,10 @@ __global__ void __launch_bounds__(256) assemble_kernel(Dims dm, const DevSlot* _
     }
     cp_async_wait_all();
     __syncthreads();
-    // ---- one warp per destination block
+    double* g1 = half == 0 ? Dsrc + (long long)k * ntp * ntp : Osrc + (long long)k * nc * nc;
+    double* g2 = half == 0 ? Ssrc + (long long)k * ns1 * ns1 : Asrc + (long long)k * ns1 * ntp;
+    if (half == 0 && ntp > dm.nt && threadIdx.x == 0) g1[(ntp - 1) * ntp + ntp - 1] = 1.0;  // padding variable: identity
+    // ---- one warp per destination block, terms in table order, result written straight to global memory
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const AsmBlock* blocks = pl.blocks[half];
     for (int b = warp; b < pl.n_blocks[half]; b += nwarps) {
@@ -106,16 +106,11 @@ __global__ void __launch_bounds__(256) assemble_kernel(Dims dm, const DevSlot* _
                 if (e0 < ne) for (int r = 0; r < rows; r++) acc0 = fma(-Js[r * cols + j0], rr[r], acc0);
             }
         }
-        double* B = bk.which == 0 ? B1 : B2;
+        double* B = bk.which == 0 ? g1 : g2;
         const int ld = bk.which == 0 ? ld1 : ld2;
         if (e0 < ne) B[(bk.row + ia0) * ld + bk.col + ib0] = acc0;
         if (e1 < ne) B[(bk.row + ia1) * ld + bk.col + ib1] = acc1;
     }
-    __syncthreads();
-    double* g1 = half == 0 ? Dsrc + (long long)k * ntp * ntp : Osrc + (long long)k * nc * nc;
-    double* g2 = half == 0 ? Ssrc + (long long)k * ns1 * ns1 : Asrc + (long long)k * ns1 * ntp;
-    for (int i = threadIdx.x; i < n1; i += blockDim.x) g1[i] = B1[i];
-    for (int i = threadIdx.x; i < n2; i += blockDim.x) g2[i] = B2[i];
 }
 
 }  // namespace b200d

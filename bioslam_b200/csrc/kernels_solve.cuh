@@ -261,15 +261,15 @@ __device__ int cta_chol_inv(double* Ms, int ld, int n) {
     if (threadIdx.x == 0) fail = 0;
     __syncthreads();
     PH_T0();
+    if (warp == 0) {
+        const int f = warp_potrf16(Ms, ld, n < B200_NB ? n : B200_NB, Tdiag, invd, Wd, true);
+        if (f && lane == 0) fail = f;
+    }
+    __syncthreads();
+    PH_ADD(8);
+    if (fail) return fail;
     for (int j0 = 0; j0 < n; j0 += B200_NB) {
         const int jb = (n - j0 < B200_NB) ? (n - j0) : B200_NB;
-        if (warp == 0) {
-            const int f = warp_potrf16(Ms + (long long)j0 * ld + j0, ld, jb, Tdiag, invd, Wd, true);
-            if (f && lane == 0) fail = j0 + f;
-        }
-        __syncthreads();
-        PH_ADD(8);
-        if (fail) return fail;
         // (b) rows r in [0, j0) U [j0 + jb, n): X[r][j0 .. j0+jb) <- X * W_jj^T, 16 (virtual) rows per warp, in place
         const int nvr = n - jb;
         for (int t = warp; t * 16 < nvr; t += nwarps) {
@@ -309,12 +309,54 @@ __device__ int cta_chol_inv(double* Ms, int ld, int n) {
         }
         __syncthreads();
         PH_ADD(9);
-        // (c) trailing update: Ms[r][c] -= sum_t Ms[r][j0+t] Ms[c][j0+t], c >= j0+16, alive rows only
         const int cb0 = j0 + B200_NB;
-        if (cb0 < n) {
-            const int ntr = (n + 15) >> 4, ntc = (n - cb0 + 31) >> 5;
-            for (int tile = warp; tile < ntr * ntc; tile += nwarps) {
-                const int m0 = (tile / ntc) << 4, c0 = cb0 + ((tile % ntc) << 5);
+        if (cb0 >= n) break;
+        // (c1) trailing update of the NEXT column block only (16 columns), alive rows: r >= c or r < cb0
+        for (int t = warp; t * 16 < n; t += nwarps) {
+            const int m0 = t * 16;
+            {
+                const double* ap[4];
+                const double* bp[2];
+#pragma unroll
+                for (int i = 0; i < 4; i++) { int r = m0 + ty + 4 * i; if (r > n - 1) r = n - 1; ap[i] = Ms + (long long)r * ld + j0; }
+#pragma unroll
+                for (int j = 0; j < 2; j++) { int c = cb0 + tx + 8 * j; if (c > n - 1) c = n - 1; bp[j] = Ms + (long long)c * ld + j0; }
+                double acc[4][2];
+#pragma unroll
+                for (int i = 0; i < 4; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+#pragma unroll
+                for (int c2 = 0; c2 < B200_NB; c2 += 2) {
+                    const double2 b0 = ld2(bp[0] + c2), b1 = ld2(bp[1] + c2);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const double2 a = ld2(ap[i] + c2);
+                        acc[i][0] = fma(a.y, b0.y, fma(a.x, b0.x, acc[i][0]));
+                        acc[i][1] = fma(a.y, b1.y, fma(a.x, b1.x, acc[i][1]));
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int r = m0 + ty + 4 * i;
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        const int c = cb0 + tx + 8 * j;
+                        if (r < n && c < n && (r >= c || r < cb0)) Ms[(long long)r * ld + c] -= acc[i][j];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // (c2) look-ahead: warp 0 factorises the next diagonal block while the other warps finish the trailing update
+        const int cb1 = cb0 + B200_NB;
+        const int wfirst = nwarps > 1 ? 1 : 0, nwork = nwarps > 1 ? nwarps - 1 : 1;
+        if (warp == 0) {
+            const int f = warp_potrf16(Ms + (long long)cb0 * ld + cb0, ld, (n - cb0 < B200_NB) ? (n - cb0) : B200_NB, Tdiag, invd, Wd, true);
+            if (f && lane == 0) fail = cb0 + f;
+        }
+        if (cb1 < n && warp >= wfirst) {
+            const int ntr = (n + 15) >> 4, ntc = (n - cb1 + 31) >> 5;
+            for (int tile = warp - wfirst; tile < ntr * ntc; tile += nwork) {
+                const int m0 = (tile / ntc) << 4, c0 = cb1 + ((tile % ntc) << 5);
                 if (m0 >= cb0 && m0 + 15 < c0) continue;   // dead zone: not-yet-started appended rows
                 double acc[4][4];
 #pragma unroll
@@ -332,9 +374,10 @@ __device__ int cta_chol_inv(double* Ms, int ld, int n) {
                     }
                 }
             }
-            __syncthreads();
         }
+        __syncthreads();
         PH_ADD(10);
+        if (fail) return fail;
     }
     return 0;
 }
@@ -514,19 +557,32 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
             const double* Dn = a.Dsrc + (src + 1) * n * n;
             for (int e = threadIdx.x * 16; e < n * n; e += blockDim.x * 16) prefetch_l2(Dn + e);
         }
-        cp_async_wait_all();
-        __syncthreads();
-        for (int r = warp; r < n; r += nwarps) {
-            double* row = Ms + (long long)r * ld;
-            const bool chain_r = (i > 0) && r >= nl;
-            const double* fr = Fin + (long long)(r - nl) * nc - nl;
-            for (int c = lane; c < n; c += 32) {
-                if (c > r) row[c] = 0.0;
-                else {
-                    double v = row[c];
-                    if (c == r) v += a.lambda;
-                    if (chain_r && c >= nl) v -= fr[c];
-                    row[c] = v;
+        // fill of the previous node (chain x chain, lower triangle): loads issued before the wait, 8 rows x 4 columns per lane
+        for (int rb = 0; rb < n; rb += 8 * nwarps) {
+            for (int cb = 0; cb < n; cb += 128) {
+                double f[8][4];
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int r = rb + warp + q * nwarps;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int c = cb + lane + 32 * u;
+                        f[q][u] = (i > 0 && r < n && r >= nl && c >= nl && c <= r) ? Fin[(long long)(r - nl) * nc + (c - nl)] : 0.0;
+                    }
+                }
+                if (rb == 0 && cb == 0) { cp_async_wait_all(); __syncthreads(); }
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int r = rb + warp + q * nwarps;
+                    if (r >= n) continue;
+                    double* row = Ms + (long long)r * ld;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int c = cb + lane + 32 * u;
+                        if (c >= n) continue;
+                        if (c > r) row[c] = 0.0;
+                        else row[c] = row[c] + ((c == r) ? a.lambda : 0.0) - f[q][u];
+                    }
                 }
             }
         }
@@ -561,7 +617,8 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                 const int r0 = base + ch * csz;
                 const int cr = (base + cnt - r0 < csz) ? (base + cnt - r0) : csz;
                 __syncthreads();   // Yb free
-                // ---- load rows (one warp per row): sources through cp.async, then the fill correction in shared memory
+                // ---- load rows (one warp per row): sources through cp.async; the fill rows of the previous node are fetched
+                // into registers before the wait (their L2 latency overlaps the copies) and applied afterwards
                 for (int lr = warp; lr < cr; lr += nwarps) {
                     const int pr = r0 + lr;
                     double* dst = Yb + (long long)lr * ld;
@@ -580,22 +637,44 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                             const double* ol = a.Oleft + (ar - ns1);
                             for (int c = lane; c < n; c += 32) dst[c] = (c >= nl) ? ol[(long long)(c - nl) * nc] : 0.0;
                         } else {
-                            for (int c = lane; c < n; c += 32) dst[c] = 0.0;
+                            for (int c = lane; c < nl; c += 32) dst[c] = 0.0;
+                            if (i == 0) for (int c = nl + lane; c < n; c += 32) dst[c] = 0.0;
                         }
                     }
                 }
-                cp_async_wait_all();
-                __syncthreads();
                 if (seg == 1 && i > 0) {
-                    // arrow rows: subtract the fill  Y_prev Dinv O^T  (chain columns)
-                    for (int lr = warp; lr < cr; lr += nwarps) {
-                        const double* fr = Fin + (long long)(nc + r0 - xo + lr) * nc;
-                        double* dr = Yb + (long long)lr * ld + nl;
-#pragma unroll 4
-                        for (int c = lane; c < nc; c += 32) dr[c] -= fr[c];
+                    const int ar0 = r0 - xo;
+                    for (int rb = 0; rb < cr; rb += 4 * nwarps) {
+                        for (int cb = 0; cb < nc; cb += 128) {
+                            double f[4][4];
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const int lr = rb + warp + q * nwarps;
+#pragma unroll
+                                for (int u = 0; u < 4; u++) {
+                                    const int c = cb + lane + 32 * u;
+                                    f[q][u] = (lr < cr && c < nc) ? Fin[(long long)(nc + ar0 + lr) * nc + c] : 0.0;
+                                }
+                            }
+                            if (rb == 0 && cb == 0) { cp_async_wait_all(); __syncthreads(); }
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const int lr = rb + warp + q * nwarps;
+                                if (lr >= cr) continue;
+                                double* dr = Yb + (long long)lr * ld + nl;
+                                const bool src_row = (ar0 + lr) < ns1;   // static / rhs rows start from A, left rows from zero
+#pragma unroll
+                                for (int u = 0; u < 4; u++) {
+                                    const int c = cb + lane + 32 * u;
+                                    if (c < nc) dr[c] = (src_row ? dr[c] : 0.0) - f[q][u];
+                                }
+                            }
+                        }
                     }
-                    __syncthreads();
+                } else {
+                    cp_async_wait_all();
                 }
+                __syncthreads();
                 PH_ADD(3);
                 const int rtiles = (cr + 15) >> 4;
                 const int tpw = nwarps / rtiles;              // column tiles per wave (rtiles <= CR/16 <= nwarps)

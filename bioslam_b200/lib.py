@@ -39,6 +39,7 @@ def load(path=None):
     for f in ("b200_time_value_dim", "b200_static_value_dim", "b200_time_tangent_dim", "b200_static_tangent_dim", "b200_get_chunks", "b200_get_groups"):
         getattr(L, f).argtypes = [C.c_void_p]
     L.b200_comm_set.argtypes = [C.c_void_p, C.c_int32, C.c_int32, ALLGATHER_FN, ALLREDUCE_FN, C.c_void_p]
+    L.b200_get_levels.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32]
     _libs[path] = L
     return L
 
@@ -91,6 +92,13 @@ class Problem:
     @property
     def groups(self):
         return self.L.b200_get_groups(self.h)
+
+    @property
+    def levels(self):
+        """chunk counts of the nested partition, level 0 first ([] = plain sequential sweep)"""
+        sizes = (C.c_int32 * 16)()
+        n = self.L.b200_get_levels(self.h, sizes, C.c_int32(16))
+        return [int(sizes[i]) for i in range(min(n, 16))]
 
     def set_values(self, tv, sv):
         tv = np.ascontiguousarray(tv, dtype=np.float64)

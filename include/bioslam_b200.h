@@ -267,6 +267,10 @@ int32_t b200_get_chunks(const b200_problem* p);
  * built-in cost model, n_groups = 1 = two-level scheme. */
 b200_status b200_set_partition(b200_problem* p, int32_t n_chunks, int32_t n_groups);
 int32_t b200_get_groups(const b200_problem* p);
+/* depth of the nested partition (0 = plain sequential sweep).  With n_groups = 0 on a single GPU the separators are
+ * partitioned recursively (as many levels as the cost model finds worthwhile); sizes[l] receives the chunk count of level l
+ * (up to max_levels entries, may be NULL). */
+int32_t b200_get_levels(const b200_problem* p, int32_t* sizes, int32_t max_levels);
 
 /* ---------------------------------------------------------------- multi-GPU (time axis sharded, section 8(e))
  * One process per GPU, every rank creates the problem with the FULL description and the same values.  Rank r owns a
