@@ -82,7 +82,7 @@ struct b200_problem {
     int P = 1, P2 = 1;                         // chunks of level 0 / level 1
     Level top{};                               // top level: one chunk over the remaining separators (or all keyframes)
     int* d_top_begin = nullptr;
-    int *d_orow = nullptr, *d_ocol = nullptr, *d_ozs = nullptr;
+    int *d_orow = nullptr, *d_ocol = nullptr, *d_ozs = nullptr, *d_ogrp = nullptr;
     double *d_Ftop = nullptr, *d_Stop = nullptr;
     size_t smem_schur = 0, smem_backsub = 0;
     int schur_ldy = 0, schur_kslab = 0;
@@ -220,7 +220,7 @@ void b200_problem_destroy(b200_problem* p) {
     cudaSetDevice(p->device);
     void* ptrs[] = {p->d_tv, p->d_tv_try, p->d_sv, p->d_sv_try, p->d_cst, p->d_stage, p->d_slots, p->d_tvars, p->d_svars, p->d_J, p->d_r,
                     p->d_e, p->d_e2, p->d_D, p->d_O, p->d_A, p->d_S, p->sb.Wst, p->sb.Yst, p->sb.ybuf, p->d_Ftop, p->d_Stop, p->sb.delta, p->sb.dstat,
-                    p->d_top_begin, p->d_orow, p->d_ocol, p->d_ozs,
+                    p->d_top_begin, p->d_orow, p->d_ocol, p->d_ozs, p->d_ogrp,
                     p->sb.scal, p->sb.status, p->d_stageS, p->d_stageF, p->d_pack, p->d_asm_items, p->d_asm_terms, p->d_asm_blocks[0], p->d_asm_blocks[1]};
     for (void* q : ptrs) if (q) cudaFree(q);
     free_levels(p);
@@ -354,6 +354,22 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
         ow = std::min(ow, dm.ntp);
         for (int i = 0; i < nc; i++) if (ozs[i] + ow > dm.ntp) ozs[i] = dm.ntp - ow;
         dm.ow = ow; dm.owp = ow + 2;
+        std::vector<int> ogrp;
+        for (int b0 = 0; b0 < nc;) {   // runs of <= 16 consecutive rows with the same window, dealt to 4-row groups with stride
+            int b1 = b0 + 1;
+            while (b1 < nc && b1 - b0 < 16 && ozs[b1] == ozs[b0]) b1++;
+            const int str = (b1 - b0 + 3) / 4;
+            for (int c = 0; c < str; c++) {
+                int cnt = 0;
+                while (cnt < 4 && b0 + c + str * cnt < b1) cnt++;
+                ogrp.push_back(b0 + c); ogrp.push_back(str); ogrp.push_back(cnt);
+            }
+            b0 = b1;
+        }
+        dm.n_ogrp = (int)ogrp.size() / 3;
+        CK(dalloc(&p->d_ogrp, ogrp.size()));
+        CK(cudaMemcpyAsync(p->d_ogrp, ogrp.data(), sizeof(int) * ogrp.size(), cudaMemcpyHostToDevice, p->stream));
+        dm.ogrp = p->d_ogrp;
         CK(dalloc(&p->d_orow, (size_t)2 * nc)); CK(dalloc(&p->d_ocol, (size_t)2 * nc)); CK(dalloc(&p->d_ozs, (size_t)nc));
         CK(cudaMemcpyAsync(p->d_orow, orow.data(), sizeof(int) * 2 * nc, cudaMemcpyHostToDevice, p->stream));
         CK(cudaMemcpyAsync(p->d_ocol, ocol.data(), sizeof(int) * 2 * nc, cudaMemcpyHostToDevice, p->stream));
@@ -455,7 +471,7 @@ static double partition_cost(int K, int P1, int P2, int sms) {
 // separator and a dense coupling block: ~2 units, plus a fixed per-level cost for the Schur / reduce / back-substitution
 // launches) and the P-1 chunk separators recurse.  Dynamic programme over m; appends the chosen chunk counts to Ps.
 static void plan_upper_levels(int m, std::vector<int>& Ps) {
-    const double step_dense = 2.0, level_fixed = 0.7, step_top = 1.0;
+    const double step_dense = 2.0, level_fixed = 1.5, step_top = 1.0;
     std::vector<double> T(m + 1, 0.0);
     std::vector<int> choice(m + 1, 1);
     for (int mm = 0; mm <= m; mm++) {
@@ -704,7 +720,9 @@ __global__ void pack_groups_kernel(Dims dm, Level lv1, const double* Dred, const
 static void launch_level_factor(b200_problem* p, const Level& lv, int c_lo, int c_hi, double lambda) {
     const Dims& dm = p->dm;
     B200_LAUNCH(chain_sweep_kernel, dim3(c_hi - c_lo), dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, dm, lv, p->sb, lambda, c_lo);
-    B200_LAUNCH(chain_schur_kernel, dim3(c_hi - c_lo), dim3(B200_SCHUR_THREADS), p->smem_schur, p->stream, dm, lv, p->sb, c_lo, p->schur_ldy,
+    // few chunks (upper levels): split the output tiles of a chunk's Schur complement over several CTAs
+    const int nsplit = (c_hi - c_lo) * 2 <= 148 ? 2 : 1;
+    B200_LAUNCH(chain_schur_kernel, dim3(c_hi - c_lo, nsplit), dim3(B200_SCHUR_THREADS), p->smem_schur, p->stream, dm, lv, p->sb, c_lo, p->schur_ldy,
                 p->schur_kslab);
     p->launches += 2;
 }
@@ -749,7 +767,7 @@ static b200_status launch_solve(b200_problem* p, double lambda) {
             if (r > 0) red_lo = l0.c_lo - 1;
         }
         if (red_hi > red_lo) {
-            B200_LAUNCH(chain_reduce_kernel, dim3(red_hi - red_lo), dim3(256), 0, p->stream, dm, l0.dev, red_lo);
+            B200_LAUNCH(chain_reduce_kernel, dim3(red_hi - red_lo, 8), dim3(256), 0, p->stream, dm, l0.dev, red_lo);
             p->launches++;
         }
     }
@@ -768,7 +786,7 @@ static b200_status launch_solve(b200_problem* p, double lambda) {
                         (long long)p->pack_doubles, 0, 1, l1.c_lo, l1.c_hi);
             p->launches += 2;
         }
-        B200_LAUNCH(chain_reduce_kernel, dim3(l1.P - 1), dim3(256), 0, p->stream, dm, l1.dev, 0);
+        B200_LAUNCH(chain_reduce_kernel, dim3(l1.P - 1, 8), dim3(256), 0, p->stream, dm, l1.dev, 0);
         p->launches++;
     }
     if (p->time_phases) CK(cudaEventRecord(p->ev[10], p->stream));

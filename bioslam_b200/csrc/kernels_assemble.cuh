@@ -22,6 +22,8 @@ struct Dims {
     const int* orow;               // [nc][2] structural non-zero column range [c0, c1) of every row of O
     const int* ocol;               // [nc][2] structural non-zero row range [r0, r1) of every column of O
     const int* ozs;                // [nc] even start column (time-block coordinates) of the packed row
+    const int* ogrp;               // [n_ogrp][3] groups (first row, stride, count <= 4) of rows of O that share the packed window ozs
+    int n_ogrp;
 };
 
 // Assembly plan, built once per problem on the host (bioslam_b200.cu: build_asm_plan):

@@ -106,6 +106,98 @@ __device__ __forceinline__ void warp_mma_nt(const double* __restrict__ A, int ld
     }
 }
 
+// Balanced variants for the TRIANGULAR products: a warp owns two 16-column blocks A and B whose contraction ranges are
+// complementary (short + long), so that every warp of a row group carries the same work.
+// NN: columns cA + 2 tx + {0,1} -> acc[.][0..1] over k in [ka, kendA), columns cB + 2 tx + {0,1} -> acc[.][2..3] over [ka, kendB);
+// kendA <= kendB.
+__device__ __forceinline__ void warp_mma_nn2(const double* __restrict__ A, int lda, int m0, int M, const double* __restrict__ B, int ldb,
+                                             int cA, int cB, int N, int ka, int kendA, int kendB, double (&acc)[4][4]) {
+    const int lane = threadIdx.x & 31, ty = lane >> 3, tx = lane & 7;
+    const double* ap[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { int m = m0 + ty + 4 * i; if (m > M - 1) m = M - 1; ap[i] = A + (long long)m * lda; }
+    int ca = cA + 2 * tx; if (ca > N - 2) ca = N - 2;
+    int cb = cB + 2 * tx; if (cb > N - 2) cb = N - 2;
+    const double* bp = B + (long long)ka * ldb;
+    int k = ka;
+    for (; k < kendA; k += 2, bp += 2 * ldb) {
+        double2 a[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) a[i] = ld2(ap[i] + k);
+        const double2 b0a = ld2(bp + ca), b1a = ld2(bp + ldb + ca), b0b = ld2(bp + cb), b1b = ld2(bp + ldb + cb);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            acc[i][0] = fma(a[i].y, b1a.x, fma(a[i].x, b0a.x, acc[i][0]));
+            acc[i][1] = fma(a[i].y, b1a.y, fma(a[i].x, b0a.y, acc[i][1]));
+            acc[i][2] = fma(a[i].y, b1b.x, fma(a[i].x, b0b.x, acc[i][2]));
+            acc[i][3] = fma(a[i].y, b1b.y, fma(a[i].x, b0b.y, acc[i][3]));
+        }
+    }
+    for (; k < kendB; k += 2, bp += 2 * ldb) {
+        double2 a[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) a[i] = ld2(ap[i] + k);
+        const double2 b0b = ld2(bp + cb), b1b = ld2(bp + ldb + cb);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            acc[i][2] = fma(a[i].y, b1b.x, fma(a[i].x, b0b.x, acc[i][2]));
+            acc[i][3] = fma(a[i].y, b1b.y, fma(a[i].x, b0b.y, acc[i][3]));
+        }
+    }
+}
+// NT: columns kA + tx + 8 j (j < 2) -> acc[.][0..1] over c in [sA, kend), columns kB + tx + 8 j -> acc[.][2..3] over [sB, kend).
+__device__ __forceinline__ void warp_mma_nt2(const double* __restrict__ A, int lda, int m0, int M, const double* __restrict__ B, int ldb,
+                                             int kA, int kB, int R, int sA, int sB, int kend, double (&acc)[4][4]) {
+    const int lane = threadIdx.x & 31, ty = lane >> 3, tx = lane & 7;
+    const double* ap[4];
+    const double* bp[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int m = m0 + ty + 4 * i; if (m > M - 1) m = M - 1;
+        int r = ((i < 2) ? kA : kB) + tx + 8 * (i & 1); if (r > R - 1) r = R - 1;
+        ap[i] = A + (long long)m * lda;
+        bp[i] = B + (long long)r * ldb;
+    }
+    // the block that starts earlier runs alone over [lo, hi)  (static register indices: two copies of the loop)
+    const int lo = sA < sB ? sA : sB, hi = sA < sB ? sB : sA;
+    int k = lo;
+    const int hic = hi < kend ? hi : kend;
+    if (sA < sB) {
+        for (; k < hic; k += 2) {
+            double2 a[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = ld2(ap[i] + k);
+            const double2 b0 = ld2(bp[0] + k), b1 = ld2(bp[1] + k);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                acc[i][0] = fma(a[i].y, b0.y, fma(a[i].x, b0.x, acc[i][0]));
+                acc[i][1] = fma(a[i].y, b1.y, fma(a[i].x, b1.x, acc[i][1]));
+            }
+        }
+    } else {
+        for (; k < hic; k += 2) {
+            double2 a[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = ld2(ap[i] + k);
+            const double2 b0 = ld2(bp[2] + k), b1 = ld2(bp[3] + k);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                acc[i][2] = fma(a[i].y, b0.y, fma(a[i].x, b0.x, acc[i][2]));
+                acc[i][3] = fma(a[i].y, b1.y, fma(a[i].x, b1.x, acc[i][3]));
+            }
+        }
+    }
+    for (; k < kend; k += 2) {
+        double2 a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { a[i] = ld2(ap[i] + k); b[i] = ld2(bp[i] + k); }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i].y, b[j].y, fma(a[i].x, b[j].x, acc[i][j]));
+    }
+}
+
 // NT, warp tile 32 x 32, thread tile 8 x 4 (Schur complement kernel): rows m0 + ty + 4 i (i < 8), columns r0 + tx + 8 j.
 __device__ __forceinline__ void warp_mma_nt32(const double* __restrict__ A, int lda, int m0, int M, int r0, int ka, int kb, double (&acc)[8][4]) {
     const int lane = threadIdx.x & 31, ty = lane >> 3, tx = lane & 7;
@@ -176,26 +268,33 @@ __device__ __forceinline__ void cta_gemm_nt(const double* __restrict__ A, int ld
 // ------------------------------------------------------------------------------------------------- 16 x 16 building blocks
 #define B200_WLD 18  // leading dimension of the 16 x 16 inverse diagonal block in shared memory (== 2 mod 4)
 
-// Diagonal block by ONE warp, entirely in registers: lane l owns row l of the jb x jb block (jb <= 16, padded with
-// identity), pivots / column entries travel by warp shuffle.  Produces W = L^-1 (L = Cholesky factor of the block):
-// Wd[i * WLD + l] = W[i][l] (row-major, lower), Tdiag / invd = L^T / reciprocal diagonal (scratch, used by the legacy
-// solver below).  If inv_in_place: the block itself becomes W^T (upper triangle incl. diagonal, strictly lower part
-// zeroed), else L is written back in place (lower) with the strictly lower part of W stashed above the diagonal.
+// Diagonal block by ONE warp, entirely in registers: lane l < 16 owns row l of the jb x jb block (jb <= 16, padded with
+// identity); lane 16 + r carries row r of an appended identity, which the same column operations turn into row r of
+// W^T = L^-T (the inverse of the factor comes for free, no separate substitution).  Pivots / column entries travel by warp
+// shuffle.  Wd[i * WLD + l] = W[i][l] (row-major, lower).  If inv_in_place: the block itself becomes W^T (upper triangle
+// incl. diagonal, strictly lower part zeroed); else L is written back in place (lower) with the strictly lower part of W
+// stashed above the diagonal, and Tdiag / invd receive L^T / the reciprocal diagonal (legacy static solver).
 // Returns 0 or 1 + index of a non-positive pivot (uniform over the warp).
 __device__ __forceinline__ int warp_potrf16(double* Db, int ld, int jb, double* Tdiag, double* invd, double* Wd, bool inv_in_place) {
     const int l = threadIdx.x & 31;
+    const int rr = l & 15;
     double r[B200_NB];
+    if (l < B200_NB) {
 #pragma unroll
-    for (int c = 0; c < B200_NB; c++) r[c] = (l < jb && c < jb && c <= l) ? Db[(long long)l * ld + c] : ((l == c) ? 1.0 : 0.0);
+        for (int c = 0; c < B200_NB; c++) r[c] = (l < jb && c < jb && c <= l) ? Db[(long long)l * ld + c] : ((l == c) ? 1.0 : 0.0);
+    } else {
+#pragma unroll
+        for (int c = 0; c < B200_NB; c++) r[c] = (c == rr) ? 1.0 : 0.0;
+    }
     int fail = 0;
 #pragma unroll
     for (int c = 0; c < B200_NB; c++) {
         double d = __shfl_sync(0xffffffffu, r[c], c);
         if (!(d > 0.0) || !(d < 1.0e300)) { if (!fail) fail = 1 + c; d = 1.0; }
         const double inv = rsqrt(d);
-        const double x = r[c] * inv;   // lane c: sqrt(d) ; lanes > c: L[l][c]
+        const double x = r[c] * inv;   // lane c: sqrt(d) ; lanes c < l < 16: L[l][c] ; lane 16 + r: W[c][r]
         r[c] = x;
-        if (l == c) invd[c] = inv;
+        if (!inv_in_place && l == c) invd[c] = inv;
 #pragma unroll
         for (int c2 = c + 1; c2 < B200_NB; c2++) {
             const double lc2 = __shfl_sync(0xffffffffu, x, c2);
@@ -203,33 +302,24 @@ __device__ __forceinline__ int warp_potrf16(double* Db, int ld, int jb, double* 
         }
     }
     if (l < B200_NB) {
+        if (!inv_in_place) {
 #pragma unroll
-        for (int c = 0; c < B200_NB; c++) {
-            if (c <= l) {
-                if (!inv_in_place && l < jb && c < jb) Db[(long long)l * ld + c] = r[c];
-                Tdiag[c * B200_NB + l] = r[c];
+            for (int c = 0; c < B200_NB; c++) {
+                if (c <= l) {
+                    if (l < jb && c < jb) Db[(long long)l * ld + c] = r[c];
+                    Tdiag[c * B200_NB + l] = r[c];
+                }
             }
         }
-    }
-    __syncwarp();
-    // W = L^-1: lane c solves L w = e_c by right-looking forward substitution (L entries broadcast from Tdiag)
-    if (l < B200_NB) {
-        double w[B200_NB];
+    } else {
+        // lane 16 + rr holds row rr of W^T: r[c] = W[c][rr] (zero for c < rr)
 #pragma unroll
-        for (int i = 0; i < B200_NB; i++) w[i] = (i == l) ? 1.0 : 0.0;
-#pragma unroll
-        for (int i = 0; i < B200_NB; i++) {
-            w[i] *= invd[i];
-#pragma unroll
-            for (int i2 = i + 1; i2 < B200_NB; i2++) w[i2] = fma(-Tdiag[i * B200_NB + i2], w[i], w[i2]);
-        }
-#pragma unroll
-        for (int i = 0; i < B200_NB; i++) {
-            Wd[i * B200_WLD + l] = (i >= l) ? w[i] : 0.0;
+        for (int c = 0; c < B200_NB; c++) {
+            Wd[c * B200_WLD + rr] = r[c];
             if (inv_in_place) {
-                if (l < jb && i < jb) Db[(long long)l * ld + i] = (i >= l) ? w[i] : 0.0;   // row l of W^T
+                if (rr < jb && c < jb) Db[(long long)rr * ld + c] = r[c];
             } else {
-                if (i > l && i < jb) Db[(long long)l * ld + i] = w[i];
+                if (c > rr && c < jb) Db[(long long)rr * ld + c] = r[c];
             }
         }
     }
@@ -678,8 +768,45 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                 PH_ADD(3);
                 const int rtiles = (cr + 15) >> 4;
                 const int tpw = nwarps / rtiles;              // column tiles per wave (rtiles <= CR/16 <= nwarps)
-                // ---- y = p W^T : column-tile waves from the right, results written back in place after a barrier
-                {
+                // ---- y = p W^T, results written back in place after a barrier.  Balanced scheme (one wave): every warp of a row
+                // group owns the 16-column blocks s and nb-1-s (short + long contraction); else column-tile waves from the right.
+                const int nb16 = (n + 15) >> 4, npair = (nb16 + 1) >> 1;
+                if (npair <= tpw) {
+                    const int slot = warp % tpw, rt = warp / tpw;
+                    const bool act = rt < rtiles && slot < npair;
+                    const int bA = slot, bB = nb16 - 1 - slot;   // bA <= bB ; equal: the middle block of an odd count
+                    double acc[4][4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) acc[q][j] = 0.0;
+                    const int m0 = rt << 4;
+                    if (act) {
+                        int ka = 0, kb = n;
+                        if (seg == 0) xrow_range(dm, a.dense_o != 0, r0 + m0, ka, kb);
+                        int kendA = (bA << 4) + 16; if (kendA > kb) kendA = kb;
+                        int kendB = (bB << 4) + 16; if (kendB > kb) kendB = kb;
+                        if (bA == bB) kendA = ka;   // single block: only the B half is used
+                        warp_mma_nn2(Yb, ld, m0, cr, Ms, ld, bA << 4, bB << 4, n, ka, kendA, kendB, acc);
+                    }
+                    __syncthreads();
+                    if (act) {
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int lr = m0 + ty + 4 * q;
+                            if (lr >= cr) continue;
+#pragma unroll
+                            for (int j = 0; j < 2; j++) {
+                                if (j == 0 && bA == bB) continue;
+                                const int c = ((j == 0 ? bA : bB) << 4) + 2 * tx;
+                                if (c >= n) continue;
+                                st2(Yb + (long long)lr * ld + c, acc[q][2 * j], acc[q][2 * j + 1]);
+                                if (seg == 1) st2(Yg + (long long)(r0 - xo + lr) * n + c, acc[q][2 * j], acc[q][2 * j + 1]);
+                            }
+                        }
+                    }
+                    __syncthreads();
+                } else {
                     const int nct = (n + 31) >> 5;
                     for (int hi = nct; hi > 0; hi -= tpw) {
                         const int lo = hi - tpw > 0 ? hi - tpw : 0;
@@ -719,8 +846,47 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                 }
                 PH_ADD(4);
                 if (!has_x) continue;
-                // ---- z = y W (chain columns only), in place after a barrier
-                {
+                // ---- z = y W (chain columns only), in place after a barrier; same balanced pairing of 16-column blocks
+                const int nbz = (n - kz0 + 15) >> 4, npz = (nbz + 1) >> 1;
+                if (npz <= tpw) {
+                    const int slot = warp % tpw, rt = warp / tpw;
+                    const bool act = rt < rtiles && slot < npz;
+                    const int bA = slot, bB = nbz - 1 - slot;
+                    const int kA = kz0 + (bA << 4), kB = kz0 + (bB << 4);
+                    double acc[4][4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) acc[q][j] = 0.0;
+                    const int m0 = rt << 4;
+                    if (act) {
+                        int sA = kA, sB = kB;
+                        if (seg == 0) {
+                            // rows of O: y is zero left of ka; z is only needed up to the last column that feeds the LOWER triangle
+                            int ka, kb; xrow_range(dm, a.dense_o != 0, r0 + m0, ka, kb);
+                            if (ka > sA) sA = ka;
+                            if (ka > sB) sB = ka;
+                            if (!a.dense_o) { if (kA >= kb) sA = n; if (kB >= kb) sB = n; }
+                        }
+                        if (bA == bB) sA = n;
+                        warp_mma_nt2(Yb, ld, m0, cr, Ms, ld, kA, kB, n, sA, sB, n, acc);
+                    }
+                    __syncthreads();
+                    if (act) {
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int lr = m0 + ty + 4 * q;
+                            if (lr >= cr) continue;
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                if (j < 2 && bA == bB) continue;
+                                const int c = ((j < 2) ? kA : kB) + tx + 8 * (j & 1);
+                                if (c < n) Yb[(long long)lr * ld + c] = acc[q][j];
+                            }
+                        }
+                    }
+                    __syncthreads();
+                } else {
                     const int nct = (n - kz0 + 31) >> 5;
                     for (int lo = 0; lo < nct; lo += tpw) {
                         const int hi = lo + tpw < nct ? lo + tpw : nct;
@@ -735,8 +901,13 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                         const int m0 = rt << 4, k0 = kz0 + (ct << 5);
                         if (act) {
                             int ca = k0;
-                            if (seg == 0) { int ka, kb; xrow_range(dm, a.dense_o != 0, r0 + m0, ka, kb); if (ka > ca) ca = ka; }
-                            warp_mma_nt(Yb, ld, m0, cr, Ms, ld, k0, n, ca, n, acc);
+                            bool need = true;
+                            if (seg == 0) {
+                                int ka, kb; xrow_range(dm, a.dense_o != 0, r0 + m0, ka, kb);
+                                if (ka > ca) ca = ka;
+                                if (!a.dense_o && k0 >= kb) need = false;
+                            }
+                            if (need) warp_mma_nt(Yb, ld, m0, cr, Ms, ld, k0, n, ca, n, acc);
                         }
                         __syncthreads();
                         if (act) {
@@ -801,40 +972,47 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                         __syncthreads();
                     }
                 } else {
-                    const int ng = (nc + 31) >> 5;
-                    const int nq = (nwarps / ng) > 0 ? (nwarps / ng) : 1;
-                    const int rpq = (cr + nq - 1) / nq;
-                    for (int item = warp; item < ng * nq; item += nwarps) {
-                        const int g = item % ng, q = item / ng;
-                        const int ci = 32 * g + lane;
-                        const bool act = ci < nc;
-                        const int cic = act ? ci : nc - 1;
-                        const int zs = dm.ozs[cic];
-                        const int lr1 = ((q + 1) * rpq < cr) ? (q + 1) * rpq : cr;
-                        if (ow <= 16) {
-                            double op[16];
+                    // block-sparse coupling: thread tile 4 rows x (group of <= 4 rows of O sharing the packed window), t in pairs
+                    // (consecutive lanes own consecutive columns of the same rows: the stores of a warp fall into few sectors)
+                    // lane order: 8 consecutive row groups (consecutive rows: conflict-free z loads, the O operand is a broadcast),
+                    // then the column groups (the stores of a warp cover 4 column groups x 8 rows = 8 sectors)
+                    const int nrg = (cr + 3) >> 2;
+                    const int total = 8 * dm.n_ogrp * ((nrg + 7) >> 3);
+                    for (int T = threadIdx.x; T < total; T += blockDim.x) {
+                        const int cg = (T >> 3) % dm.n_ogrp, rg = (T & 7) + 8 * ((T >> 3) / dm.n_ogrp);
+                        if (rg >= nrg) continue;
+                        const int i0 = dm.ogrp[3 * cg], cstr = dm.ogrp[3 * cg + 1], ncol = dm.ogrp[3 * cg + 2];
+                        const int zs = dm.ozs[i0];
+                        const double* zp[4];
+                        const double* op[4];
 #pragma unroll
-                            for (int t = 0; t < 16; t += 2) {
-                                if (t < ow) { const double2 v = ld2(Op + cic * owp + t); op[t] = v.x; op[t + 1] = v.y; }
-                                else { op[t] = 0.0; op[t + 1] = 0.0; }
-                            }
-                            for (int lr = q * rpq; lr < lr1; lr++) {
-                                const double* z = Yb + (long long)lr * ld + zs;
-                                double s0 = 0.0, s1 = 0.0;
+                        for (int q = 0; q < 4; q++) {
+                            int lr = rg + nrg * q; if (lr > cr - 1) lr = cr - 1;
+                            const int ci = i0 + cstr * (q < ncol ? q : ncol - 1);
+                            zp[q] = Yb + (long long)lr * ld + zs;
+                            op[q] = Op + ci * owp;
+                        }
+                        double acc[4][4];
 #pragma unroll
-                                for (int t = 0; t < 16; t += 2) {
-                                    if (t < ow) { const double2 v = ld2(z + t); s0 = fma(v.x, op[t], s0); s1 = fma(v.y, op[t + 1], s1); }
-                                }
-                                if (act) Fout[(long long)(r0 + lr) * nc + ci] = s0 + s1;
-                            }
-                        } else {
-                            for (int lr = q * rpq; lr < lr1; lr++) {
-                                const double* z = Yb + (long long)lr * ld + zs;
-                                const double* o = Op + cic * owp;
-                                double s0 = 0.0;
-                                for (int t = 0; t < ow; t++) s0 = fma(z[t], o[t], s0);
-                                if (act) Fout[(long long)(r0 + lr) * nc + ci] = s0;
-                            }
+                        for (int q = 0; q < 4; q++)
+#pragma unroll
+                            for (int j = 0; j < 4; j++) acc[q][j] = 0.0;
+                        for (int t = 0; t < ow; t += 2) {
+                            double2 av[4], bv[4];
+#pragma unroll
+                            for (int q = 0; q < 4; q++) { av[q] = ld2(zp[q] + t); bv[q] = ld2(op[q] + t); }
+#pragma unroll
+                            for (int q = 0; q < 4; q++)
+#pragma unroll
+                                for (int j = 0; j < 4; j++) acc[q][j] = fma(av[q].y, bv[j].y, fma(av[q].x, bv[j].x, acc[q][j]));
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int lr = rg + nrg * q;
+                            if (lr >= cr) continue;
+#pragma unroll
+                            for (int j = 0; j < 4; j++)
+                                if (j < ncol) Fout[(long long)(r0 + lr) * nc + i0 + cstr * j] = acc[q][j];
                         }
                     }
                 }
@@ -910,13 +1088,16 @@ __global__ void __launch_bounds__(B200_SCHUR_THREADS) chain_schur_kernel(Dims dm
     if (*sb.status != 0) return;
     const int nrt = (h + 31) >> 5;
     const int ntiles = nrt * (nrt + 1) / 2;
-    for (int base = 0; base < ntiles; base += 2 * nwarps) {
+    const int nsplit = gridDim.y, part = blockIdx.y;          // output tiles dealt round-robin to the CTAs of a chunk
+    const int ntl = (ntiles - part + nsplit - 1) / nsplit;    // tiles of this CTA: part, part + nsplit, ...
+    for (int base = 0; base < ntl; base += 2 * nwarps) {
         int tr[2], tc[2];
         bool act[2];
 #pragma unroll
         for (int s = 0; s < 2; s++) {
-            const int t = base + s * nwarps + warp;
-            act[s] = t < ntiles;
+            const int tloc = base + s * nwarps + warp;
+            const int t = tloc * nsplit + part;
+            act[s] = tloc < ntl;
             int r = 0;
             while ((r + 1) * (r + 2) / 2 <= (act[s] ? t : 0)) r++;
             tr[s] = r; tc[s] = (act[s] ? t : 0) - r * (r + 1) / 2;
@@ -962,6 +1143,8 @@ __global__ void __launch_bounds__(B200_SCHUR_THREADS) chain_schur_kernel(Dims dm
     for (int e = threadIdx.x; e < ns1 * ns1; e += blockDim.x) {
         const int a1 = e / ns1, a2 = e - a1 * ns1;
         if (a2 > a1) continue;
+        const int trr = a1 >> 5, tcc = a2 >> 5;
+        if ((trr * (trr + 1) / 2 + tcc) % nsplit != part) continue;   // the CTA that wrote the entry adds to it
         double s = 0.0;
         for (int i = 0; i < a.n; i++) s += a.Ssrc[((long long)a.src0 + i) * ns1 * ns1 + e];
         a.Sacc[(long long)a1 * hmax + a2] += s;
@@ -979,49 +1162,48 @@ __global__ void __launch_bounds__(256) chain_reduce_kernel(Dims dm, Level lv, in
     const int n_c = (int)(q - lv.begin[c]);                  // interior nodes of chunk c
     const double* Fc = lv.F + ((long long)c * 2 + (n_c & 1)) * Fsz;   // written by its last node
     const double* Sn = lv.S + (long long)(c + 1) * hmax * hmax;        // chunk c+1 (has left rows)
-    if (threadIdx.x == 0) lv.sep_st[c] = lv.st ? lv.st[q] : (int)q;
+    if (threadIdx.x == 0 && blockIdx.y == 0) lv.sep_st[c] = lv.st ? lv.st[q] : (int)q;
     double* Dr = lv.Dred + (long long)c * ntp * ntp;
     const double* Dg = lv.Dsrc + q * ntp * ntp;
-    for (int e = threadIdx.x; e < ntp * ntp; e += blockDim.x) {
-        const int r = e / ntp, col = e % ntp;
-        double v = Dg[e];
-        if (r >= nl && col >= nl) {
-            const int i = r - nl, j = col - nl;
-            const int hi = i > j ? i : j, lo = i > j ? j : i;
-            if (n_c > 0) v -= Fc[(long long)hi * nc + lo];
-            v += Sn[(long long)(ns1 + hi) * hmax + (ns1 + lo)];
-        }
-        Dr[e] = v;
-    }
     double* Ar = lv.Ared + (long long)c * ns1 * ntp;
     const double* Ag = lv.Asrc + q * ns1 * ntp;
-    for (int e = threadIdx.x; e < ns1 * ntp; e += blockDim.x) {
-        const int ar = e / ntp, col = e % ntp;
-        double v = Ag[e];
-        if (col >= nl) {
-            if (n_c > 0) v -= Fc[(long long)(nc + ar) * nc + (col - nl)];
-            v += Sn[(long long)(ns1 + (col - nl)) * hmax + ar];
-        }
-        Ar[e] = v;
-    }
     double* Sr = lv.Sred + (long long)c * ns1 * ns1;
     const double* Sg = lv.Ssrc + q * ns1 * ns1;
     const double* S0 = lv.S;
-    for (int e = threadIdx.x; e < ns1 * ns1; e += blockDim.x) {
-        const int r = e / ns1, col = e % ns1;
-        const int hi = r > col ? r : col, lo = r > col ? col : r;
-        double v = Sg[e] + Sn[(long long)hi * hmax + lo];
-        if (c == 0) v += S0[(long long)hi * hmax + lo];
-        Sr[e] = v;
-    }
-    if (c < P - 2) {
-        // coupling separator c -> separator c+1 through chunk c+1: -(fill of the left rows) of that chunk's last node
-        const int n_n = (int)(lv.begin[c + 2] - 1 - lv.begin[c + 1]);
-        const double* Fn = lv.F + ((long long)(c + 1) * 2 + (n_n & 1)) * Fsz;
-        double* Or = lv.Ored + (long long)c * nc * nc;
-        for (int e = threadIdx.x; e < nc * nc; e += blockDim.x) {
-            const int j = e / nc, i = e % nc;   // Or[j][i]: row = chain j of separator c+1, col = chain i of separator c
-            Or[e] = -Fn[(long long)(nc + ns1 + i) * nc + j];
+    // coupling separator c -> separator c+1 through chunk c+1: -(fill of the left rows) of that chunk's last node
+    const bool has_o = c < P - 2;
+    const int n_n = has_o ? (int)(lv.begin[c + 2] - 1 - lv.begin[c + 1]) : 0;
+    const double* Fn = lv.F + ((long long)(c + 1) * 2 + (n_n & 1)) * Fsz;
+    double* Or = lv.Ored + (long long)c * nc * nc;
+    const int e1 = ntp * ntp, e2 = e1 + ns1 * ntp, e3 = e2 + ns1 * ns1, e4 = e3 + (has_o ? nc * nc : 0);
+    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < e4; e += blockDim.x * gridDim.y) {
+        if (e < e1) {
+            const int r = e / ntp, col = e % ntp;
+            double v = Dg[e];
+            if (r >= nl && col >= nl) {
+                const int i = r - nl, j = col - nl;
+                const int hi = i > j ? i : j, lo = i > j ? j : i;
+                if (n_c > 0) v -= Fc[(long long)hi * nc + lo];
+                v += Sn[(long long)(ns1 + hi) * hmax + (ns1 + lo)];
+            }
+            Dr[e] = v;
+        } else if (e < e2) {
+            const int f = e - e1, ar = f / ntp, col = f % ntp;
+            double v = Ag[f];
+            if (col >= nl) {
+                if (n_c > 0) v -= Fc[(long long)(nc + ar) * nc + (col - nl)];
+                v += Sn[(long long)(ns1 + (col - nl)) * hmax + ar];
+            }
+            Ar[f] = v;
+        } else if (e < e3) {
+            const int f = e - e2, r = f / ns1, col = f % ns1;
+            const int hi = r > col ? r : col, lo = r > col ? col : r;
+            double v = Sg[f] + Sn[(long long)hi * hmax + lo];
+            if (c == 0) v += S0[(long long)hi * hmax + lo];
+            Sr[f] = v;
+        } else {
+            const int f = e - e3, i = f / nc, j = f % nc;   // Or[j][i]: row = chain j of separator c+1, col = chain i of separator c
+            Or[(long long)j * nc + i] = -Fn[(long long)(nc + ns1 + i) * nc + j];
         }
     }
 }
