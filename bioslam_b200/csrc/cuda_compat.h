@@ -22,6 +22,8 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) { std::me
 __device__ __forceinline__ void cp_async8(void* dst, const void* src) { std::memcpy(dst, src, 8); }
 __device__ __forceinline__ void cp_async_wait_all() {}
 __device__ __forceinline__ void prefetch_l2(const void*) {}
+__device__ __forceinline__ void named_bar_sync(int id, int count) { emu::bar_sync(id, count); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { emu::bar_arrive(id, count); }
 #else
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
@@ -33,4 +35,8 @@ __device__ __forceinline__ void cp_async8(void* dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// named barriers (ids 1..15; 0 is __syncthreads): producer/consumer hand-over between warp-specialised roles of one CTA.
+// count = number of THREADS (multiple of 32) that arrive in total; memory ordering as for bar.sync.
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 #endif

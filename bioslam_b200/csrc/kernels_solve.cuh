@@ -342,76 +342,65 @@ __device__ __forceinline__ void solve_scratch(double*& Tdiag, double*& Wd, doubl
 // row times W_jj^T (rows below: the L panel; rows above: the appended identity rows); (c) trailing update with the L panel
 // of the rows that are alive: r >= c (Cholesky) or r < j0 + 16 (appended rows already started).
 // Returns (to all threads) 0 or 1 + index of the first non-positive pivot.  Must be called by all threads of the CTA.
+// Warp-specialised: warp 0 (the "pivot" warp) runs the sequential chain of diagonal blocks -- for block s+1 it scales the
+// 16 x 16 panel block (s+1, s), applies it to the diagonal tile and factorises/inverts it -- while the other warps scale the
+// rest of column block s and apply the rank-16 trailing update.  The two roles meet at named barriers (ids 1..6, two
+// alternating instances each): W_READY (W_ss in Wd[s&1]), ROW_READY (block row s+1 scaled), T_DONE (trailing update s done).
 __device__ int cta_chol_inv(double* Ms, int ld, int n) {
     __shared__ int fail;
-    double *Tdiag, *Wd, *invd;
-    solve_scratch(Tdiag, Wd, invd);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    __shared__ __align__(16) double s_Wd2[2][B200_NB * B200_WLD];
+    double *Tdiag, *Wd0, *invd;
+    solve_scratch(Tdiag, Wd0, invd);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5, nthr = blockDim.x;
     const int ty = lane >> 3, tx = lane & 7;
+    const int nb = (n + B200_NB - 1) / B200_NB;
     if (threadIdx.x == 0) fail = 0;
     __syncthreads();
     PH_T0();
     if (warp == 0) {
-        const int f = warp_potrf16(Ms, ld, n < B200_NB ? n : B200_NB, Tdiag, invd, Wd, true);
-        if (f && lane == 0) fail = f;
-    }
-    __syncthreads();
-    PH_ADD(8);
-    if (fail) return fail;
-    for (int j0 = 0; j0 < n; j0 += B200_NB) {
-        const int jb = (n - j0 < B200_NB) ? (n - j0) : B200_NB;
-        // (b) rows r in [0, j0) U [j0 + jb, n): X[r][j0 .. j0+jb) <- X * W_jj^T, 16 (virtual) rows per warp, in place
-        const int nvr = n - jb;
-        for (int t = warp; t * 16 < nvr; t += nwarps) {
-            const double* ap[4];
-            bool ok[4];
+        // ------------------------------------------------------------------ pivot warp
+        {
+            const int f = warp_potrf16(Ms, ld, n < B200_NB ? n : B200_NB, Tdiag, invd, s_Wd2[0], true);
+            if (f && lane == 0) fail = f;
+        }
+        __syncwarp();   // W_00 (written by lanes 16..31) is read by the whole warp below
+        __threadfence_block();
+        named_bar_arrive(1, nthr);
+        for (int s = 0; s + 1 < nb; s++) {
+            const int j0 = s * B200_NB, cb0 = j0 + B200_NB;
+            const int jb1 = (n - cb0 < B200_NB) ? (n - cb0) : B200_NB;
+            const double* Wd = s_Wd2[s & 1];
+            if (s >= 1) named_bar_sync(5 + ((s - 1) & 1), nthr);     // trailing update s-1 has reached block row s+1
+            // block (s+1, s) <- block * W_ss^T  (16 rows, lane -> (row ty + 4 i, columns tx, tx + 8))
+            double acc[4][2];
+            double* xr[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                int vr = t * 16 + ty + 4 * i;
-                ok[i] = vr < nvr;
-                if (!ok[i]) vr = nvr - 1;
-                const int r = (vr < j0) ? vr : vr + jb;
-                ap[i] = Ms + (long long)r * ld + j0;
+                int r = cb0 + ty + 4 * i; if (r > n - 1) r = n - 1;
+                xr[i] = Ms + (long long)r * ld + j0;
+                acc[i][0] = 0.0; acc[i][1] = 0.0;
             }
-            double acc[4][2];
-#pragma unroll
-            for (int i = 0; i < 4; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
 #pragma unroll
             for (int c2 = 0; c2 < B200_NB; c2 += 2) {
-                if (j0 + c2 < n) {
-                    const double2 b0 = ld2(Wd + tx * B200_WLD + c2), b1 = ld2(Wd + (tx + 8) * B200_WLD + c2);
+                const double2 b0 = ld2(Wd + tx * B200_WLD + c2), b1 = ld2(Wd + (tx + 8) * B200_WLD + c2);
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const double2 a = ld2(ap[i] + c2);
-                        acc[i][0] = fma(a.y, b0.y, fma(a.x, b0.x, acc[i][0]));
-                        acc[i][1] = fma(a.y, b1.y, fma(a.x, b1.x, acc[i][1]));
-                    }
+                for (int i = 0; i < 4; i++) {
+                    const double2 av = ld2(xr[i] + c2);
+                    acc[i][0] = fma(av.y, b0.y, fma(av.x, b0.x, acc[i][0]));
+                    acc[i][1] = fma(av.y, b1.y, fma(av.x, b1.x, acc[i][1]));
                 }
             }
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                if (!ok[i]) continue;
-                double* xr = const_cast<double*>(ap[i]);
-                if (tx < jb) xr[tx] = acc[i][0];
-                if (tx + 8 < jb) xr[tx + 8] = acc[i][1];
+                if (cb0 + ty + 4 * i < n) { xr[i][tx] = acc[i][0]; xr[i][tx + 8] = acc[i][1]; }
             }
-        }
-        __syncthreads();
-        PH_ADD(9);
-        const int cb0 = j0 + B200_NB;
-        if (cb0 >= n) break;
-        // (c1) trailing update of the NEXT column block only (16 columns), alive rows: r >= c or r < cb0
-        for (int t = warp; t * 16 < n; t += nwarps) {
-            const int m0 = t * 16;
+            __syncwarp();
+            // diagonal tile (s+1, s+1), lower part: -= L L^T with the block just scaled
             {
-                const double* ap[4];
                 const double* bp[2];
 #pragma unroll
-                for (int i = 0; i < 4; i++) { int r = m0 + ty + 4 * i; if (r > n - 1) r = n - 1; ap[i] = Ms + (long long)r * ld + j0; }
-#pragma unroll
                 for (int j = 0; j < 2; j++) { int c = cb0 + tx + 8 * j; if (c > n - 1) c = n - 1; bp[j] = Ms + (long long)c * ld + j0; }
-                double acc[4][2];
 #pragma unroll
                 for (int i = 0; i < 4; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
 #pragma unroll
@@ -419,57 +408,120 @@ __device__ int cta_chol_inv(double* Ms, int ld, int n) {
                     const double2 b0 = ld2(bp[0] + c2), b1 = ld2(bp[1] + c2);
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
-                        const double2 a = ld2(ap[i] + c2);
-                        acc[i][0] = fma(a.y, b0.y, fma(a.x, b0.x, acc[i][0]));
-                        acc[i][1] = fma(a.y, b1.y, fma(a.x, b1.x, acc[i][1]));
+                        const double2 av = ld2(xr[i] + c2);
+                        acc[i][0] = fma(av.y, b0.y, fma(av.x, b0.x, acc[i][0]));
+                        acc[i][1] = fma(av.y, b1.y, fma(av.x, b1.x, acc[i][1]));
                     }
                 }
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const int r = m0 + ty + 4 * i;
+                    const int r = cb0 + ty + 4 * i;
 #pragma unroll
                     for (int j = 0; j < 2; j++) {
                         const int c = cb0 + tx + 8 * j;
-                        if (r < n && c < n && (r >= c || r < cb0)) Ms[(long long)r * ld + c] -= acc[i][j];
+                        if (r < n && c <= r) Ms[(long long)r * ld + c] -= acc[i][j];
                     }
                 }
             }
+#ifdef B200_EMU_DBG
+            if (lane == 0) printf("pivot s=%d: L[%d][%d]=%g  diag[%d]=%g\n", s, cb0, j0, Ms[(long long)cb0 * ld + j0], cb0, Ms[(long long)cb0 * ld + cb0]);
+#endif
+            __threadfence_block();
+            named_bar_arrive(3 + (s & 1), nthr);                      // block row s+1 of column block s is scaled
+            __syncwarp();
+            {
+                const int f = warp_potrf16(Ms + (long long)cb0 * ld + cb0, ld, jb1, Tdiag, invd, s_Wd2[(s + 1) & 1], true);
+                if (f && lane == 0 && fail == 0) fail = cb0 + f;
+            }
+            __syncwarp();
+            __threadfence_block();
+            named_bar_arrive(1 + ((s + 1) & 1), nthr);                // W_{s+1} ready
+            if (fail) break;                                          // (uniform: set by lane 0 before the fence)
         }
-        __syncthreads();
-        // (c2) look-ahead: warp 0 factorises the next diagonal block while the other warps finish the trailing update
-        const int cb1 = cb0 + B200_NB;
-        const int wfirst = nwarps > 1 ? 1 : 0, nwork = nwarps > 1 ? nwarps - 1 : 1;
-        if (warp == 0) {
-            const int f = warp_potrf16(Ms + (long long)cb0 * ld + cb0, ld, (n - cb0 < B200_NB) ? (n - cb0) : B200_NB, Tdiag, invd, Wd, true);
-            if (f && lane == 0) fail = cb0 + f;
-        }
-        if (cb1 < n && warp >= wfirst) {
-            const int ntr = (n + 15) >> 4, ntc = (n - cb1 + 31) >> 5;
-            for (int tile = warp - wfirst; tile < ntr * ntc; tile += nwork) {
-                const int m0 = (tile / ntc) << 4, c0 = cb1 + ((tile % ntc) << 5);
-                if (m0 >= cb0 && m0 + 15 < c0) continue;   // dead zone: not-yet-started appended rows
-                double acc[4][4];
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-#pragma unroll
-                    for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
-                warp_mma_nt(Ms, ld, m0, n, Ms, ld, c0, n, j0, cb0, acc);
+        // consume the last trailing-update barrier so that every named barrier is back to zero arrivals for the next call
+        if (nb >= 2 && !fail) named_bar_sync(5 + ((nb - 2) & 1), nthr);
+    } else {
+        // ------------------------------------------------------------------ worker warps
+        const int wk = warp - 1, nwk = nwarps - 1;
+        for (int s = 0; s < nb; s++) {
+            const int j0 = s * B200_NB, cb0 = j0 + B200_NB;
+            const int jb = (n - j0 < B200_NB) ? (n - j0) : B200_NB;
+            const double* Wd = s_Wd2[s & 1];
+            named_bar_sync(1 + (s & 1), nthr);                        // W_ss ready (and every worker has finished update s-1)
+            if (fail) break;
+            // rows r in [0, j0) U [cb0 + 16, n): X[r][j0 .. j0+jb) <- X * W_ss^T, 16 (virtual) rows per warp, in place
+            const int skip = (cb0 < n) ? ((n - cb0 < B200_NB) ? (n - cb0) : B200_NB) : 0;   // block row s+1 belongs to the pivot warp
+            const int nvr = n - jb - skip;
+            for (int t = wk; t * 16 < nvr; t += nwk) {
+                const double* ap[4];
+                bool ok[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const int r = m0 + ty + 4 * i;
+                    int vr = t * 16 + ty + 4 * i;
+                    ok[i] = vr < nvr;
+                    if (!ok[i]) vr = nvr - 1;
+                    const int r = (vr < j0) ? vr : vr + jb + skip;
+                    ap[i] = Ms + (long long)r * ld + j0;
+                }
+                double acc[4][2];
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int c = c0 + tx + 8 * j;
-                        if (r < n && c < n && (r >= c || r < cb0)) Ms[(long long)r * ld + c] -= acc[i][j];
+                for (int i = 0; i < 4; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+#pragma unroll
+                for (int c2 = 0; c2 < B200_NB; c2 += 2) {
+                    if (j0 + c2 < n) {
+                        const double2 b0 = ld2(Wd + tx * B200_WLD + c2), b1 = ld2(Wd + (tx + 8) * B200_WLD + c2);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const double2 av = ld2(ap[i] + c2);
+                            acc[i][0] = fma(av.y, b0.y, fma(av.x, b0.x, acc[i][0]));
+                            acc[i][1] = fma(av.y, b1.y, fma(av.x, b1.x, acc[i][1]));
+                        }
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (!ok[i]) continue;
+                    double* xw = const_cast<double*>(ap[i]);
+                    if (tx < jb) xw[tx] = acc[i][0];
+                    if (tx + 8 < jb) xw[tx + 8] = acc[i][1];
+                }
+            }
+            if (cb0 >= n) break;
+            __threadfence_block();
+            named_bar_sync(3 + (s & 1), nthr);                        // whole column block s scaled (pivot: block row s+1)
+            // trailing update: Ms[r][c] -= sum_t Ms[r][j0+t] Ms[c][j0+t], c >= cb0, alive rows (r >= c or r < cb0),
+            // except the diagonal tile (s+1, s+1), which the pivot warp has already updated
+            {
+                const int ntr = (n + 15) >> 4, ntc = (n - cb0 + 31) >> 5;
+                for (int tile = wk; tile < ntr * ntc; tile += nwk) {
+                    const int m0 = (tile / ntc) << 4, c0 = cb0 + ((tile % ntc) << 5);
+                    if (m0 >= cb0 && m0 + 15 < c0) continue;   // dead zone: not-yet-started appended rows
+                    double acc[4][4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+                    warp_mma_nt(Ms, ld, m0, n, Ms, ld, c0, n, j0, cb0, acc);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int r = m0 + ty + 4 * i;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int c = c0 + tx + 8 * j;
+                            const bool pivots = (r >= cb0 && r < cb0 + B200_NB && c < cb0 + B200_NB);
+                            if (r < n && c < n && (r >= c || r < cb0) && !pivots) Ms[(long long)r * ld + c] -= acc[i][j];
+                        }
                     }
                 }
             }
+            __threadfence_block();
+            named_bar_arrive(5 + (s & 1), nthr);                      // trailing update s done
         }
-        __syncthreads();
-        PH_ADD(10);
-        if (fail) return fail;
     }
-    return 0;
+    __syncthreads();
+    PH_ADD(10);
+    return fail;
 }
 
 // ------------------------------------------------------------------------------------------------- legacy in-smem Cholesky
@@ -594,13 +646,13 @@ __host__ __device__ inline long long sweep_smem_doubles(int ntp, int ld, int cr,
 __host__ __device__ inline int static_lds(int ns) { int lds = ns + (ns & 1); while ((lds & 3) != 2) lds += 2; return lds; }
 
 // [ka, kb) (even bounds, time-block coordinates) of the columns in which rows [r0, r0+16) of O can be non-zero
-__device__ __forceinline__ void xrow_range(const Dims& dm, bool dense, int r0, int& ka, int& kb) {
+__device__ __forceinline__ void xrow_range(const Dims& dm, const int* orow, bool dense, int r0, int& ka, int& kb) {
     if (dense) { ka = dm.nl & ~1; kb = dm.ntp; return; }
     const int lane = threadIdx.x & 31;
     int lo = dm.ntp, hi = 0;
     const int r = r0 + (lane & 15);
     if (r < dm.nc) {
-        const int c0 = dm.orow[2 * r], c1 = dm.orow[2 * r + 1];
+        const int c0 = orow[2 * r], c1 = orow[2 * r + 1];
         if (c1 > c0) { lo = (dm.nl + c0) & ~1; hi = (dm.nl + c1 + 1) & ~1; }
     }
 #pragma unroll
@@ -621,6 +673,12 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
     double* Yb = sm + (long long)n * ld;
     double* Op = Yb + (long long)CR * ld;
     const int kz0 = nl & ~1;                        // first column of z that is needed (chain columns, pair aligned)
+    // structure tables of O in shared memory (they are consulted at the start of every GEMM phase: keep them off the L2 path)
+    __shared__ int s_orow[2 * 256], s_ozs[256], s_ogrp[3 * 256];
+    for (int e = threadIdx.x; e < 2 * nc; e += blockDim.x) s_orow[e] = dm.orow[e];
+    for (int e = threadIdx.x; e < nc; e += blockDim.x) s_ozs[e] = dm.ozs[e];
+    for (int e = threadIdx.x; e < 3 * dm.n_ogrp; e += blockDim.x) s_ogrp[e] = dm.ogrp[e];
+    __syncthreads();
     for (int i = 0; i < a.n; i++) {
         const long long src = a.src0 + i;
         const long long st = a.st_idx ? a.st_idx[i] : src;
@@ -638,7 +696,7 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
         if (has_x && !a.dense_o) {   // packed rows of O: Op[r][t] = O[r][ozs[r] - nl + t]
             for (int e = threadIdx.x; e < nc * ow; e += blockDim.x) {
                 const int r = e / ow, t = e - r * ow;
-                const int cc = dm.ozs[r] - nl + t;
+                const int cc = s_ozs[r] - nl + t;
                 if (cc >= 0 && cc < nc) cp_async8(Op + r * owp + t, Og + (long long)r * nc + cc);
                 else Op[r * owp + t] = 0.0;
             }
@@ -647,6 +705,9 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
             const double* Dn = a.Dsrc + (src + 1) * n * n;
             for (int e = threadIdx.x * 16; e < n * n; e += blockDim.x * 16) prefetch_l2(Dn + e);
         }
+        // ... and this node's panel sources (read in phase B, after the factorisation)
+        for (int e = threadIdx.x * 16; e < ns1 * n; e += blockDim.x * 16) prefetch_l2(Ag + e);
+        if (has_x) for (int e = threadIdx.x * 16; e < nc * nc; e += blockDim.x * 16) prefetch_l2(Og + e);
         // fill of the previous node (chain x chain, lower triangle): loads issued before the wait, 8 rows x 4 columns per lane
         for (int rb = 0; rb < n; rb += 8 * nwarps) {
             for (int cb = 0; cb < n; cb += 128) {
@@ -783,7 +844,7 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                     const int m0 = rt << 4;
                     if (act) {
                         int ka = 0, kb = n;
-                        if (seg == 0) xrow_range(dm, a.dense_o != 0, r0 + m0, ka, kb);
+                        if (seg == 0) xrow_range(dm, s_orow, a.dense_o != 0, r0 + m0, ka, kb);
                         int kendA = (bA << 4) + 16; if (kendA > kb) kendA = kb;
                         int kendB = (bB << 4) + 16; if (kendB > kb) kendB = kb;
                         if (bA == bB) kendA = ka;   // single block: only the B half is used
@@ -822,7 +883,7 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                         const int m0 = rt << 4, c0 = ct << 5;
                         if (act) {
                             int ka = 0, kb = n;
-                            if (seg == 0) xrow_range(dm, a.dense_o != 0, r0 + m0, ka, kb);
+                            if (seg == 0) xrow_range(dm, s_orow, a.dense_o != 0, r0 + m0, ka, kb);
                             const int kend = (c0 + 32 < kb) ? c0 + 32 : kb;
                             warp_mma_nn(Yb, ld, m0, cr, Ms, ld, c0, n, ka, kend, acc);
                         }
@@ -863,7 +924,7 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                         int sA = kA, sB = kB;
                         if (seg == 0) {
                             // rows of O: y is zero left of ka; z is only needed up to the last column that feeds the LOWER triangle
-                            int ka, kb; xrow_range(dm, a.dense_o != 0, r0 + m0, ka, kb);
+                            int ka, kb; xrow_range(dm, s_orow, a.dense_o != 0, r0 + m0, ka, kb);
                             if (ka > sA) sA = ka;
                             if (ka > sB) sB = ka;
                             if (!a.dense_o) { if (kA >= kb) sA = n; if (kB >= kb) sB = n; }
@@ -903,7 +964,7 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                             int ca = k0;
                             bool need = true;
                             if (seg == 0) {
-                                int ka, kb; xrow_range(dm, a.dense_o != 0, r0 + m0, ka, kb);
+                                int ka, kb; xrow_range(dm, s_orow, a.dense_o != 0, r0 + m0, ka, kb);
                                 if (ka > ca) ca = ka;
                                 if (!a.dense_o && k0 >= kb) need = false;
                             }
@@ -981,8 +1042,8 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                     for (int T = threadIdx.x; T < total; T += blockDim.x) {
                         const int cg = (T >> 3) % dm.n_ogrp, rg = (T & 7) + 8 * ((T >> 3) / dm.n_ogrp);
                         if (rg >= nrg) continue;
-                        const int i0 = dm.ogrp[3 * cg], cstr = dm.ogrp[3 * cg + 1], ncol = dm.ogrp[3 * cg + 2];
-                        const int zs = dm.ozs[i0];
+                        const int i0 = s_ogrp[3 * cg], cstr = s_ogrp[3 * cg + 1], ncol = s_ogrp[3 * cg + 2];
+                        const int zs = s_ozs[i0];
                         const double* zp[4];
                         const double* op[4];
 #pragma unroll

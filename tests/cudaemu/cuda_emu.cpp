@@ -9,19 +9,21 @@ char* dyn_smem = nullptr;
 long long launch_counter = 0;
 
 namespace {
-enum State { RUNNABLE, WAIT_BLOCK, WAIT_WARP, DONE };
+enum State { RUNNABLE, WAIT_BLOCK, WAIT_WARP, WAIT_NAMED, DONE };
 struct Fiber {
     void* sp = nullptr;
     char* stack = nullptr;
     State st = RUNNABLE;
     emu_uint3 tid;
     int lin = 0;
+    int bar_id = 0;
 };
 constexpr size_t kStack = 512 * 1024;
 std::vector<Fiber> fibers;
 Fiber* cur = nullptr;
 void* sched_sp = nullptr;
 const std::function<void()>* body_fn = nullptr;
+int named_cnt[16];     // arrivals at the named barriers (bar.sync / bar.arrive id, count)
 double xbuf[64][32];  // per-warp exchange
 int xpred[64][32];
 
@@ -76,6 +78,20 @@ int lane_id() { return cur->lin & 31; }
 void sync_block() { cur->st = WAIT_BLOCK; yield_to_sched(); }
 void sync_warp() { cur->st = WAIT_WARP; yield_to_sched(); }
 
+// named barriers: the barrier completes when `count` threads have arrived (bar_sync blocks, bar_arrive does not)
+static void named_release(int id) {
+    named_cnt[id] = 0;
+    for (auto& f : fibers) if (f.st == WAIT_NAMED && f.bar_id == id) f.st = RUNNABLE;
+}
+void bar_arrive(int id, int count) {
+    if (++named_cnt[id] >= count) named_release(id);
+}
+void bar_sync(int id, int count) {
+    if (++named_cnt[id] >= count) { named_release(id); return; }
+    cur->st = WAIT_NAMED; cur->bar_id = id;
+    yield_to_sched();
+}
+
 double shfl_exchange(double v, int src_lane) {
     int w = cur->lin >> 5, l = cur->lin & 31;
     xbuf[w][l] = v;
@@ -113,6 +129,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
     for (unsigned bx = 0; bx < grid.x; bx++) {
         std::memset(dyn_smem, 0xCD, smem_bytes);  // poison: uninitialised shared memory reads show up as garbage
         blockIdx = {bx, by, bz};
+        for (int& c : named_cnt) c = 0;
         int lin = 0;
         for (unsigned tz = 0; tz < block.z; tz++)
         for (unsigned ty = 0; ty < block.y; ty++)
@@ -154,7 +171,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
             if (!progressed) {
                 std::fprintf(stderr, "emu: DEADLOCK in block (%u,%u,%u): barrier not reached by all threads\n", bx, by, bz);
                 for (int i = 0; i < nthreads; i++)
-                    if (fibers[i].st != DONE) { std::fprintf(stderr, "  thread %d state %d\n", i, (int)fibers[i].st); break; }
+                    if (fibers[i].st != DONE && (i % 32 == 0)) std::fprintf(stderr, "  thread %d state %d named-barrier %d (arrivals %d)\n", i, (int)fibers[i].st, fibers[i].bar_id, named_cnt[fibers[i].bar_id & 15]);
                 std::abort();
             }
         }

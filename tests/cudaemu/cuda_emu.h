@@ -76,6 +76,8 @@ namespace emu {
 void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()>& body);
 void sync_block();
 void sync_warp();
+void bar_sync(int id, int count);     // named barrier (bar.sync id, count)
+void bar_arrive(int id, int count);   // named barrier, non-blocking arrival (bar.arrive id, count)
 double shfl_exchange(double v, int src_lane);   // generic lane exchange within the caller's warp
 unsigned ballot(int pred);
 extern char* dyn_smem;
