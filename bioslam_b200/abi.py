@@ -110,6 +110,14 @@ def dptr(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
+class JointAngleDesc(C.Structure):
+    """b200_joint_angle_desc (include/bioslam_b200.h)"""
+    _fields_ = [("pose_var", C.c_int32 * 5), ("static_var", C.c_int32 * 14)]
+
+
+JOINT_ANGLE_NAMES = [j + "_" + a for j in ("rknee", "lknee", "rhip", "lhip") for a in ("flexEx", "abAd", "intExtRot")]
+
+
 class GraphDesc:
     """Python-side holder of a b200_problem_desc (keeps the numpy buffers alive)."""
 

@@ -8,6 +8,7 @@
 #include <vector>
 #include "kernels_preint.cuh"
 #include "kernels_solve.cuh"
+#include "kernels_jointangles.cuh"
 
 using namespace b200d;
 
@@ -72,7 +73,7 @@ struct b200_problem {
     double *d_D = nullptr, *d_O = nullptr, *d_A = nullptr, *d_S = nullptr;
     SolveBuffers sb{};
     struct HostLevel {
-        int n_nodes = 0, P = 1, c_lo = 0, c_hi = 1;
+        int n_nodes = 0, P = 1, c_lo = 0, c_hi = 1, nsplit = 1;
         std::vector<int> begin, st, sep_st;     // partition over nodes; storage index per node; per separator
         int *d_begin = nullptr, *d_st = nullptr, *d_sep_st = nullptr;
         double *F = nullptr, *S = nullptr, *Dred = nullptr, *Ored = nullptr, *Ared = nullptr, *Sred = nullptr;
@@ -588,14 +589,17 @@ static b200_status set_partition(b200_problem* p, int P1, int P2) {
         CK(cudaMemcpyAsync(l.d_sep_st, l.sep_st.data(), sizeof(int) * l.sep_st.size(), cudaMemcpyHostToDevice, p->stream));
         if (!l.st.empty()) CK(cudaMemcpyAsync(l.d_st, l.st.data(), sizeof(int) * l.st.size(), cudaMemcpyHostToDevice, p->stream));
         CK(cudaStreamSynchronize(p->stream));
-        CK(dalloc(&l.F, (P + 1) * 2 * Fsz)); CK(dalloc(&l.S, (P + 1) * Ssz));
+        // upper levels on one GPU: few chunks, many idle SMs -> several CTAs per chunk sweep (row split, see Level::nsplit)
+        l.nsplit = 1;
+        if (li > 0 && W == 1) { while (l.nsplit < 4 && l.P * (l.nsplit + 1) <= 148) l.nsplit++; }
+        CK(dalloc(&l.F, (P + 1) * l.nsplit * 2 * Fsz)); CK(dalloc(&l.S, (P + 1) * Ssz));
         CK(dalloc(&l.Dred, P * dm.ntp * dm.ntp)); CK(dalloc(&l.Ored, P * dm.nc * dm.nc));
         CK(dalloc(&l.Ared, P * dm.ns1 * dm.ntp)); CK(dalloc(&l.Sred, P * dm.ns1 * dm.ns1));
         Level& d = l.dev;
         if (li == 0) { d.Dsrc = p->d_D; d.Osrc = p->d_O; d.Asrc = p->d_A; d.Ssrc = p->d_S; d.st = nullptr; }
         else { auto& lp = p->levels[li - 1]; d.Dsrc = lp.Dred; d.Osrc = lp.Ored; d.Asrc = lp.Ared; d.Ssrc = lp.Sred; d.st = l.d_st; }
         d.begin = l.d_begin; d.P = l.P; d.F = l.F; d.S = l.S;
-        d.Dred = l.Dred; d.Ored = l.Ored; d.Ared = l.Ared; d.Sred = l.Sred; d.sep_st = l.d_sep_st; d.dense_o = (li > 0);
+        d.Dred = l.Dred; d.Ored = l.Ored; d.Ared = l.Ared; d.Sred = l.Sred; d.sep_st = l.d_sep_st; d.dense_o = (li > 0); d.nsplit = l.nsplit;
     }
     if (nlev == 0) { auto& l = p->levels[0]; l.n_nodes = K; l.P = 1; p->k_lo = 0; p->k_hi = K; }
     {   // top level: a single chunk (no separators) over whatever the levels below left
@@ -607,7 +611,7 @@ static b200_status set_partition(b200_problem* p, int P1, int P2) {
         const int tb[2] = {0, tn};
         CK(cudaMemcpyAsync(p->d_top_begin, tb, sizeof(tb), cudaMemcpyHostToDevice, p->stream));
         CK(cudaStreamSynchronize(p->stream));
-        t.begin = p->d_top_begin; t.P = 1; t.F = p->d_Ftop; t.S = p->d_Stop; t.dense_o = (nlev > 0);
+        t.begin = p->d_top_begin; t.P = 1; t.F = p->d_Ftop; t.S = p->d_Stop; t.dense_o = (nlev > 0); t.nsplit = 1;
     }
     if (W > 1) {
         if (p->d_stageS) cudaFree(p->d_stageS);
@@ -719,7 +723,7 @@ __global__ void pack_groups_kernel(Dims dm, Level lv1, const double* Dred, const
 // one level: sweep (CTA per chunk) + arrow Schur complement (CTA per chunk)
 static void launch_level_factor(b200_problem* p, const Level& lv, int c_lo, int c_hi, double lambda) {
     const Dims& dm = p->dm;
-    B200_LAUNCH(chain_sweep_kernel, dim3(c_hi - c_lo), dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, dm, lv, p->sb, lambda, c_lo);
+    B200_LAUNCH(chain_sweep_kernel, dim3(c_hi - c_lo, lv.nsplit > 0 ? lv.nsplit : 1), dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, dm, lv, p->sb, lambda, c_lo);
     // few chunks (upper levels): split the output tiles of a chunk's Schur complement over several CTAs
     const int nsplit = (c_hi - c_lo) * 2 <= 148 ? 2 : 1;
     B200_LAUNCH(chain_schur_kernel, dim3(c_hi - c_lo, nsplit), dim3(B200_SCHUR_THREADS), p->smem_schur, p->stream, dm, lv, p->sb, c_lo, p->schur_ldy,
@@ -1042,6 +1046,31 @@ b200_status b200_preintegrate(int32_t device, int32_t n_imu, int32_t n_samples, 
 b200_status b200_preintegrate_combined(int32_t device, int32_t n_imu, int32_t n_samples, int32_t n_per, int32_t n_intervals, const double* acc,
                                        const double* gyro, double dt, const double* bias_hat, const b200_imu_noise* noise, double* out) {
     return b200_preintegrate(device, n_imu, n_samples, n_per, n_intervals, acc, gyro, dt, bias_hat, noise, 1, out);
+}
+
+// ------------------------------------------------------------------------------------------ derived joint angles (N1)
+b200_status b200_lower_body_joint_angles(b200_problem* p, const b200_joint_angle_desc* d, double* angles) {
+    if (!p || !d || !angles) return B200_BAD_ARG;
+    CK(cudaSetDevice(p->device));
+    JointAngleArgs ja;
+    for (int i = 0; i < 5; i++) {
+        const int v = d->pose_var[i];
+        if (v < 0 || v >= p->ntv || p->tvtype[v] != B200_VAR_POSE3) { set_err("joint angles: pose_var must name Pose3 time variables"); return B200_BAD_ARG; }
+        ja.pose_off[i] = p->tv_valoff[v];
+    }
+    for (int i = 0; i < 14; i++) {
+        const int v = d->static_var[i];
+        if (v < 0 || v >= p->nsv || (p->svtype[v] != B200_VAR_VEC3 && p->svtype[v] != B200_VAR_UNIT3)) { set_err("joint angles: static_var must name Point3 / Unit3 static variables"); return B200_BAD_ARG; }
+        ja.static_off[i] = p->sv_valoff[v];
+    }
+    const size_t n = (size_t)p->K * 12;
+    if (n > p->stage_doubles) { set_err("internal: staging buffer too small"); return B200_NOT_IMPLEMENTED; }
+    B200_LAUNCH(joint_angles_kernel, dim3((p->K + 127) / 128), dim3(128), 0, p->stream, ja, p->K, p->dm.Kld, p->d_tv, p->d_sv, p->d_stage);
+    p->launches++;
+    CK(cudaMemcpyAsync(angles, p->d_stage, sizeof(double) * n, cudaMemcpyDeviceToHost, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    CK(cudaGetLastError());
+    return B200_OK;
 }
 
 // ------------------------------------------------------------------------------------------ multi-rank plumbing

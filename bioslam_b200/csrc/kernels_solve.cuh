@@ -351,9 +351,13 @@ __device__ int cta_chol_inv(double* Ms, int ld, int n) {
     __shared__ __align__(16) double s_Wd2[2][B200_NB * B200_WLD];
     double *Tdiag, *Wd0, *invd;
     solve_scratch(Tdiag, Wd0, invd);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5, nthr = blockDim.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int ty = lane >> 3, tx = lane & 7;
     const int nb = (n + B200_NB - 1) / B200_NB;
+    // the pivot warp's chain is latency-bound: the warps that share its scheduler (warp & 3 == 0) stay out of the way
+    const bool quiet = false;   // (measured: idling the 3 warps on the pivot scheduler does not pay -- the chain waits on the shared MIO pipe)
+    const int nwk = quiet ? nwarps - (nwarps + 3) / 4 : nwarps - 1;        // worker warps
+    const int nthr = 32 * (nwk + 1);                                       // threads taking part in the named barriers
     if (threadIdx.x == 0) fail = 0;
     __syncthreads();
     PH_T0();
@@ -440,9 +444,9 @@ __device__ int cta_chol_inv(double* Ms, int ld, int n) {
         }
         // consume the last trailing-update barrier so that every named barrier is back to zero arrivals for the next call
         if (nb >= 2 && !fail) named_bar_sync(5 + ((nb - 2) & 1), nthr);
-    } else {
+    } else if (!quiet || (warp & 3) != 0) {
         // ------------------------------------------------------------------ worker warps
-        const int wk = warp - 1, nwk = nwarps - 1;
+        const int wk = quiet ? warp - 1 - (warp >> 2) : warp - 1;
         for (int s = 0; s < nb; s++) {
             const int j0 = s * B200_NB, cb0 = j0 + B200_NB;
             const int jb = (n - j0 < B200_NB) ? (n - j0) : B200_NB;
@@ -632,6 +636,8 @@ struct SweepArgs {
     double* Sacc;        // [hmax*hmax] (lower triangle) Schur complement of this sweep (chain_schur_kernel)
     int* status;
     int dense_o;         // the coupling blocks are dense (reduced systems of the upper levels), else block-sparse (dm.orow)
+    int ar_lo, ar_hi;    // arrow rows handled by this CTA (row split of a chunk over several CTAs on the upper levels)
+    int lead;            // this CTA stores the shared results (W) of the chunk
 };
 
 // shared-memory carve-up of the sweep (doubles): Ms [ntp*ld] | Yb [cr*ld] | Op [max(nc*owp, 2*nc*OSLD)]
@@ -665,7 +671,6 @@ __device__ __forceinline__ void xrow_range(const Dims& dm, const int* orow, bool
 
 __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
     const int n = dm.ntp, nl = dm.nl, nc = dm.nc, ns1 = dm.ns1, ld = dm.ld, hmax = dm.hmax, CR = dm.cr, ow = dm.ow, owp = dm.owp;
-    const int h = a.h;
     const long long Fsz = (long long)(nc + hmax) * nc;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int ty = lane >> 3, tx = lane & 7;
@@ -753,13 +758,13 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
             for (int c = 2 * lane; c < n; c += 64) {
                 double2 v = ld2(Ms + (long long)r * ld + c);
                 if (c < r) { v.x = 0.0; if (c + 1 < r) v.y = 0.0; st2(Ms + (long long)r * ld + c, v.x, v.y); }
-                st2(Wg + (long long)r * n + c, v.x, v.y);
+                if (a.lead) st2(Wg + (long long)r * n + c, v.x, v.y);
             }
         PH_ADD(2);
         // ---------------- phase B: panel rows [X (nc, if has_x) ; arrow (h)] in chunks of <= CR rows
         const int xo = has_x ? nc : 0;
         for (int seg = 0; seg < 2; seg++) {
-            const int base = seg == 0 ? 0 : xo, cnt = seg == 0 ? xo : h;
+            const int base = seg == 0 ? 0 : xo + a.ar_lo, cnt = seg == 0 ? xo : a.ar_hi - a.ar_lo;
             if (cnt == 0) continue;
             const int nch = (cnt + CR - 1) / CR;
             int csz = (cnt + nch - 1) / nch;
@@ -1100,6 +1105,8 @@ struct Level {
     double *Dred, *Ored, *Ared, *Sred;        // [P-1] reduced sources == next level's node sources
     int* sep_st;                              // [P-1] storage index of separator c == next level's st
     int dense_o;                              // coupling blocks of this level are dense (reduced systems)
+    int nsplit;                               // CTAs per chunk sweep: each one factorises the pivot blocks and processes the rows
+                                              // of O (redundantly, bit-identical) plus its share of the arrow rows; F is [P][nsplit][2][..]
 };
 
 struct SolveBuffers {
@@ -1110,7 +1117,11 @@ struct SolveBuffers {
     int* status;
 };
 
-__device__ __forceinline__ void level_chunk_args(const Dims& dm, const Level& lv, const SolveBuffers& sb, int c, SweepArgs& a) {
+// arrow rows [lo, hi) of split y out of ns (h rows in total)
+__device__ __forceinline__ int split_lo(int h, int ns, int y) { return (int)((long long)y * h / ns); }
+__device__ __forceinline__ int split_owner(int h, int ns, int row) { int y = 0; while (y + 1 < ns && split_lo(h, ns, y + 1) <= row) y++; return y; }
+
+__device__ __forceinline__ void level_chunk_args(const Dims& dm, const Level& lv, const SolveBuffers& sb, int c, SweepArgs& a, int y = 0) {
     const int kb = lv.begin[c], ke = lv.begin[c + 1];
     a.Dsrc = lv.Dsrc; a.Osrc = lv.Osrc; a.Asrc = lv.Asrc; a.Ssrc = lv.Ssrc;
     a.src0 = kb;
@@ -1120,7 +1131,10 @@ __device__ __forceinline__ void level_chunk_args(const Dims& dm, const Level& lv
     a.Oleft = (c > 0) ? lv.Osrc + (long long)(kb - 1) * dm.nc * dm.nc : nullptr;
     a.h = dm.ns1 + ((c > 0) ? dm.nc : 0);
     a.Wst = sb.Wst; a.Yst = sb.Yst;
-    a.F = lv.F + (long long)c * 2 * (dm.nc + dm.hmax) * dm.nc;
+    const int ns = lv.nsplit > 0 ? lv.nsplit : 1;
+    a.F = lv.F + ((long long)c * ns + y) * 2 * (dm.nc + dm.hmax) * dm.nc;
+    a.ar_lo = split_lo(a.h, ns, y); a.ar_hi = (y + 1 < ns) ? split_lo(a.h, ns, y + 1) : a.h;
+    a.lead = (y == 0);
     a.Sacc = lv.S + (long long)c * dm.hmax * dm.hmax;
     a.status = sb.status;
     a.lambda = 0.0;
@@ -1131,7 +1145,7 @@ __device__ __forceinline__ void level_chunk_args(const Dims& dm, const Level& lv
 __global__ void __launch_bounds__(B200_SOLVE_THREADS) chain_sweep_kernel(Dims dm, Level lv, SolveBuffers sb, double lambda, int c_first) {
     B200_DYN_SMEM(double, sm);
     SweepArgs a;
-    level_chunk_args(dm, lv, sb, c_first + blockIdx.x, a);
+    level_chunk_args(dm, lv, sb, c_first + blockIdx.x, a, blockIdx.y);
     a.lambda = lambda;
     cta_sweep(dm, a, sm);
 }
@@ -1221,7 +1235,10 @@ __global__ void __launch_bounds__(256) chain_reduce_kernel(Dims dm, Level lv, in
     const long long q = lv.begin[c + 1] - 1;                 // node index of the separator
     const long long Fsz = (long long)(nc + hmax) * nc;
     const int n_c = (int)(q - lv.begin[c]);                  // interior nodes of chunk c
-    const double* Fc = lv.F + ((long long)c * 2 + (n_c & 1)) * Fsz;   // written by its last node
+    const int nsp = lv.nsplit > 0 ? lv.nsplit : 1;
+    // fill buffers: rows of O from split 0, arrow row a from the split that owns it
+    const double* Fc = lv.F + ((long long)c * nsp * 2 + (n_c & 1)) * Fsz;   // written by its last node (split 0)
+    const int h_c = ns1 + (c > 0 ? nc : 0), h_n = ns1 + nc;
     const double* Sn = lv.S + (long long)(c + 1) * hmax * hmax;        // chunk c+1 (has left rows)
     if (threadIdx.x == 0 && blockIdx.y == 0) lv.sep_st[c] = lv.st ? lv.st[q] : (int)q;
     double* Dr = lv.Dred + (long long)c * ntp * ntp;
@@ -1234,7 +1251,7 @@ __global__ void __launch_bounds__(256) chain_reduce_kernel(Dims dm, Level lv, in
     // coupling separator c -> separator c+1 through chunk c+1: -(fill of the left rows) of that chunk's last node
     const bool has_o = c < P - 2;
     const int n_n = has_o ? (int)(lv.begin[c + 2] - 1 - lv.begin[c + 1]) : 0;
-    const double* Fn = lv.F + ((long long)(c + 1) * 2 + (n_n & 1)) * Fsz;
+    const double* Fn = lv.F + ((long long)(c + 1) * nsp * 2 + (n_n & 1)) * Fsz;
     double* Or = lv.Ored + (long long)c * nc * nc;
     const int e1 = ntp * ntp, e2 = e1 + ns1 * ntp, e3 = e2 + ns1 * ns1, e4 = e3 + (has_o ? nc * nc : 0);
     for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < e4; e += blockDim.x * gridDim.y) {
@@ -1252,7 +1269,7 @@ __global__ void __launch_bounds__(256) chain_reduce_kernel(Dims dm, Level lv, in
             const int f = e - e1, ar = f / ntp, col = f % ntp;
             double v = Ag[f];
             if (col >= nl) {
-                if (n_c > 0) v -= Fc[(long long)(nc + ar) * nc + (col - nl)];
+                if (n_c > 0) v -= Fc[(long long)split_owner(h_c, nsp, ar) * 2 * Fsz + (long long)(nc + ar) * nc + (col - nl)];
                 v += Sn[(long long)(ns1 + (col - nl)) * hmax + ar];
             }
             Ar[f] = v;
@@ -1264,7 +1281,7 @@ __global__ void __launch_bounds__(256) chain_reduce_kernel(Dims dm, Level lv, in
             Sr[f] = v;
         } else {
             const int f = e - e3, i = f / nc, j = f % nc;   // Or[j][i]: row = chain j of separator c+1, col = chain i of separator c
-            Or[(long long)j * nc + i] = -Fn[(long long)(nc + ns1 + i) * nc + j];
+            Or[(long long)j * nc + i] = -Fn[(long long)split_owner(h_n, nsp, ns1 + i) * 2 * Fsz + (long long)(nc + ns1 + i) * nc + j];
         }
     }
 }

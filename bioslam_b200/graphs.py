@@ -134,6 +134,23 @@ def lower_body_graph(trial, n_per=10, preint=None, use_joint_vel=False):
     return g, tv, sv
 
 
+JOINT_ANGLE_POSE_IMUS = (0, 1, 2, 4, 5)   # sacrum, right thigh, right shank, left thigh, left shank (IMU order of lower_body_graph)
+JOINT_ANGLE_STATICS = ["sacrumImuToRHipCtr", "sacrumImuToLHipCtr", "rkneeAxisThigh", "rthighImuToHipCtr", "rthighImuToKneeCtr",
+                       "rkneeAxisShank", "rshankImuToKneeCtr", "rshankImuToAnkleCtr", "lkneeAxisThigh", "lthighImuToHipCtr",
+                       "lthighImuToKneeCtr", "lkneeAxisShank", "lshankImuToKneeCtr", "lshankImuToAnkleCtr"]
+
+
+def lower_body_joint_angle_desc():
+    """variable indices of lower_body_graph() for b200_lower_body_joint_angles (reference src/lowerBodyPoseEstimator.cpp:813-835)"""
+    sidx = {n: i for i, n in enumerate(STATIC_POINTS + STATIC_AXES)}
+    d = abi.JointAngleDesc()
+    for j, i in enumerate(JOINT_ANGLE_POSE_IMUS):
+        d.pose_var[j] = 3 * i
+    for j, n in enumerate(JOINT_ANGLE_STATICS):
+        d.static_var[j] = sidx[n]
+    return d
+
+
 def single_imu_graph(acc, gyro, dt, n_per=10, static_bias=False, preint=None, init_R=None, ref_local=(0.0, 1.0, 0.0)):
     """imuPoseEstimator graph for one IMU (acc, gyro [N][3]) with position / velocity / bias / compass priors
     (examples/exampleImuPoseEstimation.cpp:21-39).  Returns (GraphDesc, tv, sv)."""

@@ -257,6 +257,22 @@ b200_status b200_preintegrate(int32_t device, int32_t n_imu, int32_t n_samples, 
                               const double* acc, const double* gyro, double dt, const double* bias_hat,
                               const b200_imu_noise* noise, int32_t combined, double* out);
 
+/* ---------------------------------------------------------------- derived joint angles
+ * == lowerBodyPoseEstimator::setDerivedJointAnglesFromEstimatedStates (reference src/lowerBodyPoseEstimator.cpp:813-835):
+ * segment frames from the estimated static vectors / axes (bioutils::get_R_SacrumImu_to_Pelvis, get_R_Segment_to_N,
+ * reference src/bioutils.cpp:12-115) and clinical Grood-Suntay angles (bioutils::clinical3DofJcsAngles, :117-237), computed
+ * on the device from the problem's CURRENT values, one thread per keyframe.
+ * pose_var: time-variable indices of the Pose3 of the sacrum, right thigh, right shank, left thigh, left shank IMU.
+ * static_var: static-variable indices of sacrumImuToRHipCtr, sacrumImuToLHipCtr, rkneeAxisThigh, rthighImuToHipCtr,
+ *   rthighImuToKneeCtr, rkneeAxisShank, rshankImuToKneeCtr, rshankImuToAnkleCtr, lkneeAxisThigh, lthighImuToHipCtr,
+ *   lthighImuToKneeCtr, lkneeAxisShank, lshankImuToKneeCtr, lshankImuToAnkleCtr.
+ * angles: [K][12] = right knee, left knee, right hip, left hip x (flexion/extension, ab/adduction, int/ext rotation), rad. */
+typedef struct b200_joint_angle_desc {
+    int32_t pose_var[5];
+    int32_t static_var[14];
+} b200_joint_angle_desc;
+b200_status b200_lower_body_joint_angles(b200_problem* p, const b200_joint_angle_desc* d, double* angles);
+
 /* ---------------------------------------------------------------- solver partition
  * The time chain is cut into n_chunks contiguous windows that are eliminated in parallel (one CTA each) and joined through
  * a reduced system on the separator keyframes.  Default: ~sqrt(2.2 K), at most one per SM; 1 = plain sequential sweep. */

@@ -22,6 +22,7 @@
 #endif
 #include "factors.hpp"
 #include "preint.hpp"
+#include "jointangles.hpp"
 
 using namespace orc;
 
@@ -531,6 +532,19 @@ void orc_retract_var(int vartype, const double* x, const double* d, double* out)
 void orc_unit3_basis(const double* p, double* B) { unit3_basis(B, p); }
 void orc_so3_expmap(const double* w, double* R) { so3_expmap(R, w); }
 void orc_so3_logmap(const double* R, double* w) { so3_logmap(w, R); }
+
+// derived joint angles (jointangles.hpp)
+void orc_R_imu_to_segment(const double* right_axis, const double* to_prox, const double* to_dist, int prox_is_master, double* R) {
+    R_imu_to_segment(right_axis, to_prox, to_dist, prox_is_master != 0, R);
+}
+void orc_R_sacrum_to_pelvis(const double* up, const double* to_rhip, const double* to_lhip, int hip_is_master, double* R) {
+    R_sacrum_to_pelvis(up, to_rhip, to_lhip, hip_is_master != 0, R);
+}
+void orc_R_segment_to_N(const double* R_imu_to_N, const double* R_imu_to_seg, double* R) { R_segment_to_N(R_imu_to_N, R_imu_to_seg, R); }
+void orc_jcs_angles(const double* Rp, const double* Rd, int clinical, int right_leg, double* ang) {
+    if (clinical) clinical_jcs_angles(Rp, Rd, right_leg != 0, ang); else consistent_jcs_angles(Rp, Rd, ang);
+}
+void orc_lower_body_joint_angles(int K, const double* R_imu, const double* statics, double* out) { lower_body_joint_angles(K, R_imu, statics, out); }
 
 int orc_preintegrate(int n_imu, int n_samples, int n_per, int n_intervals, const double* acc, const double* gyro, double dt,
                      const double* bias_hat, const b200_imu_noise* noise, int combined, double* out) {

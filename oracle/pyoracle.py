@@ -146,3 +146,43 @@ def preintegrate(acc, gyro, dt, n_per, bias_hat, noise=None, combined=True):
                                 D(bh), C.byref(noise), C.c_int(1 if combined else 0), D(out))
     assert st == 0, st
     return out
+
+
+# ---- derived joint angles (oracle/jointangles.hpp)
+def R_imu_to_segment(right_axis, to_prox, to_dist, prox_is_master=True):
+    R = np.zeros(9)
+    a = [np.ascontiguousarray(v, dtype=np.float64) for v in (right_axis, to_prox, to_dist)]
+    lib().orc_R_imu_to_segment(D(a[0]), D(a[1]), D(a[2]), C.c_int(1 if prox_is_master else 0), D(R))
+    return R.reshape(3, 3)
+
+
+def R_sacrum_to_pelvis(up, to_rhip, to_lhip, hip_is_master=True):
+    R = np.zeros(9)
+    a = [np.ascontiguousarray(v, dtype=np.float64) for v in (up, to_rhip, to_lhip)]
+    lib().orc_R_sacrum_to_pelvis(D(a[0]), D(a[1]), D(a[2]), C.c_int(1 if hip_is_master else 0), D(R))
+    return R.reshape(3, 3)
+
+
+def R_segment_to_N(R_imu_to_N, R_imu_to_seg):
+    R = np.zeros(9)
+    lib().orc_R_segment_to_N(D(np.ascontiguousarray(R_imu_to_N, dtype=np.float64).ravel()), D(np.ascontiguousarray(R_imu_to_seg, dtype=np.float64).ravel()), D(R))
+    return R.reshape(3, 3)
+
+
+def jcs_angles(R_prox_to_N, R_dist_to_N, clinical=False, right_leg=True):
+    """[flexEx, abAd, intExtRot] (rad): bioutils::consistent3DofJcsAngles / clinical3DofJcsAngles"""
+    ang = np.zeros(3)
+    lib().orc_jcs_angles(D(np.ascontiguousarray(R_prox_to_N, dtype=np.float64).ravel()), D(np.ascontiguousarray(R_dist_to_N, dtype=np.float64).ravel()),
+                         C.c_int(1 if clinical else 0), C.c_int(1 if right_leg else 0), D(ang))
+    return ang
+
+
+def lower_body_joint_angles(g, tv, sv, desc):
+    """[K][12] from value arrays in GraphDesc layout (same descriptor as b200_lower_body_joint_angles)"""
+    toff, soff = g.time_value_offsets(), g.static_value_offsets()
+    K = tv.shape[0]
+    R = np.ascontiguousarray(np.stack([tv[:, toff[desc.pose_var[i]]:toff[desc.pose_var[i]] + 9] for i in range(5)]), dtype=np.float64)
+    st = np.ascontiguousarray(np.concatenate([sv[soff[desc.static_var[i]]:soff[desc.static_var[i]] + 3] for i in range(14)]), dtype=np.float64)
+    out = np.zeros((K, 12))
+    lib().orc_lower_body_joint_angles(C.c_int(K), D(R), D(st), D(out))
+    return out
