@@ -209,6 +209,18 @@ def run_b200(args):
     h2d = tv.nbytes + sv.nbytes
     d2h = tv.nbytes + sv.nbytes + 8 * 10
 
+    # ---------------- time-to-converge (BASELINE.json metric, second half): the reference's own exit rule (6 consecutive
+    # small iterations, src/lowerBodyPoseEstimator.cpp:656-663) from the reference's initial values, device-timed
+    ttc = None
+    if args.converge_max > 0:
+        p.set_values(tv0, sv0)
+        barrier()
+        res, hist = p.optimize(lm, abi.OuterParams.lower_body(max_iterations=args.converge_max))
+        barrier()
+        ttc = {"seconds": res.device_ms * 1e-3, "iterations": int(res.iterations), "lambda_trials": int(res.total_trials),
+               "initial_error": float(res.initial_error), "final_error": float(res.final_error),
+               "converged": bool(res.iterations < args.converge_max), "rule": "6 consecutive iterations with abs<1e-6 or rel<1e-5 decrease"}
+
     if rank != 0:
         return
     peak, peak_src = measured_peaks()
@@ -218,10 +230,10 @@ def run_b200(args):
     if ph[4] > 0:
         achieved = units * SWEEP_BYTES_PER_KEYFRAME / (sweep_ms * 1e-3) / 1e9
         kern = "chain_sweep_kernel"
-    else:  # single chunk: everything happens in top_solve_kernel
+    else:  # single chunk: the top-level sweep (+ its Schur / finish kernels) does everything
         sweep_ms = ph[5] / max(ph[6], 1)
         achieved = K * SWEEP_BYTES_PER_KEYFRAME / (sweep_ms * 1e-3) / 1e9
-        kern = "top_solve_kernel"
+        kern = "chain_sweep_kernel (top level)"
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "sweep_traffic.json")
     if os.path.exists(tpath):
@@ -231,16 +243,19 @@ def run_b200(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": args.workload, "baseline_config": WORKLOADS[args.workload][1], "keyframes": K, "unknowns": 126 * K + 58,
-                   "chunks": P, "cache": "working set (>2 GB of Hessian/factor blocks at K=6000) exceeds the 126 MB L2; no flush needed",
+                   "chunks": P, "partition_levels": p.levels, "cache": "working set (>2 GB of Hessian/factor blocks at K=6000) exceeds the 126 MB L2; no flush needed",
                    "init": "reference initial values (identity poses, zero vel/bias, statics at prior means)"},
         "lm_trials_per_sec": trials / (ms * 1e-3), "lambda_trials": trials, "error_after": err_after,
         "phase_ms_per_step": {"linearize+assemble": ph[0] / args.steps, "solve": ph[1] / args.steps, "model+retract+error": ph[2] / args.steps},
         "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "launch_ms": sweep_ms,
-                     "note": "algorithmic bytes = (H 4167 + F 28539 doubles) per keyframe x keyframes per launch; the kernel is fp64-latency bound, not HBM bound"},
+                     "note": "algorithmic bytes = (H 4167 + F 28539 doubles) per keyframe x keyframes per launch (SURVEY 8(d)); the kernel is bound by "
+                             "shared-memory wavefronts / the fp64 pipe and its sequential pivot chain, not by HBM (profiles/)"},
         "e2e": {"value": args.steps / e2e_s, "unit": "iter/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    if ttc is not None:
+        line["time_to_converge"] = ttc
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, K)
     print(json.dumps(line), flush=True)
@@ -257,6 +272,7 @@ def main():
     ap.add_argument("--ref-keyframes", type=int, default=600, help="window of the trial the CPU reference arm runs per step")
     ap.add_argument("--cpu-keyframes", type=int, default=600, help="window for the cpu_baseline sample of the default line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--converge-max", type=int, default=400, help="iteration cap of the time-to-converge run (0: skip it)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -22,7 +22,7 @@ def _L(so_path=None):
         L.b200h_lbpe_create.argtypes = [C.POINTER(C.c_void_p), C.c_char_p]
         L.b200h_lbpe_desc.restype = C.POINTER(abi.ProblemDesc)
         for f in ("b200h_imu_destroy", "b200h_ipe_destroy", "b200h_lbpe_destroy", "b200h_ipe_setup", "b200h_ipe_set_optimized_to_initial",
-                  "b200h_ipe_fast_optimize", "b200h_ipe_n_keyframes", "b200h_lbpe_setup", "b200h_lbpe_fast_optimize", "b200h_lbpe_desc"):
+                  "b200h_ipe_fast_optimize", "b200h_ipe_n_keyframes", "b200h_lbpe_setup", "b200h_lbpe_fast_optimize", "b200h_lbpe_set_joint_angles", "b200h_lbpe_desc"):
             getattr(L, f).argtypes = [C.c_void_p]
         for f in ("b200h_ipe_set", "b200h_lbpe_set"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.c_int]
@@ -104,6 +104,7 @@ class LowerBodyPoseEstimator(_Settable):
 
     def setup(self): _ck(self.L, self.L.b200h_lbpe_setup(self.h)); return self
     def fastOptimize(self): _ck(self.L, self.L.b200h_lbpe_fast_optimize(self.h)); return self
+    def setDerivedJointAnglesFromEstimatedStates(self): _ck(self.L, self.L.b200h_lbpe_set_joint_angles(self.h)); return self
 
     def graph(self):
         """deep copy of the flat description setup() produced + its current values"""

@@ -118,6 +118,7 @@ int b200h_lbpe_set(void* pv, const char* name, const double* v, int n) {
 }
 int b200h_lbpe_setup(void* p) { GUARD(((lowerBodyPoseEstimator*)p)->setup()); }
 int b200h_lbpe_fast_optimize(void* p) { GUARD(((lowerBodyPoseEstimator*)p)->fastOptimize()); }
+int b200h_lbpe_set_joint_angles(void* p) { GUARD(((lowerBodyPoseEstimator*)p)->setDerivedJointAnglesFromEstimatedStates()); }
 // the flat description setup() produced (valid until the estimator is destroyed) and its current values
 const b200_problem_desc* b200h_lbpe_desc(void* p) { auto& e = *(lowerBodyPoseEstimator*)p; return e.isSetup() ? &e.graph().desc() : nullptr; }
 int b200h_lbpe_values(void* pv, double* tv, double* sv) {
@@ -139,6 +140,13 @@ int b200h_lbpe_get(void* pv, const char* name, double* out, int cap) {
     const std::string s(name);
     if (s == "m_optimizationTotalError") return copyOut(p.m_optimizationTotalError, out, cap);
     if (s == "m_time") return copyOut(p.m_time, out, cap);
+    const std::map<std::string, const std::vector<double>*> angs = {{"m_rkneeFlexExAng", &p.m_rkneeFlexExAng}, {"m_rkneeAbAdAng", &p.m_rkneeAbAdAng},
+        {"m_rkneeIntExtRotAng", &p.m_rkneeIntExtRotAng}, {"m_lkneeFlexExAng", &p.m_lkneeFlexExAng}, {"m_lkneeAbAdAng", &p.m_lkneeAbAdAng},
+        {"m_lkneeIntExtRotAng", &p.m_lkneeIntExtRotAng}, {"m_rhipFlexExAng", &p.m_rhipFlexExAng}, {"m_rhipAbAdAng", &p.m_rhipAbAdAng},
+        {"m_rhipIntExtRotAng", &p.m_rhipIntExtRotAng}, {"m_lhipFlexExAng", &p.m_lhipFlexExAng}, {"m_lhipAbAdAng", &p.m_lhipAbAdAng},
+        {"m_lhipIntExtRotAng", &p.m_lhipIntExtRotAng}};
+    auto ig = angs.find(s);
+    if (ig != angs.end()) return copyOut(*ig->second, out, cap);
     const std::map<std::string, const std::vector<Pose3>*> poses = {{"m_sacrumImuPose", &p.m_sacrumImuPose}, {"m_rthighImuPose", &p.m_rthighImuPose},
         {"m_rshankImuPose", &p.m_rshankImuPose}, {"m_rfootImuPose", &p.m_rfootImuPose}, {"m_lthighImuPose", &p.m_lthighImuPose},
         {"m_lshankImuPose", &p.m_lshankImuPose}, {"m_lfootImuPose", &p.m_lfootImuPose}};

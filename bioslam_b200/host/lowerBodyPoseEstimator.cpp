@@ -1,4 +1,5 @@
 // see lowerBodyPoseEstimator.h.  IMU order everywhere: sacrum, rthigh, rshank, rfoot, lthigh, lshank, lfoot.
+#include <cstdio>
 #include "lowerBodyPoseEstimator.h"
 #include <chrono>
 #include <iostream>
@@ -185,6 +186,32 @@ void lowerBodyPoseEstimator::setMemberEstimatedStatesFromValues() {
                        &m_rankleAxisShank, &m_lankleAxisShank, &m_rankleAxisFoot, &m_lankleAxisFoot};
     for (int s = 0; s < 12; s++) { const double* v = gb.staticValue(m_staticVar[s]); *pts[s] = Point3(v[0], v[1], v[2]); }
     for (int a = 0; a < 11; a++) { const double* v = gb.staticValue(m_staticVar[12 + a]); axes[a]->p[0] = v[0]; axes[a]->p[1] = v[1]; axes[a]->p[2] = v[2]; }
+}
+
+// reference src/lowerBodyPoseEstimator.cpp:813-835 (segment frames + clinical Grood-Suntay angles: b200_lower_body_joint_angles)
+void lowerBodyPoseEstimator::setDerivedJointAnglesFromEstimatedStates(bool verbose) {
+    if (!m_gb) throw std::runtime_error("setup() must be called first");
+    GraphBuilder& gb = *m_gb;
+    b200_joint_angle_desc d{};
+    const int imus[5] = {0, 1, 2, 4, 5};                                  // sacrum, rthigh, rshank, lthigh, lshank
+    for (int i = 0; i < 5; i++) d.pose_var[i] = m_imuVars[imus[i]].pose;
+    // m_staticVar: 12 IMU-to-joint-centre vectors then 11 axes, in the order of setMemberEstimatedStatesFromValues()
+    const int st[14] = {0, 1, 12 + 0, 3, 2, 12 + 1, 4, 5, 12 + 2, 8, 7, 12 + 3, 9, 10};
+    for (int i = 0; i < 14; i++) d.static_var[i] = m_staticVar[st[i]];
+    b200_problem* prob = nullptr;
+    if (b200_problem_create(&gb.desc(), getDevice(), &prob) != B200_OK) throw std::runtime_error(std::string("b200_problem_create: ") + b200_last_error());
+    std::vector<double> ang((size_t)gb.K() * 12);
+    b200_status stt = b200_set_values(prob, gb.timeValues().data(), gb.staticValues().data());
+    if (stt == B200_OK) stt = b200_lower_body_joint_angles(prob, &d, ang.data());
+    b200_problem_destroy(prob);
+    if (stt != B200_OK) throw std::runtime_error(std::string("b200_lower_body_joint_angles: ") + b200_last_error());
+    std::vector<double>* out[12] = {&m_rkneeFlexExAng, &m_rkneeAbAdAng, &m_rkneeIntExtRotAng, &m_lkneeFlexExAng, &m_lkneeAbAdAng, &m_lkneeIntExtRotAng,
+                                    &m_rhipFlexExAng, &m_rhipAbAdAng, &m_rhipIntExtRotAng, &m_lhipFlexExAng, &m_lhipAbAdAng, &m_lhipIntExtRotAng};
+    for (int a = 0; a < 12; a++) {
+        out[a]->resize(gb.K());
+        for (int k = 0; k < gb.K(); k++) (*out[a])[k] = ang[(size_t)k * 12 + a];
+    }
+    if (verbose) std::printf("joint angles set for %d keyframes\n", gb.K());
 }
 
 }  // namespace bioslam_b200

@@ -75,6 +75,9 @@ class lowerBodyPoseEstimator {
     std::vector<double> m_time;
     std::vector<Vector3> m_sacrumImuAngVel, m_rthighImuAngVel, m_rshankImuAngVel, m_rfootImuAngVel, m_lthighImuAngVel, m_lshankImuAngVel, m_lfootImuAngVel;
     std::vector<double> m_optimizationTotalError, m_optimizationTotalTime;
+    // derived joint angles, radians (reference include/lowerBodyPoseEstimator.h:133-137)
+    std::vector<double> m_rkneeFlexExAng, m_rkneeIntExtRotAng, m_rkneeAbAdAng, m_lkneeFlexExAng, m_lkneeIntExtRotAng, m_lkneeAbAdAng;
+    std::vector<double> m_rhipFlexExAng, m_rhipIntExtRotAng, m_rhipAbAdAng, m_lhipFlexExAng, m_lhipIntExtRotAng, m_lhipAbAdAng;
 
     explicit lowerBodyPoseEstimator(const imuPoseEstimator& sacrumImuPoseProblem, const imuPoseEstimator& rthighImuPoseProblem,
                                     const imuPoseEstimator& rshankImuPoseProblem, const imuPoseEstimator& rfootImuPoseProblem,
@@ -84,6 +87,8 @@ class lowerBodyPoseEstimator {
     void setup();
     void fastOptimize(double prevGlobalErr = 9e9);
     void setMemberEstimatedStatesFromValues();
+    // == reference src/lowerBodyPoseEstimator.cpp:813-835; runs b200_lower_body_joint_angles on the device
+    void setDerivedJointAnglesFromEstimatedStates(bool verbose = false);
     // the flat description setup() produced and its current values (== m_graph / m_initialValues of the reference)
     const GraphBuilder& graph() const { return *m_gb; }
     GraphBuilder& graph() { return *m_gb; }

@@ -80,6 +80,11 @@ def test_host_fast_optimize_matches_c_abi():
     off = g.time_value_offsets()
     assert np.array_equal(pose, tvo[:, off[3]:off[3] + 12])
     assert np.allclose(np.linalg.norm(lb.get("m_rkneeAxisThigh")), 1.0)
+    # derived joint angles through the host class == the C ABI call on the same values
+    lb.setDerivedJointAnglesFromEstimatedStates()
+    ja = p.joint_angles(graphs.lower_body_joint_angle_desc())
+    assert np.array_equal(lb.get("m_rkneeFlexExAng"), ja[:, 0]) and np.array_equal(lb.get("m_lhipIntExtRotAng"), ja[:, 11])
+    assert np.array_equal(lb.get("m_rhipAbAdAng"), ja[:, 7])
 
 
 @pytest.mark.gpu
