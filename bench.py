@@ -272,7 +272,7 @@ def main():
     ap.add_argument("--ref-keyframes", type=int, default=600, help="window of the trial the CPU reference arm runs per step")
     ap.add_argument("--cpu-keyframes", type=int, default=600, help="window for the cpu_baseline sample of the default line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--converge-max", type=int, default=400, help="iteration cap of the time-to-converge run (0: skip it)")
+    ap.add_argument("--converge-max", type=int, default=3000, help="iteration cap of the time-to-converge run (0: skip it)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
