@@ -326,7 +326,7 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
     CK(cudaMemsetAsync(p->d_D, 0, sizeof(double) * K * dm.ntp * dm.ntp, p->stream)); CK(cudaMemsetAsync(p->d_O, 0, sizeof(double) * K * dm.nc * dm.nc, p->stream));
     CK(cudaMemsetAsync(p->d_A, 0, sizeof(double) * K * dm.ns1 * dm.ntp, p->stream)); CK(cudaMemsetAsync(p->d_S, 0, sizeof(double) * K * dm.ns1 * dm.ns1, p->stream));
     CK(dalloc(&p->sb.Wst, K * dm.ntp * dm.ntp)); CK(dalloc(&p->sb.Yst, K * (size_t)dm.hmax * dm.ntp)); CK(dalloc(&p->sb.ybuf, K * dm.ntp));
-    CK(dalloc(&p->sb.delta, (K + 1024) * dm.ntp)); CK(dalloc(&p->sb.dstat, (size_t)ns + 1)); CK(dalloc(&p->sb.scal, (size_t)SC_COUNT));
+    CK(dalloc(&p->sb.delta, (K + 1024) * dm.ntp)); CK(dalloc(&p->sb.dstat, (size_t)ns + 1)); CK(dalloc(&p->sb.scal, (size_t)SC_COUNT + 8));   // [SC_COUNT..): rank-local scalars that are NOT all-reduced
     CK(dalloc(&p->sb.status, (size_t)1));
     CK(dalloc(&p->d_Ftop, (size_t)2 * (dm.nc + dm.hmax) * dm.nc)); CK(dalloc(&p->d_Stop, (size_t)dm.hmax * dm.hmax));
     CK(dalloc(&p->d_top_begin, (size_t)2));
@@ -524,15 +524,22 @@ static b200_status set_partition(b200_problem* p, int P1, int P2) {
         }
         P2 = bp2;
     }
-    if (W > 1) { P2 = std::max(P2, W); P2 = (P2 + W - 1) / W * W; while (P2 > W && (P1 / W) / (P2 / W) < 3) P2 -= W; if ((P1 / W) / (P2 / W) < 2) { set_err("partition too fine for this many ranks"); return B200_BAD_ARG; } }
+    if (auto_groups && P1 > 3) {   // recursive levels above: take the first level the dynamic programme would choose
+        std::vector<int> tmp;
+        plan_upper_levels(P1 - 1, tmp);
+        P2 = tmp.empty() ? 1 : tmp[0];
+    }
+    if (W > 1) { P2 = std::max(P2, W); P2 = (P2 + W - 1) / W * W; while (P2 > W && (P1 / W - 1) / (P2 / W) < 2) P2 -= W; if ((P1 / W - 1) / (P2 / W) < 2) { set_err("partition too fine for this many ranks"); return B200_BAD_ARG; } }
     else { if (P1 < 4) P2 = 1; while (P2 > 1 && (P1 - 1) / P2 < 2) P2--; }
     free_levels(p);
     // chunk counts per level: Ps[0] over the K keyframes, Ps[l] over the Ps[l-1]-1 separators of the level below
     std::vector<int> Ps;
     if (P1 > 1) {
         Ps.push_back(P1);
-        if (W > 1 || !auto_groups) { if (P2 > 1) Ps.push_back(P2); }
-        else plan_upper_levels(P1 - 1, Ps);
+        if (P2 > 1) Ps.push_back(P2);
+        // single rank: all levels from the dynamic programme; sharded: level 1 is rank-aligned (P2 above), the levels above it
+        // are computed redundantly on every rank (their inputs are all-gathered) and recurse the same way
+        if (auto_groups && P2 > 1) plan_upper_levels(P2 - 1, Ps);
     }
     p->P = P1; p->P2 = Ps.size() > 1 ? Ps[1] : 1; P2 = p->P2;
     const int nlev = (int)Ps.size();
@@ -591,7 +598,7 @@ static b200_status set_partition(b200_problem* p, int P1, int P2) {
         CK(cudaStreamSynchronize(p->stream));
         // upper levels on one GPU: few chunks, many idle SMs -> several CTAs per chunk sweep (row split, see Level::nsplit)
         l.nsplit = 1;
-        if (li > 0 && W == 1) { while (l.nsplit < 4 && l.P * (l.nsplit + 1) <= 148) l.nsplit++; }
+        if (li > 0 && (W == 1 || li >= 2)) { while (l.nsplit < 4 && l.P * (l.nsplit + 1) <= 148) l.nsplit++; }
         CK(dalloc(&l.F, (P + 1) * l.nsplit * 2 * Fsz)); CK(dalloc(&l.S, (P + 1) * Ssz));
         CK(dalloc(&l.Dred, P * dm.ntp * dm.ntp)); CK(dalloc(&l.Ored, P * dm.nc * dm.nc));
         CK(dalloc(&l.Ared, P * dm.ns1 * dm.ntp)); CK(dalloc(&l.Sred, P * dm.ns1 * dm.ns1));
@@ -680,7 +687,7 @@ b200_status b200_get_values(b200_problem* p, double* tv, double* sv) {
 static void launch_error(b200_problem* p, const double* tv, const double* sv, double* ebuf, int scal_idx) {
     dim3 grid((p->max_inst + 127) / 128, p->n_slots);
     B200_LAUNCH(linearize_kernel<false>, grid, dim3(128), 0, p->stream, p->d_slots, tv, sv, p->d_cst, p->dm.Kld, (double*)nullptr,
-                (double*)nullptr, ebuf, p->k_lo, p->k_hi);
+                (double*)nullptr, ebuf, p->k_lo, p->k_hi, p->k_lo);
     B200_LAUNCH(reduce_sum_kernel, dim3(1), dim3(1024), 0, p->stream, ebuf, p->ne, p->sb.scal + scal_idx);
     p->launches += 2;
 }
@@ -689,7 +696,7 @@ static void launch_linearize(b200_problem* p) {
     dim3 grid((p->max_inst + 127) / 128, p->n_slots);
     // Jacobians are needed one keyframe to the left of the window (the IMU factor k_lo-1 -> k_lo feeds D[k_lo])
     B200_LAUNCH(linearize_kernel<true>, grid, dim3(128), 0, p->stream, p->d_slots, p->d_tv, p->d_sv, p->d_cst, p->dm.Kld, p->d_J, p->d_r,
-                p->d_e, std::max(p->k_lo - 1, 0), p->k_hi);
+                p->d_e, std::max(p->k_lo - 1, 0), p->k_hi, p->k_lo);
     p->launches++;
     // one extra keyframe on the left: its O block (coupling k_lo-1 -> k_lo) is the left-separator coupling of this window
     const int ka = std::max(p->k_lo - 1, 0);
@@ -854,7 +861,9 @@ b200_status b200_lm_iterate(b200_problem* p, b200_lm_state* state) {
     if (p->time_phases) CK(cudaEventRecord(p->ev[0], p->stream));
     CK(cudaMemsetAsync(p->sb.scal, 0, sizeof(double) * SC_COUNT, p->stream));
     launch_linearize(p);
-    B200_LAUNCH(reduce_sum_kernel, dim3(1), dim3(1024), 0, p->stream, p->d_e, p->ne, p->sb.scal + SC_LIN_ERR);
+    // rank-local linear.error(0); copied into the all-reduced slot at every lambda trial (the all-reduce sums the whole
+    // scalar block, so a value that survives from one trial to the next must not live in it)
+    B200_LAUNCH(reduce_sum_kernel, dim3(1), dim3(1024), 0, p->stream, p->d_e, p->ne, p->sb.scal + SC_COUNT);
     p->launches++;
     if (p->time_phases) CK(cudaEventRecord(p->ev[1], p->stream));
     p->have_lin = true;
@@ -878,6 +887,7 @@ b200_status b200_lm_iterate(b200_problem* p, b200_lm_state* state) {
             p->launches++;
         }
         launch_error(p, p->d_tv_try, p->d_sv_try, p->d_e2, SC_NEW_ERR);
+        CK(cudaMemcpyAsync(p->sb.scal + SC_LIN_ERR, p->sb.scal + SC_COUNT, sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
         st = allreduce_scal(p); if (st != B200_OK) return st;
         if (p->time_phases) CK(cudaEventRecord(p->ev[4], p->stream));
         st = fetch_scalars(p); if (st != B200_OK) return st;
@@ -1165,6 +1175,13 @@ b200_status b200_debug_solve(b200_problem* p, double lambda, double* delta_time,
         for (int i = 0; i < dm.ntp; i++)
             if (p->int2ext[i] >= 0) delta_time[(size_t)k * dm.nt + p->int2ext[i]] = dl[(size_t)k * dm.ntp + i];
     if (dm.ns) CK(cudaMemcpy(delta_static, p->sb.dstat, sizeof(double) * dm.ns, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+// scalars of the last lambda trial: [linear.error(0), linear.error(delta), error(retracted values), -]
+b200_status b200_debug_get_scalars(b200_problem* p, double out[4]) {
+    if (!p || !out) return B200_BAD_ARG;
+    for (int i = 0; i < 4; i++) out[i] = p->h_scal[i];
     return B200_OK;
 }
 

@@ -44,7 +44,9 @@ template <bool WJ>
 __global__ void __launch_bounds__(128) linearize_kernel(const DevSlot* __restrict__ slots, const double* __restrict__ tv,
                                                         const double* __restrict__ sv, const double* __restrict__ cst, long long Kld,
                                                         double* __restrict__ Jbuf, double* __restrict__ rbuf, double* __restrict__ ebuf,
-                                                        int k_lo, int k_hi) {
+                                                        int k_lo, int k_hi, int e_lo) {
+    // keyframes [k_lo, k_hi) are evaluated; only [e_lo, k_hi) count towards this rank's cost (a sharded rank also linearizes
+    // the keyframe left of its window, whose factors belong to the neighbour's cost)
     const DevSlot& s = slots[blockIdx.y];
     const int inst = blockIdx.x * blockDim.x + threadIdx.x;
     if (inst >= s.n_inst) return;
@@ -65,7 +67,7 @@ __global__ void __launch_bounds__(128) linearize_kernel(const DevSlot* __restric
     factor_whiten<WJ>(s.type, s.params, c, r, J, s.cols);
     double e = 0.0;
     for (int i = 0; i < s.rows; i++) e += r[i] * r[i];
-    ebuf[s.e_off + inst] = 0.5 * e;
+    ebuf[s.e_off + inst] = (k >= e_lo) ? 0.5 * e : 0.0;
     if (WJ) {
         // per-instance records (rows*cols then rows): the consumer (assemble_kernel) copies one keyframe's records as
         // contiguous chunks; each thread streams its own record, full 32-byte sectors

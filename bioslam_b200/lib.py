@@ -40,6 +40,7 @@ def load(path=None):
         getattr(L, f).argtypes = [C.c_void_p]
     L.b200_comm_set.argtypes = [C.c_void_p, C.c_int32, C.c_int32, ALLGATHER_FN, ALLREDUCE_FN, C.c_void_p]
     L.b200_get_levels.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32]
+    L.b200_debug_get_scalars.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.b200_lower_body_joint_angles.argtypes = [C.c_void_p, C.POINTER(abi.JointAngleDesc), C.c_void_p]
     _libs[path] = L
     return L
@@ -93,6 +94,11 @@ class Problem:
     @property
     def groups(self):
         return self.L.b200_get_groups(self.h)
+
+    def last_trial_scalars(self):
+        out = (C.c_double * 4)()
+        self._ck(self.L.b200_debug_get_scalars(self.h, out))
+        return list(out)
 
     def joint_angles(self, desc):
         """[K][12] clinical hip / knee angles (rad) of the current values, computed on the device (abi.JOINT_ANGLE_NAMES)"""

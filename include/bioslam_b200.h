@@ -310,6 +310,9 @@ b200_status b200_debug_get_hessian_blocks(b200_problem* p, int32_t k, double* D,
 b200_status b200_debug_get_static_hessian(b200_problem* p, double* S /*[ns*ns]*/);
 /* solve (J^T J + lambda I) delta = -J^T r on the last linearization */
 b200_status b200_debug_solve(b200_problem* p, double lambda, double* delta_time /*[K][nt]*/, double* delta_static);
+/* scalars of the last lambda trial: out[0] = linear.error(0) (== the cost at the linearization point, all ranks summed),
+ * out[1] = linear.error(delta), out[2] = cost of the retracted values */
+b200_status b200_debug_get_scalars(b200_problem* p, double out[4]);
 /* kernel launch counter (all launches issued by this library for p since creation) */
 int64_t b200_launch_count(const b200_problem* p);
 /* device time (CUDA events on the problem's stream) since the last reset.  out[0] linearize+assemble ms, out[1] solve ms,

@@ -30,8 +30,15 @@ p.set_values(tv, sv)
 out = {"chunks": p.chunks, "groups": p.groups}
 e0 = p.lm_begin(abi.LmParams.lower_body())
 trace = []
+err_before = e0
 for _ in range(3):
-    st = p.lm_iterate(); trace.append([st.error, st.lambda_, st.inner_trials, st.iterations])
+    st = p.lm_iterate()
+    # linear.error(0) summed over the ranks must be the cost at the linearization point: every factor counted exactly once
+    # (a rank also linearizes the keyframe left of its window; its factors belong to the neighbour's cost)
+    lin0 = p.last_trial_scalars()[0]
+    assert abs(lin0 - err_before) <= 1e-12 * err_before, (lin0, err_before)
+    err_before = st.error
+    trace.append([st.error, st.lambda_, st.inner_trials, st.iterations])
 tv2, sv2 = p.get_values()
 np.savez(sys.argv[5] + f".rank{rank}.npz", e0=e0, trace=np.array(trace), tv=tv2, sv=sv2, chunks=p.chunks, groups=p.groups)
 dist.destroy_process_group()
