@@ -151,6 +151,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib.load()
@@ -222,6 +224,8 @@ def run_b200(args):
                "converged": bool(res.iterations < args.converge_max), "rule": "6 consecutive iterations with abs<1e-6 or rel<1e-5 decrease"}
 
     if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
         return
     peak, peak_src = measured_peaks()
     P = p.chunks
@@ -259,6 +263,8 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, K)
     print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 def main():

@@ -455,23 +455,11 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
     return B200_OK;
 }
 
-// cost model (units of one narrow elimination step; an interior step carries the left separator and costs ~1.8 of them):
-// T = waves(P1) * 1.8 * (K/P1 - 1) + [P2 > 1 ? 1.8 * ((P1-1)/P2 - 1) + (P2 - 1) : (P1 - 1)]
-static double partition_cost(int K, int P1, int P2, int sms) {
-    if (P1 <= 1) return (double)K;
-    const double waves = std::ceil((double)P1 / sms);
-    double t = waves * 1.8 * ((double)K / P1 - 1.0);
-    const int n2 = P1 - 1;
-    if (P2 > 1) t += 1.8 * ((double)n2 / P2 - 1.0) + (P2 - 1);
-    else t += n2;
-    return t;
-}
-
 // Upper levels (single rank): the m separators left by a level form a chain again.  Either one CTA sweeps them sequentially
 // (cost m) or they are cut into P chunks whose interior nodes are eliminated in parallel (every step carries the left
 // separator and a dense coupling block: ~2 units, plus a fixed per-level cost for the Schur / reduce / back-substitution
 // launches) and the P-1 chunk separators recurse.  Dynamic programme over m; appends the chosen chunk counts to Ps.
-static void plan_upper_levels(int m, std::vector<int>& Ps) {
+static double plan_upper_levels(int m, std::vector<int>* Ps) {
     const double step_dense = 2.0, level_fixed = 1.5, step_top = 1.0;
     std::vector<double> T(m + 1, 0.0);
     std::vector<int> choice(m + 1, 1);
@@ -487,7 +475,17 @@ static void plan_upper_levels(int m, std::vector<int>& Ps) {
             if (t < T[mm]) { T[mm] = t; choice[mm] = P; }
         }
     }
-    while (m > 0 && choice[m] > 1) { Ps.push_back(choice[m]); m = choice[m] - 1; }
+    const double total = T[m];
+    if (Ps) while (m > 0 && choice[m] > 1) { Ps->push_back(choice[m]); m = choice[m] - 1; }
+    return total;
+}
+
+// cost of a whole solve in the same units: level 0 (sparse coupling; every interior keyframe costs one sweep step plus its
+// share of the Schur and back-substitution kernels, ~1.45 units) in waves of one chunk per SM, plus the upper levels
+static double partition_cost(int K, int P1, int sms) {
+    if (P1 <= 1) return (double)K;
+    const double waves = std::ceil((double)P1 / sms);
+    return waves * 1.45 * ((double)K / P1 - 1.0) + 1.5 + plan_upper_levels(P1 - 1, nullptr);
 }
 
 // Build the nested partition.  P1 chunks over the keyframes (every rank owns P1/world of them, inside its window of
@@ -500,33 +498,21 @@ static b200_status set_partition(b200_problem* p, int P1, int P2) {
     if ((long long)(W - 1) * p->Wk >= K || K - (W - 1) * p->Wk < 3) { set_err("too few keyframes for this many ranks"); return B200_BAD_ARG; }
     const int max_p1 = std::max(1, K / 3);
     const bool auto_groups = P2 <= 0;
-    if (P1 <= 0) {  // search the cost model
-        double best = 1e300; int bp1 = 1, bp2 = 1;
-        for (int c1 = 1; c1 <= std::min(max_p1, 8 * sms); c1++) {
-            if (c1 % W) continue;
-            for (int c2 = 1; c2 <= std::max(1, (c1 - 1) / 3); c2++) {
-                if (c2 > 1 && c2 % W) continue;
-                if (W > 1 && c2 < W) continue;
-                const double t = partition_cost(K, c1, c2, sms);
-                if (t < best) { best = t; bp1 = c1; bp2 = c2; }
-            }
+    if (P1 <= 0) {  // search the cost model (the upper levels recurse: plan_upper_levels)
+        double best = 1e300; int bp1 = 1;
+        for (int c1 = W; c1 <= std::min(max_p1, 2 * sms); c1 += W) {
+            if (c1 > 1 && W > 1 && (c1 / W) < 3) continue;
+            const double t = partition_cost(K, c1, sms);
+            if (t < best) { best = t; bp1 = c1; }
         }
-        P1 = bp1; if (P2 <= 0) P2 = bp2;
+        P1 = bp1;
     }
     P1 = std::max(1, std::min(P1, max_p1));
     if (W > 1) { P1 = std::max(P1, 2 * W); P1 = (P1 + W - 1) / W * W; while (P1 > W && p->Wk / (P1 / W) < 3) P1 -= W; }
-    if (P2 <= 0) {  // choose groups for the given P1
-        double best = 1e300; int bp2 = 1;
-        for (int c2 = 1; c2 <= std::max(1, (P1 - 1) / 3); c2++) {
-            if (W > 1 && c2 % W) continue;
-            const double t = partition_cost(K, P1, c2, sms);
-            if (t < best) { best = t; bp2 = c2; }
-        }
-        P2 = bp2;
-    }
+    if (P2 <= 0) P2 = 1;
     if (auto_groups && P1 > 3) {   // recursive levels above: take the first level the dynamic programme would choose
         std::vector<int> tmp;
-        plan_upper_levels(P1 - 1, tmp);
+        plan_upper_levels(P1 - 1, &tmp);
         P2 = tmp.empty() ? 1 : tmp[0];
     }
     if (W > 1) { P2 = std::max(P2, W); P2 = (P2 + W - 1) / W * W; while (P2 > W && (P1 / W - 1) / (P2 / W) < 2) P2 -= W; if ((P1 / W - 1) / (P2 / W) < 2) { set_err("partition too fine for this many ranks"); return B200_BAD_ARG; } }
@@ -539,7 +525,7 @@ static b200_status set_partition(b200_problem* p, int P1, int P2) {
         if (P2 > 1) Ps.push_back(P2);
         // single rank: all levels from the dynamic programme; sharded: level 1 is rank-aligned (P2 above), the levels above it
         // are computed redundantly on every rank (their inputs are all-gathered) and recurse the same way
-        if (auto_groups && P2 > 1) plan_upper_levels(P2 - 1, Ps);
+        if (auto_groups && P2 > 1) plan_upper_levels(P2 - 1, &Ps);
     }
     p->P = P1; p->P2 = Ps.size() > 1 ? Ps[1] : 1; P2 = p->P2;
     const int nlev = (int)Ps.size();
