@@ -24,7 +24,13 @@ __device__ __forceinline__ void cp_async_wait_all() {}
 __device__ __forceinline__ void prefetch_l2(const void*) {}
 __device__ __forceinline__ void named_bar_sync(int id, int count) { emu::bar_sync(id, count); }
 __device__ __forceinline__ void named_bar_arrive(int id, int count) { emu::bar_arrive(id, count); }
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) { emu::dmma884(c0, c1, a, b); }
 #else
+// fp64 tensor-core MMA (DMMA on sm_100a): C(8 x 8) += A(8 x 4) B(4 x 8).  Lane (g = lane >> 2, t = lane & 3) supplies A[g][t] and
+// B[t][g] and owns C[g][2t], C[g][2t+1].  IEEE fp64 fused multiply-adds: same rounding class as the scalar DFMA path.
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");

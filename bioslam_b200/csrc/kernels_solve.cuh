@@ -53,170 +53,180 @@ __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_ca
 __device__ __forceinline__ void st2(double* p, double x, double y) { *reinterpret_cast<double2*>(p) = make_double2(x, y); }
 
 // ------------------------------------------------------------------------------------------------- micro-kernels
-// Warp tile 16 x 32, thread tile 4 x 4.  lane -> (ty = lane >> 3, tx = lane & 7); rows m0 + ty + 4 i.
-// NN:  C += A(16 x k) B(k x 32), B row-major indexed [k][c]; columns c0 + 2 tx + 16 j + {0, 1}; ka, kb, N even.
+// Warp tile 16 x 32 on the fp64 tensor cores (DMMA, mma.sync m8n8k4 -- see dmma884 in cuda_compat.h): per contraction step
+// of 4 a warp issues 6 scalar operand loads and 8 MMAs (2048 FMAs); the r01 scalar micro-kernel needed 16 LDS.128 for the same
+// work and was shared-memory bound at ~55 % of the fp64 rate (tools/ubench/dmma_probe.cu: 22 vs 37 TFLOP/s).
+// lane -> (g = lane >> 2, t = lane & 3).  Accumulator element acc[i][j][e]: row m0 + 8 i + g, column (base of 8-column
+// block j) + 2 t + e.  Contraction ranges are arbitrary: operands at or beyond the end of a range are read as zero.
+typedef double Acc[2][4][2];
+__device__ __forceinline__ void acc_zero(Acc& acc) {
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+}
+
+// NN:  C += A(16 x k) B(k x 32), B row-major indexed [k][c]; 8-column blocks at c0 + 8 j.
 __device__ __forceinline__ void warp_mma_nn(const double* __restrict__ A, int lda, int m0, int M, const double* __restrict__ B, int ldb,
-                                            int c0, int N, int ka, int kb, double (&acc)[4][4]) {
-    const int lane = threadIdx.x & 31, ty = lane >> 3, tx = lane & 7;
-    const double* ap[4];
+                                            int c0, int N, int ka, int kb, Acc& acc) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const double* ap[2];
+    const double* bp[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) { int m = m0 + ty + 4 * i; if (m > M - 1) m = M - 1; ap[i] = A + (long long)m * lda; }
-    int cj[2];
+    for (int i = 0; i < 2; i++) { int m = m0 + 8 * i + g; if (m > M - 1) m = M - 1; ap[i] = A + (long long)m * lda + t; }
 #pragma unroll
-    for (int j = 0; j < 2; j++) { int c = c0 + 2 * tx + 16 * j; if (c > N - 2) c = N - 2; cj[j] = c; }
-    const double* bp = B + (long long)ka * ldb;
-    for (int k = ka; k < kb; k += 2, bp += 2 * ldb) {
-        double2 a[4], b0[2], b1[2];
+    for (int j = 0; j < 4; j++) { int c = c0 + 8 * j + g; if (c > N - 1) c = N - 1; bp[j] = B + (long long)t * ldb + c; }
+    for (int k = ka; k < kb; k += 4) {
+        const bool ok = k + t < kb;
+        double a[2], b[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) a[i] = ld2(ap[i] + k);
+        for (int i = 0; i < 2; i++) a[i] = ok ? ap[i][k] : 0.0;
 #pragma unroll
-        for (int j = 0; j < 2; j++) { b0[j] = ld2(bp + cj[j]); b1[j] = ld2(bp + ldb + cj[j]); }
+        for (int j = 0; j < 4; j++) b[j] = ok ? bp[j][(long long)k * ldb] : 0.0;
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+        for (int i = 0; i < 2; i++)
 #pragma unroll
-            for (int j = 0; j < 2; j++) {
-                acc[i][2 * j] = fma(a[i].y, b1[j].x, fma(a[i].x, b0[j].x, acc[i][2 * j]));
-                acc[i][2 * j + 1] = fma(a[i].y, b1[j].y, fma(a[i].x, b0[j].y, acc[i][2 * j + 1]));
-            }
+            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
 }
-// element (i, q) of an NN tile: row m0 + ty + 4 i, column c0 + 2 tx + 16 (q >> 1) + (q & 1)
 
-// NT:  C += A(16 x k) B(32 x k)^T, both row-major along k; columns r0 + tx + 8 j.
+// NT:  C += A(16 x k) B(32 x k)^T, both row-major along k; 8-column blocks = rows r0 + 8 j of B.
 __device__ __forceinline__ void warp_mma_nt(const double* __restrict__ A, int lda, int m0, int M, const double* __restrict__ B, int ldb,
-                                            int r0, int R, int ka, int kb, double (&acc)[4][4]) {
-    const int lane = threadIdx.x & 31, ty = lane >> 3, tx = lane & 7;
-    const double* ap[4];
+                                            int r0, int R, int ka, int kb, Acc& acc) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const double* ap[2];
     const double* bp[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        int m = m0 + ty + 4 * i; if (m > M - 1) m = M - 1;
-        int r = r0 + tx + 8 * i; if (r > R - 1) r = R - 1;
-        ap[i] = A + (long long)m * lda;
-        bp[i] = B + (long long)r * ldb;
-    }
-    for (int k = ka; k < kb; k += 2) {
-        double2 a[4], b[4];
+    for (int i = 0; i < 2; i++) { int m = m0 + 8 * i + g; if (m > M - 1) m = M - 1; ap[i] = A + (long long)m * lda + t; }
 #pragma unroll
-        for (int i = 0; i < 4; i++) { a[i] = ld2(ap[i] + k); b[i] = ld2(bp[i] + k); }
+    for (int j = 0; j < 4; j++) { int r = r0 + 8 * j + g; if (r > R - 1) r = R - 1; bp[j] = B + (long long)r * ldb + t; }
+    for (int k = ka; k < kb; k += 4) {
+        const bool ok = k + t < kb;
+        double a[2], b[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+        for (int i = 0; i < 2; i++) a[i] = ok ? ap[i][k] : 0.0;
 #pragma unroll
-            for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i].y, b[j].y, fma(a[i].x, b[j].x, acc[i][j]));
+        for (int j = 0; j < 4; j++) b[j] = ok ? bp[j][k] : 0.0;
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
 }
 
-// Balanced variants for the TRIANGULAR products: a warp owns two 16-column blocks A and B whose contraction ranges are
-// complementary (short + long), so that every warp of a row group carries the same work.
-// NN: columns cA + 2 tx + {0,1} -> acc[.][0..1] over k in [ka, kendA), columns cB + 2 tx + {0,1} -> acc[.][2..3] over [ka, kendB);
-// kendA <= kendB.
+// Balanced variants for the TRIANGULAR products: a warp owns two 16-column blocks A (acc[.][0..1]) and B (acc[.][2..3]) whose
+// contraction ranges are complementary (short + long), so that every warp of a row group carries the same work.
+// NN: block A = columns [cA, cA+16) over k in [ka, kendA), block B = columns [cB, cB+16) over k in [ka, kendB); kendA <= kendB.
 __device__ __forceinline__ void warp_mma_nn2(const double* __restrict__ A, int lda, int m0, int M, const double* __restrict__ B, int ldb,
-                                             int cA, int cB, int N, int ka, int kendA, int kendB, double (&acc)[4][4]) {
-    const int lane = threadIdx.x & 31, ty = lane >> 3, tx = lane & 7;
-    const double* ap[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) { int m = m0 + ty + 4 * i; if (m > M - 1) m = M - 1; ap[i] = A + (long long)m * lda; }
-    int ca = cA + 2 * tx; if (ca > N - 2) ca = N - 2;
-    int cb = cB + 2 * tx; if (cb > N - 2) cb = N - 2;
-    const double* bp = B + (long long)ka * ldb;
-    int k = ka;
-    for (; k < kendA; k += 2, bp += 2 * ldb) {
-        double2 a[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) a[i] = ld2(ap[i] + k);
-        const double2 b0a = ld2(bp + ca), b1a = ld2(bp + ldb + ca), b0b = ld2(bp + cb), b1b = ld2(bp + ldb + cb);
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            acc[i][0] = fma(a[i].y, b1a.x, fma(a[i].x, b0a.x, acc[i][0]));
-            acc[i][1] = fma(a[i].y, b1a.y, fma(a[i].x, b0a.y, acc[i][1]));
-            acc[i][2] = fma(a[i].y, b1b.x, fma(a[i].x, b0b.x, acc[i][2]));
-            acc[i][3] = fma(a[i].y, b1b.y, fma(a[i].x, b0b.y, acc[i][3]));
-        }
-    }
-    for (; k < kendB; k += 2, bp += 2 * ldb) {
-        double2 a[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) a[i] = ld2(ap[i] + k);
-        const double2 b0b = ld2(bp + cb), b1b = ld2(bp + ldb + cb);
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            acc[i][2] = fma(a[i].y, b1b.x, fma(a[i].x, b0b.x, acc[i][2]));
-            acc[i][3] = fma(a[i].y, b1b.y, fma(a[i].x, b0b.y, acc[i][3]));
-        }
-    }
-}
-// NT: columns kA + tx + 8 j (j < 2) -> acc[.][0..1] over c in [sA, kend), columns kB + tx + 8 j -> acc[.][2..3] over [sB, kend).
-__device__ __forceinline__ void warp_mma_nt2(const double* __restrict__ A, int lda, int m0, int M, const double* __restrict__ B, int ldb,
-                                             int kA, int kB, int R, int sA, int sB, int kend, double (&acc)[4][4]) {
-    const int lane = threadIdx.x & 31, ty = lane >> 3, tx = lane & 7;
-    const double* ap[4];
+                                             int cA, int cB, int N, int ka, int kendA, int kendB, Acc& acc) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const double* ap[2];
     const double* bp[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        int m = m0 + ty + 4 * i; if (m > M - 1) m = M - 1;
-        int r = ((i < 2) ? kA : kB) + tx + 8 * (i & 1); if (r > R - 1) r = R - 1;
-        ap[i] = A + (long long)m * lda;
-        bp[i] = B + (long long)r * ldb;
+    for (int i = 0; i < 2; i++) { int m = m0 + 8 * i + g; if (m > M - 1) m = M - 1; ap[i] = A + (long long)m * lda + t; }
+#pragma unroll
+    for (int j = 0; j < 4; j++) { int c = ((j < 2) ? cA : cB) + 8 * (j & 1) + g; if (c > N - 1) c = N - 1; bp[j] = B + (long long)t * ldb + c; }
+    int k = ka;
+    for (; k < kendA; k += 4) {
+        const bool ok = k + t < kendA;
+        double a[2], b[4];
+#pragma unroll
+        for (int i = 0; i < 2; i++) a[i] = ok ? ap[i][k] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) b[j] = ok ? bp[j][(long long)k * ldb] : 0.0;
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
+    for (k = (kendA > ka ? kendA : ka); k < kendB; k += 4) {
+        const bool ok = k + t < kendB;
+        double a[2], b[2];
+#pragma unroll
+        for (int i = 0; i < 2; i++) a[i] = ok ? ap[i][k] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 2; j++) b[j] = ok ? bp[2 + j][(long long)k * ldb] : 0.0;
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) dmma884(acc[i][2 + j][0], acc[i][2 + j][1], a[i], b[j]);
+    }
+}
+// NT: block A = rows [kA, kA+16) of B over c in [sA, kend), block B = rows [kB, kB+16) of B over c in [sB, kend).
+__device__ __forceinline__ void warp_mma_nt2(const double* __restrict__ A, int lda, int m0, int M, const double* __restrict__ B, int ldb,
+                                             int kA, int kB, int R, int sA, int sB, int kend, Acc& acc) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const double* ap[2];
+    const double* bp[4];
+#pragma unroll
+    for (int i = 0; i < 2; i++) { int m = m0 + 8 * i + g; if (m > M - 1) m = M - 1; ap[i] = A + (long long)m * lda + t; }
+#pragma unroll
+    for (int j = 0; j < 4; j++) { int r = ((j < 2) ? kA : kB) + 8 * (j & 1) + g; if (r > R - 1) r = R - 1; bp[j] = B + (long long)r * ldb + t; }
     // the block that starts earlier runs alone over [lo, hi)  (static register indices: two copies of the loop)
     const int lo = sA < sB ? sA : sB, hi = sA < sB ? sB : sA;
-    int k = lo;
     const int hic = hi < kend ? hi : kend;
     if (sA < sB) {
-        for (; k < hic; k += 2) {
-            double2 a[4];
+        for (int k = lo; k < hic; k += 4) {
+            const bool ok = k + t < hic;
+            double a[2], b[2];
 #pragma unroll
-            for (int i = 0; i < 4; i++) a[i] = ld2(ap[i] + k);
-            const double2 b0 = ld2(bp[0] + k), b1 = ld2(bp[1] + k);
+            for (int i = 0; i < 2; i++) a[i] = ok ? ap[i][k] : 0.0;
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                acc[i][0] = fma(a[i].y, b0.y, fma(a[i].x, b0.x, acc[i][0]));
-                acc[i][1] = fma(a[i].y, b1.y, fma(a[i].x, b1.x, acc[i][1]));
-            }
+            for (int j = 0; j < 2; j++) b[j] = ok ? bp[j][k] : 0.0;
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
     } else {
-        for (; k < hic; k += 2) {
-            double2 a[4];
+        for (int k = lo; k < hic; k += 4) {
+            const bool ok = k + t < hic;
+            double a[2], b[2];
 #pragma unroll
-            for (int i = 0; i < 4; i++) a[i] = ld2(ap[i] + k);
-            const double2 b0 = ld2(bp[2] + k), b1 = ld2(bp[3] + k);
+            for (int i = 0; i < 2; i++) a[i] = ok ? ap[i][k] : 0.0;
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                acc[i][2] = fma(a[i].y, b0.y, fma(a[i].x, b0.x, acc[i][2]));
-                acc[i][3] = fma(a[i].y, b1.y, fma(a[i].x, b1.x, acc[i][3]));
-            }
+            for (int j = 0; j < 2; j++) b[j] = ok ? bp[2 + j][k] : 0.0;
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) dmma884(acc[i][2 + j][0], acc[i][2 + j][1], a[i], b[j]);
         }
     }
-    for (; k < kend; k += 2) {
-        double2 a[4], b[4];
+    for (int k = hi; k < kend; k += 4) {
+        const bool ok = k + t < kend;
+        double a[2], b[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) { a[i] = ld2(ap[i] + k); b[i] = ld2(bp[i] + k); }
+        for (int i = 0; i < 2; i++) a[i] = ok ? ap[i][k] : 0.0;
 #pragma unroll
-        for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) b[j] = ok ? bp[j][k] : 0.0;
 #pragma unroll
-            for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i].y, b[j].y, fma(a[i].x, b[j].x, acc[i][j]));
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
 }
 
-// NT, warp tile 32 x 32, thread tile 8 x 4 (Schur complement kernel): rows m0 + ty + 4 i (i < 8), columns r0 + tx + 8 j.
-__device__ __forceinline__ void warp_mma_nt32(const double* __restrict__ A, int lda, int m0, int M, int r0, int ka, int kb, double (&acc)[8][4]) {
-    const int lane = threadIdx.x & 31, ty = lane >> 3, tx = lane & 7;
-    const double* ap[8];
+// NT, warp tile 32 x 32 (Schur complement kernel): C += A[m0.., :] A[r0.., :]^T; acc[i][j][e]: row m0 + 8 i + g, column r0 + 8 j + 2 t + e.
+typedef double Acc32[4][4][2];
+__device__ __forceinline__ void warp_mma_nt32(const double* __restrict__ A, int lda, int m0, int M, int r0, int ka, int kb, Acc32& acc) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const double* ap[4];
     const double* bp[4];
 #pragma unroll
-    for (int i = 0; i < 8; i++) { int m = m0 + ty + 4 * i; if (m > M - 1) m = M - 1; ap[i] = A + (long long)m * lda; }
+    for (int i = 0; i < 4; i++) { int m = m0 + 8 * i + g; if (m > M - 1) m = M - 1; ap[i] = A + (long long)m * lda + t; }
 #pragma unroll
-    for (int j = 0; j < 4; j++) { int r = r0 + tx + 8 * j; if (r > M - 1) r = M - 1; bp[j] = A + (long long)r * lda; }
-    for (int k = ka; k < kb; k += 2) {
-        double2 a[8], b[4];
+    for (int j = 0; j < 4; j++) { int r = r0 + 8 * j + g; if (r > M - 1) r = M - 1; bp[j] = A + (long long)r * lda + t; }
+    for (int k = ka; k < kb; k += 4) {
+        const bool ok = k + t < kb;
+        double a[4], b[4];
 #pragma unroll
-        for (int i = 0; i < 8; i++) a[i] = ld2(ap[i] + k);
+        for (int i = 0; i < 4; i++) a[i] = ok ? ap[i][k] : 0.0;
 #pragma unroll
-        for (int j = 0; j < 4; j++) b[j] = ld2(bp[j] + k);
+        for (int j = 0; j < 4; j++) b[j] = ok ? bp[j][k] : 0.0;
 #pragma unroll
-        for (int i = 0; i < 8; i++)
+        for (int i = 0; i < 4; i++)
 #pragma unroll
-            for (int j = 0; j < 4; j++) acc[i][j] = fma(a[i].y, b[j].y, fma(a[i].x, b[j].x, acc[i][j]));
+            for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
 }
 
@@ -353,6 +363,7 @@ __device__ int cta_chol_inv(double* Ms, int ld, int n) {
     solve_scratch(Tdiag, Wd0, invd);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int ty = lane >> 3, tx = lane & 7;
+    const int mg = lane >> 2, mt = lane & 3;   // MMA fragment coordinates
     const int nb = (n + B200_NB - 1) / B200_NB;
     // the pivot warp's chain is latency-bound: the warps that share its scheduler (warp & 3 == 0) stay out of the way
     const bool quiet = false;   // (measured: idling the 3 warps on the pivot scheduler does not pay -- the chain waits on the shared MIO pipe)
@@ -501,20 +512,20 @@ __device__ int cta_chol_inv(double* Ms, int ld, int n) {
                 for (int tile = wk; tile < ntr * ntc; tile += nwk) {
                     const int m0 = (tile / ntc) << 4, c0 = cb0 + ((tile % ntc) << 5);
                     if (m0 >= cb0 && m0 + 15 < c0) continue;   // dead zone: not-yet-started appended rows
-                    double acc[4][4];
-#pragma unroll
-                    for (int i = 0; i < 4; i++)
-#pragma unroll
-                        for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
+                    Acc acc;
+                    acc_zero(acc);
                     warp_mma_nt(Ms, ld, m0, n, Ms, ld, c0, n, j0, cb0, acc);
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const int r = m0 + ty + 4 * i;
+                    for (int i = 0; i < 2; i++) {
+                        const int r = m0 + 8 * i + mg;
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
-                            const int c = c0 + tx + 8 * j;
-                            const bool pivots = (r >= cb0 && r < cb0 + B200_NB && c < cb0 + B200_NB);
-                            if (r < n && c < n && (r >= c || r < cb0) && !pivots) Ms[(long long)r * ld + c] -= acc[i][j];
+#pragma unroll
+                            for (int e = 0; e < 2; e++) {
+                                const int c = c0 + 8 * j + 2 * mt + e;
+                                const bool pivots = (r >= cb0 && r < cb0 + B200_NB && c < cb0 + B200_NB);
+                                if (r < n && c < n && (r >= c || r < cb0) && !pivots) Ms[(long long)r * ld + c] -= acc[i][j][e];
+                            }
                         }
                     }
                 }
@@ -673,7 +684,7 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
     const int n = dm.ntp, nl = dm.nl, nc = dm.nc, ns1 = dm.ns1, ld = dm.ld, hmax = dm.hmax, CR = dm.cr, ow = dm.ow, owp = dm.owp;
     const long long Fsz = (long long)(nc + hmax) * nc;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int ty = lane >> 3, tx = lane & 7;
+    const int mg = lane >> 2, mt = lane & 3;   // MMA fragment coordinates (micro-kernels above)
     double* Ms = sm;
     double* Yb = sm + (long long)n * ld;
     double* Op = Yb + (long long)CR * ld;
@@ -841,11 +852,8 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                     const int slot = warp % tpw, rt = warp / tpw;
                     const bool act = rt < rtiles && slot < npair;
                     const int bA = slot, bB = nb16 - 1 - slot;   // bA <= bB ; equal: the middle block of an odd count
-                    double acc[4][4];
-#pragma unroll
-                    for (int q = 0; q < 4; q++)
-#pragma unroll
-                        for (int j = 0; j < 4; j++) acc[q][j] = 0.0;
+                    Acc acc;
+                    acc_zero(acc);
                     const int m0 = rt << 4;
                     if (act) {
                         int ka = 0, kb = n;
@@ -858,16 +866,16 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                     __syncthreads();
                     if (act) {
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const int lr = m0 + ty + 4 * q;
+                        for (int q = 0; q < 2; q++) {
+                            const int lr = m0 + 8 * q + mg;
                             if (lr >= cr) continue;
 #pragma unroll
-                            for (int j = 0; j < 2; j++) {
-                                if (j == 0 && bA == bB) continue;
-                                const int c = ((j == 0 ? bA : bB) << 4) + 2 * tx;
+                            for (int j = 0; j < 4; j++) {
+                                if (j < 2 && bA == bB) continue;
+                                const int c = ((j < 2 ? bA : bB) << 4) + 8 * (j & 1) + 2 * mt;
                                 if (c >= n) continue;
-                                st2(Yb + (long long)lr * ld + c, acc[q][2 * j], acc[q][2 * j + 1]);
-                                if (seg == 1) st2(Yg + (long long)(r0 - xo + lr) * n + c, acc[q][2 * j], acc[q][2 * j + 1]);
+                                st2(Yb + (long long)lr * ld + c, acc[q][j][0], acc[q][j][1]);
+                                if (seg == 1) st2(Yg + (long long)(r0 - xo + lr) * n + c, acc[q][j][0], acc[q][j][1]);
                             }
                         }
                     }
@@ -880,11 +888,8 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                         // spread long and short column tiles over the four schedulers (warp & 3)
                         const int ct = lo + (slot + rt) % tpw;
                         const bool act = rt < rtiles && ct < hi;
-                        double acc[4][4];
-#pragma unroll
-                        for (int q = 0; q < 4; q++)
-#pragma unroll
-                            for (int j = 0; j < 4; j++) acc[q][j] = 0.0;
+                        Acc acc;
+                        acc_zero(acc);
                         const int m0 = rt << 4, c0 = ct << 5;
                         if (act) {
                             int ka = 0, kb = n;
@@ -895,15 +900,15 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                         __syncthreads();
                         if (act) {
 #pragma unroll
-                            for (int q = 0; q < 4; q++) {
-                                const int lr = m0 + ty + 4 * q;
+                            for (int q = 0; q < 2; q++) {
+                                const int lr = m0 + 8 * q + mg;
                                 if (lr >= cr) continue;
 #pragma unroll
-                                for (int j = 0; j < 2; j++) {
-                                    const int c = c0 + 2 * tx + 16 * j;
+                                for (int j = 0; j < 4; j++) {
+                                    const int c = c0 + 8 * j + 2 * mt;
                                     if (c >= n) continue;
-                                    st2(Yb + (long long)lr * ld + c, acc[q][2 * j], acc[q][2 * j + 1]);
-                                    if (seg == 1) st2(Yg + (long long)(r0 - xo + lr) * n + c, acc[q][2 * j], acc[q][2 * j + 1]);
+                                    st2(Yb + (long long)lr * ld + c, acc[q][j][0], acc[q][j][1]);
+                                    if (seg == 1) st2(Yg + (long long)(r0 - xo + lr) * n + c, acc[q][j][0], acc[q][j][1]);
                                 }
                             }
                         }
@@ -919,11 +924,8 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                     const bool act = rt < rtiles && slot < npz;
                     const int bA = slot, bB = nbz - 1 - slot;
                     const int kA = kz0 + (bA << 4), kB = kz0 + (bB << 4);
-                    double acc[4][4];
-#pragma unroll
-                    for (int q = 0; q < 4; q++)
-#pragma unroll
-                        for (int j = 0; j < 4; j++) acc[q][j] = 0.0;
+                    Acc acc;
+                    acc_zero(acc);
                     const int m0 = rt << 4;
                     if (act) {
                         int sA = kA, sB = kB;
@@ -940,14 +942,14 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                     __syncthreads();
                     if (act) {
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const int lr = m0 + ty + 4 * q;
+                        for (int q = 0; q < 2; q++) {
+                            const int lr = m0 + 8 * q + mg;
                             if (lr >= cr) continue;
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
                                 if (j < 2 && bA == bB) continue;
-                                const int c = ((j < 2) ? kA : kB) + tx + 8 * (j & 1);
-                                if (c < n) Yb[(long long)lr * ld + c] = acc[q][j];
+                                const int c = ((j < 2) ? kA : kB) + 8 * (j & 1) + 2 * mt;
+                                if (c < n) st2(Yb + (long long)lr * ld + c, acc[q][j][0], acc[q][j][1]);
                             }
                         }
                     }
@@ -959,11 +961,8 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                         const int slot = warp % tpw, rt = warp / tpw;
                         const int ct = lo + (slot + rt) % tpw;
                         const bool act = rt < rtiles && ct < hi;
-                        double acc[4][4];
-#pragma unroll
-                        for (int q = 0; q < 4; q++)
-#pragma unroll
-                            for (int j = 0; j < 4; j++) acc[q][j] = 0.0;
+                        Acc acc;
+                        acc_zero(acc);
                         const int m0 = rt << 4, k0 = kz0 + (ct << 5);
                         if (act) {
                             int ca = k0;
@@ -978,13 +977,13 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                         __syncthreads();
                         if (act) {
 #pragma unroll
-                            for (int q = 0; q < 4; q++) {
-                                const int lr = m0 + ty + 4 * q;
+                            for (int q = 0; q < 2; q++) {
+                                const int lr = m0 + 8 * q + mg;
                                 if (lr >= cr) continue;
 #pragma unroll
                                 for (int j = 0; j < 4; j++) {
-                                    const int c = k0 + tx + 8 * j;
-                                    if (c < n) Yb[(long long)lr * ld + c] = acc[q][j];
+                                    const int c = k0 + 8 * j + 2 * mt;
+                                    if (c < n) st2(Yb + (long long)lr * ld + c, acc[q][j][0], acc[q][j][1]);
                                 }
                             }
                         }
@@ -1009,11 +1008,8 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                         const int slot = warp % tpw, rt = warp / tpw;
                         const int ct = lo + slot;
                         const bool act = rt < rtiles && ct < nctf;
-                        double acc[4][4];
-#pragma unroll
-                        for (int q = 0; q < 4; q++)
-#pragma unroll
-                            for (int j = 0; j < 4; j++) acc[q][j] = 0.0;
+                        Acc acc;
+                        acc_zero(acc);
                         const int m0 = rt << 4;
                         load_slab(0, Op);
                         for (int sidx = 0; sidx < nsl; sidx++) {
@@ -1025,13 +1021,16 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                         }
                         if (act) {
 #pragma unroll
-                            for (int q = 0; q < 4; q++) {
-                                const int lr = m0 + ty + 4 * q;
+                            for (int q = 0; q < 2; q++) {
+                                const int lr = m0 + 8 * q + mg;
                                 if (lr >= cr) continue;
 #pragma unroll
                                 for (int j = 0; j < 4; j++) {
-                                    const int ci = (ct << 5) + tx + 8 * j;
-                                    if (ci < nc) Fout[(long long)(r0 + lr) * nc + ci] = acc[q][j];
+#pragma unroll
+                                    for (int e = 0; e < 2; e++) {
+                                        const int ci = (ct << 5) + 8 * j + 2 * mt + e;
+                                        if (ci < nc) Fout[(long long)(r0 + lr) * nc + ci] = acc[q][j][e];
+                                    }
                                 }
                             }
                         }
@@ -1153,13 +1152,13 @@ __global__ void __launch_bounds__(B200_SOLVE_THREADS) chain_sweep_kernel(Dims dm
 // Arrow Schur complement of one chunk sweep:  Sacc = sum_nodes ( S_node - Y_node Y_node^T ), lower triangle of h x h.
 // One CTA per chunk, 12 warps; every warp owns up to two 32 x 32 output tiles whose accumulators stay in registers over
 // all nodes of the chunk (fixed summation order, no atomics).  The stored panel of a node is staged through shared memory.
-__global__ void __launch_bounds__(B200_SCHUR_THREADS) chain_schur_kernel(Dims dm, Level lv, SolveBuffers sb, int c_first, int ldy, int kslab) {
+__global__ void __launch_bounds__(B200_SCHUR_THREADS, 1) chain_schur_kernel(Dims dm, Level lv, SolveBuffers sb, int c_first, int ldy, int kslab) {
     B200_DYN_SMEM(double, Ys);
     SweepArgs a;
     level_chunk_args(dm, lv, sb, c_first + blockIdx.x, a);
     const int n = dm.ntp, ns1 = dm.ns1, hmax = dm.hmax, h = a.h;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int ty = lane >> 3, tx = lane & 7;
+    const int mg = lane >> 2, mt = lane & 3;   // MMA fragment coordinates
     if (*sb.status != 0) return;
     const int nrt = (h + 31) >> 5;
     const int ntiles = nrt * (nrt + 1) / 2;
@@ -1177,13 +1176,11 @@ __global__ void __launch_bounds__(B200_SCHUR_THREADS) chain_schur_kernel(Dims dm
             while ((r + 1) * (r + 2) / 2 <= (act[s] ? t : 0)) r++;
             tr[s] = r; tc[s] = (act[s] ? t : 0) - r * (r + 1) / 2;
         }
-        double acc[2][8][4];
+        Acc32 acc0, acc1;
 #pragma unroll
-        for (int s = 0; s < 2; s++)
+        for (int i = 0; i < 4; i++)
 #pragma unroll
-            for (int i = 0; i < 8; i++)
-#pragma unroll
-                for (int j = 0; j < 4; j++) acc[s][i][j] = 0.0;
+            for (int j = 0; j < 4; j++) { acc0[i][j][0] = 0.0; acc0[i][j][1] = 0.0; acc1[i][j][0] = 0.0; acc1[i][j][1] = 0.0; }
         for (int i = 0; i < a.n; i++) {
             const long long st = a.st_idx ? a.st_idx[i] : (long long)a.src0 + i;
             const double* Yg = a.Yst + st * (long long)hmax * n;
@@ -1194,24 +1191,26 @@ __global__ void __launch_bounds__(B200_SCHUR_THREADS) chain_schur_kernel(Dims dm
                     for (int c = 2 * lane; c < kw; c += 64) cp_async16(Ys + (long long)r * ldy + c, Yg + (long long)r * n + k0 + c);
                 cp_async_wait_all();
                 __syncthreads();
-#pragma unroll
-                for (int s = 0; s < 2; s++)
-                    if (act[s]) warp_mma_nt32(Ys, ldy, tr[s] << 5, h, tc[s] << 5, 0, kw, acc[s]);
+                if (act[0]) warp_mma_nt32(Ys, ldy, tr[0] << 5, h, tc[0] << 5, 0, kw, acc0);
+                if (act[1]) warp_mma_nt32(Ys, ldy, tr[1] << 5, h, tc[1] << 5, 0, kw, acc1);
             }
         }
+        auto store_tile = [&](int trs, int tcs, const Acc32& acc) {
 #pragma unroll
-        for (int s = 0; s < 2; s++) {
-            if (!act[s]) continue;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int a1 = (tr[s] << 5) + ty + 4 * i;
+            for (int i = 0; i < 4; i++) {
+                const int a1 = (trs << 5) + 8 * i + mg;
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const int a2 = (tc[s] << 5) + tx + 8 * j;
-                    if (a1 < h && a2 <= a1) a.Sacc[(long long)a1 * hmax + a2] = -acc[s][i][j];
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int a2 = (tcs << 5) + 8 * j + 2 * mt + e;
+                        if (a1 < h && a2 <= a1) a.Sacc[(long long)a1 * hmax + a2] = -acc[i][j][e];
+                    }
                 }
             }
-        }
+        };
+        if (act[0]) store_tile(tr[0], tc[0], acc0);
+        if (act[1]) store_tile(tr[1], tc[1], acc1);
     }
     __syncthreads();
     // the nodes' own static blocks

@@ -100,6 +100,21 @@ double shfl_exchange(double v, int src_lane) {
     sync_warp();
     return r;
 }
+// mma.sync.aligned.m8n8k4.row.col.f64: lane (g = lane >> 2, t = lane & 3) supplies A[g][t], B[t][g] and owns C[g][2t], C[g][2t+1];
+// the products are accumulated in the order k = 0..3 with fused multiply-adds.
+double xbuf2[64][32];
+void dmma884(double& c0, double& c1, double a, double b) {
+    int w = cur->lin >> 5, l = cur->lin & 31;
+    xbuf[w][l] = a; xbuf2[w][l] = b;
+    sync_warp();
+    const int g = l >> 2, t = l & 3;
+    for (int k = 0; k < 4; k++) {
+        const double ak = xbuf[w][g * 4 + k];
+        c0 = std::fma(ak, xbuf2[w][(2 * t) * 4 + k], c0);
+        c1 = std::fma(ak, xbuf2[w][(2 * t + 1) * 4 + k], c1);
+    }
+    sync_warp();
+}
 unsigned ballot(int pred) {
     int w = cur->lin >> 5, l = cur->lin & 31;
     xpred[w][l] = pred ? 1 : 0;

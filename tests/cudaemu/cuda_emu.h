@@ -80,6 +80,7 @@ void bar_sync(int id, int count);     // named barrier (bar.sync id, count)
 void bar_arrive(int id, int count);   // named barrier, non-blocking arrival (bar.arrive id, count)
 double shfl_exchange(double v, int src_lane);   // generic lane exchange within the caller's warp
 unsigned ballot(int pred);
+void dmma884(double& c0, double& c1, double a, double b);   // warp-collective fp64 MMA m8n8k4 (row.col)
 extern char* dyn_smem;
 extern long long launch_counter;
 int lane_id();
