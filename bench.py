@@ -162,7 +162,12 @@ def run_b200(args):
     p = lib.Problem(g, device=local, chunks=args.chunks)
     if world > 1:
         from bioslam_b200 import sharding
-        sharding.attach(p, dist, local)
+        # N GPUs = G lambda groups x T time shards: the groups try consecutive rungs of the LM lambda ladder concurrently
+        # (exactly the sequential tryLambda results), each group shards the time axis over its T ranks
+        lam_groups = args.lambda_groups if args.lambda_groups > 0 else (2 if world % 2 == 0 else 1)
+        sharding.attach(p, dist, local, lambda_groups=lam_groups)
+    else:
+        lam_groups = 1
     lm = abi.LmParams.lower_body()
 
     def barrier():
@@ -247,7 +252,8 @@ def run_b200(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": args.workload, "baseline_config": WORKLOADS[args.workload][1], "keyframes": K, "unknowns": 126 * K + 58,
-                   "chunks": P, "partition_levels": p.levels, "cache": "working set (>2 GB of Hessian/factor blocks at K=6000) exceeds the 126 MB L2; no flush needed",
+                   "chunks": P, "partition_levels": p.levels,
+                   "parallelism": f"{lam_groups} lambda group(s) x {world // lam_groups} time shard(s)", "cache": "working set (>2 GB of Hessian/factor blocks at K=6000) exceeds the 126 MB L2; no flush needed",
                    "init": "reference initial values (identity poses, zero vel/bias, statics at prior means)"},
         "lm_trials_per_sec": trials / (ms * 1e-3), "lambda_trials": trials, "error_after": err_after,
         "phase_ms_per_step": {"linearize+assemble": ph[0] / args.steps, "solve": ph[1] / args.steps, "model+retract+error": ph[2] / args.steps},
@@ -270,6 +276,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--lambda-groups", type=int, default=0, help="N > 1: groups of GPUs that try consecutive lambdas concurrently (0 = 2 when N is even)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])

@@ -109,6 +109,11 @@ struct b200_problem {
     b200_allgather_fn ag_fn = nullptr;
     b200_allreduce_fn ar_fn = nullptr;
     void* comm_ctx = nullptr;
+    // lambda speculation (b200_spec_set): spec_G groups of `world` ranks try lambda, lambda*factor, ... concurrently
+    int spec_G = 1, spec_g = 0, spec_rec = 0;
+    b200_allgather_fn spec_ag = nullptr;
+    void* spec_ctx = nullptr;
+    double *d_spec_delta = nullptr, *d_spec_rec = nullptr, *h_spec_rec = nullptr;
 };
 
 // B200_POISON=1 (debugging): fill every allocation with 0xFF bytes (NaN doubles / -1 ints) so that a read of memory the
@@ -224,6 +229,9 @@ void b200_problem_destroy(b200_problem* p) {
                     p->d_top_begin, p->d_orow, p->d_ocol, p->d_ozs, p->d_ogrp,
                     p->sb.scal, p->sb.status, p->d_stageS, p->d_stageF, p->d_pack, p->d_asm_items, p->d_asm_terms, p->d_asm_blocks[0], p->d_asm_blocks[1]};
     for (void* q : ptrs) if (q) cudaFree(q);
+    if (p->d_spec_delta) cudaFree(p->d_spec_delta);
+    if (p->d_spec_rec) cudaFree(p->d_spec_rec);
+    if (p->h_spec_rec) cudaFreeHost(p->h_spec_rec);
     free_levels(p);
     if (p->h_scal) cudaFreeHost(p->h_scal);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
@@ -839,7 +847,37 @@ b200_status b200_lm_begin(b200_problem* p, const b200_lm_params* prm, double* in
     return B200_OK;
 }
 
+// retract (values + delta -> try buffers): time variables of every keyframe, then the statics
+static void launch_retract(b200_problem* p, const double* delta, const double* dstat) {
+    B200_LAUNCH(retract_kernel, dim3((p->K + 127) / 128, 1, p->ntv), dim3(128), 0, p->stream, p->d_tvars, p->ntv, p->d_svars, p->nsv, p->K,
+                p->dm.Kld, p->d_tv, p->d_sv, delta, p->dm.ntp, dstat, p->d_tv_try, p->d_sv_try);
+    p->launches++;
+    if (p->nsv) {
+        B200_LAUNCH(retract_kernel, dim3((p->nsv + 127) / 128, 2, 1), dim3(128), 0, p->stream, p->d_tvars, 0, p->d_svars, p->nsv, 0, p->dm.Kld,
+                    p->d_tv, p->d_sv, delta, p->dm.ntp, dstat, p->d_tv_try, p->d_sv_try);
+        p->launches++;
+    }
+}
+
+// outcome of one lambda trial (gtsam @4.2 LevenbergMarquardtOptimizer::tryLambda): accept the step / stop searching
+struct TrialVerdict { bool solved, step_ok, stop; };
+static TrialVerdict judge_trial(const b200_lm_params& L, double cur_err, bool solved, double oldLin, double newLin, double newError) {
+    TrialVerdict v{solved, false, false};
+    if (!solved) return v;
+    const double linChange = oldLin - newLin;
+    if (L.gauss_newton) v.step_ok = true;
+    else if (linChange >= 0) {
+        const double costChange = cur_err - newError;
+        if (linChange > 2.220446049250313e-16 * oldLin) v.step_ok = (costChange / linChange) > L.min_model_fidelity;
+        if (std::fabs(costChange) < L.relative_error_tol * cur_err) v.stop = true;
+    }
+    return v;
+}
+
 // == LevenbergMarquardtOptimizer::iterate() (gtsam @4.2: iterate / tryLambda / increaseLambda / decreaseLambda)
+// With lambda speculation (b200_spec_set, G groups) every round evaluates the next G values of the lambda ladder at once, one
+// per group, and the verdicts are then read in ladder order exactly as the sequential loop would have met them: the accepted
+// step, the final lambda and the trial count are those of the sequential algorithm.
 b200_status b200_lm_iterate(b200_problem* p, b200_lm_state* state) {
     if (!p) return B200_BAD_ARG;
     CK(cudaSetDevice(p->device));
@@ -853,33 +891,41 @@ b200_status b200_lm_iterate(b200_problem* p, b200_lm_state* state) {
     p->launches++;
     if (p->time_phases) CK(cudaEventRecord(p->ev[1], p->stream));
     p->have_lin = true;
+    const int G = (p->spec_ag && !L.gauss_newton) ? p->spec_G : 1;
+    const int T = p->world;
     int status = B200_OK, inner = 0;
-    while (true) {  // tryLambda
-        inner++;
+    bool done = false;
+    while (!done) {  // one round of the lambda ladder: G rungs (sequential algorithm: G == 1)
+        double lam_try = p->lambda;
+        for (int i = 0; i < p->spec_g && G > 1; i++) lam_try *= L.lambda_factor;
         if (p->time_phases) CK(cudaEventRecord(p->ev[2], p->stream));
-        b200_status st = launch_solve(p, p->lambda);
+        b200_status st = launch_solve(p, lam_try);
         if (st != B200_OK) return st;
         if (p->time_phases) CK(cudaEventRecord(p->ev[3], p->stream));
         dim3 grid((p->max_inst + 127) / 128, p->n_slots);
         B200_LAUNCH(model_error_kernel, grid, dim3(128), 0, p->stream, p->d_slots, p->d_J, p->d_r, p->sb.delta, p->dm.ntp, p->sb.dstat, p->d_e2,
                     p->k_lo, p->k_hi);
         B200_LAUNCH(reduce_sum_kernel, dim3(1), dim3(1024), 0, p->stream, p->d_e2, p->ne, p->sb.scal + SC_MODEL_ERR);
-        B200_LAUNCH(retract_kernel, dim3((p->K + 127) / 128, 1, p->ntv), dim3(128), 0, p->stream, p->d_tvars, p->ntv, p->d_svars, p->nsv, p->K,
-                    p->dm.Kld, p->d_tv, p->d_sv, p->sb.delta, p->dm.ntp, p->sb.dstat, p->d_tv_try, p->d_sv_try);
-        p->launches += 3;
-        if (p->nsv) {
-            B200_LAUNCH(retract_kernel, dim3((p->nsv + 127) / 128, 2, 1), dim3(128), 0, p->stream, p->d_tvars, 0, p->d_svars, p->nsv, 0, p->dm.Kld,
-                        p->d_tv, p->d_sv, p->sb.delta, p->dm.ntp, p->sb.dstat, p->d_tv_try, p->d_sv_try);
-            p->launches++;
-        }
+        p->launches += 2;
+        launch_retract(p, p->sb.delta, p->sb.dstat);
         launch_error(p, p->d_tv_try, p->d_sv_try, p->d_e2, SC_NEW_ERR);
         CK(cudaMemcpyAsync(p->sb.scal + SC_LIN_ERR, p->sb.scal + SC_COUNT, sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
         st = allreduce_scal(p); if (st != B200_OK) return st;
+        if (G > 1) {
+            // record of this rank: [scalars | status | static step]; gathered over ALL ranks of all groups
+            double* rec = p->d_spec_rec + (size_t)(p->spec_g * T + p->rank) * p->spec_rec;
+            CK(cudaMemcpyAsync(rec, p->sb.scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToDevice, p->stream));
+            CK(cudaMemsetAsync(rec + SC_COUNT, 0, sizeof(double), p->stream));
+            CK(cudaMemcpyAsync(rec + SC_COUNT, p->sb.status, sizeof(int), cudaMemcpyDeviceToDevice, p->stream));
+            if (p->dm.ns) CK(cudaMemcpyAsync(rec + SC_COUNT + 1, p->sb.dstat, sizeof(double) * p->dm.ns, cudaMemcpyDeviceToDevice, p->stream));
+            if (p->spec_ag(p->spec_ctx, p->d_spec_rec, sizeof(double) * p->spec_rec, p->stream)) { set_err("speculation allgather failed"); return B200_NCCL_ERROR; }
+            CK(cudaMemcpyAsync(p->h_spec_rec, p->d_spec_rec, sizeof(double) * p->spec_rec * G * T, cudaMemcpyDeviceToHost, p->stream));
+        }
         if (p->time_phases) CK(cudaEventRecord(p->ev[4], p->stream));
         st = fetch_scalars(p); if (st != B200_OK) return st;
         if (p->time_phases) {
             float ms;
-            if (inner == 1) { cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]); p->phase_ms[0] += ms; }
+            if (inner == 0) { cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]); p->phase_ms[0] += ms; }
             cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]); p->phase_ms[1] += ms;
             cudaEventElapsedTime(&ms, p->ev[3], p->ev[4]); p->phase_ms[2] += ms;
             if (p->P > 1) {
@@ -888,36 +934,48 @@ b200_status b200_lm_iterate(b200_problem* p, b200_lm_state* state) {
             }
             cudaEventElapsedTime(&ms, p->ev[10], p->ev[11]); p->phase_ms[5] += ms; p->phase_ms[6] += 1;
         }
-        const bool solved = host_status(p) == 0;
-        const double oldLin = p->h_scal[SC_LIN_ERR], newLin = p->h_scal[SC_MODEL_ERR], newError = p->h_scal[SC_NEW_ERR];
-        double modelFidelity = 0.0;
-        bool step_ok = false, stop = false;
-        if (solved) {
-            const double linChange = oldLin - newLin;
-            if (L.gauss_newton) step_ok = true;
-            else if (linChange >= 0) {
-                const double costChange = p->err - newError;
-                if (linChange > 2.220446049250313e-16 * oldLin) {
-                    modelFidelity = costChange / linChange;
-                    step_ok = modelFidelity > L.min_model_fidelity;
-                }
-                if (std::fabs(costChange) < L.relative_error_tol * p->err) stop = true;
+        int winner = -1;
+        double win_err = 0.0;
+        for (int h = 0; h < G && !done; h++) {  // the rungs in the order the sequential loop meets them
+            inner++;
+            bool solved; double oldLin, newLin, newError;
+            if (G > 1) {
+                const double* rec = p->h_spec_rec + (size_t)h * T * p->spec_rec;
+                solved = true;
+                for (int t = 0; t < T; t++) if (*reinterpret_cast<const int*>(rec + (size_t)t * p->spec_rec + SC_COUNT) != 0) solved = false;
+                oldLin = rec[SC_LIN_ERR]; newLin = rec[SC_MODEL_ERR]; newError = rec[SC_NEW_ERR];
+            } else {
+                solved = host_status(p) == 0;
+                oldLin = p->h_scal[SC_LIN_ERR]; newLin = p->h_scal[SC_MODEL_ERR]; newError = p->h_scal[SC_NEW_ERR];
             }
-            status = B200_OK;
-        } else status = B200_INDETERMINATE_SYSTEM;
-        if (step_ok) {
+            const TrialVerdict v = judge_trial(L, p->err, solved, oldLin, newLin, newError);
+            status = solved ? B200_OK : B200_INDETERMINATE_SYSTEM;
+            if (v.step_ok) {
+                winner = h; win_err = newError;
+                if (!L.gauss_newton) p->lambda = std::max(L.lambda_lower_bound, p->lambda / L.lambda_factor);
+                p->iterations++; p->total_trials++;
+                p->have_lin = false;
+                status = B200_OK;
+                done = true;
+            } else if (!v.stop) {
+                p->lambda *= L.lambda_factor; p->total_trials++;
+                if (p->lambda >= L.lambda_upper_bound) { status = B200_LAMBDA_MAXED; done = true; }
+                else if (L.gauss_newton) { status = B200_INDETERMINATE_SYSTEM; done = true; }
+            } else done = true;
+        }
+        if (winner >= 0) {
+            if (G > 1) {
+                // every rank adopts the accepted group's step: gather the windows of all groups' steps, retract with the winner's
+                const size_t wdoubles = (size_t)p->Wk * p->dm.ntp;
+                CK(cudaMemcpyAsync(p->d_spec_delta + (size_t)(p->spec_g * T + p->rank) * wdoubles, p->sb.delta + (size_t)p->k_lo * p->dm.ntp,
+                                   sizeof(double) * wdoubles, cudaMemcpyDeviceToDevice, p->stream));
+                if (p->spec_ag(p->spec_ctx, p->d_spec_delta, sizeof(double) * wdoubles, p->stream)) { set_err("speculation allgather failed"); return B200_NCCL_ERROR; }
+                if (winner != p->spec_g)
+                    launch_retract(p, p->d_spec_delta + (size_t)winner * T * wdoubles, p->d_spec_rec + (size_t)winner * T * p->spec_rec + SC_COUNT + 1);
+            }
             std::swap(p->d_tv, p->d_tv_try); std::swap(p->d_sv, p->d_sv_try);
-            p->err = newError;
-            if (!L.gauss_newton) p->lambda = std::max(L.lambda_lower_bound, p->lambda / L.lambda_factor);
-            p->iterations++; p->total_trials++;
-            p->have_lin = false;
-            status = B200_OK;
-            break;
-        } else if (!stop) {
-            p->lambda *= L.lambda_factor; p->total_trials++;
-            if (p->lambda >= L.lambda_upper_bound) { status = B200_LAMBDA_MAXED; break; }
-            if (L.gauss_newton) { status = B200_INDETERMINATE_SYSTEM; break; }
-        } else break;
+            p->err = win_err;
+        }
     }
     if (state) {
         state->error = p->err; state->lambda = p->lambda; state->iterations = p->iterations; state->inner_trials = inner;
@@ -1075,6 +1133,25 @@ b200_status b200_comm_set(b200_problem* p, int32_t world_size, int32_t rank, b20
     CK(cudaSetDevice(p->device));
     p->world = world_size; p->rank = rank; p->ag_fn = ag; p->ar_fn = ar; p->comm_ctx = ctx;
     return set_partition(p, 0, 0);
+}
+
+// lambda speculation: this process belongs to group `group` of `n_groups`; each group is one (possibly sharded) solver
+// instance registered through b200_comm_set BEFORE this call; `allgather` spans all n_groups * world_size ranks, ordered
+// group-major (global rank = group * world_size + rank).
+b200_status b200_spec_set(b200_problem* p, int32_t n_groups, int32_t group, b200_allgather_fn allgather, void* ctx) {
+    if (!p || n_groups < 1 || group < 0 || group >= n_groups || (n_groups > 1 && !allgather)) return B200_BAD_ARG;
+    CK(cudaSetDevice(p->device));
+    if (p->d_spec_delta) { cudaFree(p->d_spec_delta); p->d_spec_delta = nullptr; }
+    if (p->d_spec_rec) { cudaFree(p->d_spec_rec); p->d_spec_rec = nullptr; }
+    if (p->h_spec_rec) { cudaFreeHost(p->h_spec_rec); p->h_spec_rec = nullptr; }
+    p->spec_G = n_groups; p->spec_g = group; p->spec_ag = n_groups > 1 ? allgather : nullptr; p->spec_ctx = ctx;
+    if (n_groups == 1) return B200_OK;
+    const size_t ranks = (size_t)n_groups * p->world;
+    p->spec_rec = (SC_COUNT + 1 + p->dm.ns + 1) & ~1;
+    CK(dalloc(&p->d_spec_delta, ranks * (size_t)p->Wk * p->dm.ntp));
+    CK(dalloc(&p->d_spec_rec, ranks * p->spec_rec));
+    CK(cudaMallocHost((void**)&p->h_spec_rec, ranks * p->spec_rec * sizeof(double)));
+    return B200_OK;
 }
 
 // ------------------------------------------------------------------------------------------ parity / debug accessors

@@ -44,9 +44,14 @@ namespace b200d {
 __device__ unsigned long long g_phase_clk[16];
 #define PH_T0() unsigned long long ph_t_ = clock64()
 #define PH_ADD(i) do { if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1) { unsigned long long n_ = clock64(); g_phase_clk[i] += n_ - ph_t_; ph_t_ = n_; } } while (0)
+// the same from an arbitrary thread t of the last block (worker-warp timelines of the warp-specialised Cholesky)
+#define PHW_T0() unsigned long long phw_t_ = clock64()
+#define PHW_ADD(i, t) do { if (threadIdx.x == (t) && blockIdx.x == gridDim.x - 1) { unsigned long long n_ = clock64(); g_phase_clk[i] += n_ - phw_t_; phw_t_ = n_; } } while (0)
 #else
 #define PH_T0()
 #define PH_ADD(i)
+#define PHW_T0()
+#define PHW_ADD(i, t)
 #endif
 
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
@@ -381,11 +386,14 @@ __device__ int cta_chol_inv(double* Ms, int ld, int n) {
         __syncwarp();   // W_00 (written by lanes 16..31) is read by the whole warp below
         __threadfence_block();
         named_bar_arrive(1, nthr);
+        PHW_T0();
+        PHW_ADD(8, 0);
         for (int s = 0; s + 1 < nb; s++) {
             const int j0 = s * B200_NB, cb0 = j0 + B200_NB;
             const int jb1 = (n - cb0 < B200_NB) ? (n - cb0) : B200_NB;
             const double* Wd = s_Wd2[s & 1];
             if (s >= 1) named_bar_sync(5 + ((s - 1) & 1), nthr);     // trailing update s-1 has reached block row s+1
+            PHW_ADD(11, 0);
             // block (s+1, s) <- block * W_ss^T  (16 rows, lane -> (row ty + 4 i, columns tx, tx + 8))
             double acc[4][2];
             double* xr[4];
@@ -444,6 +452,7 @@ __device__ int cta_chol_inv(double* Ms, int ld, int n) {
             __threadfence_block();
             named_bar_arrive(3 + (s & 1), nthr);                      // block row s+1 of column block s is scaled
             __syncwarp();
+            PHW_ADD(9, 0);
             {
                 const int f = warp_potrf16(Ms + (long long)cb0 * ld + cb0, ld, jb1, Tdiag, invd, s_Wd2[(s + 1) & 1], true);
                 if (f && lane == 0 && fail == 0) fail = cb0 + f;
@@ -451,6 +460,7 @@ __device__ int cta_chol_inv(double* Ms, int ld, int n) {
             __syncwarp();
             __threadfence_block();
             named_bar_arrive(1 + ((s + 1) & 1), nthr);                // W_{s+1} ready
+            PHW_ADD(8, 0);
             if (fail) break;                                          // (uniform: set by lane 0 before the fence)
         }
         // consume the last trailing-update barrier so that every named barrier is back to zero arrivals for the next call
@@ -458,11 +468,13 @@ __device__ int cta_chol_inv(double* Ms, int ld, int n) {
     } else if (!quiet || (warp & 3) != 0) {
         // ------------------------------------------------------------------ worker warps
         const int wk = quiet ? warp - 1 - (warp >> 2) : warp - 1;
+        PHW_T0();
         for (int s = 0; s < nb; s++) {
             const int j0 = s * B200_NB, cb0 = j0 + B200_NB;
             const int jb = (n - j0 < B200_NB) ? (n - j0) : B200_NB;
             const double* Wd = s_Wd2[s & 1];
             named_bar_sync(1 + (s & 1), nthr);                        // W_ss ready (and every worker has finished update s-1)
+            PHW_ADD(12, 32);
             if (fail) break;
             // rows r in [0, j0) U [cb0 + 16, n): X[r][j0 .. j0+jb) <- X * W_ss^T, 16 (virtual) rows per warp, in place
             const int skip = (cb0 < n) ? ((n - cb0 < B200_NB) ? (n - cb0) : B200_NB) : 0;   // block row s+1 belongs to the pivot warp
@@ -504,7 +516,9 @@ __device__ int cta_chol_inv(double* Ms, int ld, int n) {
             }
             if (cb0 >= n) break;
             __threadfence_block();
+            PHW_ADD(13, 32);
             named_bar_sync(3 + (s & 1), nthr);                        // whole column block s scaled (pivot: block row s+1)
+            PHW_ADD(14, 32);
             // trailing update: Ms[r][c] -= sum_t Ms[r][j0+t] Ms[c][j0+t], c >= cb0, alive rows (r >= c or r < cb0),
             // except the diagonal tile (s+1, s+1), which the pivot warp has already updated
             {
@@ -532,6 +546,7 @@ __device__ int cta_chol_inv(double* Ms, int ld, int n) {
             }
             __threadfence_block();
             named_bar_arrive(5 + (s & 1), nthr);                      // trailing update s done
+            PHW_ADD(15, 32);
         }
     }
     __syncthreads();

@@ -39,6 +39,7 @@ def load(path=None):
     for f in ("b200_time_value_dim", "b200_static_value_dim", "b200_time_tangent_dim", "b200_static_tangent_dim", "b200_get_chunks", "b200_get_groups"):
         getattr(L, f).argtypes = [C.c_void_p]
     L.b200_comm_set.argtypes = [C.c_void_p, C.c_int32, C.c_int32, ALLGATHER_FN, ALLREDUCE_FN, C.c_void_p]
+    L.b200_spec_set.argtypes = [C.c_void_p, C.c_int32, C.c_int32, ALLGATHER_FN, C.c_void_p]
     L.b200_get_levels.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32]
     L.b200_debug_get_scalars.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.b200_lower_body_joint_angles.argtypes = [C.c_void_p, C.POINTER(abi.JointAngleDesc), C.c_void_p]
@@ -190,6 +191,11 @@ class Problem:
     def comm_set(self, world, rank, allgather, allreduce):
         self._ag = ALLGATHER_FN(allgather); self._ar = ALLREDUCE_FN(allreduce)
         self._ck(self.L.b200_comm_set(self.h, C.c_int32(world), C.c_int32(rank), self._ag, self._ar, None))
+
+    def spec_set(self, n_groups, group, allgather):
+        """lambda speculation: this process is in group `group` of `n_groups` (call after comm_set)"""
+        self._spec_ag = ALLGATHER_FN(allgather)
+        self._ck(self.L.b200_spec_set(self.h, C.c_int32(n_groups), C.c_int32(group), self._spec_ag, None))
 
 
 def preintegrate(acc, gyro, dt, n_per, bias_hat, noise=None, combined=True, device=0, so_path=None):

@@ -20,9 +20,21 @@ def _view(ptr, nbytes, cuda_device):
     return torch.as_tensor(_Raw(), device=torch.device("cuda", cuda_device))
 
 
-def attach(problem, dist, cuda_device):
-    """register the collectives for `problem` (bioslam_b200.lib.Problem); cuda_device=None for the CPU (gloo) tests"""
-    world, rank = dist.get_world_size(), dist.get_rank()
+def attach(problem, dist, cuda_device, lambda_groups=1):
+    """register the collectives for `problem` (bioslam_b200.lib.Problem); cuda_device=None for the CPU (gloo) tests.
+
+    lambda_groups = G > 1 splits the world into G groups of world/G consecutive ranks: each group is one time-sharded solver
+    and the groups try consecutive rungs of the LM lambda ladder concurrently (b200_spec_set); every rank must call this."""
+    world_all, rank_all = dist.get_world_size(), dist.get_rank()
+    G = int(lambda_groups)
+    if G < 1 or world_all % G:
+        raise ValueError("lambda_groups must divide the world size")
+    world = world_all // G
+    group_idx, rank = divmod(rank_all, world)
+    pg = None
+    if G > 1:
+        pgs = [dist.new_group(list(range(h * world, (h + 1) * world))) for h in range(G)]   # collective: all ranks create all groups
+        pg = pgs[group_idx]
 
     def on_stream(stream_ptr):
         if cuda_device is None:
@@ -30,32 +42,36 @@ def attach(problem, dist, cuda_device):
             return contextlib.nullcontext()
         return torch.cuda.stream(torch.cuda.ExternalStream(stream_ptr or 0, device=torch.device("cuda", cuda_device)))
 
-    def allgather(ctx, buf, bytes_per_rank, stream):
-        try:
-            t = _view(buf, bytes_per_rank * world, cuda_device)
-            n = bytes_per_rank // 8
-            with on_stream(stream):
-                if cuda_device is None:
-                    parts = [torch.empty(n, dtype=torch.float64) for _ in range(world)]
-                    dist.all_gather(parts, t[rank * n:(rank + 1) * n].clone())
-                    for i, pt in enumerate(parts):
-                        t[i * n:(i + 1) * n] = pt
-                else:
-                    dist.all_gather_into_tensor(t, t[rank * n:(rank + 1) * n])
-            return 0
-        except Exception as e:  # noqa: BLE001 -- must not propagate through the C ABI
-            print("bioslam_b200.sharding allgather failed:", e, flush=True)
-            return 1
+    def make_allgather(n_ranks, my_rank, group):
+        def allgather(ctx, buf, bytes_per_rank, stream):
+            try:
+                t = _view(buf, bytes_per_rank * n_ranks, cuda_device)
+                n = bytes_per_rank // 8
+                with on_stream(stream):
+                    if cuda_device is None:
+                        parts = [torch.empty(n, dtype=torch.float64) for _ in range(n_ranks)]
+                        dist.all_gather(parts, t[my_rank * n:(my_rank + 1) * n].clone(), group=group)
+                        for i, pt in enumerate(parts):
+                            t[i * n:(i + 1) * n] = pt
+                    else:
+                        dist.all_gather_into_tensor(t, t[my_rank * n:(my_rank + 1) * n], group=group)
+                return 0
+            except Exception as e:  # noqa: BLE001 -- must not propagate through the C ABI
+                print("bioslam_b200.sharding allgather failed:", e, flush=True)
+                return 1
+        return allgather
 
     def allreduce(ctx, buf, n, stream):
         try:
             t = _view(buf, n * 8, cuda_device)
             with on_stream(stream):
-                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=pg)
             return 0
         except Exception as e:  # noqa: BLE001
             print("bioslam_b200.sharding allreduce failed:", e, flush=True)
             return 1
 
-    problem.comm_set(world, rank, allgather, allreduce)
+    problem.comm_set(world, rank, make_allgather(world, rank, pg), allreduce)
+    if G > 1:
+        problem.spec_set(G, group_idx, make_allgather(world_all, rank_all, None))
     return problem

@@ -301,6 +301,15 @@ typedef int (*b200_allreduce_fn)(void* ctx, double* dev_buf, int32_t n, void* cu
 b200_status b200_comm_set(b200_problem* p, int32_t world_size, int32_t rank, b200_allgather_fn allgather,
                           b200_allreduce_fn allreduce, void* ctx);
 
+/* Lambda speculation (optional, on top of the sharding above).  GTSAM's tryLambda loop (reference seam:
+ * src/lowerBodyPoseEstimator.cpp:659 `optimizer.iterate()`) re-solves the SAME linearization with lambda, 10 lambda, ... until
+ * a step is accepted; the rungs of that ladder are independent of one another.  With n_groups groups of GPUs, group g solves
+ * rung g of the ladder at the same time and the verdicts are then read in ladder order, so the accepted step, the final
+ * lambda and the trial count are exactly those of the sequential loop (bit-identical when world_size == 1).
+ * Call after b200_comm_set (world_size = ranks per group); `allgather` spans all n_groups * world_size ranks in group-major
+ * order (global rank = group * world_size + rank). */
+b200_status b200_spec_set(b200_problem* p, int32_t n_groups, int32_t group, b200_allgather_fn allgather, void* ctx);
+
 /* ---------------------------------------------------------------- parity/debug accessors (used by tests only)
  * External tangent order == variable table order (the library permutes internally). */
 b200_status b200_debug_linearize(b200_problem* p);

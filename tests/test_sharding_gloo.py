@@ -25,13 +25,16 @@ tr = synth.make_trial(seed=3, duration_s=float(sys.argv[4]))
 g, tv, sv = graphs.lower_body_graph(tr)
 tv, sv = graphs.perturbed_truth_values(tr, g, tv, sv)
 p = lib.Problem(g, so_path=EMU)
-sharding.attach(p, dist, None)
+lambda_groups = int(sys.argv[6]) if len(sys.argv) > 6 else 1
+if len(sys.argv) > 7 and sys.argv[7] == "reference_init":
+    g, tv, sv = graphs.lower_body_graph(tr)      # the reference's initial values: the first iterations reject lambda trials
+sharding.attach(p, dist, None, lambda_groups=lambda_groups)
 p.set_values(tv, sv)
 out = {"chunks": p.chunks, "groups": p.groups}
 e0 = p.lm_begin(abi.LmParams.lower_body())
 trace = []
 err_before = e0
-for _ in range(3):
+for _ in range(int(os.environ.get("B200_TEST_ITERS", "3"))):
     st = p.lm_iterate()
     # linear.error(0) summed over the ranks must be the cost at the linearization point: every factor counted exactly once
     # (a rank also linearizes the keyframe left of its window; its factors belong to the neighbour's cost)
@@ -45,11 +48,11 @@ dist.destroy_process_group()
 '''
 
 
-def run_world(world, seconds, tmp_path, port):
+def run_world(world, seconds, tmp_path, port, extra=(), tag=""):
     script = tmp_path / "worker.py"
     script.write_text(WORKER % {"root": ROOT, "here": HERE})
-    prefix = str(tmp_path / f"w{world}")
-    procs = [subprocess.Popen([sys.executable, str(script), str(r), str(world), str(port), str(seconds), prefix]) for r in range(world)]
+    prefix = str(tmp_path / f"w{world}{tag}")
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), str(world), str(port), str(seconds), prefix, *extra]) for r in range(world)]
     for pr in procs:
         assert pr.wait(timeout=600) == 0
     return [np.load(prefix + f".rank{r}.npz") for r in range(world)]
@@ -79,3 +82,22 @@ def test_sharded_lm_matches_single_rank_and_oracle(world, tmp_path, oracle_lib):
         st = o.lm_iterate()
         assert st.inner_trials == int(row[2]) and st.iterations == int(row[3])
         assert abs(st.error - row[0]) <= 5e-3 * st.error
+
+
+@pytest.mark.parametrize("world,groups", [(2, 2), (4, 2)])
+def test_lambda_speculation_equals_sequential_ladder(world, groups, tmp_path):
+    """G groups try consecutive rungs of the lambda ladder at once: accepted steps, lambda and trial counts must be those of the
+    sequential tryLambda loop run by ONE group (bit-identical: same kernels, same inputs), from the reference's initial values
+    where trials are rejected."""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "cudaemu")])
+    seconds = 3.0
+    os.environ["B200_TEST_ITERS"] = "4"
+    try:
+        spec = run_world(world, seconds, tmp_path, 29600 + world, extra=(str(groups), "reference_init"), tag="spec")
+        seq = run_world(world // groups, seconds, tmp_path, 29650 + world, extra=("1", "reference_init"), tag="seq")
+    finally:
+        del os.environ["B200_TEST_ITERS"]
+    assert any(int(row[2]) > 1 for row in seq[0]["trace"]), "test needs rejected trials"
+    for o in spec:
+        assert np.array_equal(o["trace"], seq[0]["trace"])
+        assert np.array_equal(o["tv"], seq[0]["tv"]) and np.array_equal(o["sv"], seq[0]["sv"])

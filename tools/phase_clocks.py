@@ -21,5 +21,6 @@ tot = sum(out[:7])
 print("K", g.K, "chunks", p.chunks, "last-block cycles per phase (one solve; includes the top-level kernel):")
 for n, v in zip(names, out[:7]):
     print("  %-14s %10d  %5.1f%%" % (n, v, 100.0 * v / max(tot, 1)))
-for n, i in (("chol:potrf16+inv(warp0)", 8), ("chol:panel scale", 9), ("chol:trailing", 10)):
-    print("  %-20s %10d  %5.1f%%" % (n, out[i], 100.0 * out[i] / max(tot, 1)))
+for n, i in (("chol:whole phase", 10), ("pivot:potrf16+inv", 8), ("pivot:scale row+diag tile", 9), ("pivot:wait trailing", 11),
+             ("worker1:wait W", 12), ("worker1:scale column", 13), ("worker1:wait row", 14), ("worker1:trailing", 15)):
+    print("  %-26s %10d  %5.1f%%" % (n, out[i], 100.0 * out[i] / max(tot, 1)))
