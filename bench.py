@@ -150,9 +150,13 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device: bioslam_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dist = None
+    json_fd = 1
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+        # NCCL prints its version banner on the process's stdout (fd 1): keep fd 1 for the ONE JSON line of rank 0 and send
+        # everything else that native code prints to stderr
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib.load()
@@ -268,7 +272,8 @@ def run_b200(args):
         line["time_to_converge"] = ttc
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, K)
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
 

@@ -705,10 +705,9 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
     double* Op = Yb + (long long)CR * ld;
     const int kz0 = nl & ~1;                        // first column of z that is needed (chain columns, pair aligned)
     // structure tables of O in shared memory (they are consulted at the start of every GEMM phase: keep them off the L2 path)
-    __shared__ int s_orow[2 * 256], s_ozs[256], s_ogrp[3 * 256];
+    __shared__ int s_orow[2 * 256], s_ozs[256];
     for (int e = threadIdx.x; e < 2 * nc; e += blockDim.x) s_orow[e] = dm.orow[e];
     for (int e = threadIdx.x; e < nc; e += blockDim.x) s_ozs[e] = dm.ozs[e];
-    for (int e = threadIdx.x; e < 3 * dm.n_ogrp; e += blockDim.x) s_ogrp[e] = dm.ogrp[e];
     __syncthreads();
     for (int i = 0; i < a.n; i++) {
         const long long src = a.src0 + i;
@@ -1052,47 +1051,47 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                         __syncthreads();
                     }
                 } else {
-                    // block-sparse coupling: thread tile 4 rows x (group of <= 4 rows of O sharing the packed window), t in pairs
-                    // (consecutive lanes own consecutive columns of the same rows: the stores of a warp fall into few sectors)
-                    // lane order: 8 consecutive row groups (consecutive rows: conflict-free z loads, the O operand is a broadcast),
-                    // then the column groups (the stores of a warp cover 4 column groups x 8 rows = 8 sectors)
-                    const int nrg = (cr + 3) >> 2;
-                    const int total = 8 * dm.n_ogrp * ((nrg + 7) >> 3);
-                    for (int T = threadIdx.x; T < total; T += blockDim.x) {
-                        const int cg = (T >> 3) % dm.n_ogrp, rg = (T & 7) + 8 * ((T >> 3) / dm.n_ogrp);
-                        if (rg >= nrg) continue;
-                        const int i0 = s_ogrp[3 * cg], cstr = s_ogrp[3 * cg + 1], ncol = s_ogrp[3 * cg + 2];
-                        const int zs = s_ozs[i0];
-                        const double* zp[4];
-                        const double* op[4];
+                    // block-sparse coupling on the tensor cores: a warp task = 16 panel rows x 8 fill columns (= 8 rows of O).  The
+                    // contraction runs over the union of the packed windows of those 8 rows of O (<= 2 IMU blocks for the time
+                    // chain); an entry of O outside its row's window is structurally zero and is supplied as 0.
+                    const int ncb = (nc + 7) >> 3;
+                    for (int task = warp; task < rtiles * ncb; task += nwarps) {
+                        const int rt = task % rtiles, cbk = task / rtiles;
+                        const int m0 = rt << 4;
+                        const int ci = (cbk << 3) + mg;                 // this lane's B column = row of O
+                        const bool cval = ci < nc;
+                        const int zs = cval ? s_ozs[ci] : n;
+                        int kw0 = zs, kw1 = cval ? zs + ow : 0;
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            int lr = rg + nrg * q; if (lr > cr - 1) lr = cr - 1;
-                            const int ci = i0 + cstr * (q < ncol ? q : ncol - 1);
-                            zp[q] = Yb + (long long)lr * ld + zs;
-                            op[q] = Op + ci * owp;
+                        for (int o = 4; o <= 16; o <<= 1) {
+                            const int lo2 = __shfl_xor_sync(0xffffffffu, kw0, o), hi2 = __shfl_xor_sync(0xffffffffu, kw1, o);
+                            kw0 = lo2 < kw0 ? lo2 : kw0; kw1 = hi2 > kw1 ? hi2 : kw1;
                         }
-                        double acc[4][4];
+                        if (kw1 > n) kw1 = n;
+                        const double* ap[2];
 #pragma unroll
-                        for (int q = 0; q < 4; q++)
+                        for (int q = 0; q < 2; q++) { int lr = m0 + 8 * q + mg; if (lr > cr - 1) lr = cr - 1; ap[q] = Yb + (long long)lr * ld + mt; }
+                        const double* bp = Op + (cval ? ci : 0) * owp;
+                        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+                        for (int k = kw0; k < kw1; k += 4) {
+                            const int kk = k + mt, idx = kk - zs;
+                            const bool ok = kk < kw1;
+                            const double bv = (cval && idx >= 0 && idx < ow) ? bp[idx] : 0.0;
+                            double av[2];
 #pragma unroll
-                            for (int j = 0; j < 4; j++) acc[q][j] = 0.0;
-                        for (int t = 0; t < ow; t += 2) {
-                            double2 av[4], bv[4];
+                            for (int q = 0; q < 2; q++) av[q] = ok ? ap[q][k] : 0.0;
 #pragma unroll
-                            for (int q = 0; q < 4; q++) { av[q] = ld2(zp[q] + t); bv[q] = ld2(op[q] + t); }
-#pragma unroll
-                            for (int q = 0; q < 4; q++)
-#pragma unroll
-                                for (int j = 0; j < 4; j++) acc[q][j] = fma(av[q].y, bv[j].y, fma(av[q].x, bv[j].x, acc[q][j]));
+                            for (int q = 0; q < 2; q++) dmma884(acc[q][0], acc[q][1], av[q], bv);
                         }
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const int lr = rg + nrg * q;
+                        for (int q = 0; q < 2; q++) {
+                            const int lr = m0 + 8 * q + mg;
                             if (lr >= cr) continue;
 #pragma unroll
-                            for (int j = 0; j < 4; j++)
-                                if (j < ncol) Fout[(long long)(r0 + lr) * nc + i0 + cstr * j] = acc[q][j];
+                            for (int e = 0; e < 2; e++) {
+                                const int co = (cbk << 3) + 2 * mt + e;
+                                if (co < nc) Fout[(long long)(r0 + lr) * nc + co] = acc[q][e];
+                            }
                         }
                     }
                 }

@@ -90,8 +90,8 @@ def test_lambda_speculation_equals_sequential_ladder(world, groups, tmp_path):
     sequential tryLambda loop run by ONE group (bit-identical: same kernels, same inputs), from the reference's initial values
     where trials are rejected."""
     subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "cudaemu")])
-    seconds = 3.0
-    os.environ["B200_TEST_ITERS"] = "4"
+    seconds = 2.0
+    os.environ["B200_TEST_ITERS"] = "3"
     try:
         spec = run_world(world, seconds, tmp_path, 29600 + world, extra=(str(groups), "reference_init"), tag="spec")
         seq = run_world(world // groups, seconds, tmp_path, 29650 + world, extra=("1", "reference_init"), tag="seq")
