@@ -367,7 +367,6 @@ __device__ int cta_chol_inv(double* Ms, int ld, int n) {
     double *Tdiag, *Wd0, *invd;
     solve_scratch(Tdiag, Wd0, invd);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int ty = lane >> 3, tx = lane & 7;
     const int mg = lane >> 2, mt = lane & 3;   // MMA fragment coordinates
     const int nb = (n + B200_NB - 1) / B200_NB;
     // the pivot warp's chain is latency-bound: the warps that share its scheduler (warp & 3 == 0) stay out of the way
@@ -394,55 +393,59 @@ __device__ int cta_chol_inv(double* Ms, int ld, int n) {
             const double* Wd = s_Wd2[s & 1];
             if (s >= 1) named_bar_sync(5 + ((s - 1) & 1), nthr);     // trailing update s-1 has reached block row s+1
             PHW_ADD(11, 0);
-            // block (s+1, s) <- block * W_ss^T  (16 rows, lane -> (row ty + 4 i, columns tx, tx + 8))
-            double acc[4][2];
-            double* xr[4];
+            // block (s+1, s) <- block * W_ss^T  (16 x 16 x 16 on the tensor cores: 2 x 2 MMA blocks, 4 contraction steps)
+            const double* xa[2];
+            bool rok[2];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                int r = cb0 + ty + 4 * i; if (r > n - 1) r = n - 1;
-                xr[i] = Ms + (long long)r * ld + j0;
-                acc[i][0] = 0.0; acc[i][1] = 0.0;
+            for (int i = 0; i < 2; i++) {
+                int r = cb0 + 8 * i + mg; rok[i] = r < n; if (r > n - 1) r = n - 1;
+                xa[i] = Ms + (long long)r * ld + j0;
             }
+            {
+                double sacc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
 #pragma unroll
-            for (int c2 = 0; c2 < B200_NB; c2 += 2) {
-                const double2 b0 = ld2(Wd + tx * B200_WLD + c2), b1 = ld2(Wd + (tx + 8) * B200_WLD + c2);
+                for (int k = 0; k < B200_NB; k += 4) {
+                    double av[2], bv[2];
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const double2 av = ld2(xr[i] + c2);
-                    acc[i][0] = fma(av.y, b0.y, fma(av.x, b0.x, acc[i][0]));
-                    acc[i][1] = fma(av.y, b1.y, fma(av.x, b1.x, acc[i][1]));
+                    for (int i = 0; i < 2; i++) { av[i] = xa[i][k + mt]; bv[i] = Wd[(8 * i + mg) * B200_WLD + k + mt]; }
+#pragma unroll
+                    for (int i = 0; i < 2; i++)
+#pragma unroll
+                        for (int j = 0; j < 2; j++) dmma884(sacc[i][j][0], sacc[i][j][1], av[i], bv[j]);
                 }
-            }
-            __syncwarp();
+                __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                if (cb0 + ty + 4 * i < n) { xr[i][tx] = acc[i][0]; xr[i][tx + 8] = acc[i][1]; }
+                for (int i = 0; i < 2; i++)
+#pragma unroll
+                    for (int j = 0; j < 2; j++)
+                        if (rok[i]) st2(const_cast<double*>(xa[i]) + 8 * j + 2 * mt, sacc[i][j][0], sacc[i][j][1]);
             }
             __syncwarp();
             // diagonal tile (s+1, s+1), lower part: -= L L^T with the block just scaled
             {
-                const double* bp[2];
+                const double* xb[2];
 #pragma unroll
-                for (int j = 0; j < 2; j++) { int c = cb0 + tx + 8 * j; if (c > n - 1) c = n - 1; bp[j] = Ms + (long long)c * ld + j0; }
+                for (int j = 0; j < 2; j++) { int c = cb0 + 8 * j + mg; if (c > n - 1) c = n - 1; xb[j] = Ms + (long long)c * ld + j0; }
+                double dacc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
 #pragma unroll
-                for (int i = 0; i < 4; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+                for (int k = 0; k < B200_NB; k += 4) {
+                    double av[2], bv[2];
 #pragma unroll
-                for (int c2 = 0; c2 < B200_NB; c2 += 2) {
-                    const double2 b0 = ld2(bp[0] + c2), b1 = ld2(bp[1] + c2);
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const double2 av = ld2(xr[i] + c2);
-                        acc[i][0] = fma(av.y, b0.y, fma(av.x, b0.x, acc[i][0]));
-                        acc[i][1] = fma(av.y, b1.y, fma(av.x, b1.x, acc[i][1]));
-                    }
+                    for (int i = 0; i < 2; i++) { av[i] = xa[i][k + mt]; bv[i] = xb[i][k + mt]; }
+                    dmma884(dacc[0][0][0], dacc[0][0][1], av[0], bv[0]);
+                    dmma884(dacc[1][0][0], dacc[1][0][1], av[1], bv[0]);
+                    dmma884(dacc[1][1][0], dacc[1][1][1], av[1], bv[1]);
                 }
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int r = cb0 + ty + 4 * i;
+                for (int i = 0; i < 2; i++) {
+                    const int r = cb0 + 8 * i + mg;
 #pragma unroll
-                    for (int j = 0; j < 2; j++) {
-                        const int c = cb0 + tx + 8 * j;
-                        if (r < n && c <= r) Ms[(long long)r * ld + c] -= acc[i][j];
+                    for (int j = 0; j <= i; j++) {
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const int c = cb0 + 8 * j + 2 * mt + e;
+                            if (r < n && c <= r) Ms[(long long)r * ld + c] -= dacc[i][j][e];
+                        }
                     }
                 }
             }
@@ -480,38 +483,38 @@ __device__ int cta_chol_inv(double* Ms, int ld, int n) {
             const int skip = (cb0 < n) ? ((n - cb0 < B200_NB) ? (n - cb0) : B200_NB) : 0;   // block row s+1 belongs to the pivot warp
             const int nvr = n - jb - skip;
             for (int t = wk; t * 16 < nvr; t += nwk) {
-                const double* ap[4];
-                bool ok[4];
+                const double* ap[2];
+                bool ok[2];
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    int vr = t * 16 + ty + 4 * i;
+                for (int i = 0; i < 2; i++) {
+                    int vr = t * 16 + 8 * i + mg;
                     ok[i] = vr < nvr;
                     if (!ok[i]) vr = nvr - 1;
                     const int r = (vr < j0) ? vr : vr + jb + skip;
                     ap[i] = Ms + (long long)r * ld + j0;
                 }
-                double acc[4][2];
+                double sacc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
 #pragma unroll
-                for (int i = 0; i < 4; i++) { acc[i][0] = 0.0; acc[i][1] = 0.0; }
+                for (int k = 0; k < B200_NB; k += 4) {
+                    const bool kin = j0 + k + mt < n;
+                    double av[2], bv[2];
 #pragma unroll
-                for (int c2 = 0; c2 < B200_NB; c2 += 2) {
-                    if (j0 + c2 < n) {
-                        const double2 b0 = ld2(Wd + tx * B200_WLD + c2), b1 = ld2(Wd + (tx + 8) * B200_WLD + c2);
+                    for (int i = 0; i < 2; i++) { av[i] = kin ? ap[i][k + mt] : 0.0; bv[i] = kin ? Wd[(8 * i + mg) * B200_WLD + k + mt] : 0.0; }
 #pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            const double2 av = ld2(ap[i] + c2);
-                            acc[i][0] = fma(av.y, b0.y, fma(av.x, b0.x, acc[i][0]));
-                            acc[i][1] = fma(av.y, b1.y, fma(av.x, b1.x, acc[i][1]));
-                        }
-                    }
+                    for (int i = 0; i < 2; i++)
+#pragma unroll
+                        for (int j = 0; j < 2; j++) dmma884(sacc[i][j][0], sacc[i][j][1], av[i], bv[j]);
                 }
                 __syncwarp();
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
+                for (int i = 0; i < 2; i++) {
                     if (!ok[i]) continue;
                     double* xw = const_cast<double*>(ap[i]);
-                    if (tx < jb) xw[tx] = acc[i][0];
-                    if (tx + 8 < jb) xw[tx + 8] = acc[i][1];
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        const int c = 8 * j + 2 * mt;
+                        if (c < jb) st2(xw + c, sacc[i][j][0], sacc[i][j][1]);   // jb is even: a pair is inside or outside
+                    }
                 }
             }
             if (cb0 >= n) break;
@@ -1051,46 +1054,60 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                         __syncthreads();
                     }
                 } else {
-                    // block-sparse coupling on the tensor cores: a warp task = 16 panel rows x 8 fill columns (= 8 rows of O).  The
-                    // contraction runs over the union of the packed windows of those 8 rows of O (<= 2 IMU blocks for the time
-                    // chain); an entry of O outside its row's window is structurally zero and is supplied as 0.
-                    const int ncb = (nc + 7) >> 3;
-                    for (int task = warp; task < rtiles * ncb; task += nwarps) {
-                        const int rt = task % rtiles, cbk = task / rtiles;
+                    // block-sparse coupling on the tensor cores: a warp task = 16 panel rows x 32 fill columns = four 8-column
+                    // blocks (8 rows of O each).  Every block contracts over the union of the packed windows of its 8 rows of O
+                    // (<= 2 IMU blocks for the time chain; an entry of O outside its row's window is structurally zero and is
+                    // supplied as 0); the four blocks advance in lockstep so that 8 independent accumulators are in flight.
+                    const int ncq = (nc + 31) >> 5;
+                    for (int task = warp; task < rtiles * ncq; task += nwarps) {
+                        const int rt = task % rtiles, cq = task / rtiles;
                         const int m0 = rt << 4;
-                        const int ci = (cbk << 3) + mg;                 // this lane's B column = row of O
-                        const bool cval = ci < nc;
-                        const int zs = cval ? s_ozs[ci] : n;
-                        int kw0 = zs, kw1 = cval ? zs + ow : 0;
+                        int zs[4], kw0[4], nst = 0;
+                        bool cval[4];
+                        const double* bp[4];
 #pragma unroll
-                        for (int o = 4; o <= 16; o <<= 1) {
-                            const int lo2 = __shfl_xor_sync(0xffffffffu, kw0, o), hi2 = __shfl_xor_sync(0xffffffffu, kw1, o);
-                            kw0 = lo2 < kw0 ? lo2 : kw0; kw1 = hi2 > kw1 ? hi2 : kw1;
+                        for (int j = 0; j < 4; j++) {
+                            const int ci = (cq << 5) + (j << 3) + mg;     // this lane's B column of block j = row of O
+                            cval[j] = ci < nc;
+                            zs[j] = cval[j] ? s_ozs[ci] : n;
+                            int lo = zs[j], hi = cval[j] ? zs[j] + ow : 0;
+#pragma unroll
+                            for (int o = 4; o <= 16; o <<= 1) {
+                                const int lo2 = __shfl_xor_sync(0xffffffffu, lo, o), hi2 = __shfl_xor_sync(0xffffffffu, hi, o);
+                                lo = lo2 < lo ? lo2 : lo; hi = hi2 > hi ? hi2 : hi;
+                            }
+                            if (hi > n) hi = n;
+                            kw0[j] = lo;
+                            const int steps = hi > lo ? (hi - lo + 3) >> 2 : 0;
+                            nst = steps > nst ? steps : nst;
+                            bp[j] = Op + (cval[j] ? ci : 0) * owp;
                         }
-                        if (kw1 > n) kw1 = n;
                         const double* ap[2];
 #pragma unroll
-                        for (int q = 0; q < 2; q++) { int lr = m0 + 8 * q + mg; if (lr > cr - 1) lr = cr - 1; ap[q] = Yb + (long long)lr * ld + mt; }
-                        const double* bp = Op + (cval ? ci : 0) * owp;
-                        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-                        for (int k = kw0; k < kw1; k += 4) {
-                            const int kk = k + mt, idx = kk - zs;
-                            const bool ok = kk < kw1;
-                            const double bv = (cval && idx >= 0 && idx < ow) ? bp[idx] : 0.0;
-                            double av[2];
+                        for (int q = 0; q < 2; q++) { int lr = m0 + 8 * q + mg; if (lr > cr - 1) lr = cr - 1; ap[q] = Yb + (long long)lr * ld; }
+                        Acc acc;
+                        acc_zero(acc);
+                        for (int sidx = 0; sidx < nst; sidx++) {
 #pragma unroll
-                            for (int q = 0; q < 2; q++) av[q] = ok ? ap[q][k] : 0.0;
+                            for (int j = 0; j < 4; j++) {
+                                const int kk = kw0[j] + 4 * sidx + mt, idx = kk - zs[j];
+                                const bool ok = kk < n;
+                                const double bv = (cval[j] && idx >= 0 && idx < ow) ? bp[j][idx] : 0.0;
 #pragma unroll
-                            for (int q = 0; q < 2; q++) dmma884(acc[q][0], acc[q][1], av[q], bv);
+                                for (int q = 0; q < 2; q++) dmma884(acc[q][j][0], acc[q][j][1], ok ? ap[q][kk] : 0.0, bv);
+                            }
                         }
 #pragma unroll
                         for (int q = 0; q < 2; q++) {
                             const int lr = m0 + 8 * q + mg;
                             if (lr >= cr) continue;
 #pragma unroll
-                            for (int e = 0; e < 2; e++) {
-                                const int co = (cbk << 3) + 2 * mt + e;
-                                if (co < nc) Fout[(long long)(r0 + lr) * nc + co] = acc[q][e];
+                            for (int j = 0; j < 4; j++) {
+#pragma unroll
+                                for (int e = 0; e < 2; e++) {
+                                    const int co = (cq << 5) + (j << 3) + 2 * mt + e;
+                                    if (co < nc) Fout[(long long)(r0 + lr) * nc + co] = acc[q][j][e];
+                                }
                             }
                         }
                     }
