@@ -789,98 +789,141 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                 if (a.lead) st2(Wg + (long long)r * n + c, v.x, v.y);
             }
         PH_ADD(2);
-        // ---------------- phase B: panel rows [X (nc, if has_x) ; arrow (h)] in chunks of <= CR rows
+        // ---------------- phase B: panel rows [X (nc, if has_x) ; arrow (h)] in chunks of <= CRg rows.
+        // Block-sparse levels: the 16 warps form TWO groups of 8 that work through alternate chunks independently, each in its
+        // own half of the panel buffer and with its own named barrier (ids 7, 8): one group's load / barrier / epilogue phases
+        // overlap the other group's MMA phases.  Dense levels: one group of all warps (the O slabs stream through a shared buffer).
         const int xo = has_x ? nc : 0;
-        for (int seg = 0; seg < 2; seg++) {
-            const int base = seg == 0 ? 0 : xo + a.ar_lo, cnt = seg == 0 ? xo : a.ar_hi - a.ar_lo;
-            if (cnt == 0) continue;
-            const int nch = (cnt + CR - 1) / CR;
+        const int ngroups = (!a.dense_o && (nwarps & 1) == 0 && ((CR >> 1) & ~15) >= 16) ? 2 : 1;
+        const int gnw = nwarps / ngroups, gid = warp / gnw, gw = warp - gid * gnw;
+        const int gthreads = gnw << 5, gtid = threadIdx.x - gid * gthreads;
+        const int CRg = ngroups == 2 ? ((CR >> 1) & ~15) : CR;
+        double* Ybg = Yb + (long long)gid * CRg * ld;
+#define BSYNC() do { if (ngroups == 1) __syncthreads(); else named_bar_sync(7 + gid, gthreads); } while (0)
+        const int cnt0 = xo, cnt1 = a.ar_hi - a.ar_lo;
+        const int nch0 = (cnt0 + CRg - 1) / CRg, nch1 = (cnt1 + CRg - 1) / CRg;
+        for (int qch = gid; qch < nch0 + nch1; qch += ngroups) {
+            const int seg = qch < nch0 ? 0 : 1, ch = seg ? qch - nch0 : qch;
+            const int base = seg == 0 ? 0 : xo + a.ar_lo, cnt = seg == 0 ? cnt0 : cnt1, nch = seg == 0 ? nch0 : nch1;
             int csz = (cnt + nch - 1) / nch;
             csz = (csz + 15) & ~15;
-            for (int ch = 0; ch < nch; ch++) {
-                const int r0 = base + ch * csz;
-                const int cr = (base + cnt - r0 < csz) ? (base + cnt - r0) : csz;
-                __syncthreads();   // Yb free
-                // ---- load rows (one warp per row): sources through cp.async; the fill rows of the previous node are fetched
-                // into registers before the wait (their L2 latency overlaps the copies) and applied afterwards
-                for (int lr = warp; lr < cr; lr += nwarps) {
-                    const int pr = r0 + lr;
-                    double* dst = Yb + (long long)lr * ld;
-                    if (seg == 0) {
-                        const double* og = Og + (long long)pr * nc - nl;
-                        for (int c = lane; c < n; c += 32) {
-                            if (c >= nl) cp_async8(dst + c, og + c);
-                            else dst[c] = 0.0;
-                        }
-                    } else {
-                        const int ar = pr - xo;
-                        if (ar < ns1) {
-                            const double* ag = Ag + (long long)ar * n;
-                            for (int c = 2 * lane; c < n; c += 64) cp_async16(dst + c, ag + c);
-                        } else if (i == 0 && a.Oleft) {
-                            const double* ol = a.Oleft + (ar - ns1);
-                            for (int c = lane; c < n; c += 32) dst[c] = (c >= nl) ? ol[(long long)(c - nl) * nc] : 0.0;
-                        } else {
-                            for (int c = lane; c < nl; c += 32) dst[c] = 0.0;
-                            if (i == 0) for (int c = nl + lane; c < n; c += 32) dst[c] = 0.0;
-                        }
-                    }
-                }
-                if (seg == 1 && i > 0) {
-                    const int ar0 = r0 - xo;
-                    for (int rb = 0; rb < cr; rb += 4 * nwarps) {
-                        for (int cb = 0; cb < nc; cb += 128) {
-                            double f[4][4];
-#pragma unroll
-                            for (int q = 0; q < 4; q++) {
-                                const int lr = rb + warp + q * nwarps;
-#pragma unroll
-                                for (int u = 0; u < 4; u++) {
-                                    const int c = cb + lane + 32 * u;
-                                    f[q][u] = (lr < cr && c < nc) ? Fin[(long long)(nc + ar0 + lr) * nc + c] : 0.0;
-                                }
-                            }
-                            if (rb == 0 && cb == 0) { cp_async_wait_all(); __syncthreads(); }
-#pragma unroll
-                            for (int q = 0; q < 4; q++) {
-                                const int lr = rb + warp + q * nwarps;
-                                if (lr >= cr) continue;
-                                double* dr = Yb + (long long)lr * ld + nl;
-                                const bool src_row = (ar0 + lr) < ns1;   // static / rhs rows start from A, left rows from zero
-#pragma unroll
-                                for (int u = 0; u < 4; u++) {
-                                    const int c = cb + lane + 32 * u;
-                                    if (c < nc) dr[c] = (src_row ? dr[c] : 0.0) - f[q][u];
-                                }
-                            }
-                        }
+            const int r0 = base + ch * csz;
+            const int cr = (base + cnt - r0 < csz) ? (base + cnt - r0) : csz;
+            BSYNC();   // Ybg free
+            // ---- load rows (one gw per row): sources through cp.async; the fill rows of the previous node are fetched
+            // into registers before the wait (their L2 latency overlaps the copies) and applied afterwards
+            for (int lr = gw; lr < cr; lr += gnw) {
+                const int pr = r0 + lr;
+                double* dst = Ybg + (long long)lr * ld;
+                if (seg == 0) {
+                    const double* og = Og + (long long)pr * nc - nl;
+                    for (int c = lane; c < n; c += 32) {
+                        if (c >= nl) cp_async8(dst + c, og + c);
+                        else dst[c] = 0.0;
                     }
                 } else {
-                    cp_async_wait_all();
+                    const int ar = pr - xo;
+                    if (ar < ns1) {
+                        const double* ag = Ag + (long long)ar * n;
+                        for (int c = 2 * lane; c < n; c += 64) cp_async16(dst + c, ag + c);
+                    } else if (i == 0 && a.Oleft) {
+                        const double* ol = a.Oleft + (ar - ns1);
+                        for (int c = lane; c < n; c += 32) dst[c] = (c >= nl) ? ol[(long long)(c - nl) * nc] : 0.0;
+                    } else {
+                        for (int c = lane; c < nl; c += 32) dst[c] = 0.0;
+                        if (i == 0) for (int c = nl + lane; c < n; c += 32) dst[c] = 0.0;
+                    }
                 }
-                __syncthreads();
-                PH_ADD(3);
-                const int rtiles = (cr + 15) >> 4;
-                const int tpw = nwarps / rtiles;              // column tiles per wave (rtiles <= CR/16 <= nwarps)
-                // ---- y = p W^T, results written back in place after a barrier.  Balanced scheme (one wave): every warp of a row
-                // group owns the 16-column blocks s and nb-1-s (short + long contraction); else column-tile waves from the right.
-                const int nb16 = (n + 15) >> 4, npair = (nb16 + 1) >> 1;
-                if (npair <= tpw) {
-                    const int slot = warp % tpw, rt = warp / tpw;
-                    const bool act = rt < rtiles && slot < npair;
-                    const int bA = slot, bB = nb16 - 1 - slot;   // bA <= bB ; equal: the middle block of an odd count
+            }
+            if (seg == 1 && i > 0) {
+                const int ar0 = r0 - xo;
+                for (int rb = 0; rb < cr; rb += 4 * gnw) {
+                    for (int cb = 0; cb < nc; cb += 128) {
+                        double f[4][4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int lr = rb + gw + q * gnw;
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const int c = cb + lane + 32 * u;
+                                f[q][u] = (lr < cr && c < nc) ? Fin[(long long)(nc + ar0 + lr) * nc + c] : 0.0;
+                            }
+                        }
+                        if (rb == 0 && cb == 0) { cp_async_wait_all(); BSYNC(); }
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int lr = rb + gw + q * gnw;
+                            if (lr >= cr) continue;
+                            double* dr = Ybg + (long long)lr * ld + nl;
+                            const bool src_row = (ar0 + lr) < ns1;   // static / rhs rows start from A, left rows from zero
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const int c = cb + lane + 32 * u;
+                                if (c < nc) dr[c] = (src_row ? dr[c] : 0.0) - f[q][u];
+                            }
+                        }
+                    }
+                }
+            } else {
+                cp_async_wait_all();
+            }
+            BSYNC();
+            PH_ADD(3);
+            const int rtiles = (cr + 15) >> 4;
+            const int tpw = gnw / rtiles;              // column tiles per wave (rtiles <= CRg/16 <= gnw)
+            // ---- y = p W^T, results written back in place after a barrier.  Balanced scheme (one wave): every gw of a row
+            // group owns the 16-column blocks s and nb-1-s (short + long contraction); else column-tile waves from the right.
+            const int nb16 = (n + 15) >> 4, npair = (nb16 + 1) >> 1;
+            if (npair <= tpw) {
+                const int slot = gw % tpw, rt = gw / tpw;
+                const bool act = rt < rtiles && slot < npair;
+                const int bA = slot, bB = nb16 - 1 - slot;   // bA <= bB ; equal: the middle block of an odd count
+                Acc acc;
+                acc_zero(acc);
+                const int m0 = rt << 4;
+                if (act) {
+                    int ka = 0, kb = n;
+                    if (seg == 0) xrow_range(dm, s_orow, a.dense_o != 0, r0 + m0, ka, kb);
+                    int kendA = (bA << 4) + 16; if (kendA > kb) kendA = kb;
+                    int kendB = (bB << 4) + 16; if (kendB > kb) kendB = kb;
+                    if (bA == bB) kendA = ka;   // single block: only the B half is used
+                    warp_mma_nn2(Ybg, ld, m0, cr, Ms, ld, bA << 4, bB << 4, n, ka, kendA, kendB, acc);
+                }
+                BSYNC();
+                if (act) {
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        const int lr = m0 + 8 * q + mg;
+                        if (lr >= cr) continue;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            if (j < 2 && bA == bB) continue;
+                            const int c = ((j < 2 ? bA : bB) << 4) + 8 * (j & 1) + 2 * mt;
+                            if (c >= n) continue;
+                            st2(Ybg + (long long)lr * ld + c, acc[q][j][0], acc[q][j][1]);
+                            if (seg == 1) st2(Yg + (long long)(r0 - xo + lr) * n + c, acc[q][j][0], acc[q][j][1]);
+                        }
+                    }
+                }
+                BSYNC();
+            } else {
+                const int nct = (n + 31) >> 5;
+                for (int hi = nct; hi > 0; hi -= tpw) {
+                    const int lo = hi - tpw > 0 ? hi - tpw : 0;
+                    const int slot = gw % tpw, rt = gw / tpw;
+                    // spread long and short column tiles over the four schedulers (gw & 3)
+                    const int ct = lo + (slot + rt) % tpw;
+                    const bool act = rt < rtiles && ct < hi;
                     Acc acc;
                     acc_zero(acc);
-                    const int m0 = rt << 4;
+                    const int m0 = rt << 4, c0 = ct << 5;
                     if (act) {
                         int ka = 0, kb = n;
                         if (seg == 0) xrow_range(dm, s_orow, a.dense_o != 0, r0 + m0, ka, kb);
-                        int kendA = (bA << 4) + 16; if (kendA > kb) kendA = kb;
-                        int kendB = (bB << 4) + 16; if (kendB > kb) kendB = kb;
-                        if (bA == bB) kendA = ka;   // single block: only the B half is used
-                        warp_mma_nn2(Yb, ld, m0, cr, Ms, ld, bA << 4, bB << 4, n, ka, kendA, kendB, acc);
+                        const int kend = (c0 + 32 < kb) ? c0 + 32 : kb;
+                        warp_mma_nn(Ybg, ld, m0, cr, Ms, ld, c0, n, ka, kend, acc);
                     }
-                    __syncthreads();
+                    BSYNC();
                     if (act) {
 #pragma unroll
                         for (int q = 0; q < 2; q++) {
@@ -888,75 +931,76 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                             if (lr >= cr) continue;
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
-                                if (j < 2 && bA == bB) continue;
-                                const int c = ((j < 2 ? bA : bB) << 4) + 8 * (j & 1) + 2 * mt;
+                                const int c = c0 + 8 * j + 2 * mt;
                                 if (c >= n) continue;
-                                st2(Yb + (long long)lr * ld + c, acc[q][j][0], acc[q][j][1]);
+                                st2(Ybg + (long long)lr * ld + c, acc[q][j][0], acc[q][j][1]);
                                 if (seg == 1) st2(Yg + (long long)(r0 - xo + lr) * n + c, acc[q][j][0], acc[q][j][1]);
                             }
                         }
                     }
-                    __syncthreads();
-                } else {
-                    const int nct = (n + 31) >> 5;
-                    for (int hi = nct; hi > 0; hi -= tpw) {
-                        const int lo = hi - tpw > 0 ? hi - tpw : 0;
-                        const int slot = warp % tpw, rt = warp / tpw;
-                        // spread long and short column tiles over the four schedulers (warp & 3)
-                        const int ct = lo + (slot + rt) % tpw;
-                        const bool act = rt < rtiles && ct < hi;
-                        Acc acc;
-                        acc_zero(acc);
-                        const int m0 = rt << 4, c0 = ct << 5;
-                        if (act) {
-                            int ka = 0, kb = n;
-                            if (seg == 0) xrow_range(dm, s_orow, a.dense_o != 0, r0 + m0, ka, kb);
-                            const int kend = (c0 + 32 < kb) ? c0 + 32 : kb;
-                            warp_mma_nn(Yb, ld, m0, cr, Ms, ld, c0, n, ka, kend, acc);
-                        }
-                        __syncthreads();
-                        if (act) {
+                    BSYNC();
+                }
+            }
+            PH_ADD(4);
+            if (!has_x) continue;
+            // ---- z = y W (chain columns only), in place after a barrier; same balanced pairing of 16-column blocks
+            const int nbz = (n - kz0 + 15) >> 4, npz = (nbz + 1) >> 1;
+            if (npz <= tpw) {
+                const int slot = gw % tpw, rt = gw / tpw;
+                const bool act = rt < rtiles && slot < npz;
+                const int bA = slot, bB = nbz - 1 - slot;
+                const int kA = kz0 + (bA << 4), kB = kz0 + (bB << 4);
+                Acc acc;
+                acc_zero(acc);
+                const int m0 = rt << 4;
+                if (act) {
+                    int sA = kA, sB = kB;
+                    if (seg == 0) {
+                        // rows of O: y is zero left of ka; z is only needed up to the last column that feeds the LOWER triangle
+                        int ka, kb; xrow_range(dm, s_orow, a.dense_o != 0, r0 + m0, ka, kb);
+                        if (ka > sA) sA = ka;
+                        if (ka > sB) sB = ka;
+                        if (!a.dense_o) { if (kA >= kb) sA = n; if (kB >= kb) sB = n; }
+                    }
+                    if (bA == bB) sA = n;
+                    warp_mma_nt2(Ybg, ld, m0, cr, Ms, ld, kA, kB, n, sA, sB, n, acc);
+                }
+                BSYNC();
+                if (act) {
 #pragma unroll
-                            for (int q = 0; q < 2; q++) {
-                                const int lr = m0 + 8 * q + mg;
-                                if (lr >= cr) continue;
+                    for (int q = 0; q < 2; q++) {
+                        const int lr = m0 + 8 * q + mg;
+                        if (lr >= cr) continue;
 #pragma unroll
-                                for (int j = 0; j < 4; j++) {
-                                    const int c = c0 + 8 * j + 2 * mt;
-                                    if (c >= n) continue;
-                                    st2(Yb + (long long)lr * ld + c, acc[q][j][0], acc[q][j][1]);
-                                    if (seg == 1) st2(Yg + (long long)(r0 - xo + lr) * n + c, acc[q][j][0], acc[q][j][1]);
-                                }
-                            }
+                        for (int j = 0; j < 4; j++) {
+                            if (j < 2 && bA == bB) continue;
+                            const int c = ((j < 2) ? kA : kB) + 8 * (j & 1) + 2 * mt;
+                            if (c < n) st2(Ybg + (long long)lr * ld + c, acc[q][j][0], acc[q][j][1]);
                         }
-                        __syncthreads();
                     }
                 }
-                PH_ADD(4);
-                if (!has_x) continue;
-                // ---- z = y W (chain columns only), in place after a barrier; same balanced pairing of 16-column blocks
-                const int nbz = (n - kz0 + 15) >> 4, npz = (nbz + 1) >> 1;
-                if (npz <= tpw) {
-                    const int slot = warp % tpw, rt = warp / tpw;
-                    const bool act = rt < rtiles && slot < npz;
-                    const int bA = slot, bB = nbz - 1 - slot;
-                    const int kA = kz0 + (bA << 4), kB = kz0 + (bB << 4);
+                BSYNC();
+            } else {
+                const int nct = (n - kz0 + 31) >> 5;
+                for (int lo = 0; lo < nct; lo += tpw) {
+                    const int hi = lo + tpw < nct ? lo + tpw : nct;
+                    const int slot = gw % tpw, rt = gw / tpw;
+                    const int ct = lo + (slot + rt) % tpw;
+                    const bool act = rt < rtiles && ct < hi;
                     Acc acc;
                     acc_zero(acc);
-                    const int m0 = rt << 4;
+                    const int m0 = rt << 4, k0 = kz0 + (ct << 5);
                     if (act) {
-                        int sA = kA, sB = kB;
+                        int ca = k0;
+                        bool need = true;
                         if (seg == 0) {
-                            // rows of O: y is zero left of ka; z is only needed up to the last column that feeds the LOWER triangle
                             int ka, kb; xrow_range(dm, s_orow, a.dense_o != 0, r0 + m0, ka, kb);
-                            if (ka > sA) sA = ka;
-                            if (ka > sB) sB = ka;
-                            if (!a.dense_o) { if (kA >= kb) sA = n; if (kB >= kb) sB = n; }
+                            if (ka > ca) ca = ka;
+                            if (!a.dense_o && k0 >= kb) need = false;
                         }
-                        if (bA == bB) sA = n;
-                        warp_mma_nt2(Yb, ld, m0, cr, Ms, ld, kA, kB, n, sA, sB, n, acc);
+                        if (need) warp_mma_nt(Ybg, ld, m0, cr, Ms, ld, k0, n, ca, n, acc);
                     }
-                    __syncthreads();
+                    BSYNC();
                     if (act) {
 #pragma unroll
                         for (int q = 0; q < 2; q++) {
@@ -964,139 +1008,44 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                             if (lr >= cr) continue;
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
-                                if (j < 2 && bA == bB) continue;
-                                const int c = ((j < 2) ? kA : kB) + 8 * (j & 1) + 2 * mt;
-                                if (c < n) st2(Yb + (long long)lr * ld + c, acc[q][j][0], acc[q][j][1]);
+                                const int c = k0 + 8 * j + 2 * mt;
+                                if (c < n) st2(Ybg + (long long)lr * ld + c, acc[q][j][0], acc[q][j][1]);
                             }
                         }
                     }
-                    __syncthreads();
-                } else {
-                    const int nct = (n - kz0 + 31) >> 5;
-                    for (int lo = 0; lo < nct; lo += tpw) {
-                        const int hi = lo + tpw < nct ? lo + tpw : nct;
-                        const int slot = warp % tpw, rt = warp / tpw;
-                        const int ct = lo + (slot + rt) % tpw;
-                        const bool act = rt < rtiles && ct < hi;
-                        Acc acc;
-                        acc_zero(acc);
-                        const int m0 = rt << 4, k0 = kz0 + (ct << 5);
-                        if (act) {
-                            int ca = k0;
-                            bool need = true;
-                            if (seg == 0) {
-                                int ka, kb; xrow_range(dm, s_orow, a.dense_o != 0, r0 + m0, ka, kb);
-                                if (ka > ca) ca = ka;
-                                if (!a.dense_o && k0 >= kb) need = false;
-                            }
-                            if (need) warp_mma_nt(Yb, ld, m0, cr, Ms, ld, k0, n, ca, n, acc);
-                        }
-                        __syncthreads();
-                        if (act) {
-#pragma unroll
-                            for (int q = 0; q < 2; q++) {
-                                const int lr = m0 + 8 * q + mg;
-                                if (lr >= cr) continue;
-#pragma unroll
-                                for (int j = 0; j < 4; j++) {
-                                    const int c = k0 + 8 * j + 2 * mt;
-                                    if (c < n) st2(Yb + (long long)lr * ld + c, acc[q][j][0], acc[q][j][1]);
-                                }
-                            }
-                        }
-                        __syncthreads();
-                    }
+                    BSYNC();
                 }
-                PH_ADD(5);
-                // ---- fill rows  F = z[:, chain] O^T
-                if (a.dense_o) {
-                    // dense coupling block: O streams through two 16-column slabs (cp.async), accumulators stay in registers
-                    const int nsl = (n - kz0 + 15) >> 4;
-                    const int nctf = (nc + 31) >> 5;
-                    auto load_slab = [&](int sidx, double* Os) {
-                        const int cbase = kz0 - nl + 16 * sidx;
-                        for (int e = threadIdx.x; e < nc * 16; e += blockDim.x) {
-                            const int j = e >> 4, t = e & 15, cc = cbase + t;
-                            if (cc >= 0 && cc < nc) cp_async8(Os + j * B200_OSLD + t, Og + (long long)j * nc + cc);
-                            else Os[j * B200_OSLD + t] = 0.0;
-                        }
-                    };
-                    for (int lo = 0; lo < nctf; lo += tpw) {
-                        const int slot = warp % tpw, rt = warp / tpw;
-                        const int ct = lo + slot;
-                        const bool act = rt < rtiles && ct < nctf;
-                        Acc acc;
-                        acc_zero(acc);
-                        const int m0 = rt << 4;
-                        load_slab(0, Op);
-                        for (int sidx = 0; sidx < nsl; sidx++) {
-                            cp_async_wait_all();
-                            __syncthreads();
-                            if (sidx + 1 < nsl) load_slab(sidx + 1, Op + ((sidx + 1) & 1) * nc * B200_OSLD);
-                            int kw = n - kz0 - 16 * sidx; if (kw > 16) kw = 16;
-                            if (act) warp_mma_nt(Yb + kz0 + 16 * sidx, ld, m0, cr, Op + (sidx & 1) * nc * B200_OSLD, B200_OSLD, ct << 5, nc, 0, kw, acc);
-                        }
-                        if (act) {
-#pragma unroll
-                            for (int q = 0; q < 2; q++) {
-                                const int lr = m0 + 8 * q + mg;
-                                if (lr >= cr) continue;
-#pragma unroll
-                                for (int j = 0; j < 4; j++) {
-#pragma unroll
-                                    for (int e = 0; e < 2; e++) {
-                                        const int ci = (ct << 5) + 8 * j + 2 * mt + e;
-                                        if (ci < nc) Fout[(long long)(r0 + lr) * nc + ci] = acc[q][j][e];
-                                    }
-                                }
-                            }
-                        }
-                        __syncthreads();
+            }
+            PH_ADD(5);
+            // ---- fill rows  F = z[:, chain] O^T
+            if (a.dense_o) {
+                // dense coupling block: O streams through two 16-column slabs (cp.async), accumulators stay in registers
+                const int nsl = (n - kz0 + 15) >> 4;
+                const int nctf = (nc + 31) >> 5;
+                auto load_slab = [&](int sidx, double* Os) {
+                    const int cbase = kz0 - nl + 16 * sidx;
+                    for (int e = gtid; e < nc * 16; e += gthreads) {
+                        const int j = e >> 4, t = e & 15, cc = cbase + t;
+                        if (cc >= 0 && cc < nc) cp_async8(Os + j * B200_OSLD + t, Og + (long long)j * nc + cc);
+                        else Os[j * B200_OSLD + t] = 0.0;
                     }
-                } else {
-                    // block-sparse coupling on the tensor cores: a warp task = 16 panel rows x 32 fill columns = four 8-column
-                    // blocks (8 rows of O each).  Every block contracts over the union of the packed windows of its 8 rows of O
-                    // (<= 2 IMU blocks for the time chain; an entry of O outside its row's window is structurally zero and is
-                    // supplied as 0); the four blocks advance in lockstep so that 8 independent accumulators are in flight.
-                    const int ncq = (nc + 31) >> 5;
-                    for (int task = warp; task < rtiles * ncq; task += nwarps) {
-                        const int rt = task % rtiles, cq = task / rtiles;
-                        const int m0 = rt << 4;
-                        int zs[4], kw0[4], nst = 0;
-                        bool cval[4];
-                        const double* bp[4];
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const int ci = (cq << 5) + (j << 3) + mg;     // this lane's B column of block j = row of O
-                            cval[j] = ci < nc;
-                            zs[j] = cval[j] ? s_ozs[ci] : n;
-                            int lo = zs[j], hi = cval[j] ? zs[j] + ow : 0;
-#pragma unroll
-                            for (int o = 4; o <= 16; o <<= 1) {
-                                const int lo2 = __shfl_xor_sync(0xffffffffu, lo, o), hi2 = __shfl_xor_sync(0xffffffffu, hi, o);
-                                lo = lo2 < lo ? lo2 : lo; hi = hi2 > hi ? hi2 : hi;
-                            }
-                            if (hi > n) hi = n;
-                            kw0[j] = lo;
-                            const int steps = hi > lo ? (hi - lo + 3) >> 2 : 0;
-                            nst = steps > nst ? steps : nst;
-                            bp[j] = Op + (cval[j] ? ci : 0) * owp;
-                        }
-                        const double* ap[2];
-#pragma unroll
-                        for (int q = 0; q < 2; q++) { int lr = m0 + 8 * q + mg; if (lr > cr - 1) lr = cr - 1; ap[q] = Yb + (long long)lr * ld; }
-                        Acc acc;
-                        acc_zero(acc);
-                        for (int sidx = 0; sidx < nst; sidx++) {
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                const int kk = kw0[j] + 4 * sidx + mt, idx = kk - zs[j];
-                                const bool ok = kk < n;
-                                const double bv = (cval[j] && idx >= 0 && idx < ow) ? bp[j][idx] : 0.0;
-#pragma unroll
-                                for (int q = 0; q < 2; q++) dmma884(acc[q][j][0], acc[q][j][1], ok ? ap[q][kk] : 0.0, bv);
-                            }
-                        }
+                };
+                for (int lo = 0; lo < nctf; lo += tpw) {
+                    const int slot = gw % tpw, rt = gw / tpw;
+                    const int ct = lo + slot;
+                    const bool act = rt < rtiles && ct < nctf;
+                    Acc acc;
+                    acc_zero(acc);
+                    const int m0 = rt << 4;
+                    load_slab(0, Op);
+                    for (int sidx = 0; sidx < nsl; sidx++) {
+                        cp_async_wait_all();
+                        BSYNC();
+                        if (sidx + 1 < nsl) load_slab(sidx + 1, Op + ((sidx + 1) & 1) * nc * B200_OSLD);
+                        int kw = n - kz0 - 16 * sidx; if (kw > 16) kw = 16;
+                        if (act) warp_mma_nt(Ybg + kz0 + 16 * sidx, ld, m0, cr, Op + (sidx & 1) * nc * B200_OSLD, B200_OSLD, ct << 5, nc, 0, kw, acc);
+                    }
+                    if (act) {
 #pragma unroll
                         for (int q = 0; q < 2; q++) {
                             const int lr = m0 + 8 * q + mg;
@@ -1105,16 +1054,76 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                             for (int j = 0; j < 4; j++) {
 #pragma unroll
                                 for (int e = 0; e < 2; e++) {
-                                    const int co = (cq << 5) + (j << 3) + 2 * mt + e;
-                                    if (co < nc) Fout[(long long)(r0 + lr) * nc + co] = acc[q][j][e];
+                                    const int ci = (ct << 5) + 8 * j + 2 * mt + e;
+                                    if (ci < nc) Fout[(long long)(r0 + lr) * nc + ci] = acc[q][j][e];
                                 }
                             }
                         }
                     }
+                    BSYNC();
                 }
-                PH_ADD(6);
+            } else {
+                // block-sparse coupling on the tensor cores: a gw task = 16 panel rows x 32 fill columns = four 8-column
+                // blocks (8 rows of O each).  Every block contracts over the union of the packed windows of its 8 rows of O
+                // (<= 2 IMU blocks for the time chain; an entry of O outside its row's window is structurally zero and is
+                // supplied as 0); the four blocks advance in lockstep so that 8 independent accumulators are in flight.
+                const int ncq = (nc + 31) >> 5;
+                for (int task = gw; task < rtiles * ncq; task += gnw) {
+                    const int rt = task % rtiles, cq = task / rtiles;
+                    const int m0 = rt << 4;
+                    int zs[4], kw0[4], nst = 0;
+                    bool cval[4];
+                    const double* bp[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int ci = (cq << 5) + (j << 3) + mg;     // this lane's B column of block j = row of O
+                        cval[j] = ci < nc;
+                        zs[j] = cval[j] ? s_ozs[ci] : n;
+                        int lo = zs[j], hi = cval[j] ? zs[j] + ow : 0;
+#pragma unroll
+                        for (int o = 4; o <= 16; o <<= 1) {
+                            const int lo2 = __shfl_xor_sync(0xffffffffu, lo, o), hi2 = __shfl_xor_sync(0xffffffffu, hi, o);
+                            lo = lo2 < lo ? lo2 : lo; hi = hi2 > hi ? hi2 : hi;
+                        }
+                        if (hi > n) hi = n;
+                        kw0[j] = lo;
+                        const int steps = hi > lo ? (hi - lo + 3) >> 2 : 0;
+                        nst = steps > nst ? steps : nst;
+                        bp[j] = Op + (cval[j] ? ci : 0) * owp;
+                    }
+                    const double* ap[2];
+#pragma unroll
+                    for (int q = 0; q < 2; q++) { int lr = m0 + 8 * q + mg; if (lr > cr - 1) lr = cr - 1; ap[q] = Ybg + (long long)lr * ld; }
+                    Acc acc;
+                    acc_zero(acc);
+                    for (int sidx = 0; sidx < nst; sidx++) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int kk = kw0[j] + 4 * sidx + mt, idx = kk - zs[j];
+                            const bool ok = kk < n;
+                            const double bv = (cval[j] && idx >= 0 && idx < ow) ? bp[j][idx] : 0.0;
+#pragma unroll
+                            for (int q = 0; q < 2; q++) dmma884(acc[q][j][0], acc[q][j][1], ok ? ap[q][kk] : 0.0, bv);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        const int lr = m0 + 8 * q + mg;
+                        if (lr >= cr) continue;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+#pragma unroll
+                            for (int e = 0; e < 2; e++) {
+                                const int co = (cq << 5) + (j << 3) + 2 * mt + e;
+                                if (co < nc) Fout[(long long)(r0 + lr) * nc + co] = acc[q][j][e];
+                            }
+                        }
+                    }
+                }
             }
+            PH_ADD(6);
         }
+#undef BSYNC
         __threadfence_block();
     }
     __syncthreads();

@@ -8,7 +8,7 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 constexpr int KD = 128;
-template <int V> __global__ void __launch_bounds__(512) k(double* out, int reps, int ld) {
+template <int V> __global__ void __launch_bounds__(1024) k(double* out, int reps, int ld) {
     extern __shared__ double sm[];
     double* A = sm;                 // 64 x KD
     double* B = sm + 64 * ld;       // 128 x KD
@@ -87,15 +87,15 @@ template <int V> __global__ void __launch_bounds__(512) k(double* out, int reps,
     }
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
-template <int V> void run(const char* name, double flop_per_cta_rep, int ld) {
+template <int V> void run(const char* name, double flop_per_cta_rep, int ld, int threads = 512) {
     double* out; cudaMalloc(&out, 148 * 512 * 8);
     size_t smem = (size_t)(64 + 128) * ld * 8;
     cudaFuncSetAttribute(k<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int reps = 400;
-    k<V><<<148, 512, smem>>>(out, 10, ld);
+    k<V><<<148, threads, smem>>>(out, 10, ld);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    k<V><<<148, 512, smem>>>(out, reps, ld);
+    k<V><<<148, threads, smem>>>(out, reps, ld);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     cudaError_t err = cudaGetLastError();
@@ -111,5 +111,10 @@ int main() {
     }
     run<3>("r0 dfma registers", 2.0 * 512 * 16 * KD, 130);
     run<4>("r1 dmma registers", 2.0 * 16 * 8 * 256 * (KD / 4), 130);
+    // DMMA issue interval per warp: the same register-only loop with 8 / 4 / 32 warps per SM (flops scale with the warp count)
+    run<4>("r1 dmma registers,  8 warps", 2.0 * 8 * 8 * 256 * (KD / 4), 130, 256);
+    run<4>("r1 dmma registers,  4 warps", 2.0 * 4 * 8 * 256 * (KD / 4), 130, 128);
+    run<4>("r1 dmma registers, 32 warps", 2.0 * 32 * 8 * 256 * (KD / 4), 130, 1024);
+    run<3>("r0 dfma registers,  8 warps", 2.0 * 256 * 16 * KD, 130, 256);
     return 0;
 }
