@@ -708,9 +708,22 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
     double* Op = Yb + (long long)CR * ld;
     const int kz0 = nl & ~1;                        // first column of z that is needed (chain columns, pair aligned)
     // structure tables of O in shared memory (they are consulted at the start of every GEMM phase: keep them off the L2 path)
-    __shared__ int s_orow[2 * 256], s_ozs[256];
+    __shared__ int s_orow[2 * 256], s_ozs[256], s_fblk[64], s_nfblk;
     for (int e = threadIdx.x; e < 2 * nc; e += blockDim.x) s_orow[e] = dm.orow[e];
     for (int e = threadIdx.x; e < nc; e += blockDim.x) s_ozs[e] = dm.ozs[e];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // 8-column blocks of the block-sparse fill: every run of rows of O that share a packed window is covered by blocks that
+        // stay inside the run (the last one is shifted back and overlaps its neighbour), so a block contracts over ONE window
+        int nbk = 0, i0 = 0;
+        while (i0 < nc && nbk < 60) {
+            int e = i0;
+            while (e < nc && s_ozs[e] == s_ozs[i0]) e++;
+            for (int j = i0; j < e && nbk < 60; j += 8) s_fblk[nbk++] = (j + 8 <= e) ? j : ((e - 8 > i0) ? e - 8 : i0);
+            i0 = e;
+        }
+        s_nfblk = nbk;
+    }
     __syncthreads();
     for (int i = 0; i < a.n; i++) {
         const long long src = a.src0 + i;
@@ -1063,32 +1076,23 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                     BSYNC();
                 }
             } else {
-                // block-sparse coupling on the tensor cores: a gw task = 16 panel rows x 32 fill columns = four 8-column
-                // blocks (8 rows of O each).  Every block contracts over the union of the packed windows of its 8 rows of O
-                // (<= 2 IMU blocks for the time chain; an entry of O outside its row's window is structurally zero and is
-                // supplied as 0); the four blocks advance in lockstep so that 8 independent accumulators are in flight.
-                const int ncq = (nc + 31) >> 5;
+                // block-sparse coupling on the tensor cores: a warp task = 16 panel rows x four 8-column blocks of the table
+                // s_fblk (8 rows of O sharing one packed window: the contraction runs over that window only, <= ow columns); the
+                // four blocks advance in lockstep so that 8 independent accumulators are in flight.
+                const int nfb = s_nfblk, ncq = (nfb + 3) >> 2, nst = (ow + 3) >> 2;
                 for (int task = gw; task < rtiles * ncq; task += gnw) {
                     const int rt = task % rtiles, cq = task / rtiles;
                     const int m0 = rt << 4;
-                    int zs[4], kw0[4], nst = 0;
+                    int zs[4], cs[4];
                     bool cval[4];
                     const double* bp[4];
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        const int ci = (cq << 5) + (j << 3) + mg;     // this lane's B column of block j = row of O
-                        cval[j] = ci < nc;
-                        zs[j] = cval[j] ? s_ozs[ci] : n;
-                        int lo = zs[j], hi = cval[j] ? zs[j] + ow : 0;
-#pragma unroll
-                        for (int o = 4; o <= 16; o <<= 1) {
-                            const int lo2 = __shfl_xor_sync(0xffffffffu, lo, o), hi2 = __shfl_xor_sync(0xffffffffu, hi, o);
-                            lo = lo2 < lo ? lo2 : lo; hi = hi2 > hi ? hi2 : hi;
-                        }
-                        if (hi > n) hi = n;
-                        kw0[j] = lo;
-                        const int steps = hi > lo ? (hi - lo + 3) >> 2 : 0;
-                        nst = steps > nst ? steps : nst;
+                        const int fb = (cq << 2) + j;
+                        cs[j] = fb < nfb ? s_fblk[fb] : nc;
+                        zs[j] = fb < nfb ? s_ozs[cs[j]] : n;
+                        const int ci = cs[j] + mg;                        // this lane's B column of block j = row of O
+                        cval[j] = ci < nc && s_ozs[ci < nc ? ci : 0] == zs[j];
                         bp[j] = Op + (cval[j] ? ci : 0) * owp;
                     }
                     const double* ap[2];
@@ -1097,11 +1101,12 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                     Acc acc;
                     acc_zero(acc);
                     for (int sidx = 0; sidx < nst; sidx++) {
+                        const int idx = 4 * sidx + mt;
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
-                            const int kk = kw0[j] + 4 * sidx + mt, idx = kk - zs[j];
-                            const bool ok = kk < n;
-                            const double bv = (cval[j] && idx >= 0 && idx < ow) ? bp[j][idx] : 0.0;
+                            const int kk = zs[j] + idx;
+                            const bool ok = kk < n && idx < ow;
+                            const double bv = (cval[j] && idx < ow) ? bp[j][idx] : 0.0;
 #pragma unroll
                             for (int q = 0; q < 2; q++) dmma884(acc[q][j][0], acc[q][j][1], ok ? ap[q][kk] : 0.0, bv);
                         }
@@ -1114,8 +1119,8 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                         for (int j = 0; j < 4; j++) {
 #pragma unroll
                             for (int e = 0; e < 2; e++) {
-                                const int co = (cq << 5) + (j << 3) + 2 * mt + e;
-                                if (co < nc) Fout[(long long)(r0 + lr) * nc + co] = acc[q][j][e];
+                                const int co = cs[j] + 2 * mt + e;
+                                if (co < nc && s_ozs[co] == zs[j]) Fout[(long long)(r0 + lr) * nc + co] = acc[q][j][e];
                             }
                         }
                     }
