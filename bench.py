@@ -43,31 +43,58 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons sampled DURING the timed region: NVML in-process every 10 ms (the timed region is a few
+    hundred ms, too short for repeated nvidia-smi launches), nvidia-smi as the fallback."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
     def __init__(self, device=0):
         super().__init__(daemon=True)
         self.device, self.samples, self.stop_flag = device, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
 
-    def run(self):
+    def sample(self):
+        if self.nvml is not None:
+            n = self.nvml
+            mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+            get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+            r = int(get(self.handle))
+            flags = [bool(r & 0x8), bool(r & 0x40), bool(r & 0x20), bool(r & 0x4)]   # hw, hw thermal, sw thermal, sw power cap
+            return [mhz, self.max_mhz] + flags
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if not out:
+            return None
+        f = [x.strip() for x in out.split(",")]
+        return [float(f[0]), float(f[1])] + [v.lower().startswith("active") for v in f[2:6]]
+
+    def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                smp = self.sample()
+                if smp:
+                    self.samples.append(smp)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.01 if self.nvml is not None else 0.2)
 
     def summary(self):
         self.stop_flag = True
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        mhz = sorted(float(s[0]) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(mhz)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples: NVML and nvidia-smi unavailable"]}
+        mhz = sorted(s[0] for s in self.samples)
+        reasons = sorted({n for s in self.samples for n, v in zip(self.NAMES, s[2:6]) if v})
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": self.samples[0][1], "reasons": reasons, "samples": len(mhz),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def build_problem_inputs(workload, preint, seed=0, n_keyframes=None):
@@ -248,9 +275,14 @@ def run_b200(args):
         achieved = K * SWEEP_BYTES_PER_KEYFRAME / (sweep_ms * 1e-3) / 1e9
         kern = "chain_sweep_kernel (top level)"
     traffic = None
+    fp64_mma = None
     tpath = os.path.join(ROOT, "profiles", "sweep_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        tj = json.load(open(tpath))
+        traffic = tj.get("dram_bytes_per_launch")
+        if tj.get("dmma_pipe_pct_of_peak") is not None:
+            fp64_mma = {"pipe": "DMMA m8n8k4 (mma.sync f64)", "frac_of_issue_peak_ncu": tj["dmma_pipe_pct_of_peak"] / 100.0,
+                        "peak_tflops_measured": tj.get("dmma_peak_tflops_measured"), "source": tj.get("source")}
     line = {
         "metric": "lm_iterations_per_sec", "value": value, "unit": "iter/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -263,8 +295,10 @@ def run_b200(args):
         "phase_ms_per_step": {"linearize+assemble": ph[0] / args.steps, "solve": ph[1] / args.steps, "model+retract+error": ph[2] / args.steps},
         "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "launch_ms": sweep_ms,
-                     "note": "algorithmic bytes = (H 4167 + F 28539 doubles) per keyframe x keyframes per launch (SURVEY 8(d)); the kernel is bound by "
-                             "shared-memory wavefronts / the fp64 pipe and its sequential pivot chain, not by HBM (profiles/)"},
+                     "fp64_mma": fp64_mma,
+                     "note": "algorithmic bytes = (H 4167 + F 28539 doubles) per keyframe x keyframes per launch (SURVEY 8(d)); the kernel is "
+                             "compute/latency bound, not HBM bound: its GEMMs run on the fp64 tensor pipe (DMMA), fp64_mma gives that pipe's "
+                             "share of its issue peak from the ncu capture in profiles/ (r01c)"},
         "e2e": {"value": args.steps / e2e_s, "unit": "iter/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches), "clocks": clocks,
     }
