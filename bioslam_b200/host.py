@@ -22,12 +22,14 @@ def _L(so_path=None):
         L.b200h_lbpe_create.argtypes = [C.POINTER(C.c_void_p), C.c_char_p]
         L.b200h_lbpe_desc.restype = C.POINTER(abi.ProblemDesc)
         for f in ("b200h_imu_destroy", "b200h_ipe_destroy", "b200h_lbpe_destroy", "b200h_ipe_setup", "b200h_ipe_set_optimized_to_initial",
-                  "b200h_ipe_fast_optimize", "b200h_ipe_n_keyframes", "b200h_lbpe_setup", "b200h_lbpe_fast_optimize", "b200h_lbpe_set_joint_angles", "b200h_lbpe_desc"):
+                  "b200h_ipe_fast_optimize", "b200h_ipe_n_keyframes", "b200h_lbpe_setup", "b200h_lbpe_fast_optimize", "b200h_lbpe_set_joint_angles", "b200h_lbpe_desc",
+                  "b200h_lbpe_post_hoc_axes_check", "b200h_lbpe_set_members_from_values", "b200h_lbpe_adjust_legs", "b200h_lbpe_n_restarts"):
             getattr(L, f).argtypes = [C.c_void_p]
         for f in ("b200h_ipe_set", "b200h_lbpe_set"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.c_int]
         for f in ("b200h_ipe_get", "b200h_lbpe_get"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.c_int]
+        L.b200h_lbpe_hip_ie_slopes.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.b200h_lbpe_values.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.b200h_lbpe_set_values.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L._host_ready = True
@@ -105,6 +107,24 @@ class LowerBodyPoseEstimator(_Settable):
     def setup(self): _ck(self.L, self.L.b200h_lbpe_setup(self.h)); return self
     def fastOptimize(self): _ck(self.L, self.L.b200h_lbpe_fast_optimize(self.h)); return self
     def setDerivedJointAnglesFromEstimatedStates(self): _ck(self.L, self.L.b200h_lbpe_set_joint_angles(self.h)); return self
+    def setMemberEstimatedStatesFromValues(self): _ck(self.L, self.L.b200h_lbpe_set_members_from_values(self.h)); return self
+
+    def computeHipIeRotAngleRegressionSlopesFromValues(self):
+        """reference src/lowerBodyPoseEstimator.cpp:1507-1558 -> (right, left) slope in rad/s"""
+        out = np.zeros(2)
+        _ck(self.L, self.L.b200h_lbpe_hip_ie_slopes(self.h, D(out)))
+        return float(out[0]), float(out[1])
+
+    def adjustLegsForCorrectedHipIeAngles(self): _ck(self.L, self.L.b200h_lbpe_adjust_legs(self.h)); return self
+    @property
+    def nRestarts(self): return self.L.b200h_lbpe_n_restarts(self.h)
+
+    def postHocAxesCheck(self):
+        """reference src/lowerBodyPoseEstimator.cpp:711-797; True if a knee shank axis was flipped"""
+        rc = self.L.b200h_lbpe_post_hoc_axes_check(self.h)
+        if rc < 0:
+            raise HostError(self.L.b200h_last_error().decode())
+        return bool(rc)
 
     def graph(self):
         """deep copy of the flat description setup() produced + its current values"""

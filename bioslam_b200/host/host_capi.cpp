@@ -113,12 +113,23 @@ int b200h_lbpe_set(void* pv, const char* name, const double* v, int n) {
     else if (s == "m_useMaxAnthroConstraint") p.m_useMaxAnthroConstraint = v[0] != 0;
     else if (s == "m_useMinAnthroConstraint") p.m_useMinAnthroConstraint = v[0] != 0;
     else if (s == "m_usePriorsOnImuToJointCtrVectors") p.m_usePriorsOnImuToJointCtrVectors = v[0] != 0;
+    else if (s == "m_maxNumRestarts") p.m_maxNumRestarts = (unsigned)v[0];
+    else if (s == "m_hipIeAngDriftRestartThreshold") p.m_hipIeAngDriftRestartThreshold = v[0];
     else { g_err = "unknown setting: " + s; return 1; }
     return 0;
 }
 int b200h_lbpe_setup(void* p) { GUARD(((lowerBodyPoseEstimator*)p)->setup()); }
 int b200h_lbpe_fast_optimize(void* p) { GUARD(((lowerBodyPoseEstimator*)p)->fastOptimize()); }
 int b200h_lbpe_set_joint_angles(void* p) { GUARD(((lowerBodyPoseEstimator*)p)->setDerivedJointAnglesFromEstimatedStates()); }
+// returns 1 if an axis was flipped, 0 if not, -1 on error
+int b200h_lbpe_post_hoc_axes_check(void* p) {
+    try { return ((lowerBodyPoseEstimator*)p)->postHocAxesCheck(false) ? 1 : 0; } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+// out[0], out[1] = regression slopes (rad/s) of the right / left hip int/ext rotation angle of the current values
+int b200h_lbpe_hip_ie_slopes(void* p, double* out) { GUARD(((lowerBodyPoseEstimator*)p)->computeHipIeRotAngleRegressionSlopesFromValues(out[0], out[1])); }
+int b200h_lbpe_adjust_legs(void* p) { GUARD(((lowerBodyPoseEstimator*)p)->adjustLegsForCorrectedHipIeAngles(false)); }
+int b200h_lbpe_n_restarts(void* p) { return (int)((lowerBodyPoseEstimator*)p)->m_nRestarts; }
+int b200h_lbpe_set_members_from_values(void* p) { GUARD(((lowerBodyPoseEstimator*)p)->setMemberEstimatedStatesFromValues()); }
 // the flat description setup() produced (valid until the estimator is destroyed) and its current values
 const b200_problem_desc* b200h_lbpe_desc(void* p) { auto& e = *(lowerBodyPoseEstimator*)p; return e.isSetup() ? &e.graph().desc() : nullptr; }
 int b200h_lbpe_values(void* pv, double* tv, double* sv) {

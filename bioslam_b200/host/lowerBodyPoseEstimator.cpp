@@ -1,6 +1,9 @@
 // see lowerBodyPoseEstimator.h.  IMU order everywhere: sacrum, rthigh, rshank, rfoot, lthigh, lshank, lfoot.
 #include <cstdio>
 #include "lowerBodyPoseEstimator.h"
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
 #include <chrono>
 #include <iostream>
 
@@ -139,8 +142,32 @@ void lowerBodyPoseEstimator::setup() {
     gb.finalize();
 }
 
+// pose of IMU i at keyframe k inside the GraphBuilder's value array (hipDrift.h accessor)
+static double* lbpePoseAt(void* ctx, int imu, int k) {
+    auto* self = static_cast<lowerBodyPoseEstimator*>(ctx);
+    return const_cast<double*>(self->graph().timeValue(k, self->poseVarOfImu(imu)));
+}
+hipdrift::Statics lowerBodyPoseEstimator::hipDriftStatics() const {
+    const GraphBuilder& gb = *m_gb;
+    auto S = [&](int i) { return gb.staticValue(m_staticVar[i]); };
+    // m_staticVar: 12 IMU-to-joint-centre vectors then 11 axes, in the order of setMemberEstimatedStatesFromValues()
+    return hipdrift::Statics{S(0), S(1), S(3), S(2), S(4), S(5), S(6), S(8), S(7), S(9), S(10), S(11), S(12 + 0), S(12 + 2)};
+}
+// reference src/lowerBodyPoseEstimator.cpp:1507-1558
+void lowerBodyPoseEstimator::computeHipIeRotAngleRegressionSlopesFromValues(double& rhipIntExtRotSlope, double& lhipIntExtRotSlope) {
+    if (!m_gb) throw std::runtime_error("setup() must be called first");
+    hipdrift::PoseAccess pa{&lbpePoseAt, this, m_gb->K()};
+    hipdrift::hipIeSlopes(pa, hipDriftStatics(), m_time, rhipIntExtRotSlope, lhipIntExtRotSlope);
+}
+// reference src/lowerBodyPoseEstimator.cpp:1560-1652 (edits the poses of the six leg IMUs in the current values)
+void lowerBodyPoseEstimator::adjustLegsForCorrectedHipIeAngles(bool verbose) {
+    if (!m_gb) throw std::runtime_error("setup() must be called first");
+    if (verbose) std::printf("\tcorrecting hip angles for zero hip i/e angle slope...\n");
+    hipdrift::PoseAccess pa{&lbpePoseAt, this, m_gb->K()};
+    hipdrift::adjustLegsForCorrectedHipIeAngles(pa, hipDriftStatics(), m_time);
+}
+
 void lowerBodyPoseEstimator::fastOptimize(double prevGlobalErr) {
-    (void)prevGlobalErr;  // the hip I/E drift restart (reference :668-688) is a host heuristic that is not part of this build
     if (!m_gb) throw std::runtime_error("setup() must be called first");
     GraphBuilder& gb = *m_gb;
     b200_problem* prob = nullptr;
@@ -158,7 +185,59 @@ void lowerBodyPoseEstimator::fastOptimize(double prevGlobalErr) {
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     m_optimizationTotalError.insert(m_optimizationTotalError.end(), hist.begin(), hist.begin() + res.n_history);   // :655,666 (push_back semantics)
     for (int i = 0; i < res.n_history; i++) m_optimizationTotalTime.push_back(secs * i / std::max(1, res.n_history - 1));
-    setMemberEstimatedStatesFromValues();
+    // restart condition on hip I/E drift (reference :668-688): a drifting hip int/ext rotation angle is straightened by
+    // re-seeding the leg IMU poses, and the optimisation runs again from there
+    double rhipIeSlope = 0.0, lhipIeSlope = 0.0;
+    computeHipIeRotAngleRegressionSlopesFromValues(rhipIeSlope, lhipIeSlope);
+    const bool doRestart = (std::fabs(rhipIeSlope) > m_hipIeAngDriftRestartThreshold || std::fabs(lhipIeSlope) > m_hipIeAngDriftRestartThreshold) &&
+                           res.final_error < prevGlobalErr * 0.99 && m_nRestarts < m_maxNumRestarts;
+    if (doRestart) {
+        m_nRestarts++;
+        adjustLegsForCorrectedHipIeAngles(false);
+        fastOptimize(res.final_error);
+        return;
+    }
+    setMemberEstimatedStatesFromValues();               // reference :700-702
+    postHocAxesCheck(false);
+    setDerivedJointAnglesFromEstimatedStates();
+}
+
+// reference src/lowerBodyPoseEstimator.cpp:711-797: (1) the two knee axes of a leg (thigh frame / shank frame) must point the
+// same way in the navigation frame -- mean angle between them over the trial <= 90 deg, else the SHANK axis member is flipped;
+// (2) the knee flexion angle should stay inside (-179, 20) deg, which the reference only reports.  Like the reference this
+// changes the members (m_[rl]kneeAxisShank), not the optimised values; the derived joint angles are computed from the members.
+bool lowerBodyPoseEstimator::postHocAxesCheck(bool verbose) {
+    if (!m_gb) throw std::runtime_error("setup() must be called first");
+    const double maxFlexExLimRad = 20.0 * M_PI / 180.0, minFlexExLimRad = -179.0 * M_PI / 180.0;
+    auto meanAngleDeg = [](const std::vector<Rot3>& Ra, const Unit3& a, const std::vector<Rot3>& Rb, const Unit3& b) {
+        double sum = 0.0;
+        for (size_t k = 0; k < Ra.size(); k++) {
+            const Vector3 u = Ra[k].rotate(a.unitVector()), w = Rb[k].rotate(b.unitVector());
+            const Vector3 c(u[1] * w[2] - u[2] * w[1], u[2] * w[0] - u[0] * w[2], u[0] * w[1] - u[1] * w[0]);
+            sum += std::atan2(c.norm(), u[0] * w[0] + u[1] * w[1] + u[2] * w[2]) * 180.0 / M_PI;   // mathutils::unsignedAngle (src/mathutils.cpp:63-91)
+        }
+        return Ra.empty() ? 0.0 : sum / (double)Ra.size();
+    };
+    bool anyChangesMade = false;
+    struct Leg { const char* name; const std::vector<Rot3>* Rthigh; const std::vector<Rot3>* Rshank; const Unit3* thigh; Unit3* shank; };
+    Leg legs[2] = {{"right", &m_rthighImuOrientation, &m_rshankImuOrientation, &m_rkneeAxisThigh, &m_rkneeAxisShank},
+                   {"left", &m_lthighImuOrientation, &m_lshankImuOrientation, &m_lkneeAxisThigh, &m_lkneeAxisShank}};
+    for (Leg& leg : legs) {
+        const double mean = meanAngleDeg(*leg.Rthigh, *leg.thigh, *leg.Rshank, *leg.shank);
+        if (mean > 90.0) {
+            *leg.shank = Unit3(-leg.shank->p[0], -leg.shank->p[1], -leg.shank->p[2]);
+            anyChangesMade = true;
+        }
+        if (verbose) std::printf("postHocAxesCheck: %s knee axes, mean angle between %.3f deg%s\n", leg.name, mean, mean > 90.0 ? " -> shank axis flipped" : "");
+    }
+    // knee flexion range (the reference tests the RIGHT knee's range for both legs, :771 -- kept)
+    setDerivedJointAnglesFromEstimatedStates();
+    if (!m_rkneeFlexExAng.empty()) {
+        const double mx = *std::max_element(m_rkneeFlexExAng.begin(), m_rkneeFlexExAng.end()), mn = *std::min_element(m_rkneeFlexExAng.begin(), m_rkneeFlexExAng.end());
+        if (!(mx < maxFlexExLimRad && mn > minFlexExLimRad)) std::printf("knee angle out of bounds!\n");
+    }
+    if (anyChangesMade && postHocAxesCheck(false)) std::fprintf(stderr, "Why did something changes on the second pass?\n");
+    return anyChangesMade;
 }
 
 // reference src/lowerBodyPoseEstimator.cpp:1147-1228
@@ -201,7 +280,15 @@ void lowerBodyPoseEstimator::setDerivedJointAnglesFromEstimatedStates(bool verbo
     b200_problem* prob = nullptr;
     if (b200_problem_create(&gb.desc(), getDevice(), &prob) != B200_OK) throw std::runtime_error(std::string("b200_problem_create: ") + b200_last_error());
     std::vector<double> ang((size_t)gb.K() * 12);
-    b200_status stt = b200_set_values(prob, gb.timeValues().data(), gb.staticValues().data());
+    // the knee axes come from the MEMBERS (postHocAxesCheck may have flipped a shank axis), everything else from the values
+    std::vector<double> svals = gb.staticValues();
+    const Unit3* knee[4] = {&m_rkneeAxisThigh, &m_rkneeAxisShank, &m_lkneeAxisThigh, &m_lkneeAxisShank};
+    if (!m_rthighImuOrientation.empty())
+        for (int a = 0; a < 4; a++) {
+            double* v = svals.data() + (gb.staticValue(m_staticVar[12 + a]) - gb.staticValues().data());
+            v[0] = knee[a]->p[0]; v[1] = knee[a]->p[1]; v[2] = knee[a]->p[2];
+        }
+    b200_status stt = b200_set_values(prob, gb.timeValues().data(), svals.data());
     if (stt == B200_OK) stt = b200_lower_body_joint_angles(prob, &d, ang.data());
     b200_problem_destroy(prob);
     if (stt != B200_OK) throw std::runtime_error(std::string("b200_lower_body_joint_angles: ") + b200_last_error());

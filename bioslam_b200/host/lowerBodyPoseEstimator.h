@@ -3,6 +3,8 @@
 // exactly as reference src/lowerBodyPoseEstimator.cpp:361-505 does, as flat factor slots; fastOptimize() is the loop of
 // :639-667 run by the CUDA library.
 #pragma once
+#include <cmath>
+#include "hipDrift.h"
 #include <memory>
 #include "imuPoseEstimator.h"
 
@@ -89,6 +91,14 @@ class lowerBodyPoseEstimator {
     void setMemberEstimatedStatesFromValues();
     // == reference src/lowerBodyPoseEstimator.cpp:813-835; runs b200_lower_body_joint_angles on the device
     void setDerivedJointAnglesFromEstimatedStates(bool verbose = false);
+    bool postHocAxesCheck(bool verbose = false);   // reference :711-797: flips a knee shank axis that points against its thigh axis
+    // hip int/ext rotation drift restart (reference :668-688, :1507-1661; hipDrift.h)
+    double m_hipIeAngDriftRestartThreshold = 100.0 * M_PI / 180.0 / 30.0;   // [rad/s] reference include/lowerBodyPoseEstimator.h:87
+    unsigned m_maxNumRestarts = 100, m_nRestarts = 0;                        // :88
+    void computeHipIeRotAngleRegressionSlopesFromValues(double& rhipIntExtRotSlope, double& lhipIntExtRotSlope);
+    void adjustLegsForCorrectedHipIeAngles(bool verbose = false);
+    int poseVarOfImu(int imu) const { return m_imuVars[imu].pose; }
+    hipdrift::Statics hipDriftStatics() const;
     // the flat description setup() produced and its current values (== m_graph / m_initialValues of the reference)
     const GraphBuilder& graph() const { return *m_gb; }
     GraphBuilder& graph() { return *m_gb; }

@@ -61,11 +61,91 @@ def test_host_error_behaviour(oracle_lib):
         p.setup()                            # EKF initialiser is not part of this build
 
 
+def test_host_post_hoc_axes_check(oracle_lib):
+    """reference src/lowerBodyPoseEstimator.cpp:711-797: a knee SHANK axis that points against its thigh axis (mean angle in
+    the navigation frame > 90 deg) is flipped in the members; the second pass changes nothing; the derived joint angles
+    are those of the consistent axes."""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "cudaemu")])
+    tr = synth.make_trial(seed=8, duration_s=1.5)
+    lb = host.lower_body_from_trial(tr, so_path=EMU)
+    lb.setup()
+    g, tv, sv = lb.graph()
+    tv, sv = graphs.perturbed_truth_values(tr, g, tv, sv)           # kinematically consistent values: knee axes agree
+    lb.set_values(tv, sv)
+    lb.setMemberEstimatedStatesFromValues()
+    assert lb.postHocAxesCheck() is False
+    lb.setDerivedJointAnglesFromEstimatedStates()
+    flex_ok = lb.get("m_rkneeFlexExAng").copy(); lflex_ok = lb.get("m_lkneeFlexExAng").copy()
+    shank_ok = lb.get("m_rkneeAxisShank").copy()
+    # flip the right knee's shank axis in the values (what an optimisation that converged to the mirrored axis would return)
+    so = g.static_value_offsets()
+    sv2 = sv.copy()
+    i_shank = 12 + 1                                                # static table: 12 joint-centre vectors, then the axes (rkneeAxisThigh, rkneeAxisShank, ...)
+    sv2[so[i_shank]:so[i_shank] + 3] *= -1.0
+    lb.set_values(tv, sv2)
+    lb.setMemberEstimatedStatesFromValues()
+    assert np.allclose(lb.get("m_rkneeAxisShank"), -shank_ok)
+    assert lb.postHocAxesCheck() is True
+    assert np.allclose(lb.get("m_rkneeAxisShank"), shank_ok)        # flipped back in the members
+    assert lb.postHocAxesCheck() is False
+    lb.setDerivedJointAnglesFromEstimatedStates()                   # uses the members' axes
+    assert np.allclose(lb.get("m_rkneeFlexExAng"), flex_ok, atol=1e-12) and np.allclose(lb.get("m_lkneeFlexExAng"), lflex_ok, atol=1e-12)
+    _, _, sv_after = lb.graph()
+    assert np.array_equal(sv_after, sv2)                            # like the reference, the optimised values are not touched
+
+
+def test_host_hip_ie_drift_heuristic(oracle_lib):
+    """reference src/lowerBodyPoseEstimator.cpp:668-688, 1507-1661: a hip int/ext rotation angle that drifts
+    linearly in time is detected by its regression slope; adjustLegsForCorrectedHipIeAngles removes the slope by rotating the
+    leg IMUs about the femur's long axis and leaves every joint centre connected."""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "cudaemu")])
+    tr = synth.make_trial(seed=8, duration_s=4.0)
+    lb = host.lower_body_from_trial(tr, so_path=EMU)
+    lb.setup()
+    g, tv, sv = lb.graph()
+    tv, sv = graphs.perturbed_truth_values(tr, g, tv, sv, rot_noise=0.0, pos_noise=0.0)
+    lb.set_values(tv, sv)
+    r0, l0 = lb.computeHipIeRotAngleRegressionSlopesFromValues()
+    thr = 100.0 * np.pi / 180.0 / 30.0
+    assert abs(r0) < thr and abs(l0) < thr                       # consistent gait: no drift
+    # let the whole right leg drift about the right femur's long axis at 0.2 rad/s, the left leg at -0.15 rad/s
+    t = lb.get("m_time")
+    assert t.size == g.K
+    off, so = g.time_value_offsets(), g.static_value_offsets()
+    pose_var = lambda imu: 3 * imu                              # per IMU: pose, velocity, bias (the angular velocities follow)
+    stat = lambda i: sv[so[i]:so[i] + 3]
+    tv2 = tv.copy()
+    for imus, hip, knee, rate in (((1, 2, 3), stat(3), stat(2), 0.2), ((4, 5, 6), stat(8), stat(7), -0.15)):
+        for k in range(g.K):
+            Rt = tv[k, off[pose_var(imus[0])]:off[pose_var(imus[0])] + 9].reshape(3, 3)
+            axis = Rt @ (hip - knee); axis /= np.linalg.norm(axis)
+            dR = synth.exp_so3((axis * rate * t[k])[None, :])[0]
+            for i in imus:
+                o = off[pose_var(i)]
+                tv2[k, o:o + 9] = (dR @ tv[k, o:o + 9].reshape(3, 3)).reshape(-1)
+    lb.set_values(tv2, sv)
+    r1, l1 = lb.computeHipIeRotAngleRegressionSlopesFromValues()
+    assert abs(abs(r1) - 0.2) < 0.02 and abs(abs(l1) - 0.15) < 0.02 and abs(r1) > thr and abs(l1) > thr
+    lb.adjustLegsForCorrectedHipIeAngles()
+    r2, l2 = lb.computeHipIeRotAngleRegressionSlopesFromValues()
+    assert abs(r2) < 1e-9 and abs(l2) < 1e-9                     # adjustRegressionSlopeToTargetSlope asserts 1e-10 upstream
+    _, tv3, sv3 = lb.graph()
+    assert np.array_equal(sv3, sv)
+    assert np.array_equal(tv3[:, off[0]:off[0] + 12], tv2[:, off[0]:off[0] + 12])      # the sacrum IMU does not move
+    def joint(k, imu, vec):
+        o = off[pose_var(imu)]
+        return tv3[k, o:o + 9].reshape(3, 3) @ vec + tv3[k, o + 9:o + 12]
+    for k in (0, g.K // 2, g.K - 1):
+        for (ia, va, ib, vb) in ((0, stat(0), 1, stat(3)), (1, stat(2), 2, stat(4)), (2, stat(5), 3, stat(6)),
+                                 (0, stat(1), 4, stat(8)), (4, stat(7), 5, stat(9)), (5, stat(10), 6, stat(11))):
+            assert np.abs(joint(k, ia, va) - joint(k, ib, vb)).max() < 1e-12
+
+
 @pytest.mark.gpu
 def test_host_fast_optimize_matches_c_abi():
     tr = synth.make_trial(seed=8, duration_s=3.0)
     lb = host.lower_body_from_trial(tr)
-    lb.set(m_maxIterations=12)
+    lb.set(m_maxIterations=12, m_maxNumRestarts=0)           # one LM run: the hip I/E restart hook is tested on its own
     lb.setup()
     g, tv, sv = lb.graph()
     p = lib.Problem(g); p.set_values(tv, sv)
