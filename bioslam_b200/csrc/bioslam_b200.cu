@@ -164,20 +164,20 @@ static b200_status build_asm_plan(b200_problem* p, size_t smem_cap) {
                 const bool a_atk = (kda == B200_AT_K && sel == 0) || (kda == B200_AT_K1 && sel == 1);
                 const bool a_atk1 = (kda == B200_AT_K1 && sel == 0);
                 const int ta = s.tan_off[a], da = s.tan_dim[a], ca = s.col_off[a];
-                if (a_atk) add(1, 1, dm.ns, ta, 1, da, AsmTerm{it, ca, -1, 2});                       // Ax rhs row: -g_k
+                if (a_atk) add(1, 1, dm.ns, ta, 1, da, AsmTerm{it, ca, -1, 2, 0, 0, 0, 0});                       // Ax rhs row: -g_k
                 if (a_static && sel == 0) {
-                    add(0, 1, ta, dm.ns, da, 1, AsmTerm{it, ca, -1, 1});                               // Sx rhs column
-                    add(0, 1, dm.ns, ta, 1, da, AsmTerm{it, ca, -1, 2});                               // Sx rhs row
+                    add(0, 1, ta, dm.ns, da, 1, AsmTerm{it, ca, -1, 1, 0, 0, 0, 0});                               // Sx rhs column
+                    add(0, 1, dm.ns, ta, 1, da, AsmTerm{it, ca, -1, 2, 0, 0, 0, 0});                               // Sx rhs row
                 }
                 for (int b = 0; b < s.nvars; b++) {
                     const int kdb = s.var_kind[b];
                     const bool b_static = kdb == B200_AT_STATIC;
                     const bool b_atk = (kdb == B200_AT_K && sel == 0) || (kdb == B200_AT_K1 && sel == 1);
                     const int tb = s.tan_off[b], db = s.tan_dim[b], cb = s.col_off[b];
-                    if (a_atk && b_atk) add(0, 0, ta, tb, da, db, AsmTerm{it, ca, cb, 0});
-                    else if (a_static && b_static && sel == 0) add(0, 1, ta, tb, da, db, AsmTerm{it, ca, cb, 0});
-                    if (a_atk1 && b_atk) add(1, 0, ta - dm.nl, tb - dm.nl, da, db, AsmTerm{it, ca, cb, 0});
-                    else if (a_static && b_atk) add(1, 1, ta, tb, da, db, AsmTerm{it, ca, cb, 0});
+                    if (a_atk && b_atk) add(0, 0, ta, tb, da, db, AsmTerm{it, ca, cb, 0, 0, 0, 0, 0});
+                    else if (a_static && b_static && sel == 0) add(0, 1, ta, tb, da, db, AsmTerm{it, ca, cb, 0, 0, 0, 0, 0});
+                    if (a_atk1 && b_atk) add(1, 0, ta - dm.nl, tb - dm.nl, da, db, AsmTerm{it, ca, cb, 0, 0, 0, 0, 0});
+                    else if (a_static && b_atk) add(1, 1, ta, tb, da, db, AsmTerm{it, ca, cb, 0, 0, 0, 0, 0});
                 }
             }
         }
@@ -186,7 +186,11 @@ static b200_status build_asm_plan(b200_problem* p, size_t smem_cap) {
     std::vector<AsmBlock> hb[2];
     for (auto& kv : blocks) {
         AsmBlock b{kv.first.which, kv.first.row, kv.first.col, kv.second.da, kv.second.db, (int)terms.size(), 0};
-        terms.insert(terms.end(), kv.second.terms.begin(), kv.second.terms.end());
+        for (AsmTerm t : kv.second.terms) {
+            const AsmItem& im = items[t.item];
+            t.stage_off = im.stage_off; t.rows = p->hslots[im.slot].rows; t.cols = p->hslots[im.slot].cols; t.pad = 0;
+            terms.push_back(t);
+        }
         b.term_end = (int)terms.size();
         if (b.da * b.db > 64) { set_err("internal: destination block larger than 64 entries"); return B200_NOT_IMPLEMENTED; }
         hb[kv.first.half].push_back(b);

@@ -21,6 +21,8 @@
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) { std::memcpy(dst, src, 16); }
 __device__ __forceinline__ void cp_async8(void* dst, const void* src) { std::memcpy(dst, src, 8); }
 __device__ __forceinline__ void cp_async_wait_all() {}
+__device__ __forceinline__ void cp_async_commit() {}
+__device__ __forceinline__ void cp_async_wait_but_last() {}
 __device__ __forceinline__ void prefetch_l2(const void*) {}
 __device__ __forceinline__ void named_bar_sync(int id, int count) { emu::bar_sync(id, count); }
 __device__ __forceinline__ void named_bar_arrive(int id, int count) { emu::bar_arrive(id, count); }
@@ -40,6 +42,9 @@ __device__ __forceinline__ void cp_async8(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+// software pipelines: close the current group of copies / wait for every group but the most recent one
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_last() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // named barriers (ids 1..15; 0 is __syncthreads): producer/consumer hand-over between warp-specialised roles of one CTA.
 // count = number of THREADS (multiple of 32) that arrive in total; memory ordering as for bar.sync.

@@ -34,7 +34,9 @@ struct Dims {
 // One warp owns one destination block at a time and accumulates all of its terms in registers, in table order: no
 // atomics, no barriers between factors, deterministic.
 struct AsmItem { int slot, sel, stage_off; };
-struct AsmTerm { int item, ca, cb, mode; };     // mode 0: J_a^T J_b ; 1: -J_a^T r (column block) ; 2: -(J_a^T r)^T (row block)
+// mode 0: J_a^T J_b ; 1: -J_a^T r (column block) ; 2: -(J_a^T r)^T (row block).  stage_off / rows / cols repeat the item's staging
+// offset and its slot's Jacobian shape so that the term loop needs ONE metadata load per term (no dependent item -> slot chain)
+struct __align__(16) AsmTerm { int item, ca, cb, mode, stage_off, rows, cols, pad; };
 struct AsmBlock { int which, row, col, da, db, term_begin, term_end; };   // which: 0 = B1 (D or O), 1 = B2 (Sx or Ax)
 struct AsmPlan {
     const AsmItem* items; int n_items;
@@ -95,17 +97,29 @@ __global__ void __launch_bounds__(256) assemble_kernel(Dims dm, const DevSlot* _
         for (int t = bk.term_begin; t < bk.term_end; t++) {
             const AsmTerm tm = pl.terms[t];
             if (!valid[tm.item]) continue;
-            const AsmItem im = pl.items[tm.item];
-            const DevSlot& s = slots[im.slot];
-            const int rows = s.rows, cols = s.cols;
-            const double* Js = St + im.stage_off;
+            const int rows = tm.rows, cols = tm.cols;
+            const double* Js = St + tm.stage_off;
             const double* rr = Js + rows * cols;
             if (tm.mode == 0) {
-                if (e0 < ne) for (int r = 0; r < rows; r++) acc0 = fma(Js[r * cols + tm.ca + ia0], Js[r * cols + tm.cb + ib0], acc0);
-                if (e1 < ne) for (int r = 0; r < rows; r++) acc1 = fma(Js[r * cols + tm.ca + ia1], Js[r * cols + tm.cb + ib1], acc1);
+                // both output entries of a lane walk down their two Jacobian columns together (clamped, unused entries are dropped)
+                const double* pa0 = Js + tm.ca + (e0 < ne ? ia0 : 0);
+                const double* pb0 = Js + tm.cb + (e0 < ne ? ib0 : 0);
+                const double* pa1 = Js + tm.ca + (e1 < ne ? ia1 : 0);
+                const double* pb1 = Js + tm.cb + (e1 < ne ? ib1 : 0);
+                if (ne > 32) {
+#pragma unroll 3
+                    for (int r = 0; r < rows; r++, pa0 += cols, pb0 += cols, pa1 += cols, pb1 += cols) {
+                        acc0 = fma(*pa0, *pb0, acc0);
+                        acc1 = fma(*pa1, *pb1, acc1);
+                    }
+                } else {
+#pragma unroll 3
+                    for (int r = 0; r < rows; r++, pa0 += cols, pb0 += cols) acc0 = fma(*pa0, *pb0, acc0);
+                }
             } else {
-                const int j0 = tm.ca + (tm.mode == 1 ? ia0 : ib0);
-                if (e0 < ne) for (int r = 0; r < rows; r++) acc0 = fma(-Js[r * cols + j0], rr[r], acc0);
+                const double* pj = Js + tm.ca + (e0 < ne ? (tm.mode == 1 ? ia0 : ib0) : 0);
+#pragma unroll 3
+                for (int r = 0; r < rows; r++, pj += cols) acc0 = fma(-*pj, rr[r], acc0);
             }
         }
         double* B = bk.which == 0 ? g1 : g2;

@@ -22,13 +22,14 @@
 //      appended rows, which turns them into W^T = L^-T.  L lives in the lower triangle of the shared-memory block while it
 //      is needed, W^T (upper triangle, diagonal included) is what remains; 16 x 16 diagonal blocks are factorised and
 //      inverted by one warp in registers (shuffles), panels and trailing updates run on all warps.
-//   b. every row p of the panel [O_k ; arrow rows] (processed in chunks of <= 64 rows that fit in shared memory):
+//   b. every row p of the panel [O_k ; arrow rows] (processed in chunks of <= 64 rows that fit in shared memory; two
+//      independent groups of warps on alternate 32-row chunks where O_k is block-sparse):
 //        y = p W^T            (forward substitution, one triangular GEMM against the resident W^T)
 //        z = y W  = p M^-1    (second triangular GEMM against the same block)
 //        fill row = z O_k^T   (O_k is block-sparse: packed rows, <= 16 terms per entry for the IMU chain)
 //      y is stored for the Schur complement / back-substitution; the fill rows are the corrections of the next node.
-// All GEMMs run on a register-tiled fp64 micro-kernel (4 x 4 per thread, 16 x 32 per warp, operands in shared memory
-// read as 16-byte pairs, bank-conflict free for a leading dimension == 2 mod 4).  No tensor cores (north_star).
+// All GEMMs run on the fp64 tensor pipe (DMMA, mma.sync m8n8k4; warp tile 16 x 32, operands read from shared memory as
+// scalars, see "micro-kernels" below and DESIGN.md section 3 for why this departs from the north_star's "no tensor cores").
 #pragma once
 #include "kernels_assemble.cuh"
 
@@ -277,6 +278,45 @@ __device__ __forceinline__ void cta_gemm_nt(const double* __restrict__ A, int ld
                 if (m < M && n < N) out(m, n, acc[i][j]);
             }
         }
+    }
+}
+
+// The same with the structurally dead 8 x 8 blocks of a Schur tile left out: only the first NI row blocks exist (last tile
+// row of an h that is not a multiple of 32) and, on a diagonal tile, only the blocks on or below the block diagonal.
+template <int NI, bool DIAG>
+__device__ __forceinline__ void warp_mma_nt32_t(const double* __restrict__ A, int lda, int m0, int M, int r0, int ka, int kb, Acc32& acc) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    constexpr int NJ = DIAG ? NI : 4;
+    const double* ap[NI];
+    const double* bp[NJ];
+#pragma unroll
+    for (int i = 0; i < NI; i++) { int m = m0 + 8 * i + g; if (m > M - 1) m = M - 1; ap[i] = A + (long long)m * lda + t; }
+#pragma unroll
+    for (int j = 0; j < NJ; j++) { int r = r0 + 8 * j + g; if (r > M - 1) r = M - 1; bp[j] = A + (long long)r * lda + t; }
+    for (int k = ka; k < kb; k += 4) {
+        const bool ok = k + t < kb;
+        double a[NI], b[NJ];
+#pragma unroll
+        for (int i = 0; i < NI; i++) a[i] = ok ? ap[i][k] : 0.0;
+#pragma unroll
+        for (int j = 0; j < NJ; j++) b[j] = ok ? bp[j][k] : 0.0;
+#pragma unroll
+        for (int i = 0; i < NI; i++)
+#pragma unroll
+            for (int j = 0; j < (DIAG ? i + 1 : 4); j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+}
+__device__ __forceinline__ void warp_mma_nt32_kind(int ni, bool diag, const double* __restrict__ A, int lda, int m0, int M, int r0, int ka, int kb,
+                                                   Acc32& acc) {
+    switch (ni * 2 + (diag ? 1 : 0)) {
+        case 2: warp_mma_nt32_t<1, false>(A, lda, m0, M, r0, ka, kb, acc); break;
+        case 3: warp_mma_nt32_t<1, true>(A, lda, m0, M, r0, ka, kb, acc); break;
+        case 4: warp_mma_nt32_t<2, false>(A, lda, m0, M, r0, ka, kb, acc); break;
+        case 5: warp_mma_nt32_t<2, true>(A, lda, m0, M, r0, ka, kb, acc); break;
+        case 6: warp_mma_nt32_t<3, false>(A, lda, m0, M, r0, ka, kb, acc); break;
+        case 7: warp_mma_nt32_t<3, true>(A, lda, m0, M, r0, ka, kb, acc); break;
+        case 8: warp_mma_nt32_t<4, false>(A, lda, m0, M, r0, ka, kb, acc); break;
+        default: warp_mma_nt32_t<4, true>(A, lda, m0, M, r0, ka, kb, acc); break;
     }
 }
 
@@ -1209,17 +1249,52 @@ __global__ void __launch_bounds__(B200_SCHUR_THREADS, 1) chain_schur_kernel(Dims
     const int ntiles = nrt * (nrt + 1) / 2;
     const int nsplit = gridDim.y, part = blockIdx.y;          // output tiles dealt round-robin to the CTAs of a chunk
     const int ntl = (ntiles - part + nsplit - 1) / nsplit;    // tiles of this CTA: part, part + nsplit, ...
+    // Tiles of this CTA are dealt to (warp, slot) pairs so that the MMA work -- live 8 x 8 blocks: 16 for a full tile, 10 on the
+    // diagonal, fewer in the last tile row -- is balanced over the four schedulers (warp & 3): heaviest tile first, to the
+    // scheduler with the least work so far, within it to the least loaded warp that still has a free slot.
+    __shared__ int s_asg[32][2], s_wgt[64];
+    auto tile_rc = [](int t, int& r, int& c) { r = 0; while ((r + 1) * (r + 2) / 2 <= t) r++; c = t - r * (r + 1) / 2; };
+    auto tile_ni = [&](int r) { const int rows = h - (r << 5); return rows >= 32 ? 4 : (rows + 7) >> 3; };
+    auto tile_weight = [&](int t) { int r, c; tile_rc(t, r, c); const int ni = tile_ni(r); return r == c ? ni * (ni + 1) / 2 : ni * 4; };
     for (int base = 0; base < ntl; base += 2 * nwarps) {
-        int tr[2], tc[2];
+        const int nhere = (ntl - base < 2 * nwarps) ? (ntl - base) : 2 * nwarps;
+        __syncthreads();
+        const bool balance = a.n >= 8;   // the serial assignment below costs ~10 us: only worth it for a long chunk (level 0)
+        if (!balance) {
+            if ((int)threadIdx.x < 2 * nwarps) {
+                const int w = threadIdx.x % nwarps, sl = threadIdx.x / nwarps;
+                s_asg[w][sl] = ((int)threadIdx.x < nhere) ? (base + (int)threadIdx.x) * nsplit + part : -1;
+            }
+        } else if ((int)threadIdx.x < nhere) s_wgt[threadIdx.x] = tile_weight((base + (int)threadIdx.x) * nsplit + part);
+        __syncthreads();
+        if (balance && threadIdx.x == 0) {
+            int wload[32], sload[4] = {0, 0, 0, 0}, nslot[32];
+            for (int w = 0; w < nwarps; w++) { wload[w] = 0; nslot[w] = 0; s_asg[w][0] = -1; s_asg[w][1] = -1; }
+            for (int it = 0; it < nhere; it++) {
+                int best = -1, bw = -1;
+                for (int i = 0; i < nhere; i++) {
+                    const int w = s_wgt[i];
+                    if (w > bw) { bw = w; best = i; }
+                }
+                s_wgt[best] = -1;
+                int tw = -1;
+                for (int w = 0; w < nwarps; w++) {
+                    if (nslot[w] >= 2) continue;
+                    if (tw < 0 || sload[w & 3] < sload[tw & 3] || (sload[w & 3] == sload[tw & 3] && wload[w] < wload[tw])) tw = w;
+                }
+                s_asg[tw][nslot[tw]++] = (base + best) * nsplit + part;
+                wload[tw] += bw; sload[tw & 3] += bw;
+            }
+        }
+        __syncthreads();
+        int tr[2], tc[2], ni[2];
         bool act[2];
 #pragma unroll
         for (int s = 0; s < 2; s++) {
-            const int tloc = base + s * nwarps + warp;
-            const int t = tloc * nsplit + part;
-            act[s] = tloc < ntl;
-            int r = 0;
-            while ((r + 1) * (r + 2) / 2 <= (act[s] ? t : 0)) r++;
-            tr[s] = r; tc[s] = (act[s] ? t : 0) - r * (r + 1) / 2;
+            const int t = s_asg[warp][s];
+            act[s] = t >= 0;
+            tile_rc(act[s] ? t : 0, tr[s], tc[s]);
+            ni[s] = tile_ni(tr[s]);
         }
         Acc32 acc0, acc1;
 #pragma unroll
@@ -1236,8 +1311,8 @@ __global__ void __launch_bounds__(B200_SCHUR_THREADS, 1) chain_schur_kernel(Dims
                     for (int c = 2 * lane; c < kw; c += 64) cp_async16(Ys + (long long)r * ldy + c, Yg + (long long)r * n + k0 + c);
                 cp_async_wait_all();
                 __syncthreads();
-                if (act[0]) warp_mma_nt32(Ys, ldy, tr[0] << 5, h, tc[0] << 5, 0, kw, acc0);
-                if (act[1]) warp_mma_nt32(Ys, ldy, tr[1] << 5, h, tc[1] << 5, 0, kw, acc1);
+                if (act[0]) warp_mma_nt32_kind(ni[0], tr[0] == tc[0], Ys, ldy, tr[0] << 5, h, tc[0] << 5, 0, kw, acc0);
+                if (act[1]) warp_mma_nt32_kind(ni[1], tr[1] == tc[1], Ys, ldy, tr[1] << 5, h, tc[1] << 5, 0, kw, acc1);
             }
         }
         auto store_tile = [&](int trs, int tcs, const Acc32& acc) {
