@@ -174,7 +174,8 @@ static b200_status build_asm_plan(b200_problem* p, size_t smem_cap) {
                     const bool b_static = kdb == B200_AT_STATIC;
                     const bool b_atk = (kdb == B200_AT_K && sel == 0) || (kdb == B200_AT_K1 && sel == 1);
                     const int tb = s.tan_off[b], db = s.tan_dim[b], cb = s.col_off[b];
-                    if (a_atk && b_atk) add(0, 0, ta, tb, da, db, AsmTerm{it, ca, cb, 0, 0, 0, 0, 0});
+                    // D_k: the solver reads the LOWER triangle only (cp_lower_async): blocks strictly above the diagonal are not built
+                    if (a_atk && b_atk) { if (ta >= tb) add(0, 0, ta, tb, da, db, AsmTerm{it, ca, cb, 0, 0, 0, 0, 0}); }
                     else if (a_static && b_static && sel == 0) add(0, 1, ta, tb, da, db, AsmTerm{it, ca, cb, 0, 0, 0, 0, 0});
                     if (a_atk1 && b_atk) add(1, 0, ta - dm.nl, tb - dm.nl, da, db, AsmTerm{it, ca, cb, 0, 0, 0, 0, 0});
                     else if (a_static && b_atk) add(1, 1, ta, tb, da, db, AsmTerm{it, ca, cb, 0, 0, 0, 0, 0});
@@ -1136,7 +1137,10 @@ b200_status b200_comm_set(b200_problem* p, int32_t world_size, int32_t rank, b20
     if (!p || world_size < 1 || rank < 0 || rank >= world_size) return B200_BAD_ARG;
     CK(cudaSetDevice(p->device));
     p->world = world_size; p->rank = rank; p->ag_fn = ag; p->ar_fn = ar; p->comm_ctx = ctx;
-    return set_partition(p, 0, 0);
+    b200_status st = set_partition(p, 0, 0);
+    // the speculation buffers are sized by the window of a rank: re-create them if the sharding changes afterwards
+    if (st == B200_OK && p->spec_G > 1) st = b200_spec_set(p, p->spec_G, p->spec_g, p->spec_ag, p->spec_ctx);
+    return st;
 }
 
 // lambda speculation: this process belongs to group `group` of `n_groups`; each group is one (possibly sharded) solver
@@ -1201,7 +1205,7 @@ b200_status b200_debug_get_hessian_blocks(b200_problem* p, int32_t k, double* D,
         for (int j = 0; j < ntp; j++) {
             const int ei = p->int2ext[i], ej = p->int2ext[j];
             if (ei < 0 || ej < 0) continue;
-            D[(size_t)ei * nt + ej] = Db[(size_t)i * ntp + j];
+            D[(size_t)ei * nt + ej] = (i >= j) ? Db[(size_t)i * ntp + j] : Db[(size_t)j * ntp + i];   // only the lower triangle is assembled
             // O (k, k+1): rows k, cols k+1 ; device stores (k+1 chain) x (k chain)
             if (k + 1 < p->K && i >= nl && j >= nl) O[(size_t)ej * nt + ei] = Ob[(size_t)(i - nl) * nc + (j - nl)];
         }

@@ -1,6 +1,7 @@
 // Hessian / gradient accumulation (north_star subsystem 2): per-keyframe dense blocks of J^T J built from the whitened
 // per-factor Jacobians (staged in shared memory), one CTA per (keyframe, half):
-//   half 0:  D_k  (ntp x ntp, time block of keyframe k)            + Sx_k ((ns+1) x (ns+1): static block and -g_static)
+//   half 0:  D_k  (ntp x ntp, time block of keyframe k; only the sub-blocks on or below the block diagonal: the solver reads
+//            the lower triangle)                                   + Sx_k ((ns+1) x (ns+1): static block and -g_static)
 //   half 1:  O_k  (nc x nc, chain part of keyframe k+1 vs k)        + Ax_k ((ns+1) x ntp: static rows, last row = -g_k)
 // Every block is owned by exactly one CTA and slots are visited in table order, so the sums are deterministic
 // (no atomics).  Internal tangent order inside a keyframe: [keyframe-local variables (nl) | time-chained variables (nc)].
