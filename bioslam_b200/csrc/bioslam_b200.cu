@@ -416,7 +416,8 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
     {
         cudaFuncAttributes fa;
         CK(cudaFuncGetAttributes(&fa, top_finish_kernel)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
-        CK(cudaFuncGetAttributes(&fa, chain_sweep_kernel)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
+        CK(cudaFuncGetAttributes(&fa, chain_sweep_kernel<false>)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
+        CK(cudaFuncGetAttributes(&fa, chain_sweep_kernel<true>)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
         CK(cudaFuncGetAttributes(&fa, chain_backsub_kernel)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
         CK(cudaFuncGetAttributes(&fa, chain_schur_kernel)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
         CK(cudaFuncGetAttributes(&fa, assemble_kernel)); static_smem = std::max(static_smem, (size_t)fa.sharedSizeBytes);
@@ -453,7 +454,8 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
     }
 #ifndef B200_USE_EMU
     CK(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(p->smem_asm[0], p->smem_asm[1])));
-    CK(cudaFuncSetAttribute(chain_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sweep));
+    CK(cudaFuncSetAttribute(chain_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sweep));
+    CK(cudaFuncSetAttribute(chain_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sweep));
     CK(cudaFuncSetAttribute(chain_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_schur));
     CK(cudaFuncSetAttribute(top_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_backsub));
     CK(cudaFuncSetAttribute(chain_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_backsub));
@@ -729,7 +731,9 @@ __global__ void pack_groups_kernel(Dims dm, Level lv1, const double* Dred, const
 // one level: sweep (CTA per chunk) + arrow Schur complement (CTA per chunk)
 static void launch_level_factor(b200_problem* p, const Level& lv, int c_lo, int c_hi, double lambda) {
     const Dims& dm = p->dm;
-    B200_LAUNCH(chain_sweep_kernel, dim3(c_hi - c_lo, lv.nsplit > 0 ? lv.nsplit : 1), dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, dm, lv, p->sb, lambda, c_lo);
+    const dim3 sgrid(c_hi - c_lo, lv.nsplit > 0 ? lv.nsplit : 1);
+    if (lv.dense_o) B200_LAUNCH(chain_sweep_kernel<true>, sgrid, dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, dm, lv, p->sb, lambda, c_lo);
+    else B200_LAUNCH(chain_sweep_kernel<false>, sgrid, dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, dm, lv, p->sb, lambda, c_lo);
     // few chunks (upper levels): split the output tiles of a chunk's Schur complement over several CTAs
     const int nsplit = (c_hi - c_lo) * 2 <= 148 ? 2 : 1;
     B200_LAUNCH(chain_schur_kernel, dim3(c_hi - c_lo, nsplit), dim3(B200_SCHUR_THREADS), p->smem_schur, p->stream, dm, lv, p->sb, c_lo, p->schur_ldy,
@@ -755,7 +759,7 @@ static b200_status launch_solve(b200_problem* p, double lambda) {
     if (p->time_phases) CK(cudaEventRecord(p->ev[8], p->stream));
     if (nlev >= 1) {
         auto& l0 = p->levels[0];
-        B200_LAUNCH(chain_sweep_kernel, dim3(l0.c_hi - l0.c_lo), dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, dm, l0.dev, p->sb, lambda, l0.c_lo);
+        B200_LAUNCH(chain_sweep_kernel<false>, dim3(l0.c_hi - l0.c_lo), dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, dm, l0.dev, p->sb, lambda, l0.c_lo);
         p->launches++;
         if (p->time_phases) CK(cudaEventRecord(p->ev[9], p->stream));
         B200_LAUNCH(chain_schur_kernel, dim3(l0.c_hi - l0.c_lo), dim3(B200_SCHUR_THREADS), p->smem_schur, p->stream, dm, l0.dev, p->sb, l0.c_lo,

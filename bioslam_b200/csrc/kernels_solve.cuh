@@ -738,6 +738,9 @@ __device__ __forceinline__ void xrow_range(const Dims& dm, const int* orow, bool
     ka = lo; kb = hi > dm.ntp ? dm.ntp : hi;
 }
 
+// DENSE: the coupling blocks are dense (upper levels) -- a compile-time switch, so that the level-0 kernel carries none of the
+// dense-level code (slab streaming) and the dense kernel none of the block-sparse paths
+template <bool DENSE>
 __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
     const int n = dm.ntp, nl = dm.nl, nc = dm.nc, ns1 = dm.ns1, ld = dm.ld, hmax = dm.hmax, CR = dm.cr, ow = dm.ow, owp = dm.owp;
     const long long Fsz = (long long)(nc + hmax) * nc;
@@ -779,7 +782,7 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
         PH_T0();
         __syncthreads();   // previous node done with Ms / Yb / Op
         cp_lower_async(Ms, ld, a.Dsrc + src * n * n, n, n);
-        if (has_x && !a.dense_o) {   // packed rows of O: Op[r][t] = O[r][ozs[r] - nl + t]
+        if (has_x && !DENSE) {   // packed rows of O: Op[r][t] = O[r][ozs[r] - nl + t]
             for (int e = threadIdx.x; e < nc * ow; e += blockDim.x) {
                 const int r = e / ow, t = e - r * ow;
                 const int cc = s_ozs[r] - nl + t;
@@ -847,7 +850,7 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
         // own half of the panel buffer and with its own named barrier (ids 7, 8): one group's load / barrier / epilogue phases
         // overlap the other group's MMA phases.  Dense levels: one group of all warps (the O slabs stream through a shared buffer).
         const int xo = has_x ? nc : 0;
-        const int ngroups = (!a.dense_o && (nwarps & 1) == 0 && ((CR >> 1) & ~15) >= 16) ? 2 : 1;
+        const int ngroups = (!DENSE && (nwarps & 1) == 0 && ((CR >> 1) & ~15) >= 16) ? 2 : 1;
         const int gnw = nwarps / ngroups, gid = warp / gnw, gw = warp - gid * gnw;
         const int gthreads = gnw << 5, gtid = threadIdx.x - gid * gthreads;
         const int CRg = ngroups == 2 ? ((CR >> 1) & ~15) : CR;
@@ -936,7 +939,7 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                 const int m0 = rt << 4;
                 if (act) {
                     int ka = 0, kb = n;
-                    if (seg == 0) xrow_range(dm, s_orow, a.dense_o != 0, r0 + m0, ka, kb);
+                    if (seg == 0) xrow_range(dm, s_orow, DENSE, r0 + m0, ka, kb);
                     int kendA = (bA << 4) + 16; if (kendA > kb) kendA = kb;
                     int kendB = (bB << 4) + 16; if (kendB > kb) kendB = kb;
                     if (bA == bB) kendA = ka;   // single block: only the B half is used
@@ -972,7 +975,7 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                     const int m0 = rt << 4, c0 = ct << 5;
                     if (act) {
                         int ka = 0, kb = n;
-                        if (seg == 0) xrow_range(dm, s_orow, a.dense_o != 0, r0 + m0, ka, kb);
+                        if (seg == 0) xrow_range(dm, s_orow, DENSE, r0 + m0, ka, kb);
                         const int kend = (c0 + 32 < kb) ? c0 + 32 : kb;
                         warp_mma_nn(Ybg, ld, m0, cr, Ms, ld, c0, n, ka, kend, acc);
                     }
@@ -1010,10 +1013,10 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                     int sA = kA, sB = kB;
                     if (seg == 0) {
                         // rows of O: y is zero left of ka; z is only needed up to the last column that feeds the LOWER triangle
-                        int ka, kb; xrow_range(dm, s_orow, a.dense_o != 0, r0 + m0, ka, kb);
+                        int ka, kb; xrow_range(dm, s_orow, DENSE, r0 + m0, ka, kb);
                         if (ka > sA) sA = ka;
                         if (ka > sB) sB = ka;
-                        if (!a.dense_o) { if (kA >= kb) sA = n; if (kB >= kb) sB = n; }
+                        if (!DENSE) { if (kA >= kb) sA = n; if (kB >= kb) sB = n; }
                     }
                     if (bA == bB) sA = n;
                     warp_mma_nt2(Ybg, ld, m0, cr, Ms, ld, kA, kB, n, sA, sB, n, acc);
@@ -1047,9 +1050,9 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
                         int ca = k0;
                         bool need = true;
                         if (seg == 0) {
-                            int ka, kb; xrow_range(dm, s_orow, a.dense_o != 0, r0 + m0, ka, kb);
+                            int ka, kb; xrow_range(dm, s_orow, DENSE, r0 + m0, ka, kb);
                             if (ka > ca) ca = ka;
-                            if (!a.dense_o && k0 >= kb) need = false;
+                            if (!DENSE && k0 >= kb) need = false;
                         }
                         if (need) warp_mma_nt(Ybg, ld, m0, cr, Ms, ld, k0, n, ca, n, acc);
                     }
@@ -1071,7 +1074,7 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
             }
             PH_ADD(5);
             // ---- fill rows  F = z[:, chain] O^T
-            if (a.dense_o) {
+            if (DENSE) {
                 // dense coupling block: O streams through two 16-column slabs (cp.async), accumulators stay in registers
                 const int nsl = (n - kz0 + 15) >> 4;
                 const int nctf = (nc + 31) >> 5;
@@ -1226,12 +1229,13 @@ __device__ __forceinline__ void level_chunk_args(const Dims& dm, const Level& lv
 }
 
 // grid = number of chunks of this level owned by this rank (chunk = c_first + blockIdx.x)
+template <bool DENSE>
 __global__ void __launch_bounds__(B200_SOLVE_THREADS) chain_sweep_kernel(Dims dm, Level lv, SolveBuffers sb, double lambda, int c_first) {
     B200_DYN_SMEM(double, sm);
     SweepArgs a;
     level_chunk_args(dm, lv, sb, c_first + blockIdx.x, a, blockIdx.y);
     a.lambda = lambda;
-    cta_sweep(dm, a, sm);
+    cta_sweep<DENSE>(dm, a, sm);
 }
 
 // Arrow Schur complement of one chunk sweep:  Sacc = sum_nodes ( S_node - Y_node Y_node^T ), lower triangle of h x h.

@@ -15,10 +15,10 @@ T = sum(tot.values())
 print("kernel,launches,total_ms,share,avg_ms")
 for k, v in sorted(tot.items(), key=lambda x: -x[1]): print("%s,%d,%.3f,%.3f,%.4f" % (k, cnt[k], v, v / T, v / cnt[k]))
 if "--solve" in sys.argv:
-    idx = [i for i, s in enumerate(seq) if s[0] == 'chain_sweep_kernel' and s[1].startswith('(148')]
+    idx = [i for i, s in enumerate(seq) if 'chain_sweep_kernel' in s[0] and s[1].startswith('(148')]
     i0 = idx[-1]
     print("# one solve (last):")
     j = i0
-    while j < len(seq) and seq[j][0].startswith(('chain_', 'top_')):
+    while j < len(seq) and any(t in seq[j][0] for t in ('chain_', 'top_')):
         print("#  %-32s %-14s %8.3f ms" % seq[j]); j += 1
     print("#  solve total %.3f ms" % sum(s[2] for s in seq[i0:j]))
