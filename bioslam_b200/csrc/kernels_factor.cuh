@@ -41,7 +41,7 @@ __device__ __forceinline__ void load_vars(const DevSlot& s, int k, const double*
 
 // grid: (ceil(max_inst/128), n_slots), block 128.  One thread = one factor instance.
 template <bool WJ>
-__global__ void __launch_bounds__(128) linearize_kernel(const DevSlot* __restrict__ slots, const double* __restrict__ tv,
+__global__ void __launch_bounds__(128, 3) linearize_kernel(const DevSlot* __restrict__ slots, const double* __restrict__ tv,
                                                         const double* __restrict__ sv, const double* __restrict__ cst, long long Kld,
                                                         double* __restrict__ Jbuf, double* __restrict__ rbuf, double* __restrict__ ebuf,
                                                         int k_lo, int k_hi, int e_lo) {
