@@ -153,6 +153,38 @@ def test_partition_independence_and_determinism():
     assert np.abs(auto[0][0] - sols[1][0]).max() <= 1e-5 * np.abs(sols[1][0]).max()
 
 
+def test_full_size_properties_10min_trial():
+    """BASELINE configs[3] at full size (K = 6000, 756 058 unknowns; the oracle would need minutes here): size-independent
+    properties only -- the solve does not depend on the partition beyond rounding, repeated solves are bit-identical, the
+    reduced cost predicted by the linear model is positive, LM decreases the cost monotonically from the reference's initial
+    values and the cost it reports equals the cost recomputed from the final values."""
+    _, g, tv, sv = lower_body(600.0, seed=0, near_truth=False, device_preint=True)
+    assert g.K == 6000
+    sols = []
+    for chunks in (None, None, 74):
+        p = lib.Problem(g, chunks=chunks); p.set_values(tv, sv)
+        if chunks is None:
+            assert p.chunks == 148 and len(p.levels) >= 3
+        p.linearize()
+        st, dt, ds = p.solve(1e-2)
+        assert st == abi.OK
+        sols.append((dt, ds))
+        p.close()
+    assert np.array_equal(sols[0][0], sols[1][0]) and np.array_equal(sols[0][1], sols[1][1])
+    assert np.abs(sols[0][0] - sols[2][0]).max() <= 1e-5 * np.abs(sols[0][0]).max()
+    assert np.abs(sols[0][1] - sols[2][1]).max() <= 1e-5 * max(np.abs(sols[0][1]).max(), 1e-300)
+    p = lib.Problem(g); p.set_values(tv, sv)
+    e_prev = p.lm_begin(abi.LmParams.lower_body())
+    for _ in range(4):
+        st = p.lm_iterate()
+        lin0, lin1 = p.last_trial_scalars()[:2]
+        assert lin1 <= lin0                                   # the accepted step reduces the linearised cost
+        assert st.error < e_prev
+        e_prev = st.error
+    assert abs(p.error() - st.error) <= 1e-12 * st.error
+    p.close()
+
+
 def test_lm_monotone_and_matches_error_recompute():
     _, g, tv, sv = lower_body(60.0, seed=5, near_truth=False, device_preint=True)
     p = lib.Problem(g); p.set_values(tv, sv)
