@@ -30,6 +30,7 @@ def _L(so_path=None):
         for f in ("b200h_ipe_get", "b200h_lbpe_get"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.c_int]
         L.b200h_lbpe_hip_ie_slopes.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.b200h_ekf_forward_backward.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.c_int, C.POINTER(C.c_double)]
         L.b200h_lbpe_values.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.b200h_lbpe_set_values.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L._host_ready = True
@@ -39,6 +40,15 @@ def _L(so_path=None):
 def _ck(L, rc):
     if rc != 0:
         raise HostError(L.b200h_last_error().decode())
+
+
+def ekf_forward_backward(gyro, acc, dt, passes=3, so_path=None):
+    """forward/backward orientation EKF (reference src/mathutils.cpp:489-610): quaternions (w, x, y, z) of R[N->B], [n][4]"""
+    L = _L(so_path)
+    gyro = np.ascontiguousarray(gyro, dtype=np.float64); acc = np.ascontiguousarray(acc, dtype=np.float64)
+    q = np.zeros((gyro.shape[0], 4))
+    _ck(L, L.b200h_ekf_forward_backward(gyro.shape[0], D(gyro), D(acc), float(dt), int(passes), D(q)))
+    return q
 
 
 class Imu:

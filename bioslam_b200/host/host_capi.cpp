@@ -2,6 +2,7 @@
 #include <cstring>
 #include <map>
 #include "lowerBodyPoseEstimator.h"
+#include "ekf.h"
 
 using namespace bioslam_b200;
 static thread_local std::string g_err;
@@ -121,6 +122,15 @@ int b200h_lbpe_set(void* pv, const char* name, const double* v, int n) {
 int b200h_lbpe_setup(void* p) { GUARD(((lowerBodyPoseEstimator*)p)->setup()); }
 int b200h_lbpe_fast_optimize(void* p) { GUARD(((lowerBodyPoseEstimator*)p)->fastOptimize()); }
 int b200h_lbpe_set_joint_angles(void* p) { GUARD(((lowerBodyPoseEstimator*)p)->setDerivedJointAnglesFromEstimatedStates()); }
+// forward/backward orientation EKF on raw samples: q_out [n][4] = (w, x, y, z) of R[N->B]
+int b200h_ekf_forward_backward(int n, const double* gyro, const double* acc, double dt, int passes, double* q_out) {
+    try {
+        std::vector<double> g(gyro, gyro + (size_t)n * 3), a(acc, acc + (size_t)n * 3);
+        const std::vector<double> q = bioslam_b200::ekf::forwardBackwardEkf(g, a, dt, (unsigned)passes);
+        std::memcpy(q_out, q.data(), sizeof(double) * q.size());
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
 // returns 1 if an axis was flipped, 0 if not, -1 on error
 int b200h_lbpe_post_hoc_axes_check(void* p) {
     try { return ((lowerBodyPoseEstimator*)p)->postHocAxesCheck(false) ? 1 : 0; } catch (const std::exception& e) { g_err = e.what(); return -1; }

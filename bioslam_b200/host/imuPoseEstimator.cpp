@@ -1,5 +1,6 @@
 // see imuPoseEstimator.h.  Graph topology follows reference src/imuPoseEstimator.cpp:47-60,117-312 line by line.
 #include "imuPoseEstimator.h"
+#include "ekf.h"
 #include <chrono>
 #include <iostream>
 
@@ -43,13 +44,25 @@ void imuPoseEstimator::setupCombinedImuFactor() { setupCommon(true); }
 void imuPoseEstimator::setupImuFactorStaticBias() { setupCommon(false); }
 
 void imuPoseEstimator::setupCommon(bool combined) {
-    if (m_initializationScheme != 0) throw std::runtime_error("unknown initilization scheme. only 0 (zeros) is available in this build.");
+    if (m_initializationScheme > 1) throw std::runtime_error("unknown initilization scheme. choose 0 or 1.");   // :111-113
     if (m_imu.length() < 2 * (unsigned long)m_numMeasToPreint) throw std::runtime_error("imu data too short for the requested preintegration length");
     const double dt = m_imu.getDeltaT();
     m_nKeyframes = getExpectedNumberOfKeyframesFromImuData();
     const unsigned K = m_nKeyframes;
     // initial values: zeros / identity (getInitializationData(), scheme 0, :85-91)
     m_initPose.assign(K, Pose3());
+    if (m_initializationScheme == 1) {
+        // forward/backward orientation EKF, 3 passes; it estimates R[N->B], the graph wants R[B->N] (getInitializationData(), :92-110)
+        const size_t n = m_imu.length();
+        std::vector<double> gy(n * 3), ac(n * 3);
+        for (size_t i = 0; i < n; i++) {
+            gy[3 * i] = m_imu.gx[i]; gy[3 * i + 1] = m_imu.gy[i]; gy[3 * i + 2] = m_imu.gz[i];
+            ac[3 * i] = m_imu.ax[i]; ac[3 * i + 1] = m_imu.ay[i]; ac[3 * i + 2] = m_imu.az[i];
+        }
+        const std::vector<double> q = ekf::forwardBackwardEkf(gy, ac, dt, 3);
+        const std::vector<unsigned> idx = getImuIndecesCorrespondingToKeyframes();
+        for (unsigned k = 0; k < K; k++) ekf::quatToRotBodyToNav(&q[4 * (size_t)idx[k]], m_initPose[k].R.m);
+    }
     m_initVel.assign(K, Vector3(0, 0, 0));
     m_initBias.assign(combined ? K : 1, ConstantBias());
     // estimated time domain (:174, :225): t_0 = relTimeSec[0], t_{k+1} = relTimeSec[j] with j = (k+1)*numMeasToPreint

@@ -22,7 +22,7 @@ class imuPoseEstimator {
     Vector3 m_priorPositionNoise = Vector3(1.0e-3, 1.0e-3, 1.0e-3), m_priorVelocityNoise = Vector3(1.0e-3, 1.0e-3, 1.0e-3);
     double m_priorCompassAngleNoise = 1.0e-3;
     Vector3 m_magnetometerNoise = Vector3(3.0, 3.0, 3.0);
-    unsigned m_initializationScheme = 0;  // 0: zeros.  (1, the F/B EKF of src/mathutils.cpp:489-610, is not built: SURVEY 8(f) N4)
+    unsigned m_initializationScheme = 0;  // 0: zeros; 1: forward/backward orientation EKF (host/ekf.h, reference src/mathutils.cpp:489-610)
     Vector3 m_refVecLocal = Vector3(1.0, 0.0, 0.0), m_refVecNav = Vector3(1.0, 0.0, 0.0);
     double m_relErrDecreaseLimit = 1.0e-8, m_absErrDecreaseLimit = 1.0e-10, m_absErrLimit = 1.0e-12;
     unsigned m_maxIterations = 5000;
