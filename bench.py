@@ -281,8 +281,12 @@ def run_b200(args):
         tj = json.load(open(tpath))
         traffic = tj.get("dram_bytes_per_launch")
         if tj.get("dmma_pipe_pct_of_peak") is not None:
+            # algorithmic fp64 work of the sweep: ~9.5 MFLOP per keyframe, live launch time
+            tfl = units * 9.5e6 / (sweep_ms * 1e-3) / 1e12
             fp64_mma = {"pipe": "DMMA m8n8k4 (mma.sync f64)", "frac_of_issue_peak_ncu": tj["dmma_pipe_pct_of_peak"] / 100.0,
-                        "peak_tflops_measured": tj.get("dmma_peak_tflops_measured"), "source": tj.get("source")}
+                        "achieved_tflops_algorithmic": tfl, "peak_tflops_measured": tj.get("dmma_peak_tflops_measured"),
+                        "frac_algorithmic": tfl / tj["dmma_peak_tflops_measured"] if tj.get("dmma_peak_tflops_measured") else None,
+                        "source": tj.get("source")}
     line = {
         "metric": "lm_iterations_per_sec", "value": value, "unit": "iter/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
