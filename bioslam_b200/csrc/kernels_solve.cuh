@@ -1508,29 +1508,32 @@ __device__ void cta_backsub(const Dims& dm, const SweepArgs& a, const double* co
         }
         cp_async_wait_all();
         __syncthreads();
-        // v = y + W[:, chain] u :  v[c] = y[c] + sum_{k: nl+k <= c} Wt[nl+k][c] u[k]
-        for (int c = threadIdx.x; c < n; c += blockDim.x) {
-            double s0 = yv[c], s1 = 0.0;
-            if (has_x) {
+        // v = y + W[:, chain] u :  v[c] = y[c] + sum_{k: nl+k <= c} Wt[nl+k][c] u[k].  Four adjacent lanes share a column
+        // (k = q, q + 4, ...), partial sums meet through two shuffles: the dependent FMA chain is a quarter as long
+        for (int base = 0; base < 4 * n; base += blockDim.x) {
+            const int idx = base + threadIdx.x;
+            const int c = idx >> 2, q = idx & 3;
+            double s = 0.0;
+            if (has_x && c < n) {
                 const int kmax = c - nl;   // inclusive
-                int k = 0;
-                for (; k + 1 <= kmax; k += 2) {
-                    s0 = fma(Ms[(long long)(nl + k) * ld + c], u[k], s0);
-                    s1 = fma(Ms[(long long)(nl + k + 1) * ld + c], u[k + 1], s1);
-                }
-                if (k <= kmax) s0 = fma(Ms[(long long)(nl + k) * ld + c], u[k], s0);
+                for (int k = q; k <= kmax; k += 4) s = fma(Ms[(long long)(nl + k) * ld + c], u[k], s);
             }
-            v[c] = s0 + s1;
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (q == 0 && c < n) v[c] = yv[c] + s;
         }
         __syncthreads();
-        // delta[k] = - sum_{c >= k} Wt[k][c] v[c] : one warp per row
-        for (int k = warp; k < n; k += nwarps) {
-            const double* row = Ms + (long long)k * ld;
+        // delta[k] = - sum_{c >= k} Wt[k][c] v[c]
+        for (int k0 = 2 * warp; k0 < n; k0 += 2 * nwarps) {   // half a warp per row
+            const int k = k0 + (lane >> 4), hl = lane & 15;
             double s = 0.0;
-            for (int c = k + lane; c < n; c += 32) s = fma(row[c], v[c], s);
+            if (k < n) {
+                const double* row = Ms + (long long)k * ld;
+                for (int c = k + hl; c < n; c += 16) s = fma(row[c], v[c], s);
+            }
 #pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) delta[st * n + k] = -s;
+            for (int o = 8; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (hl == 0 && k < n) delta[st * n + k] = -s;
         }
         __threadfence_block();
     }

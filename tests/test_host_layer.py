@@ -220,3 +220,21 @@ def test_host_single_imu_fast_optimize():
         err = p.get("m_optimizationTotalError")
         assert err[-1] < 1e-5 * err[0]              # reference solution test: final error <= 1e-5 (testImuEstimationSolution.cpp:20,42)
         assert p.get("m_pose").size == K * 12 and p.get("m_gyroBias").size == (3 * K if mode == 1 else 3)
+
+
+@pytest.mark.gpu
+def test_host_single_imu_with_ekf_initialisation():
+    """BASELINE configs[0] (exampleImuPoseEstimation.cpp:21-39): single IMU, static-bias ImuFactor, EKF initialisation scheme 1,
+    compass + position + velocity + bias priors; the reference's solution test asks for a final error <= 1e-5 x initial."""
+    tr = synth.make_trial(seed=4, duration_s=10.0)
+    m = host.Imu(tr.acc[0], tr.gyro[0], tr.time)
+    p = host.ImuPoseEstimator(m, "sacrum")
+    p.set(m_useCompassPrior=1, m_refVecLocal=[0, 1, 0], m_refVecNav=[1, 0, 0], m_initializationScheme=1)
+    p.setImuBiasModelMode(0)
+    p.setup()
+    p.fastOptimize()
+    err = p.get("m_optimizationTotalError")
+    assert err.size >= 2 and np.all(np.diff(err) <= 1e-9 * err[:-1])      # monotone LM history
+    assert err[-1] < 1e-5 * err[0]
+    R = p.get("m_pose").reshape(-1, 12)[:, :9].reshape(-1, 3, 3)
+    assert np.abs(R @ np.swapaxes(R, 1, 2) - np.eye(3)).max() < 1e-9
