@@ -1478,6 +1478,32 @@ __device__ void cta_backsub(const Dims& dm, const SweepArgs& a, const double* co
     double* yv = cx + 256;
     double* part = yv + 256 + 512;
     double* delta = sb.delta;
+    // The factor W^T of the NEXT node travels through registers while this node is processed: every thread owns up to NPRE
+    // 16-byte pairs of the upper triangle (rows r, columns from r & ~1), loads them right after the barrier that opens a node and
+    // writes them to shared memory after the node's last barrier, so the chain never waits for a copy (only the first node does).
+    constexpr int NPRE = 8;
+    int goff[NPRE], soff[NPRE];
+    {
+        const int half = (n + 1) >> 1;
+        long long total = 0;
+        for (int r = 0; r < n; r++) total += half - (r >> 1);
+        const bool fits = total <= (long long)NPRE * blockDim.x;
+        int r = 0;
+        long long row_begin = 0;   // flat index of the first pair of row r
+#pragma unroll
+        for (int j = 0; j < NPRE; j++) {
+            const long long e = (long long)j * blockDim.x + threadIdx.x;
+            goff[j] = -1; soff[j] = -1;
+            if (fits && e < total) {
+                while (e >= row_begin + (half - (r >> 1))) { row_begin += half - (r >> 1); r++; }
+                const int c = 2 * ((r >> 1) + (int)(e - row_begin));
+                goff[j] = r * n + c; soff[j] = r * ld + c;
+            }
+        }
+        if (!fits) goff[0] = -2;   // block too large for the register path: every node is copied synchronously
+    }
+    const bool reg_path = goff[0] != -2;
+    bool staged = false;           // Ms already holds this node's factor (written from registers at the end of the previous node)
     for (int i = a.n - 1; i >= 0; i--) {
         const long long src = a.src0 + i;
         const long long st = a.st_idx ? a.st_idx[i] : src;
@@ -1486,11 +1512,14 @@ __device__ void cta_backsub(const Dims& dm, const SweepArgs& a, const double* co
         if (i + 1 < a.n) nxt = a.st_idx ? a.st_idx[i + 1] : src + 1;
         else if (a.has_right) nxt = right_st;
         __syncthreads();
-        cp_upper_async(Ms, ld, a.Wst + st * n * n, n, n, n);
-        if (i > 0) {   // pull the next factor towards L2
+        if (!staged) cp_upper_async(Ms, ld, a.Wst + st * n * n, n, n, n);
+        double2 pre[NPRE];
+        const bool prefetch = reg_path && i > 0;
+        if (prefetch) {
             const long long stn = a.st_idx ? a.st_idx[i - 1] : src - 1;
             const double* Wn = a.Wst + stn * n * n;
-            for (int e = threadIdx.x * 16; e < n * n; e += blockDim.x * 16) prefetch_l2(Wn + e);
+#pragma unroll
+            for (int j = 0; j < NPRE; j++) pre[j] = goff[j] >= 0 ? ld2(Wn + goff[j]) : make_double2(0.0, 0.0);
         }
         if (has_x) for (int j = threadIdx.x; j < nc; j += blockDim.x) cx[j] = delta[nxt * n + nl + j];
         if (y_ready) for (int c = threadIdx.x; c < n; c += blockDim.x) yv[c] = sb.ybuf[st * n + c];
@@ -1536,6 +1565,13 @@ __device__ void cta_backsub(const Dims& dm, const SweepArgs& a, const double* co
             if (hl == 0 && k < n) delta[st * n + k] = -s;
         }
         __threadfence_block();
+        staged = false;
+        if (prefetch) {
+            __syncthreads();   // every warp is done with this node's factor
+#pragma unroll
+            for (int j = 0; j < NPRE; j++) if (soff[j] >= 0) st2(Ms + soff[j], pre[j].x, pre[j].y);
+            staged = true;
+        }
     }
     __syncthreads();
 }
