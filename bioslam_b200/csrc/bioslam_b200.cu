@@ -93,6 +93,7 @@ struct b200_problem {
     size_t smem_sweep = 0, smem_asm[2] = {0, 0};
     AsmPlan asm_plan{};
     AsmItem* d_asm_items = nullptr; AsmTerm* d_asm_terms = nullptr; AsmBlock* d_asm_blocks[2] = {nullptr, nullptr};
+    AsmElem* d_asm_elems[2] = {nullptr, nullptr};
     double* h_scal = nullptr;  // pinned: SC_COUNT doubles + status
     // LM state
     b200_lm_params lm{};
@@ -205,6 +206,15 @@ static b200_status build_asm_plan(b200_problem* p, size_t smem_cap) {
     for (int h = 0; h < 2; h++) {
         CK(dalloc(&p->d_asm_blocks[h], hb[h].size()));
         CK(cudaMemcpyAsync(p->d_asm_blocks[h], hb[h].data(), sizeof(AsmBlock) * hb[h].size(), cudaMemcpyHostToDevice, p->stream));
+        // entry list, block after block (row-major inside a block)
+        std::vector<AsmElem> he;
+        for (size_t b = 0; b < hb[h].size(); b++)
+            for (int ia = 0; ia < hb[h][b].da; ia++)
+                for (int ib = 0; ib < hb[h][b].db; ib++) he.push_back(AsmElem{(int)b, (short)ia, (short)ib});
+        CK(dalloc(&p->d_asm_elems[h], he.size()));
+        CK(cudaMemcpyAsync(p->d_asm_elems[h], he.data(), sizeof(AsmElem) * he.size(), cudaMemcpyHostToDevice, p->stream));
+        CK(cudaStreamSynchronize(p->stream));   // `he` is a local
+        p->asm_plan.elems[h] = p->d_asm_elems[h]; p->asm_plan.n_elems[h] = (int)he.size();
     }
     CK(cudaStreamSynchronize(p->stream));
     AsmPlan& pl = p->asm_plan;
@@ -232,7 +242,8 @@ void b200_problem_destroy(b200_problem* p) {
     void* ptrs[] = {p->d_tv, p->d_tv_try, p->d_sv, p->d_sv_try, p->d_cst, p->d_stage, p->d_slots, p->d_tvars, p->d_svars, p->d_J, p->d_r,
                     p->d_e, p->d_e2, p->d_D, p->d_O, p->d_A, p->d_S, p->sb.Wst, p->sb.Yst, p->sb.ybuf, p->d_Ftop, p->d_Stop, p->sb.delta, p->sb.dstat,
                     p->d_top_begin, p->d_orow, p->d_ocol, p->d_ozs, p->d_ogrp,
-                    p->sb.scal, p->sb.status, p->d_stageS, p->d_stageF, p->d_pack, p->d_asm_items, p->d_asm_terms, p->d_asm_blocks[0], p->d_asm_blocks[1]};
+                    p->sb.scal, p->sb.status, p->d_stageS, p->d_stageF, p->d_pack, p->d_asm_items, p->d_asm_terms, p->d_asm_blocks[0], p->d_asm_blocks[1],
+                    p->d_asm_elems[0], p->d_asm_elems[1]};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->d_spec_delta) cudaFree(p->d_spec_delta);
     if (p->d_spec_rec) cudaFree(p->d_spec_rec);

@@ -39,10 +39,14 @@ struct AsmItem { int slot, sel, stage_off; };
 // offset and its slot's Jacobian shape so that the term loop needs ONE metadata load per term (no dependent item -> slot chain)
 struct __align__(16) AsmTerm { int item, ca, cb, mode, stage_off, rows, cols, pad; };
 struct AsmBlock { int which, row, col, da, db, term_begin, term_end; };   // which: 0 = B1 (D or O), 1 = B2 (Sx or Ax)
+// one destination ENTRY: block index, position inside the block (the kernel walks entries, one per thread: full lanes whatever the
+// block shapes are; neighbouring lanes mostly belong to the same block and share its term list)
+struct AsmElem { int blk; short ia, ib; };
 struct AsmPlan {
     const AsmItem* items; int n_items;
     const AsmTerm* terms;
     const AsmBlock* blocks[2]; int n_blocks[2];
+    const AsmElem* elems[2]; int n_elems[2];
     int stage_doubles;
 };
 
@@ -86,47 +90,33 @@ __global__ void __launch_bounds__(256) assemble_kernel(Dims dm, const DevSlot* _
     double* g1 = half == 0 ? Dsrc + (long long)k * ntp * ntp : Osrc + (long long)k * nc * nc;
     double* g2 = half == 0 ? Ssrc + (long long)k * ns1 * ns1 : Asrc + (long long)k * ns1 * ntp;
     if (half == 0 && ntp > dm.nt && threadIdx.x == 0) g1[(ntp - 1) * ntp + ntp - 1] = 1.0;  // padding variable: identity
-    // ---- one warp per destination block, terms in table order, result written straight to global memory
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    // ---- one thread per destination entry, terms in table order (fixed summation order), result written straight to global memory
     const AsmBlock* blocks = pl.blocks[half];
-    for (int b = warp; b < pl.n_blocks[half]; b += nwarps) {
-        const AsmBlock bk = blocks[b];
-        const int ne = bk.da * bk.db;
-        double acc0 = 0.0, acc1 = 0.0;
-        const int e0 = lane, e1 = lane + 32;
-        const int ia0 = e0 / bk.db, ib0 = e0 - ia0 * bk.db, ia1 = e1 / bk.db, ib1 = e1 - ia1 * bk.db;
+    const AsmElem* elems = pl.elems[half];
+    for (int e = threadIdx.x; e < pl.n_elems[half]; e += blockDim.x) {
+        const AsmElem el = elems[e];
+        const AsmBlock bk = blocks[el.blk];
+        double acc = 0.0;
         for (int t = bk.term_begin; t < bk.term_end; t++) {
             const AsmTerm tm = pl.terms[t];
             if (!valid[tm.item]) continue;
             const int rows = tm.rows, cols = tm.cols;
             const double* Js = St + tm.stage_off;
-            const double* rr = Js + rows * cols;
             if (tm.mode == 0) {
-                // both output entries of a lane walk down their two Jacobian columns together (clamped, unused entries are dropped)
-                const double* pa0 = Js + tm.ca + (e0 < ne ? ia0 : 0);
-                const double* pb0 = Js + tm.cb + (e0 < ne ? ib0 : 0);
-                const double* pa1 = Js + tm.ca + (e1 < ne ? ia1 : 0);
-                const double* pb1 = Js + tm.cb + (e1 < ne ? ib1 : 0);
-                if (ne > 32) {
+                const double* pa = Js + tm.ca + el.ia;
+                const double* pb = Js + tm.cb + el.ib;
 #pragma unroll 3
-                    for (int r = 0; r < rows; r++, pa0 += cols, pb0 += cols, pa1 += cols, pb1 += cols) {
-                        acc0 = fma(*pa0, *pb0, acc0);
-                        acc1 = fma(*pa1, *pb1, acc1);
-                    }
-                } else {
-#pragma unroll 3
-                    for (int r = 0; r < rows; r++, pa0 += cols, pb0 += cols) acc0 = fma(*pa0, *pb0, acc0);
-                }
+                for (int r = 0; r < rows; r++, pa += cols, pb += cols) acc = fma(*pa, *pb, acc);
             } else {
-                const double* pj = Js + tm.ca + (e0 < ne ? (tm.mode == 1 ? ia0 : ib0) : 0);
+                const double* pj = Js + tm.ca + (tm.mode == 1 ? el.ia : el.ib);
+                const double* rr = Js + rows * cols;
 #pragma unroll 3
-                for (int r = 0; r < rows; r++, pj += cols) acc0 = fma(-*pj, rr[r], acc0);
+                for (int r = 0; r < rows; r++, pj += cols) acc = fma(-*pj, rr[r], acc);
             }
         }
         double* B = bk.which == 0 ? g1 : g2;
         const int ld = bk.which == 0 ? ld1 : ld2;
-        if (e0 < ne) B[(bk.row + ia0) * ld + bk.col + ib0] = acc0;
-        if (e1 < ne) B[(bk.row + ia1) * ld + bk.col + ib1] = acc1;
+        B[(bk.row + el.ia) * ld + bk.col + el.ib] = acc;
     }
 }
 
