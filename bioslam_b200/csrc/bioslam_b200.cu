@@ -712,7 +712,7 @@ static void launch_linearize(b200_problem* p) {
     p->launches++;
     // one extra keyframe on the left: its O block (coupling k_lo-1 -> k_lo) is the left-separator coupling of this window
     const int ka = std::max(p->k_lo - 1, 0);
-    B200_LAUNCH(assemble_kernel, dim3(p->k_hi - ka, 2), dim3(256), std::max(p->smem_asm[0], p->smem_asm[1]), p->stream, p->dm,
+    B200_LAUNCH(assemble_kernel, dim3(p->k_hi - ka), dim3(512), std::max(p->smem_asm[0], p->smem_asm[1]), p->stream, p->dm,
                 p->d_slots, p->asm_plan, p->d_J, p->d_r, ka, 0, p->K, p->d_D, p->d_O, p->d_A, p->d_S);
     p->launches++;
 }

@@ -1,5 +1,5 @@
 // Hessian / gradient accumulation (north_star subsystem 2): per-keyframe dense blocks of J^T J built from the whitened
-// per-factor Jacobians (staged in shared memory), one CTA per (keyframe, half):
+// per-factor Jacobians (staged in shared memory), one CTA per keyframe, both halves from the same staged Jacobians:
 //   half 0:  D_k  (ntp x ntp, time block of keyframe k; only the sub-blocks on or below the block diagonal: the solver reads
 //            the lower triangle)                                   + Sx_k ((ns+1) x (ns+1): static block and -g_static)
 //   half 1:  O_k  (nc x nc, chain part of keyframe k+1 vs k)        + Ax_k ((ns+1) x ntp: static rows, last row = -g_k)
@@ -54,16 +54,14 @@ struct AsmPlan {
 // same at every keyframe and every linearization, each one is rewritten completely (a block whose factors are all outside
 // their keyframe range writes zeros), everything else stays zero.  So a CTA only needs shared memory for the staged
 // Jacobians (several CTAs per SM) and writes ~4 k doubles per keyframe instead of the 38 k of the dense blocks.
-__global__ void __launch_bounds__(256) assemble_kernel(Dims dm, const DevSlot* __restrict__ slots, AsmPlan pl,
+__global__ void __launch_bounds__(512) assemble_kernel(Dims dm, const DevSlot* __restrict__ slots, AsmPlan pl,
                                                        const double* __restrict__ Jbuf, const double* __restrict__ rbuf,
                                                        int k_first, int win_lo, int win_hi,
                                                        double* __restrict__ Dsrc, double* __restrict__ Osrc, double* __restrict__ Asrc,
                                                        double* __restrict__ Ssrc) {
     B200_DYN_SMEM(double, St);  // staged Jacobians (rows*cols) + residuals (rows) of every item
     const int k = k_first + (int)blockIdx.x;
-    const int half = blockIdx.y;
     const int ntp = dm.ntp, nc = dm.nc, ns1 = dm.ns1;
-    const int ld1 = half == 0 ? ntp : nc, ld2 = half == 0 ? ns1 : ntp;
     __shared__ unsigned char valid[256];
     // ---- which items exist at this keyframe; stage their Jacobians (contiguous per-instance records, issued in bulk)
     for (int it = threadIdx.x; it < pl.n_items; it += blockDim.x) {
@@ -87,10 +85,13 @@ __global__ void __launch_bounds__(256) assemble_kernel(Dims dm, const DevSlot* _
     }
     cp_async_wait_all();
     __syncthreads();
+    if (ntp > dm.nt && threadIdx.x == 0) Dsrc[(long long)k * ntp * ntp + (ntp - 1) * ntp + ntp - 1] = 1.0;  // padding variable: identity
+    // ---- one thread per destination entry, terms in table order (fixed summation order), result written straight to global
+    // memory; both halves (D + Sx, then O + Ax) from the same staged Jacobians
+    for (int half = 0; half < 2; half++) {
+    const int ld1 = half == 0 ? ntp : nc, ld2 = half == 0 ? ns1 : ntp;
     double* g1 = half == 0 ? Dsrc + (long long)k * ntp * ntp : Osrc + (long long)k * nc * nc;
     double* g2 = half == 0 ? Ssrc + (long long)k * ns1 * ns1 : Asrc + (long long)k * ns1 * ntp;
-    if (half == 0 && ntp > dm.nt && threadIdx.x == 0) g1[(ntp - 1) * ntp + ntp - 1] = 1.0;  // padding variable: identity
-    // ---- one thread per destination entry, terms in table order (fixed summation order), result written straight to global memory
     const AsmBlock* blocks = pl.blocks[half];
     const AsmElem* elems = pl.elems[half];
     for (int e = threadIdx.x; e < pl.n_elems[half]; e += blockDim.x) {
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(256) assemble_kernel(Dims dm, const DevSlot* _
         double* B = bk.which == 0 ? g1 : g2;
         const int ld = bk.which == 0 ? ld1 : ld2;
         B[(bk.row + el.ia) * ld + bk.col + el.ib] = acc;
+    }
     }
 }
 
