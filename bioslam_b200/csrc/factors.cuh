@@ -291,9 +291,42 @@ __device__ void factor_eval(int type, const double* params, CstRef cst, const do
 }
 
 // whitening: diagonal sigmas in params[0..rows) ; Gaussian factors: packed upper sqrt-information at consts[70..]
+// Gaussian whitening of the IMU factors with compile-time shapes: row i of R J is accumulated in registers (COLS static
+// accumulators) while the rows j >= i of J stream by, every entry of the packed upper sqrt-information is read once
+template <bool WJ, int ROWS, int COLS>
+__device__ __forceinline__ void whiten_gaussian(CstRef cst, double* r, double* J) {
+    int off = 70;
+    for (int i = 0; i < ROWS; i++) {
+        double acc[WJ ? COLS : 1];
+        double accr = 0.0;
+        if (WJ) {
+#pragma unroll
+            for (int c = 0; c < COLS; c++) acc[c] = 0.0;
+        }
+        for (int j = i; j < ROWS; j++) {
+            const double rj = cst[off + j - i];
+            accr = fma(rj, r[j], accr);
+            if (WJ) {
+                const double* Jr = J + j * COLS;
+#pragma unroll
+                for (int c = 0; c < COLS; c++) acc[c] = fma(rj, Jr[c], acc[c]);
+            }
+        }
+        r[i] = accr;
+        if (WJ) {
+            double* Ji = J + i * COLS;
+#pragma unroll
+            for (int c = 0; c < COLS; c++) Ji[c] = acc[c];
+        }
+        off += ROWS - i;
+    }
+}
+
 template <bool WJ>
 __device__ void factor_whiten(int type, const double* params, CstRef cst, double* r, double* J, int cols) {
     const int rows = factor_rows(type);
+    if (type == B200_F_IMU_COMBINED && cols == 30) { whiten_gaussian<WJ, 15, 30>(cst, r, J); return; }
+    if (type == B200_F_IMU_STATICBIAS && cols == 24) { whiten_gaussian<WJ, 9, 24>(cst, r, J); return; }
     if (type == B200_F_IMU_COMBINED || type == B200_F_IMU_STATICBIAS) {
         int off = 70;
         for (int i = 0; i < rows; i++) {
