@@ -293,8 +293,9 @@ __device__ void factor_eval(int type, const double* params, CstRef cst, const do
 // whitening: diagonal sigmas in params[0..rows) ; Gaussian factors: packed upper sqrt-information at consts[70..]
 // Gaussian whitening of the IMU factors with compile-time shapes: row i of R J is accumulated in registers (COLS static
 // accumulators) while the rows j >= i of J stream by, every entry of the packed upper sqrt-information is read once
+// (Jout != nullptr: the whitened rows go straight to the caller's record in global memory instead of back into J)
 template <bool WJ, int ROWS, int COLS>
-__device__ __forceinline__ void whiten_gaussian(CstRef cst, double* r, double* J) {
+__device__ __forceinline__ void whiten_gaussian(CstRef cst, double* r, double* J, double* Jout) {
     int off = 70;
     for (int i = 0; i < ROWS; i++) {
         double acc[WJ ? COLS : 1];
@@ -314,7 +315,7 @@ __device__ __forceinline__ void whiten_gaussian(CstRef cst, double* r, double* J
         }
         r[i] = accr;
         if (WJ) {
-            double* Ji = J + i * COLS;
+            double* Ji = (Jout ? Jout : J) + i * COLS;
 #pragma unroll
             for (int c = 0; c < COLS; c++) Ji[c] = acc[c];
         }
@@ -322,11 +323,12 @@ __device__ __forceinline__ void whiten_gaussian(CstRef cst, double* r, double* J
     }
 }
 
+// returns true if the whitened Jacobian was written to Jout (the caller then skips its own copy)
 template <bool WJ>
-__device__ void factor_whiten(int type, const double* params, CstRef cst, double* r, double* J, int cols) {
+__device__ bool factor_whiten(int type, const double* params, CstRef cst, double* r, double* J, int cols, double* Jout = nullptr) {
     const int rows = factor_rows(type);
-    if (type == B200_F_IMU_COMBINED && cols == 30) { whiten_gaussian<WJ, 15, 30>(cst, r, J); return; }
-    if (type == B200_F_IMU_STATICBIAS && cols == 24) { whiten_gaussian<WJ, 9, 24>(cst, r, J); return; }
+    if (type == B200_F_IMU_COMBINED && cols == 30) { whiten_gaussian<WJ, 15, 30>(cst, r, J, Jout); return WJ && Jout != nullptr; }
+    if (type == B200_F_IMU_STATICBIAS && cols == 24) { whiten_gaussian<WJ, 9, 24>(cst, r, J, Jout); return WJ && Jout != nullptr; }
     if (type == B200_F_IMU_COMBINED || type == B200_F_IMU_STATICBIAS) {
         int off = 70;
         for (int i = 0; i < rows; i++) {
@@ -350,6 +352,7 @@ __device__ void factor_whiten(int type, const double* params, CstRef cst, double
             if (WJ) for (int c = 0; c < cols; c++) J[i * cols + c] *= s;
         }
     }
+    return false;
 }
 
 }  // namespace b200d

@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(128, 3) linearize_kernel(const DevSlot* __rest
     double r[B200_MAX_FACTOR_ROWS];
     double J[WJ ? B200_MAX_FACTOR_ROWS * B200_MAX_FACTOR_COLS : 1];
     factor_eval<WJ>(s.type, s.params, c, x, r, J, s.cols);
-    factor_whiten<WJ>(s.type, s.params, c, r, J, s.cols);
+    double* jout = WJ ? Jbuf + s.J_off + (long long)inst * s.rows * s.cols : nullptr;
+    const bool j_written = factor_whiten<WJ>(s.type, s.params, c, r, J, s.cols, jout);
     double e = 0.0;
     for (int i = 0; i < s.rows; i++) e += r[i] * r[i];
     ebuf[s.e_off + inst] = (k >= e_lo) ? 0.5 * e : 0.0;
@@ -73,9 +74,10 @@ __global__ void __launch_bounds__(128, 3) linearize_kernel(const DevSlot* __rest
         // contiguous chunks; each thread streams its own record, full 32-byte sectors
         double* rp = rbuf + s.r_off + (long long)inst * s.rows;
         for (int i = 0; i < s.rows; i++) rp[i] = r[i];
-        const int ne = s.rows * s.cols;
-        double* jp = Jbuf + s.J_off + (long long)inst * ne;
-        for (int i = 0; i < ne; i++) jp[i] = J[i];
+        if (!j_written) {
+            const int ne = s.rows * s.cols;
+            for (int i = 0; i < ne; i++) jout[i] = J[i];
+        }
     }
 }
 
