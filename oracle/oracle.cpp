@@ -23,6 +23,7 @@
 #include "factors.hpp"
 #include "preint.hpp"
 #include "jointangles.hpp"
+#include "fastsolve.hpp"
 
 using namespace orc;
 
@@ -46,6 +47,10 @@ struct orc_problem {
     double err = 0, lambda = 0;
     int iterations = 0, total_trials = 0;
     int threads = 1;
+    // solver selection: 0 = plain dense block sweep (solve(), the pinned restatement), 1 = orcfast::Solver (fastsolve.hpp)
+    int fast = 0, fast_chunks = 16;
+    bool fast_ready = false;
+    orcfast::Solver fs;
 };
 
 static void var_ptrs(const orc_problem& p, const b200_factor_slot& s, int k, const std::vector<double>& tv, const std::vector<double>& sv,
@@ -64,21 +69,27 @@ static double graph_error(const orc_problem& p, const std::vector<double>& tv, c
     for (const auto& s : p.slots) {
         const FactorInfo& fi = factor_info(s.type);
         const int n = s.k_end - s.k_begin;
-        double sub = 0;
-#pragma omp parallel for reduction(+ : sub) num_threads(p.threads) schedule(static)
-        for (int i = 0; i < n; i++) {
-            int k = s.k_begin + i;
-            const double* x[B200_MAX_FACTOR_VARS];
-            var_ptrs(p, s, k, tv, sv, x);
-            const double* c = s.const_offset >= 0 ? p.consts.data() + (size_t)k * p.cstride + s.const_offset : nullptr;
-            double r[B200_MAX_FACTOR_ROWS];
-            factor_eval(s.type, s.params, c, x, r, nullptr);
-            factor_whiten(s.type, s.params, c, r, nullptr);
-            double e = 0;
-            for (int j = 0; j < fi.rows; j++) e += r[j] * r[j];
-            sub += 0.5 * e;
+        // fixed blocks of 64 instances summed in block order: the result does not depend on the number of threads
+        const int nblk = (n + 63) / 64;
+        std::vector<double> part(nblk, 0.0);
+#pragma omp parallel for num_threads(p.threads) schedule(static)
+        for (int b = 0; b < nblk; b++) {
+            double sub = 0;
+            for (int i = b * 64; i < std::min(n, (b + 1) * 64); i++) {
+                int k = s.k_begin + i;
+                const double* x[B200_MAX_FACTOR_VARS];
+                var_ptrs(p, s, k, tv, sv, x);
+                const double* c = s.const_offset >= 0 ? p.consts.data() + (size_t)k * p.cstride + s.const_offset : nullptr;
+                double r[B200_MAX_FACTOR_ROWS];
+                factor_eval(s.type, s.params, c, x, r, nullptr);
+                factor_whiten(s.type, s.params, c, r, nullptr);
+                double e = 0;
+                for (int j = 0; j < fi.rows; j++) e += r[j] * r[j];
+                sub += 0.5 * e;
+            }
+            part[b] = sub;
         }
-        total += sub;
+        for (int b = 0; b < nblk; b++) total += part[b];
     }
     return total;
 }
@@ -93,6 +104,7 @@ static void linearize(orc_problem& p) {
     std::fill(p.gs.begin(), p.gs.end(), 0.0);
     p.Jw.resize(p.slots.size());
     p.rw.resize(p.slots.size());
+    // ---- whitened residuals and Jacobians of every factor instance
     for (size_t si = 0; si < p.slots.size(); si++) {
         const auto& s = p.slots[si];
         const FactorInfo& fi = factor_info(s.type);
@@ -110,51 +122,73 @@ static void linearize(orc_problem& p) {
             factor_eval(s.type, s.params, c, x, r, J);
             factor_whiten(s.type, s.params, c, r, J);
         }
-        // scatter J^T J and J^T r (sequential over instances: deterministic)
-        int coff[B200_MAX_FACTOR_VARS], cdim[B200_MAX_FACTOR_VARS];
-        {
-            int o = 0;
-            for (int v = 0; v < fi.nvars; v++) { coff[v] = o; cdim[v] = kTanDim[fi.vartype[v]]; o += cdim[v]; }
-        }
-        for (int i = 0; i < n; i++) {
-            int k = s.k_begin + i;
-            const double* r = p.rw[si].data() + (size_t)i * rows;
-            const double* J = p.Jw[si].data() + (size_t)i * rows * cols;
-            for (int a = 0; a < fi.nvars; a++) {
-                const int ka = s.var_kind[a];
-                const int ta = (ka == B200_AT_STATIC) ? p.svtoff[s.var_index[a]] : p.tvtoff[s.var_index[a]];
-                // gradient
-                for (int ia = 0; ia < cdim[a]; ia++) {
-                    double acc = 0;
-                    for (int rr = 0; rr < rows; rr++) acc += J[rr * cols + coff[a] + ia] * r[rr];
-                    if (ka == B200_AT_STATIC) p.gs[ta + ia] += acc;
-                    else p.g[(size_t)(k + (ka == B200_AT_K1)) * nt + ta + ia] += acc;
+    }
+    // ---- J^T J and J^T r gathered per DESTINATION keyframe kk (parallel over kk, fixed order inside: slots in order, for every
+    // slot first the instance kk-1 (its variables at k+1), then the instance kk (its variables at k)).  Static x static terms
+    // are summed per block of 64 keyframes and the blocks are added in order: thread-count independent.
+    const int nblk = (K + 63) / 64;
+    std::vector<double> Spart((size_t)nblk * ns * ns, 0.0), gspart((size_t)nblk * std::max(ns, 1), 0.0);
+#pragma omp parallel for num_threads(p.threads) schedule(static)
+    for (int blk = 0; blk < nblk; blk++) {
+        double* Sb = Spart.data() + (size_t)blk * ns * ns;
+        double* gsb = gspart.data() + (size_t)blk * std::max(ns, 1);
+        for (int kk = blk * 64; kk < std::min(K, (blk + 1) * 64); kk++) {
+            for (size_t si = 0; si < p.slots.size(); si++) {
+                const auto& s = p.slots[si];
+                const FactorInfo& fi = factor_info(s.type);
+                const int cols = factor_ncols(s.type), rows = fi.rows;
+                int coff[B200_MAX_FACTOR_VARS], cdim[B200_MAX_FACTOR_VARS];
+                {
+                    int o = 0;
+                    for (int v = 0; v < fi.nvars; v++) { coff[v] = o; cdim[v] = kTanDim[fi.vartype[v]]; o += cdim[v]; }
                 }
-                for (int b = 0; b < fi.nvars; b++) {
-                    const int kb = s.var_kind[b];
-                    const int tb = (kb == B200_AT_STATIC) ? p.svtoff[s.var_index[b]] : p.tvtoff[s.var_index[b]];
-                    for (int ia = 0; ia < cdim[a]; ia++)
-                        for (int ib = 0; ib < cdim[b]; ib++) {
-                            double acc = 0;
-                            for (int rr = 0; rr < rows; rr++) acc += J[rr * cols + coff[a] + ia] * J[rr * cols + coff[b] + ib];
-                            if (ka == B200_AT_STATIC && kb == B200_AT_STATIC) p.S[(size_t)(ta + ia) * ns + tb + ib] += acc;
-                            else if (ka == B200_AT_STATIC) {  // A[kb][static row][time col]
-                                int kk = k + (kb == B200_AT_K1);
-                                p.A[((size_t)kk * ns + ta + ia) * nt + tb + ib] += acc;
-                            } else if (kb == B200_AT_STATIC) {
-                                // symmetric counterpart is filled by the (static, time) visit
-                            } else if (ka == kb) {
-                                int kk = k + (ka == B200_AT_K1);
-                                p.D[((size_t)kk * nt + ta + ia) * nt + tb + ib] += acc;
-                            } else if (ka == B200_AT_K1 && kb == B200_AT_K) {  // O[k]: rows (k+1), cols (k)
-                                p.O[((size_t)k * nt + ta + ia) * nt + tb + ib] += acc;
+                for (int sel = 1; sel >= 0; sel--) {   // sel 1: instance kk-1 seen from its k+1 side ; sel 0: instance kk
+                    const int k = kk - sel;
+                    if (k < s.k_begin || k >= s.k_end) continue;
+                    const int i = k - s.k_begin;
+                    const double* r = p.rw[si].data() + (size_t)i * rows;
+                    const double* J = p.Jw[si].data() + (size_t)i * rows * cols;
+                    for (int a = 0; a < fi.nvars; a++) {
+                        const int ka = s.var_kind[a];
+                        const bool a_static = ka == B200_AT_STATIC;
+                        const bool a_here = (ka == B200_AT_K && sel == 0) || (ka == B200_AT_K1 && sel == 1);
+                        const bool a_next = (ka == B200_AT_K1 && sel == 0);
+                        const int ta = a_static ? p.svtoff[s.var_index[a]] : p.tvtoff[s.var_index[a]];
+                        if (a_here || (a_static && sel == 0)) {
+                            for (int ia = 0; ia < cdim[a]; ia++) {
+                                double acc = 0;
+                                for (int rr = 0; rr < rows; rr++) acc += J[rr * cols + coff[a] + ia] * r[rr];
+                                if (a_static) gsb[ta + ia] += acc;
+                                else p.g[(size_t)kk * nt + ta + ia] += acc;
                             }
                         }
+                        for (int b = 0; b < fi.nvars; b++) {
+                            const int kb = s.var_kind[b];
+                            const bool b_static = kb == B200_AT_STATIC;
+                            const bool b_here = (kb == B200_AT_K && sel == 0) || (kb == B200_AT_K1 && sel == 1);
+                            const int tb = b_static ? p.svtoff[s.var_index[b]] : p.tvtoff[s.var_index[b]];
+                            double* dst; int ldd;
+                            if (a_here && b_here) { dst = p.D.data() + ((size_t)kk * nt + ta) * nt + tb; ldd = nt; }
+                            else if (a_static && b_static && sel == 0) { dst = Sb + (size_t)ta * ns + tb; ldd = ns; }
+                            else if (a_next && b_here) { dst = p.O.data() + ((size_t)kk * nt + ta) * nt + tb; ldd = nt; }   // O[k]: rows (k+1), cols (k)
+                            else if (a_static && b_here) { dst = p.A.data() + ((size_t)kk * ns + ta) * nt + tb; ldd = nt; }
+                            else continue;
+                            for (int ia = 0; ia < cdim[a]; ia++)
+                                for (int ib = 0; ib < cdim[b]; ib++) {
+                                    double acc = 0;
+                                    for (int rr = 0; rr < rows; rr++) acc += J[rr * cols + coff[a] + ia] * J[rr * cols + coff[b] + ib];
+                                    dst[(size_t)ia * ldd + ib] += acc;
+                                }
+                        }
+                    }
                 }
             }
         }
     }
-    (void)K;
+    for (int blk = 0; blk < nblk; blk++) {
+        for (int i = 0; i < ns * ns; i++) p.S[i] += Spart[(size_t)blk * ns * ns + i];
+        for (int i = 0; i < ns; i++) p.gs[i] += gspart[(size_t)blk * std::max(ns, 1) + i];
+    }
 }
 
 // in-place lower Cholesky of n x n (ld), returns false on non-positive pivot
@@ -316,31 +350,68 @@ static double linear_error(const orc_problem& p, const std::vector<double>& dt, 
         const auto& s = p.slots[si];
         const FactorInfo& fi = factor_info(s.type);
         const int cols = factor_ncols(s.type), rows = fi.rows, n = s.k_end - s.k_begin;
-        double sub = 0;
-        for (int i = 0; i < n; i++) {
-            int k = s.k_begin + i;
-            const double* r = p.rw[si].data() + (size_t)i * rows;
-            const double* J = p.Jw[si].data() + (size_t)i * rows * cols;
-            double dl[B200_MAX_FACTOR_COLS];
-            int o = 0;
-            for (int v = 0; v < fi.nvars; v++) {
-                int dim = kTanDim[fi.vartype[v]];
-                const double* src;
-                if (s.var_kind[v] == B200_AT_STATIC) src = ds.data() + p.svtoff[s.var_index[v]];
-                else src = dt.data() + (size_t)(k + (s.var_kind[v] == B200_AT_K1)) * p.nt + p.tvtoff[s.var_index[v]];
-                for (int j = 0; j < dim; j++) dl[o++] = zero ? 0.0 : src[j];
+        const int nblk = (n + 63) / 64;   // fixed blocks, summed in order (thread-count independent)
+        std::vector<double> part(nblk, 0.0);
+#pragma omp parallel for num_threads(p.threads) schedule(static)
+        for (int b = 0; b < nblk; b++) {
+            double sub = 0;
+            for (int i = b * 64; i < std::min(n, (b + 1) * 64); i++) {
+                int k = s.k_begin + i;
+                const double* r = p.rw[si].data() + (size_t)i * rows;
+                const double* J = p.Jw[si].data() + (size_t)i * rows * cols;
+                double dl[B200_MAX_FACTOR_COLS];
+                int o = 0;
+                for (int v = 0; v < fi.nvars; v++) {
+                    int dim = kTanDim[fi.vartype[v]];
+                    const double* src;
+                    if (s.var_kind[v] == B200_AT_STATIC) src = ds.data() + p.svtoff[s.var_index[v]];
+                    else src = dt.data() + (size_t)(k + (s.var_kind[v] == B200_AT_K1)) * p.nt + p.tvtoff[s.var_index[v]];
+                    for (int j = 0; j < dim; j++) dl[o++] = zero ? 0.0 : src[j];
+                }
+                double e = 0;
+                for (int rr = 0; rr < rows; rr++) {
+                    double v = r[rr];
+                    for (int c = 0; c < cols; c++) v += J[rr * cols + c] * dl[c];
+                    e += v * v;
+                }
+                sub += 0.5 * e;
             }
-            double e = 0;
-            for (int rr = 0; rr < rows; rr++) {
-                double v = r[rr];
-                for (int c = 0; c < cols; c++) v += J[rr * cols + c] * dl[c];
-                e += v * v;
-            }
-            sub += 0.5 * e;
+            part[b] = sub;
         }
-        total += sub;
+        for (int b = 0; b < nblk; b++) total += part[b];
     }
     return total;
+}
+
+// solver dispatch: the plain restatement or the structure-aware fast solver (same system, pinned against each other)
+static bool solve_any(orc_problem& p, double lambda, std::vector<double>& dt, std::vector<double>& ds) {
+    if (!p.fast) return solve(p, lambda, dt, ds);
+    if (!p.fast_ready) {
+        // time-chained dofs: variables of a factor that spans k and k+1; per chain row of O the first column that can be non-zero
+        std::vector<char> chained(p.nt, 0);
+        std::vector<int> ostart(p.nt, p.nt);
+        for (const auto& s : p.slots) {
+            bool spans = false;
+            for (int v = 0; v < s.nvars; v++) spans |= (s.var_kind[v] == B200_AT_K1);
+            if (!spans) continue;
+            const FactorInfo& fi = factor_info(s.type);
+            int lo = p.nt;
+            for (int v = 0; v < s.nvars; v++) if (s.var_kind[v] == B200_AT_K) lo = std::min(lo, p.tvtoff[s.var_index[v]]);
+            for (int v = 0; v < s.nvars; v++) {
+                if (s.var_kind[v] == B200_AT_STATIC) continue;
+                const int t0 = p.tvtoff[s.var_index[v]], d = kTanDim[fi.vartype[v]];
+                for (int j = 0; j < d; j++) { chained[t0 + j] = 1; if (s.var_kind[v] == B200_AT_K1) ostart[t0 + j] = std::min(ostart[t0 + j], lo); }
+            }
+        }
+        for (int i = 0; i < p.nt; i++) if (ostart[i] >= p.nt) ostart[i] = 0;
+        // a row's start column must be a chain dof: move it down to the first chain dof at or after it (conservative: lower)
+        for (int i = 0; i < p.nt; i++) { int e = ostart[i]; while (e > 0 && !chained[e]) e--; if (!chained[e]) e = 0; ostart[i] = e; }
+        p.fs.setup(p.K, p.nt, p.ns, chained, ostart, p.fast_chunks);
+        p.fast_ready = true;
+    }
+    dt.assign((size_t)p.K * p.nt, 0.0);
+    ds.assign(p.ns, 0.0);
+    return p.fs.solve(p.D.data(), p.O.data(), p.A.data(), p.g.data(), p.S.data(), p.gs.data(), lambda, p.threads, dt.data(), ds.data());
 }
 
 extern "C" {
@@ -364,6 +435,8 @@ orc_problem* orc_create(const b200_problem_desc* d) {
 }
 void orc_destroy(orc_problem* p) { delete p; }
 void orc_set_threads(orc_problem* p, int n) { p->threads = n < 1 ? 1 : n; }
+// fast != 0: structure-aware solver (fastsolve.hpp) with `chunks` time chunks (results depend on chunks, not on threads)
+void orc_set_solver(orc_problem* p, int fast, int chunks) { p->fast = fast; p->fast_chunks = chunks < 1 ? 1 : chunks; p->fast_ready = false; }
 int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
@@ -401,7 +474,7 @@ void orc_get_hessian_blocks(const orc_problem* p, int k, double* D, double* O, d
 }
 void orc_get_static_hessian(const orc_problem* p, double* S) { std::copy(p->S.begin(), p->S.end(), S); }
 int orc_solve(orc_problem* p, double lambda, double* dt, double* ds) {
-    bool ok = solve(*p, lambda, p->dt_, p->ds_);
+    bool ok = solve_any(*p, lambda, p->dt_, p->ds_);
     if (!ok) return B200_INDETERMINATE_SYSTEM;
     std::copy(p->dt_.begin(), p->dt_.end(), dt);
     std::copy(p->ds_.begin(), p->ds_.end(), ds);
@@ -428,7 +501,7 @@ int orc_lm_iterate(orc_problem* p, b200_lm_state* st) {
     const b200_lm_params& P = p->lm;
     while (true) {  // tryLambda
         inner++;
-        bool solved = solve(*p, p->lambda, p->dt_, p->ds_);
+        bool solved = solve_any(*p, p->lambda, p->dt_, p->ds_);
         double modelFidelity = 0.0, newError = 0.0;
         bool step_ok = false, stop = false;
         if (solved) {

@@ -24,7 +24,7 @@ def lib():
         L.orc_create.argtypes = [C.POINTER(abi.ProblemDesc)]
         L.orc_error.restype = C.c_double
         for f in ("orc_destroy", "orc_set_threads", "orc_set_values", "orc_get_values", "orc_linearize", "orc_get_gradient",
-                  "orc_get_hessian_blocks", "orc_get_static_hessian", "orc_retract", "orc_lm_begin"):
+                  "orc_get_hessian_blocks", "orc_get_static_hessian", "orc_retract", "orc_lm_begin", "orc_set_solver"):
             getattr(L, f).restype = None
         _lib = L
     return _lib
@@ -58,6 +58,10 @@ class OracleProblem:
         tv = np.zeros((self.K, self.tvd)); sv = np.zeros(max(self.svd, 1))
         self.L.orc_get_values(self.h, D(tv), D(sv))
         return tv, sv[:self.svd]
+
+    def set_solver(self, fast=True, chunks=16):
+        """fast: the structure-aware solver of oracle/fastsolve.hpp (results depend on `chunks`, not on the thread count)"""
+        self.L.orc_set_solver(self.h, C.c_int(1 if fast else 0), C.c_int(chunks))
 
     def error(self):
         return float(self.L.orc_error(self.h))

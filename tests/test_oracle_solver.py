@@ -1,5 +1,6 @@
 """-m "not gpu": the oracle's linear algebra, preintegration and LM loop against independent numpy/scipy computations."""
 import numpy as np
+import pytest
 import scipy.linalg as sl
 from bioslam_b200 import abi, synth
 from oracle import pyoracle as po
@@ -120,3 +121,52 @@ def test_gauss_newton_mode(oracle_lib):
     st = o.lm_iterate()
     # lambda == 0, exactly one solve, the step is taken unconditionally (matlab/src/lowerBodyPoseEstimator.m:1108-1110)
     assert st.lambda_ == 0.0 and st.iterations == 1 and st.inner_trials == 1 and abs(st.error - o.error()) <= 1e-12 * st.error
+
+
+def test_fast_solver_matches_plain_restatement(oracle_lib):
+    """oracle/fastsolve.hpp (local dofs pre-eliminated, chunked, blocked AVX2 kernels: the CPU baseline solver) against the plain
+    dense block sweep on the same damped systems: same normal-equation residual class, for 1..7 chunks, any thread count"""
+    import parity_checks as pc
+    _, g, tv, sv = small_problem(seconds=3.0)
+    o = po.OracleProblem(g, threads=4); o.set_values(tv, sv); o.linearize()
+    for lam in (1e-5, 1e-3, 1.0, 1e3):
+        o.set_solver(False)
+        st, dt0, ds0 = o.solve(lam)
+        r0 = pc.normal_eq_residual(o, g, lam, dt0, ds0)
+        for chunks in (1, 2, 3, 7):
+            o.set_solver(True, chunks)
+            st, dt, ds = o.solve(lam)
+            assert st == 0
+            assert pc.normal_eq_residual(o, g, lam, dt, ds) <= max(10 * r0, 1e-9), (lam, chunks)
+            if lam >= 1.0:
+                assert np.abs(dt - dt0).max() <= 1e-5 * np.abs(dt0).max()
+    # thread count does not change a single bit
+    o.set_solver(True, 3); _, dta, dsa = o.solve(1e-3)
+    o2 = po.OracleProblem(g, threads=1); o2.set_values(tv, sv); o2.linearize(); o2.set_solver(True, 3)
+    _, dtb, dsb = o2.solve(1e-3)
+    assert np.array_equal(dta, dtb) and np.array_equal(dsa, dsb)
+
+
+@pytest.mark.parametrize("static_bias", [False, True])
+def test_fast_solver_single_imu(oracle_lib, static_bias):
+    """no keyframe-local dofs, no statics (dynamic bias) / a 6-dof static arrow (static bias)"""
+    import parity_checks as pc
+    tr = synth.make_trial(seed=4, duration_s=4.0)
+    K = graphs.n_keyframes(tr.N, 10)
+    R0 = tr.poses_at((graphs.keyframe_sample_idx(K, 10) + 1) * tr.dt)["sacrum"][0]
+    g, tv, sv = graphs.single_imu_graph(tr.acc[0], tr.gyro[0], tr.dt, static_bias=static_bias, init_R=R0, ref_local=(0, 1, 0))
+    o = po.OracleProblem(g); o.set_values(tv, sv); o.linearize()
+    for lam in (1e-2, 10.0):
+        o.set_solver(False); _, dt0, ds0 = o.solve(lam)
+        r0 = pc.normal_eq_residual(o, g, lam, dt0, ds0)
+        for chunks in (1, 4):
+            o.set_solver(True, chunks); st, dt, ds = o.solve(lam)
+            assert st == 0 and pc.normal_eq_residual(o, g, lam, dt, ds) <= max(10 * r0, 1e-9)
+
+
+def test_fast_solver_reports_indefinite_system(oracle_lib):
+    _, g, tv, sv = small_problem(seconds=1.0)
+    o = po.OracleProblem(g); o.set_values(tv, sv); o.linearize()
+    o.set_solver(True, 2)
+    st, _, _ = o.solve(-1e12)
+    assert st == abi.INDETERMINATE_SYSTEM
