@@ -1264,6 +1264,35 @@ b200_status b200_debug_solve(b200_problem* p, double lambda, double* delta_time,
     return B200_OK;
 }
 
+// one factor instance on the device from explicit inputs (tests over all factor types against tests/golden/factors.npz)
+b200_status b200_debug_factor_eval(int32_t device, int32_t type, const double* params, const double* consts, const double* xcat,
+                                   int32_t whiten, double* r, double* J) {
+    FInfo fi;
+    if (!finfo(type, fi) || !params || !xcat || !r || !J) { set_err("factor_eval: bad arguments"); return B200_BAD_ARG; }
+    if (fi.nconst > 0 && !consts) { set_err("factor_eval: this factor type needs its constant record"); return B200_BAD_ARG; }
+    CK(cudaSetDevice(device));
+    int nx = 0, cols = 0;
+    for (int v = 0; v < fi.nvars; v++) { nx += kValDim[fi.vt[v]]; cols += kTanDim[fi.vt[v]]; }
+    const int rows = factor_rows(type), nc = std::max(fi.nconst, 1);
+    double *d_prm = nullptr, *d_c = nullptr, *d_x = nullptr, *d_r = nullptr, *d_J = nullptr;
+    int* d_vt = nullptr;
+    auto cleanup = [&]() { cudaFree(d_prm); cudaFree(d_c); cudaFree(d_x); cudaFree(d_r); cudaFree(d_J); cudaFree(d_vt); };
+#define CKF(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { set_err(std::string(#call) + ": " + cudaGetErrorString(e__)); cleanup(); return B200_CUDA_ERROR; } } while (0)
+    CKF(dalloc(&d_prm, (size_t)B200_MAX_FACTOR_PARAMS)); CKF(dalloc(&d_c, (size_t)nc)); CKF(dalloc(&d_x, (size_t)nx));
+    CKF(dalloc(&d_r, (size_t)rows)); CKF(dalloc(&d_J, (size_t)rows * cols)); CKF(dalloc(&d_vt, (size_t)fi.nvars));
+    CKF(cudaMemcpy(d_prm, params, sizeof(double) * B200_MAX_FACTOR_PARAMS, cudaMemcpyHostToDevice));
+    if (fi.nconst > 0) CKF(cudaMemcpy(d_c, consts, sizeof(double) * fi.nconst, cudaMemcpyHostToDevice));
+    CKF(cudaMemcpy(d_x, xcat, sizeof(double) * nx, cudaMemcpyHostToDevice));
+    CKF(cudaMemcpy(d_vt, fi.vt, sizeof(int) * fi.nvars, cudaMemcpyHostToDevice));
+    B200_LAUNCH(factor_eval_kernel, dim3(1), dim3(32), 0, (cudaStream_t)0, type, fi.nvars, d_vt, cols, d_prm, d_c, d_x, whiten, d_r, d_J);
+    CKF(cudaDeviceSynchronize());
+    CKF(cudaGetLastError());
+    CKF(cudaMemcpy(r, d_r, sizeof(double) * rows, cudaMemcpyDeviceToHost));
+    CKF(cudaMemcpy(J, d_J, sizeof(double) * rows * cols, cudaMemcpyDeviceToHost));
+    cleanup();
+    return B200_OK;
+}
+
 // scalars of the last lambda trial: [linear.error(0), linear.error(delta), error(retracted values), -]
 b200_status b200_debug_get_scalars(b200_problem* p, double out[4]) {
     if (!p || !out) return B200_BAD_ARG;

@@ -81,6 +81,36 @@ __global__ void __launch_bounds__(128, 3) linearize_kernel(const DevSlot* __rest
     }
 }
 
+// One factor instance from explicit inputs (parity tests over every factor type): thread 0 evaluates residual + Jacobian of
+// `type` exactly as linearize_kernel does (same factor_eval / factor_whiten device functions).  x: the variables' values
+// concatenated in factor order; consts: the per-keyframe constant record (stride 1).
+__global__ void factor_eval_kernel(int type, int nvars, const int* __restrict__ var_type, int cols, const double* __restrict__ params,
+                                   const double* __restrict__ consts, const double* __restrict__ xcat, int whiten, double* __restrict__ r_out,
+                                   double* __restrict__ J_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double xv[B200_MAX_FACTOR_VARS][12];
+    const double* x[B200_MAX_FACTOR_VARS];
+    int o = 0;
+    for (int v = 0; v < nvars; v++) {
+        const int n = val_dim_of(var_type[v]);
+        for (int c = 0; c < n; c++) xv[v][c] = xcat[o + c];
+        x[v] = xv[v];
+        o += n;
+    }
+    double prm[B200_MAX_FACTOR_PARAMS];
+    for (int i = 0; i < B200_MAX_FACTOR_PARAMS; i++) prm[i] = params[i];
+    CstRef c; c.p = consts; c.stride = 1;
+    double r[B200_MAX_FACTOR_ROWS];
+    double J[B200_MAX_FACTOR_ROWS * B200_MAX_FACTOR_COLS];
+    const int rows = factor_rows(type);
+    for (int i = 0; i < rows * cols; i++) J[i] = 0.0;
+    factor_eval<true>(type, prm, c, x, r, J, cols);
+    bool written = false;
+    if (whiten) written = factor_whiten<true>(type, prm, c, r, J, cols, J_out);
+    for (int i = 0; i < rows; i++) r_out[i] = r[i];
+    if (!written) for (int i = 0; i < rows * cols; i++) J_out[i] = J[i];
+}
+
 // deterministic sum of n doubles: fixed strided partials per thread, fixed shared-memory tree.  grid 1, block 1024.
 __global__ void __launch_bounds__(1024) reduce_sum_kernel(const double* __restrict__ v, long long n, double* __restrict__ out) {
     __shared__ double sh[1024];

@@ -33,8 +33,12 @@ def keyframe_sample_idx(K, n_per):
     return idx
 
 
-def lower_body_graph(trial, n_per=10, preint=None, use_joint_vel=False):
-    """Returns (GraphDesc, time_values [K][168], static_values [69]) for the default 7-IMU configuration."""
+def lower_body_graph(trial, n_per=10, preint=None, use_joint_vel=False, hinge_dim=3, joint_pos_dim=3, magnetometer=False, global_B=(19.5, -5.1, -47.8)):
+    """Returns (GraphDesc, time_values [K][168], static_values [69]) for the 7-IMU configuration.  Defaults = the reference's
+    (include/lowerBodyPoseEstimator.h:24-89); hinge_dim / joint_pos_dim = 1 select the norm-error factors
+    (m_hingeAxisFactorDim / m_jointPosFactorDim, sigma = norm of the 3-vector sigma, src/lowerBodyPoseEstimator.cpp:296-312);
+    magnetometer adds a MagPose3Factor per IMU on every pose k+1 (m_useMagnetometer, src/imuPoseEstimator.cpp:216-220) with a
+    synthetic field measurement R_true^T B_global (sigma 3 uT, include/imuPoseEstimator.h:43)."""
     if preint is None:
         raise ValueError("preint callable required (e.g. bioslam_b200.lib.preintegrate)")
     N = trial.acc.shape[1]
@@ -49,7 +53,7 @@ def lower_body_graph(trial, n_per=10, preint=None, use_joint_vel=False):
     angv = lambda i: 21 + i
     svt = [V] * 12 + [U] * 11
     sidx = {n: i for i, n in enumerate(STATIC_POINTS + STATIC_AXES)}
-    g = abi.GraphDesc(K, tvt, svt, const_stride=7 * 190 + 7 * 3)
+    g = abi.GraphDesc(K, tvt, svt, const_stride=7 * 190 + 7 * 3 + (21 if magnetometer else 0))
     rec = preint(trial.acc, trial.gyro, trial.dt, n_per, np.zeros((7, 6)))  # [7][K-1][190]
     kidx = keyframe_sample_idx(K, n_per)
     for i in range(7):
@@ -67,7 +71,19 @@ def lower_body_graph(trial, n_per=10, preint=None, use_joint_vel=False):
     for i in range(7):
         g.add_slot(abi.F_ANGVEL, [(K_, angv(i)), (K_, bias(i))], [0.000157079633 * 0.5] * 3, const_offset=1330 + 3 * i)
     SAC, RT, RS, RF, LT, LS, LF = range(7)
+    if magnetometer:
+        t_k = (kidx + 1) * trial.dt
+        t_k[0] = 0.0
+        poses_true = trial.poses_at(t_k)
+        Bn = np.asarray(global_B, dtype=float)
+        for i, name in enumerate(synth.IMU_NAMES):
+            Rt = poses_true[name][0]                                  # [K][3][3] body -> nav
+            g.consts[:, 1351 + 3 * i:1354 + 3 * i] = np.einsum("kji,j->ki", Rt, Bn)
+            g.add_slot(abi.F_MAG_POSE3, [(K_, pose(i))], [3.0, 3.0, 3.0] + list(Bn), 1, K, const_offset=1351 + 3 * i)
     def hinge(a, b, axis, sig):
+        if hinge_dim == 1:
+            g.add_slot(abi.F_HINGE_NORM, [(K_, pose(a)), (K_, angv(a)), (K_, pose(b)), (K_, angv(b)), (ST, sidx[axis])], [sig * np.sqrt(3.0)])
+            return
         g.add_slot(abi.F_HINGE_VEC, [(K_, pose(a)), (K_, angv(a)), (K_, pose(b)), (K_, angv(b)), (ST, sidx[axis])], [sig] * 3)
     # knee (:243-246), hip (:213-216), ankle (:265-268)
     hinge(RT, RS, "rkneeAxisThigh", 10.0); hinge(RS, RT, "rkneeAxisShank", 10.0)
@@ -80,6 +96,9 @@ def lower_body_graph(trial, n_per=10, preint=None, use_joint_vel=False):
     kneeN = np.array([6.7348, 12.3006, 10.1090]) * 1.0e-2 * 1.2
     ankN = np.array([7.3741, 6.2212, 4.6993]) * 1.0e-2 * 1.2
     def joint(a, b, sa, sb, sig):
+        if joint_pos_dim == 1:   # expected distance 0 (include/factors/ConstrainedJointCenterPositionFactor.h default)
+            g.add_slot(abi.F_JOINTPOS_NORM, [(K_, pose(a)), (K_, pose(b)), (ST, sidx[sa]), (ST, sidx[sb])], [float(np.linalg.norm(sig)), 0.0])
+            return
         g.add_slot(abi.F_JOINTPOS_VEC, [(K_, pose(a)), (K_, pose(b)), (ST, sidx[sa]), (ST, sidx[sb])], sig)
     joint(SAC, RT, "sacrumImuToRHipCtr", "rthighImuToHipCtr", hipN)
     joint(RT, RS, "rthighImuToKneeCtr", "rshankImuToKneeCtr", kneeN)

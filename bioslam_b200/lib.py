@@ -198,6 +198,20 @@ class Problem:
         self._ck(self.L.b200_spec_set(self.h, C.c_int32(n_groups), C.c_int32(group), self._spec_ag, None))
 
 
+def factor_eval(ftype, params, consts, xcat, whiten=False, device=0, so_path=None):
+    """one factor instance on the device (b200_debug_factor_eval): (r[rows], J[rows][cols])"""
+    L = load(so_path)
+    rows, cols = abi.FACTOR_INFO[ftype][0], sum(abi.TAN_DIM[v] for v in abi.FACTOR_INFO[ftype][1])
+    p = np.zeros(abi.MAX_FACTOR_PARAMS); p[:len(params)] = params
+    c = np.ascontiguousarray(consts if consts is not None and len(consts) else np.zeros(1), dtype=np.float64)
+    x = np.ascontiguousarray(xcat, dtype=np.float64)
+    r = np.zeros(rows); J = np.zeros((rows, cols))
+    st = L.b200_debug_factor_eval(C.c_int32(device), C.c_int32(ftype), D(p), D(c), D(x), C.c_int32(1 if whiten else 0), D(r), D(J))
+    if st != abi.OK:
+        raise B200Error(st, L.b200_last_error().decode())
+    return r, J
+
+
 def preintegrate(acc, gyro, dt, n_per, bias_hat, noise=None, combined=True, device=0, so_path=None):
     """Device preintegration (A0). acc, gyro: [n_imu][n_samples][3] -> records [n_imu][K-1][190|115]."""
     L = load(so_path)

@@ -319,6 +319,12 @@ b200_status b200_debug_get_hessian_blocks(b200_problem* p, int32_t k, double* D,
 b200_status b200_debug_get_static_hessian(b200_problem* p, double* S /*[ns*ns]*/);
 /* solve (J^T J + lambda I) delta = -J^T r on the last linearization */
 b200_status b200_debug_solve(b200_problem* p, double lambda, double* delta_time /*[K][nt]*/, double* delta_static);
+/* one factor instance of `type` evaluated on the device by the same device functions linearize_kernel uses: residual r[rows]
+ * and Jacobian J[rows*cols] (row-major; whitened if whiten != 0).  params: B200_MAX_FACTOR_PARAMS doubles; consts: the factor's
+ * per-keyframe constant record (or NULL); xcat: the variables' values concatenated in factor order.  Replaces, for tests, the
+ * reference's per-factor evaluateError(...) call sites (src/factors/ all .cpp files). */
+b200_status b200_debug_factor_eval(int32_t device, int32_t type, const double* params, const double* consts, const double* xcat,
+                                   int32_t whiten, double* r, double* J);
 /* scalars of the last lambda trial: out[0] = linear.error(0) (== the cost at the linearization point, all ranks summed),
  * out[1] = linear.error(delta), out[2] = cost of the retracted values */
 b200_status b200_debug_get_scalars(b200_problem* p, double out[4]);

@@ -8,8 +8,8 @@ def _oracle_preint(combined):
     return lambda acc, gyro, dt, n_per, bh: pyoracle.preintegrate(acc, gyro, dt, n_per, bh, combined=combined)
 
 
-def lower_body_graph(trial, n_per=10, preint=None, use_joint_vel=False):
-    return _g.lower_body_graph(trial, n_per, preint or _oracle_preint(True), use_joint_vel)
+def lower_body_graph(trial, n_per=10, preint=None, use_joint_vel=False, **kw):
+    return _g.lower_body_graph(trial, n_per, preint or _oracle_preint(True), use_joint_vel, **kw)
 
 
 def single_imu_graph(acc, gyro, dt, n_per=10, static_bias=False, preint=None, init_R=None, ref_local=(0.0, 1.0, 0.0)):

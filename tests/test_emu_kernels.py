@@ -91,3 +91,27 @@ def test_bad_arguments_are_rejected(emu):
     with pytest.raises(lib.B200Error) as e:
         lib.Problem(g, so_path=emu)
     assert e.value.status == abi.BAD_ARG
+
+
+def test_every_factor_type_device_functions(emu):
+    """the device residual / Jacobian functions of all 20 factor types (emulated) against tests/golden/factors.npz"""
+    d = np.load(os.path.join(HERE, "golden", "factors.npz"))
+    for ft in sorted(abi.FACTOR_INFO):
+        r, J = lib.factor_eval(ft, d[f"f{ft}_params"], d[f"f{ft}_consts"], d[f"f{ft}_x"], so_path=emu)
+        assert np.allclose(r, d[f"f{ft}_r"], rtol=1e-13, atol=1e-13), ft
+        assert np.allclose(J, d[f"f{ft}_J"], rtol=1e-12, atol=1e-12), ft
+        rw, Jw = lib.factor_eval(ft, d[f"f{ft}_params"], d[f"f{ft}_consts"], d[f"f{ft}_x"], whiten=True, so_path=emu)
+        ro, Jo = po.factor_eval(ft, d[f"f{ft}_params"], d[f"f{ft}_consts"], d[f"f{ft}_x"], whiten=True)
+        assert np.allclose(rw, ro, rtol=1e-11, atol=1e-11 * max(1.0, np.abs(ro).max())), ft
+        assert np.allclose(Jw, Jo, rtol=1e-11, atol=1e-11 * max(1.0, np.abs(Jo).max())), ft
+
+
+def test_non_default_factor_variants(emu):
+    """norm-error hinge / joint-centre factors and the magnetometer factor inside the lower-body graph"""
+    tr = synth.make_trial(seed=8, duration_s=1.0)
+    g, tv, sv = graphs.lower_body_graph(tr, hinge_dim=1, joint_pos_dim=1, magnetometer=True)
+    tv, sv = graphs.perturbed_truth_values(tr, g, tv, sv)
+    o = po.OracleProblem(g); o.set_values(tv, sv)
+    p = lib.Problem(g, so_path=emu, chunks=2); p.set_values(tv, sv)
+    pc.assert_linearization_parity(p, o, g)
+    pc.assert_solve_parity(p, o, g)

@@ -216,3 +216,58 @@ def test_indeterminate_and_bad_args():
     g.slots[0].k_end = 9
     with pytest.raises(lib.B200Error):
         lib.Problem(g)
+
+
+def test_every_factor_type_on_device_matches_fixtures(po):
+    """all 20 factor types (incl. the non-default HingeJointConstraintNormErrEstAngVel, ConstrainedJointCenterNormPositionFactor,
+    MagPose3Factor and PriorFactor<Pose3>) evaluated by the device functions of linearize_kernel against tests/golden/factors.npz
+    (residual 1e-13, Jacobian 1e-12) and, whitened, against the oracle on the same inputs"""
+    import os
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "factors.npz"))
+    assert len(abi.FACTOR_INFO) == 20
+    for ft in sorted(abi.FACTOR_INFO):
+        params, consts, x = d[f"f{ft}_params"], d[f"f{ft}_consts"], d[f"f{ft}_x"]
+        r, J = lib.factor_eval(ft, params, consts, x)
+        assert np.allclose(r, d[f"f{ft}_r"], rtol=1e-13, atol=1e-13), ft
+        assert np.allclose(J, d[f"f{ft}_J"], rtol=1e-12, atol=1e-12), ft
+        rw, Jw = lib.factor_eval(ft, params, consts, x, whiten=True)
+        ro, Jo = po.factor_eval(ft, params, consts, x, whiten=True)
+        assert np.allclose(rw, ro, rtol=1e-11, atol=1e-11 * max(1.0, np.abs(ro).max())), ft
+        assert np.allclose(Jw, Jo, rtol=1e-11, atol=1e-11 * max(1.0, np.abs(Jo).max())), ft
+
+
+@pytest.mark.parametrize("variant", ["hinge_norm", "jointpos_norm", "magnetometer", "all"])
+def test_non_default_factor_variants_in_the_graph(po, variant):
+    """m_hingeAxisFactorDim = 1, m_jointPosFactorDim = 1, m_useMagnetometer = true (reference src/lowerBodyPoseEstimator.cpp:170,218,
+    248,270; src/imuPoseEstimator.cpp:216-219): linearization, solve and LM parity with the oracle on the CUDA path"""
+    kw = {"hinge_norm": dict(hinge_dim=1), "jointpos_norm": dict(joint_pos_dim=1), "magnetometer": dict(magnetometer=True),
+          "all": dict(hinge_dim=1, joint_pos_dim=1, magnetometer=True)}[variant]
+    tr = synth.make_trial(seed=8, duration_s=4.0)
+    g, tv, sv = graphs.lower_body_graph(tr, **kw)
+    types = {s.type for s in g.slots}
+    if "hinge_dim" in kw: assert abi.F_HINGE_NORM in types and abi.F_HINGE_VEC not in types
+    if "joint_pos_dim" in kw: assert abi.F_JOINTPOS_NORM in types and abi.F_JOINTPOS_VEC not in types
+    if "magnetometer" in kw: assert abi.F_MAG_POSE3 in types
+    tv, sv = graphs.perturbed_truth_values(tr, g, tv, sv)
+    o = po.OracleProblem(g, threads=8); o.set_values(tv, sv)
+    p = lib.Problem(g, chunks=3); p.set_values(tv, sv)
+    pc.assert_linearization_parity(p, o, g)
+    pc.assert_solve_parity(p, o, g, lams=(1e-3, 1.0))
+    o.set_values(tv, sv); p.set_values(tv, sv)
+    pc.assert_lm_parity(p, o, abi.LmParams.lower_body(), 4, rel=2e-2)
+    p.close()
+
+
+def test_pose3_prior_factor_in_a_graph(po):
+    """gtsam::PriorFactor<Pose3> (A11) on the first pose of a single-IMU chain"""
+    tr = synth.make_trial(seed=4, duration_s=3.0)
+    K = graphs.n_keyframes(tr.N, 10)
+    R0 = tr.poses_at((graphs.keyframe_sample_idx(K, 10) + 1) * tr.dt)["sacrum"][0] @ synth.exp_so3(np.random.default_rng(0).normal(scale=0.05, size=(K, 3)))
+    g, tv, sv = graphs.single_imu_graph(tr.acc[0], tr.gyro[0], tr.dt, init_R=R0, ref_local=(0, 1, 0))
+    prior = np.concatenate([synth.exp_so3(np.array([[0.1, -0.2, 0.3]]))[0].ravel(), [0.01, 0.02, -0.03]])
+    g.add_slot(abi.F_PRIOR_POSE3, [(abi.AT_K, 0)], [0.1, 0.1, 0.1, 0.05, 0.05, 0.05] + list(prior), 0, 1)
+    o = po.OracleProblem(g); o.set_values(tv, sv)
+    p = lib.Problem(g, chunks=2); p.set_values(tv, sv)
+    pc.assert_linearization_parity(p, o, g)
+    pc.assert_lm_parity(p, o, abi.LmParams.single_imu(), 3, rel=2e-2)
+    p.close()
