@@ -23,6 +23,14 @@ __device__ __forceinline__ void put33(double* J, int ld, int r0, int c0, const d
         for (int j = 0; j < 3; j++) J[(r0 + i) * ld + c0 + j] = s * M[3 * i + j];
 }
 
+// gradient of the Euclidean norm as gtsam::norm3 defines it (gtsam/geometry/Point3.cpp @4.2): v / |v|, and (1, 1, 1) when
+// |v| <= 1e-10 -- every norm on the path goes through it (reference src/mathutils.cpp:75,754, src/factors/*.cpp), so a
+// degenerate geometry (parallel / anti-parallel vectors, coincident points) keeps a finite Jacobian exactly as upstream
+__device__ __forceinline__ void norm3_grad(const double* v, double n, double* u) {
+    if (fabs(n) > 1e-10) { u[0] = v[0] / n; u[1] = v[1] / n; u[2] = v[2] / n; }
+    else { u[0] = 1.0; u[1] = 1.0; u[2] = 1.0; }
+}
+
 // atan2(|a x b|, a.b) and its gradients (reference src/mathutils.cpp:63-91)
 template <bool WJ>
 __device__ __forceinline__ double unsigned_angle(const double* a, const double* b, double* Ha, double* Hb) {
@@ -31,7 +39,7 @@ __device__ __forceinline__ double unsigned_angle(const double* a, const double* 
     if (WJ) {
         const double D = x * x + y * y;
         const double fy = x / D, fx = -y / D;
-        const double u[3] = {c[0] / y, c[1] / y, c[2] / y};
+        double u[3]; norm3_grad(c, y, u);
         // d|c|/da = u^T(-[b]x) = (b x u)... as row vectors: u^T(-[b]x) = (u x b)^T ... computed explicitly below
         double ub[3], au[3];
         cross3(ub, b, u);   // u^T(-[b]x) = (b x u)^T
@@ -154,7 +162,7 @@ __device__ void factor_eval(int type, const double* params, CstRef cst, const do
         hinge_vec<WJ>(x[0], x[1], x[2], x[3], x[4], e, J3);
         const double n = sqrt(dot3(e, e));
         r[0] = n;
-        if (WJ) for (int c = 0; c < 20; c++) J[c] = (e[0] * J3[c] + e[1] * J3[20 + c] + e[2] * J3[40 + c]) / n;
+        if (WJ) { double u[3]; norm3_grad(e, n, u); for (int c = 0; c < 20; c++) J[c] = u[0] * J3[c] + u[1] * J3[20 + c] + u[2] * J3[40 + c]; }
     } break;
     case B200_F_JOINTPOS_VEC:
     case B200_F_JOINTPOS_NORM: {  // reference src/mathutils.cpp:735-747, src/factors/ConstrainedJointCenterPositionFactor.cpp:12-123
@@ -174,7 +182,7 @@ __device__ void factor_eval(int type, const double* params, CstRef cst, const do
         else {
             const double n = sqrt(dot3(e, e));
             r[0] = n - params[1];
-            if (WJ) for (int c = 0; c < 18; c++) J[c] = (e[0] * J3[c] + e[1] * J3[18 + c] + e[2] * J3[36 + c]) / n;
+            if (WJ) { double u[3]; norm3_grad(e, n, u); for (int c = 0; c < 18; c++) J[c] = u[0] * J3[c] + u[1] * J3[18 + c] + u[2] * J3[36 + c]; }
         }
     } break;
     case B200_F_JOINTVEL_VEC: {  // reference src/factors/ConstrainedJointCenterVelocityFactor.cpp:68-131
@@ -212,14 +220,14 @@ __device__ void factor_eval(int type, const double* params, CstRef cst, const do
             }
         }
         r[0] = e;
-        if (WJ) for (int i = 0; i < 3; i++) { J[i] = dedn * d[i] / n; J[3 + i] = -dedn * d[i] / n; }
+        if (WJ) { double u[3]; norm3_grad(d, n, u); for (int i = 0; i < 3; i++) { J[i] = dedn * u[i]; J[3 + i] = -dedn * u[i]; } }
     } break;
     case B200_F_SEGLEN_DISCREPANCY: {  // reference src/factors/SegmentLengthDiscrepancyFactor.cpp:43-72
         double a[3], b[3];
         for (int i = 0; i < 3; i++) { a[i] = x[0][i] - x[1][i]; b[i] = x[2][i] - x[3][i]; }
         const double na = sqrt(dot3(a, a)), nb = sqrt(dot3(b, b));
         r[0] = na - nb;
-        if (WJ) for (int i = 0; i < 3; i++) { J[i] = a[i] / na; J[3 + i] = -a[i] / na; J[6 + i] = -b[i] / nb; J[9 + i] = b[i] / nb; }
+        if (WJ) { double ua[3], ub[3]; norm3_grad(a, na, ua); norm3_grad(b, nb, ub); for (int i = 0; i < 3; i++) { J[i] = ua[i]; J[3 + i] = -ua[i]; J[6 + i] = -ub[i]; J[9 + i] = ub[i]; } }
     } break;
     case B200_F_ANGLE_AXIS_SEG: {  // reference src/factors/AngleBetweenAxisAndSegmentFactor.cpp:38-92
         const double* k = x[0];

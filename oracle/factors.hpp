@@ -66,6 +66,13 @@ inline void putI3(double* J, int ld, int r0, int c0, double s) {
     for (int i = 0; i < 3; i++) J[(r0 + i) * ld + c0 + i] = s;
 }
 
+// gradient of gtsam::norm3 (gtsam/geometry/Point3.cpp @4.2): v / |v|, and (1, 1, 1) when |v| <= 1e-10.  Every norm of the
+// reference's factors goes through it (src/mathutils.cpp:75,754; src/factors/*.cpp), so degenerate geometry keeps a finite Jacobian.
+inline void norm3_grad(const double* v, double n, double* u) {
+    if (std::fabs(n) > 1e-10) { u[0] = v[0] / n; u[1] = v[1] / n; u[2] = v[2] / n; }
+    else { u[0] = 1.0; u[1] = 1.0; u[2] = 1.0; }
+}
+
 // mathutils::unsignedAngle (reference src/mathutils.cpp:63-91): atan2(||a x b||, a.b) with Jacobians
 inline double unsigned_angle(const double* a, const double* b, double* Ha, double* Hb) {
     double c[3]; v3cross(c, a, b);
@@ -73,7 +80,7 @@ inline double unsigned_angle(const double* a, const double* b, double* Ha, doubl
     if (Ha || Hb) {
         double D = x * x + y * y;
         double dfdy = x / D, dfdx = -y / D;
-        double dydc[3] = {c[0] / y, c[1] / y, c[2] / y};
+        double dydc[3]; norm3_grad(c, y, dydc);
         // dc/da = -[b]x, dc/db = [a]x ; dx/da = b^T, dx/db = a^T
         if (Ha) {
             double Sb[9]; skew(Sb, b);
@@ -226,7 +233,8 @@ inline void factor_eval(int type, const double* params, const double* consts, co
             r[0] = n;
             if (J) {
                 double J3[60]; hinge_jac(h, x[3], J3);
-                for (int c = 0; c < 20; c++) J[c] = (h.e[0] * J3[c] + h.e[1] * J3[20 + c] + h.e[2] * J3[40 + c]) / n;
+                double u[3]; norm3_grad(h.e, n, u);
+                for (int c = 0; c < 20; c++) J[c] = u[0] * J3[c] + u[1] * J3[20 + c] + u[2] * J3[40 + c];
             }
         }
     } break;
@@ -250,7 +258,7 @@ inline void factor_eval(int type, const double* params, const double* consts, co
         } else {  // ConstrainedJointCenterNormPositionFactor: ||e|| - expectedDist
             double n = v3norm(e);
             r[0] = n - params[1];
-            if (J) for (int c = 0; c < 18; c++) J[c] = (e[0] * J3[c] + e[1] * J3[18 + c] + e[2] * J3[36 + c]) / n;
+            if (J) { double u[3]; norm3_grad(e, n, u); for (int c = 0; c < 18; c++) J[c] = u[0] * J3[c] + u[1] * J3[18 + c] + u[2] * J3[36 + c]; }
         }
     } break;
     case B200_F_JOINTVEL_VEC: {  // src/factors/ConstrainedJointCenterVelocityFactor.cpp:68-131
@@ -297,13 +305,13 @@ inline void factor_eval(int type, const double* params, const double* consts, co
             }
         }
         r[0] = e;
-        if (J) for (int i = 0; i < 3; i++) { J[i] = dedn * d[i] / n; J[3 + i] = -dedn * d[i] / n; }
+        if (J) { double u[3]; norm3_grad(d, n, u); for (int i = 0; i < 3; i++) { J[i] = dedn * u[i]; J[3 + i] = -dedn * u[i]; } }
     } break;
     case B200_F_SEGLEN_DISCREPANCY: {  // src/factors/SegmentLengthDiscrepancyFactor.cpp:43-72
         double a[3], b[3]; v3sub(a, x[0], x[1]); v3sub(b, x[2], x[3]);
         double na = v3norm(a), nb = v3norm(b);
         r[0] = na - nb;
-        if (J) for (int i = 0; i < 3; i++) { J[i] = a[i] / na; J[3 + i] = -a[i] / na; J[6 + i] = -b[i] / nb; J[9 + i] = b[i] / nb; }
+        if (J) { double ua[3], ub[3]; norm3_grad(a, na, ua); norm3_grad(b, nb, ub); for (int i = 0; i < 3; i++) { J[i] = ua[i]; J[3 + i] = -ua[i]; J[6 + i] = -ub[i]; J[9 + i] = ub[i]; } }
     } break;
     case B200_F_ANGLE_AXIS_SEG: {  // src/factors/AngleBetweenAxisAndSegmentFactor.cpp:38-92 ; cols [k(2) v1(3) v2(3)]
         const double *k = x[0];

@@ -115,3 +115,18 @@ def test_non_default_factor_variants(emu):
     p = lib.Problem(g, so_path=emu, chunks=2); p.set_values(tv, sv)
     pc.assert_linearization_parity(p, o, g)
     pc.assert_solve_parity(p, o, g)
+
+
+def test_degenerate_geometry_on_device_functions(emu):
+    """same guard as gtsam::norm3 on the device: finite Jacobians at parallel / anti-parallel / coincident configurations,
+    equal to the oracle's"""
+    eye = np.concatenate([np.eye(3).ravel(), np.zeros(3)])
+    half_turn = np.concatenate([np.diag([-1.0, -1.0, 1.0]).ravel(), np.zeros(3)])
+    cases = [(abi.F_POSE3_COMPASS_PRIOR, [1e-3, 0.0, 1, 0, 0, 1, 0, 0, 0, 0, 1], eye),
+             (abi.F_POSE3_COMPASS_PRIOR, [1e-3, 0.0, 1, 0, 0, 1, 0, 0, 0, 0, 1], half_turn),
+             (abi.F_SEGLEN_MAG, [0.01, 0.4], np.array([0.1, 0.2, 0.3, 0.1, 0.2, 0.3])),
+             (abi.F_SEGLEN_DISCREPANCY, [0.002], np.array([0.1, 0.2, 0.3, 0.1, 0.2, 0.3, 0, 0, 0, 0, 0, 1.0]))]
+    for ft, prm, x in cases:
+        r, J = lib.factor_eval(ft, prm, None, x, so_path=emu)
+        ro, Jo = po.factor_eval(ft, prm, None, x)
+        assert np.all(np.isfinite(J)) and np.allclose(J, Jo, atol=1e-14) and np.allclose(r, ro, atol=1e-14)

@@ -152,3 +152,21 @@ def test_factor_with_priors_optimises_to_zero(ft, tight, oracle_lib):
         x = tv2[0]
         r = po.factor_eval(ft, [1] * 24, None, x, jac=False)
         assert np.abs(r).max() < 1e-3, (ft, tight, r)
+
+
+def test_degenerate_geometry_keeps_finite_jacobians_like_gtsam_norm3(oracle_lib):
+    """gtsam::norm3 returns the gradient (1, 1, 1) for |v| <= 1e-10 (gtsam/geometry/Point3.cpp @4.2); every norm of the reference's
+    factors goes through it (src/mathutils.cpp:75,754).  Reachable case: Pose3CompassPrior with the class defaults
+    refVecLocal == refVecNav == [1,0,0]: the literal projection (v x n) x n is MINUS the horizontal projection
+    (src/mathutils.cpp:771-781), so an identity pose gives the anti-parallel case (angle pi) and a half-turn about z the parallel one."""
+    from bioslam_b200 import abi
+    eye = np.concatenate([np.eye(3).ravel(), np.zeros(3)])
+    half_turn = np.concatenate([np.diag([-1.0, -1.0, 1.0]).ravel(), np.zeros(3)])
+    for pose, expect in ((eye, np.pi), (half_turn, 0.0)):
+        r, J = po.factor_eval(abi.F_POSE3_COMPASS_PRIOR, [1e-3, 0.0, 1, 0, 0, 1, 0, 0, 0, 0, 1], None, pose)
+        assert np.all(np.isfinite(J)) and np.isfinite(r[0]) and abs(abs(r[0]) - expect) < 1e-12
+    # coincident points: |v| = 0 -> gradient (1,1,1) for the first point, -(1,1,1) for the second
+    r, J = po.factor_eval(abi.F_SEGLEN_MAG, [0.01, 0.4], None, np.array([0.1, 0.2, 0.3, 0.1, 0.2, 0.3]))
+    assert np.allclose(J, [[1, 1, 1, -1, -1, -1]]) and abs(r[0] + 0.4) < 1e-15
+    r, J = po.factor_eval(abi.F_SEGLEN_DISCREPANCY, [0.002], None, np.array([0.1, 0.2, 0.3, 0.1, 0.2, 0.3, 0, 0, 0, 0, 0, 1.0]))
+    assert np.allclose(J, [[1, 1, 1, -1, -1, -1, 0, 0, 1, 0, 0, -1]])
