@@ -8,6 +8,7 @@
 #include <vector>
 #include "kernels_preint.cuh"
 #include "kernels_solve.cuh"
+#include "kernels_local.cuh"
 #include "kernels_jointangles.cuh"
 
 using namespace b200d;
@@ -49,7 +50,20 @@ static bool finfo(int type, FInfo& f) {
     }
 }
 
-enum { SC_LIN_ERR = 0, SC_MODEL_ERR = 1, SC_NEW_ERR = 2, SC_CUR_ERR = 3, SC_COUNT = 8 };
+enum { SC_LIN_ERR = 0, SC_MODEL_ERR = 1, SC_NEW_ERR = 2, SC_CUR_ERR = 3, SC_FAIL = 4, SC_COUNT = 8 };
+
+// Levenberg-Marquardt state on the device (north_star subsystem 4: "the trust-region / damping update on device"): written by
+// lm_judge_kernel after every lambda trial, read by the host once per iterate().
+struct LmDev {
+    double lambda;       // damping of the LM state (what the next iterate() starts from)
+    double lambda_try;   // damping of the trial being solved (sb.lam points here)
+    double err;          // cost at the current values
+    double new_err;      // cost of the last accepted trial
+    int iterations, total_trials, inner, status;
+    int done;            // the tryLambda loop of this iterate() has ended: queued trials return at once (sb.skip points here)
+    int accepted;        // the try buffers hold the accepted step
+    int pad0, pad1;
+};
 
 struct b200_problem {
     int device = 0;
@@ -58,7 +72,15 @@ struct b200_problem {
     std::vector<int> tvtype, svtype;
     std::vector<b200_factor_slot> slots;
     std::vector<DevSlot> hslots;
-    Dims dm{};
+    Dims dm{};   // assembly / internal tangent layout [local | chain]
+    Dims ds{};   // solver layout: == dm, or the chain dofs only when the keyframe-local dofs are pre-eliminated (kernels_local.cuh)
+    bool use_le = false;
+    LocalElim le{};
+    size_t smem_le = 0;
+    double *d_Dc = nullptr, *d_Ac = nullptr, *d_Sc = nullptr, *d_V = nullptr, *d_Wl = nullptr;
+    double* d_delta = nullptr;   // full step [K][ntp] in internal order (== sb.delta without pre-elimination)
+    LmDev* d_lm = nullptr;
+    LmDev* h_lm = nullptr;       // pinned mirror
     int tvd = 0, svd = 0;
     std::vector<int> tv_valoff, tv_tan_int, tv_tan_ext, sv_valoff, sv_tan;
     std::vector<int> int2ext;  // internal tangent index -> external (or -1 for the padding variable)
@@ -99,9 +121,17 @@ struct b200_problem {
     b200_lm_params lm{};
     double err = 0, lambda = 0;
     int iterations = 0, total_trials = 0;
-    bool have_lin = false;
-    long long launches = 0;
+    bool have_lin = false, err_stale = false, lm_started = false;
+    long long launches = 0, host_syncs = 0;
+    int spec_trials = 2;           // lambda trials queued per host synchronisation (device-resident ladder)
+    bool use_graph = true;         // launch every trial as an instantiated CUDA graph (single rank)
+    int parity = 0;                // which of the two value buffers is current (one trial graph per parity)
+#ifndef B200_USE_EMU
+    cudaGraphExec_t trial_graph[2] = {nullptr, nullptr};
+#endif
+    long long graph_launches = 0;  // kernels inside one trial graph
     cudaEvent_t ev[16] = {};
+    cudaEvent_t tev[4][8] = {};    // per queued trial: phase events (TE_*)
     double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // lin, solve, retract+error, sweep ms, sweep launches, top ms, top launches, backsub ms
     std::vector<float> pending;
     bool time_phases = false;
@@ -128,7 +158,9 @@ static cudaError_t dalloc(T** p, size_t n) {
     return e;
 }
 
-static int choose_ld(int ntp) { int ld = ntp; while ((ld & 3) != 2) ld++; return ld; }
+// shared-memory row stride == 4 mod 8 doubles: the 8 x 4 / 4 x 8 operand fragments of mma.m8n8k4.f64 (lane -> row g = lane >> 2,
+// element t = lane & 3) then fall into 16 distinct 8-byte bank pairs per half warp, for the A role, the NN B role and the NT B role
+static int choose_ld(int ntp) { int ld = ntp; while ((ld & 7) != 4) ld++; return ld; }
 
 // assembly plan: see kernels_assemble.cuh
 static b200_status build_asm_plan(b200_problem* p, size_t smem_cap) {
@@ -234,6 +266,8 @@ static void free_levels(b200_problem* p) {
 
 extern "C" {
 
+static void free_graphs(b200_problem* p);
+
 const char* b200_last_error(void) { return g_last_error.c_str(); }
 
 void b200_problem_destroy(b200_problem* p) {
@@ -245,12 +279,17 @@ void b200_problem_destroy(b200_problem* p) {
                     p->sb.scal, p->sb.status, p->d_stageS, p->d_stageF, p->d_pack, p->d_asm_items, p->d_asm_terms, p->d_asm_blocks[0], p->d_asm_blocks[1],
                     p->d_asm_elems[0], p->d_asm_elems[1]};
     for (void* q : ptrs) if (q) cudaFree(q);
+    if (p->use_le && p->d_delta) cudaFree(p->d_delta);
+    for (void* q : {(void*)p->d_Dc, (void*)p->d_Ac, (void*)p->d_Sc, (void*)p->d_V, (void*)p->d_Wl, (void*)p->d_lm}) if (q) cudaFree(q);
+    if (p->h_lm) cudaFreeHost(p->h_lm);
     if (p->d_spec_delta) cudaFree(p->d_spec_delta);
     if (p->d_spec_rec) cudaFree(p->d_spec_rec);
     if (p->h_spec_rec) cudaFreeHost(p->h_spec_rec);
     free_levels(p);
     if (p->h_scal) cudaFreeHost(p->h_scal);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
+    for (auto& q : p->tev) for (auto& e : q) if (e) cudaEventDestroy(e);
+    free_graphs(p);
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
 }
@@ -305,37 +344,49 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
     Dims& dm = p->dm;
     dm.K = p->K; dm.Kld = (p->K + 3) & ~3LL;
     dm.nt = nt; dm.ntp = nt + (nt & 1); dm.nl = nl; dm.nc = dm.ntp - nl; dm.ns = ns; dm.ns1 = ns + 1;
-    dm.ld = choose_ld(dm.ntp); dm.hmax = dm.ns1 + dm.nc;
-    if (dm.ntp > 256 || dm.hmax > 512) return fail("time block larger than 256 or arrow larger than 512 tangent dims is not supported", B200_NOT_IMPLEMENTED);
+    if (dm.ntp > 256 || dm.ns1 + dm.nc + 1 > 512) return fail("time block larger than 256 or arrow larger than 512 tangent dims is not supported", B200_NOT_IMPLEMENTED);
+    // ---- solver layout: with keyframe-local dofs (and a chain to solve) they are eliminated per keyframe before the sweep, the
+    // chain solver then sees the time-chained dofs only (padded to an even count)
+    p->use_le = nl > 0 && nl <= B200_LE_MAXNL && dm.nc >= 2 && !std::getenv("B200_NO_LOCAL_ELIM");
+    Dims& ds = p->ds;
+    ds = dm;
+    if (p->use_le) { ds.nt = dm.nc; ds.ntp = (dm.nc + 1) & ~1; ds.nl = 0; ds.nc = ds.ntp; }
+    dm.nco = ds.nc;   // O_k is assembled with the solver's chain dimension as its stride
+    ds.nco = ds.nc;
+    ds.ld = choose_ld(ds.ntp); ds.hmax = ds.ns1 + ds.nc;
+    dm.ld = ds.ld; dm.hmax = ds.hmax;
     p->int2ext.assign(dm.ntp, -1);
     for (int v = 0; v < p->ntv; v++) for (int j = 0; j < kTanDim[p->tvtype[v]]; j++) p->int2ext[p->tv_tan_int[v] + j] = p->tv_tan_ext[v] + j;
     // ---- device slots
     p->hslots.resize(p->n_slots);
     for (int si = 0; si < p->n_slots; si++) {
         const auto& s = p->slots[si];
-        DevSlot& ds = p->hslots[si];
+        DevSlot& dsl = p->hslots[si];
         FInfo fi; finfo(s.type, fi);
-        std::memset(&ds, 0, sizeof(ds));
-        ds.type = s.type; ds.k_begin = s.k_begin; ds.k_end = s.k_end; ds.n_inst = s.k_end - s.k_begin;
-        ds.nvars = s.nvars; ds.rows = factor_rows(s.type); ds.const_off = s.const_offset;
+        std::memset(&dsl, 0, sizeof(dsl));
+        dsl.type = s.type; dsl.k_begin = s.k_begin; dsl.k_end = s.k_end; dsl.n_inst = s.k_end - s.k_begin;
+        dsl.nvars = s.nvars; dsl.rows = factor_rows(s.type); dsl.const_off = s.const_offset;
         int col = 0;
         for (int v = 0; v < s.nvars; v++) {
-            ds.var_kind[v] = s.var_kind[v]; ds.var_type[v] = fi.vt[v];
+            dsl.var_kind[v] = s.var_kind[v]; dsl.var_type[v] = fi.vt[v];
             const int idx = s.var_index[v];
-            if (s.var_kind[v] == B200_AT_STATIC) { ds.val_off[v] = p->sv_valoff[idx]; ds.tan_off[v] = p->sv_tan[idx]; }
-            else { ds.val_off[v] = p->tv_valoff[idx]; ds.tan_off[v] = p->tv_tan_int[idx]; }
-            ds.col_off[v] = col; ds.tan_dim[v] = kTanDim[fi.vt[v]]; col += ds.tan_dim[v];
+            if (s.var_kind[v] == B200_AT_STATIC) { dsl.val_off[v] = p->sv_valoff[idx]; dsl.tan_off[v] = p->sv_tan[idx]; }
+            else { dsl.val_off[v] = p->tv_valoff[idx]; dsl.tan_off[v] = p->tv_tan_int[idx]; }
+            dsl.col_off[v] = col; dsl.tan_dim[v] = kTanDim[fi.vt[v]]; col += dsl.tan_dim[v];
         }
-        ds.cols = col;
-        ds.J_off = p->nJ; ds.r_off = p->nr; ds.e_off = p->ne;
-        p->nJ += (long long)ds.rows * ds.cols * ds.n_inst; p->nr += (long long)ds.rows * ds.n_inst; p->ne += ds.n_inst;
-        p->max_inst = std::max(p->max_inst, ds.n_inst);
-        std::memcpy(ds.params, s.params, sizeof(ds.params));
+        dsl.cols = col;
+        dsl.J_off = p->nJ; dsl.r_off = p->nr; dsl.e_off = p->ne;
+        p->nJ += (long long)dsl.rows * dsl.cols * dsl.n_inst; p->nr += (long long)dsl.rows * dsl.n_inst; p->ne += dsl.n_inst;
+        p->max_inst = std::max(p->max_inst, dsl.n_inst);
+        std::memcpy(dsl.params, s.params, sizeof(dsl.params));
     }
     // ---- allocate
     const long long Kld = dm.Kld;
     CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     for (auto& e : p->ev) CK(cudaEventCreate(&e));
+    for (auto& q : p->tev) for (auto& e : q) CK(cudaEventCreate(&e));
+    if (const char* env = std::getenv("B200_NO_GRAPH")) p->use_graph = std::atoi(env) == 0;
+    if (const char* env = std::getenv("B200_SPEC_TRIALS")) p->spec_trials = std::max(1, std::atoi(env));
     CK(dalloc(&p->d_tv, (size_t)p->tvd * Kld)); CK(dalloc(&p->d_tv_try, (size_t)p->tvd * Kld));
     CK(dalloc(&p->d_sv, (size_t)p->svd)); CK(dalloc(&p->d_sv_try, (size_t)p->svd));
     CK(dalloc(&p->d_cst, (size_t)std::max(p->cstride, 1) * Kld));
@@ -344,19 +395,40 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
     CK(dalloc(&p->d_slots, (size_t)p->n_slots)); CK(dalloc(&p->d_tvars, (size_t)p->ntv)); CK(dalloc(&p->d_svars, (size_t)p->nsv));
     CK(dalloc(&p->d_J, (size_t)p->nJ)); CK(dalloc(&p->d_r, (size_t)p->nr)); CK(dalloc(&p->d_e, (size_t)p->ne)); CK(dalloc(&p->d_e2, (size_t)p->ne));
     const size_t K = p->K;
-    CK(dalloc(&p->d_D, K * dm.ntp * dm.ntp)); CK(dalloc(&p->d_O, K * dm.nc * dm.nc));
+    CK(dalloc(&p->d_D, K * dm.ntp * dm.ntp)); CK(dalloc(&p->d_O, K * dm.nco * dm.nco));
     CK(dalloc(&p->d_A, K * dm.ns1 * dm.ntp)); CK(dalloc(&p->d_S, K * dm.ns1 * dm.ns1));
     // assemble_kernel only rewrites the structurally non-zero sub-blocks: everything else is zeroed here, once
-    CK(cudaMemsetAsync(p->d_D, 0, sizeof(double) * K * dm.ntp * dm.ntp, p->stream)); CK(cudaMemsetAsync(p->d_O, 0, sizeof(double) * K * dm.nc * dm.nc, p->stream));
+    CK(cudaMemsetAsync(p->d_D, 0, sizeof(double) * K * dm.ntp * dm.ntp, p->stream)); CK(cudaMemsetAsync(p->d_O, 0, sizeof(double) * K * dm.nco * dm.nco, p->stream));
     CK(cudaMemsetAsync(p->d_A, 0, sizeof(double) * K * dm.ns1 * dm.ntp, p->stream)); CK(cudaMemsetAsync(p->d_S, 0, sizeof(double) * K * dm.ns1 * dm.ns1, p->stream));
-    CK(dalloc(&p->sb.Wst, K * dm.ntp * dm.ntp)); CK(dalloc(&p->sb.Yst, K * (size_t)dm.hmax * dm.ntp)); CK(dalloc(&p->sb.ybuf, K * dm.ntp));
-    CK(dalloc(&p->sb.delta, (K + 1024) * dm.ntp)); CK(dalloc(&p->sb.dstat, (size_t)ns + 1)); CK(dalloc(&p->sb.scal, (size_t)SC_COUNT + 8));   // [SC_COUNT..): rank-local scalars that are NOT all-reduced
+    CK(dalloc(&p->sb.Wst, K * ds.ntp * ds.ntp)); CK(dalloc(&p->sb.Yst, K * (size_t)ds.hmax * ds.ntp)); CK(dalloc(&p->sb.ybuf, K * ds.ntp));
+    CK(dalloc(&p->sb.delta, (K + 1024) * ds.ntp)); CK(dalloc(&p->sb.dstat, (size_t)ns + 1)); CK(dalloc(&p->sb.scal, (size_t)SC_COUNT + 8));   // [SC_COUNT..): rank-local scalars that are NOT all-reduced
     CK(dalloc(&p->sb.status, (size_t)1));
-    CK(dalloc(&p->d_Ftop, (size_t)2 * (dm.nc + dm.hmax) * dm.nc)); CK(dalloc(&p->d_Stop, (size_t)dm.hmax * dm.hmax));
+    CK(dalloc(&p->d_lm, (size_t)1));
+    CK(cudaMemsetAsync(p->d_lm, 0, sizeof(LmDev), p->stream));
+    CK(cudaMallocHost((void**)&p->h_lm, sizeof(LmDev)));
+    std::memset(p->h_lm, 0, sizeof(LmDev));
+    p->sb.lam = &p->d_lm->lambda_try; p->sb.lam_in_sweep = p->use_le ? 0 : 1; p->sb.skip = nullptr;
+    if (p->use_le) {
+        // reduced blocks (what the chain solver reads), the local factors, and the full step in internal order.  Only the entries
+        // local_elim_kernel writes ever change: the padding column / the upper triangle stay zero from here on
+        CK(dalloc(&p->d_Dc, K * ds.ntp * ds.ntp)); CK(dalloc(&p->d_Ac, K * ds.ns1 * ds.ntp)); CK(dalloc(&p->d_Sc, K * ds.ns1 * ds.ns1));
+        CK(cudaMemsetAsync(p->d_Dc, 0, sizeof(double) * K * ds.ntp * ds.ntp, p->stream));
+        CK(cudaMemsetAsync(p->d_Ac, 0, sizeof(double) * K * ds.ns1 * ds.ntp, p->stream));
+        CK(cudaMemsetAsync(p->d_Sc, 0, sizeof(double) * K * ds.ns1 * ds.ns1, p->stream));
+        CK(dalloc(&p->d_V, K * (size_t)(dm.nc + dm.ns1) * nl)); CK(dalloc(&p->d_Wl, K * (size_t)nl * nl));
+        CK(dalloc(&p->d_delta, (K + 1024) * dm.ntp));
+        CK(cudaMemsetAsync(p->d_delta, 0, sizeof(double) * (K + 1024) * dm.ntp, p->stream));
+        LocalElim& le = p->le;
+        le.nl = nl; le.nc = dm.nc; le.ncp = ds.ntp; le.ns1 = dm.ns1; le.ntp = dm.ntp; le.ldl = le_ldl(nl);
+        le.D = p->d_D; le.A = p->d_A; le.S = p->d_S; le.Dc = p->d_Dc; le.Ac = p->d_Ac; le.Sc = p->d_Sc; le.V = p->d_V; le.Wl = p->d_Wl;
+        p->smem_le = sizeof(double) * (size_t)le_smem_doubles(nl, dm.nc, dm.ns1);
+    } else p->d_delta = p->sb.delta;
+    CK(dalloc(&p->d_Ftop, (size_t)2 * (ds.nc + ds.hmax) * ds.nc)); CK(dalloc(&p->d_Stop, (size_t)ds.hmax * ds.hmax));
     CK(dalloc(&p->d_top_begin, (size_t)2));
     {
-        // structure of the time-coupling block O: which chain dofs of keyframe k+1 (rows) meet which chain dofs of k (columns)
-        const int nc = dm.nc, nl_ = dm.nl;
+        // structure of the time-coupling block O in SOLVER coordinates: which chain dofs of keyframe k+1 (rows) meet which chain
+        // dofs of k (columns); dm.nl = first chain dof in the internal order, ds.nl = first chain column of the solver's time block
+        const int nc = ds.nc, nl_ = ds.nl;
         std::vector<int> orow(2 * nc), ocol(2 * nc), ozs(nc);
         for (int i = 0; i < nc; i++) { orow[2 * i] = nc; orow[2 * i + 1] = 0; ocol[2 * i] = nc; ocol[2 * i + 1] = 0; }
         for (const DevSlot& s : p->hslots)
@@ -364,7 +436,7 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
                 if (s.var_kind[a] != B200_AT_K1) continue;
                 for (int b = 0; b < s.nvars; b++) {
                     if (s.var_kind[b] != B200_AT_K) continue;
-                    const int ra = s.tan_off[a] - nl_, cb = s.tan_off[b] - nl_;
+                    const int ra = s.tan_off[a] - dm.nl, cb = s.tan_off[b] - dm.nl;
                     for (int i = ra; i < ra + s.tan_dim[a]; i++) { orow[2 * i] = std::min(orow[2 * i], cb); orow[2 * i + 1] = std::max(orow[2 * i + 1], cb + s.tan_dim[b]); }
                     for (int j = cb; j < cb + s.tan_dim[b]; j++) { ocol[2 * j] = std::min(ocol[2 * j], ra); ocol[2 * j + 1] = std::max(ocol[2 * j + 1], ra + s.tan_dim[a]); }
                 }
@@ -376,9 +448,9 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
             ozs[i] = (nl_ + orow[2 * i]) & ~1;
             ow = std::max(ow, (nl_ + orow[2 * i + 1] - ozs[i] + 1) & ~1);
         }
-        ow = std::min(ow, dm.ntp);
-        for (int i = 0; i < nc; i++) if (ozs[i] + ow > dm.ntp) ozs[i] = dm.ntp - ow;
-        dm.ow = ow; dm.owp = ow + 2;
+        ow = std::min(ow, ds.ntp);
+        for (int i = 0; i < nc; i++) if (ozs[i] + ow > ds.ntp) ozs[i] = ds.ntp - ow;
+        ds.ow = ow; ds.owp = ow; while ((ds.owp & 7) != 4) ds.owp++;   // packed-row stride == 4 mod 8 (conflict-free B-operand loads)
         std::vector<int> ogrp;
         for (int b0 = 0; b0 < nc;) {   // runs of <= 16 consecutive rows with the same window, dealt to 4-row groups with stride
             int b1 = b0 + 1;
@@ -391,16 +463,17 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
             }
             b0 = b1;
         }
-        dm.n_ogrp = (int)ogrp.size() / 3;
+        ds.n_ogrp = (int)ogrp.size() / 3;
         CK(dalloc(&p->d_ogrp, ogrp.size()));
         CK(cudaMemcpyAsync(p->d_ogrp, ogrp.data(), sizeof(int) * ogrp.size(), cudaMemcpyHostToDevice, p->stream));
-        dm.ogrp = p->d_ogrp;
+        ds.ogrp = p->d_ogrp;
         CK(dalloc(&p->d_orow, (size_t)2 * nc)); CK(dalloc(&p->d_ocol, (size_t)2 * nc)); CK(dalloc(&p->d_ozs, (size_t)nc));
         CK(cudaMemcpyAsync(p->d_orow, orow.data(), sizeof(int) * 2 * nc, cudaMemcpyHostToDevice, p->stream));
         CK(cudaMemcpyAsync(p->d_ocol, ocol.data(), sizeof(int) * 2 * nc, cudaMemcpyHostToDevice, p->stream));
         CK(cudaMemcpyAsync(p->d_ozs, ozs.data(), sizeof(int) * nc, cudaMemcpyHostToDevice, p->stream));
         CK(cudaStreamSynchronize(p->stream));
-        dm.orow = p->d_orow; dm.ocol = p->d_ocol; dm.ozs = p->d_ozs;
+        ds.orow = p->d_orow; ds.ocol = p->d_ocol; ds.ozs = p->d_ozs;
+        dm.ow = ds.ow; dm.owp = ds.owp; dm.orow = ds.orow; dm.ocol = ds.ocol; dm.ozs = ds.ozs; dm.ogrp = ds.ogrp; dm.n_ogrp = ds.n_ogrp;
     }
     CK(cudaMallocHost((void**)&p->h_scal, (SC_COUNT + 2) * sizeof(double)));
     // uploads
@@ -421,8 +494,6 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
         CK(cudaStreamSynchronize(p->stream));
     }
     // ---- shared memory budgets
-    p->smem_asm[0] = sizeof(double) * ((size_t)dm.ntp * dm.ntp + (size_t)dm.ns1 * dm.ns1 + B200_MAX_FACTOR_ROWS * (B200_MAX_FACTOR_COLS + 1));
-    p->smem_asm[1] = sizeof(double) * ((size_t)dm.nc * dm.nc + (size_t)dm.ns1 * dm.ntp + B200_MAX_FACTOR_ROWS * (B200_MAX_FACTOR_COLS + 1));
     size_t static_smem = 0;
     {
         cudaFuncAttributes fa;
@@ -438,30 +509,32 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
         b200_status ast = build_asm_plan(p, smem_cap);
         if (ast != B200_OK) { b200_problem_destroy(p); return ast; }
     }
+    if (p->use_le && p->smem_le > smem_cap) return fail("local block does not fit in shared memory", B200_NOT_IMPLEMENTED);
     {
         // sweep: pivot block + packed O rows resident, the panel streams through in chunks of cr rows
         const long long cap_d = (long long)(smem_cap / sizeof(double));
-        const long long fixed = (long long)dm.ntp * dm.ld + sweep_op_doubles(dm.nc, dm.owp);
-        long long rows_fit = (cap_d - fixed) / dm.ld;
+        const long long fixed = (long long)ds.ntp * ds.ld + sweep_op_doubles(ds.nc, ds.owp);
+        long long rows_fit = (cap_d - fixed) / ds.ld;
         if (rows_fit < 16) return fail("time block does not fit in shared memory", B200_NOT_IMPLEMENTED);
-        dm.cr = (int)std::min<long long>(64, rows_fit & ~15LL);
-        p->smem_sweep = sizeof(double) * (size_t)sweep_smem_doubles(dm.ntp, dm.ld, dm.cr, dm.nc, dm.owp);
+        ds.cr = (int)std::min<long long>(64, rows_fit & ~15LL);
+        p->smem_sweep = sizeof(double) * (size_t)sweep_smem_doubles(ds.ntp, ds.ld, ds.cr, ds.nc, ds.owp);
         // back-substitution / top level: factor block + vectors; the static system (ns1 x lds) reuses the block area
-        const size_t bs = (size_t)backsub_smem_doubles(dm.ntp, dm.ld);
-        if ((size_t)static_lds(dm.ns) * (dm.ns1 + 1) > (size_t)dm.ntp * dm.ld + 4 * 256)
+        const size_t bs = (size_t)backsub_smem_doubles(ds.ntp, ds.ld);
+        if ((size_t)static_lds(ds.ns) * (ds.ns1 + 1) > (size_t)ds.ntp * ds.ld + 4 * 256)
             return fail("static block larger than the time block is not supported", B200_NOT_IMPLEMENTED);
         p->smem_backsub = (sizeof(double) * bs + 15) & ~(size_t)15;
         if (p->smem_backsub > smem_cap) return fail("solver working set does not fit in shared memory", B200_NOT_IMPLEMENTED);
-        dm.sm_doubles = (int)(p->smem_sweep / sizeof(double));
+        ds.sm_doubles = (int)(p->smem_sweep / sizeof(double));
         // Schur kernel: the stored arrow panel of one node (hmax rows), whole rows if they fit, else column slabs
-        int ldy = choose_ld(dm.ntp), kslab = dm.ntp;
-        if ((long long)dm.hmax * ldy > cap_d) {
-            kslab = (int)((cap_d / dm.hmax) & ~3LL) - 2;
-            if (kslab < 2) return fail("arrow panel does not fit in shared memory", B200_NOT_IMPLEMENTED);
-            ldy = kslab;   // == 2 mod 4
+        int ldy = choose_ld(ds.ntp), kslab = ds.ntp;
+        if ((long long)ds.hmax * ldy > cap_d) {
+            kslab = (int)((cap_d / ds.hmax) & ~7LL) - 4;
+            if (kslab < 4) return fail("arrow panel does not fit in shared memory", B200_NOT_IMPLEMENTED);
+            ldy = kslab;   // == 4 mod 8
         }
         p->schur_ldy = ldy; p->schur_kslab = kslab;
-        p->smem_schur = sizeof(double) * (size_t)dm.hmax * ldy;
+        p->smem_schur = sizeof(double) * (size_t)ds.hmax * ldy;
+        dm.cr = ds.cr; dm.sm_doubles = ds.sm_doubles;
     }
 #ifndef B200_USE_EMU
     CK(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(p->smem_asm[0], p->smem_asm[1])));
@@ -470,6 +543,7 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
     CK(cudaFuncSetAttribute(chain_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_schur));
     CK(cudaFuncSetAttribute(top_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_backsub));
     CK(cudaFuncSetAttribute(chain_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_backsub));
+    if (p->use_le) CK(cudaFuncSetAttribute(local_elim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_le));
 #endif
     p->k_lo = 0; p->k_hi = p->K;
     int P1 = 0, P2 = 0;   // 0: choose from the cost model
@@ -518,7 +592,7 @@ static double partition_cost(int K, int P1, int sms) {
 // ceil(K/world) keyframes); P2 > 1: the P1-1 separators are themselves cut into P2 groups (rank-aligned) and only the
 // P2-1 group separators are eliminated sequentially by the single top-level CTA.  Chunks hold >= 2 nodes.
 static b200_status set_partition(b200_problem* p, int P1, int P2) {
-    const Dims& dm = p->dm;
+    const Dims& dm = p->ds;   // solver layout
     const int K = p->K, W = p->world, sms = 148 * p->world;   // one chunk CTA per SM and wave, on every rank
     p->Wk = (K + W - 1) / W;
     if ((long long)(W - 1) * p->Wk >= K || K - (W - 1) * p->Wk < 3) { set_err("too few keyframes for this many ranks"); return B200_BAD_ARG; }
@@ -544,6 +618,7 @@ static b200_status set_partition(b200_problem* p, int P1, int P2) {
     if (W > 1) { P2 = std::max(P2, W); P2 = (P2 + W - 1) / W * W; while (P2 > W && (P1 / W - 1) / (P2 / W) < 2) P2 -= W; if ((P1 / W - 1) / (P2 / W) < 2) { set_err("partition too fine for this many ranks"); return B200_BAD_ARG; } }
     else { if (P1 < 4) P2 = 1; while (P2 > 1 && (P1 - 1) / P2 < 2) P2--; }
     free_levels(p);
+    free_graphs(p);
     // chunk counts per level: Ps[0] over the K keyframes, Ps[l] over the Ps[l-1]-1 separators of the level below
     std::vector<int> Ps;
     if (P1 > 1) {
@@ -615,7 +690,9 @@ static b200_status set_partition(b200_problem* p, int P1, int P2) {
         CK(dalloc(&l.Dred, P * dm.ntp * dm.ntp)); CK(dalloc(&l.Ored, P * dm.nc * dm.nc));
         CK(dalloc(&l.Ared, P * dm.ns1 * dm.ntp)); CK(dalloc(&l.Sred, P * dm.ns1 * dm.ns1));
         Level& d = l.dev;
-        if (li == 0) { d.Dsrc = p->d_D; d.Osrc = p->d_O; d.Asrc = p->d_A; d.Ssrc = p->d_S; d.st = nullptr; }
+        if (li == 0) {   // keyframes: the assembled blocks, or the reduced ones when the local dofs are pre-eliminated
+            d.Dsrc = p->use_le ? p->d_Dc : p->d_D; d.Osrc = p->d_O; d.Asrc = p->use_le ? p->d_Ac : p->d_A; d.Ssrc = p->use_le ? p->d_Sc : p->d_S; d.st = nullptr;
+        }
         else { auto& lp = p->levels[li - 1]; d.Dsrc = lp.Dred; d.Osrc = lp.Ored; d.Asrc = lp.Ared; d.Ssrc = lp.Sred; d.st = l.d_st; }
         d.begin = l.d_begin; d.P = l.P; d.F = l.F; d.S = l.S;
         d.Dred = l.Dred; d.Ored = l.Ored; d.Ared = l.Ared; d.Sred = l.Sred; d.sep_st = l.d_sep_st; d.dense_o = (li > 0); d.nsplit = l.nsplit;
@@ -625,7 +702,7 @@ static b200_status set_partition(b200_problem* p, int P1, int P2) {
         Level& t = p->top;
         t = Level{};
         int tn = K;
-        if (nlev == 0) { t.Dsrc = p->d_D; t.Osrc = p->d_O; t.Asrc = p->d_A; t.Ssrc = p->d_S; t.st = nullptr; }
+        if (nlev == 0) { t.Dsrc = p->use_le ? p->d_Dc : p->d_D; t.Osrc = p->d_O; t.Asrc = p->use_le ? p->d_Ac : p->d_A; t.Ssrc = p->use_le ? p->d_Sc : p->d_S; t.st = nullptr; }
         else { auto& l = p->levels[nlev - 1]; t.Dsrc = l.Dred; t.Osrc = l.Ored; t.Asrc = l.Ared; t.Ssrc = l.Sred; t.st = l.d_sep_st; tn = l.P - 1; }
         const int tb[2] = {0, tn};
         CK(cudaMemcpyAsync(p->d_top_begin, tb, sizeof(tb), cudaMemcpyHostToDevice, p->stream));
@@ -679,6 +756,7 @@ b200_status b200_set_values(b200_problem* p, const double* tv, const double* sv)
     CK(cudaStreamSynchronize(p->stream));
     CK(cudaGetLastError());
     p->have_lin = false;
+    p->err_stale = true;   // the LM state's cost refers to the previous values: b200_lm_iterate re-evaluates it
     return B200_OK;
 }
 
@@ -696,11 +774,11 @@ b200_status b200_get_values(b200_problem* p, double* tv, double* sv) {
 }
 
 // ------------------------------------------------------------------------------------------ pipeline stages (async)
-static void launch_error(b200_problem* p, const double* tv, const double* sv, double* ebuf, int scal_idx) {
+static void launch_error(b200_problem* p, const double* tv, const double* sv, double* ebuf, int scal_idx, const int* skip = nullptr) {
     dim3 grid((p->max_inst + 127) / 128, p->n_slots);
     B200_LAUNCH(linearize_kernel<false>, grid, dim3(128), 0, p->stream, p->d_slots, tv, sv, p->d_cst, p->dm.Kld, (double*)nullptr,
-                (double*)nullptr, ebuf, p->k_lo, p->k_hi, p->k_lo);
-    B200_LAUNCH(reduce_sum_kernel, dim3(1), dim3(1024), 0, p->stream, ebuf, p->ne, p->sb.scal + scal_idx);
+                (double*)nullptr, ebuf, p->k_lo, p->k_hi, p->k_lo, skip);
+    B200_LAUNCH(reduce_sum_kernel, dim3(1), dim3(1024), 0, p->stream, ebuf, p->ne, p->sb.scal + scal_idx, skip);
     p->launches += 2;
 }
 
@@ -708,7 +786,7 @@ static void launch_linearize(b200_problem* p) {
     dim3 grid((p->max_inst + 127) / 128, p->n_slots);
     // Jacobians are needed one keyframe to the left of the window (the IMU factor k_lo-1 -> k_lo feeds D[k_lo])
     B200_LAUNCH(linearize_kernel<true>, grid, dim3(128), 0, p->stream, p->d_slots, p->d_tv, p->d_sv, p->d_cst, p->dm.Kld, p->d_J, p->d_r,
-                p->d_e, std::max(p->k_lo - 1, 0), p->k_hi, p->k_lo);
+                p->d_e, std::max(p->k_lo - 1, 0), p->k_hi, p->k_lo, (const int*)nullptr);
     p->launches++;
     // one extra keyframe on the left: its O block (coupling k_lo-1 -> k_lo) is the left-separator coupling of this window
     const int ka = std::max(p->k_lo - 1, 0);
@@ -740,11 +818,11 @@ __global__ void pack_groups_kernel(Dims dm, Level lv1, const double* Dred, const
 }
 
 // one level: sweep (CTA per chunk) + arrow Schur complement (CTA per chunk)
-static void launch_level_factor(b200_problem* p, const Level& lv, int c_lo, int c_hi, double lambda) {
-    const Dims& dm = p->dm;
+static void launch_level_factor(b200_problem* p, const Level& lv, int c_lo, int c_hi) {
+    const Dims& dm = p->ds;
     const dim3 sgrid(c_hi - c_lo, lv.nsplit > 0 ? lv.nsplit : 1);
-    if (lv.dense_o) B200_LAUNCH(chain_sweep_kernel<true>, sgrid, dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, dm, lv, p->sb, lambda, c_lo);
-    else B200_LAUNCH(chain_sweep_kernel<false>, sgrid, dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, dm, lv, p->sb, lambda, c_lo);
+    if (lv.dense_o) B200_LAUNCH(chain_sweep_kernel<true>, sgrid, dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, dm, lv, p->sb, c_lo);
+    else B200_LAUNCH(chain_sweep_kernel<false>, sgrid, dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, dm, lv, p->sb, c_lo);
     // few chunks (upper levels): split the output tiles of a chunk's Schur complement over several CTAs
     const int nsplit = (c_hi - c_lo) * 2 <= 148 ? 2 : 1;
     B200_LAUNCH(chain_schur_kernel, dim3(c_hi - c_lo, nsplit), dim3(B200_SCHUR_THREADS), p->smem_schur, p->stream, dm, lv, p->sb, c_lo, p->schur_ldy,
@@ -752,7 +830,7 @@ static void launch_level_factor(b200_problem* p, const Level& lv, int c_lo, int 
     p->launches += 2;
 }
 static void launch_level_backsub(b200_problem* p, const b200_problem::HostLevel& l) {
-    const Dims& dm = p->dm;
+    const Dims& dm = p->ds;
     int max_nodes = 1;
     for (int c = l.c_lo; c < l.c_hi; c++) max_nodes = std::max(max_nodes, l.begin[c + 1] - l.begin[c]);
     B200_LAUNCH(chain_backsub_prepass_kernel, dim3(max_nodes, l.c_hi - l.c_lo), dim3(B200_PREPASS_THREADS), 0, p->stream, dm, l.dev, p->sb, l.c_lo);
@@ -760,19 +838,25 @@ static void launch_level_backsub(b200_problem* p, const b200_problem::HostLevel&
     p->launches += 2;
 }
 
-// (H + lambda I) delta = -g : nested partitioned factorisation + back-substitution, all on p->stream
-static b200_status launch_solve(b200_problem* p, double lambda) {
+// (H + lambda I) delta = -g with lambda = *sb.lam (device scalar): local elimination, nested partitioned factorisation,
+// back-substitution, all on p->stream.  tev != nullptr: phase events of this trial slot (direct launches only, not under capture).
+enum { TE_SOLVE0 = 0, TE_SWEEP0, TE_SWEEP1, TE_TOP0, TE_TOP1, TE_BACK1, TE_SOLVE1, TE_TRIAL1, TE_COUNT };
+static b200_status launch_solve(b200_problem* p, cudaEvent_t* tev) {
     CK(cudaMemsetAsync(p->sb.status, 0, sizeof(int), p->stream));
-    const Dims& dm = p->dm;
+    const Dims& dm = p->ds;
     const int W = p->world, r = p->rank;
     const size_t Fsz = (size_t)(dm.nc + dm.hmax) * dm.nc, Ssz = (size_t)dm.hmax * dm.hmax;
     const int nlev = (p->P > 1) ? (int)p->levels.size() : 0;
-    if (p->time_phases) CK(cudaEventRecord(p->ev[8], p->stream));
+    if (p->use_le) {
+        B200_LAUNCH(local_elim_kernel, dim3(p->k_hi - p->k_lo), dim3(B200_LE_THREADS), p->smem_le, p->stream, p->le, p->k_lo, p->sb.lam, p->sb.status, p->sb.skip);
+        p->launches++;
+    }
+    if (tev) CK(cudaEventRecord(tev[TE_SWEEP0], p->stream));
     if (nlev >= 1) {
         auto& l0 = p->levels[0];
-        B200_LAUNCH(chain_sweep_kernel<false>, dim3(l0.c_hi - l0.c_lo), dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, dm, l0.dev, p->sb, lambda, l0.c_lo);
+        B200_LAUNCH(chain_sweep_kernel<false>, dim3(l0.c_hi - l0.c_lo), dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, dm, l0.dev, p->sb, l0.c_lo);
         p->launches++;
-        if (p->time_phases) CK(cudaEventRecord(p->ev[9], p->stream));
+        if (tev) CK(cudaEventRecord(tev[TE_SWEEP1], p->stream));
         B200_LAUNCH(chain_schur_kernel, dim3(l0.c_hi - l0.c_lo), dim3(B200_SCHUR_THREADS), p->smem_schur, p->stream, dm, l0.dev, p->sb, l0.c_lo,
                     p->schur_ldy, p->schur_kslab);
         p->launches++;
@@ -792,14 +876,14 @@ static b200_status launch_solve(b200_problem* p, double lambda) {
             if (r > 0) red_lo = l0.c_lo - 1;
         }
         if (red_hi > red_lo) {
-            B200_LAUNCH(chain_reduce_kernel, dim3(red_hi - red_lo, 8), dim3(256), 0, p->stream, dm, l0.dev, red_lo);
+            B200_LAUNCH(chain_reduce_kernel, dim3(red_hi - red_lo, 8), dim3(256), 0, p->stream, dm, l0.dev, red_lo, p->sb.skip);
             p->launches++;
         }
-    }
+    } else if (tev) CK(cudaEventRecord(tev[TE_SWEEP1], p->stream));
     for (int li = 1; li < nlev; li++) {
         auto& l0 = p->levels[0];
         auto& l1 = p->levels[li];
-        launch_level_factor(p, l1.dev, l1.c_lo, l1.c_hi, lambda);
+        launch_level_factor(p, l1.dev, l1.c_lo, l1.c_hi);
         if (W > 1 && li == 1) {
             const int gpr = l1.P / W;
             b200_status st = allgather(p, l1.F, sizeof(double) * 2 * Fsz * gpr); if (st != B200_OK) return st;
@@ -811,18 +895,23 @@ static b200_status launch_solve(b200_problem* p, double lambda) {
                         (long long)p->pack_doubles, 0, 1, l1.c_lo, l1.c_hi);
             p->launches += 2;
         }
-        B200_LAUNCH(chain_reduce_kernel, dim3(l1.P - 1, 8), dim3(256), 0, p->stream, dm, l1.dev, 0);
+        B200_LAUNCH(chain_reduce_kernel, dim3(l1.P - 1, 8), dim3(256), 0, p->stream, dm, l1.dev, 0, p->sb.skip);
         p->launches++;
     }
-    if (p->time_phases) CK(cudaEventRecord(p->ev[10], p->stream));
-    launch_level_factor(p, p->top, 0, 1, lambda);
-    B200_LAUNCH(top_finish_kernel, dim3(1), dim3(B200_SOLVE_THREADS), p->smem_backsub, p->stream, dm, p->top, p->sb, lambda);
+    if (tev) CK(cudaEventRecord(tev[TE_TOP0], p->stream));
+    launch_level_factor(p, p->top, 0, 1);
+    B200_LAUNCH(top_finish_kernel, dim3(1), dim3(B200_SOLVE_THREADS), p->smem_backsub, p->stream, dm, p->top, p->sb);
     p->launches++;
-    if (p->time_phases) CK(cudaEventRecord(p->ev[11], p->stream));
+    if (tev) CK(cudaEventRecord(tev[TE_TOP1], p->stream));
     for (int li = nlev - 1; li >= 0; li--) launch_level_backsub(p, p->levels[li]);
-    if (p->time_phases) CK(cudaEventRecord(p->ev[12], p->stream));
+    if (p->use_le) {
+        B200_LAUNCH(local_backsub_kernel, dim3(p->k_hi - p->k_lo), dim3(128), 0, p->stream, p->le, p->k_lo, p->k_hi, p->sb.delta, p->sb.dstat, p->d_delta,
+                    p->sb.status, p->sb.skip);
+        p->launches++;
+    }
+    if (tev) CK(cudaEventRecord(tev[TE_BACK1], p->stream));
     if (W > 1) {  // every rank needs every keyframe's step: the values are replicated
-        b200_status st = allgather(p, p->sb.delta, sizeof(double) * (size_t)p->Wk * dm.ntp); if (st != B200_OK) return st;
+        b200_status st = allgather(p, p->d_delta, sizeof(double) * (size_t)p->Wk * p->dm.ntp); if (st != B200_OK) return st;
     }
     return B200_OK;
 }
@@ -840,6 +929,22 @@ static b200_status allreduce_scal(b200_problem* p) {
     if (p->world <= 1) return B200_OK;
     if (!p->ar_fn) { set_err("world_size > 1 but no collective registered"); return B200_NCCL_ERROR; }
     if (p->ar_fn(p->comm_ctx, p->sb.scal, SC_COUNT, p->stream)) { set_err("allreduce failed"); return B200_NCCL_ERROR; }
+    return B200_OK;
+}
+
+// upload the LM state mirror (pinned) to the device; the caller has synchronised the stream since the mirror was last in flight
+static b200_status push_lm_state(b200_problem* p) {
+    LmDev& h = *p->h_lm;
+    h.lambda = p->lambda; h.lambda_try = p->lambda; h.err = p->err; h.new_err = p->err;
+    h.iterations = p->iterations; h.total_trials = p->total_trials; h.inner = 0; h.status = B200_OK; h.done = 0; h.accepted = 0;
+    CK(cudaMemcpyAsync(p->d_lm, p->h_lm, sizeof(LmDev), cudaMemcpyHostToDevice, p->stream));
+    CK(cudaStreamSynchronize(p->stream));
+    return B200_OK;
+}
+// set the damping of the next solve from the host (sharded / speculative path, debug_solve)
+static b200_status push_lambda_try(b200_problem* p, double lam) {
+    p->h_lm->lambda_try = lam;
+    CK(cudaMemcpyAsync(&p->d_lm->lambda_try, &p->h_lm->lambda_try, sizeof(double), cudaMemcpyHostToDevice, p->stream));
     return B200_OK;
 }
 
@@ -862,26 +967,26 @@ b200_status b200_lm_begin(b200_problem* p, const b200_lm_params* prm, double* in
     double e;
     b200_status st = b200_error(p, &e);
     if (st != B200_OK) return st;
-    p->err = e;
+    p->err = e; p->err_stale = false; p->lm_started = true;
     if (initial_error) *initial_error = e;
-    return B200_OK;
+    return push_lm_state(p);
 }
 
 // retract (values + delta -> try buffers): time variables of every keyframe, then the statics
-static void launch_retract(b200_problem* p, const double* delta, const double* dstat) {
+static void launch_retract(b200_problem* p, const double* delta, const double* dstat, const int* skip = nullptr) {
     B200_LAUNCH(retract_kernel, dim3((p->K + 127) / 128, 1, p->ntv), dim3(128), 0, p->stream, p->d_tvars, p->ntv, p->d_svars, p->nsv, p->K,
-                p->dm.Kld, p->d_tv, p->d_sv, delta, p->dm.ntp, dstat, p->d_tv_try, p->d_sv_try);
+                p->dm.Kld, p->d_tv, p->d_sv, delta, p->dm.ntp, dstat, p->d_tv_try, p->d_sv_try, skip);
     p->launches++;
     if (p->nsv) {
         B200_LAUNCH(retract_kernel, dim3((p->nsv + 127) / 128, 2, 1), dim3(128), 0, p->stream, p->d_tvars, 0, p->d_svars, p->nsv, 0, p->dm.Kld,
-                    p->d_tv, p->d_sv, delta, p->dm.ntp, dstat, p->d_tv_try, p->d_sv_try);
+                    p->d_tv, p->d_sv, delta, p->dm.ntp, dstat, p->d_tv_try, p->d_sv_try, skip);
         p->launches++;
     }
 }
 
 // outcome of one lambda trial (gtsam @4.2 LevenbergMarquardtOptimizer::tryLambda): accept the step / stop searching
 struct TrialVerdict { bool solved, step_ok, stop; };
-static TrialVerdict judge_trial(const b200_lm_params& L, double cur_err, bool solved, double oldLin, double newLin, double newError) {
+__host__ __device__ inline TrialVerdict judge_trial(const b200_lm_params& L, double cur_err, bool solved, double oldLin, double newLin, double newError) {
     TrialVerdict v{solved, false, false};
     if (!solved) return v;
     const double linChange = oldLin - newLin;
@@ -889,112 +994,240 @@ static TrialVerdict judge_trial(const b200_lm_params& L, double cur_err, bool so
     else if (linChange >= 0) {
         const double costChange = cur_err - newError;
         if (linChange > 2.220446049250313e-16 * oldLin) v.step_ok = (costChange / linChange) > L.min_model_fidelity;
-        if (std::fabs(costChange) < L.relative_error_tol * cur_err) v.stop = true;
+        if (fabs(costChange) < L.relative_error_tol * cur_err) v.stop = true;
     }
     return v;
 }
 
+// The damping / accept-reject logic of one lambda trial ON THE DEVICE (north_star subsystem 4): one thread reads the three cost
+// scalars of the trial and the pivot status, applies gtsam's tryLambda rules (judge_trial + increaseLambda / decreaseLambda) to
+// the LM state in device memory and, when the ladder has ended, raises `done` so that the trials already queued behind this
+// one return at once.  The host reads the state once per iterate().
+__global__ void lm_judge_kernel(LmDev* st, const double* __restrict__ scal, const int* __restrict__ solve_status, b200_lm_params L) {
+    if (threadIdx.x != 0 || blockIdx.x != 0 || st->done) return;
+    const bool solved = *solve_status == 0;
+    const TrialVerdict v = judge_trial(L, st->err, solved, scal[SC_LIN_ERR], scal[SC_MODEL_ERR], scal[SC_NEW_ERR]);
+    st->inner++;
+    st->status = solved ? B200_OK : B200_INDETERMINATE_SYSTEM;
+    if (v.step_ok) {
+        st->new_err = scal[SC_NEW_ERR]; st->err = scal[SC_NEW_ERR];
+        if (!L.gauss_newton) { const double l = st->lambda / L.lambda_factor; st->lambda = l > L.lambda_lower_bound ? l : L.lambda_lower_bound; }
+        st->iterations++; st->total_trials++;
+        st->status = B200_OK; st->accepted = 1; st->done = 1;
+    } else if (!v.stop) {
+        st->lambda *= L.lambda_factor; st->total_trials++;
+        if (st->lambda >= L.lambda_upper_bound) { st->status = B200_LAMBDA_MAXED; st->done = 1; }
+        else if (L.gauss_newton) { st->status = B200_INDETERMINATE_SYSTEM; st->done = 1; }
+    } else st->done = 1;
+    st->lambda_try = st->lambda;
+}
+__global__ void lm_begin_iter_kernel(LmDev* st) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    st->done = 0; st->accepted = 0; st->inner = 0; st->lambda_try = st->lambda;
+}
+// pivot status of this rank as a 0/1 entry of the all-reduced scalar block: a failure on ANY rank marks the trial unsolved on all
+__global__ void status_to_scal_kernel(const int* __restrict__ status, double* __restrict__ scal) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) scal[SC_FAIL] = (*status != 0) ? 1.0 : 0.0;
+}
+
+// one lambda trial: solve at *sb.lam, linear-model error of the step, retraction into the try buffers, cost of the try values;
+// device_judge: followed by lm_judge_kernel.  Everything is launched on p->stream; no host decision in between.
+static b200_status launch_trial(b200_problem* p, cudaEvent_t* tev, bool device_judge) {
+    if (tev) CK(cudaEventRecord(tev[TE_SOLVE0], p->stream));
+    b200_status st = launch_solve(p, tev);
+    if (st != B200_OK) return st;
+    if (tev) CK(cudaEventRecord(tev[TE_SOLVE1], p->stream));
+    dim3 grid((p->max_inst + 127) / 128, p->n_slots);
+    B200_LAUNCH(model_error_kernel, grid, dim3(128), 0, p->stream, p->d_slots, p->d_J, p->d_r, p->d_delta, p->dm.ntp, p->sb.dstat, p->d_e2,
+                p->k_lo, p->k_hi, p->sb.skip);
+    B200_LAUNCH(reduce_sum_kernel, dim3(1), dim3(1024), 0, p->stream, p->d_e2, p->ne, p->sb.scal + SC_MODEL_ERR, p->sb.skip);
+    p->launches += 2;
+    launch_retract(p, p->d_delta, p->sb.dstat, p->sb.skip);
+    launch_error(p, p->d_tv_try, p->d_sv_try, p->d_e2, SC_NEW_ERR, p->sb.skip);
+    // rank-local linear.error(0) lives outside the all-reduced block (scal[SC_COUNT]); it is copied in at every trial
+    CK(cudaMemcpyAsync(p->sb.scal + SC_LIN_ERR, p->sb.scal + SC_COUNT, sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    if (device_judge) {
+        B200_LAUNCH(lm_judge_kernel, dim3(1), dim3(32), 0, p->stream, p->d_lm, p->sb.scal, p->sb.status, p->lm);
+        p->launches++;
+    }
+    if (tev) CK(cudaEventRecord(tev[TE_TRIAL1], p->stream));
+    return B200_OK;
+}
+
+static void free_graphs(b200_problem* p) {
+#ifndef B200_USE_EMU
+    for (int i = 0; i < 2; i++) if (p->trial_graph[i]) { cudaGraphExecDestroy(p->trial_graph[i]); p->trial_graph[i] = nullptr; }
+#endif
+    p->graph_launches = 0;
+}
+
+// the trial of the current buffer parity as an instantiated CUDA graph (captured once per parity and partition)
+static b200_status trial_graph(b200_problem* p, int parity) {
+#ifndef B200_USE_EMU
+    if (p->trial_graph[parity]) return B200_OK;
+    const long long l0 = p->launches;
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+    b200_status st = launch_trial(p, nullptr, true);
+    cudaError_t e = cudaStreamEndCapture(p->stream, &g);
+    if (st != B200_OK) { if (g) cudaGraphDestroy(g); return st; }
+    if (e != cudaSuccess) { set_err(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e)); return B200_CUDA_ERROR; }
+    e = cudaGraphInstantiate(&p->trial_graph[parity], g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) { set_err(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); return B200_CUDA_ERROR; }
+    p->graph_launches = p->launches - l0;   // kernels inside one trial graph
+    p->launches = l0;
+#endif
+    return B200_OK;
+}
+
+static void accumulate_phase_ms(b200_problem* p, cudaEvent_t* tev) {
+    float ms;
+    cudaEventElapsedTime(&ms, tev[TE_SOLVE0], tev[TE_SOLVE1]); p->phase_ms[1] += ms;
+    cudaEventElapsedTime(&ms, tev[TE_SOLVE1], tev[TE_TRIAL1]); p->phase_ms[2] += ms;
+    if (p->P > 1) {
+        cudaEventElapsedTime(&ms, tev[TE_SWEEP0], tev[TE_SWEEP1]); p->phase_ms[3] += ms; p->phase_ms[4] += 1;
+        cudaEventElapsedTime(&ms, tev[TE_TOP1], tev[TE_BACK1]); p->phase_ms[7] += ms;
+    }
+    cudaEventElapsedTime(&ms, tev[TE_TOP0], tev[TE_TOP1]); p->phase_ms[5] += ms; p->phase_ms[6] += 1;
+}
+
 // == LevenbergMarquardtOptimizer::iterate() (gtsam @4.2: iterate / tryLambda / increaseLambda / decreaseLambda)
-// With lambda speculation (b200_spec_set, G groups) every round evaluates the next G values of the lambda ladder at once, one
-// per group, and the verdicts are then read in ladder order exactly as the sequential loop would have met them: the accepted
-// step, the final lambda and the trial count are those of the sequential algorithm.
+// Single rank: the whole ladder runs on the device -- `spec_trials` trials are queued back to back (each one a CUDA graph), the
+// accept / reject / damping decisions are taken by lm_judge_kernel, the host synchronises once per round and reads the state.
+// Sharded / speculative (b200_comm_set / b200_spec_set): the ranks exchange the trial scalars through the registered
+// collectives and every rank applies the same rules on the host.  With lambda speculation (G groups) every round evaluates the
+// next G values of the lambda ladder at once, one per group, and the verdicts are then read in ladder order exactly as the
+// sequential loop would have met them: the accepted step, the final lambda and the trial count are those of the sequential algorithm.
 b200_status b200_lm_iterate(b200_problem* p, b200_lm_state* state) {
-    if (!p) return B200_BAD_ARG;
+    if (!p || !p->lm_started) return B200_BAD_ARG;
     CK(cudaSetDevice(p->device));
     const b200_lm_params& L = p->lm;
+    if (p->err_stale) {   // b200_set_values since the last cost evaluation: refresh the cost the trials are judged against
+        double e; b200_status st = b200_error(p, &e); if (st != B200_OK) return st;
+        p->err = e; p->err_stale = false;
+        st = push_lm_state(p); if (st != B200_OK) return st;
+    }
     if (p->time_phases) CK(cudaEventRecord(p->ev[0], p->stream));
     CK(cudaMemsetAsync(p->sb.scal, 0, sizeof(double) * SC_COUNT, p->stream));
     launch_linearize(p);
-    // rank-local linear.error(0); copied into the all-reduced slot at every lambda trial (the all-reduce sums the whole
-    // scalar block, so a value that survives from one trial to the next must not live in it)
-    B200_LAUNCH(reduce_sum_kernel, dim3(1), dim3(1024), 0, p->stream, p->d_e, p->ne, p->sb.scal + SC_COUNT);
+    B200_LAUNCH(reduce_sum_kernel, dim3(1), dim3(1024), 0, p->stream, p->d_e, p->ne, p->sb.scal + SC_COUNT, (const int*)nullptr);
     p->launches++;
     if (p->time_phases) CK(cudaEventRecord(p->ev[1], p->stream));
     p->have_lin = true;
     const int G = (p->spec_ag && !L.gauss_newton) ? p->spec_G : 1;
     const int T = p->world;
     int status = B200_OK, inner = 0;
-    bool done = false;
-    while (!done) {  // one round of the lambda ladder: G rungs (sequential algorithm: G == 1)
-        double lam_try = p->lambda;
-        for (int i = 0; i < p->spec_g && G > 1; i++) lam_try *= L.lambda_factor;
-        if (p->time_phases) CK(cudaEventRecord(p->ev[2], p->stream));
-        b200_status st = launch_solve(p, lam_try);
-        if (st != B200_OK) return st;
-        if (p->time_phases) CK(cudaEventRecord(p->ev[3], p->stream));
-        dim3 grid((p->max_inst + 127) / 128, p->n_slots);
-        B200_LAUNCH(model_error_kernel, grid, dim3(128), 0, p->stream, p->d_slots, p->d_J, p->d_r, p->sb.delta, p->dm.ntp, p->sb.dstat, p->d_e2,
-                    p->k_lo, p->k_hi);
-        B200_LAUNCH(reduce_sum_kernel, dim3(1), dim3(1024), 0, p->stream, p->d_e2, p->ne, p->sb.scal + SC_MODEL_ERR);
-        p->launches += 2;
-        launch_retract(p, p->sb.delta, p->sb.dstat);
-        launch_error(p, p->d_tv_try, p->d_sv_try, p->d_e2, SC_NEW_ERR);
-        CK(cudaMemcpyAsync(p->sb.scal + SC_LIN_ERR, p->sb.scal + SC_COUNT, sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
-        st = allreduce_scal(p); if (st != B200_OK) return st;
-        if (G > 1) {
-            // record of this rank: [scalars | status | static step]; gathered over ALL ranks of all groups
-            double* rec = p->d_spec_rec + (size_t)(p->spec_g * T + p->rank) * p->spec_rec;
-            CK(cudaMemcpyAsync(rec, p->sb.scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToDevice, p->stream));
-            CK(cudaMemsetAsync(rec + SC_COUNT, 0, sizeof(double), p->stream));
-            CK(cudaMemcpyAsync(rec + SC_COUNT, p->sb.status, sizeof(int), cudaMemcpyDeviceToDevice, p->stream));
-            if (p->dm.ns) CK(cudaMemcpyAsync(rec + SC_COUNT + 1, p->sb.dstat, sizeof(double) * p->dm.ns, cudaMemcpyDeviceToDevice, p->stream));
-            if (p->spec_ag(p->spec_ctx, p->d_spec_rec, sizeof(double) * p->spec_rec, p->stream)) { set_err("speculation allgather failed"); return B200_NCCL_ERROR; }
-            CK(cudaMemcpyAsync(p->h_spec_rec, p->d_spec_rec, sizeof(double) * p->spec_rec * G * T, cudaMemcpyDeviceToHost, p->stream));
-        }
-        if (p->time_phases) CK(cudaEventRecord(p->ev[4], p->stream));
-        st = fetch_scalars(p); if (st != B200_OK) return st;
-        if (p->time_phases) {
-            float ms;
-            if (inner == 0) { cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]); p->phase_ms[0] += ms; }
-            cudaEventElapsedTime(&ms, p->ev[2], p->ev[3]); p->phase_ms[1] += ms;
-            cudaEventElapsedTime(&ms, p->ev[3], p->ev[4]); p->phase_ms[2] += ms;
-            if (p->P > 1) {
-                cudaEventElapsedTime(&ms, p->ev[8], p->ev[9]); p->phase_ms[3] += ms; p->phase_ms[4] += 1;
-                cudaEventElapsedTime(&ms, p->ev[11], p->ev[12]); p->phase_ms[7] += ms;
+    if (T == 1 && G == 1) {
+        // ------------------------------------------------------------ device-resident ladder
+        p->sb.skip = &p->d_lm->done;
+        B200_LAUNCH(lm_begin_iter_kernel, dim3(1), dim3(32), 0, p->stream, p->d_lm);
+        p->launches++;
+        const int nq = L.gauss_newton ? 1 : std::max(1, std::min(p->spec_trials, 4));
+#ifndef B200_USE_EMU
+        const bool graph = p->use_graph && !p->time_phases;
+#else
+        const bool graph = false;
+#endif
+        bool first = true;
+        while (true) {
+            for (int q = 0; q < nq; q++) {
+                if (graph) {
+#ifndef B200_USE_EMU
+                    b200_status st = trial_graph(p, p->parity); if (st != B200_OK) { p->sb.skip = nullptr; return st; }
+                    CK(cudaGraphLaunch(p->trial_graph[p->parity], p->stream));
+                    p->launches += p->graph_launches;
+#endif
+                } else {
+                    b200_status st = launch_trial(p, p->time_phases ? p->tev[q] : nullptr, true);
+                    if (st != B200_OK) { p->sb.skip = nullptr; return st; }
+                }
             }
-            cudaEventElapsedTime(&ms, p->ev[10], p->ev[11]); p->phase_ms[5] += ms; p->phase_ms[6] += 1;
+            CK(cudaMemcpyAsync(p->h_lm, p->d_lm, sizeof(LmDev), cudaMemcpyDeviceToHost, p->stream));
+            CK(cudaMemcpyAsync(p->h_scal, p->sb.scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, p->stream));   // (b200_debug_get_scalars)
+            CK(cudaStreamSynchronize(p->stream));
+            CK(cudaGetLastError());
+            p->host_syncs++;
+            if (p->time_phases) {
+                float ms;
+                if (first) { cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]); p->phase_ms[0] += ms; }
+                for (int q = 0; q < nq && q < p->h_lm->inner - inner; q++) accumulate_phase_ms(p, p->tev[q]);
+            }
+            first = false;
+            inner = p->h_lm->inner;
+            if (p->h_lm->done) break;
         }
-        int winner = -1;
-        double win_err = 0.0;
-        for (int h = 0; h < G && !done; h++) {  // the rungs in the order the sequential loop meets them
-            inner++;
-            bool solved; double oldLin, newLin, newError;
+        p->sb.skip = nullptr;
+        const LmDev& h = *p->h_lm;
+        status = h.status;
+        p->lambda = h.lambda; p->iterations = h.iterations; p->total_trials = h.total_trials;
+        if (h.accepted) {
+            std::swap(p->d_tv, p->d_tv_try); std::swap(p->d_sv, p->d_sv_try); p->parity ^= 1;
+            p->err = h.err; p->have_lin = false;
+        }
+    } else {
+        // ------------------------------------------------------------ sharded / speculative ladder (host verdicts)
+        bool done = false;
+        while (!done) {  // one round of the lambda ladder: G rungs (sequential algorithm: G == 1)
+            double lam_try = p->lambda;
+            for (int i = 0; i < p->spec_g && G > 1; i++) lam_try *= L.lambda_factor;
+            b200_status st = push_lambda_try(p, lam_try); if (st != B200_OK) return st;
+            st = launch_trial(p, p->time_phases ? p->tev[0] : nullptr, false);
+            if (st != B200_OK) return st;
+            B200_LAUNCH(status_to_scal_kernel, dim3(1), dim3(32), 0, p->stream, p->sb.status, p->sb.scal);
+            p->launches++;
+            st = allreduce_scal(p); if (st != B200_OK) return st;
             if (G > 1) {
-                const double* rec = p->h_spec_rec + (size_t)h * T * p->spec_rec;
-                solved = true;
-                for (int t = 0; t < T; t++) if (*reinterpret_cast<const int*>(rec + (size_t)t * p->spec_rec + SC_COUNT) != 0) solved = false;
-                oldLin = rec[SC_LIN_ERR]; newLin = rec[SC_MODEL_ERR]; newError = rec[SC_NEW_ERR];
-            } else {
-                solved = host_status(p) == 0;
-                oldLin = p->h_scal[SC_LIN_ERR]; newLin = p->h_scal[SC_MODEL_ERR]; newError = p->h_scal[SC_NEW_ERR];
+                // record of this rank: [scalars | static step]; gathered over ALL ranks of all groups
+                double* rec = p->d_spec_rec + (size_t)(p->spec_g * T + p->rank) * p->spec_rec;
+                CK(cudaMemcpyAsync(rec, p->sb.scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToDevice, p->stream));
+                if (p->dm.ns) CK(cudaMemcpyAsync(rec + SC_COUNT + 1, p->sb.dstat, sizeof(double) * p->dm.ns, cudaMemcpyDeviceToDevice, p->stream));
+                if (p->spec_ag(p->spec_ctx, p->d_spec_rec, sizeof(double) * p->spec_rec, p->stream)) { set_err("speculation allgather failed"); return B200_NCCL_ERROR; }
+                CK(cudaMemcpyAsync(p->h_spec_rec, p->d_spec_rec, sizeof(double) * p->spec_rec * G * T, cudaMemcpyDeviceToHost, p->stream));
             }
-            const TrialVerdict v = judge_trial(L, p->err, solved, oldLin, newLin, newError);
-            status = solved ? B200_OK : B200_INDETERMINATE_SYSTEM;
-            if (v.step_ok) {
-                winner = h; win_err = newError;
-                if (!L.gauss_newton) p->lambda = std::max(L.lambda_lower_bound, p->lambda / L.lambda_factor);
-                p->iterations++; p->total_trials++;
-                p->have_lin = false;
-                status = B200_OK;
-                done = true;
-            } else if (!v.stop) {
-                p->lambda *= L.lambda_factor; p->total_trials++;
-                if (p->lambda >= L.lambda_upper_bound) { status = B200_LAMBDA_MAXED; done = true; }
-                else if (L.gauss_newton) { status = B200_INDETERMINATE_SYSTEM; done = true; }
-            } else done = true;
-        }
-        if (winner >= 0) {
-            if (G > 1) {
-                // every rank adopts the accepted group's step: gather the windows of all groups' steps, retract with the winner's
-                const size_t wdoubles = (size_t)p->Wk * p->dm.ntp;
-                CK(cudaMemcpyAsync(p->d_spec_delta + (size_t)(p->spec_g * T + p->rank) * wdoubles, p->sb.delta + (size_t)p->k_lo * p->dm.ntp,
-                                   sizeof(double) * wdoubles, cudaMemcpyDeviceToDevice, p->stream));
-                if (p->spec_ag(p->spec_ctx, p->d_spec_delta, sizeof(double) * wdoubles, p->stream)) { set_err("speculation allgather failed"); return B200_NCCL_ERROR; }
-                if (winner != p->spec_g)
-                    launch_retract(p, p->d_spec_delta + (size_t)winner * T * wdoubles, p->d_spec_rec + (size_t)winner * T * p->spec_rec + SC_COUNT + 1);
+            st = fetch_scalars(p); if (st != B200_OK) return st;
+            p->host_syncs++;
+            if (p->time_phases) {
+                float ms;
+                if (inner == 0) { cudaEventElapsedTime(&ms, p->ev[0], p->ev[1]); p->phase_ms[0] += ms; }
+                accumulate_phase_ms(p, p->tev[0]);
             }
-            std::swap(p->d_tv, p->d_tv_try); std::swap(p->d_sv, p->d_sv_try);
-            p->err = win_err;
+            int winner = -1;
+            double win_err = 0.0;
+            for (int h = 0; h < G && !done; h++) {  // the rungs in the order the sequential loop meets them
+                inner++;
+                // SC_FAIL is the all-reduced count of ranks (of this group) whose factorisation met a non-positive pivot
+                const double* sc = (G > 1) ? p->h_spec_rec + (size_t)h * T * p->spec_rec : p->h_scal;
+                const bool solved = sc[SC_FAIL] == 0.0;
+                const double newError = sc[SC_NEW_ERR];
+                const TrialVerdict v = judge_trial(L, p->err, solved, sc[SC_LIN_ERR], sc[SC_MODEL_ERR], newError);
+                status = solved ? B200_OK : B200_INDETERMINATE_SYSTEM;
+                if (v.step_ok) {
+                    winner = h; win_err = newError;
+                    if (!L.gauss_newton) p->lambda = std::max(L.lambda_lower_bound, p->lambda / L.lambda_factor);
+                    p->iterations++; p->total_trials++;
+                    p->have_lin = false;
+                    status = B200_OK;
+                    done = true;
+                } else if (!v.stop) {
+                    p->lambda *= L.lambda_factor; p->total_trials++;
+                    if (p->lambda >= L.lambda_upper_bound) { status = B200_LAMBDA_MAXED; done = true; }
+                    else if (L.gauss_newton) { status = B200_INDETERMINATE_SYSTEM; done = true; }
+                } else done = true;
+            }
+            if (winner >= 0) {
+                if (G > 1) {
+                    // every rank adopts the accepted group's step: gather the windows of all groups' steps, retract with the winner's
+                    const size_t wdoubles = (size_t)p->Wk * p->dm.ntp;
+                    CK(cudaMemcpyAsync(p->d_spec_delta + (size_t)(p->spec_g * T + p->rank) * wdoubles, p->d_delta + (size_t)p->k_lo * p->dm.ntp,
+                                       sizeof(double) * wdoubles, cudaMemcpyDeviceToDevice, p->stream));
+                    if (p->spec_ag(p->spec_ctx, p->d_spec_delta, sizeof(double) * wdoubles, p->stream)) { set_err("speculation allgather failed"); return B200_NCCL_ERROR; }
+                    if (winner != p->spec_g)
+                        launch_retract(p, p->d_spec_delta + (size_t)winner * T * wdoubles, p->d_spec_rec + (size_t)winner * T * p->spec_rec + SC_COUNT + 1);
+                }
+                std::swap(p->d_tv, p->d_tv_try); std::swap(p->d_sv, p->d_sv_try); p->parity ^= 1;
+                p->err = win_err;
+            }
         }
     }
     if (state) {
@@ -1003,6 +1236,7 @@ b200_status b200_lm_iterate(b200_problem* p, b200_lm_state* state) {
     }
     return (b200_status)status;
 }
+
 
 // bioslam's fastOptimize loops (reference src/lowerBodyPoseEstimator.cpp:651-667 ; src/imuPoseEstimator.cpp:330-359)
 b200_status b200_optimize(b200_problem* p, const b200_lm_params* lm, const b200_outer_params* op, double* hist, b200_optimize_result* res) {
@@ -1055,11 +1289,24 @@ b200_status b200_optimize(b200_problem* p, const b200_lm_params* lm, const b200_
 
 b200_status b200_phase_ms(b200_problem* p, double out[8], int32_t reset) {
     if (!p) return B200_BAD_ARG;
-    p->time_phases = true;
+    if (reset >= 0) p->time_phases = true;   // reset < 0: read without switching the per-phase events on
     if (out) for (int i = 0; i < 8; i++) out[i] = p->phase_ms[i];
-    if (reset) for (int i = 0; i < 8; i++) p->phase_ms[i] = 0;
+    if (reset > 0) for (int i = 0; i < 8; i++) p->phase_ms[i] = 0;
     return B200_OK;
 }
+
+// runtime switches: "graph" (0/1: launch lambda trials as CUDA graphs), "spec_trials" (trials queued per host synchronisation),
+// "phase_timing" (0/1: per-phase CUDA events; implies direct launches)
+b200_status b200_set_option(b200_problem* p, const char* name, int32_t value) {
+    if (!p || !name) return B200_BAD_ARG;
+    const std::string n(name);
+    if (n == "graph") p->use_graph = value != 0;
+    else if (n == "spec_trials") p->spec_trials = std::max(1, std::min((int)value, 4));
+    else if (n == "phase_timing") p->time_phases = value != 0;
+    else { set_err("unknown option " + n); return B200_BAD_ARG; }
+    return B200_OK;
+}
+int64_t b200_host_sync_count(const b200_problem* p) { return p ? p->host_syncs : 0; }
 
 b200_status b200_timer_begin(b200_problem* p) {
     if (!p) return B200_BAD_ARG;
@@ -1152,6 +1399,7 @@ b200_status b200_comm_set(b200_problem* p, int32_t world_size, int32_t rank, b20
     if (!p || world_size < 1 || rank < 0 || rank >= world_size) return B200_BAD_ARG;
     CK(cudaSetDevice(p->device));
     p->world = world_size; p->rank = rank; p->ag_fn = ag; p->ar_fn = ar; p->comm_ctx = ctx;
+    free_graphs(p);
     b200_status st = set_partition(p, 0, 0);
     // the speculation buffers are sized by the window of a rank: re-create them if the sharding changes afterwards
     if (st == B200_OK && p->spec_G > 1) st = b200_spec_set(p, p->spec_G, p->spec_g, p->spec_ag, p->spec_ctx);
@@ -1211,9 +1459,10 @@ b200_status b200_debug_get_hessian_blocks(b200_problem* p, int32_t k, double* D,
     if (!p || !p->have_lin || k < 0 || k >= p->K) return B200_BAD_ARG;
     const Dims& dm = p->dm;
     const int nt = dm.nt, ntp = dm.ntp, nc = dm.nc, nl = dm.nl, ns = dm.ns, ns1 = dm.ns1;
-    std::vector<double> Db((size_t)ntp * ntp), Ob((size_t)nc * nc), Ab((size_t)ns1 * ntp);
+    const int nco = dm.nco;
+    std::vector<double> Db((size_t)ntp * ntp), Ob((size_t)nco * nco), Ab((size_t)ns1 * ntp);
     CK(cudaMemcpy(Db.data(), p->d_D + (size_t)k * ntp * ntp, sizeof(double) * Db.size(), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(Ob.data(), p->d_O + (size_t)k * nc * nc, sizeof(double) * Ob.size(), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(Ob.data(), p->d_O + (size_t)k * nco * nco, sizeof(double) * Ob.size(), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(Ab.data(), p->d_A + (size_t)k * ns1 * ntp, sizeof(double) * Ab.size(), cudaMemcpyDeviceToHost));
     for (int i = 0; i < nt * nt; i++) { D[i] = 0; O[i] = 0; }
     for (int i = 0; i < ntp; i++)
@@ -1222,7 +1471,7 @@ b200_status b200_debug_get_hessian_blocks(b200_problem* p, int32_t k, double* D,
             if (ei < 0 || ej < 0) continue;
             D[(size_t)ei * nt + ej] = (i >= j) ? Db[(size_t)i * ntp + j] : Db[(size_t)j * ntp + i];   // only the lower triangle is assembled
             // O (k, k+1): rows k, cols k+1 ; device stores (k+1 chain) x (k chain)
-            if (k + 1 < p->K && i >= nl && j >= nl) O[(size_t)ej * nt + ei] = Ob[(size_t)(i - nl) * nc + (j - nl)];
+            if (k + 1 < p->K && i >= nl && j >= nl) O[(size_t)ej * nt + ei] = Ob[(size_t)(i - nl) * nco + (j - nl)];
         }
     for (int i = 0; i < ntp; i++) {
         const int ei = p->int2ext[i];
@@ -1250,17 +1499,69 @@ b200_status b200_debug_solve(b200_problem* p, double lambda, double* delta_time,
     if (!p || !p->have_lin) return B200_BAD_ARG;
     CK(cudaSetDevice(p->device));
     const Dims& dm = p->dm;
-    b200_status st = launch_solve(p, lambda);
+    b200_status st = push_lambda_try(p, lambda);
+    if (st != B200_OK) return st;
+    st = launch_solve(p, nullptr);
+    if (st != B200_OK) return st;
+    // a non-positive pivot on ANY rank marks the solve indeterminate on every rank
+    CK(cudaMemsetAsync(p->sb.scal, 0, sizeof(double) * SC_COUNT, p->stream));
+    B200_LAUNCH(status_to_scal_kernel, dim3(1), dim3(32), 0, p->stream, p->sb.status, p->sb.scal);
+    p->launches++;
+    st = allreduce_scal(p);
     if (st != B200_OK) return st;
     st = fetch_scalars(p);
     if (st != B200_OK) return st;
-    if (host_status(p) != 0) return B200_INDETERMINATE_SYSTEM;
+    if (p->h_scal[SC_FAIL] != 0.0) return B200_INDETERMINATE_SYSTEM;
     std::vector<double> dl((size_t)p->K * dm.ntp);
-    CK(cudaMemcpy(dl.data(), p->sb.delta, sizeof(double) * dl.size(), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(dl.data(), p->d_delta, sizeof(double) * dl.size(), cudaMemcpyDeviceToHost));
     for (int k = 0; k < p->K; k++)
         for (int i = 0; i < dm.ntp; i++)
             if (p->int2ext[i] >= 0) delta_time[(size_t)k * dm.nt + p->int2ext[i]] = dl[(size_t)k * dm.ntp + i];
     if (dm.ns) CK(cudaMemcpy(delta_static, p->sb.dstat, sizeof(double) * dm.ns, cudaMemcpyDeviceToHost));
+    return B200_OK;
+}
+
+// reduced blocks of keyframe k after the keyframe-local dofs have been eliminated at damping lambda (kernels_local.cuh), in the
+// internal chain order: Dc[nc*nc] (symmetric, both triangles filled here), Ac[ns1*nc] (static rows + rhs row), Sc[ns1*ns1].
+// dims[4] = {nl, nc, ns1, used (0: this problem has no pre-elimination)}; chain_ext[nc]: external tangent index of every chain dof.
+b200_status b200_debug_local_elim(b200_problem* p, int32_t k, double lambda, int32_t dims[4], int32_t* chain_ext, double* Dc, double* Ac, double* Sc) {
+    if (!p || !p->have_lin || k < 0 || k >= p->K || !dims) return B200_BAD_ARG;
+    CK(cudaSetDevice(p->device));
+    const Dims& dm = p->dm;
+    dims[0] = dm.nl; dims[1] = dm.nc; dims[2] = dm.ns1; dims[3] = p->use_le ? 1 : 0;
+    if (chain_ext) for (int i = 0; i < dm.nc; i++) chain_ext[i] = p->int2ext[dm.nl + i];
+    if (!p->use_le || !Dc || !Ac || !Sc) return B200_OK;
+    if (lambda >= 0.0) {   // (negative: read the blocks the last solve left behind)
+        b200_status st = push_lambda_try(p, lambda);
+        if (st != B200_OK) return st;
+        CK(cudaMemsetAsync(p->sb.status, 0, sizeof(int), p->stream));
+        B200_LAUNCH(local_elim_kernel, dim3(1), dim3(B200_LE_THREADS), p->smem_le, p->stream, p->le, (int)k, p->sb.lam, p->sb.status, (const int*)nullptr);
+        p->launches++;
+    }
+    CK(cudaStreamSynchronize(p->stream));
+    CK(cudaGetLastError());
+    const int nc = dm.nc, ncp = p->ds.ntp, ns1 = dm.ns1;
+    std::vector<double> d((size_t)ncp * ncp), a((size_t)ns1 * ncp);
+    CK(cudaMemcpy(d.data(), p->d_Dc + (size_t)k * ncp * ncp, sizeof(double) * d.size(), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(a.data(), p->d_Ac + (size_t)k * ns1 * ncp, sizeof(double) * a.size(), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(Sc, p->d_Sc + (size_t)k * ns1 * ns1, sizeof(double) * ns1 * ns1, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < nc; i++) for (int j = 0; j < nc; j++) Dc[(size_t)i * nc + j] = i >= j ? d[(size_t)i * ncp + j] : d[(size_t)j * ncp + i];
+    for (int r = 0; r < ns1; r++) for (int j = 0; j < nc; j++) Ac[(size_t)r * nc + j] = a[(size_t)r * ncp + j];
+    return B200_OK;
+}
+
+// raw read of a solver buffer (development / tests): name in {"Wst", "Yst", "delta_c", "delta", "Dc", "Ac", "O", "F0"}
+b200_status b200_debug_read(b200_problem* p, const char* name, int64_t offset, int64_t n, double* out) {
+    if (!p || !name || !out) return B200_BAD_ARG;
+    CK(cudaSetDevice(p->device));
+    const std::string s(name);
+    const double* src = nullptr;
+    if (s == "Wst") src = p->sb.Wst; else if (s == "Yst") src = p->sb.Yst; else if (s == "delta_c") src = p->sb.delta;
+    else if (s == "delta") src = p->d_delta; else if (s == "Dc") src = p->d_Dc; else if (s == "Ac") src = p->d_Ac; else if (s == "O") src = p->d_O;
+    else if (s == "F0") src = p->levels.empty() || !p->levels[0].F ? p->d_Ftop : p->levels[0].F;
+    if (!src) return B200_BAD_ARG;
+    CK(cudaStreamSynchronize(p->stream));
+    CK(cudaMemcpy(out, src + offset, sizeof(double) * n, cudaMemcpyDeviceToHost));
     return B200_OK;
 }
 

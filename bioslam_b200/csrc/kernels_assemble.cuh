@@ -2,7 +2,7 @@
 // per-factor Jacobians (staged in shared memory), one CTA per keyframe, both halves from the same staged Jacobians:
 //   half 0:  D_k  (ntp x ntp, time block of keyframe k; only the sub-blocks on or below the block diagonal: the solver reads
 //            the lower triangle)                                   + Sx_k ((ns+1) x (ns+1): static block and -g_static)
-//   half 1:  O_k  (nc x nc, chain part of keyframe k+1 vs k)        + Ax_k ((ns+1) x ntp: static rows, last row = -g_k)
+//   half 1:  O_k  (nc x nc, stride nco, chain part of keyframe k+1 vs k)        + Ax_k ((ns+1) x ntp: static rows, last row = -g_k)
 // Every block is owned by exactly one CTA and slots are visited in table order, so the sums are deterministic
 // (no atomics).  Internal tangent order inside a keyframe: [keyframe-local variables (nl) | time-chained variables (nc)].
 #pragma once
@@ -14,6 +14,7 @@ struct Dims {
     int K;
     long long Kld;
     int nt, ntp, nl, nc, ns, ns1;  // ntp = nt padded to even, nc = ntp - nl, ns1 = ns + 1
+    int nco;                       // row stride / dimension of the stored coupling blocks O_k (the SOLVER's chain dimension, >= nc)
     int ld;                        // shared-memory leading dimension (>= ntp, == 2 mod 4)
     int hmax;                      // ns1 + nc
     int sm_doubles;                // dynamic shared memory of the solver kernels, in doubles
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(512) assemble_kernel(Dims dm, const DevSlot* _
                                                        double* __restrict__ Ssrc) {
     B200_DYN_SMEM(double, St);  // staged Jacobians (rows*cols) + residuals (rows) of every item
     const int k = k_first + (int)blockIdx.x;
-    const int ntp = dm.ntp, nc = dm.nc, ns1 = dm.ns1;
+    const int ntp = dm.ntp, nc = dm.nco, ns1 = dm.ns1;   // nc: stride of O_k
     __shared__ unsigned char valid[256];
     // ---- which items exist at this keyframe; stage their Jacobians (contiguous per-instance records, issued in bulk)
     for (int it = threadIdx.x; it < pl.n_items; it += blockDim.x) {

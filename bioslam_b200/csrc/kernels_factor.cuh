@@ -44,7 +44,8 @@ template <bool WJ>
 __global__ void __launch_bounds__(128, 3) linearize_kernel(const DevSlot* __restrict__ slots, const double* __restrict__ tv,
                                                         const double* __restrict__ sv, const double* __restrict__ cst, long long Kld,
                                                         double* __restrict__ Jbuf, double* __restrict__ rbuf, double* __restrict__ ebuf,
-                                                        int k_lo, int k_hi, int e_lo) {
+                                                        int k_lo, int k_hi, int e_lo, const int* __restrict__ skip) {
+    if (skip != nullptr && *skip != 0) return;   // (lambda trial no longer needed: see lm_judge_kernel)
     // keyframes [k_lo, k_hi) are evaluated; only [e_lo, k_hi) count towards this rank's cost (a sharded rank also linearizes
     // the keyframe left of its window, whose factors belong to the neighbour's cost)
     const DevSlot& s = slots[blockIdx.y];
@@ -112,8 +113,10 @@ __global__ void factor_eval_kernel(int type, int nvars, const int* __restrict__ 
 }
 
 // deterministic sum of n doubles: fixed strided partials per thread, fixed shared-memory tree.  grid 1, block 1024.
-__global__ void __launch_bounds__(1024) reduce_sum_kernel(const double* __restrict__ v, long long n, double* __restrict__ out) {
+__global__ void __launch_bounds__(1024) reduce_sum_kernel(const double* __restrict__ v, long long n, double* __restrict__ out,
+                                                          const int* __restrict__ skip) {
     __shared__ double sh[1024];
+    if (skip != nullptr && *skip != 0) return;
     double acc = 0.0;
     for (long long i = threadIdx.x; i < n; i += 1024) acc += v[i];
     sh[threadIdx.x] = acc;
@@ -129,7 +132,9 @@ __global__ void __launch_bounds__(1024) reduce_sum_kernel(const double* __restri
 // dtime[K][ntp], dstat[ns].  zero_delta: evaluate at delta = 0 (== linear.error(Zero)).
 __global__ void __launch_bounds__(128) model_error_kernel(const DevSlot* __restrict__ slots, const double* __restrict__ Jbuf,
                                                           const double* __restrict__ rbuf, const double* __restrict__ dtime, int ntp,
-                                                          const double* __restrict__ dstat, double* __restrict__ ebuf, int k_lo, int k_hi) {
+                                                          const double* __restrict__ dstat, double* __restrict__ ebuf, int k_lo, int k_hi,
+                                                          const int* __restrict__ skip) {
+    if (skip != nullptr && *skip != 0) return;
     const DevSlot& s = slots[blockIdx.y];
     const int inst = blockIdx.x * blockDim.x + threadIdx.x;
     if (inst >= s.n_inst) return;
@@ -161,7 +166,8 @@ struct DevVar {
 __global__ void __launch_bounds__(128) retract_kernel(const DevVar* __restrict__ tvars, int ntv, const DevVar* __restrict__ svars, int nsv,
                                                       int K, long long Kld, const double* __restrict__ tv, const double* __restrict__ sv,
                                                       const double* __restrict__ dtime, int ntp, const double* __restrict__ dstat,
-                                                      double* __restrict__ tv_out, double* __restrict__ sv_out) {
+                                                      double* __restrict__ tv_out, double* __restrict__ sv_out, const int* __restrict__ skip) {
+    if (skip != nullptr && *skip != 0) return;
     if (blockIdx.y == 1) {
         const int v = blockIdx.x * blockDim.x + threadIdx.x;
         if (v >= nsv) return;

@@ -1,0 +1,187 @@
+// Keyframe-local dofs (the angular velocities of the 7-IMU graph: SURVEY.md section 7 step 6a, section 8(e) "ang-vel is not
+// time-coupled") are eliminated for ALL keyframes in one parallel kernel before the sequential chain sweep, so the chain
+// pivot shrinks from ntp (126) to the time-chained dofs only (105 -> 106 with padding):
+//
+//   [ D_ll + lambda I   D_lc   A_l^T ] [d_l]   [-g_l]        L L^T = D_ll + lambda I,   V = [D_cl ; A_l ; -g_l^T] L^-T
+//   [ D_cl              D_cc   A_c^T ] [d_c] = [-g_c]   ->   Dc = D_cc + lambda I - V_c V_c^T,  Ac = [A_c ; -g_c^T] - V_a V_c^T,
+//   [ A_l               A_c    S     ] [d_s]   [-g_s]        Sc = S_k - V_a V_a^T            (V_c: first nc rows, V_a: last ns1)
+//
+// and recovered after the chain back-substitution:  d_l = -L^-T ( V_c^T d_c + V_a^T [d_s, -1] ).
+// The rank-nl updates run on the fp64 tensor pipe (same 16 x 32 DMMA warp tile as the sweep); the kernel is bound by HBM
+// (reads the lower triangle of D_k, A_k, S_k once, writes the reduced blocks once).
+#pragma once
+#include "kernels_solve.cuh"
+
+namespace b200d {
+
+#define B200_LE_THREADS 256
+#define B200_LE_MAXNL 32
+
+struct LocalElim {
+    int nl, nc, ncp, ns1, ntp;      // local dofs, chain dofs (incl. the padding dof of an odd nt), chain dim of the solver (even), statics + rhs
+    int ldl;                        // shared-memory stride of the nl-wide panels (== 4 mod 8: conflict-free DMMA operand loads)
+    const double *D, *A, *S;        // assembled blocks: [K][ntp*ntp] (lower), [K][ns1*ntp], [K][ns1*ns1]
+    double *Dc, *Ac, *Sc;           // reduced blocks: [K][ncp*ncp] (lower), [K][ns1*ncp], [K][ns1*ns1]
+    double *V, *Wl;                 // [K][(nc+ns1)*nl] forward-substituted local panel, [K][nl*nl] L^-1 (lower)
+};
+__host__ __device__ inline int le_ldl(int nl) { int l = nl; while ((l & 7) != 4) l++; return l; }
+__host__ __device__ inline long long le_smem_doubles(int nl, int nc, int ns1) { return (long long)(2 * nl + nc + ns1) * le_ldl(nl); }
+
+// grid = keyframes [k_first, k_first + gridDim.x)
+__global__ void __launch_bounds__(B200_LE_THREADS) local_elim_kernel(LocalElim le, int k_first, const double* __restrict__ lambda_p, int* status,
+                                                                     const int* __restrict__ skip) {
+    B200_DYN_SMEM(double, sm);
+    if (skip && *skip) return;
+    const int nl = le.nl, nc = le.nc, ncp = le.ncp, ns1 = le.ns1, ntp = le.ntp, ldl = le.ldl, hp = nc + ns1;
+    const long long k = k_first + (long long)blockIdx.x;
+    const double lambda = *lambda_p;
+    double* Ls = sm;                                   // nl x ldl: L (lower)
+    double* Ws = Ls + (long long)nl * ldl;             // nl x ldl: L^-1 (lower)
+    double* Vs = Ws + (long long)nl * ldl;             // (nc + ns1) x ldl: panel -> V
+    const double* Dk = le.D + k * ntp * ntp;
+    const double* Ak = le.A + k * ns1 * ntp;
+    const double* Sk = le.S + k * ns1 * ns1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    __shared__ int s_fail;
+    if (threadIdx.x == 0) s_fail = 0;
+    for (int e = threadIdx.x; e < nl * nl; e += blockDim.x) {
+        const int r = e / nl, c = e - r * nl;
+        Ls[r * ldl + c] = (c <= r) ? Dk[(long long)r * ntp + c] + (r == c ? lambda : 0.0) : 0.0;
+        Ws[r * ldl + c] = 0.0;
+    }
+    for (int e = threadIdx.x; e < hp * nl; e += blockDim.x) {
+        const int r = e / nl, c = e - r * nl;
+        Vs[r * ldl + c] = (r < nc) ? Dk[(long long)(nl + r) * ntp + c] : Ak[(long long)(r - nc) * ntp + c];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // Cholesky of the nl x nl block (right-looking, one column per step), then its inverse column by column
+        int fail = 0;
+        for (int j = 0; j < nl; j++) {
+            const double d = Ls[j * ldl + j];
+            __syncwarp();   // every lane has read the pivot before lane 0 overwrites it with its square root
+            if (!(d > 0.0) || !(d < 1.0e300)) { fail = 1; break; }
+            const double s = rsqrt(d);
+            for (int i = j + lane; i < nl; i += 32) Ls[i * ldl + j] *= s;   // diagonal: d * rsqrt(d) = sqrt(d)
+            __syncwarp();
+            for (int i = j + 1 + lane; i < nl; i += 32) {
+                const double f = Ls[i * ldl + j];
+                for (int c = j + 1; c <= i; c++) Ls[i * ldl + c] = fma(-f, Ls[c * ldl + j], Ls[i * ldl + c]);
+            }
+            __syncwarp();
+        }
+        if (fail) { if (lane == 0) s_fail = 1; }
+        else {
+            for (int c = lane; c < nl; c += 32) {   // column c of L^-1 (private to the lane)
+                for (int r = c; r < nl; r++) {
+                    double v = (r == c) ? 1.0 : 0.0;
+                    for (int q = c; q < r; q++) v = fma(-Ls[r * ldl + q], Ws[q * ldl + c], v);
+                    Ws[r * ldl + c] = v / Ls[r * ldl + r];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (s_fail) { if (threadIdx.x == 0) atomicCAS(status, 0, (int)(k + 1)); return; }
+    // V = P L^-T :  V[r][j] = sum_{c <= j} P[r][c] W[j][c]   (one thread per row, row in registers)
+    for (int r = threadIdx.x; r < hp; r += blockDim.x) {
+        double x[B200_LE_MAXNL];
+#pragma unroll
+        for (int c = 0; c < B200_LE_MAXNL; c++) x[c] = (c < nl) ? Vs[r * ldl + c] : 0.0;
+        for (int j = nl - 1; j >= 0; j--) {   // descending: entry j only needs entries <= j of the ORIGINAL row
+            double v = 0.0;
+#pragma unroll
+            for (int c = 0; c < B200_LE_MAXNL; c++) if (c <= j) v = fma(x[c], Ws[j * ldl + c], v);
+            Vs[r * ldl + j] = v;
+        }
+        for (int c = nl; c < ldl; c++) Vs[r * ldl + c] = 0.0;
+    }
+    __syncthreads();
+    {   // factors of the local block for the back-substitution
+        double* Vg = le.V + k * (long long)hp * nl;
+        for (int e = threadIdx.x; e < hp * nl; e += blockDim.x) { const int r = e / nl, c = e - r * nl; Vg[e] = Vs[r * ldl + c]; }
+        double* Wg = le.Wl + k * (long long)nl * nl;
+        for (int e = threadIdx.x; e < nl * nl; e += blockDim.x) { const int r = e / nl, c = e - r * nl; Wg[e] = Ws[r * ldl + c]; }
+    }
+    // rank-nl updates, 16 x 32 warp tiles: [0, nD) Dc (lower), [nD, nD + nA) Ac, then Sc (lower, mirrored)
+    const int rtc = (nc + 15) >> 4, ctc = (nc + 31) >> 5, rts = (ns1 + 15) >> 4;
+    int nD = 0;
+    for (int rt = 0; rt < rtc; rt++) nD += ((16 * rt + 15) >> 5) + 1;
+    const int nA = rts * ctc;
+    int nS = 0;
+    for (int rt = 0; rt < rts; rt++) nS += ((16 * rt + 15) >> 5) + 1;
+    double* Dck = le.Dc + k * (long long)ncp * ncp;
+    double* Ack = le.Ac + k * (long long)ns1 * ncp;
+    double* Sck = le.Sc + k * (long long)ns1 * ns1;
+    const int mg = lane >> 2, mt = lane & 3;
+    const double* Va = Vs + (long long)nc * ldl;
+    for (int tile = warp; tile < nD + nA + nS; tile += nwarps) {
+        int kind, rt = 0, ct = 0;
+        if (tile < nD) { kind = 0; int t = tile; while (t >= ((16 * rt + 15) >> 5) + 1) { t -= ((16 * rt + 15) >> 5) + 1; rt++; } ct = t; }
+        else if (tile < nD + nA) { kind = 1; rt = (tile - nD) / ctc; ct = (tile - nD) % ctc; }
+        else { kind = 2; int t = tile - nD - nA; while (t >= ((16 * rt + 15) >> 5) + 1) { t -= ((16 * rt + 15) >> 5) + 1; rt++; } ct = t; }
+        Acc acc;
+        acc_zero(acc);
+        const int m0 = rt << 4, c0 = ct << 5;
+        if (kind == 0) warp_mma_nt(Vs, ldl, m0, nc, Vs, ldl, c0, nc, 0, nl, acc);
+        else if (kind == 1) warp_mma_nt(Va, ldl, m0, ns1, Vs, ldl, c0, nc, 0, nl, acc);
+        else warp_mma_nt(Va, ldl, m0, ns1, Va, ldl, c0, ns1, 0, nl, acc);
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int r = m0 + 8 * i + mg;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int c = c0 + 8 * j + 2 * mt + e;
+                    if (kind == 0) {
+                        if (r < nc && c <= r) Dck[(long long)r * ncp + c] = Dk[(long long)(nl + r) * ntp + nl + c] + (r == c ? lambda : 0.0) - acc[i][j][e];
+                    } else if (kind == 1) {
+                        if (r < ns1 && c < nc) Ack[(long long)r * ncp + c] = Ak[(long long)r * ntp + nl + c] - acc[i][j][e];
+                    } else if (r < ns1 && c <= r) {
+                        const double v = Sk[(long long)r * ns1 + c] - acc[i][j][e];
+                        Sck[(long long)r * ns1 + c] = v;
+                        Sck[(long long)c * ns1 + r] = v;
+                    }
+                }
+            }
+        }
+    }
+    // padding dof of the solver's chain block (ncp > nc): identity
+    if (threadIdx.x == 0 && ncp > nc) Dck[(long long)nc * ncp + nc] = 1.0;
+}
+
+// d_l = -L^-T ( V_c^T d_c + V_a^T [d_s, -1] ) for every keyframe of [k_first, ...), and the full step in the internal order
+// [local | chain] that retract_kernel / model_error_kernel consume.  delta_c: [K][ncp] (solver), delta: [K][ntp].
+__global__ void __launch_bounds__(128) local_backsub_kernel(LocalElim le, int k_first, int k_end, const double* __restrict__ delta_c,
+                                                            const double* __restrict__ dstat, double* __restrict__ delta, const int* __restrict__ status,
+                                                            const int* __restrict__ skip) {
+    if (skip && *skip) return;
+    if (*status != 0) return;
+    const int nl = le.nl, nc = le.nc, ncp = le.ncp, ns1 = le.ns1, ntp = le.ntp, hp = nc + ns1;
+    const long long k = k_first + (long long)blockIdx.x;
+    if (k >= k_end) return;
+    __shared__ double x[512 + 256], part[4][B200_LE_MAXNL], t[B200_LE_MAXNL];
+    for (int j = threadIdx.x; j < nc; j += blockDim.x) x[j] = delta_c[k * ncp + j];
+    for (int a = threadIdx.x; a < ns1; a += blockDim.x) x[nc + a] = (a < ns1 - 1) ? dstat[a] : -1.0;
+    __syncthreads();
+    const double* Vg = le.V + k * (long long)hp * nl;
+    const int c = threadIdx.x & 31, q = threadIdx.x >> 5;
+    double s = 0.0;
+    if (c < nl) for (int r = q; r < hp; r += 4) s = fma(Vg[(long long)r * nl + c], x[r], s);
+    part[q][c] = s;
+    __syncthreads();
+    if (threadIdx.x < (unsigned)nl) t[threadIdx.x] = (part[0][threadIdx.x] + part[1][threadIdx.x]) + (part[2][threadIdx.x] + part[3][threadIdx.x]);
+    __syncthreads();
+    double* dk = delta + k * ntp;
+    if (threadIdx.x < (unsigned)nl) {
+        const double* Wg = le.Wl + k * (long long)nl * nl;
+        const int i = threadIdx.x;
+        double v = 0.0;
+        for (int j = i; j < nl; j++) v = fma(Wg[(long long)j * nl + i], t[j], v);
+        dk[i] = -v;
+    }
+    for (int j = threadIdx.x; j < nc; j += blockDim.x) dk[nl + j] = x[j];
+}
+
+}  // namespace b200d

@@ -321,7 +321,7 @@ __device__ __forceinline__ void warp_mma_nt32_kind(int ni, bool diag, const doub
 }
 
 // ------------------------------------------------------------------------------------------------- 16 x 16 building blocks
-#define B200_WLD 18  // leading dimension of the 16 x 16 inverse diagonal block in shared memory (== 2 mod 4)
+#define B200_WLD 20  // leading dimension of the 16 x 16 inverse diagonal block in shared memory (== 4 mod 8: conflict-free DMMA operand loads)
 
 // Diagonal block by ONE warp, entirely in registers: lane l < 16 owns row l of the jb x jb block (jb <= 16, padded with
 // identity); lane 16 + r carries row r of an appended identity, which the same column operations turn into row r of
@@ -710,7 +710,7 @@ struct SweepArgs {
 };
 
 // shared-memory carve-up of the sweep (doubles): Ms [ntp*ld] | Yb [cr*ld] | Op [max(nc*owp, 2*nc*OSLD)]
-#define B200_OSLD 18   // row stride of a 16-column slab of a dense coupling block (== 2 mod 4)
+#define B200_OSLD 20   // row stride of a 16-column slab of a dense coupling block (== 4 mod 8)
 __host__ __device__ inline long long sweep_op_doubles(int nc, int owp) {
     const long long a = ((long long)nc * owp + 1) & ~1LL, b = 2LL * nc * B200_OSLD;
     return a > b ? a : b;
@@ -1202,7 +1202,11 @@ struct SolveBuffers {
     double *delta, *dstat;                    // solution (internal order), delta per storage index
     double* scal;                             // scalar outputs
     int* status;
+    const double* lam;                        // lambda of the trial being solved (device scalar: written by the LM judge kernel / the host)
+    int lam_in_sweep;                         // the sweeps add lambda to the pivot blocks (0: already in the sources, see kernels_local.cuh)
+    const int* skip;                          // non-null and *skip != 0: this lambda trial is not needed any more, every kernel returns at once
 };
+__device__ __forceinline__ bool solve_skipped(const SolveBuffers& sb) { return sb.skip != nullptr && *sb.skip != 0; }
 
 // arrow rows [lo, hi) of split y out of ns (h rows in total)
 __device__ __forceinline__ int split_lo(int h, int ns, int y) { return (int)((long long)y * h / ns); }
@@ -1230,11 +1234,12 @@ __device__ __forceinline__ void level_chunk_args(const Dims& dm, const Level& lv
 
 // grid = number of chunks of this level owned by this rank (chunk = c_first + blockIdx.x)
 template <bool DENSE>
-__global__ void __launch_bounds__(B200_SOLVE_THREADS) chain_sweep_kernel(Dims dm, Level lv, SolveBuffers sb, double lambda, int c_first) {
+__global__ void __launch_bounds__(B200_SOLVE_THREADS) chain_sweep_kernel(Dims dm, Level lv, SolveBuffers sb, int c_first) {
     B200_DYN_SMEM(double, sm);
+    if (solve_skipped(sb)) return;
     SweepArgs a;
     level_chunk_args(dm, lv, sb, c_first + blockIdx.x, a, blockIdx.y);
-    a.lambda = lambda;
+    a.lambda = sb.lam_in_sweep ? *sb.lam : 0.0;
     cta_sweep<DENSE>(dm, a, sm);
 }
 
@@ -1243,6 +1248,7 @@ __global__ void __launch_bounds__(B200_SOLVE_THREADS) chain_sweep_kernel(Dims dm
 // all nodes of the chunk (fixed summation order, no atomics).  The stored panel of a node is staged through shared memory.
 __global__ void __launch_bounds__(B200_SCHUR_THREADS, 1) chain_schur_kernel(Dims dm, Level lv, SolveBuffers sb, int c_first, int ldy, int kslab) {
     B200_DYN_SMEM(double, Ys);
+    if (solve_skipped(sb)) return;
     SweepArgs a;
     level_chunk_args(dm, lv, sb, c_first + blockIdx.x, a);
     const int n = dm.ntp, ns1 = dm.ns1, hmax = dm.hmax, h = a.h;
@@ -1351,7 +1357,8 @@ __global__ void __launch_bounds__(B200_SCHUR_THREADS, 1) chain_schur_kernel(Dims
 
 // Schur complements onto separator c of this level: from chunk c (its right side) and chunk c+1 (its left side).
 // grid = separators handled (separator = c_first + blockIdx.x)
-__global__ void __launch_bounds__(256) chain_reduce_kernel(Dims dm, Level lv, int c_first) {
+__global__ void __launch_bounds__(256) chain_reduce_kernel(Dims dm, Level lv, int c_first, const int* __restrict__ skip) {
+    if (skip != nullptr && *skip != 0) return;
     const int c = c_first + blockIdx.x;
     const int P = lv.P;
     const int ntp = dm.ntp, nl = dm.nl, nc = dm.nc, ns1 = dm.ns1, hmax = dm.hmax;
@@ -1452,6 +1459,7 @@ __device__ __forceinline__ void cta_yt_coef(const double* __restrict__ Yg, int n
 __global__ void __launch_bounds__(B200_PREPASS_THREADS) chain_backsub_prepass_kernel(Dims dm, Level lv, SolveBuffers sb, int c_first) {
     __shared__ double coef[512];
     __shared__ double part[B200_PREPASS_THREADS];
+    if (solve_skipped(sb)) return;
     const int c = c_first + blockIdx.y;
     SweepArgs a;
     level_chunk_args(dm, lv, sb, c, a);
@@ -1579,6 +1587,7 @@ __device__ void cta_backsub(const Dims& dm, const SweepArgs& a, const double* co
 // grid = chunks of this level owned by this rank: back-substitution of the chunk's interior nodes
 __global__ void __launch_bounds__(B200_SOLVE_THREADS) chain_backsub_kernel(Dims dm, Level lv, SolveBuffers sb, int c_first) {
     B200_DYN_SMEM(double, sm);
+    if (solve_skipped(sb)) return;
     const int c = c_first + blockIdx.x;
     const int ke = lv.begin[c + 1];
     SweepArgs a;
@@ -1591,10 +1600,12 @@ __global__ void __launch_bounds__(B200_SOLVE_THREADS) chain_backsub_kernel(Dims 
 }
 
 // single CTA, after the top-level sweep + Schur kernels (Level with P == 1): static system, back-substitution of the top nodes
-__global__ void __launch_bounds__(B200_SOLVE_THREADS) top_finish_kernel(Dims dm, Level lv, SolveBuffers sb, double lambda) {
+__global__ void __launch_bounds__(B200_SOLVE_THREADS) top_finish_kernel(Dims dm, Level lv, SolveBuffers sb) {
     B200_DYN_SMEM(double, sm);
     const int ns = dm.ns, ns1 = dm.ns1, hmax = dm.hmax;
+    if (solve_skipped(sb)) return;
     if (*sb.status != 0) return;
+    const double lambda = *sb.lam;
     SweepArgs a;
     level_chunk_args(dm, lv, sb, 0, a);
     // static system: (Sacc[0:ns,0:ns] + lambda I) ds = Sacc[ns][0:ns]; the rhs row rides along as a panel row

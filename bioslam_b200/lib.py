@@ -42,6 +42,10 @@ def load(path=None):
     L.b200_spec_set.argtypes = [C.c_void_p, C.c_int32, C.c_int32, ALLGATHER_FN, C.c_void_p]
     L.b200_get_levels.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.c_int32]
     L.b200_debug_get_scalars.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    L.b200_debug_local_elim.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_void_p]
+    L.b200_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int32]
+    L.b200_host_sync_count.argtypes = [C.c_void_p]
+    L.b200_host_sync_count.restype = C.c_int64
     L.b200_lower_body_joint_angles.argtypes = [C.c_void_p, C.POINTER(abi.JointAngleDesc), C.c_void_p]
     _libs[path] = L
     return L
@@ -147,6 +151,12 @@ class Problem:
                  ok=(abi.OK, abi.LAMBDA_MAXED, abi.INDETERMINATE_SYSTEM))
         return res, hist[:res.n_history].copy()
 
+    def set_option(self, name, value):
+        self._ck(self.L.b200_set_option(self.h, name.encode(), C.c_int32(int(value))))
+
+    def host_sync_count(self):
+        return int(self.L.b200_host_sync_count(self.h))
+
     def launch_count(self):
         return int(self.L.b200_launch_count(self.h))
 
@@ -181,6 +191,18 @@ class Problem:
         S = np.zeros(max(self.ns * self.ns, 1))
         self._ck(self.L.b200_debug_get_static_hessian(self.h, D(S)))
         return S[:self.ns * self.ns].reshape(self.ns, self.ns)
+
+    def local_elim(self, k, lam):
+        """(chain_ext, Dc, Ac, Sc) of keyframe k: the blocks left after the keyframe-local dofs are eliminated at damping lam
+        (None if this problem has no pre-elimination)"""
+        dims = (C.c_int32 * 4)()
+        self._ck(self.L.b200_debug_local_elim(self.h, C.c_int32(k), C.c_double(lam), dims, None, None, None, None))
+        nl, nc, ns1, used = list(dims)
+        if not used:
+            return None
+        ext = (C.c_int32 * nc)(); Dc = np.zeros((nc, nc)); Ac = np.zeros((ns1, nc)); Sc = np.zeros((ns1, ns1))
+        self._ck(self.L.b200_debug_local_elim(self.h, C.c_int32(k), C.c_double(lam), dims, ext, D(Dc), D(Ac), D(Sc)))
+        return np.array(list(ext)), Dc, Ac, Sc
 
     def solve(self, lam):
         dt = np.zeros((self.K, self.nt)); ds = np.zeros(max(self.ns, 1))

@@ -319,6 +319,13 @@ b200_status b200_debug_get_hessian_blocks(b200_problem* p, int32_t k, double* D,
 b200_status b200_debug_get_static_hessian(b200_problem* p, double* S /*[ns*ns]*/);
 /* solve (J^T J + lambda I) delta = -J^T r on the last linearization */
 b200_status b200_debug_solve(b200_problem* p, double lambda, double* delta_time /*[K][nt]*/, double* delta_static);
+/* reduced blocks of keyframe k after the elimination of the keyframe-local dofs (angular velocities) at damping lambda -- the
+ * Schur complement the chain solver works on.  dims[4] = {nl, nc, ns1, used}; chain_ext[nc] = external tangent index of every
+ * chain dof; Dc[nc*nc] (symmetric), Ac[ns1*nc] (static rows, last row = -gradient), Sc[ns1*ns1].  Call with NULL outputs to
+ * query the dimensions. */
+b200_status b200_debug_local_elim(b200_problem* p, int32_t k, double lambda, int32_t dims[4], int32_t* chain_ext, double* Dc, double* Ac, double* Sc);
+/* raw read of an internal solver buffer (development only; layouts in DESIGN.md section 2) */
+b200_status b200_debug_read(b200_problem* p, const char* name, int64_t offset, int64_t n, double* out);
 /* one factor instance of `type` evaluated on the device by the same device functions linearize_kernel uses: residual r[rows]
  * and Jacobian J[rows*cols] (row-major; whitened if whiten != 0).  params: B200_MAX_FACTOR_PARAMS doubles; consts: the factor's
  * per-keyframe constant record (or NULL); xcat: the variables' values concatenated in factor order.  Replaces, for tests, the
@@ -335,6 +342,14 @@ int64_t b200_launch_count(const b200_problem* p);
  * out[5] top_solve_kernel ms, out[6] top_solve_kernel launches, out[7] chain_backsub_kernel ms.
  * The first call switches the per-phase events on. */
 b200_status b200_phase_ms(b200_problem* p, double out[8], int32_t reset);
+/* runtime switches of the LM driver (b200_lm_iterate): "graph" 0/1 -- every lambda trial is one instantiated CUDA graph (default
+ * 1, single rank); "spec_trials" 1..4 -- lambda trials queued on the device per host synchronisation (default 2: the accept /
+ * reject / damping decisions are taken on the device by lm_judge_kernel, trials queued behind an accepted one return at once);
+ * "phase_timing" 0/1 -- per-phase CUDA events (direct launches instead of graphs). */
+b200_status b200_set_option(b200_problem* p, const char* name, int32_t value);
+/* host <-> device synchronisations issued by b200_lm_iterate since creation (1 per iterate() when the ladder ends inside the
+ * queued trials) */
+int64_t b200_host_sync_count(const b200_problem* p);
 /* CUDA-event stopwatch on the problem's stream (the stream every kernel of this problem is launched on) */
 b200_status b200_timer_begin(b200_problem* p);
 b200_status b200_timer_end(b200_problem* p, double* ms);

@@ -86,3 +86,38 @@ def assert_preintegration_parity(a, b, combined):
             Ia, Ib = Ra.T @ Ra, Rb.T @ Rb
             s = np.sqrt(np.outer(np.diag(Ia), np.diag(Ia)))
             assert np.abs((Ia - Ib) / s).max() < 1e-11
+
+
+def assert_local_elimination_parity(p, g, lam, ks, tol=1e-13):
+    """the Schur complement of the keyframe-local dofs (kernels_local.cuh) against a 40-digit mpmath evaluation on the blocks the
+    device assembled: D_cc + lam I - D_cl (D_ll + lam I)^-1 D_lc cancels eight digits in the gyro-bias block (the angular-velocity
+    factor ties bias and angular velocity with information 1.6e8), so a double-precision reference is itself wrong at 1e-10;
+    entrywise tolerance relative to the magnitude of the terms that cancel."""
+    import mpmath as mp
+    mp.mp.dps = 40
+    for k in ks:
+        out = p.local_elim(k, lam)
+        if out is None:
+            return False
+        ext, Dc, Ac, Sc = out
+        D, _, A = p.hessian_blocks(k)
+        gt, _ = p.gradient()
+        nt = g.nt
+        chain = [int(e) for e in ext if e >= 0]
+        loc = [i for i in range(nt) if i not in set(chain)]
+        n, nl = len(chain), len(loc)
+        Dl = mp.matrix(D[np.ix_(loc, loc)].tolist())
+        for i in range(nl):
+            Dl[i, i] += mp.mpf(lam)
+        Dli = mp.inverse(Dl)
+        Dcl = mp.matrix(D[np.ix_(chain, loc)].tolist())
+        Pl = mp.matrix(np.vstack([A[loc].T, -gt[k][loc][None]]).tolist())           # (ns + 1) x nl: static rows, rhs row
+        Pc = np.vstack([A[chain].T, -gt[k][chain][None]])
+        cD, cA = Dcl * Dli * Dcl.T, Pl * Dli * Dcl.T
+        refD = np.array([[float(mp.mpf(D[chain[i], chain[j]]) + (mp.mpf(lam) if i == j else 0) - cD[i, j]) for j in range(n)] for i in range(n)])
+        sD = np.array([[float(mp.sqrt(abs(cD[i, i] * cD[j, j]))) for j in range(n)] for i in range(n)]) + np.abs(D[np.ix_(chain, chain)]) + 1e-300
+        assert (np.abs(Dc[:n, :n] - refD) / sD).max() <= tol, (k, (np.abs(Dc[:n, :n] - refD) / sD).max())
+        refA = np.array([[float(mp.mpf(Pc[a, j]) - cA[a, j]) for j in range(n)] for a in range(Pc.shape[0])])
+        sA = np.abs(np.array([[float(cA[a, j]) for j in range(n)] for a in range(Pc.shape[0])])) + np.abs(Pc) + 1e-9 * np.abs(Pc).max()
+        assert (np.abs(Ac[:, :n] - refA) / sA).max() <= 1e-11, (k, (np.abs(Ac[:, :n] - refA) / sA).max())
+    return True

@@ -130,3 +130,15 @@ def test_degenerate_geometry_on_device_functions(emu):
         r, J = lib.factor_eval(ft, prm, None, x, so_path=emu)
         ro, Jo = po.factor_eval(ft, prm, None, x)
         assert np.all(np.isfinite(J)) and np.allclose(J, Jo, atol=1e-14) and np.allclose(r, ro, atol=1e-14)
+
+
+def test_local_dof_elimination_is_exact_to_rounding(emu):
+    """kernels_local.cuh: the angular velocities eliminated per keyframe before the chain sweep (Schur complement against mpmath)"""
+    _, g, tv, sv = lower_body(1.0)
+    p = lib.Problem(g, so_path=emu, chunks=2); p.set_values(tv, sv); p.linearize()
+    assert pc.assert_local_elimination_parity(p, g, 1e-3, [0, 4, g.K - 1])
+    # a graph without keyframe-local dofs has nothing to pre-eliminate
+    tr = synth.make_trial(seed=4, duration_s=1.0)
+    g1, tv1, sv1 = graphs.single_imu_graph(tr.acc[0], tr.gyro[0], tr.dt)
+    p1 = lib.Problem(g1, so_path=emu, chunks=1); p1.set_values(tv1, sv1); p1.linearize()
+    assert p1.local_elim(0, 1.0) is None
