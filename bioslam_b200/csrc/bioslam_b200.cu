@@ -9,7 +9,13 @@
 #include "kernels_preint.cuh"
 #include "kernels_solve.cuh"
 #include "kernels_local.cuh"
+#include "kernels_sweep_pipe.cuh"
 #include "kernels_jointangles.cuh"
+
+#ifndef B200_USE_EMU
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: the entry points are resolved with dlsym, so the library loads without NCCL
+#endif
 
 using namespace b200d;
 
@@ -64,6 +70,48 @@ struct LmDev {
     int accepted;        // the try buffers hold the accepted step
     int pad0, pad1;
 };
+
+#ifndef B200_USE_EMU
+// NCCL, resolved at run time from the libnccl.so.2 the process already has (torch's bundled copy in the Python host) or the
+// system one.  In-library collectives (b200_nccl_init) remove the host round trip of the b200_comm_set callbacks.
+struct NcclApi {
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommSplit) CommSplit = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    bool ok = false;
+};
+static NcclApi& nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return api;
+#define B200_NCCL_SYM(n) api.n = reinterpret_cast<decltype(api.n)>(dlsym(h, "nccl" #n))
+    B200_NCCL_SYM(GetUniqueId); B200_NCCL_SYM(CommInitRank); B200_NCCL_SYM(CommSplit); B200_NCCL_SYM(CommDestroy); B200_NCCL_SYM(AllGather);
+    B200_NCCL_SYM(AllReduce); B200_NCCL_SYM(GroupStart); B200_NCCL_SYM(GroupEnd); B200_NCCL_SYM(GetErrorString);
+#undef B200_NCCL_SYM
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommSplit && api.CommDestroy && api.AllGather && api.AllReduce && api.GroupStart && api.GroupEnd;
+    return api;
+}
+struct NcclCtx { ncclComm_t comm = nullptr; int nranks = 1, rank = 0; };
+static int nccl_allgather_cb(void* ctx, void* buf, uint64_t bytes_per_rank, void* stream) {
+    NcclCtx* c = static_cast<NcclCtx*>(ctx);
+    return nccl_api().AllGather(static_cast<char*>(buf) + (size_t)c->rank * bytes_per_rank, buf, bytes_per_rank / sizeof(double), ncclFloat64, c->comm,
+                                static_cast<cudaStream_t>(stream)) == ncclSuccess ? 0 : 1;
+}
+static int nccl_allreduce_cb(void* ctx, double* buf, int32_t n, void* stream) {
+    NcclCtx* c = static_cast<NcclCtx*>(ctx);
+    return nccl_api().AllReduce(buf, buf, (size_t)n, ncclFloat64, ncclSum, c->comm, static_cast<cudaStream_t>(stream)) == ncclSuccess ? 0 : 1;
+}
+#endif
 
 struct b200_problem {
     int device = 0;
@@ -145,6 +193,13 @@ struct b200_problem {
     b200_allgather_fn spec_ag = nullptr;
     void* spec_ctx = nullptr;
     double *d_spec_delta = nullptr, *d_spec_rec = nullptr, *h_spec_rec = nullptr;
+#ifndef B200_USE_EMU
+    NcclCtx nccl_all, nccl_grp;    // in-library NCCL (b200_nccl_init): all ranks / the ranks of this lambda group
+    bool own_nccl = false;
+#endif
+    double comm_ms = 0;            // device time of the collectives (phase timing on)
+    long long comm_calls = 0;
+    cudaEvent_t cev[2] = {};
 };
 
 // B200_POISON=1 (debugging): fill every allocation with 0xFF bytes (NaN doubles / -1 ints) so that a read of memory the
@@ -289,6 +344,13 @@ void b200_problem_destroy(b200_problem* p) {
     if (p->h_scal) cudaFreeHost(p->h_scal);
     for (auto& e : p->ev) if (e) cudaEventDestroy(e);
     for (auto& q : p->tev) for (auto& e : q) if (e) cudaEventDestroy(e);
+    for (auto& e : p->cev) if (e) cudaEventDestroy(e);
+#ifndef B200_USE_EMU
+    if (p->own_nccl) {
+        if (p->nccl_grp.comm && p->nccl_grp.comm != p->nccl_all.comm) nccl_api().CommDestroy(p->nccl_grp.comm);
+        if (p->nccl_all.comm) nccl_api().CommDestroy(p->nccl_all.comm);
+    }
+#endif
     free_graphs(p);
     if (p->stream) cudaStreamDestroy(p->stream);
     delete p;
@@ -385,6 +447,7 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
     CK(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     for (auto& e : p->ev) CK(cudaEventCreate(&e));
     for (auto& q : p->tev) for (auto& e : q) CK(cudaEventCreate(&e));
+    for (auto& e : p->cev) CK(cudaEventCreate(&e));
     if (const char* env = std::getenv("B200_NO_GRAPH")) p->use_graph = std::atoi(env) == 0;
     if (const char* env = std::getenv("B200_SPEC_TRIALS")) p->spec_trials = std::max(1, std::atoi(env));
     CK(dalloc(&p->d_tv, (size_t)p->tvd * Kld)); CK(dalloc(&p->d_tv_try, (size_t)p->tvd * Kld));
@@ -518,6 +581,12 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
         if (rows_fit < 16) return fail("time block does not fit in shared memory", B200_NOT_IMPLEMENTED);
         ds.cr = (int)std::min<long long>(64, rows_fit & ~15LL);
         p->smem_sweep = sizeof(double) * (size_t)sweep_smem_doubles(ds.ntp, ds.ld, ds.cr, ds.nc, ds.owp);
+        // keyframe-pipelined level-0 sweep: needs the solver layout without local dofs and its (larger) shared-memory carve-up
+        ds.pipe = (ds.nl == 0 && ds.ntp >= 64 && !std::getenv("B200_NO_PIPE")) ? 1 : 0;
+        if (ds.pipe) {
+            const size_t need = sizeof(double) * (size_t)sweep_pipe_smem_doubles(ds.ntp, ds.ld, ds.nc, ds.owp);
+            if (need <= smem_cap) p->smem_sweep = std::max(p->smem_sweep, need); else ds.pipe = 0;
+        }
         // back-substitution / top level: factor block + vectors; the static system (ns1 x lds) reuses the block area
         const size_t bs = (size_t)backsub_smem_doubles(ds.ntp, ds.ld);
         if ((size_t)static_lds(ds.ns) * (ds.ns1 + 1) > (size_t)ds.ntp * ds.ld + 4 * 256)
@@ -795,8 +864,30 @@ static void launch_linearize(b200_problem* p) {
     p->launches++;
 }
 
+// Collectives.  A "group" is a run of exchanges issued together (one ncclGroupStart / ncclGroupEnd with the in-library NCCL).
+// With phase timing on, every group is bracketed by CUDA events and waited for, so that its device time can be attributed
+// (b200_comm_ms); the production path never synchronises here.
+static b200_status comm_begin(b200_problem* p) {
+    if (p->time_phases) CK(cudaEventRecord(p->cev[0], p->stream));
+#ifndef B200_USE_EMU
+    if (p->own_nccl) nccl_api().GroupStart();
+#endif
+    return B200_OK;
+}
+static b200_status comm_end(b200_problem* p) {
+#ifndef B200_USE_EMU
+    if (p->own_nccl && nccl_api().GroupEnd() != ncclSuccess) { set_err("ncclGroupEnd failed"); return B200_NCCL_ERROR; }
+#endif
+    p->comm_calls++;
+    if (p->time_phases) {
+        CK(cudaEventRecord(p->cev[1], p->stream));
+        CK(cudaEventSynchronize(p->cev[1]));
+        float ms = 0; cudaEventElapsedTime(&ms, p->cev[0], p->cev[1]); p->comm_ms += ms;
+    }
+    return B200_OK;
+}
 static b200_status allgather(b200_problem* p, void* buf, size_t bytes_per_rank) {
-    if (!p->ag_fn) { set_err("world_size > 1 but no collective registered (b200_comm_set)"); return B200_NCCL_ERROR; }
+    if (!p->ag_fn) { set_err("world_size > 1 but no collective registered (b200_comm_set / b200_nccl_init)"); return B200_NCCL_ERROR; }
     if (p->ag_fn(p->comm_ctx, buf, (uint64_t)bytes_per_rank, p->stream)) { set_err("allgather failed"); return B200_NCCL_ERROR; }
     return B200_OK;
 }
@@ -865,8 +956,10 @@ static b200_status launch_solve(b200_problem* p, cudaEvent_t* tev) {
             // the separator that closes this rank's window needs the Schur complement / fill of the NEXT rank's first chunk
             CK(cudaMemcpyAsync(p->d_stageS + (size_t)r * Ssz, l0.S + (size_t)l0.c_lo * Ssz, sizeof(double) * Ssz, cudaMemcpyDeviceToDevice, p->stream));
             CK(cudaMemcpyAsync(p->d_stageF + (size_t)r * 2 * Fsz, l0.F + (size_t)l0.c_lo * 2 * Fsz, sizeof(double) * 2 * Fsz, cudaMemcpyDeviceToDevice, p->stream));
-            b200_status st = allgather(p, p->d_stageS, sizeof(double) * Ssz); if (st != B200_OK) return st;
+            b200_status st = comm_begin(p); if (st != B200_OK) return st;
+            st = allgather(p, p->d_stageS, sizeof(double) * Ssz); if (st != B200_OK) return st;
             st = allgather(p, p->d_stageF, sizeof(double) * 2 * Fsz); if (st != B200_OK) return st;
+            st = comm_end(p); if (st != B200_OK) return st;
             if (r + 1 < W) {
                 CK(cudaMemcpyAsync(l0.S + (size_t)l0.c_hi * Ssz, p->d_stageS + (size_t)(r + 1) * Ssz, sizeof(double) * Ssz, cudaMemcpyDeviceToDevice, p->stream));
                 CK(cudaMemcpyAsync(l0.F + (size_t)l0.c_hi * 2 * Fsz, p->d_stageF + (size_t)(r + 1) * 2 * Fsz, sizeof(double) * 2 * Fsz, cudaMemcpyDeviceToDevice, p->stream));
@@ -886,11 +979,14 @@ static b200_status launch_solve(b200_problem* p, cudaEvent_t* tev) {
         launch_level_factor(p, l1.dev, l1.c_lo, l1.c_hi);
         if (W > 1 && li == 1) {
             const int gpr = l1.P / W;
-            b200_status st = allgather(p, l1.F, sizeof(double) * 2 * Fsz * gpr); if (st != B200_OK) return st;
-            st = allgather(p, l1.S, sizeof(double) * Ssz * gpr); if (st != B200_OK) return st;
+            // (the packed blocks are level-1 SOURCES: ready before the level-1 sweep; packed here so that the three exchanges form one group)
             B200_LAUNCH(pack_groups_kernel, dim3(gpr), dim3(256), 0, p->stream, dm, l1.dev, l0.Dred, l0.Ared, l0.Sred, p->d_pack,
                         (long long)p->pack_doubles, l1.c_lo, 0, 0, 0);
+            b200_status st = comm_begin(p); if (st != B200_OK) return st;
+            st = allgather(p, l1.F, sizeof(double) * 2 * Fsz * gpr); if (st != B200_OK) return st;
+            st = allgather(p, l1.S, sizeof(double) * Ssz * gpr); if (st != B200_OK) return st;
             st = allgather(p, p->d_pack, sizeof(double) * p->pack_doubles * gpr); if (st != B200_OK) return st;
+            st = comm_end(p); if (st != B200_OK) return st;
             B200_LAUNCH(pack_groups_kernel, dim3(l1.P), dim3(256), 0, p->stream, dm, l1.dev, l0.Dred, l0.Ared, l0.Sred, p->d_pack,
                         (long long)p->pack_doubles, 0, 1, l1.c_lo, l1.c_hi);
             p->launches += 2;
@@ -911,7 +1007,9 @@ static b200_status launch_solve(b200_problem* p, cudaEvent_t* tev) {
     }
     if (tev) CK(cudaEventRecord(tev[TE_BACK1], p->stream));
     if (W > 1) {  // every rank needs every keyframe's step: the values are replicated
-        b200_status st = allgather(p, p->d_delta, sizeof(double) * (size_t)p->Wk * p->dm.ntp); if (st != B200_OK) return st;
+        b200_status st = comm_begin(p); if (st != B200_OK) return st;
+        st = allgather(p, p->d_delta, sizeof(double) * (size_t)p->Wk * p->dm.ntp); if (st != B200_OK) return st;
+        st = comm_end(p); if (st != B200_OK) return st;
     }
     return B200_OK;
 }
@@ -928,8 +1026,9 @@ static int host_status(const b200_problem* p) { return *reinterpret_cast<const i
 static b200_status allreduce_scal(b200_problem* p) {
     if (p->world <= 1) return B200_OK;
     if (!p->ar_fn) { set_err("world_size > 1 but no collective registered"); return B200_NCCL_ERROR; }
+    b200_status st = comm_begin(p); if (st != B200_OK) return st;
     if (p->ar_fn(p->comm_ctx, p->sb.scal, SC_COUNT, p->stream)) { set_err("allreduce failed"); return B200_NCCL_ERROR; }
-    return B200_OK;
+    return comm_end(p);
 }
 
 // upload the LM state mirror (pinned) to the device; the caller has synchronised the stream since the mirror was last in flight
@@ -1003,9 +1102,9 @@ __host__ __device__ inline TrialVerdict judge_trial(const b200_lm_params& L, dou
 // scalars of the trial and the pivot status, applies gtsam's tryLambda rules (judge_trial + increaseLambda / decreaseLambda) to
 // the LM state in device memory and, when the ladder has ended, raises `done` so that the trials already queued behind this
 // one return at once.  The host reads the state once per iterate().
-__global__ void lm_judge_kernel(LmDev* st, const double* __restrict__ scal, const int* __restrict__ solve_status, b200_lm_params L) {
+__global__ void lm_judge_kernel(LmDev* st, const double* __restrict__ scal, b200_lm_params L) {
     if (threadIdx.x != 0 || blockIdx.x != 0 || st->done) return;
-    const bool solved = *solve_status == 0;
+    const bool solved = scal[SC_FAIL] == 0.0;   // number of ranks whose factorisation met a non-positive pivot (all-reduced)
     const TrialVerdict v = judge_trial(L, st->err, solved, scal[SC_LIN_ERR], scal[SC_MODEL_ERR], scal[SC_NEW_ERR]);
     st->inner++;
     st->status = solved ? B200_OK : B200_INDETERMINATE_SYSTEM;
@@ -1046,8 +1145,11 @@ static b200_status launch_trial(b200_problem* p, cudaEvent_t* tev, bool device_j
     launch_error(p, p->d_tv_try, p->d_sv_try, p->d_e2, SC_NEW_ERR, p->sb.skip);
     // rank-local linear.error(0) lives outside the all-reduced block (scal[SC_COUNT]); it is copied in at every trial
     CK(cudaMemcpyAsync(p->sb.scal + SC_LIN_ERR, p->sb.scal + SC_COUNT, sizeof(double), cudaMemcpyDeviceToDevice, p->stream));
+    B200_LAUNCH(status_to_scal_kernel, dim3(1), dim3(32), 0, p->stream, p->sb.status, p->sb.scal);
+    p->launches++;
+    st = allreduce_scal(p); if (st != B200_OK) return st;   // (sharded: the same scalars, bit for bit, on every rank of the group)
     if (device_judge) {
-        B200_LAUNCH(lm_judge_kernel, dim3(1), dim3(32), 0, p->stream, p->d_lm, p->sb.scal, p->sb.status, p->lm);
+        B200_LAUNCH(lm_judge_kernel, dim3(1), dim3(32), 0, p->stream, p->d_lm, p->sb.scal, p->lm);
         p->launches++;
     }
     if (tev) CK(cudaEventRecord(tev[TE_TRIAL1], p->stream));
@@ -1118,14 +1220,15 @@ b200_status b200_lm_iterate(b200_problem* p, b200_lm_state* state) {
     const int G = (p->spec_ag && !L.gauss_newton) ? p->spec_G : 1;
     const int T = p->world;
     int status = B200_OK, inner = 0;
-    if (T == 1 && G == 1) {
-        // ------------------------------------------------------------ device-resident ladder
+    if (G == 1) {
+        // ------------------------------------------------------------ device-resident ladder (single rank, or one time-sharded
+        // group: after the all-reduce every rank holds the same scalars, so every rank's judge kernel takes the same decision)
         p->sb.skip = &p->d_lm->done;
         B200_LAUNCH(lm_begin_iter_kernel, dim3(1), dim3(32), 0, p->stream, p->d_lm);
         p->launches++;
         const int nq = L.gauss_newton ? 1 : std::max(1, std::min(p->spec_trials, 4));
 #ifndef B200_USE_EMU
-        const bool graph = p->use_graph && !p->time_phases;
+        const bool graph = p->use_graph && !p->time_phases && T == 1;
 #else
         const bool graph = false;
 #endif
@@ -1174,9 +1277,6 @@ b200_status b200_lm_iterate(b200_problem* p, b200_lm_state* state) {
             b200_status st = push_lambda_try(p, lam_try); if (st != B200_OK) return st;
             st = launch_trial(p, p->time_phases ? p->tev[0] : nullptr, false);
             if (st != B200_OK) return st;
-            B200_LAUNCH(status_to_scal_kernel, dim3(1), dim3(32), 0, p->stream, p->sb.status, p->sb.scal);
-            p->launches++;
-            st = allreduce_scal(p); if (st != B200_OK) return st;
             if (G > 1) {
                 // record of this rank: [scalars | static step]; gathered over ALL ranks of all groups
                 double* rec = p->d_spec_rec + (size_t)(p->spec_g * T + p->rank) * p->spec_rec;
@@ -1425,6 +1525,57 @@ b200_status b200_spec_set(b200_problem* p, int32_t n_groups, int32_t group, b200
     return B200_OK;
 }
 
+// In-library NCCL (alternative to the b200_comm_set / b200_spec_set callbacks): rank 0 calls b200_nccl_unique_id and hands the
+// 128 bytes to every rank by any transport; every rank then calls b200_nccl_init with the TOTAL rank count, its global rank and
+// the number of lambda groups G (ranks are group-major: global rank = group * (n_ranks / G) + rank in group).
+b200_status b200_nccl_unique_id(char out[128]) {
+#ifndef B200_USE_EMU
+    if (!out) return B200_BAD_ARG;
+    NcclApi& N = nccl_api();
+    if (!N.ok) { set_err("libnccl.so.2 not found"); return B200_NCCL_ERROR; }
+    ncclUniqueId id;
+    if (N.GetUniqueId(&id) != ncclSuccess) { set_err("ncclGetUniqueId failed"); return B200_NCCL_ERROR; }
+    std::memcpy(out, id.internal, 128);
+    return B200_OK;
+#else
+    (void)out; set_err("the emulator build has no NCCL"); return B200_NOT_IMPLEMENTED;
+#endif
+}
+b200_status b200_nccl_init(b200_problem* p, int32_t n_ranks, int32_t global_rank, const char id_bytes[128], int32_t n_groups) {
+#ifndef B200_USE_EMU
+    if (!p || !id_bytes || n_ranks < 1 || global_rank < 0 || global_rank >= n_ranks || n_groups < 1 || n_ranks % n_groups) return B200_BAD_ARG;
+    NcclApi& N = nccl_api();
+    if (!N.ok) { set_err("libnccl.so.2 not found"); return B200_NCCL_ERROR; }
+    CK(cudaSetDevice(p->device));
+    ncclUniqueId id;
+    std::memcpy(id.internal, id_bytes, 128);
+    ncclResult_t r = N.CommInitRank(&p->nccl_all.comm, n_ranks, id, global_rank);
+    if (r != ncclSuccess) { set_err(std::string("ncclCommInitRank: ") + (N.GetErrorString ? N.GetErrorString(r) : "error")); return B200_NCCL_ERROR; }
+    p->nccl_all.nranks = n_ranks; p->nccl_all.rank = global_rank;
+    const int T = n_ranks / n_groups, group = global_rank / T, rank = global_rank % T;
+    if (n_groups > 1) {
+        r = N.CommSplit(p->nccl_all.comm, group, rank, &p->nccl_grp.comm, nullptr);
+        if (r != ncclSuccess) { set_err(std::string("ncclCommSplit: ") + (N.GetErrorString ? N.GetErrorString(r) : "error")); return B200_NCCL_ERROR; }
+    } else p->nccl_grp.comm = p->nccl_all.comm;
+    p->nccl_grp.nranks = T; p->nccl_grp.rank = rank;
+    p->own_nccl = true;
+    b200_status st = b200_comm_set(p, T, rank, nccl_allgather_cb, nccl_allreduce_cb, &p->nccl_grp);
+    if (st != B200_OK) return st;
+    return b200_spec_set(p, n_groups, group, n_groups > 1 ? nccl_allgather_cb : nullptr, &p->nccl_all);
+#else
+    (void)p; (void)n_ranks; (void)global_rank; (void)id_bytes; (void)n_groups; set_err("the emulator build has no NCCL"); return B200_NOT_IMPLEMENTED;
+#endif
+}
+// device time spent in the collectives since the last reset (measured only while phase timing is on) and the number of
+// collective groups issued
+b200_status b200_comm_ms(b200_problem* p, double* ms, int64_t* calls, int32_t reset) {
+    if (!p) return B200_BAD_ARG;
+    if (ms) *ms = p->comm_ms;
+    if (calls) *calls = p->comm_calls;
+    if (reset) { p->comm_ms = 0; p->comm_calls = 0; }
+    return B200_OK;
+}
+
 // ------------------------------------------------------------------------------------------ parity / debug accessors
 b200_status b200_debug_linearize(b200_problem* p) {
     if (!p) return B200_BAD_ARG;
@@ -1555,6 +1706,11 @@ b200_status b200_debug_read(b200_problem* p, const char* name, int64_t offset, i
     if (!p || !name || !out) return B200_BAD_ARG;
     CK(cudaSetDevice(p->device));
     const std::string s(name);
+    if (s == "config") {   // out[0..3] = {local pre-elimination on, pipelined level-0 sweep on, solver time-block size, shared bytes of the sweep}
+        const double v[4] = {p->use_le ? 1.0 : 0.0, p->ds.pipe ? 1.0 : 0.0, (double)p->ds.ntp, (double)p->smem_sweep};
+        for (int64_t i = 0; i < n && i < 4; i++) out[i] = v[i];
+        return B200_OK;
+    }
     const double* src = nullptr;
     if (s == "Wst") src = p->sb.Wst; else if (s == "Yst") src = p->sb.Yst; else if (s == "delta_c") src = p->sb.delta;
     else if (s == "delta") src = p->d_delta; else if (s == "Dc") src = p->d_Dc; else if (s == "Ac") src = p->d_Ac; else if (s == "O") src = p->d_O;

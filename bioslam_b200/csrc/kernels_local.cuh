@@ -6,7 +6,7 @@
 //   [ D_cl              D_cc   A_c^T ] [d_c] = [-g_c]   ->   Dc = D_cc + lambda I - V_c V_c^T,  Ac = [A_c ; -g_c^T] - V_a V_c^T,
 //   [ A_l               A_c    S     ] [d_s]   [-g_s]        Sc = S_k - V_a V_a^T            (V_c: first nc rows, V_a: last ns1)
 //
-// and recovered after the chain back-substitution:  d_l = -L^-T ( V_c^T d_c + V_a^T [d_s, -1] ).
+// and recovered after the chain back-substitution:  d_l = -L^-T ( V_c^T d_c + V_a^T [d_s, -1] )   (L stored, back substitution).
 // The rank-nl updates run on the fp64 tensor pipe (same 16 x 32 DMMA warp tile as the sweep); the kernel is bound by HBM
 // (reads the lower triangle of D_k, A_k, S_k once, writes the reduced blocks once).
 #pragma once
@@ -15,95 +15,105 @@
 namespace b200d {
 
 #define B200_LE_THREADS 256
-#define B200_LE_MAXNL 32
+#define B200_LE_MAXNL 24
 
 struct LocalElim {
     int nl, nc, ncp, ns1, ntp;      // local dofs, chain dofs (incl. the padding dof of an odd nt), chain dim of the solver (even), statics + rhs
     int ldl;                        // shared-memory stride of the nl-wide panels (== 4 mod 8: conflict-free DMMA operand loads)
     const double *D, *A, *S;        // assembled blocks: [K][ntp*ntp] (lower), [K][ns1*ntp], [K][ns1*ns1]
     double *Dc, *Ac, *Sc;           // reduced blocks: [K][ncp*ncp] (lower), [K][ns1*ncp], [K][ns1*ns1]
-    double *V, *Wl;                 // [K][(nc+ns1)*nl] forward-substituted local panel, [K][nl*nl] L^-1 (lower)
+    double *V, *Wl;                 // [K][(nc+ns1)*nl] forward-substituted local panel, [K][nl*nl] Cholesky factor L of the local block (lower)
 };
 __host__ __device__ inline int le_ldl(int nl) { int l = nl; while ((l & 7) != 4) l++; return l; }
 __host__ __device__ inline long long le_smem_doubles(int nl, int nc, int ns1) { return (long long)(2 * nl + nc + ns1) * le_ldl(nl); }
 
 // grid = keyframes [k_first, k_first + gridDim.x)
-__global__ void __launch_bounds__(B200_LE_THREADS) local_elim_kernel(LocalElim le, int k_first, const double* __restrict__ lambda_p, int* status,
-                                                                     const int* __restrict__ skip) {
+__global__ void __launch_bounds__(B200_LE_THREADS, 3) local_elim_kernel(LocalElim le, int k_first, const double* __restrict__ lambda_p, int* status,
+                                                                        const int* __restrict__ skip) {
     B200_DYN_SMEM(double, sm);
     if (skip && *skip) return;
     const int nl = le.nl, nc = le.nc, ncp = le.ncp, ns1 = le.ns1, ntp = le.ntp, ldl = le.ldl, hp = nc + ns1;
     const long long k = k_first + (long long)blockIdx.x;
     const double lambda = *lambda_p;
     double* Ls = sm;                                   // nl x ldl: L (lower)
-    double* Ws = Ls + (long long)nl * ldl;             // nl x ldl: L^-1 (lower)
-    double* Vs = Ws + (long long)nl * ldl;             // (nc + ns1) x ldl: panel -> V
+    double* invd = Ls + (long long)nl * ldl;           // [nl] 1 / L[j][j]   (the rest of this nl x ldl area is unused)
+    double* Vs = invd + (long long)nl * ldl;           // (nc + ns1) x ldl: panel -> V
     const double* Dk = le.D + k * ntp * ntp;
     const double* Ak = le.A + k * ns1 * ntp;
     const double* Sk = le.S + k * ns1 * ns1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     __shared__ int s_fail;
     if (threadIdx.x == 0) s_fail = 0;
-    for (int e = threadIdx.x; e < nl * nl; e += blockDim.x) {
-        const int r = e / nl, c = e - r * nl;
-        Ls[r * ldl + c] = (c <= r) ? Dk[(long long)r * ntp + c] + (r == c ? lambda : 0.0) : 0.0;
-        Ws[r * ldl + c] = 0.0;
-    }
-    for (int e = threadIdx.x; e < hp * nl; e += blockDim.x) {
-        const int r = e / nl, c = e - r * nl;
-        Vs[r * ldl + c] = (r < nc) ? Dk[(long long)(nl + r) * ntp + c] : Ak[(long long)(r - nc) * ntp + c];
-    }
-    __syncthreads();
-    if (warp == 0) {
-        // Cholesky of the nl x nl block (right-looking, one column per step), then its inverse column by column
-        int fail = 0;
-        for (int j = 0; j < nl; j++) {
-            const double d = Ls[j * ldl + j];
-            __syncwarp();   // every lane has read the pivot before lane 0 overwrites it with its square root
-            if (!(d > 0.0) || !(d < 1.0e300)) { fail = 1; break; }
-            const double s = rsqrt(d);
-            for (int i = j + lane; i < nl; i += 32) Ls[i * ldl + j] *= s;   // diagonal: d * rsqrt(d) = sqrt(d)
-            __syncwarp();
-            for (int i = j + 1 + lane; i < nl; i += 32) {
-                const double f = Ls[i * ldl + j];
-                for (int c = j + 1; c <= i; c++) Ls[i * ldl + c] = fma(-f, Ls[c * ldl + j], Ls[i * ldl + c]);
-            }
-            __syncwarp();
+    // pull everything this keyframe reads towards L2 now (lower triangle of D_k, A_k, S_k: ~150 KB): the epilogue below reads
+    // D_cc / A_c / S_k entry by entry and would otherwise wait for DRAM tile after tile
+    for (int r = threadIdx.x; r < ntp; r += blockDim.x)
+        for (int c = 0; c <= r; c += 16) prefetch_l2(Dk + (long long)r * ntp + c);
+    for (int e = threadIdx.x * 16; e < ns1 * ntp; e += blockDim.x * 16) prefetch_l2(Ak + e);
+    for (int e = threadIdx.x * 16; e < ns1 * ns1; e += blockDim.x * 16) prefetch_l2(Sk + e);
+    // panel rows [D_cl ; A_l ; -g_l^T] (every warp but the first), while warp 0 factorises the local block
+    if (warp > 0) {
+        for (int e = threadIdx.x - 32; e < hp * nl; e += blockDim.x - 32) {
+            const int r = e / nl, c = e - r * nl;
+            Vs[r * ldl + c] = (r < nc) ? Dk[(long long)(nl + r) * ntp + c] : Ak[(long long)(r - nc) * ntp + c];
         }
-        if (fail) { if (lane == 0) s_fail = 1; }
-        else {
-            for (int c = lane; c < nl; c += 32) {   // column c of L^-1 (private to the lane)
-                for (int r = c; r < nl; r++) {
-                    double v = (r == c) ? 1.0 : 0.0;
-                    for (int q = c; q < r; q++) v = fma(-Ls[r * ldl + q], Ws[q * ldl + c], v);
-                    Ws[r * ldl + c] = v / Ls[r * ldl + r];
+    } else {
+        // Cholesky of the nl x nl block (nl <= 32) by ONE warp in registers: lane l owns row l (identity beyond nl), the pivot and
+        // the column entries travel by shuffle (right-looking: 1 rsqrt + 31 - c shuffle/FMA pairs per pivot)
+        double r[B200_LE_MAXNL];
+#pragma unroll
+        for (int c = 0; c < B200_LE_MAXNL; c++)
+            r[c] = (lane < nl && c <= lane) ? Dk[(long long)lane * ntp + c] + (c == lane ? lambda : 0.0) : ((c == lane) ? 1.0 : 0.0);
+        int fail = 0;
+#pragma unroll
+        for (int c = 0; c < B200_LE_MAXNL; c++) {
+            if (c < nl) {
+                double d = __shfl_sync(0xffffffffu, r[c], c);
+                if (!(d > 0.0) || !(d < 1.0e300)) { fail = 1; d = 1.0; }
+                const double x = r[c] * rsqrt(d);
+                r[c] = x;
+#pragma unroll
+                for (int c2 = c + 1; c2 < B200_LE_MAXNL; c2++) {
+                    const double lc2 = __shfl_sync(0xffffffffu, x, c2);
+                    r[c2] = fma(-x, lc2, r[c2]);
                 }
             }
         }
+        if (lane < nl) {
+#pragma unroll
+            for (int c = 0; c < B200_LE_MAXNL; c++) {
+                if (c <= lane) Ls[lane * ldl + c] = r[c];
+                if (c == lane) invd[lane] = 1.0 / r[c];
+            }
+        }
+        if (fail && lane == 0) s_fail = 1;
     }
     __syncthreads();
     if (s_fail) { if (threadIdx.x == 0) atomicCAS(status, 0, (int)(k + 1)); return; }
-    // V = P L^-T :  V[r][j] = sum_{c <= j} P[r][c] W[j][c]   (one thread per row, row in registers)
+    // V = P L^-T by forward substitution, one thread per row, the row in registers
     for (int r = threadIdx.x; r < hp; r += blockDim.x) {
         double x[B200_LE_MAXNL];
 #pragma unroll
         for (int c = 0; c < B200_LE_MAXNL; c++) x[c] = (c < nl) ? Vs[r * ldl + c] : 0.0;
-        for (int j = nl - 1; j >= 0; j--) {   // descending: entry j only needs entries <= j of the ORIGINAL row
-            double v = 0.0;
 #pragma unroll
-            for (int c = 0; c < B200_LE_MAXNL; c++) if (c <= j) v = fma(x[c], Ws[j * ldl + c], v);
-            Vs[r * ldl + j] = v;
+        for (int j = 0; j < B200_LE_MAXNL; j++) {
+            if (j < nl) {
+                double v = x[j];
+#pragma unroll
+                for (int c = 0; c < j; c++) v = fma(-x[c], Ls[j * ldl + c], v);
+                x[j] = v * invd[j];
+                Vs[r * ldl + j] = x[j];
+            }
         }
         for (int c = nl; c < ldl; c++) Vs[r * ldl + c] = 0.0;
     }
     __syncthreads();
-    {   // factors of the local block for the back-substitution
+    {   // factors of the local block for the back-substitution: V and L (lower, row-major nl x nl)
         double* Vg = le.V + k * (long long)hp * nl;
         for (int e = threadIdx.x; e < hp * nl; e += blockDim.x) { const int r = e / nl, c = e - r * nl; Vg[e] = Vs[r * ldl + c]; }
         double* Wg = le.Wl + k * (long long)nl * nl;
-        for (int e = threadIdx.x; e < nl * nl; e += blockDim.x) { const int r = e / nl, c = e - r * nl; Wg[e] = Ws[r * ldl + c]; }
+        for (int e = threadIdx.x; e < nl * nl; e += blockDim.x) { const int r = e / nl, c = e - r * nl; Wg[e] = (c <= r) ? Ls[r * ldl + c] : 0.0; }
     }
-    // rank-nl updates, 16 x 32 warp tiles: [0, nD) Dc (lower), [nD, nD + nA) Ac, then Sc (lower, mirrored)
+    // rank-nl updates, 16 x 32 warp tiles: [0, nD) Dc (lower), [nD, nD + nA) Ac, then Sc (lower)
     const int rtc = (nc + 15) >> 4, ctc = (nc + 31) >> 5, rts = (ns1 + 15) >> 4;
     int nD = 0;
     for (int rt = 0; rt < rtc; rt++) nD += ((16 * rt + 15) >> 5) + 1;
@@ -139,9 +149,7 @@ __global__ void __launch_bounds__(B200_LE_THREADS) local_elim_kernel(LocalElim l
                     } else if (kind == 1) {
                         if (r < ns1 && c < nc) Ack[(long long)r * ncp + c] = Ak[(long long)r * ntp + nl + c] - acc[i][j][e];
                     } else if (r < ns1 && c <= r) {
-                        const double v = Sk[(long long)r * ns1 + c] - acc[i][j][e];
-                        Sck[(long long)r * ns1 + c] = v;
-                        Sck[(long long)c * ns1 + r] = v;
+                        Sck[(long long)r * ns1 + c] = Sk[(long long)r * ns1 + c] - acc[i][j][e];   // (consumers read the lower triangle)
                     }
                 }
             }
@@ -161,7 +169,7 @@ __global__ void __launch_bounds__(128) local_backsub_kernel(LocalElim le, int k_
     const int nl = le.nl, nc = le.nc, ncp = le.ncp, ns1 = le.ns1, ntp = le.ntp, hp = nc + ns1;
     const long long k = k_first + (long long)blockIdx.x;
     if (k >= k_end) return;
-    __shared__ double x[512 + 256], part[4][B200_LE_MAXNL], t[B200_LE_MAXNL];
+    __shared__ double x[512 + 256], part[4][32], t[32];
     for (int j = threadIdx.x; j < nc; j += blockDim.x) x[j] = delta_c[k * ncp + j];
     for (int a = threadIdx.x; a < ns1; a += blockDim.x) x[nc + a] = (a < ns1 - 1) ? dstat[a] : -1.0;
     __syncthreads();
@@ -174,12 +182,17 @@ __global__ void __launch_bounds__(128) local_backsub_kernel(LocalElim le, int k_
     if (threadIdx.x < (unsigned)nl) t[threadIdx.x] = (part[0][threadIdx.x] + part[1][threadIdx.x]) + (part[2][threadIdx.x] + part[3][threadIdx.x]);
     __syncthreads();
     double* dk = delta + k * ntp;
-    if (threadIdx.x < (unsigned)nl) {
-        const double* Wg = le.Wl + k * (long long)nl * nl;
-        const int i = threadIdx.x;
-        double v = 0.0;
-        for (int j = i; j < nl; j++) v = fma(Wg[(long long)j * nl + i], t[j], v);
-        dk[i] = -v;
+    if (threadIdx.x < 32) {
+        // d_l = -L^-T t: backward substitution with the transpose, lane i holds entry i; row i of L is read coalesced
+        const double* Lg = le.Wl + k * (long long)nl * nl;
+        const int l = threadIdx.x;
+        double v = (l < nl) ? t[l] : 0.0;
+        for (int i = nl - 1; i >= 0; i--) {
+            const double yi = __shfl_sync(0xffffffffu, v, i) / Lg[(long long)i * nl + i];
+            if (l == i) v = yi;
+            else if (l < i) v = fma(-Lg[(long long)i * nl + l], yi, v);
+        }
+        if (l < nl) dk[l] = -v;
     }
     for (int j = threadIdx.x; j < nc; j += blockDim.x) dk[nl + j] = x[j];
 }

@@ -43,11 +43,12 @@ namespace b200d {
 // optional per-phase cycle counters of the sweep (debug builds: -DB200_PHASE_CLOCKS), accumulated by thread 0 of the last block
 #ifdef B200_PHASE_CLOCKS
 __device__ unsigned long long g_phase_clk[16];
+__device__ int g_phase_on;   // set by the level-0 (block-sparse) sweep, cleared by the dense ones: only level 0 is profiled
 #define PH_T0() unsigned long long ph_t_ = clock64()
-#define PH_ADD(i) do { if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1) { unsigned long long n_ = clock64(); g_phase_clk[i] += n_ - ph_t_; ph_t_ = n_; } } while (0)
+#define PH_ADD(i) do { if (threadIdx.x == 0 && blockIdx.x == 1 && g_phase_on) { unsigned long long n_ = clock64(); g_phase_clk[i] += n_ - ph_t_; ph_t_ = n_; } } while (0)
 // the same from an arbitrary thread t of the last block (worker-warp timelines of the warp-specialised Cholesky)
 #define PHW_T0() unsigned long long phw_t_ = clock64()
-#define PHW_ADD(i, t) do { if (threadIdx.x == (t) && blockIdx.x == gridDim.x - 1) { unsigned long long n_ = clock64(); g_phase_clk[i] += n_ - phw_t_; phw_t_ = n_; } } while (0)
+#define PHW_ADD(i, t) do { if (threadIdx.x == (t) && blockIdx.x == 1 && g_phase_on) { unsigned long long n_ = clock64(); g_phase_clk[i] += n_ - phw_t_; phw_t_ = n_; } } while (0)
 #else
 #define PH_T0()
 #define PH_ADD(i)
@@ -401,20 +402,24 @@ __device__ __forceinline__ void solve_scratch(double*& Tdiag, double*& Wd, doubl
 // 16 x 16 panel block (s+1, s), applies it to the diagonal tile and factorises/inverts it -- while the other warps scale the
 // rest of column block s and apply the rank-16 trailing update.  The two roles meet at named barriers (ids 1..6, two
 // alternating instances each): W_READY (W_ss in Wd[s&1]), ROW_READY (block row s+1 scaled), T_DONE (trailing update s done).
-__device__ int cta_chol_inv(double* Ms, int ld, int n) {
+// Runs on a GROUP of gnw consecutive warps (warp index in the group gw; default: the whole CTA); gsync = named barrier id the group
+// may use for its own full-group synchronisation (0: __syncthreads, i.e. the group is the CTA).
+__device__ int cta_chol_inv(double* Ms, int ld, int n, int gw = -1, int gnw = 0, int gsync = 0) {
     __shared__ int fail;
     __shared__ __align__(16) double s_Wd2[2][B200_NB * B200_WLD];
     double *Tdiag, *Wd0, *invd;
     solve_scratch(Tdiag, Wd0, invd);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int warp = gw >= 0 ? gw : (int)(threadIdx.x >> 5), nwarps = gw >= 0 ? gnw : (int)(blockDim.x >> 5);
     const int mg = lane >> 2, mt = lane & 3;   // MMA fragment coordinates
     const int nb = (n + B200_NB - 1) / B200_NB;
+#define CHOL_GSYNC() do { if (gsync == 0) __syncthreads(); else named_bar_sync(gsync, nwarps << 5); } while (0)
     // the pivot warp's chain is latency-bound: the warps that share its scheduler (warp & 3 == 0) stay out of the way
     const bool quiet = false;   // (measured: idling the 3 warps on the pivot scheduler does not pay -- the chain waits on the shared MIO pipe)
     const int nwk = quiet ? nwarps - (nwarps + 3) / 4 : nwarps - 1;        // worker warps
     const int nthr = 32 * (nwk + 1);                                       // threads taking part in the named barriers
-    if (threadIdx.x == 0) fail = 0;
-    __syncthreads();
+    if (warp == 0 && lane == 0) fail = 0;
+    CHOL_GSYNC();
     PH_T0();
     if (warp == 0) {
         // ------------------------------------------------------------------ pivot warp
@@ -592,9 +597,10 @@ __device__ int cta_chol_inv(double* Ms, int ld, int n) {
             PHW_ADD(15, 32);
         }
     }
-    __syncthreads();
+    CHOL_GSYNC();
     PH_ADD(10);
     return fail;
+#undef CHOL_GSYNC
 }
 
 // ------------------------------------------------------------------------------------------------- legacy in-smem Cholesky
@@ -750,6 +756,9 @@ __device__ void cta_sweep(const Dims& dm, const SweepArgs& a, double* sm) {
     double* Yb = sm + (long long)n * ld;
     double* Op = Yb + (long long)CR * ld;
     const int kz0 = nl & ~1;                        // first column of z that is needed (chain columns, pair aligned)
+#ifdef B200_PHASE_CLOCKS
+    if (threadIdx.x == 0) g_phase_on = DENSE ? 0 : 1;
+#endif
     // structure tables of O in shared memory (they are consulted at the start of every GEMM phase: keep them off the L2 path)
     __shared__ int s_orow[2 * 256], s_ozs[256], s_fblk[64], s_nfblk;
     for (int e = threadIdx.x; e < 2 * nc; e += blockDim.x) s_orow[e] = dm.orow[e];
@@ -1232,6 +1241,8 @@ __device__ __forceinline__ void level_chunk_args(const Dims& dm, const Level& lv
     a.dense_o = lv.dense_o;
 }
 
+__device__ void cta_sweep_pipe(const Dims& dm, const SweepArgs& a, double* sm);   // kernels_sweep_pipe.cuh
+
 // grid = number of chunks of this level owned by this rank (chunk = c_first + blockIdx.x)
 template <bool DENSE>
 __global__ void __launch_bounds__(B200_SOLVE_THREADS) chain_sweep_kernel(Dims dm, Level lv, SolveBuffers sb, int c_first) {
@@ -1240,7 +1251,8 @@ __global__ void __launch_bounds__(B200_SOLVE_THREADS) chain_sweep_kernel(Dims dm
     SweepArgs a;
     level_chunk_args(dm, lv, sb, c_first + blockIdx.x, a, blockIdx.y);
     a.lambda = sb.lam_in_sweep ? *sb.lam : 0.0;
-    cta_sweep<DENSE>(dm, a, sm);
+    if (!DENSE && dm.pipe && gridDim.y == 1 && a.n > 0) cta_sweep_pipe(dm, a, sm);   // keyframe-pipelined variant (kernels_sweep_pipe.cuh)
+    else cta_sweep<DENSE>(dm, a, sm);
 }
 
 // Arrow Schur complement of one chunk sweep:  Sacc = sum_nodes ( S_node - Y_node Y_node^T ), lower triangle of h x h.

@@ -44,6 +44,8 @@ def load(path=None):
     L.b200_debug_get_scalars.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.b200_debug_local_elim.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_void_p]
     L.b200_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int32]
+    L.b200_nccl_init.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_char_p, C.c_int32]
+    L.b200_comm_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]
     L.b200_host_sync_count.argtypes = [C.c_void_p]
     L.b200_host_sync_count.restype = C.c_int64
     L.b200_lower_body_joint_angles.argtypes = [C.c_void_p, C.POINTER(abi.JointAngleDesc), C.c_void_p]
@@ -214,10 +216,28 @@ class Problem:
         self._ag = ALLGATHER_FN(allgather); self._ar = ALLREDUCE_FN(allreduce)
         self._ck(self.L.b200_comm_set(self.h, C.c_int32(world), C.c_int32(rank), self._ag, self._ar, None))
 
+    def nccl_init(self, n_ranks, global_rank, unique_id, n_groups=1):
+        """collectives inside the library (NCCL resolved with dlopen): unique_id = the 128 bytes rank 0 got from nccl_unique_id()"""
+        self._ck(self.L.b200_nccl_init(self.h, C.c_int32(n_ranks), C.c_int32(global_rank), C.c_char_p(bytes(unique_id)), C.c_int32(n_groups)))
+
+    def comm_ms(self, reset=False):
+        ms = C.c_double(); calls = C.c_int64()
+        self._ck(self.L.b200_comm_ms(self.h, C.byref(ms), C.byref(calls), C.c_int32(1 if reset else 0)))
+        return ms.value, int(calls.value)
+
     def spec_set(self, n_groups, group, allgather):
         """lambda speculation: this process is in group `group` of `n_groups` (call after comm_set)"""
         self._spec_ag = ALLGATHER_FN(allgather)
         self._ck(self.L.b200_spec_set(self.h, C.c_int32(n_groups), C.c_int32(group), self._spec_ag, None))
+
+
+def nccl_unique_id(so_path=None):
+    L = load(so_path)
+    buf = C.create_string_buffer(128)
+    st = L.b200_nccl_unique_id(buf)
+    if st != abi.OK:
+        raise B200Error(st, L.b200_last_error().decode())
+    return buf.raw
 
 
 def factor_eval(ftype, params, consts, xcat, whiten=False, device=0, so_path=None):

@@ -20,6 +20,27 @@ def _view(ptr, nbytes, cuda_device):
     return torch.as_tensor(_Raw(), device=torch.device("cuda", cuda_device))
 
 
+class Comm:
+    """what attach() returns: how the collectives run and how long they took (device ms, measured while phase timing is on)"""
+
+    def __init__(self, problem, mode, world, groups):
+        self.problem, self.mode, self.world, self.groups = problem, mode, world, groups
+
+    def take_ms(self):
+        ms, calls = self.problem.comm_ms(reset=True)
+        return {"mode": self.mode, "device_ms": ms, "groups_issued": calls}
+
+
+def attach_nccl(problem, dist, lambda_groups=1):
+    """production path: NCCL inside the library (b200_nccl_init).  torch.distributed only carries the 128-byte unique id."""
+    from . import lib
+    world_all, rank_all = dist.get_world_size(), dist.get_rank()
+    box = [lib.nccl_unique_id() if rank_all == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    problem.nccl_init(world_all, rank_all, box[0], lambda_groups)
+    return Comm(problem, "in-library NCCL (ncclGroup per exchange step)", world_all, lambda_groups)
+
+
 def attach(problem, dist, cuda_device, lambda_groups=1):
     """register the collectives for `problem` (bioslam_b200.lib.Problem); cuda_device=None for the CPU (gloo) tests.
 
@@ -74,4 +95,4 @@ def attach(problem, dist, cuda_device, lambda_groups=1):
     problem.comm_set(world, rank, make_allgather(world, rank, pg), allreduce)
     if G > 1:
         problem.spec_set(G, group_idx, make_allgather(world_all, rank_all, None))
-    return problem
+    return Comm(problem, "torch.distributed callbacks", world_all, G)

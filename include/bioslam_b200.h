@@ -301,6 +301,18 @@ typedef int (*b200_allreduce_fn)(void* ctx, double* dev_buf, int32_t n, void* cu
 b200_status b200_comm_set(b200_problem* p, int32_t world_size, int32_t rank, b200_allgather_fn allgather,
                           b200_allreduce_fn allreduce, void* ctx);
 
+/* NCCL inside the library (the production multi-GPU path; the callbacks above stay for hosts that own their communicators and for
+ * the gloo tests).  Rank 0 calls b200_nccl_unique_id and distributes the 128 bytes; every rank calls b200_nccl_init with the
+ * total rank count, its global rank and the number of lambda groups (see b200_spec_set; ranks are group-major).  libnccl.so.2 is
+ * resolved at run time (dlopen), so the library itself has no link-time dependency on NCCL.  The exchanges of one solve are
+ * issued as ncclGroupStart/End groups on the problem's stream: {window-boundary Schur complement + fill}, {level-1 outputs +
+ * group-separator blocks}, {step}, plus one all-reduce of the cost scalars per lambda trial. */
+b200_status b200_nccl_unique_id(char out[128]);
+b200_status b200_nccl_init(b200_problem* p, int32_t n_ranks, int32_t global_rank, const char id_bytes[128], int32_t n_groups);
+/* device time (ms) of the collectives and number of collective groups since the last reset; the time is measured only while
+ * "phase_timing" is on (every group is then bracketed by CUDA events and waited for) */
+b200_status b200_comm_ms(b200_problem* p, double* ms, int64_t* calls, int32_t reset);
+
 /* Lambda speculation (optional, on top of the sharding above).  GTSAM's tryLambda loop (reference seam:
  * src/lowerBodyPoseEstimator.cpp:659 `optimizer.iterate()`) re-solves the SAME linearization with lambda, 10 lambda, ... until
  * a step is accepted; the rungs of that ladder are independent of one another.  With n_groups groups of GPUs, group g solves

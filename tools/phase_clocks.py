@@ -10,7 +10,7 @@ dur = float(sys.argv[1]); chunks = int(sys.argv[2])
 tr = synth.make_trial(seed=5, duration_s=dur)
 g, tv, sv = graphs.lower_body_graph(tr, preint=lambda a, w, dt, n_, bh: lib.preintegrate(a, w, dt, n_, bh, so_path=SO))
 tv, sv = graphs.perturbed_truth_values(tr, g, tv, sv)
-p = lib.Problem(g, chunks=chunks, groups=1, so_path=SO); p.set_values(tv, sv)
+p = lib.Problem(g, chunks=chunks if chunks > 0 else None, so_path=SO); p.set_values(tv, sv)
 p.linearize()
 L = lib.load(SO)
 out = (C.c_ulonglong * 16)()
@@ -18,7 +18,7 @@ p.solve(1e-3); L.b200_debug_phase_clocks(out, 1)
 p.solve(1e-3); L.b200_debug_phase_clocks(out, 1)
 names = ["A:load D+fill", "A:chol+inv", "A:store W", "B:load panel", "B:y=pW^T", "B:z=yW", "B:fill=zO^T"]
 tot = sum(out[:7])
-print("K", g.K, "chunks", p.chunks, "last-block cycles per phase (one solve; includes the top-level kernel):")
+print("K", g.K, "chunks", p.chunks, "levels", p.levels, "cycles per phase of CTA 1 of the level-0 sweep (a chunk with left-separator rows), one solve:")
 for n, v in zip(names, out[:7]):
     print("  %-14s %10d  %5.1f%%" % (n, v, 100.0 * v / max(tot, 1)))
 for n, i in (("chol:whole phase", 10), ("pivot:potrf16+inv", 8), ("pivot:scale row+diag tile", 9), ("pivot:wait trailing", 11),
