@@ -1759,8 +1759,8 @@ b200_status b200_debug_get_scalars(b200_problem* p, double out[4]) {
 
 #ifdef B200_PHASE_CLOCKS
 b200_status b200_debug_phase_clocks(unsigned long long* out, int32_t reset) {
-    CK(cudaMemcpyFromSymbol(out, g_phase_clk, sizeof(unsigned long long) * 16));
-    if (reset) { unsigned long long z[16] = {0}; CK(cudaMemcpyToSymbol(g_phase_clk, z, sizeof(z))); }
+    CK(cudaMemcpyFromSymbol(out, g_phase_clk, sizeof(unsigned long long) * 24));
+    if (reset) { unsigned long long z[24] = {0}; CK(cudaMemcpyToSymbol(g_phase_clk, z, sizeof(z))); }
     return B200_OK;
 }
 #endif

@@ -42,7 +42,7 @@ namespace b200d {
 
 // optional per-phase cycle counters of the sweep (debug builds: -DB200_PHASE_CLOCKS), accumulated by thread 0 of the last block
 #ifdef B200_PHASE_CLOCKS
-__device__ unsigned long long g_phase_clk[16];
+__device__ unsigned long long g_phase_clk[24];
 __device__ int g_phase_on;   // set by the level-0 (block-sparse) sweep, cleared by the dense ones: only level 0 is profiled
 #define PH_T0() unsigned long long ph_t_ = clock64()
 #define PH_ADD(i) do { if (threadIdx.x == 0 && blockIdx.x == 1 && g_phase_on) { unsigned long long n_ = clock64(); g_phase_clk[i] += n_ - ph_t_; ph_t_ = n_; } } while (0)

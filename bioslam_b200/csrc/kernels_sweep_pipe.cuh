@@ -125,6 +125,9 @@ __device__ void cta_sweep_pipe(const Dims& dm, const SweepArgs& a, double* sm) {
     const int gnw = 8, gid = warp >> 3, gw = warp & 7, gthreads = gnw << 5, gtid = threadIdx.x & (gthreads - 1);
 #define GSYNC() named_bar_sync(7 + gid, gthreads)
 
+#ifdef B200_PHASE_CLOCKS
+    unsigned long long pp_t = 0;
+#endif
     // ---- pivot block of node j: M = D - fill (lower triangle), fused Cholesky + inverse.  Executed by group 0 only.
     auto factor_node = [&](int j) {
         const long long src = a.src0 + j;
@@ -165,6 +168,9 @@ __device__ void cta_sweep_pipe(const Dims& dm, const SweepArgs& a, double* sm) {
             }
         }
         GSYNC();
+#ifdef B200_PHASE_CLOCKS
+        if (threadIdx.x == 0 && blockIdx.x == 1 && j > 0) { unsigned long long n_ = clock64(); g_phase_clk[3] += n_ - pp_t; pp_t = n_; }
+#endif
         const int fail = cta_chol_inv(Ms, ld, n, gw, gnw, 7);
         if (fail && gtid == 0) {
             const long long st = a.st_idx ? a.st_idx[j] : src;
@@ -357,12 +363,21 @@ __device__ void cta_sweep_pipe(const Dims& dm, const SweepArgs& a, double* sm) {
     };
 
     // ---- prologue: pivot block of the first node
+#ifdef B200_PHASE_CLOCKS
+    if (threadIdx.x == 0) g_phase_on = 1;
+    pp_t = clock64();
+#define PP_ADD(i, t) do { if (threadIdx.x == (t) && blockIdx.x == 1) { unsigned long long n_ = clock64(); g_phase_clk[i] += n_ - pp_t; pp_t = n_; } } while (0)
+#else
+#define PP_ADD(i, t)
+#endif
     if (gid == 0) factor_node(0);
+    PP_ADD(7, 0); PP_ADD(7, 256);
     for (int i = 0; i < a.n; i++) {
         const long long src = a.src0 + i;
         const long long st = a.st_idx ? a.st_idx[i] : src;
         const bool has_x = nc > 0 && ((i + 1 < a.n) || a.has_right);
         __syncthreads();   // [A] W_i^T complete in Ms; the arrow rows of node i-1 are done (Pb, Wt, Op free)
+        PP_ADD(0, 0); PP_ADD(5, 256);
         if (s_abort) return;
         // ---- S2: W^T -> tile layout (zero padded to whole tiles) + global store; packed rows of O
         {
@@ -407,6 +422,7 @@ __device__ void cta_sweep_pipe(const Dims& dm, const SweepArgs& a, double* sm) {
             cp_async_wait_all();
         }
         __syncthreads();   // [B] Wt / Op complete, Ms free
+        PP_ADD(1, 0); PP_ADD(16, 256);
         // ---- S1: rows of O (they feed the next pivot block): both groups, alternate chunks; group 0 in Pb, group 1 in the pivot buffer
         if (has_x) {
             int nch, csz;
@@ -420,6 +436,7 @@ __device__ void cta_sweep_pipe(const Dims& dm, const SweepArgs& a, double* sm) {
         }
         __threadfence_block();
         __syncthreads();   // [C] the fill of the next pivot block is complete
+        PP_ADD(2, 0); PP_ADD(17, 256);
         // ---- S3: group 1: arrow rows of node i   ||   group 0: pivot block of node i + 1
         if (gid == 1) {
             const int xo = has_x ? nc : 0;
@@ -432,8 +449,10 @@ __device__ void cta_sweep_pipe(const Dims& dm, const SweepArgs& a, double* sm) {
                 panel_chunk(i, 1, r0, cr, Pb, has_x);
             }
             __threadfence_block();
+            PP_ADD(6, 256);
         } else if (i + 1 < a.n) {
             factor_node(i + 1);
+            PP_ADD(4, 0);
         }
     }
 #undef GSYNC

@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--stride", type=int, default=1)
     ap.add_argument("--out", required=True)
     ap.add_argument("--progress", type=int, default=50)
+    ap.add_argument("--checkpoint", type=int, default=0, help="write <out>.partial.npz (history / lambdas / trials so far) every N iterations")
     args = ap.parse_args()
 
     from bioslam_b200 import abi, synth
@@ -61,6 +62,9 @@ def main():
         status = st.status
         if args.progress and (len(hist) - 1) % args.progress == 0:
             print(f"it {len(hist) - 1} cost {cur:.10f} lambda {st.lambda_:g} trials {sum(trials)} t {time.perf_counter() - t0:.1f}s", flush=True)
+        if args.checkpoint and (len(hist) - 1) % args.checkpoint == 0:
+            np.savez_compressed(args.out + ".partial.npz", history=np.array(hist), lambdas=np.array(lams), inner_trials=np.array(trials, dtype=np.int32),
+                                wall_s=time.perf_counter() - t0)
         if st.status != 0 and st.iterations == len(hist) - 2:
             break
     wall = time.perf_counter() - t0

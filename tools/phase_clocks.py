@@ -13,7 +13,7 @@ tv, sv = graphs.perturbed_truth_values(tr, g, tv, sv)
 p = lib.Problem(g, chunks=chunks if chunks > 0 else None, so_path=SO); p.set_values(tv, sv)
 p.linearize()
 L = lib.load(SO)
-out = (C.c_ulonglong * 16)()
+out = (C.c_ulonglong * 24)()
 p.solve(1e-3); L.b200_debug_phase_clocks(out, 1)
 p.solve(1e-3); L.b200_debug_phase_clocks(out, 1)
 names = ["A:load D+fill", "A:chol+inv", "A:store W", "B:load panel", "B:y=pW^T", "B:z=yW", "B:fill=zO^T"]
@@ -24,3 +24,10 @@ for n, v in zip(names, out[:7]):
 for n, i in (("chol:whole phase", 10), ("pivot:potrf16+inv", 8), ("pivot:scale row+diag tile", 9), ("pivot:wait trailing", 11),
              ("worker1:wait W", 12), ("worker1:scale column", 13), ("worker1:wait row", 14), ("worker1:trailing", 15)):
     print("  %-26s %10d  %5.1f%%" % (n, out[i], 100.0 * out[i] / max(tot, 1)))
+
+if out[0] or out[1] or out[2]:
+    print("keyframe-pipelined level-0 sweep (kernels_sweep_pipe.cuh), CTA 1, cycles over one solve:")
+    g0 = out[0] + out[1] + out[2] + out[3] + out[4]
+    for n, i in (("g0: wait [A] (arrow rows of g1)", 0), ("g0: S2 W^T -> tiles, store", 1), ("g0: S1 rows of O", 2), ("g0: S3 load D - fill", 3),
+                 ("g0: S3 chol + inverse", 4), ("g1: wait [A] (chol of g0)", 5), ("g1: S2", 16), ("g1: S1 rows of O", 17), ("g1: S3 arrow rows", 6), ("prologue", 7)):
+        print("  %-34s %10d  %5.1f%%" % (n, out[i], 100.0 * out[i] / max(g0, 1)))
