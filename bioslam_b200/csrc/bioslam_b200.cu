@@ -582,7 +582,8 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
         ds.cr = (int)std::min<long long>(64, rows_fit & ~15LL);
         p->smem_sweep = sizeof(double) * (size_t)sweep_smem_doubles(ds.ntp, ds.ld, ds.cr, ds.nc, ds.owp);
         // keyframe-pipelined level-0 sweep: needs the solver layout without local dofs and its (larger) shared-memory carve-up
-        ds.pipe = (ds.nl == 0 && ds.ntp >= 64 && !std::getenv("B200_NO_PIPE")) ? 1 : 0;
+        // (row tiles of <= 128 columns fit the per-warp slice of Tensor Memory)
+        ds.pipe = (ds.nl == 0 && ds.ntp >= 64 && ds.ntp <= 128 && (ds.ow & 1) == 0 && !std::getenv("B200_NO_PIPE")) ? 1 : 0;
         if (ds.pipe) {
             const size_t need = sizeof(double) * (size_t)sweep_pipe_smem_doubles(ds.ntp, ds.ld, ds.nc, ds.owp);
             if (need <= smem_cap) p->smem_sweep = std::max(p->smem_sweep, need); else ds.pipe = 0;

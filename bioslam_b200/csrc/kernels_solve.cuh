@@ -382,6 +382,141 @@ __device__ __forceinline__ int warp_potrf16(double* Db, int ld, int jb, double* 
     return fail;
 }
 
+// ---- the same diagonal block WITHOUT shuffles on the pivot chain: the block is split 8 + 8 and each 8 x 8 half is factorised and
+// inverted REDUNDANTLY IN EVERY LANE, entirely in registers (36 + 36 doubles, statically indexed): per pivot the chain is
+// rsqrt -> scale -> update, no warp shuffle and no shared-memory round trip (the shuffle version measured ~590 cycles per pivot
+// next to 15 warps that saturate the MIO pipe with operand loads; r2 profile).  The three 8 x 8 products that join the halves
+//   L21 = A21 W11^T,  A22 -= L21 L21^T,  W21 = -W22 L21 W11
+// run on the tensor pipe.  An accumulator fragment (row g, columns 2t, 2t+1) is fed back as an A or B operand by permuting the
+// contraction index (slot t of step e <-> k = 2t + e), so L21 and T never leave the registers.
+#define B200_TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
+// a: packed lower triangle of an SPD 8 x 8 block, identical in all lanes.  Returns W = L^-1 (packed lower) in w; a holds L.
+__device__ __forceinline__ int potrf8_regs(double (&a)[36], double (&w)[36]) {
+    int fail = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        double d = a[B200_TRI(c, c)];
+        if (!(d > 0.0) || !(d < 1.0e300)) { if (!fail) fail = 1 + c; d = 1.0; }
+        const double inv = rsqrt(d);
+        // row c of W: W[c][j] = -inv * sum_{k = j}^{c-1} L[c][k] W[k][j]   (the sums do not wait for the reciprocal root)
+        w[B200_TRI(c, c)] = inv;
+#pragma unroll
+        for (int j = 0; j < c; j++) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int k = j; k < c; k++) sacc = fma(a[B200_TRI(c, k)], w[B200_TRI(k, j)], sacc);
+            w[B200_TRI(c, j)] = -inv * sacc;
+        }
+#pragma unroll
+        for (int i = c + 1; i < 8; i++) a[B200_TRI(i, c)] *= inv;
+#pragma unroll
+        for (int j = c + 1; j < 8; j++)
+#pragma unroll
+            for (int i = j; i < 8; i++) a[B200_TRI(i, j)] = fma(-a[B200_TRI(i, c)], a[B200_TRI(j, c)], a[B200_TRI(i, j)]);
+    }
+    return fail;
+}
+// row (lane & 7) of the packed lower-triangular w as 8 doubles (zeros right of the diagonal): a select tree instead of
+// dynamically indexed registers
+__device__ __forceinline__ void tri_row_select(const double (&w)[36], int row, double (&out)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        double v = 0.0;
+#pragma unroll
+        for (int i = j; i < 8; i++) v = (row == i) ? w[B200_TRI(i, j)] : v;
+        out[j] = v;
+    }
+}
+// In: lower triangle of the jb x jb diagonal block at Db (row-major, ld).  Out: the block holds W^T = L^-T (upper triangle incl.
+// the diagonal, strictly lower part zero), Wd[i * WLD + l] = W[i][l] (16 x 16, identity padding beyond jb).  One warp.
+__device__ __forceinline__ int warp_potrf16_r8(double* Db, int ld, int jb, double* Wd) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    double a[36], w[36];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) a[B200_TRI(i, j)] = (i < jb) ? Db[(long long)i * ld + j] : ((i == j) ? 1.0 : 0.0);
+    // A21 as an A operand (row 8 + g, columns 4 s + t) and A22 as an accumulator fragment (row 8 + g, columns 8 + 2t + e)
+    double a21[2], a22[2];
+    {
+        const int r = 8 + g;
+#pragma unroll
+        for (int s = 0; s < 2; s++) a21[s] = (r < jb) ? Db[(long long)r * ld + 4 * s + t] : 0.0;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int c = 8 + 2 * t + e;
+            a22[e] = (r < jb && c <= r) ? Db[(long long)r * ld + c] : ((r == c) ? 1.0 : 0.0);
+        }
+    }
+    int fail = potrf8_regs(a, w);
+    {   // rows 0..7 of W (columns 8..15 are zero)
+        double row[8];
+        tri_row_select(w, lane & 7, row);
+        if (lane < 8) {
+            double* wr = Wd + lane * B200_WLD;
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) { st2(wr + j, row[j], row[j + 1]); st2(wr + 8 + j, 0.0, 0.0); }
+        }
+    }
+    __syncwarp();
+    // L21 = A21 W11^T (natural contraction order) -> fragment l21[e] = L21[g][2t + e]
+    double l21[2] = {0.0, 0.0};
+#pragma unroll
+    for (int s = 0; s < 2; s++) dmma884(l21[0], l21[1], a21[s], Wd[g * B200_WLD + 4 * s + t]);
+    // A22 - L21 L21^T: the fragment is both operands (slot t of step e <-> k = 2t + e)
+    double u[2] = {0.0, 0.0};
+#pragma unroll
+    for (int e = 0; e < 2; e++) dmma884(u[0], u[1], l21[e], l21[e]);
+    st2(Wd + (8 + g) * B200_WLD + 8 + 2 * t, a22[0] - u[0], a22[1] - u[1]);   // scratch: the W22 area of Wd
+    // T^T = W11^T L21^T (needed after the second half; issued here, off the chain): tT[e] = T^T[g][2t + e]
+    double tT[2] = {0.0, 0.0};
+#pragma unroll
+    for (int e = 0; e < 2; e++) dmma884(tT[0], tT[1], Wd[(2 * t + e) * B200_WLD + g], l21[e]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) a[B200_TRI(i, j)] = Wd[(8 + i) * B200_WLD + 8 + j];
+    __syncwarp();   // every lane has read the scratch before rows 8..15 of W overwrite it
+    {
+        const int f2 = potrf8_regs(a, w);
+        if (!fail && f2) fail = 8 + f2;
+    }
+    {   // W22 into rows 8..15, columns 8..15
+        double row[8];
+        tri_row_select(w, lane & 7, row);
+        if (lane < 8) {
+            double* wr = Wd + (8 + lane) * B200_WLD + 8;
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) st2(wr + j, row[j], row[j + 1]);
+        }
+    }
+    __syncwarp();
+    // W21^T = -T^T W22^T: x[e] = (T^T W22^T)[g][2t + e] = -W[8 + 2t + e][g]
+    double x[2] = {0.0, 0.0};
+#pragma unroll
+    for (int e = 0; e < 2; e++) dmma884(x[0], x[1], tT[e], Wd[(8 + g) * B200_WLD + 8 + 2 * t + e]);
+    Wd[(8 + 2 * t) * B200_WLD + g] = -x[0];
+    Wd[(8 + 2 * t + 1) * B200_WLD + g] = -x[1];
+    __syncwarp();
+    // the block itself <- W^T (upper triangle incl. the diagonal; zero below), rows / columns < jb only
+    {
+        const int r = lane >> 1, c0 = (lane & 1) << 3;
+        if (r < jb) {
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+                const int c = c0 + j;
+                if (c < jb) {   // (jb is even or the last column is written alone)
+                    const double v0 = (c >= r) ? Wd[c * B200_WLD + r] : 0.0;
+                    if (c + 1 < jb) { const double v1 = (c + 1 >= r) ? Wd[(c + 1) * B200_WLD + r] : 0.0; st2(Db + (long long)r * ld + c, v0, v1); }
+                    else Db[(long long)r * ld + c] = v0;
+                }
+            }
+        }
+    }
+    return fail;
+}
+
 // small static shared scratch of the diagonal-block routines (one instance per kernel)
 __device__ __forceinline__ void solve_scratch(double*& Tdiag, double*& Wd, double*& invd) {
     __shared__ __align__(16) double s_Tdiag[B200_NB * B200_NB];
@@ -424,7 +559,7 @@ __device__ int cta_chol_inv(double* Ms, int ld, int n, int gw = -1, int gnw = 0,
     if (warp == 0) {
         // ------------------------------------------------------------------ pivot warp
         {
-            const int f = warp_potrf16(Ms, ld, n < B200_NB ? n : B200_NB, Tdiag, invd, s_Wd2[0], true);
+            const int f = warp_potrf16_r8(Ms, ld, n < B200_NB ? n : B200_NB, s_Wd2[0]);
             if (f && lane == 0) fail = f;
         }
         __syncwarp();   // W_00 (written by lanes 16..31) is read by the whole warp below
@@ -502,7 +637,7 @@ __device__ int cta_chol_inv(double* Ms, int ld, int n, int gw = -1, int gnw = 0,
             __syncwarp();
             PHW_ADD(9, 0);
             {
-                const int f = warp_potrf16(Ms + (long long)cb0 * ld + cb0, ld, jb1, Tdiag, invd, s_Wd2[(s + 1) & 1], true);
+                const int f = warp_potrf16_r8(Ms + (long long)cb0 * ld + cb0, ld, jb1, s_Wd2[(s + 1) & 1]);
                 if (f && lane == 0 && fail == 0) fail = cb0 + f;
             }
             __syncwarp();

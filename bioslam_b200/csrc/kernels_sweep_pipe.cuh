@@ -1,20 +1,31 @@
-// Level-0 chain sweep, software-pipelined ACROSS keyframes (the kernel VERDICT r1 names: chain_sweep_kernel<0>).
+// Level-0 chain sweep, software-pipelined ACROSS keyframes, panel rows streamed through Tensor Memory (the kernel VERDICT r1
+// names: chain_sweep_kernel<0>).
 //
-// The plain sweep (cta_sweep in kernels_solve.cuh) runs, per keyframe, the latency-bound fused Cholesky + inverse of the pivot block
-// (one warp walks 106 sequential pivots) and THEN the panel GEMMs; the fp64 tensor pipe idles during the first and the pivot warp
-// during the second.  Only the rows of the coupling block O_k feed the NEXT pivot block; the arrow rows (statics, right-hand side,
-// left-separator rows: 165 of the 271 panel rows) are not needed before the next keyframe's own arrow rows.  So, per keyframe k:
+// Per keyframe k the sweep has a latency-bound part -- the fused Cholesky + inverse of the pivot block, a chain of 106 sequential
+// pivots -- and a throughput-bound part: the panel rows [O_k ; statics ; rhs ; left separator] (271 rows) that go through
+//     y = p W^T  ->  z = y W  ->  fill = z O_k^T          (two triangular GEMMs + one block-sparse GEMM per row)
+// Only the rows of O_k feed the NEXT pivot block; the arrow rows are not needed before the next keyframe's own arrow rows.
 //
-//   S2  all 16 warps   W_k^T (upper triangle of the pivot buffer) -> 16 x 16 tile layout `Wt` (+ global store for the
-//                      back-substitution); packed rows of O_k -> Op
-//   S1  all 16 warps   rows of O_k:  y = p W^T, z = y W, fill = z O_k^T        (two groups of 8 warps on alternate 32-row chunks)
-//   S3  warps 8..15    arrow rows of keyframe k against Wt / Op                 |  concurrently
-//       warps 0..7     pivot block of keyframe k+1: load D - fill, Cholesky + inverse in the pivot buffer
+//   S2  all 16 warps    W_k^T (upper triangle of the pivot buffer) -> 16 x 16 tile layout `Wt` (+ global store for the
+//                       back-substitution); packed rows of O_k -> Op
+//   S1  all 16 warps    rows of O_k (7 row tiles): fill of the next pivot block
+//   S3  warps 4..15     arrow rows of keyframe k (11 row tiles)                      |  concurrently
+//       warps 0..3      pivot block of keyframe k+1: load D - fill, Cholesky + inverse in the pivot buffer
 //
-// Shared memory: pivot buffer n x ld | Wt: n_tiles x (16 x 20) | panel buffer 32 x ld | Op   (~208 KB for n = 106).
-// All panel GEMMs read W^T from the tile layout: tile (kb, cb), kb <= cb, row stride 20 doubles (== 4 mod 8: the DMMA operand
-// fragments of both the NN use (y) and the NT use (z) fall into 16 distinct bank pairs per half warp).
-// Same arithmetic as cta_sweep up to the summation order inside a dot product (contraction in whole 16-blocks).
+// ROW TILES LIVE IN TENSOR MEMORY.  A row tile (16 rows x n columns) is owned by ONE warp from its load to its last store: the
+// warp keeps it in its private slice of TMEM as accumulator-layout fragments (lane (g, t): rows g and 8 + g, columns 8 j + 2 t + e
+// of every 8-column block j), reads it back with tcgen05.ld as the A operand of the fp64 MMA -- the contraction index is permuted,
+// slot t of step e <-> k = 8 j + 2 t + e, so that an accumulator fragment IS an A fragment, no shuffle, no shared-memory round
+// trip -- and overwrites it in place (y over p from the last column block down, z over y from the first one up).  No panel
+// buffer in shared memory, no barrier between the three GEMMs, no barrier between row tiles: every warp streams MMAs
+// independently against the read-only W^T tiles and the packed O rows (r2 profile of the previous version: 32-row chunks shared
+// by 8 warps, six group barriers per chunk, 33 % of the tensor pipe in the arrow phase; tools/ubench/tmem_probe.cu: 79 % with 8
+// independent warps and the A operand in TMEM).
+//
+// Shared memory: pivot buffer n x ld | Wt: n_tiles x (16 x 20) | Op   (~181 KB for n = 106).  TMEM: 512 columns, warp w owns
+// lanes 32 (w & 3).. and columns 128 (w >> 2)..
+// W^T tiles: tile (kb, cb), kb <= cb, row stride 20 doubles (== 4 mod 8): the B fragments of the NN use (y: rows 2t + e, column
+// g, two LDS.64) and of the NT use (z: row g, columns 2t, 2t + 1, one LDS.128) are both bank-conflict free.
 #pragma once
 #include "kernels_solve.cuh"
 
@@ -22,113 +33,247 @@ namespace b200d {
 
 #define B200_TLD 20
 #define B200_TSZ (16 * B200_TLD)
+#define B200_PIVOT_WARPS 4
 __host__ __device__ inline int pipe_ntiles(int n) { const int nb = (n + 15) >> 4; return nb * (nb + 1) / 2; }
 __host__ __device__ inline long long sweep_pipe_smem_doubles(int n, int ld, int nc, int owp) {
-    return (long long)n * ld + (long long)pipe_ntiles(n) * B200_TSZ + 32LL * ld + (((long long)nc * owp + 1) & ~1LL);
+    return (long long)n * ld + (long long)pipe_ntiles(n) * B200_TSZ + (((long long)nc * owp + 1) & ~1LL);
 }
 __device__ __forceinline__ int tile_off(int kb, int cb) { return (cb * (cb + 1) / 2 + kb) * B200_TSZ; }
 
-// y tile: acc[.][0..1] += A[16 x k] W^T[k][block bA], acc[.][2..3] += ... [block bB]; k-blocks kb in [kb_lo, min(bA, .)] for A and
-// [kb_lo, min(bB, kb_hi)] for B (W^T is upper triangular: only tiles kb <= cb exist).  A is row-major (ld), zero beyond column n.
-__device__ __forceinline__ void tile_mma_y(const double* __restrict__ A, int lda, int m0, int M, int n, const double* __restrict__ Wt, int bA, int bB,
-                                           int kb_lo, int kb_hi, bool useA, Acc& acc) {
+struct RowTile {
+    int seg;        // 0: rows of O (fill of the next pivot block), 1: arrow rows
+    int pr0;        // first panel row of the tile (row of the fill buffer); arrow row index = pr0 - xo
+    int cr;         // rows in the tile (<= 16)
+    int xo;         // nc when the node has rows of O, else 0
+    bool has_x;
+};
+
+// One row tile, start to finish, by the calling warp (all 32 lanes, convergent).  tb: TMEM address of the warp's slice.
+__device__ __forceinline__ void stream_row_tile(const Dims& dm, const SweepArgs& a, int i, const RowTile rt, const double* __restrict__ Wt,
+                                                const double* __restrict__ Op, const int* s_orow, const int* s_ozs, const int* s_fk, unsigned tb) {
+    const int n = dm.ntp, nc = dm.nc, ns1 = dm.ns1, hmax = dm.hmax, ow = dm.ow, owp = dm.owp;
+    const long long Fsz = (long long)(nc + hmax) * nc;
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const double* ap[2];
+    const int nb16 = (n + 15) >> 4;
+    const long long src = a.src0 + i;
+    const long long st = a.st_idx ? a.st_idx[i] : src;
+    const double* Fin = a.F + (long long)(i & 1) * Fsz;
+    double* Fout = a.F + (long long)((i + 1) & 1) * Fsz;
+    const bool rv[2] = {g < rt.cr, 8 + g < rt.cr};   // the two row halves of this lane exist
+    // ---- k range of the rows of O of this tile (block-sparse coupling): p is zero outside [ka, kb)
+    int ka = 0, kb = n;
+    if (rt.seg == 0) xrow_range(dm, s_orow, false, rt.pr0, ka, kb);
+    if (kb <= ka) {   // rows without structure: their fill is zero
+        for (int c = 2 * t; c < nc; c += 8)
 #pragma unroll
-    for (int i = 0; i < 2; i++) { int m = m0 + 8 * i + g; if (m > M - 1) m = M - 1; ap[i] = A + (long long)m * lda + t; }
-    const int kend = bB < kb_hi ? bB : kb_hi;   // (the rows of A are zero beyond k-block kb_hi)
-    for (int kb = kb_lo; kb <= kend; kb++) {
-        const bool doA = useA && kb <= bA;
-        const double* tB = Wt + tile_off(kb, bB) + t * B200_TLD + g;
-        const double* tA = Wt + tile_off(kb, doA ? bA : bB) + t * B200_TLD + g;
-        const int k0 = kb << 4;
+            for (int ih = 0; ih < 2; ih++)
+                if (rv[ih]) st2(Fout + (long long)(rt.pr0 + 8 * ih + g) * nc + c, 0.0, 0.0);
+        return;
+    }
+    const int kb_lo = ka >> 4, kb_hi = (kb - 1) >> 4;
+    // ---- load p into TMEM (fragment layout)
+    if (rt.seg == 0) {
+        const double* Og = a.Osrc + src * nc * nc;
+        for (int j = 2 * kb_lo; j <= 2 * kb_hi + 1; j++) {
+            const int c = 8 * j + 2 * t;
+            double v[4];
 #pragma unroll
-        for (int ks = 0; ks < 4; ks++) {
-            const int k = k0 + 4 * ks;
-            const bool ok = k + t < n;
-            double a[2];
+            for (int ih = 0; ih < 2; ih++) {
+                double2 x = make_double2(0.0, 0.0);
+                if (rv[ih] && c < nc) x = ld2(Og + (long long)(rt.pr0 + 8 * ih + g) * nc + c);   // (nc even: the pair is inside or outside)
+                v[2 * ih] = x.x; v[2 * ih + 1] = x.y;
+            }
+            tmem_st4(tb + 8 * j, v);
+        }
+    } else {
+        const double* Ag = a.Asrc + src * ns1 * n;
+        const int ar0 = rt.pr0 - rt.xo;
+        for (int j0 = 0; j0 < 2 * nb16; j0 += 2) {
+            double2 x[2][2], f[2][2];
 #pragma unroll
-            for (int i = 0; i < 2; i++) a[i] = ok ? ap[i][k] : 0.0;
-            const double b2 = tB[4 * ks * B200_TLD], b3 = tB[4 * ks * B200_TLD + 8];
-            if (doA) {
-                const double b0 = tA[4 * ks * B200_TLD], b1 = tA[4 * ks * B200_TLD + 8];
+            for (int jj = 0; jj < 2; jj++) {
+                const int c = 8 * (j0 + jj) + 2 * t;
 #pragma unroll
-                for (int i = 0; i < 2; i++) { dmma884(acc[i][0][0], acc[i][0][1], a[i], b0); dmma884(acc[i][1][0], acc[i][1][1], a[i], b1); }
+                for (int ih = 0; ih < 2; ih++) {
+                    const int ar = ar0 + 8 * ih + g;
+                    x[jj][ih] = make_double2(0.0, 0.0); f[jj][ih] = make_double2(0.0, 0.0);
+                    if (!rv[ih] || c >= n) continue;
+                    if (ar < ns1) x[jj][ih] = ld2(Ag + (long long)ar * n + c);
+                    else if (i == 0 && a.Oleft) { const double* ol = a.Oleft + (ar - ns1); x[jj][ih].x = ol[(long long)c * nc]; x[jj][ih].y = ol[(long long)(c + 1) * nc]; }
+                    if (i > 0 && c < nc) f[jj][ih] = ld2(Fin + (long long)(nc + ar) * nc + c);
+                }
             }
 #pragma unroll
-            for (int i = 0; i < 2; i++) { dmma884(acc[i][2][0], acc[i][2][1], a[i], b2); dmma884(acc[i][3][0], acc[i][3][1], a[i], b3); }
+            for (int jj = 0; jj < 2; jj++) {
+                double v[4];
+#pragma unroll
+                for (int ih = 0; ih < 2; ih++) { v[2 * ih] = x[jj][ih].x - f[jj][ih].x; v[2 * ih + 1] = x[jj][ih].y - f[jj][ih].y; }
+                tmem_st4(tb + 8 * (j0 + jj), v);
+            }
         }
     }
-}
-// z tile: acc[.][0..1] += sum_{cb >= loA} Y[:, block cb] tile(bA, cb)^T, acc[.][2..3] likewise for bB (loX >= bX; loX >= nb: nothing)
-__device__ __forceinline__ void tile_mma_z(const double* __restrict__ A, int lda, int m0, int M, int n, const double* __restrict__ Wt, int bA, int bB,
-                                           int loA, int loB, int nb, Acc& acc) {
-    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const double* ap[2];
+    tmem_wait_st();
+    // ---- y = p W^T, in place from the last 16-column block down: pass over the blocks (c1, c0 = c1 - 1); y[:, c] needs p[:, k <= c]
+    double* Yg = a.Yst + st * (long long)hmax * n;
+    for (int c1 = nb16 - 1; c1 >= kb_lo; c1 -= 2) {
+        const int c0 = c1 - 1;
+        const bool use0 = c0 >= kb_lo;
+        Acc acc;
+        acc_zero(acc);
+        const int kend = c1 < kb_hi ? c1 : kb_hi;
+        for (int kbk = kb_lo; kbk <= kend; kbk++) {
+            const bool do0 = use0 && kbk <= c0;
+            const double* t1 = Wt + tile_off(kbk, c1) + g;
+            const double* t0 = Wt + tile_off(kbk, do0 ? c0 : c1) + g;
 #pragma unroll
-    for (int i = 0; i < 2; i++) { int m = m0 + 8 * i + g; if (m > M - 1) m = M - 1; ap[i] = A + (long long)m * lda + t; }
-    const int lo = loA < loB ? loA : loB;
-    for (int cb = lo; cb < nb; cb++) {
-        const bool doA = cb >= loA, doB = cb >= loB;
-        const double* tA = Wt + tile_off(doA ? bA : 0, cb) + g * B200_TLD + t;
-        const double* tB = Wt + tile_off(doB ? bB : 0, cb) + g * B200_TLD + t;
-        const int k0 = cb << 4;
+            for (int h = 0; h < 2; h++) {
+                double av[4];
+                tmem_ld4(tb + 8 * (2 * kbk + h), av);
 #pragma unroll
-        for (int ks = 0; ks < 4; ks++) {
-            const int k = k0 + 4 * ks;
-            const bool ok = k + t < n;
-            double a[2];
+                for (int e = 0; e < 2; e++) {
+                    const int kr = (8 * h + 2 * t + e) * B200_TLD;
+                    const double b2 = t1[kr], b3 = t1[kr + 8];
+                    if (do0) {
+                        const double b0 = t0[kr], b1 = t0[kr + 8];
 #pragma unroll
-            for (int i = 0; i < 2; i++) a[i] = ok ? ap[i][k] : 0.0;
-            if (doA) {
-                const double b0 = tA[4 * ks], b1 = tA[8 * B200_TLD + 4 * ks];
+                        for (int ih = 0; ih < 2; ih++) { dmma884(acc[ih][0][0], acc[ih][0][1], av[2 * ih + e], b0); dmma884(acc[ih][1][0], acc[ih][1][1], av[2 * ih + e], b1); }
+                    }
 #pragma unroll
-                for (int i = 0; i < 2; i++) { dmma884(acc[i][0][0], acc[i][0][1], a[i], b0); dmma884(acc[i][1][0], acc[i][1][1], a[i], b1); }
+                    for (int ih = 0; ih < 2; ih++) { dmma884(acc[ih][2][0], acc[ih][2][1], av[2 * ih + e], b2); dmma884(acc[ih][3][0], acc[ih][3][1], av[2 * ih + e], b3); }
+                }
             }
-            if (doB) {
-                const double b2 = tB[4 * ks], b3 = tB[8 * B200_TLD + 4 * ks];
+        }
 #pragma unroll
-                for (int i = 0; i < 2; i++) { dmma884(acc[i][2][0], acc[i][2][1], a[i], b2); dmma884(acc[i][3][0], acc[i][3][1], a[i], b3); }
+        for (int q = 0; q < 4; q++) {
+            if (q < 2 && !use0) continue;
+            const int j = 2 * (q < 2 ? c0 : c1) + (q & 1);
+            double v[4] = {acc[0][q][0], acc[0][q][1], acc[1][q][0], acc[1][q][1]};
+            tmem_st4(tb + 8 * j, v);
+            if (rt.seg == 1) {
+                const int c = 8 * j + 2 * t;
+                if (c < n) {
+#pragma unroll
+                    for (int ih = 0; ih < 2; ih++)
+                        if (rv[ih]) st2(Yg + (long long)(rt.pr0 - rt.xo + 8 * ih + g) * n + c, acc[ih][q][0], acc[ih][q][1]);
+                }
+            }
+        }
+    }
+    if (!rt.has_x) return;
+    tmem_wait_st();
+    // ---- z = y W, in place from the first 16-column block up: z[:, c] = sum_{k >= max(c, kb_lo)} y[:, k] tile(c, k)^T.
+    // Rows of O: z is only needed left of kb (the columns that feed the lower triangle of the fill).
+    const int zc_hi = rt.seg == 0 ? kb_hi : nb16 - 1;
+    for (int c0 = 0; c0 <= zc_hi; c0 += 2) {
+        const int c1 = c0 + 1;
+        const bool use1 = c1 <= zc_hi;
+        Acc acc;
+        acc_zero(acc);
+        const int k0 = c0 > kb_lo ? c0 : kb_lo;
+        for (int kbk = k0; kbk < nb16; kbk++) {
+            const bool do1 = use1 && kbk >= c1;
+            const double* t0 = Wt + tile_off(c0, kbk) + g * B200_TLD + 2 * t;
+            const double* t1 = Wt + tile_off(do1 ? c1 : c0, kbk) + g * B200_TLD + 2 * t;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                double av[4];
+                tmem_ld4(tb + 8 * (2 * kbk + h), av);
+                const double2 b0 = ld2(t0 + 8 * h), b1 = ld2(t0 + 8 * B200_TLD + 8 * h);
+#pragma unroll
+                for (int ih = 0; ih < 2; ih++) {
+                    dmma884(acc[ih][0][0], acc[ih][0][1], av[2 * ih], b0.x); dmma884(acc[ih][0][0], acc[ih][0][1], av[2 * ih + 1], b0.y);
+                    dmma884(acc[ih][1][0], acc[ih][1][1], av[2 * ih], b1.x); dmma884(acc[ih][1][0], acc[ih][1][1], av[2 * ih + 1], b1.y);
+                }
+                if (do1) {
+                    const double2 b2 = ld2(t1 + 8 * h), b3 = ld2(t1 + 8 * B200_TLD + 8 * h);
+#pragma unroll
+                    for (int ih = 0; ih < 2; ih++) {
+                        dmma884(acc[ih][2][0], acc[ih][2][1], av[2 * ih], b2.x); dmma884(acc[ih][2][0], acc[ih][2][1], av[2 * ih + 1], b2.y);
+                        dmma884(acc[ih][3][0], acc[ih][3][1], av[2 * ih], b3.x); dmma884(acc[ih][3][0], acc[ih][3][1], av[2 * ih + 1], b3.y);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (q >= 2 && !use1) continue;
+            const int j = 2 * (q < 2 ? c0 : c1) + (q & 1);
+            double v[4] = {acc[0][q][0], acc[0][q][1], acc[1][q][0], acc[1][q][1]};
+            tmem_st4(tb + 8 * j, v);
+        }
+    }
+    tmem_wait_st();
+    // ---- fill rows F = z O^T (block-sparse coupling): aligned 8-column output blocks; row co of O is packed in Op as the window
+    // [ozs[co], ozs[co] + ow) and the block contracts over the union of its rows' windows (s_fk: first / last 8-column block of k)
+    {
+        const int jz_hi = 2 * zc_hi + 1;   // last 8-column block of z that exists
+        const int jo_hi = rt.seg == 0 ? ((rt.pr0 + rt.cr - 1) >> 3) : ((nc - 1) >> 3);   // rows of O: lower triangle of the fill only
+        for (int jo = 0; jo <= jo_hi && 8 * jo < nc; jo++) {
+            const int co = 8 * jo + g;
+            const bool cok = co < nc;
+            const int zs = cok ? s_ozs[co] : 0;
+            const double* orow_p = Op + (long long)(cok ? co : 0) * owp;
+            double f[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+            const int jk0 = s_fk[2 * jo];
+            const int jk1 = s_fk[2 * jo + 1] < jz_hi ? s_fk[2 * jo + 1] : jz_hi;
+            for (int jk = jk0; jk <= jk1; jk++) {
+                double av[4];
+                tmem_ld4(tb + 8 * jk, av);
+                const int off = 8 * jk + 2 * t - zs;
+                double2 b = make_double2(0.0, 0.0);
+                if (cok && off >= 0 && off < ow) b = ld2(orow_p + off);
+#pragma unroll
+                for (int ih = 0; ih < 2; ih++) { dmma884(f[ih][0], f[ih][1], av[2 * ih], b.x); dmma884(f[ih][0], f[ih][1], av[2 * ih + 1], b.y); }
+            }
+            const int cw = 8 * jo + 2 * t;
+            if (cw < nc) {
+#pragma unroll
+                for (int ih = 0; ih < 2; ih++)
+                    if (rv[ih]) st2(Fout + (long long)(rt.pr0 + 8 * ih + g) * nc + cw, f[ih][0], f[ih][1]);
             }
         }
     }
 }
 
-// requires: dm.nl == 0 (solver layout), block-sparse O, blockDim.x == 512, a.n >= 1
+// requires: dm.nl == 0 (solver layout), block-sparse O, blockDim.x == 512, a.n >= 1, ntp <= 128, ow even
 __device__ void cta_sweep_pipe(const Dims& dm, const SweepArgs& a, double* sm) {
     const int n = dm.ntp, nc = dm.nc, ns1 = dm.ns1, ld = dm.ld, hmax = dm.hmax, ow = dm.ow, owp = dm.owp;
     const long long Fsz = (long long)(nc + hmax) * nc;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mg = lane >> 2, mt = lane & 3;
-    const int nb16 = (n + 15) >> 4, npair = (nb16 + 1) >> 1;
     double* Ms = sm;
     double* Wt = Ms + (long long)n * ld;
-    double* Pb = Wt + (long long)pipe_ntiles(n) * B200_TSZ;
-    double* Op = Pb + 32LL * ld;
-    __shared__ int s_orow[2 * 256], s_ozs[256], s_fblk[64], s_nfblk, s_abort;
+    double* Op = Wt + (long long)pipe_ntiles(n) * B200_TSZ;
+    __shared__ int s_orow[2 * 128], s_ozs[128], s_fk[2 * 16], s_abort;
+    __shared__ unsigned s_tmem;
     for (int e = threadIdx.x; e < 2 * nc; e += blockDim.x) s_orow[e] = dm.orow[e];
     for (int e = threadIdx.x; e < nc; e += blockDim.x) s_ozs[e] = dm.ozs[e];
     if (threadIdx.x == 0) s_abort = 0;
+    if (warp == 0) tmem_alloc512(&s_tmem);
+    tmem_fence_before_sync();
     __syncthreads();
-    if (threadIdx.x == 0) {   // 8-column blocks of the block-sparse fill (see cta_sweep)
-        int nbk = 0, i0 = 0;
-        while (i0 < nc && nbk < 60) {
-            int e = i0;
-            while (e < nc && s_ozs[e] == s_ozs[i0]) e++;
-            for (int j = i0; j < e && nbk < 60; j += 8) s_fblk[nbk++] = (j + 8 <= e) ? j : ((e - 8 > i0) ? e - 8 : i0);
-            i0 = e;
+    tmem_fence_after_sync();
+    if (threadIdx.x < 16) {   // contraction range (8-column blocks of z) of every aligned 8-column output block of the fill
+        const int jo = threadIdx.x;
+        int lo = n, hi = 0;
+        for (int co = 8 * jo; co < 8 * jo + 8 && co < nc; co++) {
+            if (s_ozs[co] < lo) lo = s_ozs[co];
+            if (s_ozs[co] + ow > hi) hi = s_ozs[co] + ow;
         }
-        s_nfblk = nbk;
+        if (hi > n) hi = n;
+        s_fk[2 * jo] = lo >> 3; s_fk[2 * jo + 1] = hi > lo ? (hi - 1) >> 3 : (lo >> 3) - 1;
     }
     __syncthreads();
-    // two groups of 8 warps; group barrier ids 7 / 8
-    const int gnw = 8, gid = warp >> 3, gw = warp & 7, gthreads = gnw << 5, gtid = threadIdx.x & (gthreads - 1);
-#define GSYNC() named_bar_sync(7 + gid, gthreads)
-
+    const unsigned tb = s_tmem + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)(128 * (warp >> 2));
+    // pivot group: warps [0, B200_PIVOT_WARPS), named barrier 7
+    const int gnw = B200_PIVOT_WARPS, gthreads = gnw << 5;
+    const bool pivot_grp = warp < gnw;
+    const int gw = warp, gtid = threadIdx.x;
+#define GSYNC() named_bar_sync(7, gthreads)
 #ifdef B200_PHASE_CLOCKS
     unsigned long long pp_t = 0;
 #endif
-    // ---- pivot block of node j: M = D - fill (lower triangle), fused Cholesky + inverse.  Executed by group 0 only.
+
+    // ---- pivot block of node j: M = D - fill (lower triangle), fused Cholesky + inverse.  Executed by the pivot group only.
     auto factor_node = [&](int j) {
         const long long src = a.src0 + j;
         const double* Fin = a.F + (long long)(j & 1) * Fsz;
@@ -179,189 +324,6 @@ __device__ void cta_sweep_pipe(const Dims& dm, const SweepArgs& a, double* sm) {
         }
     };
 
-    // ---- one chunk of <= 32 panel rows [r0, r0 + cr) of node i by this thread's group, in buffer Yb.  seg 0: rows of O, seg 1: arrow rows.
-    auto panel_chunk = [&](int i, int seg, int r0, int cr, double* Yb, bool has_x) {
-        const long long src = a.src0 + i;
-        const long long st = a.st_idx ? a.st_idx[i] : src;
-        const int xo = has_x ? nc : 0;
-        const double* Fin = a.F + (long long)(i & 1) * Fsz;
-        double* Fout = a.F + (long long)((i + 1) & 1) * Fsz;
-        double* Yg = a.Yst + st * (long long)hmax * n;
-        const double* Og = a.Osrc + src * nc * nc;
-        const double* Ag = a.Asrc + src * ns1 * n;
-        GSYNC();   // Yb free
-        for (int lr = gw; lr < cr; lr += gnw) {
-            const int pr = r0 + lr;
-            double* dst = Yb + (long long)lr * ld;
-            if (seg == 0) {
-                const double* og = Og + (long long)pr * nc;
-                for (int c = lane; c < n; c += 32) cp_async8(dst + c, og + c);
-            } else {
-                const int ar = pr - xo;
-                if (ar < ns1) {
-                    const double* ag = Ag + (long long)ar * n;
-                    for (int c = 2 * lane; c < n; c += 64) cp_async16(dst + c, ag + c);
-                } else if (i == 0 && a.Oleft) {
-                    const double* ol = a.Oleft + (ar - ns1);
-                    for (int c = lane; c < n; c += 32) dst[c] = ol[(long long)c * nc];
-                } else if (i == 0) {
-                    for (int c = lane; c < n; c += 32) dst[c] = 0.0;
-                }
-            }
-        }
-        if (seg == 1 && i > 0) {
-            const int ar0 = r0 - xo;
-            for (int rb = 0; rb < cr; rb += 4 * gnw) {
-                for (int cb = 0; cb < nc; cb += 128) {
-                    double f[4][4];
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const int lr = rb + gw + q * gnw;
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const int c = cb + lane + 32 * u;
-                            f[q][u] = (lr < cr && c < nc) ? Fin[(long long)(nc + ar0 + lr) * nc + c] : 0.0;
-                        }
-                    }
-                    if (rb == 0 && cb == 0) { cp_async_wait_all(); GSYNC(); }
-#pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const int lr = rb + gw + q * gnw;
-                        if (lr >= cr) continue;
-                        double* dr = Yb + (long long)lr * ld;
-                        const bool src_row = (ar0 + lr) < ns1;   // static / rhs rows start from A, left rows from zero
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const int c = cb + lane + 32 * u;
-                            if (c < nc) dr[c] = (src_row ? dr[c] : 0.0) - f[q][u];
-                        }
-                    }
-                }
-            }
-        } else {
-            cp_async_wait_all();
-        }
-        GSYNC();
-        // ---- y = p W^T : every warp owns one 16-row tile and the 16-column blocks (s, nb16 - 1 - s)
-        const int rtiles = (cr + 15) >> 4;
-        const int slot = gw & 3, rt = gw >> 2;
-        const bool act = rt < rtiles && slot < npair;
-        const int bA = slot, bB = nb16 - 1 - slot;
-        const int m0 = rt << 4;
-        int ka = 0, kb = n;
-        if (seg == 0 && act) xrow_range(dm, s_orow, false, r0 + m0, ka, kb);
-        {
-            Acc acc;
-            acc_zero(acc);
-            if (act && kb > ka) tile_mma_y(Yb, ld, m0, cr, n, Wt, bA, bB, ka >> 4, (kb - 1) >> 4, bA != bB, acc);
-            GSYNC();
-            if (act) {
-#pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    const int lr = m0 + 8 * q + mg;
-                    if (lr >= cr) continue;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        if (j < 2 && bA == bB) continue;
-                        const int c = ((j < 2 ? bA : bB) << 4) + 8 * (j & 1) + 2 * mt;
-                        if (c >= n) continue;
-                        st2(Yb + (long long)lr * ld + c, acc[q][j][0], acc[q][j][1]);
-                        if (seg == 1) st2(Yg + (long long)(r0 - xo + lr) * n + c, acc[q][j][0], acc[q][j][1]);
-                    }
-                }
-            }
-            GSYNC();
-        }
-        if (!has_x) return;
-        // ---- z = y W, in place after a barrier
-        {
-            Acc acc;
-            acc_zero(acc);
-            if (act && kb > ka) {
-                int loA = bA, loB = bB;
-                if (seg == 0) {
-                    // rows of O: y is zero left of ka; z is only needed left of kb (the columns that feed the lower triangle of the fill)
-                    const int klo = ka >> 4;
-                    if (klo > loA) loA = klo;
-                    if (klo > loB) loB = klo;
-                    if ((bA << 4) >= kb) loA = nb16;
-                    if ((bB << 4) >= kb) loB = nb16;
-                }
-                if (bA == bB) loA = nb16;
-                tile_mma_z(Yb, ld, m0, cr, n, Wt, bA, bB, loA, loB, nb16, acc);
-            }
-            GSYNC();
-            if (act) {
-#pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    const int lr = m0 + 8 * q + mg;
-                    if (lr >= cr) continue;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        if (j < 2 && bA == bB) continue;
-                        const int c = ((j < 2 ? bA : bB) << 4) + 8 * (j & 1) + 2 * mt;
-                        if (c < n) st2(Yb + (long long)lr * ld + c, acc[q][j][0], acc[q][j][1]);
-                    }
-                }
-            }
-            GSYNC();
-        }
-        // ---- fill rows F = z O^T (block-sparse coupling: 8-column blocks of rows of O that share one packed window)
-        {
-            const int nfb = s_nfblk, ncq = (nfb + 3) >> 2, nst = (ow + 3) >> 2;
-            for (int task = gw; task < rtiles * ncq; task += gnw) {
-                const int trt = task % rtiles, cq = task / rtiles;
-                const int tm0 = trt << 4;
-                int zs[4], cs[4];
-                bool cval[4];
-                const double* bp[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int fb = (cq << 2) + j;
-                    cs[j] = fb < nfb ? s_fblk[fb] : nc;
-                    zs[j] = fb < nfb ? s_ozs[cs[j]] : n;
-                    const int ci = cs[j] + mg;
-                    cval[j] = ci < nc && s_ozs[ci < nc ? ci : 0] == zs[j];
-                    bp[j] = Op + (cval[j] ? ci : 0) * owp;
-                }
-                const double* ap[2];
-#pragma unroll
-                for (int q = 0; q < 2; q++) { int lr = tm0 + 8 * q + mg; if (lr > cr - 1) lr = cr - 1; ap[q] = Yb + (long long)lr * ld; }
-                Acc acc;
-                acc_zero(acc);
-                for (int sidx = 0; sidx < nst; sidx++) {
-                    const int idx = 4 * sidx + mt;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int kk = zs[j] + idx;
-                        const bool ok = kk < n && idx < ow;
-                        const double bv = (cval[j] && idx < ow) ? bp[j][idx] : 0.0;
-#pragma unroll
-                        for (int q = 0; q < 2; q++) dmma884(acc[q][j][0], acc[q][j][1], ok ? ap[q][kk] : 0.0, bv);
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    const int lr = tm0 + 8 * q + mg;
-                    if (lr >= cr) continue;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-#pragma unroll
-                        for (int e = 0; e < 2; e++) {
-                            const int co = cs[j] + 2 * mt + e;
-                            if (co < nc && s_ozs[co] == zs[j]) Fout[(long long)(r0 + lr) * nc + co] = acc[q][j][e];
-                        }
-                    }
-                }
-            }
-        }
-    };
-    // chunks of a segment of cnt rows starting at panel row `base`: balanced sizes, multiples of 16, <= 32
-    auto seg_chunks = [&](int cnt, int& nch, int& csz) {
-        nch = (cnt + 31) / 32;
-        csz = nch ? (((cnt + nch - 1) / nch + 15) & ~15) : 0;
-    };
-
     // ---- prologue: pivot block of the first node
 #ifdef B200_PHASE_CLOCKS
     if (threadIdx.x == 0) g_phase_on = 1;
@@ -370,15 +332,16 @@ __device__ void cta_sweep_pipe(const Dims& dm, const SweepArgs& a, double* sm) {
 #else
 #define PP_ADD(i, t)
 #endif
-    if (gid == 0) factor_node(0);
+    if (pivot_grp) factor_node(0);
     PP_ADD(7, 0); PP_ADD(7, 256);
     for (int i = 0; i < a.n; i++) {
         const long long src = a.src0 + i;
         const long long st = a.st_idx ? a.st_idx[i] : src;
         const bool has_x = nc > 0 && ((i + 1 < a.n) || a.has_right);
-        __syncthreads();   // [A] W_i^T complete in Ms; the arrow rows of node i-1 are done (Pb, Wt, Op free)
+        const int xo = has_x ? nc : 0;
+        __syncthreads();   // [A] W_i^T complete in Ms; the arrow rows of node i-1 are done (Wt, Op free)
         PP_ADD(0, 0); PP_ADD(5, 256);
-        if (s_abort) return;
+        if (s_abort) break;
         // ---- S2: W^T -> tile layout (zero padded to whole tiles) + global store; packed rows of O
         {
             double* Wg = a.Wst + st * n * n;
@@ -413,7 +376,6 @@ __device__ void cta_sweep_pipe(const Dims& dm, const SweepArgs& a, double* sm) {
                     if (cc >= 0 && cc < nc) cp_async8(Op + r * owp + t, Og + (long long)r * nc + cc);
                     else Op[r * owp + t] = 0.0;
                 }
-                for (int e = threadIdx.x * 16; e < nc * nc; e += blockDim.x * 16) prefetch_l2(Og + e);
             }
             {
                 const double* Ag = a.Asrc + src * ns1 * n;
@@ -423,30 +385,26 @@ __device__ void cta_sweep_pipe(const Dims& dm, const SweepArgs& a, double* sm) {
         }
         __syncthreads();   // [B] Wt / Op complete, Ms free
         PP_ADD(1, 0); PP_ADD(16, 256);
-        // ---- S1: rows of O (they feed the next pivot block): both groups, alternate chunks; group 0 in Pb, group 1 in the pivot buffer
+        // ---- S1: rows of O (they feed the next pivot block): one 16-row tile per warp
         if (has_x) {
-            int nch, csz;
-            seg_chunks(nc, nch, csz);
-            double* Yb = gid == 0 ? Pb : Ms;
-            for (int ch = gid; ch < nch; ch += 2) {
-                const int r0 = ch * csz;
-                const int cr = (nc - r0 < csz) ? (nc - r0) : csz;
-                panel_chunk(i, 0, r0, cr, Yb, has_x);
+            const int ntile = (nc + 15) >> 4;
+            for (int tl = warp; tl < ntile; tl += 16) {
+                RowTile rt;
+                rt.seg = 0; rt.pr0 = tl << 4; rt.cr = (nc - rt.pr0 < 16) ? (nc - rt.pr0) : 16; rt.xo = xo; rt.has_x = true;
+                stream_row_tile(dm, a, i, rt, Wt, Op, s_orow, s_ozs, s_fk, tb);
             }
         }
         __threadfence_block();
         __syncthreads();   // [C] the fill of the next pivot block is complete
         PP_ADD(2, 0); PP_ADD(17, 256);
-        // ---- S3: group 1: arrow rows of node i   ||   group 0: pivot block of node i + 1
-        if (gid == 1) {
-            const int xo = has_x ? nc : 0;
+        // ---- S3: panel warps: arrow rows of node i   ||   pivot group: pivot block of node i + 1
+        if (!pivot_grp) {
             const int cnt = a.ar_hi - a.ar_lo;
-            int nch, csz;
-            seg_chunks(cnt, nch, csz);
-            for (int ch = 0; ch < nch; ch++) {
-                const int r0 = xo + a.ar_lo + ch * csz;
-                const int cr = (xo + a.ar_lo + cnt - r0 < csz) ? (xo + a.ar_lo + cnt - r0) : csz;
-                panel_chunk(i, 1, r0, cr, Pb, has_x);
+            const int ntile = (cnt + 15) >> 4;
+            for (int tl = warp - gnw; tl < ntile; tl += 16 - gnw) {
+                RowTile rt;
+                rt.seg = 1; rt.pr0 = xo + a.ar_lo + (tl << 4); rt.cr = (cnt - (tl << 4) < 16) ? (cnt - (tl << 4)) : 16; rt.xo = xo; rt.has_x = has_x;
+                stream_row_tile(dm, a, i, rt, Wt, Op, s_orow, s_ozs, s_fk, tb);
             }
             __threadfence_block();
             PP_ADD(6, 256);
@@ -456,7 +414,9 @@ __device__ void cta_sweep_pipe(const Dims& dm, const SweepArgs& a, double* sm) {
         }
     }
 #undef GSYNC
+    tmem_fence_before_sync();
     __syncthreads();
+    if (warp == 0) tmem_dealloc512(s_tmem);
 }
 
 }  // namespace b200d

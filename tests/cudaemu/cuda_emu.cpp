@@ -75,6 +75,14 @@ void init_fiber(Fiber& f) {
 
 int lane_id() { return cur->lin & 31; }
 
+static unsigned tmem_cells[128][512];
+unsigned* tmem_cell(int lane, int col) {
+    if (lane < 0 || lane >= 128 || col < 0 || col + 8 > 512) { std::fprintf(stderr, "emu: TMEM access out of range (lane %d column %d)\n", lane, col); std::abort(); }
+    // tcgen05 32x32b: a warp reaches only the lane quarter 32 * (warp id % 4)
+    if ((lane >> 5) != ((cur->lin >> 5) & 3)) { std::fprintf(stderr, "emu: TMEM lane %d is not in the quarter of warp %d\n", lane, cur->lin >> 5); std::abort(); }
+    return &tmem_cells[lane][col];
+}
+
 void sync_block() { cur->st = WAIT_BLOCK; yield_to_sched(); }
 void sync_warp() { cur->st = WAIT_WARP; yield_to_sched(); }
 
@@ -143,6 +151,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
     for (unsigned by = 0; by < grid.y; by++)
     for (unsigned bx = 0; bx < grid.x; bx++) {
         std::memset(dyn_smem, 0xCD, smem_bytes);  // poison: uninitialised shared memory reads show up as garbage
+        std::memset(tmem_cells, 0xCD, sizeof(tmem_cells));
         blockIdx = {bx, by, bz};
         for (int& c : named_cnt) c = 0;
         int lin = 0;

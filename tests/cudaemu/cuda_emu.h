@@ -81,6 +81,7 @@ void bar_arrive(int id, int count);   // named barrier, non-blocking arrival (ba
 double shfl_exchange(double v, int src_lane);   // generic lane exchange within the caller's warp
 unsigned ballot(int pred);
 void dmma884(double& c0, double& c1, double a, double b);   // warp-collective fp64 MMA m8n8k4 (row.col)
+unsigned* tmem_cell(int lane, int col);   // Tensor Memory of the running block: 128 lanes x 512 columns of 32-bit cells
 extern char* dyn_smem;
 extern long long launch_counter;
 int lane_id();
