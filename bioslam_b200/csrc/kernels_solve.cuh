@@ -539,7 +539,10 @@ __device__ __forceinline__ void solve_scratch(double*& Tdiag, double*& Wd, doubl
 // alternating instances each): W_READY (W_ss in Wd[s&1]), ROW_READY (block row s+1 scaled), T_DONE (trailing update s done).
 // Runs on a GROUP of gnw consecutive warps (warp index in the group gw; default: the whole CTA); gsync = named barrier id the group
 // may use for its own full-group synchronisation (0: __syncthreads, i.e. the group is the CTA).
-__device__ int cta_chol_inv(double* Ms, int ld, int n, int gw = -1, int gnw = 0, int gsync = 0) {
+// lower_only: plain blocked Cholesky -- the appended identity rows (the upper triangle) are left alone: on return the strictly lower
+// blocks hold L, the diagonal 16 x 16 tiles hold W_ss^T = L_ss^-T (upper incl. the diagonal, zero below) and nothing else is touched.
+// Half the trailing-update work of the fused version; the caller builds W^T from L by forward substitution (kernels_sweep_pipe.cuh).
+__device__ int cta_chol_inv(double* Ms, int ld, int n, int gw = -1, int gnw = 0, int gsync = 0, bool lower_only = false) {
     __shared__ int fail;
     __shared__ __align__(16) double s_Wd2[2][B200_NB * B200_WLD];
     double *Tdiag, *Wd0, *invd;
@@ -661,7 +664,8 @@ __device__ int cta_chol_inv(double* Ms, int ld, int n, int gw = -1, int gnw = 0,
             if (fail) break;
             // rows r in [0, j0) U [cb0 + 16, n): X[r][j0 .. j0+jb) <- X * W_ss^T, 16 (virtual) rows per warp, in place
             const int skip = (cb0 < n) ? ((n - cb0 < B200_NB) ? (n - cb0) : B200_NB) : 0;   // block row s+1 belongs to the pivot warp
-            const int nvr = n - jb - skip;
+            const int vabove = lower_only ? 0 : j0;   // (lower_only: no appended rows above the block)
+            const int nvr = n - jb - skip - (j0 - vabove);
             for (int t = wk; t * 16 < nvr; t += nwk) {
                 const double* ap[2];
                 bool ok[2];
@@ -670,7 +674,7 @@ __device__ int cta_chol_inv(double* Ms, int ld, int n, int gw = -1, int gnw = 0,
                     int vr = t * 16 + 8 * i + mg;
                     ok[i] = vr < nvr;
                     if (!ok[i]) vr = nvr - 1;
-                    const int r = (vr < j0) ? vr : vr + jb + skip;
+                    const int r = (vr < vabove) ? vr : vr - vabove + j0 + jb + skip;
                     ap[i] = Ms + (long long)r * ld + j0;
                 }
                 double sacc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
@@ -704,7 +708,33 @@ __device__ int cta_chol_inv(double* Ms, int ld, int n, int gw = -1, int gnw = 0,
             PHW_ADD(14, 32);
             // trailing update: Ms[r][c] -= sum_t Ms[r][j0+t] Ms[c][j0+t], c >= cb0, alive rows (r >= c or r < cb0),
             // except the diagonal tile (s+1, s+1), which the pivot warp has already updated
-            {
+            if (lower_only) {
+                // live tiles only: 16-row tiles below block row s+1, 32-column tiles up to the diagonal
+                int idx = 0;
+                for (int m0 = cb0 + B200_NB; m0 < n; m0 += 16) {
+                    for (int c0 = cb0; c0 <= m0; c0 += 32) {
+                        if ((idx++) % nwk != wk) continue;
+                        Acc acc;
+                        acc_zero(acc);
+                        warp_mma_nt(Ms, ld, m0, n, Ms, ld, c0, n, j0, cb0, acc);
+#pragma unroll
+                        for (int i = 0; i < 2; i++) {
+                            const int r = m0 + 8 * i + mg;
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const int c = c0 + 8 * j + 2 * mt;
+                                if (r < n && c <= r) {   // (c even, n even: the pair is inside the matrix; c == r rewrites (r, r+1) unchanged)
+                                    double* q = Ms + (long long)r * ld + c;
+                                    double2 v = ld2(q);
+                                    v.x -= acc[i][j][0];
+                                    if (c + 1 <= r) v.y -= acc[i][j][1];
+                                    st2(q, v.x, v.y);
+                                }
+                            }
+                        }
+                    }
+                }
+            } else {
                 const int ntr = (n + 15) >> 4, ntc = (n - cb0 + 31) >> 5;
                 for (int tile = wk; tile < ntr * ntc; tile += nwk) {
                     const int m0 = (tile / ntc) << 4, c0 = cb0 + ((tile % ntc) << 5);
@@ -862,12 +892,12 @@ __host__ __device__ inline long long sweep_smem_doubles(int ntp, int ld, int cr,
 __host__ __device__ inline int static_lds(int ns) { int lds = ns + (ns & 1); while ((lds & 3) != 2) lds += 2; return lds; }
 
 // [ka, kb) (even bounds, time-block coordinates) of the columns in which rows [r0, r0+16) of O can be non-zero
-__device__ __forceinline__ void xrow_range(const Dims& dm, const int* orow, bool dense, int r0, int& ka, int& kb) {
+__device__ __forceinline__ void xrow_range(const Dims& dm, const int* orow, bool dense, int r0, int& ka, int& kb, int nrows = 16) {
     if (dense) { ka = dm.nl & ~1; kb = dm.ntp; return; }
     const int lane = threadIdx.x & 31;
     int lo = dm.ntp, hi = 0;
     const int r = r0 + (lane & 15);
-    if (r < dm.nc) {
+    if (r < dm.nc && (lane & 15) < nrows) {
         const int c0 = orow[2 * r], c1 = orow[2 * r + 1];
         if (c1 > c0) { lo = (dm.nl + c0) & ~1; hi = (dm.nl + c1 + 1) & ~1; }
     }

@@ -8,9 +8,9 @@
 //
 //   S2  all 16 warps    W_k^T (upper triangle of the pivot buffer) -> 16 x 16 tile layout `Wt` (+ global store for the
 //                       back-substitution); packed rows of O_k -> Op
-//   S1  all 16 warps    rows of O_k (7 row tiles): fill of the next pivot block
-//   S3  warps 4..15     arrow rows of keyframe k (11 row tiles)                      |  concurrently
-//       warps 0..3      pivot block of keyframe k+1: load D - fill, Cholesky + inverse in the pivot buffer
+//   S1  all 16 warps    rows of O_k (7 row tiles): their fill goes straight into the pivot buffer, M_k+1 = D_k+1 + lambda I - fill
+//   S3  warps 5..15     arrow rows of keyframe k (11 row tiles, one per warp)        |  concurrently
+//       warps 0..4      pivot block of keyframe k+1: Cholesky + inverse in the pivot buffer
 //
 // ROW TILES LIVE IN TENSOR MEMORY.  A row tile (16 rows x n columns) is owned by ONE warp from its load to its last store: the
 // warp keeps it in its private slice of TMEM as accumulator-layout fragments (lane (g, t): rows g and 8 + g, columns 8 j + 2 t + e
@@ -33,7 +33,7 @@ namespace b200d {
 
 #define B200_TLD 20
 #define B200_TSZ (16 * B200_TLD)
-#define B200_PIVOT_WARPS 4
+#define B200_PIVOT_WARPS 5
 __host__ __device__ inline int pipe_ntiles(int n) { const int nb = (n + 15) >> 4; return nb * (nb + 1) / 2; }
 __host__ __device__ inline long long sweep_pipe_smem_doubles(int n, int ld, int nc, int owp) {
     return (long long)n * ld + (long long)pipe_ntiles(n) * B200_TSZ + (((long long)nc * owp + 1) & ~1LL);
@@ -49,8 +49,10 @@ struct RowTile {
 };
 
 // One row tile, start to finish, by the calling warp (all 32 lanes, convergent).  tb: TMEM address of the warp's slice.
+template <int NH>
 __device__ __forceinline__ void stream_row_tile(const Dims& dm, const SweepArgs& a, int i, const RowTile rt, const double* __restrict__ Wt,
-                                                const double* __restrict__ Op, const int* s_orow, const int* s_ozs, const int* s_fk, unsigned tb) {
+                                                const double* __restrict__ Op, const int* s_orow, const int* s_ozs, const int* s_fk, unsigned tb,
+                                                double* Mnext = nullptr) {
     const int n = dm.ntp, nc = dm.nc, ns1 = dm.ns1, hmax = dm.hmax, ow = dm.ow, owp = dm.owp;
     const long long Fsz = (long long)(nc + hmax) * nc;
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -59,15 +61,21 @@ __device__ __forceinline__ void stream_row_tile(const Dims& dm, const SweepArgs&
     const long long st = a.st_idx ? a.st_idx[i] : src;
     const double* Fin = a.F + (long long)(i & 1) * Fsz;
     double* Fout = a.F + (long long)((i + 1) & 1) * Fsz;
-    const bool rv[2] = {g < rt.cr, 8 + g < rt.cr};   // the two row halves of this lane exist
+    const bool rv[2] = {g < rt.cr, NH > 1 && 8 + g < rt.cr};   // the row halves of this lane exist (NH = 1: 8-row tile)
     // ---- k range of the rows of O of this tile (block-sparse coupling): p is zero outside [ka, kb)
     int ka = 0, kb = n;
-    if (rt.seg == 0) xrow_range(dm, s_orow, false, rt.pr0, ka, kb);
+    if (rt.seg == 0) xrow_range(dm, s_orow, false, rt.pr0, ka, kb, rt.cr);
     if (kb <= ka) {   // rows without structure: their fill is zero
         for (int c = 2 * t; c < nc; c += 8)
 #pragma unroll
-            for (int ih = 0; ih < 2; ih++)
-                if (rv[ih]) st2(Fout + (long long)(rt.pr0 + 8 * ih + g) * nc + c, 0.0, 0.0);
+            for (int ih = 0; ih < NH; ih++) {
+                if (!rv[ih]) continue;
+                const int r = rt.pr0 + 8 * ih + g;
+                if (Mnext) {
+                    const double2 d = ld2(a.Dsrc + (src + 1) * n * n + (long long)r * n + c);
+                    st2(Mnext + (long long)r * dm.ld + c, (c <= r) ? d.x + ((c == r) ? a.lambda : 0.0) : 0.0, (c + 1 <= r) ? d.y + ((c + 1 == r) ? a.lambda : 0.0) : 0.0);
+                } else st2(Fout + (long long)r * nc + c, 0.0, 0.0);
+            }
         return;
     }
     const int kb_lo = ka >> 4, kb_hi = (kb - 1) >> 4;
@@ -76,9 +84,9 @@ __device__ __forceinline__ void stream_row_tile(const Dims& dm, const SweepArgs&
         const double* Og = a.Osrc + src * nc * nc;
         for (int j = 2 * kb_lo; j <= 2 * kb_hi + 1; j++) {
             const int c = 8 * j + 2 * t;
-            double v[4];
+            double v[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-            for (int ih = 0; ih < 2; ih++) {
+            for (int ih = 0; ih < NH; ih++) {
                 double2 x = make_double2(0.0, 0.0);
                 if (rv[ih] && c < nc) x = ld2(Og + (long long)(rt.pr0 + 8 * ih + g) * nc + c);   // (nc even: the pair is inside or outside)
                 v[2 * ih] = x.x; v[2 * ih + 1] = x.y;
@@ -94,7 +102,7 @@ __device__ __forceinline__ void stream_row_tile(const Dims& dm, const SweepArgs&
             for (int jj = 0; jj < 2; jj++) {
                 const int c = 8 * (j0 + jj) + 2 * t;
 #pragma unroll
-                for (int ih = 0; ih < 2; ih++) {
+                for (int ih = 0; ih < NH; ih++) {
                     const int ar = ar0 + 8 * ih + g;
                     x[jj][ih] = make_double2(0.0, 0.0); f[jj][ih] = make_double2(0.0, 0.0);
                     if (!rv[ih] || c >= n) continue;
@@ -105,9 +113,9 @@ __device__ __forceinline__ void stream_row_tile(const Dims& dm, const SweepArgs&
             }
 #pragma unroll
             for (int jj = 0; jj < 2; jj++) {
-                double v[4];
+                double v[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-                for (int ih = 0; ih < 2; ih++) { v[2 * ih] = x[jj][ih].x - f[jj][ih].x; v[2 * ih + 1] = x[jj][ih].y - f[jj][ih].y; }
+                for (int ih = 0; ih < NH; ih++) { v[2 * ih] = x[jj][ih].x - f[jj][ih].x; v[2 * ih + 1] = x[jj][ih].y - f[jj][ih].y; }
                 tmem_st4(tb + 8 * (j0 + jj), v);
             }
         }
@@ -136,10 +144,10 @@ __device__ __forceinline__ void stream_row_tile(const Dims& dm, const SweepArgs&
                     if (do0) {
                         const double b0 = t0[kr], b1 = t0[kr + 8];
 #pragma unroll
-                        for (int ih = 0; ih < 2; ih++) { dmma884(acc[ih][0][0], acc[ih][0][1], av[2 * ih + e], b0); dmma884(acc[ih][1][0], acc[ih][1][1], av[2 * ih + e], b1); }
+                        for (int ih = 0; ih < NH; ih++) { dmma884(acc[ih][0][0], acc[ih][0][1], av[2 * ih + e], b0); dmma884(acc[ih][1][0], acc[ih][1][1], av[2 * ih + e], b1); }
                     }
 #pragma unroll
-                    for (int ih = 0; ih < 2; ih++) { dmma884(acc[ih][2][0], acc[ih][2][1], av[2 * ih + e], b2); dmma884(acc[ih][3][0], acc[ih][3][1], av[2 * ih + e], b3); }
+                    for (int ih = 0; ih < NH; ih++) { dmma884(acc[ih][2][0], acc[ih][2][1], av[2 * ih + e], b2); dmma884(acc[ih][3][0], acc[ih][3][1], av[2 * ih + e], b3); }
                 }
             }
         }
@@ -147,13 +155,13 @@ __device__ __forceinline__ void stream_row_tile(const Dims& dm, const SweepArgs&
         for (int q = 0; q < 4; q++) {
             if (q < 2 && !use0) continue;
             const int j = 2 * (q < 2 ? c0 : c1) + (q & 1);
-            double v[4] = {acc[0][q][0], acc[0][q][1], acc[1][q][0], acc[1][q][1]};
+            double v[4] = {acc[0][q][0], acc[0][q][1], NH > 1 ? acc[NH - 1][q][0] : 0.0, NH > 1 ? acc[NH - 1][q][1] : 0.0};
             tmem_st4(tb + 8 * j, v);
             if (rt.seg == 1) {
                 const int c = 8 * j + 2 * t;
                 if (c < n) {
 #pragma unroll
-                    for (int ih = 0; ih < 2; ih++)
+                    for (int ih = 0; ih < NH; ih++)
                         if (rv[ih]) st2(Yg + (long long)(rt.pr0 - rt.xo + 8 * ih + g) * n + c, acc[ih][q][0], acc[ih][q][1]);
                 }
             }
@@ -180,14 +188,14 @@ __device__ __forceinline__ void stream_row_tile(const Dims& dm, const SweepArgs&
                 tmem_ld4(tb + 8 * (2 * kbk + h), av);
                 const double2 b0 = ld2(t0 + 8 * h), b1 = ld2(t0 + 8 * B200_TLD + 8 * h);
 #pragma unroll
-                for (int ih = 0; ih < 2; ih++) {
+                for (int ih = 0; ih < NH; ih++) {
                     dmma884(acc[ih][0][0], acc[ih][0][1], av[2 * ih], b0.x); dmma884(acc[ih][0][0], acc[ih][0][1], av[2 * ih + 1], b0.y);
                     dmma884(acc[ih][1][0], acc[ih][1][1], av[2 * ih], b1.x); dmma884(acc[ih][1][0], acc[ih][1][1], av[2 * ih + 1], b1.y);
                 }
                 if (do1) {
                     const double2 b2 = ld2(t1 + 8 * h), b3 = ld2(t1 + 8 * B200_TLD + 8 * h);
 #pragma unroll
-                    for (int ih = 0; ih < 2; ih++) {
+                    for (int ih = 0; ih < NH; ih++) {
                         dmma884(acc[ih][2][0], acc[ih][2][1], av[2 * ih], b2.x); dmma884(acc[ih][2][0], acc[ih][2][1], av[2 * ih + 1], b2.y);
                         dmma884(acc[ih][3][0], acc[ih][3][1], av[2 * ih], b3.x); dmma884(acc[ih][3][0], acc[ih][3][1], av[2 * ih + 1], b3.y);
                     }
@@ -198,7 +206,7 @@ __device__ __forceinline__ void stream_row_tile(const Dims& dm, const SweepArgs&
         for (int q = 0; q < 4; q++) {
             if (q >= 2 && !use1) continue;
             const int j = 2 * (q < 2 ? c0 : c1) + (q & 1);
-            double v[4] = {acc[0][q][0], acc[0][q][1], acc[1][q][0], acc[1][q][1]};
+            double v[4] = {acc[0][q][0], acc[0][q][1], NH > 1 ? acc[NH - 1][q][0] : 0.0, NH > 1 ? acc[NH - 1][q][1] : 0.0};
             tmem_st4(tb + 8 * j, v);
         }
     }
@@ -208,6 +216,17 @@ __device__ __forceinline__ void stream_row_tile(const Dims& dm, const SweepArgs&
     {
         const int jz_hi = 2 * zc_hi + 1;   // last 8-column block of z that exists
         const int jo_hi = rt.seg == 0 ? ((rt.pr0 + rt.cr - 1) >> 3) : ((nc - 1) >> 3);   // rows of O: lower triangle of the fill only
+        // rows of O with a next node in this chunk: the fill goes STRAIGHT into the pivot buffer, M_next = D_next + lambda I - fill
+        // (lower triangle; zeros above the diagonal), no round trip through global memory and no separate load phase
+        const double* Dn = Mnext ? a.Dsrc + (src + 1) * n * n : nullptr;
+        const int ld = dm.ld;
+        // D_next of output block jo + 1 is fetched while block jo is computed (the L2 latency stays off the chain of fill blocks)
+        double2 dnx[2] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
+        if (Mnext && 2 * t < n) {
+#pragma unroll
+            for (int ih = 0; ih < NH; ih++)
+                if (rv[ih]) dnx[ih] = ld2(Dn + (long long)(rt.pr0 + 8 * ih + g) * n + 2 * t);
+        }
         for (int jo = 0; jo <= jo_hi && 8 * jo < nc; jo++) {
             const int co = 8 * jo + g;
             const bool cok = co < nc;
@@ -216,6 +235,12 @@ __device__ __forceinline__ void stream_row_tile(const Dims& dm, const SweepArgs&
             double f[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
             const int jk0 = s_fk[2 * jo];
             const int jk1 = s_fk[2 * jo + 1] < jz_hi ? s_fk[2 * jo + 1] : jz_hi;
+            const double2 dn[2] = {dnx[0], dnx[1]};
+            if (Mnext && jo + 1 <= jo_hi && 8 * (jo + 1) + 2 * t < n) {
+#pragma unroll
+                for (int ih = 0; ih < NH; ih++)
+                    if (rv[ih]) dnx[ih] = ld2(Dn + (long long)(rt.pr0 + 8 * ih + g) * n + 8 * (jo + 1) + 2 * t);
+            }
             for (int jk = jk0; jk <= jk1; jk++) {
                 double av[4];
                 tmem_ld4(tb + 8 * jk, av);
@@ -223,15 +248,102 @@ __device__ __forceinline__ void stream_row_tile(const Dims& dm, const SweepArgs&
                 double2 b = make_double2(0.0, 0.0);
                 if (cok && off >= 0 && off < ow) b = ld2(orow_p + off);
 #pragma unroll
-                for (int ih = 0; ih < 2; ih++) { dmma884(f[ih][0], f[ih][1], av[2 * ih], b.x); dmma884(f[ih][0], f[ih][1], av[2 * ih + 1], b.y); }
+                for (int ih = 0; ih < NH; ih++) { dmma884(f[ih][0], f[ih][1], av[2 * ih], b.x); dmma884(f[ih][0], f[ih][1], av[2 * ih + 1], b.y); }
             }
             const int cw = 8 * jo + 2 * t;
             if (cw < nc) {
 #pragma unroll
-                for (int ih = 0; ih < 2; ih++)
-                    if (rv[ih]) st2(Fout + (long long)(rt.pr0 + 8 * ih + g) * nc + cw, f[ih][0], f[ih][1]);
+                for (int ih = 0; ih < NH; ih++) {
+                    if (!rv[ih]) continue;
+                    const int r = rt.pr0 + 8 * ih + g;
+                    if (Mnext) {
+                        const double m0 = (cw <= r) ? dn[ih].x + ((cw == r) ? a.lambda : 0.0) - f[ih][0] : 0.0;
+                        const double m1 = (cw + 1 <= r) ? dn[ih].y + ((cw + 1 == r) ? a.lambda : 0.0) - f[ih][1] : 0.0;
+                        st2(Mnext + (long long)r * ld + cw, m0, m1);
+                    } else st2(Fout + (long long)r * nc + cw, f[ih][0], f[ih][1]);
+                }
             }
         }
+        if (Mnext) {   // the rest of the strictly upper part of these rows
+            for (int cw = 8 * (jo_hi + 1) + 2 * t; cw < n; cw += 8)
+#pragma unroll
+                for (int ih = 0; ih < NH; ih++)
+                    if (rv[ih]) st2(Mnext + (long long)(rt.pr0 + 8 * ih + g) * ld + cw, 0.0, 0.0);
+        }
+    }
+}
+
+// Rows [16 j + 8 ih0, +8) of W^T = L^-T from the plain Cholesky factor left in the pivot buffer (strictly lower blocks = L, diagonal
+// tiles = W_cc^T): block forward substitution of an identity row tile, right-looking and entirely in registers,
+//     U[:, j] = W_jj^T;   for k = j, j+1, ...:  T_c += U[:, k] L[c][k]^T for every c > k (independent accumulators),
+//                                               U[:, k+1] = -T_{k+1} W_{k+1,k+1}^T
+// An accumulator fragment is fed back as the A operand through the permuted contraction index (slot t of step (q, e) <->
+// k = 8 q + 2 t + e), so nothing leaves the registers between the steps; the dependent chain is 8 MMAs per column block.
+// Writes the tile layout Wt (all tiles (j, c >= j), zero padded) and the global copy for the back-substitution.
+__device__ __forceinline__ void build_wt_rows(const double* __restrict__ Ms, int ld, int n, int j, int ih0, double* __restrict__ Wt,
+                                              double* __restrict__ Wg) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int nb16 = (n + 15) >> 4;   // <= 8
+    const int lr = 8 * ih0 + g, r = 16 * j + lr;   // this lane's row (local / global)
+    const bool rok = r < n;
+    // zeros left of the diagonal tile (the global copy holds whole rows)
+    if (Wg && rok) for (int c = 2 * t; c < 16 * j; c += 8) st2(Wg + (long long)r * n + c, 0.0, 0.0);
+    double u[2][2];   // current column block: fragment (q = 8-column half, e)
+#pragma unroll
+    for (int q = 0; q < 2; q++) {   // U[:, j] = W_jj^T: upper triangle incl. the diagonal of the diagonal tile
+        const int c = 16 * j + 8 * q + 2 * t;
+        double2 v = make_double2(0.0, 0.0);
+        if (rok && c < n) { v = ld2(Ms + (long long)r * ld + c); if (c < r) v.x = 0.0; if (c + 1 < r) v.y = 0.0; }
+        u[q][0] = v.x; u[q][1] = v.y;
+    }
+    double T[8][2][2];
+#pragma unroll
+    for (int c = 0; c < 8; c++) { T[c][0][0] = 0.0; T[c][0][1] = 0.0; T[c][1][0] = 0.0; T[c][1][1] = 0.0; }
+    for (int k = j; k < nb16; k++) {
+        // store block k: tile layout, global copy
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int cc = 16 * k + 8 * q + 2 * t;
+            const bool in = rok && cc < n;
+            st2(Wt + tile_off(j, k) + lr * B200_TLD + 8 * q + 2 * t, in ? u[q][0] : 0.0, in ? u[q][1] : 0.0);
+            if (Wg && in) st2(Wg + (long long)r * n + cc, u[q][0], u[q][1]);
+        }
+        if (k + 1 >= nb16) break;
+        // T_c += U[:, k] L[c][k]^T, c > k   (B[slot][nn] = L[16 c + nn][16 k + 8 q + 2 t + e])
+#pragma unroll
+        for (int c = 1; c < 8; c++) {
+            if (c > k && c < nb16) {
+                const int rb0 = 16 * c + g, rb1 = 16 * c + 8 + g;
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const int kc = 16 * k + 8 * q + 2 * t;
+                    const double2 b0 = rb0 < n ? ld2(Ms + (long long)rb0 * ld + kc) : make_double2(0.0, 0.0);
+                    const double2 b1 = rb1 < n ? ld2(Ms + (long long)rb1 * ld + kc) : make_double2(0.0, 0.0);
+                    dmma884(T[c][0][0], T[c][0][1], u[q][0], b0.x); dmma884(T[c][0][0], T[c][0][1], u[q][1], b0.y);
+                    dmma884(T[c][1][0], T[c][1][1], u[q][0], b1.x); dmma884(T[c][1][0], T[c][1][1], u[q][1], b1.y);
+                }
+            }
+        }
+        // U[:, k+1] = -T_{k+1} W_cc^T, cc = k + 1   (A: T fragments; B[slot][nn] = W_cc^T[8 q + 2 t + e][nn])
+        double tk[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+        for (int c = 1; c < 8; c++)
+            if (c == k + 1) { tk[0][0] = T[c][0][0]; tk[0][1] = T[c][0][1]; tk[1][0] = T[c][1][0]; tk[1][1] = T[c][1][1]; }
+        double o[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        const int cb = 16 * (k + 1);
+#pragma unroll
+        for (int q = 0; q < 2; q++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int kr = cb + 8 * q + 2 * t + e;
+                const int cc0 = cb + g, cc1 = cb + 8 + g;
+                const double b0 = (kr < n && cc0 < n && cc0 >= kr) ? Ms[(long long)kr * ld + cc0] : 0.0;
+                const double b1 = (kr < n && cc1 < n && cc1 >= kr) ? Ms[(long long)kr * ld + cc1] : 0.0;
+                dmma884(o[0][0], o[0][1], tk[q][e], b0);
+                dmma884(o[1][0], o[1][1], tk[q][e], b1);
+            }
+#pragma unroll
+        for (int q = 0; q < 2; q++) { u[q][0] = -o[q][0]; u[q][1] = -o[q][1]; }
     }
 }
 
@@ -276,47 +388,25 @@ __device__ void cta_sweep_pipe(const Dims& dm, const SweepArgs& a, double* sm) {
     // ---- pivot block of node j: M = D - fill (lower triangle), fused Cholesky + inverse.  Executed by the pivot group only.
     auto factor_node = [&](int j) {
         const long long src = a.src0 + j;
-        const double* Fin = a.F + (long long)(j & 1) * Fsz;
-        const double* Dg = a.Dsrc + src * n * n;
-        for (int r = gw; r < n; r += gnw)
-            for (int c2 = lane; 2 * c2 <= r; c2 += 32) cp_async16(Ms + (long long)r * ld + 2 * c2, Dg + (long long)r * n + 2 * c2);
-        if (j + 1 < a.n) {
-            const double* Dn = a.Dsrc + (src + 1) * n * n;
-            for (int e = gtid * 16; e < n * n; e += gthreads * 16) prefetch_l2(Dn + e);
-        }
-        for (int rb = 0; rb < n; rb += 8 * gnw) {
-            for (int cb = 0; cb < n; cb += 128) {
-                double f[8][4];
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    const int r = rb + gw + q * gnw;
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int c = cb + lane + 32 * u;
-                        f[q][u] = (j > 0 && r < n && c <= r) ? Fin[(long long)r * nc + c] : 0.0;
+        if (j == 0) {   // first node of the chunk: M = D + lambda I from global memory (later nodes: written in place by the rows of O)
+            const double* Dg = a.Dsrc + src * n * n;
+            for (int r = gw; r < n; r += gnw)
+                for (int c = 2 * lane; c < n; c += 64) {
+                    double2 v = make_double2(0.0, 0.0);
+                    if (c <= r) {
+                        v = ld2(Dg + (long long)r * n + c);
+                        if (c == r) v.x += a.lambda;
+                        if (c + 1 == r) v.y += a.lambda;
+                        if (c + 1 > r) v.y = 0.0;
                     }
+                    st2(Ms + (long long)r * ld + c, v.x, v.y);
                 }
-                if (rb == 0 && cb == 0) { cp_async_wait_all(); GSYNC(); }
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    const int r = rb + gw + q * gnw;
-                    if (r >= n) continue;
-                    double* row = Ms + (long long)r * ld;
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const int c = cb + lane + 32 * u;
-                        if (c >= n) continue;
-                        if (c > r) row[c] = 0.0;
-                        else row[c] = row[c] + ((c == r) ? a.lambda : 0.0) - f[q][u];
-                    }
-                }
-            }
         }
         GSYNC();
 #ifdef B200_PHASE_CLOCKS
         if (threadIdx.x == 0 && blockIdx.x == 1 && j > 0) { unsigned long long n_ = clock64(); g_phase_clk[3] += n_ - pp_t; pp_t = n_; }
 #endif
-        const int fail = cta_chol_inv(Ms, ld, n, gw, gnw, 7);
+        const int fail = cta_chol_inv(Ms, ld, n, gw, gnw, 7, true);
         if (fail && gtid == 0) {
             const long long st = a.st_idx ? a.st_idx[j] : src;
             atomicCAS(a.status, 0, (int)(st + 1));
@@ -342,32 +432,10 @@ __device__ void cta_sweep_pipe(const Dims& dm, const SweepArgs& a, double* sm) {
         __syncthreads();   // [A] W_i^T complete in Ms; the arrow rows of node i-1 are done (Wt, Op free)
         PP_ADD(0, 0); PP_ADD(5, 256);
         if (s_abort) break;
-        // ---- S2: W^T -> tile layout (zero padded to whole tiles) + global store; packed rows of O
+        // ---- S2: W^T = L^-T row tiles by forward substitution (two warps per 16-row tile) -> tile layout + global store; packed rows of O
         {
             double* Wg = a.Wst + st * n * n;
-            const int nt = pipe_ntiles(n);
-            for (int e = threadIdx.x; e < nt * 128; e += blockDim.x) {   // 128 pairs per tile
-                const int tile = e >> 7, w = e & 127, tr = w >> 3, tc2 = (w & 7) << 1;
-                int cb = 0;
-                while ((cb + 1) * (cb + 2) / 2 <= tile) cb++;
-                const int kb = tile - cb * (cb + 1) / 2;
-                const int r = (kb << 4) + tr, c = (cb << 4) + tc2;
-                double2 v = make_double2(0.0, 0.0);
-                if (r < n && c < n) {   // (n is even: the pair is inside or outside)
-                    v = ld2(Ms + (long long)r * ld + c);
-                    if (c < r) v.x = 0.0;          // what is left of L below the diagonal is not part of W^T
-                    if (c + 1 < r) v.y = 0.0;
-                }
-                st2(Wt + tile * B200_TSZ + tr * B200_TLD + tc2, v.x, v.y);
-            }
-            if (a.lead) {
-                for (int r = warp; r < n; r += 16)
-                    for (int c = 2 * lane; c < n; c += 64) {
-                        double2 v = ld2(Ms + (long long)r * ld + c);
-                        if (c < r) { v.x = 0.0; if (c + 1 < r) v.y = 0.0; }
-                        st2(Wg + (long long)r * n + c, v.x, v.y);
-                    }
-            }
+            const int nbt = (n + 15) >> 4;
             if (has_x) {
                 const double* Og = a.Osrc + src * nc * nc;
                 for (int e = threadIdx.x; e < nc * ow; e += blockDim.x) {
@@ -377,21 +445,18 @@ __device__ void cta_sweep_pipe(const Dims& dm, const SweepArgs& a, double* sm) {
                     else Op[r * owp + t] = 0.0;
                 }
             }
-            {
-                const double* Ag = a.Asrc + src * ns1 * n;
-                for (int e = threadIdx.x * 16; e < ns1 * n; e += blockDim.x * 16) prefetch_l2(Ag + e);
-            }
+            for (int task = warp; task < 2 * nbt; task += 16) build_wt_rows(Ms, ld, n, task >> 1, task & 1, Wt, a.lead ? Wg : nullptr);
             cp_async_wait_all();
         }
         __syncthreads();   // [B] Wt / Op complete, Ms free
         PP_ADD(1, 0); PP_ADD(16, 256);
         // ---- S1: rows of O (they feed the next pivot block): one 16-row tile per warp
         if (has_x) {
-            const int ntile = (nc + 15) >> 4;
+            const int ntile = (nc + 7) >> 3;   // 8-row tiles: 14 tasks for the 16 warps
             for (int tl = warp; tl < ntile; tl += 16) {
                 RowTile rt;
-                rt.seg = 0; rt.pr0 = tl << 4; rt.cr = (nc - rt.pr0 < 16) ? (nc - rt.pr0) : 16; rt.xo = xo; rt.has_x = true;
-                stream_row_tile(dm, a, i, rt, Wt, Op, s_orow, s_ozs, s_fk, tb);
+                rt.seg = 0; rt.pr0 = tl << 3; rt.cr = (nc - rt.pr0 < 8) ? (nc - rt.pr0) : 8; rt.xo = xo; rt.has_x = true;
+                stream_row_tile<1>(dm, a, i, rt, Wt, Op, s_orow, s_ozs, s_fk, tb, (i + 1 < a.n) ? Ms : nullptr);
             }
         }
         __threadfence_block();
@@ -404,7 +469,17 @@ __device__ void cta_sweep_pipe(const Dims& dm, const SweepArgs& a, double* sm) {
             for (int tl = warp - gnw; tl < ntile; tl += 16 - gnw) {
                 RowTile rt;
                 rt.seg = 1; rt.pr0 = xo + a.ar_lo + (tl << 4); rt.cr = (cnt - (tl << 4) < 16) ? (cnt - (tl << 4)) : 16; rt.xo = xo; rt.has_x = has_x;
-                stream_row_tile(dm, a, i, rt, Wt, Op, s_orow, s_ozs, s_fk, tb);
+                stream_row_tile<2>(dm, a, i, rt, Wt, Op, s_orow, s_ozs, s_fk, tb);
+            }
+            // idle until the pivot group is done: pull the sources of the next nodes towards L2 (pivot block of node i + 2 for the
+            // rows of O of node i + 1, arrow rows and coupling block of node i + 1)
+            {
+                const int pt = threadIdx.x - gthreads, pn = blockDim.x - gthreads;
+                if (i + 2 < a.n) { const double* Dn = a.Dsrc + (src + 2) * n * n; for (int e = pt * 16; e < n * n; e += pn * 16) prefetch_l2(Dn + e); }
+                if (i + 1 < a.n) {
+                    const double* An = a.Asrc + (src + 1) * ns1 * n; for (int e = pt * 16; e < ns1 * n; e += pn * 16) prefetch_l2(An + e);
+                    const double* On = a.Osrc + (src + 1) * nc * nc; for (int e = pt * 16; e < nc * nc; e += pn * 16) prefetch_l2(On + e);
+                }
             }
             __threadfence_block();
             PP_ADD(6, 256);
