@@ -223,7 +223,8 @@ def run_b200(args):
         from bioslam_b200 import sharding
         # N GPUs = G lambda groups x T time shards: the groups try consecutive rungs of the LM lambda ladder concurrently
         # (exactly the sequential tryLambda results), each group shards the time axis over its T ranks
-        lam_groups = args.lambda_groups if args.lambda_groups > 0 else (2 if world % 2 == 0 else 1)
+        # measured on 8 B200 (profiles/README.md): 4 x 2 136 iter/s, 2 x 4 130, 8 x 1 116; on 4: 2 x 2; on 2: 2 x 1 84 against 1 x 2 70
+        lam_groups = args.lambda_groups if args.lambda_groups > 0 else (4 if world % 8 == 0 else (2 if world % 2 == 0 else 1))
         comm = sharding.attach(p, dist, local, lambda_groups=lam_groups) if args.comm == "torch" else sharding.attach_nccl(p, dist, lambda_groups=lam_groups)
     else:
         lam_groups, comm = 1, None
@@ -334,6 +335,7 @@ def run_b200(args):
         ncu = json.load(open(tpath))
         traffic = ncu.get("dram_bytes_per_launch")
     solve_ms = ph[1] / max(trials_attr, 1)
+    ntr = max(ph[6], 1)   # lambda trials solved by this rank's group in the attribution pass (one top-level launch each)
     line = {
         "metric": "lm_iterations_per_sec", "value": value, "unit": "iter/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -348,7 +350,15 @@ def run_b200(args):
                              "lambda_trials": trials_attr,
                              "phase_ms_per_step": {"linearize+assemble": ph[0] / args.steps, "solve": ph[1] / args.steps, "model+retract+error": ph[2] / args.steps},
                              "solve_ms_per_trial": solve_ms, "sweep_level0_ms": sweep_ms, "top_level_ms": ph[5] / max(ph[6], 1),
-                             "backsub_ms": ph[7] / max(ph[4], 1)},
+                             "backsub_ms": ph[7] / max(ph[4], 1),
+                             "solve_ms_per_trial_split": {"local_elimination": ph[8] / ntr, "level0_sweep": ph[3] / ntr,
+                                                          "level0_schur+boundary_exchange+reduce": ph[9] / ntr, "level1": ph[10] / ntr,
+                                                          "levels>=2": ph[11] / ntr, "top_level+static_system": ph[5] / ntr,
+                                                          "back_substitution+step_exchange": ph[7] / ntr}},
+        # N > 1: what does not shrink with the number of time shards (computed redundantly on every rank of a group) and the device time of the
+        # collectives, per lambda trial solved by this rank's group (attribution pass, every exchange group bracketed by CUDA events)
+        "replicated_ms_per_trial": (ph[11] + ph[5]) / ntr,
+        "nccl_ms_per_trial": (comm_ms["device_ms"] / ntr) if comm_ms is not None else 0.0,
         "roofline": {"bound": "tensor", "kernel": kern, "achieved": achieved_tf, "peak": tpeak, "unit": "TFLOP/s", "frac": achieved_tf / tpeak,
                      "traffic": traffic, "peak_source": tpeak_src, "launch_ms": sweep_ms,
                      "flops_per_launch": units_rank * SWEEP_FLOP_PER_KEYFRAME,
@@ -377,6 +387,93 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_batch(args):
+    """BASELINE.json configs[4]: a batch of independent synthetic subjects (60 s each, K = 600, seeds 0..B-1), every one optimised to the
+    reference's convergence rule (b200_optimize) from the reference's initial values.  SURVEY.md section 8(e): replicas only -- the
+    subjects are dealt round-robin to the ranks (one process per GPU), no data-path collective; on a GPU `--concurrent` host threads
+    each drive their own b200_problem on its own CUDA stream.  Host buffers in and out per solve (values uploaded, optimised values
+    downloaded): `value` and `e2e` are the same measurement.  metric: converged solves per second, whole job."""
+    import queue
+    import torch
+    from bioslam_b200 import abi, graphs, lib, synth
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: bioslam_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    json_fd = 1
+    if world > 1:
+        sys.stdout.flush(); json_fd = os.dup(1); os.dup2(2, 1)
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib.load()
+    B = args.subjects
+    mine = list(range(rank, B, world))
+    pre = lambda a, w, dt, n, bh: lib.preintegrate(a, w, dt, n, bh, device=local)
+    inputs = {i: graphs.lower_body_graph(synth.make_trial(seed=i, duration_s=60.0), preint=pre) for i in mine}
+    lm, outer = abi.LmParams.lower_body(), abi.OuterParams.lower_body(max_iterations=args.converge_max if args.converge_max > 0 else 3000)
+    g0, tv0, sv0 = next(iter(inputs.values()))
+    for _ in range(max(args.warmup, 1)):   # warm-up: module load, graph instantiation, first-launch costs
+        p = lib.Problem(g0, device=local); p.set_values(tv0, sv0); p.lm_begin(lm); p.lm_iterate(); p.close()
+    results = {}
+    work = queue.Queue()
+    for i in mine: work.put(i)
+    launches = [0]
+
+    def worker():
+        torch.cuda.set_device(local)
+        while True:
+            try:
+                i = work.get_nowait()
+            except queue.Empty:
+                return
+            g, tv, sv = inputs[i]
+            p = lib.Problem(g, device=local); p.set_values(tv, sv)
+            res, _ = p.optimize(lm, outer)
+            tvf, svf = p.get_values()
+            results[i] = (int(res.iterations), int(res.total_trials), float(res.final_error), float(res.device_ms), int(res.status))
+            launches[0] += p.launch_count()
+            p.close()
+
+    if dist is not None: dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local); sampler.start()
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=worker) for _ in range(args.concurrent)]
+    for t in ths: t.start()
+    for t in ths: t.join()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clocks = sampler.summary()
+    if dist is not None:
+        tt = torch.tensor([wall], dtype=torch.float64, device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); wall = float(tt.item())
+        gathered = [None] * world
+        dist.all_gather_object(gathered, results)
+        results = {k: v for d in gathered for k, v in d.items()}
+        dist.barrier()
+    if rank == 0:
+        g = g0
+        its = [results[i][0] for i in range(B)]
+        line = {"metric": "converged_solves_per_sec", "value": B / wall, "unit": "solves/s", "n_gpus": world, "steps": B, "warmup": max(args.warmup, 1),
+                "ms_per_step": wall / B * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "batch_60s_100hz_7imu", "baseline_config": "configs[4]", "subjects": B, "keyframes": g.K, "unknowns": g.nt * g.K + g.ns,
+                           "parallelism": f"replicas only: {world} rank(s) x {args.concurrent} concurrent problems (one CUDA stream each), no collective",
+                           "rule": "6 consecutive iterations with abs<1e-6 or rel<1e-5 decrease (reference exit rule)",
+                           "cache": "independent problems of ~0.25 GB each; concurrent working sets exceed L2"},
+                "iterations": {"min": min(its), "max": max(its), "mean": float(np.mean(its))},
+                "lambda_trials_total": int(sum(results[i][1] for i in range(B))), "all_converged": all(results[i][4] == 0 for i in range(B)),
+                "mean_device_s_per_solve": float(np.mean([results[i][3] for i in range(B)])) * 1e-3,
+                "final_error_range": [min(results[i][2] for i in range(B)), max(results[i][2] for i in range(B))],
+                "e2e": {"value": B / wall, "unit": "solves/s", "h2d_bytes_per_step": int(tv0.nbytes + sv0.nbytes), "d2h_bytes_per_step": int(tv0.nbytes + sv0.nbytes)},
+                "gpu_launches": int(launches[0]), "clocks": clocks}
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -384,13 +481,19 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="gait_10min_100hz_7imu", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="gait_10min_100hz_7imu", choices=sorted(WORKLOADS) + ["batch_60s_100hz_7imu"])
+    ap.add_argument("--subjects", type=int, default=64, help="batch workload: number of independent subjects (BASELINE configs[4]: 64)")
+    ap.add_argument("--concurrent", type=int, default=8, help="batch workload: problems in flight per GPU (host threads, one CUDA stream each)")
     ap.add_argument("--comm", default="nccl", choices=["nccl", "torch"], help="N > 1: NCCL inside the library (default) or torch.distributed callbacks")
     ap.add_argument("--chunks", type=int, default=None, help="solver partition (default: library heuristic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--converge-max", type=int, default=3000, help="iteration cap of the time-to-converge run (0: skip it)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "batch_60s_100hz_7imu":
+        if args.impl == "reference":
+            raise SystemExit("the CPU arm of the batch workload is the single-subject CPU arm (--workload gait_60s_100hz_7imu) times the subject count")
+        run_batch(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)

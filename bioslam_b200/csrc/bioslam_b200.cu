@@ -15,6 +15,13 @@
 #ifndef B200_USE_EMU
 #include <dlfcn.h>
 #include <nccl.h>   // types and prototypes only: the entry points are resolved with dlsym, so the library loads without NCCL
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges around linearize / solve levels / retract (no cost without a profiler)
+struct NvtxRange { explicit NvtxRange(const char* n) { nvtxRangePushA(n); } ~NvtxRange() { nvtxRangePop(); } };
+#define B200_NVTX_CAT2(a, b) a##b
+#define B200_NVTX_CAT(a, b) B200_NVTX_CAT2(a, b)
+#define B200_NVTX(name) NvtxRange B200_NVTX_CAT(nvtx_range_, __LINE__)(name)
+#else
+#define B200_NVTX(name)
 #endif
 
 using namespace b200d;
@@ -179,8 +186,9 @@ struct b200_problem {
 #endif
     long long graph_launches = 0;  // kernels inside one trial graph
     cudaEvent_t ev[16] = {};
-    cudaEvent_t tev[4][8] = {};    // per queued trial: phase events (TE_*)
-    double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // lin, solve, retract+error, sweep ms, sweep launches, top ms, top launches, backsub ms
+    cudaEvent_t tev[4][12] = {};   // per queued trial: phase events (TE_*)
+    double phase_ms[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // lin, solve, retract+error, sweep ms, sweep launches, top ms, top launches, backsub ms,
+                                                                 // local elimination, level-0 Schur + boundary exchange + reduce, level 1, levels >= 2
     std::vector<float> pending;
     bool time_phases = false;
     // sharding (time axis): this rank owns chunks [c_lo, c_hi) == keyframes [k_lo, k_hi)
@@ -853,6 +861,7 @@ static void launch_error(b200_problem* p, const double* tv, const double* sv, do
 }
 
 static void launch_linearize(b200_problem* p) {
+    B200_NVTX("linearize + assemble");
     dim3 grid((p->max_inst + 127) / 128, p->n_slots);
     // Jacobians are needed one keyframe to the left of the window (the IMU factor k_lo-1 -> k_lo feeds D[k_lo])
     B200_LAUNCH(linearize_kernel<true>, grid, dim3(128), 0, p->stream, p->d_slots, p->d_tv, p->d_sv, p->d_cst, p->dm.Kld, p->d_J, p->d_r,
@@ -932,8 +941,9 @@ static void launch_level_backsub(b200_problem* p, const b200_problem::HostLevel&
 
 // (H + lambda I) delta = -g with lambda = *sb.lam (device scalar): local elimination, nested partitioned factorisation,
 // back-substitution, all on p->stream.  tev != nullptr: phase events of this trial slot (direct launches only, not under capture).
-enum { TE_SOLVE0 = 0, TE_SWEEP0, TE_SWEEP1, TE_TOP0, TE_TOP1, TE_BACK1, TE_SOLVE1, TE_TRIAL1, TE_COUNT };
+enum { TE_SOLVE0 = 0, TE_SWEEP0, TE_SWEEP1, TE_TOP0, TE_TOP1, TE_BACK1, TE_SOLVE1, TE_TRIAL1, TE_L0DONE, TE_L1DONE, TE_COUNT };
 static b200_status launch_solve(b200_problem* p, cudaEvent_t* tev) {
+    B200_NVTX("solve");
     CK(cudaMemsetAsync(p->sb.status, 0, sizeof(int), p->stream));
     const Dims& dm = p->ds;
     const int W = p->world, r = p->rank;
@@ -945,6 +955,7 @@ static b200_status launch_solve(b200_problem* p, cudaEvent_t* tev) {
     }
     if (tev) CK(cudaEventRecord(tev[TE_SWEEP0], p->stream));
     if (nlev >= 1) {
+        B200_NVTX("solve: level 0 (keyframes)");
         auto& l0 = p->levels[0];
         B200_LAUNCH(chain_sweep_kernel<false>, dim3(l0.c_hi - l0.c_lo), dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, dm, l0.dev, p->sb, l0.c_lo);
         p->launches++;
@@ -974,7 +985,9 @@ static b200_status launch_solve(b200_problem* p, cudaEvent_t* tev) {
             p->launches++;
         }
     } else if (tev) CK(cudaEventRecord(tev[TE_SWEEP1], p->stream));
+    if (tev) { CK(cudaEventRecord(tev[TE_L0DONE], p->stream)); if (nlev < 2) CK(cudaEventRecord(tev[TE_L1DONE], p->stream)); }
     for (int li = 1; li < nlev; li++) {
+        B200_NVTX(li == 1 ? "solve: level 1 (separators, rank-aligned)" : "solve: level >= 2 (replicated)");
         auto& l0 = p->levels[0];
         auto& l1 = p->levels[li];
         launch_level_factor(p, l1.dev, l1.c_lo, l1.c_hi);
@@ -994,12 +1007,17 @@ static b200_status launch_solve(b200_problem* p, cudaEvent_t* tev) {
         }
         B200_LAUNCH(chain_reduce_kernel, dim3(l1.P - 1, 8), dim3(256), 0, p->stream, dm, l1.dev, 0, p->sb.skip);
         p->launches++;
+        if (tev && li == 1) CK(cudaEventRecord(tev[TE_L1DONE], p->stream));
     }
     if (tev) CK(cudaEventRecord(tev[TE_TOP0], p->stream));
+    {
+    B200_NVTX("solve: top level + static system");
     launch_level_factor(p, p->top, 0, 1);
     B200_LAUNCH(top_finish_kernel, dim3(1), dim3(B200_SOLVE_THREADS), p->smem_backsub, p->stream, dm, p->top, p->sb);
     p->launches++;
+    }
     if (tev) CK(cudaEventRecord(tev[TE_TOP1], p->stream));
+    B200_NVTX("solve: back-substitution");
     for (int li = nlev - 1; li >= 0; li--) launch_level_backsub(p, p->levels[li]);
     if (p->use_le) {
         B200_LAUNCH(local_backsub_kernel, dim3(p->k_hi - p->k_lo), dim3(128), 0, p->stream, p->le, p->k_lo, p->k_hi, p->sb.delta, p->sb.dstat, p->d_delta,
@@ -1074,6 +1092,7 @@ b200_status b200_lm_begin(b200_problem* p, const b200_lm_params* prm, double* in
 
 // retract (values + delta -> try buffers): time variables of every keyframe, then the statics
 static void launch_retract(b200_problem* p, const double* delta, const double* dstat, const int* skip = nullptr) {
+    B200_NVTX("retract");
     B200_LAUNCH(retract_kernel, dim3((p->K + 127) / 128, 1, p->ntv), dim3(128), 0, p->stream, p->d_tvars, p->ntv, p->d_svars, p->nsv, p->K,
                 p->dm.Kld, p->d_tv, p->d_sv, delta, p->dm.ntp, dstat, p->d_tv_try, p->d_sv_try, skip);
     p->launches++;
@@ -1193,6 +1212,10 @@ static void accumulate_phase_ms(b200_problem* p, cudaEvent_t* tev) {
         cudaEventElapsedTime(&ms, tev[TE_TOP1], tev[TE_BACK1]); p->phase_ms[7] += ms;
     }
     cudaEventElapsedTime(&ms, tev[TE_TOP0], tev[TE_TOP1]); p->phase_ms[5] += ms; p->phase_ms[6] += 1;
+    cudaEventElapsedTime(&ms, tev[TE_SOLVE0], tev[TE_SWEEP0]); p->phase_ms[8] += ms;
+    cudaEventElapsedTime(&ms, tev[TE_SWEEP1], tev[TE_L0DONE]); p->phase_ms[9] += ms;
+    cudaEventElapsedTime(&ms, tev[TE_L0DONE], tev[TE_L1DONE]); p->phase_ms[10] += ms;
+    cudaEventElapsedTime(&ms, tev[TE_L1DONE], tev[TE_TOP0]); p->phase_ms[11] += ms;
 }
 
 // == LevenbergMarquardtOptimizer::iterate() (gtsam @4.2: iterate / tryLambda / increaseLambda / decreaseLambda)
@@ -1204,6 +1227,7 @@ static void accumulate_phase_ms(b200_problem* p, cudaEvent_t* tev) {
 // sequential loop would have met them: the accepted step, the final lambda and the trial count are those of the sequential algorithm.
 b200_status b200_lm_iterate(b200_problem* p, b200_lm_state* state) {
     if (!p || !p->lm_started) return B200_BAD_ARG;
+    B200_NVTX("b200_lm_iterate");
     CK(cudaSetDevice(p->device));
     const b200_lm_params& L = p->lm;
     if (p->err_stale) {   // b200_set_values since the last cost evaluation: refresh the cost the trials are judged against
@@ -1388,11 +1412,11 @@ b200_status b200_optimize(b200_problem* p, const b200_lm_params* lm, const b200_
     return st;
 }
 
-b200_status b200_phase_ms(b200_problem* p, double out[8], int32_t reset) {
+b200_status b200_phase_ms(b200_problem* p, double out[12], int32_t reset) {
     if (!p) return B200_BAD_ARG;
     if (reset >= 0) p->time_phases = true;   // reset < 0: read without switching the per-phase events on
-    if (out) for (int i = 0; i < 8; i++) out[i] = p->phase_ms[i];
-    if (reset > 0) for (int i = 0; i < 8; i++) p->phase_ms[i] = 0;
+    if (out) for (int i = 0; i < 12; i++) out[i] = p->phase_ms[i];
+    if (reset > 0) for (int i = 0; i < 12; i++) p->phase_ms[i] = 0;
     return B200_OK;
 }
 

@@ -163,7 +163,7 @@ class Problem:
         return int(self.L.b200_launch_count(self.h))
 
     def phase_ms(self, reset=False):
-        out = (C.c_double * 8)()
+        out = (C.c_double * 12)()
         self._ck(self.L.b200_phase_ms(self.h, out, C.c_int32(1 if reset else 0)))
         return list(out)
 

@@ -351,9 +351,11 @@ b200_status b200_debug_get_scalars(b200_problem* p, double out[4]);
 int64_t b200_launch_count(const b200_problem* p);
 /* device time (CUDA events on the problem's stream) since the last reset.  out[0] linearize+assemble ms, out[1] solve ms,
  * out[2] model-error+retract+error ms, out[3] chain_sweep_kernel ms, out[4] chain_sweep_kernel launches,
- * out[5] top_solve_kernel ms, out[6] top_solve_kernel launches, out[7] chain_backsub_kernel ms.
+ * out[5] top_solve_kernel ms, out[6] top_solve_kernel launches, out[7] chain_backsub_kernel ms, out[8] local elimination ms,
+ * out[9] level-0 Schur complement + window-boundary exchange + reduce ms, out[10] level 1 (rank-aligned separators) ms,
+ * out[11] levels >= 2 (computed redundantly on every rank of a time-sharded group) ms.
  * The first call switches the per-phase events on. */
-b200_status b200_phase_ms(b200_problem* p, double out[8], int32_t reset);
+b200_status b200_phase_ms(b200_problem* p, double out[12], int32_t reset);
 /* runtime switches of the LM driver (b200_lm_iterate): "graph" 0/1 -- every lambda trial is one instantiated CUDA graph (default
  * 1, single rank); "spec_trials" 1..4 -- lambda trials queued on the device per host synchronisation (default 2: the accept /
  * reject / damping decisions are taken on the device by lm_judge_kernel, trials queued behind an accepted one return at once);
