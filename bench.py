@@ -430,7 +430,9 @@ def run_batch(args):
             except queue.Empty:
                 return
             g, tv, sv = inputs[i]
-            p = lib.Problem(g, device=local); p.set_values(tv, sv)
+            # --chunks: level-0 partition per problem (upper levels from the cost model).  The library default spreads ONE problem over
+            # all 148 SMs; problems that run side by side do better with 148 / concurrent chunks each (longer chains, fewer separators)
+            p = lib.Problem(g, device=local, chunks=args.chunks, groups=0 if args.chunks else None); p.set_values(tv, sv)
             res, _ = p.optimize(lm, outer)
             tvf, svf = p.get_values()
             results[i] = (int(res.iterations), int(res.total_trials), float(res.final_error), float(res.device_ms), int(res.status))
@@ -459,7 +461,7 @@ def run_batch(args):
         line = {"metric": "converged_solves_per_sec", "value": B / wall, "unit": "solves/s", "n_gpus": world, "steps": B, "warmup": max(args.warmup, 1),
                 "ms_per_step": wall / B * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "batch_60s_100hz_7imu", "baseline_config": "configs[4]", "subjects": B, "keyframes": g.K, "unknowns": g.nt * g.K + g.ns,
-                           "parallelism": f"replicas only: {world} rank(s) x {args.concurrent} concurrent problems (one CUDA stream each), no collective",
+                           "parallelism": f"replicas only: {world} rank(s) x {args.concurrent} concurrent problems (one CUDA stream each), no collective", "chunks_per_problem": args.chunks,
                            "rule": "6 consecutive iterations with abs<1e-6 or rel<1e-5 decrease (reference exit rule)",
                            "cache": "independent problems of ~0.25 GB each; concurrent working sets exceed L2"},
                 "iterations": {"min": min(its), "max": max(its), "mean": float(np.mean(its))},
