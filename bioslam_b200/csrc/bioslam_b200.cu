@@ -595,6 +595,7 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
         if (ds.pipe) {
             const size_t need = sizeof(double) * (size_t)sweep_pipe_smem_doubles(ds.ntp, ds.ld, ds.nc, ds.owp);
             if (need <= smem_cap) p->smem_sweep = std::max(p->smem_sweep, need); else ds.pipe = 0;
+            if (ds.pipe && std::getenv("B200_NO_DENSE_STREAM")) ds.pipe = 2;   // (development switch: level 0 pipelined, dense levels on the round-1 kernel)
         }
         // back-substitution / top level: factor block + vectors; the static system (ns1 x lds) reuses the block area
         const size_t bs = (size_t)backsub_smem_doubles(ds.ntp, ds.ld);

@@ -35,6 +35,9 @@ __device__ __forceinline__ void tmem_fence_after_sync() {}
 __device__ __forceinline__ void tmem_wait_st() {}
 __device__ __forceinline__ void tmem_st4(unsigned taddr, const double (&v)[4]) { std::memcpy(emu::tmem_cell((int)(taddr >> 16) + emu::lane_id(), (int)(taddr & 0xffffu)), v, 32); }
 __device__ __forceinline__ void tmem_ld4(unsigned taddr, double (&v)[4]) { std::memcpy(v, emu::tmem_cell((int)(taddr >> 16) + emu::lane_id(), (int)(taddr & 0xffffu)), 32); }
+struct TmemRaw { int r[8]; };
+__device__ __forceinline__ void tmem_ld4_issue(unsigned taddr, TmemRaw& raw) { std::memcpy(raw.r, emu::tmem_cell((int)(taddr >> 16) + emu::lane_id(), (int)(taddr & 0xffffu)), 32); }
+__device__ __forceinline__ void tmem_ld4_wait(TmemRaw& raw, double (&v)[4]) { std::memcpy(v, raw.r, 32); }
 #else
 // fp64 tensor-core MMA (DMMA on sm_100a): C(8 x 8) += A(8 x 4) B(4 x 8).  Lane (g = lane >> 2, t = lane & 3) supplies A[g][t] and
 // B[t][g] and owns C[g][2t], C[g][2t+1].  IEEE fp64 fused multiply-adds: same rounding class as the scalar DFMA path.
@@ -83,5 +86,19 @@ __device__ __forceinline__ void tmem_ld4(unsigned taddr, double (&v)[4]) {
                  "=r"(r6), "=r"(r7) : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     v[0] = __hiloint2double(r1, r0); v[1] = __hiloint2double(r3, r2); v[2] = __hiloint2double(r5, r4); v[3] = __hiloint2double(r7, r6);
+}
+// the same in two halves, for software pipelining: the load of the NEXT fragment is in flight while the MMAs of the current one
+// issue.  The destination registers are outputs of the issue statement and in/out operands of the wait statement, so the compiler
+// can neither read nor move them in between (tcgen05.ld writes them asynchronously until tcgen05.wait::ld).
+struct TmemRaw { int r[8]; };
+__device__ __forceinline__ void tmem_ld4_issue(unsigned taddr, TmemRaw& raw) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=r"(raw.r[0]), "=r"(raw.r[1]), "=r"(raw.r[2]), "=r"(raw.r[3]),
+                 "=r"(raw.r[4]), "=r"(raw.r[5]), "=r"(raw.r[6]), "=r"(raw.r[7]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4_wait(TmemRaw& raw, double (&v)[4]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(raw.r[0]), "+r"(raw.r[1]), "+r"(raw.r[2]), "+r"(raw.r[3]), "+r"(raw.r[4]), "+r"(raw.r[5]),
+                 "+r"(raw.r[6]), "+r"(raw.r[7]) :: "memory");
+    v[0] = __hiloint2double(raw.r[1], raw.r[0]); v[1] = __hiloint2double(raw.r[3], raw.r[2]); v[2] = __hiloint2double(raw.r[5], raw.r[4]);
+    v[3] = __hiloint2double(raw.r[7], raw.r[6]);
 }
 #endif

@@ -1407,6 +1407,7 @@ __device__ __forceinline__ void level_chunk_args(const Dims& dm, const Level& lv
 }
 
 __device__ void cta_sweep_pipe(const Dims& dm, const SweepArgs& a, double* sm);   // kernels_sweep_pipe.cuh
+__device__ void cta_sweep_dense_stream(const Dims& dm, const SweepArgs& a, double* sm);
 
 // grid = number of chunks of this level owned by this rank (chunk = c_first + blockIdx.x)
 template <bool DENSE>
@@ -1417,6 +1418,7 @@ __global__ void __launch_bounds__(B200_SOLVE_THREADS) chain_sweep_kernel(Dims dm
     level_chunk_args(dm, lv, sb, c_first + blockIdx.x, a, blockIdx.y);
     a.lambda = sb.lam_in_sweep ? *sb.lam : 0.0;
     if (!DENSE && dm.pipe && gridDim.y == 1 && a.n > 0) cta_sweep_pipe(dm, a, sm);   // keyframe-pipelined variant (kernels_sweep_pipe.cuh)
+    else if (DENSE && dm.pipe == 1 && a.n > 0) cta_sweep_dense_stream(dm, a, sm);      // dense levels, row tiles streamed through Tensor Memory
     else cta_sweep<DENSE>(dm, a, sm);
 }
 

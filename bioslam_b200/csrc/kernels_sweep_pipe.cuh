@@ -49,7 +49,9 @@ struct RowTile {
 };
 
 // One row tile, start to finish, by the calling warp (all 32 lanes, convergent).  tb: TMEM address of the warp's slice.
-template <int NH>
+// DENSE: the coupling block is dense (reduced systems of the upper levels): Op points at the whole block O (row-major, stride dm.ld)
+// and the fill is a dense GEMM z O^T; else O is block-sparse and Op holds its packed rows.
+template <int NH, bool DENSE = false>
 __device__ __forceinline__ void stream_row_tile(const Dims& dm, const SweepArgs& a, int i, const RowTile rt, const double* __restrict__ Wt,
                                                 const double* __restrict__ Op, const int* s_orow, const int* s_ozs, const int* s_fk, unsigned tb,
                                                 double* Mnext = nullptr) {
@@ -64,7 +66,7 @@ __device__ __forceinline__ void stream_row_tile(const Dims& dm, const SweepArgs&
     const bool rv[2] = {g < rt.cr, NH > 1 && 8 + g < rt.cr};   // the row halves of this lane exist (NH = 1: 8-row tile)
     // ---- k range of the rows of O of this tile (block-sparse coupling): p is zero outside [ka, kb)
     int ka = 0, kb = n;
-    if (rt.seg == 0) xrow_range(dm, s_orow, false, rt.pr0, ka, kb, rt.cr);
+    if (rt.seg == 0) xrow_range(dm, s_orow, DENSE, rt.pr0, ka, kb, rt.cr);
     if (kb <= ka) {   // rows without structure: their fill is zero
         for (int c = 2 * t; c < nc; c += 8)
 #pragma unroll
@@ -129,14 +131,14 @@ __device__ __forceinline__ void stream_row_tile(const Dims& dm, const SweepArgs&
         Acc acc;
         acc_zero(acc);
         const int kend = c1 < kb_hi ? c1 : kb_hi;
-        for (int kbk = kb_lo; kbk <= kend; kbk++) {
+        for (int j8 = 2 * kb_lo; j8 <= 2 * kend + 1; j8++) {
+            const int kbk = j8 >> 1, h = j8 & 1;
             const bool do0 = use0 && kbk <= c0;
             const double* t1 = Wt + tile_off(kbk, c1) + g;
             const double* t0 = Wt + tile_off(kbk, do0 ? c0 : c1) + g;
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
+            {
                 double av[4];
-                tmem_ld4(tb + 8 * (2 * kbk + h), av);
+                tmem_ld4(tb + 8 * j8, av);
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
                     const int kr = (8 * h + 2 * t + e) * B200_TLD;
@@ -178,14 +180,14 @@ __device__ __forceinline__ void stream_row_tile(const Dims& dm, const SweepArgs&
         Acc acc;
         acc_zero(acc);
         const int k0 = c0 > kb_lo ? c0 : kb_lo;
-        for (int kbk = k0; kbk < nb16; kbk++) {
+        for (int j8 = 2 * k0; j8 < 2 * nb16; j8++) {
+            const int kbk = j8 >> 1, h = j8 & 1;
             const bool do1 = use1 && kbk >= c1;
             const double* t0 = Wt + tile_off(c0, kbk) + g * B200_TLD + 2 * t;
             const double* t1 = Wt + tile_off(do1 ? c1 : c0, kbk) + g * B200_TLD + 2 * t;
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
+            {
                 double av[4];
-                tmem_ld4(tb + 8 * (2 * kbk + h), av);
+                tmem_ld4(tb + 8 * j8, av);
                 const double2 b0 = ld2(t0 + 8 * h), b1 = ld2(t0 + 8 * B200_TLD + 8 * h);
 #pragma unroll
                 for (int ih = 0; ih < NH; ih++) {
@@ -211,6 +213,50 @@ __device__ __forceinline__ void stream_row_tile(const Dims& dm, const SweepArgs&
         }
     }
     tmem_wait_st();
+    if (DENSE) {
+        // ---- fill rows F = z O^T, dense coupling block in shared memory (row-major, stride ld): four 8-column output blocks per pass,
+        // B[slot][nn] = O[co + nn][8 jk + 2 t + e] as one LDS.128 per block (row g, columns 2t, 2t + 1: conflict free for ld == 4 mod 8)
+        const int ldo = dm.ld;
+        const int jz_hi = 2 * zc_hi + 1;
+        const int jo_hi = rt.seg == 0 ? ((rt.pr0 + rt.cr - 1) >> 3) : ((nc - 1) >> 3);   // rows of O: lower triangle of the fill only
+        for (int jo = 0; jo <= jo_hi && 8 * jo < nc; jo += 4) {
+            Acc acc;
+            acc_zero(acc);
+            const double* op[4];
+            bool ok[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int co = 8 * (jo + q) + g;
+                ok[q] = (jo + q <= jo_hi) && co < nc;
+                op[q] = Op + (long long)(ok[q] ? co : 0) * ldo + 2 * t;
+            }
+            for (int jk = 0; jk <= jz_hi; jk++) {
+                double av[4];
+                tmem_ld4(tb + 8 * jk, av);
+                const bool kin = 8 * jk + 2 * t < nc;
+                double2 b[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) b[q] = (ok[q] && kin) ? ld2(op[q] + 8 * jk) : make_double2(0.0, 0.0);
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+#pragma unroll
+                    for (int ih = 0; ih < NH; ih++) dmma884(acc[ih][q][0], acc[ih][q][1], av[2 * ih], b[q].x);
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+#pragma unroll
+                    for (int ih = 0; ih < NH; ih++) dmma884(acc[ih][q][0], acc[ih][q][1], av[2 * ih + 1], b[q].y);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int cw = 8 * (jo + q) + 2 * t;
+                if (jo + q > jo_hi || cw >= nc) continue;
+#pragma unroll
+                for (int ih = 0; ih < NH; ih++)
+                    if (rv[ih]) st2(Fout + (long long)(rt.pr0 + 8 * ih + g) * nc + cw, acc[ih][q][0], acc[ih][q][1]);
+            }
+        }
+        return;
+    }
     // ---- fill rows F = z O^T (block-sparse coupling): aligned 8-column output blocks; row co of O is packed in Op as the window
     // [ozs[co], ozs[co] + ow) and the block contracts over the union of its rows' windows (s_fk: first / last 8-column block of k)
     {
@@ -489,6 +535,124 @@ __device__ void cta_sweep_pipe(const Dims& dm, const SweepArgs& a, double* sm) {
         }
     }
 #undef GSYNC
+    tmem_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc512(s_tmem);
+}
+
+// Dense levels (the separators of the level below: dense coupling blocks, 1..3 nodes per chunk, the arrow rows of a chunk split over
+// gridDim.y CTAs): the same building blocks without the cross-keyframe pipeline -- plain Cholesky by all 16 warps, W^T by block
+// substitution into the tile layout, then the dense coupling block takes the pivot buffer's place in shared memory and every panel
+// row tile (rows of O and this CTA's arrow rows) is streamed through Tensor Memory by one warp.  Replaces cta_sweep<true> (fused
+// Cholesky + inverse, 64-row panel chunks through shared memory, O streamed in slabs: ~135 us per dense node).
+__device__ void cta_sweep_dense_stream(const Dims& dm, const SweepArgs& a, double* sm) {
+    const int n = dm.ntp, nc = dm.nc, ns1 = dm.ns1, ld = dm.ld, hmax = dm.hmax;
+    const long long Fsz = (long long)(nc + hmax) * nc;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    double* Ms = sm;
+    double* Wt = Ms + (long long)n * ld;
+    __shared__ unsigned s_tmem;
+    __shared__ int s_abort;
+    if (threadIdx.x == 0) s_abort = 0;
+    if (warp == 0) tmem_alloc512(&s_tmem);
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    const unsigned tb = s_tmem + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)(128 * (warp >> 2));
+#ifdef B200_PHASE_CLOCKS
+    unsigned long long dd_t = clock64();
+#define DD_ADD(i) do { if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) { unsigned long long n_ = clock64(); g_phase_clk[i] += n_ - dd_t; dd_t = n_; } } while (0)
+#else
+#define DD_ADD(i)
+#endif
+    for (int i = 0; i < a.n; i++) {
+        const long long src = a.src0 + i;
+        const long long st = a.st_idx ? a.st_idx[i] : src;
+        const bool has_x = nc > 0 && ((i + 1 < a.n) || a.has_right);
+        const int xo = has_x ? nc : 0;
+        const double* Fin = a.F + (long long)(i & 1) * Fsz;
+        // ---- pivot block M = D + lambda I - fill (lower triangle; zeros above), fill of the previous node from global memory (L2)
+        {
+            const double* Dg = a.Dsrc + src * n * n;
+            for (int r0 = warp; r0 < n; r0 += 4 * nwarps) {   // 4 rows x 2 column pairs per lane requested before the first use
+                double2 d[4][2], f[4][2];
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const int r = r0 + q * nwarps, c = 2 * lane + 64 * u;
+                        d[q][u] = make_double2(0.0, 0.0); f[q][u] = make_double2(0.0, 0.0);
+                        if (r < n && c < n && c <= r) {
+                            d[q][u] = ld2(Dg + (long long)r * n + c);
+                            if (i > 0) f[q][u] = ld2(Fin + (long long)r * nc + c);
+                        }
+                    }
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        const int r = r0 + q * nwarps, c = 2 * lane + 64 * u;
+                        if (r >= n || c >= n) continue;
+                        double2 v = make_double2(0.0, 0.0);
+                        if (c <= r) {
+                            v.x = d[q][u].x - f[q][u].x; v.y = d[q][u].y - f[q][u].y;
+                            if (c == r) v.x += a.lambda;
+                            if (c + 1 == r) v.y += a.lambda;
+                            if (c + 1 > r) v.y = 0.0;
+                        }
+                        st2(Ms + (long long)r * ld + c, v.x, v.y);
+                    }
+            }
+        }
+        __syncthreads();
+        DD_ADD(18);
+        const int fail = cta_chol_inv(Ms, ld, n, -1, 0, 0, true);
+        DD_ADD(19);
+        if (fail) {
+            if (threadIdx.x == 0) atomicCAS(a.status, 0, (int)(st + 1));
+            break;
+        }
+        // ---- W^T = L^-T: tile layout + global copy
+        {
+            double* Wg = a.Wst + st * n * n;
+            const int nbt = (n + 15) >> 4;
+            for (int task = warp; task < 2 * nbt; task += nwarps) build_wt_rows(Ms, ld, n, task >> 1, task & 1, Wt, a.lead ? Wg : nullptr);
+        }
+        __syncthreads();
+        DD_ADD(20);
+        // ---- the dense coupling block takes the pivot buffer's place
+        if (has_x) {
+            const double* Og = a.Osrc + src * nc * nc;
+            for (int r = warp; r < nc; r += nwarps)
+                for (int c = 2 * lane; c < nc; c += 64) cp_async16(Ms + (long long)r * ld + c, Og + (long long)r * nc + c);
+            cp_async_wait_all();
+        }
+        __syncthreads();
+        DD_ADD(21);
+        // ---- panel row tiles: rows of O (every CTA of the chunk, bit-identical) then this CTA's arrow rows
+        {
+            // tasks, heaviest first: the arrow rows in 16-row tiles, then the rows of O in 16-row tiles from the last one (whose fill
+            // spans all column blocks) down to the first -- a node is as slow as its slowest single-warp task
+            const int cnt = a.ar_hi - a.ar_lo;
+            const int nt1 = (cnt + 15) >> 4;
+            const int nt0 = has_x ? (nc + 15) >> 4 : 0;
+            for (int tl = warp; tl < nt0 + nt1; tl += nwarps) {
+                RowTile rt;
+                rt.xo = xo; rt.has_x = has_x;
+                if (tl < nt1) {
+                    rt.seg = 1; rt.pr0 = xo + a.ar_lo + (tl << 4); rt.cr = (cnt - (tl << 4) < 16) ? (cnt - (tl << 4)) : 16;
+                    stream_row_tile<2, true>(dm, a, i, rt, Wt, Ms, nullptr, nullptr, nullptr, tb);
+                } else {
+                    const int u = nt0 - 1 - (tl - nt1);
+                    rt.seg = 0; rt.pr0 = u << 4; rt.cr = (nc - rt.pr0 < 16) ? (nc - rt.pr0) : 16;
+                    stream_row_tile<2, true>(dm, a, i, rt, Wt, Ms, nullptr, nullptr, nullptr, tb);
+                }
+            }
+        }
+        __threadfence_block();
+        __syncthreads();
+        DD_ADD(22);
+    }
     tmem_fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc512(s_tmem);

@@ -31,3 +31,9 @@ if out[0] or out[1] or out[2]:
     for n, i in (("g0: wait [A] (arrow rows of g1)", 0), ("g0: S2 W^T -> tiles, store", 1), ("g0: S1 rows of O", 2), ("g0: S3 load D - fill", 3),
                  ("g0: S3 chol + inverse", 4), ("g1: wait [A] (chol of g0)", 5), ("g1: S2", 16), ("g1: S1 rows of O", 17), ("g1: S3 arrow rows", 6), ("prologue", 7)):
         print("  %-34s %10d  %5.1f%%" % (n, out[i], 100.0 * out[i] / max(g0, 1)))
+
+if out[18] or out[19]:
+    print("dense levels (cta_sweep_dense_stream), CTA (0, 0) of every dense sweep of one solve, cycles:")
+    tot = sum(out[18:23])
+    for n, i in (("load M = D - fill", 18), ("Cholesky (16 warps)", 19), ("W^T by substitution", 20), ("load dense O", 21), ("row tiles (TMEM)", 22)):
+        print("  %-26s %10d  %5.1f%%" % (n, out[i], 100.0 * out[i] / max(tot, 1)))
