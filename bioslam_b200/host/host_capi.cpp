@@ -173,15 +173,29 @@ int b200h_lbpe_get(void* pv, const char* name, double* out, int cap) {
         {"m_lshankImuPose", &p.m_lshankImuPose}, {"m_lfootImuPose", &p.m_lfootImuPose}};
     auto it = poses.find(s);
     if (it != poses.end()) return copyOut(flatPoses(*it->second), out, cap);
-    const std::map<std::string, const std::vector<Vector3>*> vecs = {{"m_sacrumImuAngVel", &p.m_sacrumImuAngVel}, {"m_rthighImuAngVel", &p.m_rthighImuAngVel},
-        {"m_sacrumImuVelocity", &p.m_sacrumImuVelocity}, {"m_rthighImuVelocity", &p.m_rthighImuVelocity}, {"m_sacrumImuGyroBias", &p.m_sacrumImuGyroBias}};
-    auto iv = vecs.find(s);
-    if (iv != vecs.end()) return copyOut(flatVecs(*iv->second), out, cap);
+    // every per-keyframe Vector3 member of the reference (include/lowerBodyPoseEstimator.h:118-131): <imu>Imu{AngVel, Velocity, GyroBias, AccelBias}
+    const char* imuName[7] = {"sacrum", "rthigh", "rshank", "rfoot", "lthigh", "lshank", "lfoot"};
+    const std::vector<Vector3>* angv[7] = {&p.m_sacrumImuAngVel, &p.m_rthighImuAngVel, &p.m_rshankImuAngVel, &p.m_rfootImuAngVel, &p.m_lthighImuAngVel, &p.m_lshankImuAngVel, &p.m_lfootImuAngVel};
+    const std::vector<Vector3>* vel[7] = {&p.m_sacrumImuVelocity, &p.m_rthighImuVelocity, &p.m_rshankImuVelocity, &p.m_rfootImuVelocity, &p.m_lthighImuVelocity, &p.m_lshankImuVelocity, &p.m_lfootImuVelocity};
+    const std::vector<Vector3>* gb[7] = {&p.m_sacrumImuGyroBias, &p.m_rthighImuGyroBias, &p.m_rshankImuGyroBias, &p.m_rfootImuGyroBias, &p.m_lthighImuGyroBias, &p.m_lshankImuGyroBias, &p.m_lfootImuGyroBias};
+    const std::vector<Vector3>* ab[7] = {&p.m_sacrumImuAccelBias, &p.m_rthighImuAccelBias, &p.m_rshankImuAccelBias, &p.m_rfootImuAccelBias, &p.m_lthighImuAccelBias, &p.m_lshankImuAccelBias, &p.m_lfootImuAccelBias};
+    for (int i = 0; i < 7; i++) {
+        const std::string base = std::string("m_") + imuName[i] + "Imu";
+        if (s == base + "AngVel") return copyOut(flatVecs(*angv[i]), out, cap);
+        if (s == base + "Velocity") return copyOut(flatVecs(*vel[i]), out, cap);
+        if (s == base + "GyroBias") return copyOut(flatVecs(*gb[i]), out, cap);
+        if (s == base + "AccelBias") return copyOut(flatVecs(*ab[i]), out, cap);
+    }
     const std::map<std::string, const Unit3*> ax = {{"m_rkneeAxisThigh", &p.m_rkneeAxisThigh}, {"m_rkneeAxisShank", &p.m_rkneeAxisShank},
-        {"m_lkneeAxisThigh", &p.m_lkneeAxisThigh}, {"m_lkneeAxisShank", &p.m_lkneeAxisShank}, {"m_hipAxisSacrum", &p.m_hipAxisSacrum}};
+        {"m_lkneeAxisThigh", &p.m_lkneeAxisThigh}, {"m_lkneeAxisShank", &p.m_lkneeAxisShank}, {"m_hipAxisSacrum", &p.m_hipAxisSacrum},
+        {"m_rhipAxisThigh", &p.m_rhipAxisThigh}, {"m_lhipAxisThigh", &p.m_lhipAxisThigh}, {"m_rankleAxisShank", &p.m_rankleAxisShank},
+        {"m_rankleAxisFoot", &p.m_rankleAxisFoot}, {"m_lankleAxisShank", &p.m_lankleAxisShank}, {"m_lankleAxisFoot", &p.m_lankleAxisFoot}};
     auto ia = ax.find(s);
     if (ia != ax.end()) return copyOut({ia->second->p[0], ia->second->p[1], ia->second->p[2]}, out, cap);
-    const std::map<std::string, const Point3*> pt = {{"m_sacrumImuToRHipCtr", &p.m_sacrumImuToRHipCtr}, {"m_rthighImuToKneeCtr", &p.m_rthighImuToKneeCtr},
+    const std::map<std::string, const Point3*> pt = {{"m_sacrumImuToRHipCtr", &p.m_sacrumImuToRHipCtr}, {"m_sacrumImuToLHipCtr", &p.m_sacrumImuToLHipCtr},
+        {"m_rthighImuToHipCtr", &p.m_rthighImuToHipCtr}, {"m_rthighImuToKneeCtr", &p.m_rthighImuToKneeCtr}, {"m_rshankImuToKneeCtr", &p.m_rshankImuToKneeCtr},
+        {"m_rshankImuToAnkleCtr", &p.m_rshankImuToAnkleCtr}, {"m_rfootImuToAnkleCtr", &p.m_rfootImuToAnkleCtr}, {"m_lthighImuToHipCtr", &p.m_lthighImuToHipCtr},
+        {"m_lthighImuToKneeCtr", &p.m_lthighImuToKneeCtr}, {"m_lshankImuToKneeCtr", &p.m_lshankImuToKneeCtr}, {"m_lshankImuToAnkleCtr", &p.m_lshankImuToAnkleCtr},
         {"m_lfootImuToAnkleCtr", &p.m_lfootImuToAnkleCtr}};
     auto ip = pt.find(s);
     if (ip != pt.end()) return copyOut({ip->second->v[0], ip->second->v[1], ip->second->v[2]}, out, cap);

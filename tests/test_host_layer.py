@@ -238,3 +238,43 @@ def test_host_single_imu_with_ekf_initialisation():
     assert err[-1] < 1e-5 * err[0]
     R = p.get("m_pose").reshape(-1, 12)[:, :9].reshape(-1, 3, 3)
     assert np.abs(R @ np.swapaxes(R, 1, 2) - np.eye(3)).max() < 1e-9
+
+
+@pytest.mark.gpu
+def test_host_fast_optimize_restarts_on_hip_ie_drift():
+    """the restart recursion of fastOptimize END TO END on the GPU (reference src/lowerBodyPoseEstimator.cpp:668-688): initial values
+    whose right leg drifts about the femur's long axis at 0.2 rad/s, LM runs capped at 2 iterations so the drift survives the first
+    run -> slope above the threshold -> adjustLegsForCorrectedHipIeAngles -> second LM run from the straightened poses (-> ...);
+    the error history is the concatenation of the runs, the final estimate has no drift and a lower cost than the first run."""
+    tr = synth.make_trial(seed=8, duration_s=4.0)
+    lb = host.lower_body_from_trial(tr)
+    lb.set(m_maxIterations=2, m_maxNumRestarts=2)
+    lb.setup()
+    g, tv, sv = lb.graph()
+    tv, sv = graphs.perturbed_truth_values(tr, g, tv, sv, rot_noise=0.0, pos_noise=0.0)
+    t = lb.get("m_time")
+    off, so = g.time_value_offsets(), g.static_value_offsets()
+    stat = lambda i: sv[so[i]:so[i] + 3]
+    tv2 = tv.copy()
+    for k in range(g.K):
+        Rt = tv[k, off[3]:off[3] + 9].reshape(3, 3)
+        axis = Rt @ (stat(3) - stat(2)); axis /= np.linalg.norm(axis)
+        dR = synth.exp_so3((axis * 0.2 * t[k])[None, :])[0]
+        for i in (1, 2, 3):
+            o = off[3 * i]
+            tv2[k, o:o + 9] = (dR @ tv[k, o:o + 9].reshape(3, 3)).reshape(-1)
+    lb.set_values(tv2, sv)
+    thr = 100.0 * np.pi / 180.0 / 30.0
+    r_before, _ = lb.computeHipIeRotAngleRegressionSlopesFromValues()
+    assert abs(r_before) > thr
+    lb.fastOptimize()
+    n_restarts = lb.nRestarts()
+    assert 1 <= n_restarts <= 2
+    h = lb.get("m_optimizationTotalError")
+    assert h.size == (n_restarts + 1) * 3                      # every run: initial error + 2 iterations
+    runs = h.reshape(n_restarts + 1, 3)
+    assert np.all(np.diff(runs, axis=1) <= 0)                   # LM never accepts an increase inside a run
+    assert runs[-1, -1] < runs[0, -1]                           # the restarted run ends lower than the first one
+    r_after, l_after = lb.computeHipIeRotAngleRegressionSlopesFromValues()
+    assert abs(r_after) < abs(r_before) and (abs(r_after) < thr or n_restarts == 2)
+    assert lb.get("m_rhipIntExtRotAng").size == g.K             # derived angles filled after the last run
