@@ -268,7 +268,7 @@ def test_host_fast_optimize_restarts_on_hip_ie_drift():
     r_before, _ = lb.computeHipIeRotAngleRegressionSlopesFromValues()
     assert abs(r_before) > thr
     lb.fastOptimize()
-    n_restarts = lb.nRestarts()
+    n_restarts = lb.nRestarts
     assert 1 <= n_restarts <= 2
     h = lb.get("m_optimizationTotalError")
     assert h.size == (n_restarts + 1) * 3                      # every run: initial error + 2 iterations
