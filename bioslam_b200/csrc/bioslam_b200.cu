@@ -133,6 +133,7 @@ struct b200_problem {
     LocalElim le{};
     size_t smem_le = 0;
     double *d_Dc = nullptr, *d_Ac = nullptr, *d_Sc = nullptr, *d_V = nullptr, *d_Wl = nullptr;
+    int* d_le_fresh = nullptr;   // device flag: the reduced blocks do not belong to the current linearization yet (kernels_local.cuh)
     double* d_delta = nullptr;   // full step [K][ntp] in internal order (== sb.delta without pre-elimination)
     LmDev* d_lm = nullptr;
     LmDev* h_lm = nullptr;       // pinned mirror
@@ -343,7 +344,7 @@ void b200_problem_destroy(b200_problem* p) {
                     p->d_asm_elems[0], p->d_asm_elems[1]};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->use_le && p->d_delta) cudaFree(p->d_delta);
-    for (void* q : {(void*)p->d_Dc, (void*)p->d_Ac, (void*)p->d_Sc, (void*)p->d_V, (void*)p->d_Wl, (void*)p->d_lm}) if (q) cudaFree(q);
+    for (void* q : {(void*)p->d_Dc, (void*)p->d_Ac, (void*)p->d_Sc, (void*)p->d_V, (void*)p->d_Wl, (void*)p->d_lm, (void*)p->d_le_fresh}) if (q) cudaFree(q);
     if (p->h_lm) cudaFreeHost(p->h_lm);
     if (p->d_spec_delta) cudaFree(p->d_spec_delta);
     if (p->d_spec_rec) cudaFree(p->d_spec_rec);
@@ -487,6 +488,8 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
         CK(cudaMemsetAsync(p->d_Ac, 0, sizeof(double) * K * ds.ns1 * ds.ntp, p->stream));
         CK(cudaMemsetAsync(p->d_Sc, 0, sizeof(double) * K * ds.ns1 * ds.ns1, p->stream));
         CK(dalloc(&p->d_V, K * (size_t)(dm.nc + dm.ns1) * nl)); CK(dalloc(&p->d_Wl, K * (size_t)nl * nl));
+        CK(dalloc(&p->d_le_fresh, (size_t)1));
+        CK(cudaMemsetAsync(p->d_le_fresh, 1, sizeof(int), p->stream));
         CK(dalloc(&p->d_delta, (K + 1024) * dm.ntp));
         CK(cudaMemsetAsync(p->d_delta, 0, sizeof(double) * (K + 1024) * dm.ntp, p->stream));
         LocalElim& le = p->le;
@@ -873,6 +876,7 @@ static void launch_linearize(b200_problem* p) {
     B200_LAUNCH(assemble_kernel, dim3(p->k_hi - ka), dim3(512), std::max(p->smem_asm[0], p->smem_asm[1]), p->stream, p->dm,
                 p->d_slots, p->asm_plan, p->d_J, p->d_r, ka, 0, p->K, p->d_D, p->d_O, p->d_A, p->d_S);
     p->launches++;
+    if (p->d_le_fresh) cudaMemsetAsync(p->d_le_fresh, 1, sizeof(int), p->stream);   // new linearization: the next local elimination writes everything
 }
 
 // Collectives.  A "group" is a run of exchanges issued together (one ncclGroupStart / ncclGroupEnd with the in-library NCCL).
@@ -901,6 +905,11 @@ static b200_status allgather(b200_problem* p, void* buf, size_t bytes_per_rank) 
     if (!p->ag_fn) { set_err("world_size > 1 but no collective registered (b200_comm_set / b200_nccl_init)"); return B200_NCCL_ERROR; }
     if (p->ag_fn(p->comm_ctx, buf, (uint64_t)bytes_per_rank, p->stream)) { set_err("allgather failed"); return B200_NCCL_ERROR; }
     return B200_OK;
+}
+
+// the reduced blocks now belong to the current linearization (a skipped trial leaves the flag alone: it wrote nothing)
+__global__ void clear_flag_kernel(int* flag, const int* __restrict__ skip) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && !(skip && *skip)) *flag = 0;
 }
 
 // pack / unpack the level-1 source blocks of the group separators (D, A, S of the reduced system) for the all-gather
@@ -951,8 +960,10 @@ static b200_status launch_solve(b200_problem* p, cudaEvent_t* tev) {
     const size_t Fsz = (size_t)(dm.nc + dm.hmax) * dm.nc, Ssz = (size_t)dm.hmax * dm.hmax;
     const int nlev = (p->P > 1) ? (int)p->levels.size() : 0;
     if (p->use_le) {
-        B200_LAUNCH(local_elim_kernel, dim3(p->k_hi - p->k_lo), dim3(B200_LE_THREADS), p->smem_le, p->stream, p->le, p->k_lo, p->sb.lam, p->sb.status, p->sb.skip);
-        p->launches++;
+        B200_LAUNCH(local_elim_kernel, dim3(p->k_hi - p->k_lo), dim3(B200_LE_THREADS), p->smem_le, p->stream, p->le, p->k_lo, p->sb.lam, p->sb.status, p->sb.skip,
+                    (const int*)p->d_le_fresh);
+        B200_LAUNCH(clear_flag_kernel, dim3(1), dim3(32), 0, p->stream, p->d_le_fresh, p->sb.skip);
+        p->launches += 2;
     }
     if (tev) CK(cudaEventRecord(tev[TE_SWEEP0], p->stream));
     if (nlev >= 1) {
@@ -1712,7 +1723,7 @@ b200_status b200_debug_local_elim(b200_problem* p, int32_t k, double lambda, int
         b200_status st = push_lambda_try(p, lambda);
         if (st != B200_OK) return st;
         CK(cudaMemsetAsync(p->sb.status, 0, sizeof(int), p->stream));
-        B200_LAUNCH(local_elim_kernel, dim3(1), dim3(B200_LE_THREADS), p->smem_le, p->stream, p->le, (int)k, p->sb.lam, p->sb.status, (const int*)nullptr);
+        B200_LAUNCH(local_elim_kernel, dim3(1), dim3(B200_LE_THREADS), p->smem_le, p->stream, p->le, (int)k, p->sb.lam, p->sb.status, (const int*)nullptr, (const int*)nullptr);
         p->launches++;
     }
     CK(cudaStreamSynchronize(p->stream));

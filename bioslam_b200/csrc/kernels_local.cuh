@@ -28,10 +28,16 @@ __host__ __device__ inline int le_ldl(int nl) { int l = nl; while ((l & 7) != 4)
 __host__ __device__ inline long long le_smem_doubles(int nl, int nc, int ns1) { return (long long)(2 * nl + nc + ns1) * le_ldl(nl); }
 
 // grid = keyframes [k_first, k_first + gridDim.x)
+// fresh (device flag, may be null = always): non-zero on the first lambda trial after a linearization -> every reduced entry is written.
+// On the later trials of the same linearization only lambda has changed: V V^T touches the entries whose row AND column couple to a
+// local dof (6 of every 15 chain dofs of the 7-IMU graph: 16 % of Dc) plus the diagonals -- everything else still holds the right value
+// from the first trial and is neither read nor written (the kernel is bound by exactly that traffic).
 __global__ void __launch_bounds__(B200_LE_THREADS, 3) local_elim_kernel(LocalElim le, int k_first, const double* __restrict__ lambda_p, int* status,
-                                                                        const int* __restrict__ skip) {
+                                                                        const int* __restrict__ skip, const int* __restrict__ fresh) {
     B200_DYN_SMEM(double, sm);
     if (skip && *skip) return;
+    const bool full = (fresh == nullptr) || (*fresh != 0);
+    __shared__ unsigned char s_row[512];   // panel row r (chain rows, then statics + rhs) has a non-zero row in V
     const int nl = le.nl, nc = le.nc, ncp = le.ncp, ns1 = le.ns1, ntp = le.ntp, ldl = le.ldl, hp = nc + ns1;
     const long long k = k_first + (long long)blockIdx.x;
     const double lambda = *lambda_p;
@@ -46,10 +52,12 @@ __global__ void __launch_bounds__(B200_LE_THREADS, 3) local_elim_kernel(LocalEli
     if (threadIdx.x == 0) s_fail = 0;
     // pull everything this keyframe reads towards L2 now (lower triangle of D_k, A_k, S_k: ~150 KB): the epilogue below reads
     // D_cc / A_c / S_k entry by entry and would otherwise wait for DRAM tile after tile
-    for (int r = threadIdx.x; r < ntp; r += blockDim.x)
-        for (int c = 0; c <= r; c += 16) prefetch_l2(Dk + (long long)r * ntp + c);
-    for (int e = threadIdx.x * 16; e < ns1 * ntp; e += blockDim.x * 16) prefetch_l2(Ak + e);
-    for (int e = threadIdx.x * 16; e < ns1 * ns1; e += blockDim.x * 16) prefetch_l2(Sk + e);
+    if (full) {
+        for (int r = threadIdx.x; r < ntp; r += blockDim.x)
+            for (int c = 0; c <= r; c += 16) prefetch_l2(Dk + (long long)r * ntp + c);
+        for (int e = threadIdx.x * 16; e < ns1 * ntp; e += blockDim.x * 16) prefetch_l2(Ak + e);
+        for (int e = threadIdx.x * 16; e < ns1 * ns1; e += blockDim.x * 16) prefetch_l2(Sk + e);
+    }
     // panel rows [D_cl ; A_l ; -g_l^T] (every warp but the first), while warp 0 factorises the local block
     if (warp > 0) {
         for (int e = threadIdx.x - 32; e < hp * nl; e += blockDim.x - 32) {
@@ -104,6 +112,10 @@ __global__ void __launch_bounds__(B200_LE_THREADS, 3) local_elim_kernel(LocalEli
                 Vs[r * ldl + j] = x[j];
             }
         }
+        bool nz = false;
+#pragma unroll
+        for (int j = 0; j < B200_LE_MAXNL; j++) nz |= (j < nl) && (x[j] != 0.0);
+        s_row[r] = nz ? 1 : 0;
         for (int c = nl; c < ldl; c++) Vs[r * ldl + c] = 0.0;
     }
     __syncthreads();
@@ -145,10 +157,11 @@ __global__ void __launch_bounds__(B200_LE_THREADS, 3) local_elim_kernel(LocalEli
                 for (int e = 0; e < 2; e++) {
                     const int c = c0 + 8 * j + 2 * mt + e;
                     if (kind == 0) {
-                        if (r < nc && c <= r) Dck[(long long)r * ncp + c] = Dk[(long long)(nl + r) * ntp + nl + c] + (r == c ? lambda : 0.0) - acc[i][j][e];
+                        if (r < nc && c <= r && (full || r == c || (s_row[r] && s_row[c])))
+                            Dck[(long long)r * ncp + c] = Dk[(long long)(nl + r) * ntp + nl + c] + (r == c ? lambda : 0.0) - acc[i][j][e];
                     } else if (kind == 1) {
-                        if (r < ns1 && c < nc) Ack[(long long)r * ncp + c] = Ak[(long long)r * ntp + nl + c] - acc[i][j][e];
-                    } else if (r < ns1 && c <= r) {
+                        if (r < ns1 && c < nc && (full || (s_row[nc + r] && s_row[c]))) Ack[(long long)r * ncp + c] = Ak[(long long)r * ntp + nl + c] - acc[i][j][e];
+                    } else if (r < ns1 && c <= r && (full || (s_row[nc + r] && s_row[nc + c]))) {
                         Sck[(long long)r * ns1 + c] = Sk[(long long)r * ns1 + c] - acc[i][j][e];   // (consumers read the lower triangle)
                     }
                 }
