@@ -159,6 +159,14 @@ __device__ __forceinline__ void stream_row_tile(const Dims& dm, const SweepArgs&
             const int j = 2 * (q < 2 ? c0 : c1) + (q & 1);
             double v[4] = {acc[0][q][0], acc[0][q][1], NH > 1 ? acc[NH - 1][q][0] : 0.0, NH > 1 ? acc[NH - 1][q][1] : 0.0};
             tmem_st4(tb + 8 * j, v);
+            if (DENSE && rt.seg == 0 && Mnext) {   // dense levels: the rows of X = O W^T, B operand of every fill of this node
+                const int c = 8 * j + 2 * t;
+                if (c < n) {
+#pragma unroll
+                    for (int ih = 0; ih < NH; ih++)
+                        if (rv[ih]) st2(Mnext + (long long)(rt.pr0 + 8 * ih + g) * dm.ld + c, acc[ih][q][0], acc[ih][q][1]);
+                }
+            }
             if (rt.seg == 1) {
                 const int c = 8 * j + 2 * t;
                 if (c < n) {
@@ -169,6 +177,7 @@ __device__ __forceinline__ void stream_row_tile(const Dims& dm, const SweepArgs&
             }
         }
     }
+    if (DENSE) { tmem_wait_st(); return; }   // dense levels: the fill is y X^T (dense_fill_tile), after every tile of the node has its y
     if (!rt.has_x) return;
     tmem_wait_st();
     // ---- z = y W, in place from the first 16-column block up: z[:, c] = sum_{k >= max(c, kb_lo)} y[:, k] tile(c, k)^T.
@@ -213,50 +222,6 @@ __device__ __forceinline__ void stream_row_tile(const Dims& dm, const SweepArgs&
         }
     }
     tmem_wait_st();
-    if (DENSE) {
-        // ---- fill rows F = z O^T, dense coupling block in shared memory (row-major, stride ld): four 8-column output blocks per pass,
-        // B[slot][nn] = O[co + nn][8 jk + 2 t + e] as one LDS.128 per block (row g, columns 2t, 2t + 1: conflict free for ld == 4 mod 8)
-        const int ldo = dm.ld;
-        const int jz_hi = 2 * zc_hi + 1;
-        const int jo_hi = rt.seg == 0 ? ((rt.pr0 + rt.cr - 1) >> 3) : ((nc - 1) >> 3);   // rows of O: lower triangle of the fill only
-        for (int jo = 0; jo <= jo_hi && 8 * jo < nc; jo += 4) {
-            Acc acc;
-            acc_zero(acc);
-            const double* op[4];
-            bool ok[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int co = 8 * (jo + q) + g;
-                ok[q] = (jo + q <= jo_hi) && co < nc;
-                op[q] = Op + (long long)(ok[q] ? co : 0) * ldo + 2 * t;
-            }
-            for (int jk = 0; jk <= jz_hi; jk++) {
-                double av[4];
-                tmem_ld4(tb + 8 * jk, av);
-                const bool kin = 8 * jk + 2 * t < nc;
-                double2 b[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) b[q] = (ok[q] && kin) ? ld2(op[q] + 8 * jk) : make_double2(0.0, 0.0);
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-#pragma unroll
-                    for (int ih = 0; ih < NH; ih++) dmma884(acc[ih][q][0], acc[ih][q][1], av[2 * ih], b[q].x);
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-#pragma unroll
-                    for (int ih = 0; ih < NH; ih++) dmma884(acc[ih][q][0], acc[ih][q][1], av[2 * ih + 1], b[q].y);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int cw = 8 * (jo + q) + 2 * t;
-                if (jo + q > jo_hi || cw >= nc) continue;
-#pragma unroll
-                for (int ih = 0; ih < NH; ih++)
-                    if (rv[ih]) st2(Fout + (long long)(rt.pr0 + 8 * ih + g) * nc + cw, acc[ih][q][0], acc[ih][q][1]);
-            }
-        }
-        return;
-    }
     // ---- fill rows F = z O^T (block-sparse coupling): aligned 8-column output blocks; row co of O is packed in Op as the window
     // [ozs[co], ozs[co] + ow) and the block contracts over the union of its rows' windows (s_fk: first / last 8-column block of k)
     {
@@ -315,6 +280,57 @@ __device__ __forceinline__ void stream_row_tile(const Dims& dm, const SweepArgs&
 #pragma unroll
                 for (int ih = 0; ih < NH; ih++)
                     if (rv[ih]) st2(Mnext + (long long)(rt.pr0 + 8 * ih + g) * ld + cw, 0.0, 0.0);
+        }
+    }
+}
+
+// Dense levels: fill rows of one tile, F = y X^T with X = O W^T (= z O^T, one triangular GEMM less): y from the warp's TMEM slice,
+// X rows in shared memory (row-major, stride ld; written by the rows-of-O tiles of the same node).  Four 8-column output blocks
+// per pass; B[slot][nn] = X[co + nn][8 jk + 2 t + e] as one LDS.128 per block (row g, columns 2t, 2t + 1: conflict free for ld == 4 mod 8).
+template <int NH>
+__device__ __forceinline__ void dense_fill_tile(const Dims& dm, const SweepArgs& a, int i, const RowTile rt, const double* __restrict__ Xs, unsigned tb) {
+    const int n = dm.ntp, nc = dm.nc, hmax = dm.hmax, ldo = dm.ld;
+    const long long Fsz = (long long)(nc + hmax) * nc;
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int nb16 = (n + 15) >> 4;
+    double* Fout = a.F + (long long)((i + 1) & 1) * Fsz;
+    const bool rv[2] = {g < rt.cr, NH > 1 && 8 + g < rt.cr};
+    const int jz_hi = 2 * nb16 - 1;
+    const int jo_hi = rt.seg == 0 ? ((rt.pr0 + rt.cr - 1) >> 3) : ((nc - 1) >> 3);   // rows of O: lower triangle of the fill only
+    for (int jo = 0; jo <= jo_hi && 8 * jo < nc; jo += 4) {
+        Acc acc;
+        acc_zero(acc);
+        const double* op[4];
+        bool ok[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int co = 8 * (jo + q) + g;
+            ok[q] = (jo + q <= jo_hi) && co < nc;
+            op[q] = Xs + (long long)(ok[q] ? co : 0) * ldo + 2 * t;
+        }
+        for (int jk = 0; jk <= jz_hi; jk++) {
+            double av[4];
+            tmem_ld4(tb + 8 * jk, av);
+            const bool kin = 8 * jk + 2 * t < n;
+            double2 b[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) b[q] = (ok[q] && kin) ? ld2(op[q] + 8 * jk) : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+#pragma unroll
+                for (int ih = 0; ih < NH; ih++) dmma884(acc[ih][q][0], acc[ih][q][1], av[2 * ih], b[q].x);
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+#pragma unroll
+                for (int ih = 0; ih < NH; ih++) dmma884(acc[ih][q][0], acc[ih][q][1], av[2 * ih + 1], b[q].y);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int cw = 8 * (jo + q) + 2 * t;
+            if (jo + q > jo_hi || cw >= nc) continue;
+#pragma unroll
+            for (int ih = 0; ih < NH; ih++)
+                if (rv[ih]) st2(Fout + (long long)(rt.pr0 + 8 * ih + g) * nc + cw, acc[ih][q][0], acc[ih][q][1]);
         }
     }
 }
@@ -620,33 +636,28 @@ __device__ void cta_sweep_dense_stream(const Dims& dm, const SweepArgs& a, doubl
         }
         __syncthreads();
         DD_ADD(20);
-        // ---- the dense coupling block takes the pivot buffer's place
-        if (has_x) {
-            const double* Og = a.Osrc + src * nc * nc;
-            for (int r = warp; r < nc; r += nwarps)
-                for (int c = 2 * lane; c < nc; c += 64) cp_async16(Ms + (long long)r * ld + c, Og + (long long)r * nc + c);
-            cp_async_wait_all();
-        }
-        __syncthreads();
         DD_ADD(21);
-        // ---- panel row tiles: rows of O (every CTA of the chunk, bit-identical) then this CTA's arrow rows
+        // ---- panel row tiles, two phases.  A: y = p W^T of every tile (rows of O first: their y is X = O W^T, written to the pivot
+        // buffer, which is free now).  B: fill = y X^T.  A warp keeps the y of its tile in Tensor Memory between the phases.
         {
-            // tasks, heaviest first: the arrow rows in 16-row tiles, then the rows of O in 16-row tiles from the last one (whose fill
-            // spans all column blocks) down to the first -- a node is as slow as its slowest single-warp task
+            const int nt0 = has_x ? (nc + 15) >> 4 : 0;
             const int cnt = a.ar_hi - a.ar_lo;
             const int nt1 = (cnt + 15) >> 4;
-            const int nt0 = has_x ? (nc + 15) >> 4 : 0;
-            for (int tl = warp; tl < nt0 + nt1; tl += nwarps) {
-                RowTile rt;
+            auto tile_of = [&](int tl, RowTile& rt) {
                 rt.xo = xo; rt.has_x = has_x;
-                if (tl < nt1) {
-                    rt.seg = 1; rt.pr0 = xo + a.ar_lo + (tl << 4); rt.cr = (cnt - (tl << 4) < 16) ? (cnt - (tl << 4)) : 16;
-                    stream_row_tile<2, true>(dm, a, i, rt, Wt, Ms, nullptr, nullptr, nullptr, tb);
-                } else {
-                    const int u = nt0 - 1 - (tl - nt1);
-                    rt.seg = 0; rt.pr0 = u << 4; rt.cr = (nc - rt.pr0 < 16) ? (nc - rt.pr0) : 16;
-                    stream_row_tile<2, true>(dm, a, i, rt, Wt, Ms, nullptr, nullptr, nullptr, tb);
+                if (tl < nt0) { rt.seg = 0; rt.pr0 = tl << 4; rt.cr = (nc - rt.pr0 < 16) ? (nc - rt.pr0) : 16; }
+                else { const int u = tl - nt0; rt.seg = 1; rt.pr0 = xo + a.ar_lo + (u << 4); rt.cr = (cnt - (u << 4) < 16) ? (cnt - (u << 4)) : 16; }
+            };
+            for (int base = 0; base < nt0 + nt1; base += nwarps) {   // (rounds of one tile per warp; the rows of O are all in the first one)
+                const int tl = base + warp;
+                RowTile rt;
+                if (tl < nt0 + nt1) {
+                    tile_of(tl, rt);
+                    stream_row_tile<2, true>(dm, a, i, rt, Wt, nullptr, nullptr, nullptr, nullptr, tb, has_x ? Ms : nullptr);
                 }
+                __syncthreads();   // X complete (first round)
+                if (has_x && tl < nt0 + nt1) dense_fill_tile<2>(dm, a, i, rt, Ms, tb);
+                if (base + nwarps < nt0 + nt1) __syncthreads();
             }
         }
         __threadfence_block();

@@ -126,8 +126,14 @@ class Problem:
         assert tv.shape == (self.K, self.tvd) and (sv.size == self.svd or not self.svd)
         self._ck(self.L.b200_set_values(self.h, D(tv), D(sv)))
 
-    def get_values(self):
-        tv = np.zeros((self.K, self.tvd)); sv = np.zeros(max(self.svd, 1))
+    def get_values(self, out=None):
+        """out = (tv, sv): caller-owned C-contiguous float64 buffers of shapes (K, tvd) / (>= max(svd, 1),), e.g. pinned host memory
+        (the library copies straight into them: cudaMemcpyAsync device -> host on the problem's stream)"""
+        if out is None:
+            tv = np.zeros((self.K, self.tvd)); sv = np.zeros(max(self.svd, 1))
+        else:
+            tv, sv = out
+            assert tv.dtype == np.float64 and sv.dtype == np.float64 and tv.flags.c_contiguous and tv.shape == (self.K, self.tvd) and sv.size >= max(self.svd, 1)
         self._ck(self.L.b200_get_values(self.h, D(tv), D(sv)))
         return tv, sv[:self.svd]
 
