@@ -13,7 +13,7 @@ VAL_DIM = (12, 3, 6, 3)
 TAN_DIM = (6, 3, 6, 2)
 (F_IMU_COMBINED, F_IMU_STATICBIAS, F_ANGVEL, F_HINGE_VEC, F_HINGE_NORM, F_JOINTPOS_VEC, F_JOINTPOS_NORM, F_JOINTVEL_VEC,
  F_SEGLEN_MAG, F_SEGLEN_MAX, F_SEGLEN_MIN, F_SEGLEN_DISCREPANCY, F_ANGLE_AXIS_SEG, F_POSE3_TRANSLATION_PRIOR,
- F_POSE3_COMPASS_PRIOR, F_PRIOR_VEC3, F_PRIOR_BIAS6, F_PRIOR_UNIT3, F_PRIOR_POSE3, F_MAG_POSE3, F_NUM_TYPES) = range(21)
+ F_POSE3_COMPASS_PRIOR, F_PRIOR_VEC3, F_PRIOR_BIAS6, F_PRIOR_UNIT3, F_PRIOR_POSE3, F_MAG_POSE3, F_JOINTVEL_NORM, F_NUM_TYPES) = range(22)
 AT_K, AT_K1, AT_STATIC = range(3)
 MAX_FACTOR_VARS, MAX_FACTOR_PARAMS = 8, 24
 
@@ -39,6 +39,7 @@ FACTOR_INFO = {
     F_PRIOR_UNIT3: (2, (VAR_UNIT3,), 0),
     F_PRIOR_POSE3: (6, (VAR_POSE3,), 0),
     F_MAG_POSE3: (3, (VAR_POSE3,), 3),
+    F_JOINTVEL_NORM: (1, (VAR_POSE3, VAR_VEC3, VAR_VEC3, VAR_VEC3, VAR_POSE3, VAR_VEC3, VAR_VEC3, VAR_VEC3), 0),
 }
 
 

@@ -50,7 +50,7 @@ static bool finfo(int type, FInfo& f) {
     case B200_F_ANGVEL: f = {2, {V, B}, 3}; return true;
     case B200_F_HINGE_VEC: case B200_F_HINGE_NORM: f = {5, {P, V, P, V, U}, 0}; return true;
     case B200_F_JOINTPOS_VEC: case B200_F_JOINTPOS_NORM: f = {4, {P, P, V, V}, 0}; return true;
-    case B200_F_JOINTVEL_VEC: f = {8, {P, V, V, V, P, V, V, V}, 0}; return true;
+    case B200_F_JOINTVEL_VEC: case B200_F_JOINTVEL_NORM: f = {8, {P, V, V, V, P, V, V, V}, 0}; return true;
     case B200_F_SEGLEN_MAG: case B200_F_SEGLEN_MAX: case B200_F_SEGLEN_MIN: f = {2, {V, V}, 0}; return true;
     case B200_F_SEGLEN_DISCREPANCY: f = {4, {V, V, V, V}, 0}; return true;
     case B200_F_ANGLE_AXIS_SEG: f = {3, {U, V, V}, 0}; return true;

@@ -56,7 +56,7 @@ __host__ __device__ __forceinline__ int factor_rows(int t) {
     case B200_F_IMU_STATICBIAS: return 9;
     case B200_F_PRIOR_BIAS6: case B200_F_PRIOR_POSE3: return 6;
     case B200_F_PRIOR_UNIT3: return 2;
-    case B200_F_HINGE_NORM: case B200_F_JOINTPOS_NORM: case B200_F_SEGLEN_MAG: case B200_F_SEGLEN_MAX: case B200_F_SEGLEN_MIN:
+    case B200_F_HINGE_NORM: case B200_F_JOINTPOS_NORM: case B200_F_JOINTVEL_NORM: case B200_F_SEGLEN_MAG: case B200_F_SEGLEN_MAX: case B200_F_SEGLEN_MIN:
     case B200_F_SEGLEN_DISCREPANCY: case B200_F_ANGLE_AXIS_SEG: case B200_F_POSE3_COMPASS_PRIOR: return 1;
     default: return 3;
     }
@@ -185,21 +185,33 @@ __device__ void factor_eval(int type, const double* params, CstRef cst, const do
             if (WJ) { double u[3]; norm3_grad(e, n, u); for (int c = 0; c < 18; c++) J[c] = u[0] * J3[c] + u[1] * J3[18 + c] + u[2] * J3[36 + c]; }
         }
     } break;
-    case B200_F_JOINTVEL_VEC: {  // reference src/factors/ConstrainedJointCenterVelocityFactor.cpp:68-131
+    case B200_F_JOINTVEL_VEC:
+    case B200_F_JOINTVEL_NORM: {  // reference src/factors/ConstrainedJointCenterVelocityFactor.cpp:68-131 (vector), :137-214 (norm)
+        const bool vec = type == B200_F_JOINTVEL_VEC;
+        double e[3], J3[90];
+        double* Jt = vec ? J : J3;
+        const int ldt = vec ? ld : 30;
+        if (WJ && !vec) for (int i = 0; i < 90; i++) J3[i] = 0.0;
         for (int side = 0; side < 2; side++) {
             const double *X = x[4 * side], *V = x[4 * side + 1], *W = x[4 * side + 2], *S_ = x[4 * side + 3];
             const double sg = side == 0 ? 1.0 : -1.0;
             double ws[3], Rws[3];
             cross3(ws, W, S_); mat_vec(Rws, X, ws);
-            for (int i = 0; i < 3; i++) { const double t = V[i] + Rws[i]; if (side == 0) r[i] = t; else r[i] -= t; }
+            for (int i = 0; i < 3; i++) { const double t = V[i] + Rws[i]; if (side == 0) e[i] = t; else e[i] -= t; }
             if (WJ) {
                 const int c0 = 15 * side;
                 double T[9];
-                m_skew(T, X, ws); put33(J, ld, 0, c0, T, -sg);
-                for (int i = 0; i < 3; i++) J[i * ld + c0 + 6 + i] = sg;
-                m_skew(T, X, S_); put33(J, ld, 0, c0 + 9, T, -sg);
-                m_skew(T, X, W); put33(J, ld, 0, c0 + 12, T, sg);
+                m_skew(T, X, ws); put33(Jt, ldt, 0, c0, T, -sg);
+                for (int i = 0; i < 3; i++) Jt[i * ldt + c0 + 6 + i] = sg;
+                m_skew(T, X, S_); put33(Jt, ldt, 0, c0 + 9, T, -sg);
+                m_skew(T, X, W); put33(Jt, ldt, 0, c0 + 12, T, sg);
             }
+        }
+        if (vec) { r[0] = e[0]; r[1] = e[1]; r[2] = e[2]; }
+        else {
+            const double n = sqrt(dot3(e, e));
+            r[0] = n;
+            if (WJ) { double u[3]; norm3_grad(e, n, u); for (int c = 0; c < 30; c++) J[c] = u[0] * J3[c] + u[1] * J3[30 + c] + u[2] * J3[60 + c]; }
         }
     } break;
     case B200_F_SEGLEN_MAG:

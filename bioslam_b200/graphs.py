@@ -33,7 +33,8 @@ def keyframe_sample_idx(K, n_per):
     return idx
 
 
-def lower_body_graph(trial, n_per=10, preint=None, use_joint_vel=False, hinge_dim=3, joint_pos_dim=3, magnetometer=False, global_B=(19.5, -5.1, -47.8)):
+def lower_body_graph(trial, n_per=10, preint=None, use_joint_vel=False, hinge_dim=3, joint_pos_dim=3, magnetometer=False, global_B=(19.5, -5.1, -47.8),
+                     joint_vel_dim=3):
     """Returns (GraphDesc, time_values [K][168], static_values [69]) for the 7-IMU configuration.  Defaults = the reference's
     (include/lowerBodyPoseEstimator.h:24-89); hinge_dim / joint_pos_dim = 1 select the norm-error factors
     (m_hingeAxisFactorDim / m_jointPosFactorDim, sigma = norm of the 3-vector sigma, src/lowerBodyPoseEstimator.cpp:296-312);
@@ -108,8 +109,10 @@ def lower_body_graph(trial, n_per=10, preint=None, use_joint_vel=False, hinge_di
     joint(LS, LF, "lshankImuToAnkleCtr", "lfootImuToAnkleCtr", ankN)
     if use_joint_vel:
         def jvel(a, b, sa, sb):
-            g.add_slot(abi.F_JOINTVEL_VEC, [(K_, pose(a)), (K_, vel(a)), (K_, angv(a)), (ST, sidx[sa]),
-                                            (K_, pose(b)), (K_, vel(b)), (K_, angv(b)), (ST, sidx[sb])], [10.0] * 3)
+            # m_jointVelFactorDim == 1: ConstrainedJointCenterNormVelocityFactor (reference src/lowerBodyPoseEstimator.cpp:194-204)
+            ft, sig = (abi.F_JOINTVEL_VEC, [10.0] * 3) if joint_vel_dim == 3 else (abi.F_JOINTVEL_NORM, [float(np.linalg.norm([10.0] * 3))])
+            g.add_slot(ft, [(K_, pose(a)), (K_, vel(a)), (K_, angv(a)), (ST, sidx[sa]),
+                            (K_, pose(b)), (K_, vel(b)), (K_, angv(b)), (ST, sidx[sb])], sig)
         jvel(SAC, RT, "sacrumImuToRHipCtr", "rthighImuToHipCtr"); jvel(RT, RS, "rthighImuToKneeCtr", "rshankImuToKneeCtr")
         jvel(RS, RF, "rshankImuToAnkleCtr", "rfootImuToAnkleCtr"); jvel(SAC, LT, "sacrumImuToLHipCtr", "lthighImuToHipCtr")
         jvel(LT, LS, "lthighImuToKneeCtr", "lshankImuToKneeCtr"); jvel(LS, LF, "lshankImuToAnkleCtr", "lfootImuToAnkleCtr")

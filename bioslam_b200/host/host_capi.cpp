@@ -103,6 +103,7 @@ int b200h_lbpe_set(void* pv, const char* name, const double* v, int n) {
     const std::string s(name);
     (void)n;
     if (s == "m_useJointVelFactor") p.m_useJointVelFactor = v[0] != 0;
+    else if (s == "m_jointVelFactorDim") p.m_jointVelFactorDim = (unsigned)v[0];
     else if (s == "m_assumeHipHinge") p.m_assumeHipHinge = v[0] != 0;
     else if (s == "m_assumeAnkleHinge") p.m_assumeAnkleHinge = v[0] != 0;
     else if (s == "m_hingeAxisFactorDim") p.m_hingeAxisFactorDim = (unsigned)v[0];

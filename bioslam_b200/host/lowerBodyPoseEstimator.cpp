@@ -103,8 +103,10 @@ void lowerBodyPoseEstimator::setup() {
     joint(LT, LS, lthighImuToKneeCtr, lshankImuToKneeCtr, m_kneeJointCtrConnectionNoise);
     joint(LS, LF, lshankImuToAnkleCtr, lfootImuToAnkleCtr, m_ankleJointCtrConnectionNoise);
     if (m_useJointVelFactor) {  // :183-204
-        if (m_jointVelFactorDim != 3) throw std::runtime_error("only the vector joint-velocity error model is available in this build");
-        auto jvel = [&](int a, int b, int sa, int sb) { gb.addSlot(B200_F_JOINTVEL_VEC, {pose(a), vel(a), angv(a), S(sa), pose(b), vel(b), angv(b), S(sb)}, v3(m_jointCtrVelConnectionNoise), 0, (int)K); };
+        const int jvType = m_jointVelFactorDim == 3 ? B200_F_JOINTVEL_VEC : (m_jointVelFactorDim == 1 ? B200_F_JOINTVEL_NORM : -1);   // :186-204
+        if (jvType < 0) throw std::runtime_error("unknown factor dimension");
+        const std::vector<double> jvSig = m_jointVelFactorDim == 3 ? v3(m_jointCtrVelConnectionNoise) : std::vector<double>{m_jointCtrVelConnectionNoise.norm()};
+        auto jvel = [&](int a, int b, int sa, int sb) { gb.addSlot(jvType, {pose(a), vel(a), angv(a), S(sa), pose(b), vel(b), angv(b), S(sb)}, jvSig, 0, (int)K); };
         jvel(SAC, RT, sacrumImuToRHipCtr, rthighImuToHipCtr); jvel(RT, RS, rthighImuToKneeCtr, rshankImuToKneeCtr); jvel(RS, RF, rshankImuToAnkleCtr, rfootImuToAnkleCtr);
         jvel(SAC, LT, sacrumImuToLHipCtr, lthighImuToHipCtr); jvel(LT, LS, lthighImuToKneeCtr, lshankImuToKneeCtr); jvel(LS, LF, lshankImuToAnkleCtr, lfootImuToAnkleCtr);
     }

@@ -109,7 +109,10 @@ typedef enum {
     /* bioslam::MagPose3Factor (src/factors/MagPose3Factor.cpp:12-38). vars: pose.
      * params[0..2]=sigmas, [3..5]=B_global (scale*direction + bias).  consts (3): measured field in body frame */
     B200_F_MAG_POSE3 = 19,
-    B200_F_NUM_TYPES = 20
+    /* bioslam::ConstrainedJointCenterNormVelocityFactor (src/factors/ConstrainedJointCenterVelocityFactor.cpp:137-214): the norm of the
+     * vector error of B200_F_JOINTVEL_VEC (gtsam::norm3 chain rule).  Same variables.  params[0]=sigma */
+    B200_F_JOINTVEL_NORM = 20,
+    B200_F_NUM_TYPES = 21
 } b200_factor_type;
 
 #define B200_MAX_FACTOR_VARS 8

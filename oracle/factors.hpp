@@ -46,6 +46,7 @@ inline const FactorInfo& factor_info(int type) {
         /* PRIOR_UNIT3    */ {2, 1, {B200_VAR_UNIT3}, 0, 0, 0},
         /* PRIOR_POSE3    */ {6, 1, {B200_VAR_POSE3}, 0, 0, 0},
         /* MAG_POSE3      */ {3, 1, {B200_VAR_POSE3}, 3, 0, 0},
+        /* JOINTVEL_NORM  */ {1, 8, {B200_VAR_POSE3, B200_VAR_VEC3, B200_VAR_VEC3, B200_VAR_VEC3, B200_VAR_POSE3, B200_VAR_VEC3, B200_VAR_VEC3, B200_VAR_VEC3}, 0, 0, 0},
     };
     return T[type];
 }
@@ -261,22 +262,33 @@ inline void factor_eval(int type, const double* params, const double* consts, co
             if (J) { double u[3]; norm3_grad(e, n, u); for (int c = 0; c < 18; c++) J[c] = u[0] * J3[c] + u[1] * J3[18 + c] + u[2] * J3[36 + c]; }
         }
     } break;
-    case B200_F_JOINTVEL_VEC: {  // src/factors/ConstrainedJointCenterVelocityFactor.cpp:68-131
+    case B200_F_JOINTVEL_VEC:
+    case B200_F_JOINTVEL_NORM: {  // src/factors/ConstrainedJointCenterVelocityFactor.cpp:68-131 (vector error), :137-214 (its norm)
         // cols: xA(6) vA(3) wA(3) sA(3) xB(6) vB(3) wB(3) sB(3) = 30
+        const bool vec = type == B200_F_JOINTVEL_VEC;
+        double e[3], J3[90] = {0};
+        double* Jt = vec ? J : J3;
+        const int ldt = vec ? ld : 30;
         for (int side = 0; side < 2; side++) {
             const double *X = x[4 * side], *V = x[4 * side + 1], *W = x[4 * side + 2], *S_ = x[4 * side + 3];
             double sg = side == 0 ? 1.0 : -1.0;
             double ws[3], Rws[3];
             v3cross(ws, W, S_); m3v(Rws, X, ws);
-            for (int i = 0; i < 3; i++) { double t = V[i] + Rws[i]; if (side == 0) r[i] = t; else r[i] -= t; }
+            for (int i = 0; i < 3; i++) { double t = V[i] + Rws[i]; if (side == 0) e[i] = t; else e[i] -= t; }
             if (J) {
                 int c0 = 15 * side;
                 double Sk[9], T[9];
-                skew(Sk, ws); m3mul(T, X, Sk); put33(J, ld, 0, c0, T, -sg);        // -R [w x s]x
-                putI3(J, ld, 0, c0 + 6, sg);
-                skew(Sk, S_); m3mul(T, X, Sk); put33(J, ld, 0, c0 + 9, T, -sg);    // -R [s]x
-                skew(Sk, W); m3mul(T, X, Sk); put33(J, ld, 0, c0 + 12, T, sg);     //  R [w]x
+                skew(Sk, ws); m3mul(T, X, Sk); put33(Jt, ldt, 0, c0, T, -sg);        // -R [w x s]x
+                putI3(Jt, ldt, 0, c0 + 6, sg);
+                skew(Sk, S_); m3mul(T, X, Sk); put33(Jt, ldt, 0, c0 + 9, T, -sg);    // -R [s]x
+                skew(Sk, W); m3mul(T, X, Sk); put33(Jt, ldt, 0, c0 + 12, T, sg);     //  R [w]x
             }
+        }
+        if (vec) v3copy(r, e);
+        else {  // ConstrainedJointCenterNormVelocityFactor: ||e|| through gtsam::norm3
+            double n = v3norm(e);
+            r[0] = n;
+            if (J) { double u[3]; norm3_grad(e, n, u); for (int c = 0; c < 30; c++) J[c] = u[0] * J3[c] + u[1] * J3[30 + c] + u[2] * J3[60 + c]; }
         }
     } break;
     case B200_F_SEGLEN_MAG:

@@ -107,9 +107,10 @@ def test_every_factor_type_device_functions(emu):
 
 
 def test_non_default_factor_variants(emu):
-    """norm-error hinge / joint-centre factors and the magnetometer factor inside the lower-body graph"""
+    """norm-error hinge / joint-centre position / joint-centre velocity factors and the magnetometer factor inside the lower-body graph"""
     tr = synth.make_trial(seed=8, duration_s=1.0)
-    g, tv, sv = graphs.lower_body_graph(tr, hinge_dim=1, joint_pos_dim=1, magnetometer=True)
+    g, tv, sv = graphs.lower_body_graph(tr, hinge_dim=1, joint_pos_dim=1, magnetometer=True, use_joint_vel=True, joint_vel_dim=1)
+    assert abi.F_JOINTVEL_NORM in {s.type for s in g.slots}
     tv, sv = graphs.perturbed_truth_values(tr, g, tv, sv)
     o = po.OracleProblem(g); o.set_values(tv, sv)
     p = lib.Problem(g, so_path=emu, chunks=2); p.set_values(tv, sv)

@@ -219,12 +219,12 @@ def test_indeterminate_and_bad_args():
 
 
 def test_every_factor_type_on_device_matches_fixtures(po):
-    """all 20 factor types (incl. the non-default HingeJointConstraintNormErrEstAngVel, ConstrainedJointCenterNormPositionFactor,
+    """all 21 factor types (incl. the non-default HingeJointConstraintNormErrEstAngVel, ConstrainedJointCenterNormPositionFactor,
     MagPose3Factor and PriorFactor<Pose3>) evaluated by the device functions of linearize_kernel against tests/golden/factors.npz
     (residual 1e-13, Jacobian 1e-12) and, whitened, against the oracle on the same inputs"""
     import os
     d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "factors.npz"))
-    assert len(abi.FACTOR_INFO) == 20
+    assert len(abi.FACTOR_INFO) == 21
     for ft in sorted(abi.FACTOR_INFO):
         params, consts, x = d[f"f{ft}_params"], d[f"f{ft}_consts"], d[f"f{ft}_x"]
         r, J = lib.factor_eval(ft, params, consts, x)
@@ -236,18 +236,20 @@ def test_every_factor_type_on_device_matches_fixtures(po):
         assert np.allclose(Jw, Jo, rtol=1e-11, atol=1e-11 * max(1.0, np.abs(Jo).max())), ft
 
 
-@pytest.mark.parametrize("variant", ["hinge_norm", "jointpos_norm", "magnetometer", "all"])
+@pytest.mark.parametrize("variant", ["hinge_norm", "jointpos_norm", "magnetometer", "jointvel_norm", "all"])
 def test_non_default_factor_variants_in_the_graph(po, variant):
     """m_hingeAxisFactorDim = 1, m_jointPosFactorDim = 1, m_useMagnetometer = true (reference src/lowerBodyPoseEstimator.cpp:170,218,
     248,270; src/imuPoseEstimator.cpp:216-219): linearization, solve and LM parity with the oracle on the CUDA path"""
     kw = {"hinge_norm": dict(hinge_dim=1), "jointpos_norm": dict(joint_pos_dim=1), "magnetometer": dict(magnetometer=True),
-          "all": dict(hinge_dim=1, joint_pos_dim=1, magnetometer=True)}[variant]
+          "jointvel_norm": dict(use_joint_vel=True, joint_vel_dim=1),
+          "all": dict(hinge_dim=1, joint_pos_dim=1, magnetometer=True, use_joint_vel=True, joint_vel_dim=1)}[variant]
     tr = synth.make_trial(seed=8, duration_s=4.0)
     g, tv, sv = graphs.lower_body_graph(tr, **kw)
     types = {s.type for s in g.slots}
     if "hinge_dim" in kw: assert abi.F_HINGE_NORM in types and abi.F_HINGE_VEC not in types
     if "joint_pos_dim" in kw: assert abi.F_JOINTPOS_NORM in types and abi.F_JOINTPOS_VEC not in types
     if "magnetometer" in kw: assert abi.F_MAG_POSE3 in types
+    if "joint_vel_dim" in kw: assert abi.F_JOINTVEL_NORM in types and abi.F_JOINTVEL_VEC not in types
     tv, sv = graphs.perturbed_truth_values(tr, g, tv, sv)
     o = po.OracleProblem(g, threads=8); o.set_values(tv, sv)
     p = lib.Problem(g, chunks=3); p.set_values(tv, sv)

@@ -11,7 +11,7 @@ TOL = {  # reference tolerances: test/unit/test*.cpp (1e-9 hinge/joint-pos, 1e-7
     abi.F_HINGE_VEC: 1e-8, abi.F_JOINTPOS_VEC: 1e-8, abi.F_ANGVEL: 1e-7, abi.F_SEGLEN_MAG: 1e-7, abi.F_SEGLEN_MAX: 1e-7,
     abi.F_SEGLEN_MIN: 1e-7, abi.F_SEGLEN_DISCREPANCY: 1e-7, abi.F_JOINTVEL_VEC: 1e-7, abi.F_HINGE_NORM: 1e-5, abi.F_JOINTPOS_NORM: 1e-5,
     abi.F_ANGLE_AXIS_SEG: 1e-5, abi.F_POSE3_COMPASS_PRIOR: 5e-3, abi.F_POSE3_TRANSLATION_PRIOR: 1e-8, abi.F_PRIOR_VEC3: 1e-9,
-    abi.F_PRIOR_BIAS6: 1e-9, abi.F_MAG_POSE3: 1e-8, abi.F_IMU_COMBINED: 1e-6, abi.F_IMU_STATICBIAS: 1e-6,
+    abi.F_PRIOR_BIAS6: 1e-9, abi.F_MAG_POSE3: 1e-8, abi.F_IMU_COMBINED: 1e-6, abi.F_IMU_STATICBIAS: 1e-6, abi.F_JOINTVEL_NORM: 1e-5,
 }
 
 
