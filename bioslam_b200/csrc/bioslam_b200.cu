@@ -601,7 +601,8 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
             if (ds.pipe && std::getenv("B200_NO_DENSE_STREAM")) ds.pipe = 2;   // (development switch: level 0 pipelined, dense levels on the round-1 kernel)
         }
         // back-substitution / top level: factor block + vectors; the static system (ns1 x lds) reuses the block area
-        const size_t bs = (size_t)backsub_smem_doubles(ds.ntp, ds.ld);
+        ds.bs_os = (sizeof(double) * (size_t)backsub_smem_doubles(ds.ntp, ds.ld, ds.nc) + 16 <= smem_cap) ? 1 : 0;
+        const size_t bs = (size_t)backsub_smem_doubles(ds.ntp, ds.ld, ds.bs_os ? ds.nc : 0);
         if ((size_t)static_lds(ds.ns) * (ds.ns1 + 1) > (size_t)ds.ntp * ds.ld + 4 * 256)
             return fail("static block larger than the time block is not supported", B200_NOT_IMPLEMENTED);
         p->smem_backsub = (sizeof(double) * bs + 15) & ~(size_t)15;
@@ -935,7 +936,8 @@ static void launch_level_factor(b200_problem* p, const Level& lv, int c_lo, int 
     if (lv.dense_o) B200_LAUNCH(chain_sweep_kernel<true>, sgrid, dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, dm, lv, p->sb, c_lo);
     else B200_LAUNCH(chain_sweep_kernel<false>, sgrid, dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, dm, lv, p->sb, c_lo);
     // few chunks (upper levels): split the output tiles of a chunk's Schur complement over several CTAs
-    const int nsplit = (c_hi - c_lo) * 2 <= 148 ? 2 : 1;
+    // (21 = 32 x 32 tiles of the lower triangle of a 165 x 165 complement; a CTA with one or two tiles still stages whole panels, from L2)
+    const int nsplit = std::max(1, std::min(148 / std::max(1, c_hi - c_lo), 21));
     B200_LAUNCH(chain_schur_kernel, dim3(c_hi - c_lo, nsplit), dim3(B200_SCHUR_THREADS), p->smem_schur, p->stream, dm, lv, p->sb, c_lo, p->schur_ldy,
                 p->schur_kslab);
     p->launches += 2;

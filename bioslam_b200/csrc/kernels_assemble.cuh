@@ -21,6 +21,7 @@ struct Dims {
     // solver: structure of the time-coupling block O (rows = chain dofs of keyframe k+1, columns = chain dofs of k)
     int cr;                        // panel rows resident in shared memory at a time (multiple of 16)
     int pipe;                      // level-0 sweep: use the keyframe-pipelined variant (kernels_sweep_pipe.cuh)
+    int bs_os;                     // back-substitution: the coupling block of the node in flight is staged in shared memory
     int ow, owp;                   // packed width of a row of O (even) and its shared-memory stride (ow + 2)
     const int* orow;               // [nc][2] structural non-zero column range [c0, c1) of every row of O
     const int* ocol;               // [nc][2] structural non-zero row range [r0, r1) of every column of O

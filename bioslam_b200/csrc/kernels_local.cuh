@@ -60,9 +60,20 @@ __global__ void __launch_bounds__(B200_LE_THREADS, 3) local_elim_kernel(LocalEli
     }
     // panel rows [D_cl ; A_l ; -g_l^T] (every warp but the first), while warp 0 factorises the local block
     if (warp > 0) {
-        for (int e = threadIdx.x - 32; e < hp * nl; e += blockDim.x - 32) {
-            const int r = e / nl, c = e - r * nl;
-            Vs[r * ldl + c] = (r < nc) ? Dk[(long long)(nl + r) * ntp + c] : Ak[(long long)(r - nc) * ntp + c];
+        // lane c < nl reads column c of the rows  warp - 1, warp - 1 + (nwarps - 1), ...; eight rows per batch, all loads of a batch
+        // issued before the first shared-memory store
+        for (int r0 = warp - 1; r0 < hp; r0 += 8 * (nwarps - 1)) {
+            double x[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int r = r0 + q * (nwarps - 1);
+                x[q] = (lane < nl && r < hp) ? __ldg((r < nc) ? Dk + (long long)(nl + r) * ntp + lane : Ak + (long long)(r - nc) * ntp + lane) : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int r = r0 + q * (nwarps - 1);
+                if (lane < nl && r < hp) Vs[r * ldl + lane] = x[q];
+            }
         }
     } else {
         // Cholesky of the nl x nl block (nl <= 32) by ONE warp in registers: lane l owns row l (identity beyond nl), the pivot and
@@ -148,22 +159,40 @@ __global__ void __launch_bounds__(B200_LE_THREADS, 3) local_elim_kernel(LocalEli
         if (kind == 0) warp_mma_nt(Vs, ldl, m0, nc, Vs, ldl, c0, nc, 0, nl, acc);
         else if (kind == 1) warp_mma_nt(Va, ldl, m0, ns1, Vs, ldl, c0, nc, 0, nl, acc);
         else warp_mma_nt(Va, ldl, m0, ns1, Va, ldl, c0, ns1, 0, nl, acc);
+        // epilogue: reduced = source - acc.  The source entries of half a tile (8 per lane) are loaded in ONE batch before the first
+        // store: source and destination pointers may alias as far as the compiler knows, so a load written after a store waits for it
+        // -- entry by entry that is 16 exposed L2 / DRAM round trips per tile instead of 2.
+        const int R = (kind == 0) ? nc : ns1;                       // rows of this tile's matrix
+        const int rb = (kind == 0) ? 0 : nc, cb = (kind == 2) ? nc : 0;   // s_row offsets of its rows / columns
+        const bool tri = kind != 1;                                 // lower triangle only
 #pragma unroll
         for (int i = 0; i < 2; i++) {
             const int r = m0 + 8 * i + mg;
+            const bool rok = r < R;
+            const int rr = rok ? r : 0;
+            const bool rnz = s_row[rb + rr] != 0;
+            const double* srcp = (kind == 0) ? Dk + (long long)(nl + rr) * ntp + nl : (kind == 1) ? Ak + (long long)rr * ntp + nl : Sk + (long long)rr * ns1;
+            double* dstp = (kind == 0) ? Dck + (long long)rr * ncp : (kind == 1) ? Ack + (long long)rr * ncp : Sck + (long long)rr * ns1;
+            const int cend = tri ? rr + 1 : nc;
+            double src[4][2];
+            bool w[4][2];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
                     const int c = c0 + 8 * j + 2 * mt + e;
-                    if (kind == 0) {
-                        if (r < nc && c <= r && (full || r == c || (s_row[r] && s_row[c])))
-                            Dck[(long long)r * ncp + c] = Dk[(long long)(nl + r) * ntp + nl + c] + (r == c ? lambda : 0.0) - acc[i][j][e];
-                    } else if (kind == 1) {
-                        if (r < ns1 && c < nc && (full || (s_row[nc + r] && s_row[c]))) Ack[(long long)r * ncp + c] = Ak[(long long)r * ntp + nl + c] - acc[i][j][e];
-                    } else if (r < ns1 && c <= r && (full || (s_row[nc + r] && s_row[nc + c]))) {
-                        Sck[(long long)r * ns1 + c] = Sk[(long long)r * ns1 + c] - acc[i][j][e];   // (consumers read the lower triangle)
-                    }
+                    bool ok = rok && c < cend;
+                    if (ok && !full) ok = (kind == 0 && r == c) || (rnz && s_row[cb + c] != 0);
+                    w[j][e] = ok;
+                    src[j][e] = ok ? __ldg(srcp + c) : 0.0;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int c = c0 + 8 * j + 2 * mt + e;
+                    if (w[j][e]) dstp[c] = src[j][e] + ((kind == 0 && r == c) ? lambda : 0.0) - acc[i][j][e];
                 }
             }
         }

@@ -1563,7 +1563,9 @@ __global__ void __launch_bounds__(256) chain_reduce_kernel(Dims dm, Level lv, in
     const double* Fn = lv.F + ((long long)(c + 1) * nsp * 2 + (n_n & 1)) * Fsz;
     double* Or = lv.Ored + (long long)c * nc * nc;
     const int e1 = ntp * ntp, e2 = e1 + ns1 * ntp, e3 = e2 + ns1 * ns1, e4 = e3 + (has_o ? nc * nc : 0);
-    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < e4; e += blockDim.x * gridDim.y) {
+    // value and destination of entry e.  Four entries per pass: their loads are all issued before the first store (the source and
+    // destination pointers may alias as far as the compiler knows, so a load written after a store would wait for it)
+    auto entry = [&](int e, double*& dst) -> double {
         if (e < e1) {
             const int r = e / ntp, col = e % ntp;
             double v = Dg[e];
@@ -1573,7 +1575,8 @@ __global__ void __launch_bounds__(256) chain_reduce_kernel(Dims dm, Level lv, in
                 if (n_c > 0) v -= Fc[(long long)hi * nc + lo];
                 v += Sn[(long long)(ns1 + hi) * hmax + (ns1 + lo)];
             }
-            Dr[e] = v;
+            dst = Dr + e;
+            return v;
         } else if (e < e2) {
             const int f = e - e1, ar = f / ntp, col = f % ntp;
             double v = Ag[f];
@@ -1581,17 +1584,29 @@ __global__ void __launch_bounds__(256) chain_reduce_kernel(Dims dm, Level lv, in
                 if (n_c > 0) v -= Fc[(long long)split_owner(h_c, nsp, ar) * 2 * Fsz + (long long)(nc + ar) * nc + (col - nl)];
                 v += Sn[(long long)(ns1 + (col - nl)) * hmax + ar];
             }
-            Ar[f] = v;
+            dst = Ar + f;
+            return v;
         } else if (e < e3) {
             const int f = e - e2, r = f / ns1, col = f % ns1;
             const int hi = r > col ? r : col, lo = r > col ? col : r;
             double v = Sg[f] + Sn[(long long)hi * hmax + lo];
             if (c == 0) v += S0[(long long)hi * hmax + lo];
-            Sr[f] = v;
+            dst = Sr + f;
+            return v;
         } else {
             const int f = e - e3, i = f / nc, j = f % nc;   // Or[j][i]: row = chain j of separator c+1, col = chain i of separator c
-            Or[(long long)j * nc + i] = -Fn[(long long)split_owner(h_n, nsp, ns1 + i) * 2 * Fsz + (long long)(nc + ns1 + i) * nc + j];
+            dst = Or + (long long)j * nc + i;
+            return -Fn[(long long)split_owner(h_n, nsp, ns1 + i) * 2 * Fsz + (long long)(nc + ns1 + i) * nc + j];
         }
+    };
+    const int stride = blockDim.x * gridDim.y;
+    for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < e4; e += 4 * stride) {
+        double v[4];
+        double* d[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { d[q] = nullptr; v[q] = 0.0; if (e + q * stride < e4) v[q] = entry(e + q * stride, d[q]); }
+#pragma unroll
+        for (int q = 0; q < 4; q++) if (d[q]) *d[q] = v[q];
     }
 }
 
@@ -1650,10 +1665,16 @@ __global__ void __launch_bounds__(B200_PREPASS_THREADS) chain_backsub_prepass_ke
 }
 
 // shared-memory carve-up of the back-substitution (doubles): Ms [ntp*ld] | u [256] | v [256] | cx [256] | yv [256] | coef [512] | part [512]
-__host__ __device__ inline long long backsub_smem_doubles(int ntp, int ld) { return (long long)ntp * ld + 4 * 256 + 512 + 512; }
+// | Os [nc*nc] (the coupling block of the node in flight, only when dm.bs_os: it fits next to the rest)
+__host__ __device__ inline long long backsub_smem_doubles(int ntp, int ld, int nc_os = 0) {
+    return (long long)ntp * ld + 4 * 256 + 512 + 512 + (long long)nc_os * nc_os;
+}
 
 // back-substitution over the nodes of a sweep (reverse order).  right_st: storage index of the right neighbour (or -1).
 // y_ready: y = Y^T coef was computed by the pre-pass (sb.ybuf), else it is computed here from coef (shared memory).
+// Nothing on the chain waits for global memory after the first node: the factor W^T and y of the NEXT node travel through
+// registers while this node is processed, its coupling block O is copied (cp.async) into shared memory as soon as this node's
+// O^T delta is done, and the step of this node is handed to the next one in shared memory.
 __device__ void cta_backsub(const Dims& dm, const SweepArgs& a, const double* coef, long long right_st, const SolveBuffers& sb, bool y_ready,
                             double* sm) {
     const int n = dm.ntp, nl = dm.nl, nc = dm.nc, ld = dm.ld, hmax = dm.hmax;
@@ -1664,10 +1685,49 @@ __device__ void cta_backsub(const Dims& dm, const SweepArgs& a, const double* co
     double* cx = v + 256;
     double* yv = cx + 256;
     double* part = yv + 256 + 512;
+    double* Os = part + 512;
     double* delta = sb.delta;
-    // The factor W^T of the NEXT node travels through registers while this node is processed: every thread owns up to NPRE
-    // 16-byte pairs of the upper triangle (rows r, columns from r & ~1), loads them right after the barrier that opens a node and
-    // writes them to shared memory after the node's last barrier, so the chain never waits for a copy (only the first node does).
+    const bool os_ok = dm.bs_os != 0 && nc > 0;
+    // structural part of the coupling block of node `src` -> Os (same row-major layout as in global memory).  Sparse coupling
+    // (level 0): every thread owns up to NOS structural entries, their offsets found once (registers), not per node.
+    constexpr int NOS = 6;
+    int ooff[NOS];
+    bool o_list = false;
+    if (os_ok && !a.dense_o) {
+        int total = 0;
+        for (int r = 0; r < nc; r++) total += dm.orow[2 * r + 1] - dm.orow[2 * r];
+        o_list = total <= NOS * (int)blockDim.x;
+        int r = 0, row_begin = 0, len = nc > 0 ? dm.orow[1] - dm.orow[0] : 0;
+#pragma unroll
+        for (int j = 0; j < NOS; j++) {
+            const int e = j * (int)blockDim.x + (int)threadIdx.x;
+            ooff[j] = -1;
+            if (o_list && e < total) {
+                while (e >= row_begin + len) { row_begin += len; r++; len = dm.orow[2 * r + 1] - dm.orow[2 * r]; }
+                ooff[j] = r * nc + dm.orow[2 * r] + (e - row_begin);
+            }
+        }
+    }
+    auto stage_o = [&](long long src) {
+        const double* Og = a.Osrc + src * nc * nc;
+        if (a.dense_o) {
+            if ((nc & 1) == 0) for (int e = 2 * threadIdx.x; e < nc * nc; e += 2 * blockDim.x) cp_async16(Os + e, Og + e);
+            else for (int e = threadIdx.x; e < nc * nc; e += blockDim.x) cp_async8(Os + e, Og + e);
+        } else if (o_list) {
+#pragma unroll
+            for (int j = 0; j < NOS; j++) if (ooff[j] >= 0) cp_async8(Os + ooff[j], Og + ooff[j]);
+        } else {
+            for (int r = warp; r < nc; r += nwarps) {
+                const int c0 = dm.orow[2 * r], c1 = dm.orow[2 * r + 1];
+                for (int c = c0 + lane; c < c1; c += 32) cp_async8(Os + (long long)r * nc + c, Og + (long long)r * nc + c);
+            }
+        }
+    };
+    // structural row range of this thread's column of O (u = O^T delta_next), found once
+    int ur0 = 0, ur1 = nc;
+    if (!a.dense_o && (int)threadIdx.x < nc) { ur0 = dm.ocol[2 * threadIdx.x]; ur1 = dm.ocol[2 * threadIdx.x + 1]; }
+    // every thread owns up to NPRE 16-byte pairs of the upper triangle of W^T (rows r, columns from r & ~1): loaded right after the
+    // barrier that opens a node, written to shared memory after the node's last barrier
     constexpr int NPRE = 8;
     int goff[NPRE], soff[NPRE];
     {
@@ -1690,7 +1750,9 @@ __device__ void cta_backsub(const Dims& dm, const SweepArgs& a, const double* co
         if (!fits) goff[0] = -2;   // block too large for the register path: every node is copied synchronously
     }
     const bool reg_path = goff[0] != -2;
-    bool staged = false;           // Ms already holds this node's factor (written from registers at the end of the previous node)
+    const bool y_pre = y_ready && reg_path && n <= (int)blockDim.x;   // y of the next node through a register as well
+    bool staged = false;           // Ms / yv already hold this node's factor and y (written from registers at the end of the previous node)
+    bool first = true;
     for (int i = a.n - 1; i >= 0; i--) {
         const long long src = a.src0 + i;
         const long long st = a.st_idx ? a.st_idx[i] : src;
@@ -1700,30 +1762,42 @@ __device__ void cta_backsub(const Dims& dm, const SweepArgs& a, const double* co
         else if (a.has_right) nxt = right_st;
         __syncthreads();
         if (!staged) cp_upper_async(Ms, ld, a.Wst + st * n * n, n, n, n);
+        if (first && has_x && os_ok) stage_o(src);
         double2 pre[NPRE];
+        double ypre = 0.0;
         const bool prefetch = reg_path && i > 0;
         if (prefetch) {
             const long long stn = a.st_idx ? a.st_idx[i - 1] : src - 1;
             const double* Wn = a.Wst + stn * n * n;
 #pragma unroll
             for (int j = 0; j < NPRE; j++) pre[j] = goff[j] >= 0 ? ld2(Wn + goff[j]) : make_double2(0.0, 0.0);
+            if (y_pre && (int)threadIdx.x < n) ypre = sb.ybuf[stn * n + threadIdx.x];
         }
-        if (has_x) for (int j = threadIdx.x; j < nc; j += blockDim.x) cx[j] = delta[nxt * n + nl + j];
-        if (y_ready) for (int c = threadIdx.x; c < n; c += blockDim.x) yv[c] = sb.ybuf[st * n + c];
-        __syncthreads();
+        if (first) {
+            if (has_x) for (int j = threadIdx.x; j < nc; j += blockDim.x) cx[j] = delta[nxt * n + nl + j];
+            if (os_ok) cp_async_wait_all();
+        }
+        if (y_ready && !(staged && y_pre)) for (int c = threadIdx.x; c < n; c += blockDim.x) yv[c] = sb.ybuf[st * n + c];
+        if (first || !(staged && y_pre)) __syncthreads();
         if (!y_ready) cta_yt_coef(a.Yst + st * (long long)hmax * n, n, a.h, coef, part, yv);
         if (has_x) {
             // u = O^T delta_next (structural row range of every column)
-            const double* Og = a.Osrc + src * nc * nc;
+            const double* Ob = os_ok ? Os : a.Osrc + src * nc * nc;
             for (int k = threadIdx.x; k < nc; k += blockDim.x) {
-                const int r0 = a.dense_o ? 0 : dm.ocol[2 * k], r1 = a.dense_o ? nc : dm.ocol[2 * k + 1];
-                double s = 0.0;
-                for (int r = r0; r < r1; r++) s = fma(Og[(long long)r * nc + k], cx[r], s);
-                u[k] = s;
+                const int r0 = (k == (int)threadIdx.x) ? ur0 : (a.dense_o ? 0 : dm.ocol[2 * k]), r1 = (k == (int)threadIdx.x) ? ur1 : (a.dense_o ? nc : dm.ocol[2 * k + 1]);
+                double s0 = 0.0, s1 = 0.0;
+                int r = r0;
+                for (; r + 1 < r1; r += 2) {
+                    s0 = fma(Ob[(long long)r * nc + k], cx[r], s0);
+                    s1 = fma(Ob[(long long)(r + 1) * nc + k], cx[r + 1], s1);
+                }
+                if (r < r1) s0 = fma(Ob[(long long)r * nc + k], cx[r], s0);
+                u[k] = s0 + s1;
             }
         }
         cp_async_wait_all();
         __syncthreads();
+        if (os_ok && i > 0) stage_o(src - 1);   // (lands during the two products below; waited for before the next node opens)
         // v = y + W[:, chain] u :  v[c] = y[c] + sum_{k: nl+k <= c} Wt[nl+k][c] u[k].  Four adjacent lanes share a column
         // (k = q, q + 4, ...), partial sums meet through two shuffles: the dependent FMA chain is a quarter as long
         for (int base = 0; base < 4 * n; base += blockDim.x) {
@@ -1739,26 +1813,32 @@ __device__ void cta_backsub(const Dims& dm, const SweepArgs& a, const double* co
             if (q == 0 && c < n) v[c] = yv[c] + s;
         }
         __syncthreads();
-        // delta[k] = - sum_{c >= k} Wt[k][c] v[c]
-        for (int k0 = 2 * warp; k0 < n; k0 += 2 * nwarps) {   // half a warp per row
-            const int k = k0 + (lane >> 4), hl = lane & 15;
+        // delta[k] = - sum_{c >= k} Wt[k][c] v[c]; the chain part is handed to the next node in shared memory (cx)
+        for (int base = 0; base < 4 * n; base += blockDim.x) {   // four adjacent lanes per row (c = k + q, k + q + 4, ...)
+            const int idx = base + threadIdx.x;
+            const int k = idx >> 2, q = idx & 3;
             double s = 0.0;
             if (k < n) {
                 const double* row = Ms + (long long)k * ld;
-                for (int c = k + hl; c < n; c += 16) s = fma(row[c], v[c], s);
+                for (int c = k + q; c < n; c += 4) s = fma(row[c], v[c], s);
             }
-#pragma unroll
-            for (int o = 8; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (hl == 0 && k < n) delta[st * n + k] = -s;
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (q == 0 && k < n) {
+                delta[st * n + k] = -s;
+                if (k >= nl) cx[k - nl] = -s;
+            }
         }
-        __threadfence_block();
         staged = false;
         if (prefetch) {
             __syncthreads();   // every warp is done with this node's factor
 #pragma unroll
             for (int j = 0; j < NPRE; j++) if (soff[j] >= 0) st2(Ms + soff[j], pre[j].x, pre[j].y);
+            if (y_pre && (int)threadIdx.x < n) yv[threadIdx.x] = ypre;
             staged = true;
         }
+        cp_async_wait_all();
+        first = false;
     }
     __syncthreads();
 }
