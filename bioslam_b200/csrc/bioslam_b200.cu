@@ -63,6 +63,7 @@ static bool finfo(int type, FInfo& f) {
     }
 }
 
+#define B200_MAX_SPLIT 11   // CTAs per chunk sweep on the upper levels (arrow rows split in whole 16-row tiles: 165 rows = 11 tiles)
 enum { SC_LIN_ERR = 0, SC_MODEL_ERR = 1, SC_NEW_ERR = 2, SC_CUR_ERR = 3, SC_FAIL = 4, SC_COUNT = 8 };
 
 // Levenberg-Marquardt state on the device (north_star subsystem 4: "the trust-region / damping update on device"): written by
@@ -497,7 +498,7 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
         le.D = p->d_D; le.A = p->d_A; le.S = p->d_S; le.Dc = p->d_Dc; le.Ac = p->d_Ac; le.Sc = p->d_Sc; le.V = p->d_V; le.Wl = p->d_Wl;
         p->smem_le = sizeof(double) * (size_t)le_smem_doubles(nl, dm.nc, dm.ns1);
     } else p->d_delta = p->sb.delta;
-    CK(dalloc(&p->d_Ftop, (size_t)2 * (ds.nc + ds.hmax) * ds.nc)); CK(dalloc(&p->d_Stop, (size_t)ds.hmax * ds.hmax));
+    CK(dalloc(&p->d_Ftop, (size_t)B200_MAX_SPLIT * 2 * (ds.nc + ds.hmax) * ds.nc)); CK(dalloc(&p->d_Stop, (size_t)ds.hmax * ds.hmax));
     CK(dalloc(&p->d_top_begin, (size_t)2));
     {
         // structure of the time-coupling block O in SOLVER coordinates: which chain dofs of keyframe k+1 (rows) meet which chain
@@ -768,7 +769,7 @@ static b200_status set_partition(b200_problem* p, int P1, int P2) {
         CK(cudaStreamSynchronize(p->stream));
         // upper levels on one GPU: few chunks, many idle SMs -> several CTAs per chunk sweep (row split, see Level::nsplit)
         l.nsplit = 1;
-        if (li > 0 && (W == 1 || li >= 2)) { while (l.nsplit < 4 && l.P * (l.nsplit + 1) <= 148) l.nsplit++; }
+        if (li > 0 && (W == 1 || li >= 2)) { while (l.nsplit < B200_MAX_SPLIT && l.P * (l.nsplit + 1) <= 148) l.nsplit++; }
         CK(dalloc(&l.F, (P + 1) * l.nsplit * 2 * Fsz)); CK(dalloc(&l.S, (P + 1) * Ssz));
         CK(dalloc(&l.Dred, P * dm.ntp * dm.ntp)); CK(dalloc(&l.Ored, P * dm.nc * dm.nc));
         CK(dalloc(&l.Ared, P * dm.ns1 * dm.ntp)); CK(dalloc(&l.Sred, P * dm.ns1 * dm.ns1));
@@ -791,6 +792,7 @@ static b200_status set_partition(b200_problem* p, int P1, int P2) {
         CK(cudaMemcpyAsync(p->d_top_begin, tb, sizeof(tb), cudaMemcpyHostToDevice, p->stream));
         CK(cudaStreamSynchronize(p->stream));
         t.begin = p->d_top_begin; t.P = 1; t.F = p->d_Ftop; t.S = p->d_Stop; t.dense_o = (nlev > 0); t.nsplit = 1;
+        if (t.dense_o && dm.pipe == 1) t.nsplit = B200_MAX_SPLIT;   // the single top-level chunk: its arrow rows over several CTAs as well
     }
     if (W > 1) {
         if (p->d_stageS) cudaFree(p->d_stageS);

@@ -1383,7 +1383,8 @@ struct SolveBuffers {
 __device__ __forceinline__ bool solve_skipped(const SolveBuffers& sb) { return sb.skip != nullptr && *sb.skip != 0; }
 
 // arrow rows [lo, hi) of split y out of ns (h rows in total)
-__device__ __forceinline__ int split_lo(int h, int ns, int y) { return (int)((long long)y * h / ns); }
+// (boundaries on multiples of 16 rows = whole row tiles of the sweep; a split may own no rows at all)
+__device__ __forceinline__ int split_lo(int h, int ns, int y) { const int lo = 16 * (int)((long long)y * ((h + 15) >> 4) / ns); return lo < h ? lo : h; }
 __device__ __forceinline__ int split_owner(int h, int ns, int row) { int y = 0; while (y + 1 < ns && split_lo(h, ns, y + 1) <= row) y++; return y; }
 
 __device__ __forceinline__ void level_chunk_args(const Dims& dm, const Level& lv, const SolveBuffers& sb, int c, SweepArgs& a, int y = 0) {

@@ -20,8 +20,13 @@ for l in dis[start + 1:]:
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
     if m:
         line_of_off[int(m.group(1), 16)] = (cur, m.group(2))
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + (os.environ.get("NCU_IMPORT_ARGS", "").split()), capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
+# a report with several launches repeats the two header rows per launch: keep launch NCU_LAUNCH (default 0)
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+if len(starts) > 1:
+    w = int(os.environ.get("NCU_LAUNCH", "0"))
+    rows = rows[starts[w]:(starts[w + 1] if w + 1 < len(starts) else len(rows))]
 hdr = rows[1]
 ia, isamp = hdr.index("Address"), hdr.index("# Samples")
 stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
