@@ -61,7 +61,10 @@ void imuPoseEstimator::setupCommon(bool combined) {
         }
         const std::vector<double> q = ekf::forwardBackwardEkf(gy, ac, dt, 3);
         const std::vector<unsigned> idx = getImuIndecesCorrespondingToKeyframes();
-        for (unsigned k = 0; k < K; k++) ekf::quatToRotBodyToNav(&q[4 * (size_t)idx[k]], m_initPose[k].R.m);
+        // upstream's setup loop inserts initPose[k] at keyframe k + 1 (src/imuPoseEstimator.cpp:221-223; keyframe 0 gets initPose[0],
+        // :170): keyframes 0 and 1 start from the same EKF sample and keyframe k >= 1 from the sample of keyframe k - 1.  Reproduced
+        // literally so that the LM trajectory starts where upstream's does.
+        for (unsigned k = 0; k < K; k++) ekf::quatToRotBodyToNav(&q[4 * (size_t)idx[k > 0 ? k - 1 : 0]], m_initPose[k].R.m);
     }
     m_initVel.assign(K, Vector3(0, 0, 0));
     m_initBias.assign(combined ? K : 1, ConstantBias());
@@ -195,7 +198,9 @@ void imuPoseEstimator::fastOptimize() {
     if (b200_problem_create(&gb.desc(), getDevice(), &prob) != B200_OK) throw std::runtime_error(std::string("b200_problem_create: ") + b200_last_error());
     b200_status st = b200_set_values(prob, gb.timeValues().data(), gb.staticValues().data());
     // LM parameters: :324-325 (lambda in [1e-8, 1e10]); tolerances from the members
-    b200_lm_params lm{1.0e-5, 10.0, 1.0e-8, 1.0e10, m_relErrDecreaseLimit, m_absErrDecreaseLimit, 1.0e-3, m_optType == 0 ? 1 : 0, 0};
+    b200_lm_params lm{1.0e-5, 10.0, 1.0e-8, 1.0e10, m_relErrDecreaseLimit, m_absErrDecreaseLimit, 1.0e-3, 0, 0};
+    // (gauss_newton = 0 whatever m_optType says: upstream's fastOptimize() always constructs a LevenbergMarquardtOptimizer, the
+    // Gauss-Newton line is commented out, src/imuPoseEstimator.cpp:327-329; m_optType is only a stored setting)
     std::vector<double> hist(m_maxIterations + 2, 0.0);
     b200_outer_params outer{m_absErrDecreaseLimit, m_relErrDecreaseLimit, m_absErrLimit, (int)m_maxIterations, 1, 1, (int)hist.size()};
     b200_optimize_result res{};

@@ -175,7 +175,8 @@ void lowerBodyPoseEstimator::fastOptimize(double prevGlobalErr) {
     b200_problem* prob = nullptr;
     if (b200_problem_create(&gb.desc(), getDevice(), &prob) != B200_OK) throw std::runtime_error(std::string("b200_problem_create: ") + b200_last_error());
     b200_status st = b200_set_values(prob, gb.timeValues().data(), gb.staticValues().data());
-    b200_lm_params lm{m_lambdaInitial, m_lambdaFactor, m_lambdaLowerBound, m_lambdaUpperBound, 1.0e-20, 1.0e-20, 1.0e-3, m_optimizerType == 0 ? 1 : 0, 0};  // :644-647
+    b200_lm_params lm{m_lambdaInitial, m_lambdaFactor, m_lambdaLowerBound, m_lambdaUpperBound, 1.0e-20, 1.0e-20, 1.0e-3, 0, 0};  // :644-647
+    // (always Levenberg-Marquardt, as upstream: m_optimizerType is only written to the results file, src/lowerBodyPoseEstimator.cpp:650, 1064)
     std::vector<double> hist(m_maxIterations + 2, 0.0);
     b200_outer_params outer{m_absErrDecreaseLimit, m_relErrDecreaseLimit, m_absErrLimit, (int)m_maxIterations, (int)m_convergeAtConsecSmallIter, 0, (int)hist.size()};
     b200_optimize_result res{};
