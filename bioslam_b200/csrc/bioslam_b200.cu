@@ -602,7 +602,7 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
             if (ds.pipe && std::getenv("B200_NO_DENSE_STREAM")) ds.pipe = 2;   // (development switch: level 0 pipelined, dense levels on the round-1 kernel)
         }
         // back-substitution / top level: factor block + vectors; the static system (ns1 x lds) reuses the block area
-        ds.bs_os = (sizeof(double) * (size_t)backsub_smem_doubles(ds.ntp, ds.ld, ds.nc) + 16 <= smem_cap) ? 1 : 0;
+        ds.bs_os = (sizeof(double) * (size_t)backsub_smem_doubles(ds.ntp, ds.ld, ds.nc) + 16 <= smem_cap && !std::getenv("B200_NO_BS_OSTAGE")) ? 1 : 0;
         const size_t bs = (size_t)backsub_smem_doubles(ds.ntp, ds.ld, ds.bs_os ? ds.nc : 0);
         if ((size_t)static_lds(ds.ns) * (ds.ns1 + 1) > (size_t)ds.ntp * ds.ld + 4 * 256)
             return fail("static block larger than the time block is not supported", B200_NOT_IMPLEMENTED);

@@ -143,3 +143,19 @@ def test_local_dof_elimination_is_exact_to_rounding(emu):
     g1, tv1, sv1 = graphs.single_imu_graph(tr.acc[0], tr.gyro[0], tr.dt)
     p1 = lib.Problem(g1, so_path=emu, chunks=1); p1.set_values(tv1, sv1); p1.linearize()
     assert p1.local_elim(0, 1.0) is None
+
+
+def test_backsub_without_staged_coupling_block(emu, monkeypatch):
+    """kernels_solve.cuh cta_backsub: the coupling block of the node in flight is staged in shared memory when it fits next to the
+    factor; a block too large for that is read from global memory.  Both paths give the same step, bit for bit."""
+    _, g, tv, sv = lower_body(1.2)
+    steps = []
+    for off in (False, True):
+        if off: monkeypatch.setenv("B200_NO_BS_OSTAGE", "1")
+        p = lib.Problem(g, so_path=emu, chunks=3); p.set_values(tv, sv); p.linearize()
+        steps.append(p.solve(1e-3))
+    assert all(np.array_equal(a, b) for a, b in zip(steps[0], steps[1]))
+    o = po.OracleProblem(g); o.set_values(tv, sv)
+    p = lib.Problem(g, so_path=emu, chunks=3); p.set_values(tv, sv)
+    pc.assert_linearization_parity(p, o, g)
+    pc.assert_solve_parity(p, o, g)   # (the global-memory path against the oracle)
