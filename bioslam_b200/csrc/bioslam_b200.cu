@@ -419,7 +419,7 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
     if (dm.ntp > 256 || dm.ns1 + dm.nc + 1 > 512) return fail("time block larger than 256 or arrow larger than 512 tangent dims is not supported", B200_NOT_IMPLEMENTED);
     // ---- solver layout: with keyframe-local dofs (and a chain to solve) they are eliminated per keyframe before the sweep, the
     // chain solver then sees the time-chained dofs only (padded to an even count)
-    p->use_le = nl > 0 && nl <= B200_LE_MAXNL && dm.nc >= 2 && !std::getenv("B200_NO_LOCAL_ELIM");
+    p->use_le = nl > 0 && nl <= B200_LE_MAXNL && dm.nc >= 2 && dm.nc + dm.ns1 <= B200_LE_THREADS - 32 && !std::getenv("B200_NO_LOCAL_ELIM");   // (one thread per panel row)
     Dims& ds = p->ds;
     ds = dm;
     if (p->use_le) { ds.nt = dm.nc; ds.ntp = (dm.nc + 1) & ~1; ds.nl = 0; ds.nc = ds.ntp; }

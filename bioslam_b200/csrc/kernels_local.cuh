@@ -7,8 +7,9 @@
 //   [ A_l               A_c    S     ] [d_s]   [-g_s]        Sc = S_k - V_a V_a^T            (V_c: first nc rows, V_a: last ns1)
 //
 // and recovered after the chain back-substitution:  d_l = -L^-T ( V_c^T d_c + V_a^T [d_s, -1] )   (L stored, back substitution).
-// The rank-nl updates run on the fp64 tensor pipe (same 16 x 32 DMMA warp tile as the sweep); the kernel is bound by HBM
-// (reads the lower triangle of D_k, A_k, S_k once, writes the reduced blocks once).
+// L and V come out of ONE right-looking elimination of the stacked block [D_ll + lambda I ; D_cl ; A_l ; -g_l^T] (a thread per row);
+// the rank-nl updates run on the fp64 tensor pipe (same 16 x 32 DMMA warp tile as the sweep).  The kernel is latency-bound (0.65 ms
+// per trial against ~0.2 ms of HBM traffic): what is exposed is one DRAM round trip per half tile of the epilogue and the nl pivots.
 #pragma once
 #include "kernels_solve.cuh"
 
@@ -42,14 +43,11 @@ __global__ void __launch_bounds__(B200_LE_THREADS, 3) local_elim_kernel(LocalEli
     const long long k = k_first + (long long)blockIdx.x;
     const double lambda = *lambda_p;
     double* Ls = sm;                                   // nl x ldl: L (lower)
-    double* invd = Ls + (long long)nl * ldl;           // [nl] 1 / L[j][j]   (the rest of this nl x ldl area is unused)
-    double* Vs = invd + (long long)nl * ldl;           // (nc + ns1) x ldl: panel -> V
+    double* Vs = Ls + 2LL * nl * ldl;                  // (nc + ns1) x ldl: V
     const double* Dk = le.D + k * ntp * ntp;
     const double* Ak = le.A + k * ns1 * ntp;
     const double* Sk = le.S + k * ns1 * ns1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    __shared__ int s_fail;
-    if (threadIdx.x == 0) s_fail = 0;
     // pull everything this keyframe reads towards L2 now (lower triangle of D_k, A_k, S_k: ~150 KB): the epilogue below reads
     // D_cc / A_c / S_k entry by entry and would otherwise wait for DRAM tile after tile
     if (full) {
@@ -58,76 +56,55 @@ __global__ void __launch_bounds__(B200_LE_THREADS, 3) local_elim_kernel(LocalEli
         for (int e = threadIdx.x * 16; e < ns1 * ntp; e += blockDim.x * 16) prefetch_l2(Ak + e);
         for (int e = threadIdx.x * 16; e < ns1 * ns1; e += blockDim.x * 16) prefetch_l2(Sk + e);
     }
-    // panel rows [D_cl ; A_l ; -g_l^T] (every warp but the first), while warp 0 factorises the local block
-    if (warp > 0) {
-        // lane c < nl reads column c of the rows  warp - 1, warp - 1 + (nwarps - 1), ...; eight rows per batch, all loads of a batch
-        // issued before the first shared-memory store
-        for (int r0 = warp - 1; r0 < hp; r0 += 8 * (nwarps - 1)) {
-            double x[8];
+    // Stacked elimination of [D_ll + lambda I ; D_cl ; A_l ; -g_l^T] ((nl + hp) x nl): ONE thread per row, the row in registers,
+    // right-looking.  Pivot c: the rows of the local block publish their column-c entries (shared memory), one barrier, then EVERY
+    // row scales its entry (x = r[c] / sqrt(d)) and updates its trailing entries r[c2] -= x * L[c2][c] -- the Cholesky factor L of the
+    // local block and V = P L^-T (the forward substitution of the panel rows) come out of the same nl steps.
+    // Thread map: warp 0, lane l < nl = row l of the local block; thread 32 + r = panel row r (hp <= blockDim.x - 32).
+    __shared__ double s_col[2][32];
+    const bool top = warp == 0 && lane < nl;
+    const int prow = (int)threadIdx.x - 32;                      // panel row of this thread (warps >= 1)
+    const bool pan = warp > 0 && prow < hp;
+    double r[B200_LE_MAXNL];
+    if (top) {
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
-                const int r = r0 + q * (nwarps - 1);
-                x[q] = (lane < nl && r < hp) ? __ldg((r < nc) ? Dk + (long long)(nl + r) * ntp + lane : Ak + (long long)(r - nc) * ntp + lane) : 0.0;
-            }
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                const int r = r0 + q * (nwarps - 1);
-                if (lane < nl && r < hp) Vs[r * ldl + lane] = x[q];
-            }
-        }
+        for (int c = 0; c < B200_LE_MAXNL; c++) r[c] = (c <= lane) ? Dk[(long long)lane * ntp + c] + (c == lane ? lambda : 0.0) : 0.0;
+        s_col[0][lane] = r[0];
     } else {
-        // Cholesky of the nl x nl block (nl <= 32) by ONE warp in registers: lane l owns row l (identity beyond nl), the pivot and
-        // the column entries travel by shuffle (right-looking: 1 rsqrt + 31 - c shuffle/FMA pairs per pivot)
-        double r[B200_LE_MAXNL];
+        const double* src = (prow < nc) ? Dk + (long long)(nl + (pan ? prow : 0)) * ntp : Ak + (long long)((pan ? prow : nc) - nc) * ntp;
 #pragma unroll
-        for (int c = 0; c < B200_LE_MAXNL; c++)
-            r[c] = (lane < nl && c <= lane) ? Dk[(long long)lane * ntp + c] + (c == lane ? lambda : 0.0) : ((c == lane) ? 1.0 : 0.0);
-        int fail = 0;
-#pragma unroll
-        for (int c = 0; c < B200_LE_MAXNL; c++) {
-            if (c < nl) {
-                double d = __shfl_sync(0xffffffffu, r[c], c);
-                if (!(d > 0.0) || !(d < 1.0e300)) { fail = 1; d = 1.0; }
-                const double x = r[c] * rsqrt(d);
-                r[c] = x;
-#pragma unroll
-                for (int c2 = c + 1; c2 < B200_LE_MAXNL; c2++) {
-                    const double lc2 = __shfl_sync(0xffffffffu, x, c2);
-                    r[c2] = fma(-x, lc2, r[c2]);
-                }
-            }
-        }
-        if (lane < nl) {
-#pragma unroll
-            for (int c = 0; c < B200_LE_MAXNL; c++) {
-                if (c <= lane) Ls[lane * ldl + c] = r[c];
-                if (c == lane) invd[lane] = 1.0 / r[c];
-            }
-        }
-        if (fail && lane == 0) s_fail = 1;
+        for (int c = 0; c < B200_LE_MAXNL; c++) r[c] = (pan && c < nl) ? __ldg(src + c) : 0.0;
     }
     __syncthreads();
-    if (s_fail) { if (threadIdx.x == 0) atomicCAS(status, 0, (int)(k + 1)); return; }
-    // V = P L^-T by forward substitution, one thread per row, the row in registers
-    for (int r = threadIdx.x; r < hp; r += blockDim.x) {
-        double x[B200_LE_MAXNL];
+    int fail = 0;
 #pragma unroll
-        for (int c = 0; c < B200_LE_MAXNL; c++) x[c] = (c < nl) ? Vs[r * ldl + c] : 0.0;
+    for (int c = 0; c < B200_LE_MAXNL; c++) {
+        if (c < nl) {
+            const double* col = s_col[c & 1];
+            double d = col[c];
+            if (!(d > 0.0) || !(d < 1.0e300)) { fail = 1; d = 1.0; }
+            const double rs = rsqrt(d);
+            const double x = r[c] * rs;
+            r[c] = x;
 #pragma unroll
-        for (int j = 0; j < B200_LE_MAXNL; j++) {
-            if (j < nl) {
-                double v = x[j];
-#pragma unroll
-                for (int c = 0; c < j; c++) v = fma(-x[c], Ls[j * ldl + c], v);
-                x[j] = v * invd[j];
-                Vs[r * ldl + j] = x[j];
+            for (int c2 = c + 1; c2 < B200_LE_MAXNL; c2++)
+                if (c2 < nl) r[c2] = fma(-x, col[c2] * rs, r[c2]);
+            if (c + 1 < nl) {
+                if (top) s_col[(c + 1) & 1][lane] = r[c + 1];
+                __syncthreads();
             }
         }
+    }
+    if (fail) { if (threadIdx.x == 0) atomicCAS(status, 0, (int)(k + 1)); return; }   // (the same d on every thread: uniform)
+    if (top) {
+#pragma unroll
+        for (int c = 0; c < B200_LE_MAXNL; c++) if (c <= lane) Ls[lane * ldl + c] = r[c];
+    } else if (pan) {
         bool nz = false;
 #pragma unroll
-        for (int j = 0; j < B200_LE_MAXNL; j++) nz |= (j < nl) && (x[j] != 0.0);
-        s_row[r] = nz ? 1 : 0;
-        for (int c = nl; c < ldl; c++) Vs[r * ldl + c] = 0.0;
+        for (int c = 0; c < B200_LE_MAXNL; c++) { if (c < nl) { Vs[prow * ldl + c] = r[c]; nz |= (r[c] != 0.0); } }
+        s_row[prow] = nz ? 1 : 0;
+        for (int c = nl; c < ldl; c++) Vs[prow * ldl + c] = 0.0;
     }
     __syncthreads();
     {   // factors of the local block for the back-substitution: V and L (lower, row-major nl x nl)
