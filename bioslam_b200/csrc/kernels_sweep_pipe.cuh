@@ -463,8 +463,8 @@ __device__ void cta_sweep_pipe(const Dims& dm, const SweepArgs& a, double* sm) {
                     }
                     st2(Ms + (long long)r * ld + c, v.x, v.y);
                 }
-        }
-        GSYNC();
+            GSYNC();
+        }   // (later nodes: the pivot buffer was completed before barrier [C], which every warp of the group has just left)
 #ifdef B200_PHASE_CLOCKS
         if (threadIdx.x == 0 && blockIdx.x == 1 && j > 0) { unsigned long long n_ = clock64(); g_phase_clk[3] += n_ - pp_t; pp_t = n_; }
 #endif
