@@ -55,6 +55,9 @@ int b200h_ipe_set(void* pv, const char* name, const double* v, int n) {
     else if (s == "m_maxIterations") p.m_maxIterations = (unsigned)v[0];
     else if (s == "m_initializationScheme") p.m_initializationScheme = (unsigned)v[0];
     else if (s == "m_optType") p.m_optType = (unsigned)v[0];
+    else if (s == "m_absErrLimit") p.m_absErrLimit = v[0];
+    else if (s == "m_relErrDecreaseLimit") p.m_relErrDecreaseLimit = v[0];
+    else if (s == "m_absErrDecreaseLimit") p.m_absErrDecreaseLimit = v[0];
     else if (s == "initialOrientations") {  // [K][9]: overrides the zero initialisation (stand-in for the EKF initialiser)
         if (!p.isSetup() || n != (int)p.m_nKeyframes * 9) ok = false;
         else for (unsigned k = 0; k < p.m_nKeyframes; k++) for (int c = 0; c < 9; c++) p.m_initPose[k].R.m[c] = v[(size_t)k * 9 + c];

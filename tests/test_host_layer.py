@@ -226,6 +226,30 @@ def test_host_single_imu_fast_optimize():
 
 
 @pytest.mark.gpu
+def test_host_single_imu_reference_solution_test():
+    """the reference's own solution test, by its settings and thresholds (test/solution/testImuEstimationSolution.cpp:17-51): one IMU,
+    dynamic bias model, zero initialisation, m_absErrLimit = 0.99e-5 -> the final total graph error must be <= 1e-5 ABSOLUTE and the
+    estimated velocity must agree with the discrete derivative of the estimated position to < 0.5 m/s RMSE (synthetic right-thigh
+    stream here: the reference's HDF5 trial is not in the mount)."""
+    tr = synth.make_trial(seed=4, duration_s=10.0)
+    m = host.Imu(tr.acc[1], tr.gyro[1], tr.time)
+    p = host.ImuPoseEstimator(m, "solutionTest")
+    p.setImuBiasModelMode(1)
+    p.set(m_useMagnetometer=0, m_initializationScheme=0, m_absErrLimit=0.99e-5)
+    p.setup()
+    p.fastOptimize()
+    err = p.get("m_optimizationTotalError")
+    assert err[-1] <= 1.0e-5, err[-5:]
+    K = p.nKeyframes
+    pos = p.get("m_pose").reshape(K, 12)[:, 9:]
+    vel = p.get("m_velocity").reshape(K, 3)
+    t = p.get("m_time")
+    vd = (pos[1:] - pos[:-1]) / (t[1] - t[0])
+    rmse = np.sqrt(np.mean(np.sum((vel[:-1] - vd) ** 2, axis=1)))
+    assert rmse < 0.5, rmse
+
+
+@pytest.mark.gpu
 def test_host_single_imu_with_ekf_initialisation():
     """BASELINE configs[0] (exampleImuPoseEstimation.cpp:21-39): single IMU, static-bias ImuFactor, EKF initialisation scheme 1,
     compass + position + velocity + bias priors; the reference's solution test asks for a final error <= 1e-5 x initial."""

@@ -68,6 +68,12 @@ def test_sharded_lm_matches_single_rank_and_oracle(world, tmp_path, oracle_lib):
         assert np.array_equal(o["tv"], outs[0]["tv"]) and np.array_equal(o["sv"], outs[0]["sv"])
         assert np.array_equal(o["trace"], outs[0]["trace"])
     assert int(outs[0]["groups"]) % world == 0 and int(outs[0]["chunks"]) % world == 0
+    # the single-rank run of the same library on the same inputs: same accept / reject sequence and damping, costs and values to what
+    # two partitions of the same damped systems (condition numbers up to 1e16 at lambda <= 1e-5) can agree
+    one = run_world(1, seconds, tmp_path, 29520 + world, tag="single")[0]
+    assert np.array_equal(one["trace"][:, 1:], outs[0]["trace"][:, 1:])
+    assert np.allclose(one["trace"][:, 0], outs[0]["trace"][:, 0], rtol=5e-3, atol=0.0)
+    assert float(one["e0"]) == float(outs[0]["e0"]) or abs(float(one["e0"]) - float(outs[0]["e0"])) <= 1e-12 * float(one["e0"])
     # oracle on the same inputs
     from bioslam_b200 import abi, synth
     from oracle import pyoracle as po
