@@ -134,6 +134,7 @@ struct b200_problem {
     LocalElim le{};
     size_t smem_le = 0;
     double *d_Dc = nullptr, *d_Ac = nullptr, *d_Sc = nullptr, *d_V = nullptr, *d_Wl = nullptr;
+    double* d_red_partial = nullptr; int* d_red_ticket = nullptr;   // scratch of reduce_sum_kernel (per problem: problems run concurrently)
     int* d_le_fresh = nullptr;   // device flag: the reduced blocks do not belong to the current linearization yet (kernels_local.cuh)
     double* d_delta = nullptr;   // full step [K][ntp] in internal order (== sb.delta without pre-elimination)
     LmDev* d_lm = nullptr;
@@ -345,7 +346,7 @@ void b200_problem_destroy(b200_problem* p) {
                     p->d_asm_elems[0], p->d_asm_elems[1]};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->use_le && p->d_delta) cudaFree(p->d_delta);
-    for (void* q : {(void*)p->d_Dc, (void*)p->d_Ac, (void*)p->d_Sc, (void*)p->d_V, (void*)p->d_Wl, (void*)p->d_lm, (void*)p->d_le_fresh}) if (q) cudaFree(q);
+    for (void* q : {(void*)p->d_Dc, (void*)p->d_Ac, (void*)p->d_Sc, (void*)p->d_V, (void*)p->d_Wl, (void*)p->d_lm, (void*)p->d_le_fresh, (void*)p->d_red_partial, (void*)p->d_red_ticket}) if (q) cudaFree(q);
     if (p->h_lm) cudaFreeHost(p->h_lm);
     if (p->d_spec_delta) cudaFree(p->d_spec_delta);
     if (p->d_spec_rec) cudaFree(p->d_spec_rec);
@@ -477,6 +478,8 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
     CK(dalloc(&p->sb.delta, (K + 1024) * ds.ntp)); CK(dalloc(&p->sb.dstat, (size_t)ns + 1)); CK(dalloc(&p->sb.scal, (size_t)SC_COUNT + 8));   // [SC_COUNT..): rank-local scalars that are NOT all-reduced
     CK(dalloc(&p->sb.status, (size_t)1));
     CK(dalloc(&p->d_lm, (size_t)1));
+    CK(dalloc(&p->d_red_partial, (size_t)B200_REDUCE_BLOCKS)); CK(dalloc(&p->d_red_ticket, (size_t)1));
+    CK(cudaMemsetAsync(p->d_red_ticket, 0, sizeof(int), p->stream));
     CK(cudaMemsetAsync(p->d_lm, 0, sizeof(LmDev), p->stream));
     CK(cudaMallocHost((void**)&p->h_lm, sizeof(LmDev)));
     std::memset(p->h_lm, 0, sizeof(LmDev));
@@ -863,7 +866,7 @@ static void launch_error(b200_problem* p, const double* tv, const double* sv, do
     dim3 grid((p->max_inst + 127) / 128, p->n_slots);
     B200_LAUNCH(linearize_kernel<false>, grid, dim3(128), 0, p->stream, p->d_slots, tv, sv, p->d_cst, p->dm.Kld, (double*)nullptr,
                 (double*)nullptr, ebuf, p->k_lo, p->k_hi, p->k_lo, skip);
-    B200_LAUNCH(reduce_sum_kernel, dim3(1), dim3(1024), 0, p->stream, ebuf, p->ne, p->sb.scal + scal_idx, skip);
+    B200_LAUNCH(reduce_sum_kernel, dim3(B200_REDUCE_BLOCKS), dim3(B200_REDUCE_THREADS), 0, p->stream, ebuf, p->ne, p->sb.scal + scal_idx, skip, p->d_red_partial, p->d_red_ticket);
     p->launches += 2;
 }
 
@@ -1021,7 +1024,8 @@ static b200_status launch_solve(b200_problem* p, cudaEvent_t* tev) {
                         (long long)p->pack_doubles, 0, 1, l1.c_lo, l1.c_hi);
             p->launches += 2;
         }
-        B200_LAUNCH(chain_reduce_kernel, dim3(l1.P - 1, 8), dim3(256), 0, p->stream, dm, l1.dev, 0, p->sb.skip);
+        // (few separators up here: 32 CTAs each, so that every thread handles one batch of four entries)
+        B200_LAUNCH(chain_reduce_kernel, dim3(l1.P - 1, (l1.P - 1) * 32 <= 2048 ? 32 : 8), dim3(256), 0, p->stream, dm, l1.dev, 0, p->sb.skip);
         p->launches++;
         if (tev && li == 1) CK(cudaEventRecord(tev[TE_L1DONE], p->stream));
     }
@@ -1175,7 +1179,7 @@ static b200_status launch_trial(b200_problem* p, cudaEvent_t* tev, bool device_j
     dim3 grid((p->max_inst + 127) / 128, p->n_slots);
     B200_LAUNCH(model_error_kernel, grid, dim3(128), 0, p->stream, p->d_slots, p->d_J, p->d_r, p->d_delta, p->dm.ntp, p->sb.dstat, p->d_e2,
                 p->k_lo, p->k_hi, p->sb.skip);
-    B200_LAUNCH(reduce_sum_kernel, dim3(1), dim3(1024), 0, p->stream, p->d_e2, p->ne, p->sb.scal + SC_MODEL_ERR, p->sb.skip);
+    B200_LAUNCH(reduce_sum_kernel, dim3(B200_REDUCE_BLOCKS), dim3(B200_REDUCE_THREADS), 0, p->stream, p->d_e2, p->ne, p->sb.scal + SC_MODEL_ERR, p->sb.skip, p->d_red_partial, p->d_red_ticket);
     p->launches += 2;
     launch_retract(p, p->d_delta, p->sb.dstat, p->sb.skip);
     launch_error(p, p->d_tv_try, p->d_sv_try, p->d_e2, SC_NEW_ERR, p->sb.skip);
@@ -1254,7 +1258,7 @@ b200_status b200_lm_iterate(b200_problem* p, b200_lm_state* state) {
     if (p->time_phases) CK(cudaEventRecord(p->ev[0], p->stream));
     CK(cudaMemsetAsync(p->sb.scal, 0, sizeof(double) * SC_COUNT, p->stream));
     launch_linearize(p);
-    B200_LAUNCH(reduce_sum_kernel, dim3(1), dim3(1024), 0, p->stream, p->d_e, p->ne, p->sb.scal + SC_COUNT, (const int*)nullptr);
+    B200_LAUNCH(reduce_sum_kernel, dim3(B200_REDUCE_BLOCKS), dim3(B200_REDUCE_THREADS), 0, p->stream, p->d_e, p->ne, p->sb.scal + SC_COUNT, (const int*)nullptr, p->d_red_partial, p->d_red_ticket);
     p->launches++;
     if (p->time_phases) CK(cudaEventRecord(p->ev[1], p->stream));
     p->have_lin = true;

@@ -112,20 +112,37 @@ __global__ void factor_eval_kernel(int type, int nvars, const int* __restrict__ 
     if (!written) for (int i = 0; i < rows * cols; i++) J_out[i] = J[i];
 }
 
-// deterministic sum of n doubles: fixed strided partials per thread, fixed shared-memory tree.  grid 1, block 1024.
-__global__ void __launch_bounds__(1024) reduce_sum_kernel(const double* __restrict__ v, long long n, double* __restrict__ out,
-                                                          const int* __restrict__ skip) {
-    __shared__ double sh[1024];
+// deterministic sum of n doubles over B200_REDUCE_BLOCKS CTAs: fixed strided partials per thread, fixed shared-memory tree per CTA,
+// and the CTA that finishes last (ticket counter) adds the per-CTA partials in index order -- the result does not depend on which CTA
+// that is.  partial: B200_REDUCE_BLOCKS doubles, ticket: one int (zero before the first launch; reset by the last CTA).
+#define B200_REDUCE_BLOCKS 64
+#define B200_REDUCE_THREADS 256
+__global__ void __launch_bounds__(B200_REDUCE_THREADS) reduce_sum_kernel(const double* __restrict__ v, long long n, double* __restrict__ out,
+                                                                         const int* __restrict__ skip, double* partial, int* ticket) {
+    __shared__ double sh[B200_REDUCE_THREADS];
+    __shared__ int s_last;
     if (skip != nullptr && *skip != 0) return;
     double acc = 0.0;
-    for (long long i = threadIdx.x; i < n; i += 1024) acc += v[i];
+    for (long long i = (long long)blockIdx.x * B200_REDUCE_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * B200_REDUCE_THREADS) acc += v[i];
     sh[threadIdx.x] = acc;
     __syncthreads();
-    for (int s = 512; s > 0; s >>= 1) {
+    for (int s = B200_REDUCE_THREADS / 2; s > 0; s >>= 1) {
         if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
         __syncthreads();
     }
-    if (threadIdx.x == 0) *out = sh[0];
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = sh[0];
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        double s = 0.0;
+        for (int b = 0; b < (int)gridDim.x; b++) s += ((volatile double*)partial)[b];
+        *out = s;
+        *ticket = 0;
+    }
 }
 
 // 0.5*||J delta + r||^2 per factor instance on the stored linearization; delta in internal order:

@@ -202,14 +202,21 @@ __global__ void __launch_bounds__(128) local_backsub_kernel(LocalElim le, int k_
     __syncthreads();
     double* dk = delta + k * ntp;
     if (threadIdx.x < 32) {
-        // d_l = -L^-T t: backward substitution with the transpose, lane i holds entry i; row i of L is read coalesced
+        // d_l = -L^-T t: backward substitution with the transpose, lane l holds entry l and COLUMN l of L (loaded before the chain
+        // starts: rows of L are read coalesced, no memory access sits between two dependent steps)
         const double* Lg = le.Wl + k * (long long)nl * nl;
         const int l = threadIdx.x;
+        double Lc[B200_LE_MAXNL];
+#pragma unroll
+        for (int i = 0; i < B200_LE_MAXNL; i++) Lc[i] = (i < nl && l <= i) ? Lg[(long long)i * nl + l] : 0.0;
         double v = (l < nl) ? t[l] : 0.0;
-        for (int i = nl - 1; i >= 0; i--) {
-            const double yi = __shfl_sync(0xffffffffu, v, i) / Lg[(long long)i * nl + i];
-            if (l == i) v = yi;
-            else if (l < i) v = fma(-Lg[(long long)i * nl + l], yi, v);
+#pragma unroll
+        for (int i = B200_LE_MAXNL - 1; i >= 0; i--) {
+            if (i < nl) {
+                const double yi = __shfl_sync(0xffffffffu, v, i) / __shfl_sync(0xffffffffu, Lc[i], i);
+                if (l == i) v = yi;
+                else if (l < i) v = fma(-Lc[i], yi, v);
+            }
         }
         if (l < nl) dk[l] = -v;
     }
