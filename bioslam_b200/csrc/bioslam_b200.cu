@@ -166,7 +166,9 @@ struct b200_problem {
     int *d_orow = nullptr, *d_ocol = nullptr, *d_ozs = nullptr, *d_ogrp = nullptr;
     double *d_Ftop = nullptr, *d_Stop = nullptr;
     size_t smem_schur = 0, smem_backsub = 0;
-    int schur_ldy = 0, schur_kslab = 0;
+    int schur_ldy = 0, schur_kslab = 0, schur_tile_ldy = 0;
+    size_t smem_schur_tile = 0;
+    bool schur_tile_ok = false;
     int Wk = 0;                                // keyframes per rank window
     double *d_stageS = nullptr, *d_stageF = nullptr, *d_pack = nullptr;
     size_t pack_doubles = 0;
@@ -621,6 +623,9 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
         }
         p->schur_ldy = ldy; p->schur_kslab = kslab;
         p->smem_schur = sizeof(double) * (size_t)ds.hmax * ldy;
+        p->schur_tile_ldy = choose_ld(ds.ntp);
+        p->smem_schur_tile = sizeof(double) * (size_t)schur_tile_smem_doubles(p->schur_tile_ldy);
+        p->schur_tile_ok = 64LL * p->schur_tile_ldy >= 4 * 32 * 33 && p->smem_schur_tile <= smem_cap && !std::getenv("B200_NO_SCHUR_TILE");
         dm.cr = ds.cr; dm.sm_doubles = ds.sm_doubles;
     }
 #ifndef B200_USE_EMU
@@ -628,6 +633,7 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
     CK(cudaFuncSetAttribute(chain_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sweep));
     CK(cudaFuncSetAttribute(chain_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_sweep));
     CK(cudaFuncSetAttribute(chain_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_schur));
+    if (p->schur_tile_ok) CK(cudaFuncSetAttribute(chain_schur_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_schur_tile));
     CK(cudaFuncSetAttribute(top_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_backsub));
     CK(cudaFuncSetAttribute(chain_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_backsub));
     if (p->use_le) CK(cudaFuncSetAttribute(local_elim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem_le));
@@ -941,10 +947,16 @@ static void launch_level_factor(b200_problem* p, const Level& lv, int c_lo, int 
     if (lv.dense_o) B200_LAUNCH(chain_sweep_kernel<true>, sgrid, dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, dm, lv, p->sb, c_lo);
     else B200_LAUNCH(chain_sweep_kernel<false>, sgrid, dim3(B200_SOLVE_THREADS), p->smem_sweep, p->stream, dm, lv, p->sb, c_lo);
     // few chunks (upper levels): split the output tiles of a chunk's Schur complement over several CTAs
-    // (21 = 32 x 32 tiles of the lower triangle of a 165 x 165 complement; a CTA with one or two tiles still stages whole panels, from L2)
-    const int nsplit = std::max(1, std::min(148 / std::max(1, c_hi - c_lo), 21));
-    B200_LAUNCH(chain_schur_kernel, dim3(c_hi - c_lo, nsplit), dim3(B200_SCHUR_THREADS), p->smem_schur, p->stream, dm, lv, p->sb, c_lo, p->schur_ldy,
-                p->schur_kslab);
+    const int nrt = (dm.hmax + 31) >> 5, ntmax = nrt * (nrt + 1) / 2;   // 32 x 32 tiles of the lower triangle of the complement (21 for 165 rows)
+    if (p->schur_tile_ok && (c_hi - c_lo) * ntmax <= 8 * 148) {
+        // few chunks: one output tile per CTA, three CTAs per SM (kernels_solve.cuh: chain_schur_tile_kernel)
+        B200_LAUNCH(chain_schur_tile_kernel, dim3(c_hi - c_lo, ntmax), dim3(B200_SCHUR_TILE_THREADS), p->smem_schur_tile, p->stream, dm, lv, p->sb, c_lo,
+                    p->schur_tile_ldy);
+    } else {
+        const int nsplit = std::max(1, std::min(148 / std::max(1, c_hi - c_lo), ntmax));
+        B200_LAUNCH(chain_schur_kernel, dim3(c_hi - c_lo, nsplit), dim3(B200_SCHUR_THREADS), p->smem_schur, p->stream, dm, lv, p->sb, c_lo, p->schur_ldy,
+                    p->schur_kslab);
+    }
     p->launches += 2;
 }
 static void launch_level_backsub(b200_problem* p, const b200_problem::HostLevel& l) {

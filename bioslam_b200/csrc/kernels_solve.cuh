@@ -1535,6 +1535,79 @@ __global__ void __launch_bounds__(B200_SCHUR_THREADS, 1) chain_schur_kernel(Dims
     }
 }
 
+// The same Schur complement for the upper levels (few chunks of 2..4 nodes, most SMs idle): ONE 32 x 32 output tile per CTA
+// (grid = chunks x tiles of the lower triangle), only the two 32-row slices of the panel that the tile needs are staged, and the four
+// warps split the contraction range (partial tiles added in warp order: fixed summation order).  The nodes' own static blocks are
+// added in the same pass.  ~15 us per launch against ~48 us of chain_schur_kernel with its tiles dealt to 21 CTAs.
+#define B200_SCHUR_TILE_THREADS 128
+__host__ __device__ inline long long schur_tile_smem_doubles(int ldy) { return 64LL * ldy; }   // (>= 4 x 32 x 33 for the partial tiles)
+__global__ void __launch_bounds__(B200_SCHUR_TILE_THREADS) chain_schur_tile_kernel(Dims dm, Level lv, SolveBuffers sb, int c_first, int ldy) {
+    B200_DYN_SMEM(double, Ys);
+    if (solve_skipped(sb)) return;
+    SweepArgs a;
+    level_chunk_args(dm, lv, sb, c_first + blockIdx.x, a);
+    const int n = dm.ntp, ns1 = dm.ns1, hmax = dm.hmax, h = a.h;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int mg = lane >> 2, mt = lane & 3;
+    if (*sb.status != 0) return;
+    const int nrt = (h + 31) >> 5;
+    const int t = blockIdx.y;
+    if (t >= nrt * (nrt + 1) / 2) return;
+    int tr = 0;
+    while ((tr + 1) * (tr + 2) / 2 <= t) tr++;
+    const int tc = t - tr * (tr + 1) / 2;
+    const bool diag = tr == tc;
+    const int rowsA = (h - (tr << 5) < 32) ? (h - (tr << 5)) : 32;     // valid rows of the tile
+    const int ni = (rowsA + 7) >> 3;
+    const int M = diag ? rowsA : 64, r0 = diag ? 0 : 32;                // staged rows: [0, 32) = output rows, [32, 64) = output columns
+    const int kq = ((n + 4 * nwarps - 1) / (4 * nwarps)) * 4;           // contraction range of a warp (multiple of 4)
+    const int ka = warp * kq, kb = (ka + kq < n) ? (ka + kq) : n;
+    Acc32 acc;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    for (int r = rowsA + warp; r < 32; r += nwarps)   // output rows beyond h (last tile row): defined zeros, results discarded
+        for (int c = lane; c < n; c += 32) Ys[(long long)r * ldy + c] = 0.0;
+    for (int i = 0; i < a.n; i++) {
+        const long long st = a.st_idx ? a.st_idx[i] : (long long)a.src0 + i;
+        const double* Yg = a.Yst + st * (long long)hmax * n;
+        __syncthreads();
+        for (int r = warp; r < (diag ? rowsA : 64); r += nwarps) {
+            const int gr = (r < 32) ? (tr << 5) + r : (tc << 5) + r - 32;
+            if (r < 32 && r >= rowsA) continue;
+            for (int c = 2 * lane; c < n; c += 64) cp_async16(Ys + (long long)r * ldy + c, Yg + (long long)gr * n + c);
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        if (ka < kb) warp_mma_nt32_kind(ni, diag, Ys, ldy, 0, M, r0, ka, kb, acc);
+    }
+    __syncthreads();
+    // partial tiles -> shared memory (stride 33), then entry (r, c) = sum over the warps in order, minus sign, plus the static blocks
+    double* red = Ys;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) red[(warp * 32 + 8 * i + mg) * 33 + 8 * j + 2 * mt + e] = acc[i][j][e];
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * 32; e += blockDim.x) {
+        const int r = e >> 5, c = e & 31;
+        const int a1 = (tr << 5) + r, a2 = (tc << 5) + c;
+        if (a1 >= h || a2 > a1) continue;
+        double s = 0.0;
+        for (int w = 0; w < nwarps; w++) s += red[(w * 32 + r) * 33 + c];
+        double v = -s;
+        if (a1 < ns1) {   // (a2 <= a1 < ns1) the nodes' own static blocks
+            double q = 0.0;
+            for (int i = 0; i < a.n; i++) q += a.Ssrc[((long long)a.src0 + i) * ns1 * ns1 + a1 * ns1 + a2];
+            v += q;
+        }
+        a.Sacc[(long long)a1 * hmax + a2] = v;
+    }
+}
+
 // Schur complements onto separator c of this level: from chunk c (its right side) and chunk c+1 (its left side).
 // grid = separators handled (separator = c_first + blockIdx.x)
 __global__ void __launch_bounds__(256) chain_reduce_kernel(Dims dm, Level lv, int c_first, const int* __restrict__ skip) {
