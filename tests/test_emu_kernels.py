@@ -159,3 +159,19 @@ def test_backsub_without_staged_coupling_block(emu, monkeypatch):
     p = lib.Problem(g, so_path=emu, chunks=3); p.set_values(tv, sv)
     pc.assert_linearization_parity(p, o, g)
     pc.assert_solve_parity(p, o, g)   # (the global-memory path against the oracle)
+
+
+def test_schur_tile_kernel_against_the_chunk_kernel(emu, monkeypatch):
+    """kernels_solve.cuh: on the upper levels the arrow Schur complement is computed one 32 x 32 tile per CTA (contraction split over
+    four warps); B200_NO_SCHUR_TILE forces the level-0 kernel (whole panels, one warp per tile) everywhere.  Same complement up to
+    the summation order: the steps agree far below the solver's own residual."""
+    _, g, tv, sv = lower_body(1.6)
+    steps = []
+    for off in (False, True):
+        if off: monkeypatch.setenv("B200_NO_SCHUR_TILE", "1")
+        p = lib.Problem(g, so_path=emu, chunks=4); p.set_values(tv, sv); p.linearize()
+        steps.append(p.solve(1.0))
+    (st0, dt0, ds0), (st1, dt1, ds1) = steps
+    assert st0 == 0 and st1 == 0
+    assert np.abs(dt0 - dt1).max() <= 1e-9 * np.abs(dt0).max() and np.abs(ds0 - ds1).max() <= 1e-9 * np.abs(ds0).max()
+    assert not (np.array_equal(dt0, dt1) and np.array_equal(ds0, ds1)), "the switch did not change the kernel"
