@@ -778,7 +778,8 @@ static b200_status set_partition(b200_problem* p, int P1, int P2) {
         CK(cudaStreamSynchronize(p->stream));
         // upper levels on one GPU: few chunks, many idle SMs -> several CTAs per chunk sweep (row split, see Level::nsplit)
         l.nsplit = 1;
-        if (li > 0 && (W == 1 || li >= 2)) { while (l.nsplit < B200_MAX_SPLIT && l.P * (l.nsplit + 1) <= 148) l.nsplit++; }
+        const int max_split = std::max(1, std::min(B200_MAX_SPLIT, (dm.hmax + 15) / 16));   // (at most one CTA per 16-row tile of the arrow rows)
+        if (li > 0 && (W == 1 || li >= 2)) { while (l.nsplit < max_split && l.P * (l.nsplit + 1) <= 148) l.nsplit++; }
         CK(dalloc(&l.F, (P + 1) * l.nsplit * 2 * Fsz)); CK(dalloc(&l.S, (P + 1) * Ssz));
         CK(dalloc(&l.Dred, P * dm.ntp * dm.ntp)); CK(dalloc(&l.Ored, P * dm.nc * dm.nc));
         CK(dalloc(&l.Ared, P * dm.ns1 * dm.ntp)); CK(dalloc(&l.Sred, P * dm.ns1 * dm.ns1));
@@ -801,7 +802,7 @@ static b200_status set_partition(b200_problem* p, int P1, int P2) {
         CK(cudaMemcpyAsync(p->d_top_begin, tb, sizeof(tb), cudaMemcpyHostToDevice, p->stream));
         CK(cudaStreamSynchronize(p->stream));
         t.begin = p->d_top_begin; t.P = 1; t.F = p->d_Ftop; t.S = p->d_Stop; t.dense_o = (nlev > 0); t.nsplit = 1;
-        if (t.dense_o && dm.pipe == 1) t.nsplit = B200_MAX_SPLIT;   // the single top-level chunk: its arrow rows over several CTAs as well
+        if (t.dense_o && dm.pipe == 1) t.nsplit = std::max(1, std::min(B200_MAX_SPLIT, (dm.hmax + 15) / 16));   // the single top-level chunk: its arrow rows over several CTAs as well
     }
     if (W > 1) {
         if (p->d_stageS) cudaFree(p->d_stageS);
