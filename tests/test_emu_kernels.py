@@ -175,3 +175,19 @@ def test_schur_tile_kernel_against_the_chunk_kernel(emu, monkeypatch):
     assert st0 == 0 and st1 == 0
     assert np.abs(dt0 - dt1).max() <= 1e-9 * np.abs(dt0).max() and np.abs(ds0 - ds1).max() <= 1e-9 * np.abs(ds0).max()
     assert not (np.array_equal(dt0, dt1) and np.array_equal(ds0, ds1)), "the switch did not change the kernel"
+
+
+def test_apdm_rate_128hz_trial(emu):
+    """the sensor's own rate (APDM Opal, 128 Hz) with a sample count that is not a multiple of the preintegration length:
+    154 samples -> floor(154 / 10) + 1 = 16 keyframes (src/imuPoseEstimator.cpp:117-125); device preintegration kernel, linearization
+    and a damped solve against the oracle (the GPU twin of this test runs 6 s and LM iterations)."""
+    tr = synth.make_trial(seed=6, duration_s=1.2, rate_hz=128.0)
+    assert tr.acc.shape[1] == 154
+    g, tv, sv = graphs.lower_body_graph(tr, preint=lambda a, w, dt, n, bh: lib.preintegrate(a, w, dt, n, bh, so_path=emu))
+    go, _, _ = graphs.lower_body_graph(tr)
+    assert g.K == go.K == 16
+    tv, sv = graphs.perturbed_truth_values(tr, g, tv, sv)
+    o = po.OracleProblem(go); o.set_values(tv, sv)
+    p = lib.Problem(g, so_path=emu, chunks=2); p.set_values(tv, sv)
+    pc.assert_linearization_parity(p, o, g)
+    pc.assert_solve_parity(p, o, g)

@@ -273,3 +273,22 @@ def test_pose3_prior_factor_in_a_graph(po):
     pc.assert_linearization_parity(p, o, g)
     pc.assert_lm_parity(p, o, abi.LmParams.single_imu(), 3, rel=2e-2)
     p.close()
+
+
+def test_apdm_rate_128hz_trial(po):
+    """BASELINE configs[1] stand-in at the sensor's own rate (APDM Opal: 128 Hz; the reference's test trial is a ~30 s TUG): 128 Hz x
+    6.05 s = 774 samples, not a multiple of the 10-sample preintegration -> floor(774 / 10) + 1 = 78 keyframes
+    (getExpectedNumberOfKeyframesFromImuData, src/imuPoseEstimator.cpp:117-125) -- preintegration on the device, linearization, damped
+    solves and the first LM iterations against the oracle."""
+    tr = synth.make_trial(seed=6, duration_s=6.05, rate_hz=128.0)
+    assert abs(tr.dt - 1.0 / 128.0) < 1e-15 and tr.acc.shape[1] % 10 != 0
+    g, tv, sv = graphs.lower_body_graph(tr, preint=lambda a, w, dt, n, bh: lib.preintegrate(a, w, dt, n, bh))
+    go, _, _ = graphs.lower_body_graph(tr)                                  # the same graph with the oracle's preintegration
+    assert g.K == go.K
+    tv, sv = graphs.perturbed_truth_values(tr, g, tv, sv)
+    o = po.OracleProblem(go, threads=8); o.set_values(tv, sv)
+    p = lib.Problem(g, chunks=None); p.set_values(tv, sv)
+    pc.assert_linearization_parity(p, o, g)
+    pc.assert_solve_parity(p, o, g, lams=(1e-3, 1.0))
+    pc.assert_lm_parity(p, o, abi.LmParams.lower_body(), 4, rel=2e-2)
+    p.close()
