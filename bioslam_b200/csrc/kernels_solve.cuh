@@ -813,6 +813,36 @@ __device__ int cta_chol_smem(double* Ms, int ld, int n, int nrows) {
     return fail;
 }
 
+// The same factorisation for a SMALL block (the static system: 58 x 58 plus the rhs row), right-looking with one barrier per pivot:
+// after pivot c every entry (r, c2), c < c2 <= r, takes  M[r][c2] -= M[r][c] M[c2][c] / d_c  from the still unscaled column c, all
+// threads of the CTA sharing the entries; the columns are scaled by 1 / sqrt(d_c) in one pass at the end.  ~2 x n barriers instead of
+// the blocked version's serial 16 x 16 steps (one warp factorises while 15 wait): 58 x 58 in ~7 us instead of ~40.
+// rs: n doubles of scratch.  Rows [n, nrows) ride along (forward substitution of the rhs row).  Returns 0 or 1 + failing pivot.
+__device__ int cta_chol_rl_smem(double* Ms, int ld, int n, int nrows, double* rs) {
+    __shared__ int fail;
+    if (threadIdx.x == 0) fail = 0;
+    __syncthreads();
+    for (int c = 0; c < n; c++) {
+        double d = Ms[(long long)c * ld + c];
+        if (!(d > 0.0) || !(d < 1.0e300)) { if (threadIdx.x == 0 && fail == 0) fail = c + 1; d = 1.0; }
+        const double inv = 1.0 / d;
+        const int m = nrows - 1 - c;   // rows below the pivot
+        for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+            const int i = e / m, r = c + 1 + i, c2 = c + 1 + (e - i * m);
+            if (c2 <= r && c2 < n) Ms[(long long)r * ld + c2] = fma(-(Ms[(long long)r * ld + c] * inv), Ms[(long long)c2 * ld + c], Ms[(long long)r * ld + c2]);
+        }
+        __syncthreads();
+    }
+    for (int c = threadIdx.x; c < n; c += blockDim.x) { const double d = Ms[(long long)c * ld + c]; rs[c] = (d > 0.0 && d < 1.0e300) ? rsqrt(d) : 1.0; }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nrows * n; e += blockDim.x) {
+        const int r = e / n, c = e - r * n;
+        if (c <= r) Ms[(long long)r * ld + c] *= rs[c];   // (diagonal: d / sqrt(d))
+    }
+    __syncthreads();
+    return fail;
+}
+
 // x <- L^-T x for the n x n lower factor in shared memory (ld); x in shared memory (tv).  Blocked: the 16 x 16 diagonal
 // solves run in one warp (registers + shuffles), the updates of the remaining entries on all threads.
 __device__ void cta_solve_LT(const double* Ms, int ld, int n, double* tv) {
@@ -1951,7 +1981,7 @@ __global__ void __launch_bounds__(B200_SOLVE_THREADS) top_finish_kernel(Dims dm,
     }
     __syncthreads();
     if (ns > 0) {
-        const int fail = cta_chol_smem(Ss, lds, ns, ns1);
+        const int fail = (ns <= 256) ? cta_chol_rl_smem(Ss, lds, ns, ns1, coef) : cta_chol_smem(Ss, lds, ns, ns1);
         if (fail) { if (threadIdx.x == 0) atomicCAS(sb.status, 0, 1 << 30); return; }
         for (int i = threadIdx.x; i < ns; i += blockDim.x) coef[i] = Ss[ns * lds + i];
         __syncthreads();
