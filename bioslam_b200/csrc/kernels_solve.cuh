@@ -1568,7 +1568,7 @@ __global__ void __launch_bounds__(B200_SCHUR_THREADS, 1) chain_schur_kernel(Dims
 // The same Schur complement for the upper levels (few chunks of 2..4 nodes, most SMs idle): ONE 32 x 32 output tile per CTA
 // (grid = chunks x tiles of the lower triangle), only the two 32-row slices of the panel that the tile needs are staged, and the four
 // warps split the contraction range (partial tiles added in warp order: fixed summation order).  The nodes' own static blocks are
-// added in the same pass.  ~15 us per launch against ~48 us of chain_schur_kernel with its tiles dealt to 21 CTAs.
+// added in the same pass.  27-36 us per launch against 45-52 us of chain_schur_kernel with its tiles dealt to 21 CTAs.
 #define B200_SCHUR_TILE_THREADS 128
 __host__ __device__ inline long long schur_tile_smem_doubles(int ldy) { return 64LL * ldy; }   // (>= 4 x 32 x 33 for the partial tiles)
 __global__ void __launch_bounds__(B200_SCHUR_TILE_THREADS) chain_schur_tile_kernel(Dims dm, Level lv, SolveBuffers sb, int c_first, int ldy) {
