@@ -1,4 +1,8 @@
-"""Per-phase cycle breakdown of the solver sweep (debug build with -DB200_PHASE_CLOCKS): python tools/phase_clocks.py <sec> <chunks>"""
+"""Per-phase cycle breakdown of the solver sweep (debug build with -DB200_PHASE_CLOCKS): python tools/phase_clocks.py <sec> <chunks>
+
+Build the instrumented library first (from bioslam_b200/):
+  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -O3 --expt-relaxed-constexpr \
+       -DB200_PHASE_CLOCKS -shared -o ../tools/libb200_clk.so csrc/bioslam_b200.cu host/*.cpp -lcudart"""
 import ctypes as C, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
