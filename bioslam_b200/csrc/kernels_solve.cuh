@@ -1728,26 +1728,36 @@ __device__ __forceinline__ void load_coef(const Dims& dm, const Level& lv, const
     }
 }
 
-// y[c] = sum_r Y[r][c] coef[r]   (h x n panel in global memory), all threads of the CTA; part: blockDim.x doubles of scratch
+// y[c] = sum_r Y[r][c] coef[r]   (h x n panel in global memory, n even).  Thread = (column pair, row group): 16-byte loads, up to four
+// row groups (the first 256 threads), two independent partial sums per column; part: 512 doubles of scratch.
 __device__ __forceinline__ void cta_yt_coef(const double* __restrict__ Yg, int n, int h, const double* coef, double* part, double* y) {
-    const int half = threadIdx.x >> 7, nhalf = blockDim.x >> 7;
+    const int cp = threadIdx.x & 63, rg = threadIdx.x >> 6;
+    const int nrg = ((int)(blockDim.x >> 6) < 4) ? (int)(blockDim.x >> 6) : 4;
     for (int cb = 0; cb < n; cb += 128) {
-        const int c = cb + (threadIdx.x & 127);
-        double t0 = 0.0, t1 = 0.0;
-        if (c < n) {
-            int r = half;
-            for (; r + nhalf < h; r += 2 * nhalf) {
-                t0 = fma(Yg[(long long)r * n + c], coef[r], t0);
-                t1 = fma(Yg[(long long)(r + nhalf) * n + c], coef[r + nhalf], t1);
+        const int c = cb + 2 * cp;
+        if (rg < nrg) {
+            double2 t0 = make_double2(0.0, 0.0), t1 = make_double2(0.0, 0.0);
+            if (c < n) {
+                int r = rg;
+                for (; r + nrg < h; r += 2 * nrg) {
+                    const double2 a0 = ld2(Yg + (long long)r * n + c), a1 = ld2(Yg + (long long)(r + nrg) * n + c);
+                    const double c0 = coef[r], c1 = coef[r + nrg];
+                    t0.x = fma(a0.x, c0, t0.x); t0.y = fma(a0.y, c0, t0.y);
+                    t1.x = fma(a1.x, c1, t1.x); t1.y = fma(a1.y, c1, t1.y);
+                }
+                if (r < h) {
+                    const double2 a0 = ld2(Yg + (long long)r * n + c);
+                    t0.x = fma(a0.x, coef[r], t0.x); t0.y = fma(a0.y, coef[r], t0.y);
+                }
             }
-            if (r < h) t0 = fma(Yg[(long long)r * n + c], coef[r], t0);
+            part[2 * (rg * 64 + cp)] = t0.x + t1.x;
+            part[2 * (rg * 64 + cp) + 1] = t0.y + t1.y;
         }
-        part[threadIdx.x] = t0 + t1;
         __syncthreads();
-        if (half == 0 && c < n) {
-            double s = 0.0;
-            for (int q = 0; q < nhalf; q++) s += part[q * 128 + (threadIdx.x & 127)];
-            y[c] = s;
+        if (rg == 0 && c < n) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int q = 0; q < nrg; q++) { s0 += part[2 * (q * 64 + cp)]; s1 += part[2 * (q * 64 + cp) + 1]; }
+            y[c] = s0; y[c + 1] = s1;
         }
         __syncthreads();
     }
@@ -1756,7 +1766,7 @@ __device__ __forceinline__ void cta_yt_coef(const double* __restrict__ Yg, int n
 // grid = (max nodes per chunk, chunks owned)
 __global__ void __launch_bounds__(B200_PREPASS_THREADS) chain_backsub_prepass_kernel(Dims dm, Level lv, SolveBuffers sb, int c_first) {
     __shared__ double coef[512];
-    __shared__ double part[B200_PREPASS_THREADS];
+    __shared__ double part[512];
     if (solve_skipped(sb)) return;
     const int c = c_first + blockIdx.y;
     SweepArgs a;
