@@ -148,7 +148,8 @@ struct b200_problem {
     DevSlot* d_slots = nullptr;
     DevVar *d_tvars = nullptr, *d_svars = nullptr;
     double *d_J = nullptr, *d_r = nullptr, *d_e = nullptr, *d_e2 = nullptr;
-    long long nJ = 0, nr = 0, ne = 0;
+    long long nJ = 0, nr = 0, ne = 0, max_rows = 0;
+    double* d_e2r = nullptr;     // per factor ROW: 0.5 (J delta + r)^2 of the trial step (model_error_rows_kernel)
     int max_inst = 0;
     double *d_D = nullptr, *d_O = nullptr, *d_A = nullptr, *d_S = nullptr;
     SolveBuffers sb{};
@@ -348,7 +349,7 @@ void b200_problem_destroy(b200_problem* p) {
                     p->d_asm_elems[0], p->d_asm_elems[1]};
     for (void* q : ptrs) if (q) cudaFree(q);
     if (p->use_le && p->d_delta) cudaFree(p->d_delta);
-    for (void* q : {(void*)p->d_Dc, (void*)p->d_Ac, (void*)p->d_Sc, (void*)p->d_V, (void*)p->d_Wl, (void*)p->d_lm, (void*)p->d_le_fresh, (void*)p->d_red_partial, (void*)p->d_red_ticket}) if (q) cudaFree(q);
+    for (void* q : {(void*)p->d_Dc, (void*)p->d_Ac, (void*)p->d_Sc, (void*)p->d_V, (void*)p->d_Wl, (void*)p->d_lm, (void*)p->d_le_fresh, (void*)p->d_red_partial, (void*)p->d_red_ticket, (void*)p->d_e2r}) if (q) cudaFree(q);
     if (p->h_lm) cudaFreeHost(p->h_lm);
     if (p->d_spec_delta) cudaFree(p->d_spec_delta);
     if (p->d_spec_rec) cudaFree(p->d_spec_rec);
@@ -452,6 +453,7 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
         dsl.cols = col;
         dsl.J_off = p->nJ; dsl.r_off = p->nr; dsl.e_off = p->ne;
         p->nJ += (long long)dsl.rows * dsl.cols * dsl.n_inst; p->nr += (long long)dsl.rows * dsl.n_inst; p->ne += dsl.n_inst;
+        p->max_rows = std::max(p->max_rows, (long long)dsl.rows * dsl.n_inst);
         p->max_inst = std::max(p->max_inst, dsl.n_inst);
         std::memcpy(dsl.params, s.params, sizeof(dsl.params));
     }
@@ -469,7 +471,7 @@ b200_status b200_problem_create(const b200_problem_desc* d, int32_t device, b200
     p->stage_doubles = (size_t)p->K * std::max(std::max(p->tvd, p->cstride), dm.ntp);
     CK(dalloc(&p->d_stage, p->stage_doubles));
     CK(dalloc(&p->d_slots, (size_t)p->n_slots)); CK(dalloc(&p->d_tvars, (size_t)p->ntv)); CK(dalloc(&p->d_svars, (size_t)p->nsv));
-    CK(dalloc(&p->d_J, (size_t)p->nJ)); CK(dalloc(&p->d_r, (size_t)p->nr)); CK(dalloc(&p->d_e, (size_t)p->ne)); CK(dalloc(&p->d_e2, (size_t)p->ne));
+    CK(dalloc(&p->d_J, (size_t)p->nJ)); CK(dalloc(&p->d_r, (size_t)p->nr)); CK(dalloc(&p->d_e, (size_t)p->ne)); CK(dalloc(&p->d_e2, (size_t)p->ne)); CK(dalloc(&p->d_e2r, (size_t)p->nr));
     const size_t K = p->K;
     CK(dalloc(&p->d_D, K * dm.ntp * dm.ntp)); CK(dalloc(&p->d_O, K * dm.nco * dm.nco));
     CK(dalloc(&p->d_A, K * dm.ns1 * dm.ntp)); CK(dalloc(&p->d_S, K * dm.ns1 * dm.ns1));
@@ -1189,10 +1191,10 @@ static b200_status launch_trial(b200_problem* p, cudaEvent_t* tev, bool device_j
     b200_status st = launch_solve(p, tev);
     if (st != B200_OK) return st;
     if (tev) CK(cudaEventRecord(tev[TE_SOLVE1], p->stream));
-    dim3 grid((p->max_inst + 127) / 128, p->n_slots);
-    B200_LAUNCH(model_error_kernel, grid, dim3(128), 0, p->stream, p->d_slots, p->d_J, p->d_r, p->d_delta, p->dm.ntp, p->sb.dstat, p->d_e2,
+    dim3 grid((unsigned)((p->max_rows + 127) / 128), p->n_slots);   // one thread per factor row
+    B200_LAUNCH(model_error_rows_kernel, grid, dim3(128), 0, p->stream, p->d_slots, p->d_J, p->d_r, p->d_delta, p->dm.ntp, p->sb.dstat, p->d_e2r,
                 p->k_lo, p->k_hi, p->sb.skip);
-    B200_LAUNCH(reduce_sum_kernel, dim3(B200_REDUCE_BLOCKS), dim3(B200_REDUCE_THREADS), 0, p->stream, p->d_e2, p->ne, p->sb.scal + SC_MODEL_ERR, p->sb.skip, p->d_red_partial, p->d_red_ticket);
+    B200_LAUNCH(reduce_sum_kernel, dim3(B200_REDUCE_BLOCKS), dim3(B200_REDUCE_THREADS), 0, p->stream, p->d_e2r, p->nr, p->sb.scal + SC_MODEL_ERR, p->sb.skip, p->d_red_partial, p->d_red_ticket);
     p->launches += 2;
     launch_retract(p, p->d_delta, p->sb.dstat, p->sb.skip);
     launch_error(p, p->d_tv_try, p->d_sv_try, p->d_e2, SC_NEW_ERR, p->sb.skip);

@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(B200_LE_THREADS, 3) local_elim_kernel(LocalEli
 }
 
 // d_l = -L^-T ( V_c^T d_c + V_a^T [d_s, -1] ) for every keyframe of [k_first, ...), and the full step in the internal order
-// [local | chain] that retract_kernel / model_error_kernel consume.  delta_c: [K][ncp] (solver), delta: [K][ntp].
+// [local | chain] that retract_kernel / model_error_rows_kernel consume.  delta_c: [K][ncp] (solver), delta: [K][ntp].
 __global__ void __launch_bounds__(128) local_backsub_kernel(LocalElim le, int k_first, int k_end, const double* __restrict__ delta_c,
                                                             const double* __restrict__ dstat, double* __restrict__ delta, const int* __restrict__ status,
                                                             const int* __restrict__ skip) {
